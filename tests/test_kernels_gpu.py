@@ -1,0 +1,283 @@
+"""sm_100a kernels vs plain PyTorch fp32 references (run on a B200: ``pytest -m gpu``)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def C():
+    from trlx_b200 import ops
+
+    assert ops.available(), "extension must load on a GPU box"
+    return ops.C
+
+
+def _bf(*shape, scale=1.0):
+    return (torch.randn(*shape, device="cuda") * scale).to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 2304, 768), (1600, 3072, 768), (100, 776, 3072), (257, 50257, 768), (32, 768, 64)])
+@pytest.mark.parametrize("bn", [0, 32, 64, 128])
+def test_gemm_matches_fp32(C, M, N, K, bn):
+    torch.manual_seed(0)
+    x, w = _bf(M, K), _bf(N, K, scale=K ** -0.5)
+    ref = x.float() @ w.float().t()
+    out = C.gemm(x, w, None, None, "none", True, None, None, 1.0, bn)
+    torch.testing.assert_close(out, ref, atol=2e-3, rtol=2e-3)
+    out16 = C.gemm(x, w, force_bn=bn)
+    torch.testing.assert_close(out16.float(), ref, atol=3e-2, rtol=3e-2)
+
+
+@pytest.mark.parametrize("act", ["none", "gelu_new", "gelu", "relu", "silu"])
+def test_gemm_epilogue(C, act):
+    torch.manual_seed(1)
+    M, N, K = 300, 1536, 768
+    x, w, b, r = _bf(M, K), _bf(N, K, scale=K ** -0.5), _bf(N), _bf(M, N)
+    from trlx_b200.ops import reference
+
+    ref = reference.linear(x.float(), w.float(), b.float(), act, r.float())
+    out = C.gemm(x, w, b, r, act)
+    torch.testing.assert_close(out.float(), ref, atol=5e-2, rtol=3e-2)
+
+
+def test_gemm_strided_input(C):
+    torch.manual_seed(2)
+    big = _bf(64, 3 * 768)
+    x = big[:, 768:1536]  # row pitch 2304, offset 768 elements (16B aligned)
+    w = _bf(256, 768, scale=0.03)
+    out = C.gemm(x, w, out_f32=True)
+    torch.testing.assert_close(out, x.float() @ w.float().t(), atol=2e-3, rtol=2e-3)
+
+
+@pytest.mark.parametrize("M,V,K", [(128, 50257, 768), (77, 1000, 256), (300, 32000, 128)])
+def test_lmhead_logprob(C, M, V, K):
+    torch.manual_seed(3)
+    h, w, b = _bf(M, K), _bf(V, K, scale=0.05), _bf(V, scale=0.1)
+    labels = torch.randint(0, V, (M,), device="cuda")
+    labels[0] = -1
+    lse, lp, _, _ = C.lmhead(h, w, b, labels)
+    logits = h.float() @ w.float().t() + b.float()
+    ref_lse = torch.logsumexp(logits, -1)
+    ref_lp = logits.gather(-1, labels.clamp_min(0)[:, None]).squeeze(-1) - ref_lse
+    ref_lp[0] = 0
+    torch.testing.assert_close(lse, ref_lse, atol=2e-3, rtol=1e-4)
+    torch.testing.assert_close(lp, ref_lp, atol=3e-3, rtol=1e-3)
+
+
+def test_lmhead_greedy_and_sampling(C):
+    torch.manual_seed(4)
+    M, V, K = 128, 5000, 256
+    h, w = _bf(M, K), _bf(V, K, scale=0.2)
+    logits = h.float() @ w.float().t()
+    lse, _, tok, tlp = C.lmhead(h, w, None, None, True, 0.0, 0)
+    assert torch.equal(tok, logits.argmax(-1))
+    torch.testing.assert_close(tlp, logits.max(-1).values - torch.logsumexp(logits, -1), atol=3e-3, rtol=1e-3)
+    # sampling: empirical frequencies of a peaked 8-way distribution
+    V2 = 8
+    w2 = torch.zeros(V2, K, device="cuda", dtype=torch.bfloat16)
+    w2[:, 0] = torch.tensor([2.0, 1.0, 0.5, 0.0, -0.5, -1.0, -2.0, -3.0], dtype=torch.bfloat16)
+    h2 = torch.zeros(4096, K, device="cuda", dtype=torch.bfloat16)
+    h2[:, 0] = 1.0
+    counts = torch.zeros(V2, device="cuda")
+    for seed in range(8):
+        _, _, t, l = C.lmhead(h2, w2, None, None, True, 1.0, 1234 + seed)
+        counts += torch.bincount(t, minlength=V2).float()
+    p = torch.softmax(w2[:, 0].float(), 0)
+    freq = counts / counts.sum()
+    assert (freq - p).abs().max() < 0.01, (freq, p)
+    torch.testing.assert_close(l, torch.log(p)[t], atol=2e-3, rtol=1e-3)
+    # suppression of a column while step < suppress_until
+    step = torch.zeros(1, dtype=torch.int32, device="cuda")
+    _, _, t, _ = C.lmhead(h2[:256], w2, None, None, True, 1.0, 7, step, 0, 5)
+    assert (t != 0).all()
+
+
+@pytest.mark.parametrize("rms", [False, True])
+def test_norm(C, rms):
+    torch.manual_seed(5)
+    x, w, b = _bf(333, 768), _bf(768), _bf(768)
+    y = C.norm(x, w, None if rms else b, 1e-5, rms)
+    xf = x.float()
+    if rms:
+        ref = xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-5) * w.float()
+    else:
+        ref = F.layer_norm(xf, (768,), w.float(), b.float(), 1e-5)
+    torch.testing.assert_close(y.float(), ref, atol=3e-2, rtol=2e-2)
+
+
+def test_embed_rowdot(C):
+    torch.manual_seed(6)
+    wte, wpe = _bf(1000, 256), _bf(64, 256)
+    tok = torch.randint(0, 1000, (50,), device="cuda")
+    pos = torch.randint(0, 60, (50,), device="cuda", dtype=torch.int32)
+    x = C.embed(tok, pos, wte, wpe, 2)
+    torch.testing.assert_close(x.float(), (wte[tok].float() + wpe[pos.long() + 2].float()), atol=2e-2, rtol=2e-2)
+    w, b = _bf(256), _bf(1)
+    out = C.rowdot(x, w, b)
+    torch.testing.assert_close(out, x.float() @ w.float() + b.float(), atol=2e-2, rtol=2e-2)
+
+
+@pytest.mark.parametrize("nq,nkv,d,rot,interleaved", [(12, 12, 64, 0, False), (8, 2, 128, 128, False), (4, 4, 64, 32, True),
+                                                      (4, 4, 96, 24, False), (2, 2, 256, 64, True)])
+def test_decode_attention(C, nq, nkv, d, rot, interleaved):
+    torch.manual_seed(7)
+    from trlx_b200.nn.transformer import apply_rotary
+
+    B, page, max_pages = 9, 16, 8
+    lens = torch.randint(1, page * max_pages, (B,), device="cuda", dtype=torch.int32)
+    lens[0] = 1
+    num_pages = B * max_pages
+    kc, vc = _bf(num_pages, page, nkv, d), _bf(num_pages, page, nkv, d)
+    bt = torch.randperm(num_pages, device="cuda", dtype=torch.int32).view(B, max_pages).contiguous()
+    qkv = _bf(B, (nq + 2 * nkv) * d)
+    pos = (lens - 1).to(torch.int32)
+    kc0, vc0 = kc.clone(), vc.clone()
+    out = C.decode_attention(qkv, kc, vc, bt, lens, pos, nq, nkv, d, 1 / math.sqrt(d), rot, 10000.0, interleaved)
+    # reference
+    q, k, v = qkv.float().split([nq * d, nkv * d, nkv * d], -1)
+    q, k, v = q.view(B, nq, 1, d), k.view(B, nkv, 1, d), v.view(B, nkv, 1, d)
+    if rot:
+        half = rot // 2
+        inv = 1.0 / (10000.0 ** (torch.arange(half, device="cuda").float() / half))
+        ang = pos.float()[:, None, None] * inv
+        q = apply_rotary(q, ang.cos(), ang.sin(), rot, interleaved)
+        k = apply_rotary(k, ang.cos(), ang.sin(), rot, interleaved)
+    for b in range(B):
+        L = int(lens[b])
+        slots = torch.arange(L - 1, device="cuda")
+        pg = bt[b, (slots // page).long()].long()
+        kk = torch.cat([kc0[pg, (slots % page).long()].float(), k[b].transpose(0, 1).to(torch.bfloat16).float()], 0)  # [L, nkv, d]
+        vv = torch.cat([vc0[pg, (slots % page).long()].float(), v[b].transpose(0, 1)], 0)
+        kk = kk.repeat_interleave(nq // nkv, 1).transpose(0, 1)  # [nq, L, d]
+        vv = vv.repeat_interleave(nq // nkv, 1).transpose(0, 1)
+        att = torch.softmax((q[b] @ kk.transpose(1, 2)) / math.sqrt(d), -1)
+        ref = (att @ vv).reshape(nq * d)
+        torch.testing.assert_close(out[b].float(), ref, atol=3e-2, rtol=3e-2)
+        # cache append
+        last = L - 1
+        torch.testing.assert_close(kc[bt[b, last // page].long(), last % page].float(), k[b, :, 0], atol=2e-2, rtol=2e-2)
+        torch.testing.assert_close(vc[bt[b, last // page].long(), last % page].float(), v[b, :, 0], atol=2e-2, rtol=2e-2)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_logprob_from_logits(C, dtype):
+    torch.manual_seed(8)
+    logits = (torch.randn(4, 37, 5003, device="cuda") * 3).to(dtype)
+    labels = torch.randint(0, 5003, (4, 37), device="cuda")
+    lp, lse = C.logprob_from_logits(logits, labels)
+    ref = torch.log_softmax(logits.float(), -1).gather(-1, labels[..., None]).squeeze(-1)
+    torch.testing.assert_close(lp, ref, atol=2e-3, rtol=1e-3)
+
+
+@pytest.mark.parametrize("width", [40, 17])
+def test_gae_whiten(C, width):
+    torch.manual_seed(9)
+    from trlx_b200.ops import reference
+
+    v, r = torch.randn(32, 40, device="cuda"), torch.randn(32, 40, device="cuda")
+    adv, ret, stats = C.gae(v, r, width, 0.99, 0.95, True, True)
+    radv, rret = reference.gae(v, r, width, 0.99, 0.95)
+    var, mean = torch.var_mean(radv)
+    torch.testing.assert_close(ret[:, :width], rret, atol=1e-4, rtol=1e-4)
+    torch.testing.assert_close(adv[:, :width], (radv - mean) * torch.rsqrt(var + 1e-8), atol=1e-3, rtol=1e-3)
+    assert int(stats[0].item()) == 32 * width
+
+
+def test_ppo_loss_and_grads():
+    torch.manual_seed(10)
+    from trlx_b200 import ops
+    from trlx_b200.ops import reference
+
+    B, R = 32, 40
+    lp = (torch.randn(B, R, device="cuda") * 0.3 - 2).requires_grad_()
+    val = torch.randn(B, R, device="cuda").requires_grad_()
+    old_lp = lp.detach() + torch.randn(B, R, device="cuda") * 0.3
+    old_v = val.detach() + torch.randn(B, R, device="cuda") * 0.3
+    adv, ret = torch.randn(B, R, device="cuda"), torch.randn(B, R, device="cuda")
+    mask = (torch.arange(R, device="cuda")[None] < torch.randint(1, R + 1, (B, 1), device="cuda")).float()
+    loss, stats = ops.ppo_loss(lp, val, old_lp, old_v, adv, ret, mask, 0.2, 0.2, 1.3)
+    loss.backward()
+    g_lp, g_v = lp.grad.clone(), val.grad.clone()
+    lp.grad = val.grad = None
+    rloss, rstats = reference.ppo_loss(lp, val, old_lp, old_v, adv, ret, mask, 0.2, 0.2, 1.3)
+    rloss.backward()
+    torch.testing.assert_close(loss, rloss, atol=1e-4, rtol=1e-4)
+    torch.testing.assert_close(g_lp, lp.grad, atol=1e-5, rtol=1e-3)
+    torch.testing.assert_close(g_v, val.grad, atol=1e-5, rtol=1e-3)
+    for k, v in rstats.items():
+        torch.testing.assert_close(stats[k].float(), torch.as_tensor(v, device="cuda").float(), atol=2e-3, rtol=2e-3, msg=k)
+
+
+def test_kl_rewards(C):
+    torch.manual_seed(11)
+    from trlx_b200.ops import reference
+
+    B, R = 16, 12
+    lp, rlp = torch.randn(B, R, device="cuda"), torch.randn(B, R, device="cuda")
+    lens = torch.randint(1, R + 1, (B,), device="cuda", dtype=torch.int32)
+    scores = torch.randn(B, device="cuda")
+    rw, st = C.kl_rewards(lp, rlp, lens, scores, 0.05)
+    ref_rw, ref_kl = reference.kl_rewards(lp, rlp, lens, scores, 0.05)
+    torch.testing.assert_close(rw, ref_rw, atol=1e-5, rtol=1e-4)
+    torch.testing.assert_close(st[0].float(), ref_kl.sum(), atol=1e-2, rtol=1e-3)
+
+
+def test_adamw_flat(C):
+    torch.manual_seed(12)
+    from trlx_b200.ops import reference
+
+    n = 100003
+    master = torch.randn(n, device="cuda")
+    param = master.to(torch.bfloat16)
+    m, v = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    rw, rm, rv = master.clone(), m.clone(), v.clone()
+    for step in range(1, 4):
+        g = torch.randn(n, device="cuda").to(torch.bfloat16)
+        hyper = torch.tensor([1e-2, 1 - 0.9 ** step, 1 - 0.95 ** step, 1.0], device="cuda")
+        C.adamw_flat(param, master, g, m, v, 0.9, 0.95, 1e-8, 0.01, True, hyper)
+        reference.adamw_step(rw, g.float(), rm, rv, step, 1e-2, 0.9, 0.95, 1e-8, 0.01)
+    torch.testing.assert_close(master, rw, atol=1e-5, rtol=1e-4)
+    torch.testing.assert_close(param.float(), rw, atol=2e-2, rtol=1e-2)
+
+
+def test_linear_autograd():
+    torch.manual_seed(13)
+    from trlx_b200 import ops
+
+    x = _bf(4, 50, 768).requires_grad_()
+    w = _bf(1024, 768, scale=0.03).requires_grad_()
+    b = _bf(1024).requires_grad_()
+    r = _bf(4, 50, 1024).requires_grad_()
+    y = ops.linear(x, w, b, "none", r)
+    y.float().pow(2).sum().backward()
+    gx, gw, gb, gr = x.grad.clone(), w.grad.clone(), b.grad.clone(), r.grad.clone()
+    for t in (x, w, b, r):
+        t.grad = None
+    yr = F.linear(x, w, b) + r
+    yr.float().pow(2).sum().backward()
+    torch.testing.assert_close(y.float(), yr.float(), atol=5e-2, rtol=3e-2)
+    for a, bb in ((gx, x.grad), (gw, w.grad), (gb, b.grad), (gr, r.grad)):
+        torch.testing.assert_close(a.float(), bb.float(), atol=0.5, rtol=5e-2)
+
+
+def test_fused_logprob_autograd():
+    torch.manual_seed(14)
+    from trlx_b200 import ops
+
+    M, V, K = 200, 3000, 256
+    h = _bf(M, K).requires_grad_()
+    w = _bf(V, K, scale=0.05).requires_grad_()
+    labels = torch.randint(0, V, (M,), device="cuda")
+    lp, _ = ops.fused_logprob(h, w, None, labels)
+    (lp * torch.arange(M, device="cuda")).sum().backward()
+    gh, gw = h.grad.clone(), w.grad.clone()
+    h.grad = w.grad = None
+    ref = torch.log_softmax(F.linear(h.float(), w.float()), -1).gather(-1, labels[:, None]).squeeze(-1)
+    (ref * torch.arange(M, device="cuda")).sum().backward()
+    torch.testing.assert_close(lp, ref, atol=3e-3, rtol=1e-3)
+    torch.testing.assert_close(gh.float(), h.grad.float(), atol=0.3, rtol=5e-2)
+    torch.testing.assert_close(gw.float(), w.grad.float(), atol=0.5, rtol=5e-2)

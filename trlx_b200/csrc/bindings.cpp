@@ -1,0 +1,459 @@
+// Python bindings (torch tensors in, raw pointers out) + the host-side C++ runtime pieces:
+//   * PagedKVAllocator — free-list page allocator behind the paged KV cache used by the rollout engine
+// Kernels live in the .cu files of this directory and export a plain C ABI so that they compile in seconds
+// without torch headers.
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/extension.h>
+
+#include <deque>
+#include <stdexcept>
+#include <unordered_map>
+#include <vector>
+
+using torch::Tensor;
+typedef c10::optional<Tensor> OptTensor;
+
+extern "C" {
+int b200_gemm_bf16(const void*, const void*, void*, int, int, int, long long, long long, long long, const void*, const void*,
+                   long long, const float*, float, int, int, int, cudaStream_t);
+int b200_lmhead_tiles(int);
+int b200_lmhead_bf16(const void*, const void*, int, int, int, long long, long long, const void*, const long long*, float*,
+                     float*, float*, int, float, unsigned long long, const int*, int, int, long long*, float*, cudaStream_t);
+int b200_norm_bf16(const void*, const void*, const void*, void*, int, int, long long, long long, float, int, cudaStream_t);
+int b200_embed_bf16(const long long*, const int*, const void*, const void*, int, void*, int, int, cudaStream_t);
+int b200_decode_attention_bf16(const void*, void*, void*, const int*, const int*, const int*, void*, int, int, int, int, int,
+                               int, float, int, float, int, const float*, int, cudaStream_t);
+int b200_rowdot_bf16(const void*, const void*, const void*, float*, int, int, long long, cudaStream_t);
+int b200_decode_step(const long long*, const float*, const float*, const float*, int*, int, int, long long, long long,
+                     long long*, float*, float*, float*, int*, int*, int*, int*, long long*, int*, cudaStream_t);
+int b200_paged_kv_write(const void*, const void*, void*, void*, const int*, const int*, const int*, int, int, int, int, int,
+                        int, long long, long long, cudaStream_t);
+int b200_logprob_from_logits(const void*, const long long*, float*, float*, long long, int, long long, int, cudaStream_t);
+int b200_logprob_backward_inplace(void*, const long long*, const float*, const float*, long long, int, long long, int,
+                                  cudaStream_t);
+int b200_gae(const float*, const float*, float*, float*, int, int, int, long long, float, float, double*, cudaStream_t);
+int b200_whiten(float*, int, int, long long, const double*, int, cudaStream_t);
+int b200_ppo_loss_num_outputs();
+int b200_ppo_loss_workspace_floats(int);
+int b200_ppo_loss(const float*, const float*, const float*, const float*, const float*, const float*, const float*, int, float,
+                  float, float, float*, float*, float*, int, float*, cudaStream_t);
+int b200_kl_rewards(const float*, const float*, const int*, const float*, int, int, float, float*, double*, cudaStream_t);
+int b200_adamw_flat(void*, float*, const void*, int, float*, float*, long long, float, float, float, float, int, const float*,
+                    cudaStream_t);
+int b200_sqnorm(const void*, int, long long, double*, cudaStream_t);
+int b200_clip_coef(const double*, float, float*, float*, cudaStream_t);
+int b200_signal_barrier(void* const*, int, int, unsigned int, cudaStream_t);
+int b200_rs_adamw_ag(void* const*, void* const*, int, long long, long long, float*, float*, float*, float*, int, float, float,
+                     float, float, int, const float*, double*, cudaStream_t);
+int b200_lerp_bf16(void*, const void*, long long, float, cudaStream_t);
+}
+
+namespace {
+
+inline cudaStream_t stream() { return at::cuda::getCurrentCUDAStream().stream(); }
+
+inline void check(int code, const char* what) {
+  if (code == 0) return;
+  if (code > 0) throw std::runtime_error(std::string(what) + ": CUDA error " + cudaGetErrorString((cudaError_t)code));
+  throw std::runtime_error(std::string(what) + ": invalid arguments / driver entry point unavailable (code " +
+                           std::to_string(code) + ")");
+}
+
+inline const void* optptr(const OptTensor& t) { return t.has_value() ? t->data_ptr() : nullptr; }
+
+#define CHECK_BF16(x) TORCH_CHECK((x).is_cuda() && (x).scalar_type() == at::kBFloat16, #x " must be a CUDA bf16 tensor")
+#define CHECK_F32(x) TORCH_CHECK((x).is_cuda() && (x).scalar_type() == at::kFloat, #x " must be a CUDA fp32 tensor")
+
+int act_code(const std::string& a) {
+  if (a.empty() || a == "none") return 0;
+  if (a == "gelu_new" || a == "gelu_tanh" || a == "gelu_pytorch_tanh" || a == "gelu_fast") return 1;
+  if (a == "gelu") return 2;
+  if (a == "relu") return 3;
+  if (a == "silu" || a == "swish") return 4;
+  throw std::invalid_argument("unknown activation " + a);
+}
+
+// y[M,N] = act(alpha * x[M,K] @ w[N,K]^T * col_scale + bias) + residual
+Tensor gemm(const Tensor& x, const Tensor& w, const OptTensor& bias, const OptTensor& residual, const std::string& act,
+            bool out_f32, const OptTensor& out_, const OptTensor& col_scale, double alpha, int64_t force_bn) {
+  CHECK_BF16(x); CHECK_BF16(w);
+  TORCH_CHECK(x.dim() == 2 && w.dim() == 2 && x.size(1) == w.size(1), "gemm: shape mismatch");
+  TORCH_CHECK(x.stride(1) == 1 && w.stride(1) == 1, "gemm: operands must be K-major");
+  const int64_t M = x.size(0), N = w.size(0), K = x.size(1);
+  TORCH_CHECK(K % 8 == 0 && x.stride(0) % 8 == 0 && w.stride(0) % 8 == 0, "gemm: K and row pitches must be multiples of 8");
+  TORCH_CHECK(reinterpret_cast<uintptr_t>(x.data_ptr()) % 16 == 0 && reinterpret_cast<uintptr_t>(w.data_ptr()) % 16 == 0,
+              "gemm: operands must be 16-byte aligned");
+  c10::cuda::CUDAGuard guard(x.device());
+  Tensor out = out_.has_value() ? *out_ : torch::empty({M, N}, x.options().dtype(out_f32 ? at::kFloat : at::kBFloat16));
+  TORCH_CHECK(out.size(0) == M && out.size(1) == N && out.stride(1) == 1, "gemm: bad out");
+  if (bias.has_value()) { CHECK_BF16(*bias); TORCH_CHECK(bias->numel() == N); }
+  long long ldr = 0;
+  if (residual.has_value()) { CHECK_BF16(*residual); TORCH_CHECK(residual->size(0) == M && residual->size(1) == N && residual->stride(1) == 1); ldr = residual->stride(0); }
+  if (col_scale.has_value()) { CHECK_F32(*col_scale); TORCH_CHECK(col_scale->numel() == N); }
+  check(b200_gemm_bf16(x.data_ptr(), w.data_ptr(), out.data_ptr(), (int)M, (int)N, (int)K, x.stride(0), w.stride(0),
+                       out.stride(0), optptr(bias), optptr(residual), ldr, (const float*)optptr(col_scale), (float)alpha,
+                       act_code(act), out.scalar_type() == at::kFloat, (int)force_bn, stream()),
+        "gemm");
+  return out;
+}
+
+// Fused LM head: returns (lse[M], logprob[M], token[M], token_logprob[M]); unused outputs are empty tensors.
+std::vector<Tensor> lmhead(const Tensor& h, const Tensor& w, const OptTensor& bias, const OptTensor& labels, bool sample,
+                           double temperature, int64_t seed, const OptTensor& step, int64_t suppress_col,
+                           int64_t suppress_until, const OptTensor& workspace_) {
+  CHECK_BF16(h); CHECK_BF16(w);
+  TORCH_CHECK(h.dim() == 2 && w.dim() == 2 && h.size(1) == w.size(1) && h.stride(1) == 1 && w.stride(1) == 1);
+  const int64_t M = h.size(0), N = w.size(0), K = h.size(1);
+  TORCH_CHECK(K % 8 == 0 && h.stride(0) % 8 == 0 && w.stride(0) % 8 == 0);
+  c10::cuda::CUDAGuard guard(h.device());
+  const int64_t nt = b200_lmhead_tiles((int)N);
+  auto f32 = h.options().dtype(at::kFloat);
+  Tensor ws = workspace_.has_value() ? *workspace_ : torch::empty({5 * M * nt + M}, f32);
+  TORCH_CHECK(ws.numel() >= 5 * M * nt + M);
+  Tensor lse = torch::empty({M}, f32), lp = torch::empty({M}, f32);
+  Tensor tok = sample ? torch::empty({M}, h.options().dtype(at::kLong)) : Tensor();
+  Tensor tlp = sample ? torch::empty({M}, f32) : Tensor();
+  const long long* lab = nullptr;
+  if (labels.has_value()) { TORCH_CHECK(labels->scalar_type() == at::kLong && labels->numel() == M && labels->is_contiguous()); lab = labels->data_ptr<int64_t>() ? (const long long*)labels->data_ptr<int64_t>() : nullptr; }
+  const int* sp = nullptr;
+  if (step.has_value()) { TORCH_CHECK(step->scalar_type() == at::kInt); sp = step->data_ptr<int>(); }
+  check(b200_lmhead_bf16(h.data_ptr(), w.data_ptr(), (int)M, (int)N, (int)K, h.stride(0), w.stride(0), optptr(bias), lab,
+                         ws.data_ptr<float>(), lse.data_ptr<float>(), lp.data_ptr<float>(), sample ? 1 : 0,
+                         (float)temperature, (unsigned long long)seed, sp, (int)suppress_col, (int)suppress_until,
+                         sample ? (long long*)tok.data_ptr<int64_t>() : nullptr, sample ? tlp.data_ptr<float>() : nullptr,
+                         stream()),
+        "lmhead");
+  return {lse, lp, tok, tlp};
+}
+
+Tensor norm(const Tensor& x, const Tensor& w, const OptTensor& b, double eps, bool rms, const OptTensor& out_) {
+  CHECK_BF16(x); CHECK_BF16(w);
+  TORCH_CHECK(x.dim() == 2 && x.stride(1) == 1 && x.stride(0) % 8 == 0);
+  c10::cuda::CUDAGuard guard(x.device());
+  Tensor y = out_.has_value() ? *out_ : torch::empty_like(x, at::MemoryFormat::Contiguous);
+  check(b200_norm_bf16(x.data_ptr(), w.data_ptr(), optptr(b), y.data_ptr(), (int)x.size(0), (int)x.size(1), x.stride(0),
+                       y.stride(0), (float)eps, rms ? 1 : 0, stream()),
+        "norm");
+  return y;
+}
+
+Tensor embed(const Tensor& tokens, const Tensor& positions, const Tensor& wte, const OptTensor& wpe, int64_t pos_offset,
+             const OptTensor& out_) {
+  CHECK_BF16(wte);
+  TORCH_CHECK(tokens.scalar_type() == at::kLong && positions.scalar_type() == at::kInt);
+  c10::cuda::CUDAGuard guard(wte.device());
+  const int64_t B = tokens.numel(), H = wte.size(1);
+  TORCH_CHECK(H % 8 == 0);
+  Tensor x = out_.has_value() ? *out_ : torch::empty({B, H}, wte.options());
+  check(b200_embed_bf16((const long long*)tokens.data_ptr<int64_t>(), positions.data_ptr<int>(), wte.data_ptr(), optptr(wpe),
+                        (int)pos_offset, x.data_ptr(), (int)B, (int)H, stream()),
+        "embed");
+  return x;
+}
+
+Tensor decode_attention(const Tensor& qkv, Tensor& kcache, Tensor& vcache, const Tensor& block_table, const Tensor& seq_lens,
+                        const Tensor& positions, int64_t nq, int64_t nkv, int64_t d, double scale, int64_t rot_dim,
+                        double rot_base, bool rot_interleaved, const OptTensor& alibi, int64_t window, const OptTensor& out_) {
+  CHECK_BF16(qkv); CHECK_BF16(kcache); CHECK_BF16(vcache);
+  TORCH_CHECK(qkv.is_contiguous() && kcache.is_contiguous() && vcache.is_contiguous() && block_table.is_contiguous());
+  TORCH_CHECK(block_table.scalar_type() == at::kInt && seq_lens.scalar_type() == at::kInt && positions.scalar_type() == at::kInt);
+  c10::cuda::CUDAGuard guard(qkv.device());
+  const int64_t B = qkv.size(0);
+  Tensor out = out_.has_value() ? *out_ : torch::empty({B, nq * d}, qkv.options());
+  check(b200_decode_attention_bf16(qkv.data_ptr(), kcache.data_ptr(), vcache.data_ptr(), block_table.data_ptr<int>(),
+                                   seq_lens.data_ptr<int>(), positions.data_ptr<int>(), out.data_ptr(), (int)B, (int)nq,
+                                   (int)nkv, (int)d, (int)kcache.size(1), (int)block_table.size(1), (float)scale,
+                                   (int)rot_dim, (float)rot_base, rot_interleaved ? 1 : 0, (const float*)optptr(alibi),
+                                   (int)window, stream()),
+        "decode_attention");
+  return out;
+}
+
+Tensor rowdot(const Tensor& x, const Tensor& w, const OptTensor& bias, const OptTensor& out_) {
+  CHECK_BF16(x); CHECK_BF16(w);
+  c10::cuda::CUDAGuard guard(x.device());
+  Tensor out = out_.has_value() ? *out_ : torch::empty({x.size(0)}, x.options().dtype(at::kFloat));
+  check(b200_rowdot_bf16(x.data_ptr(), w.data_ptr(), optptr(bias), out.data_ptr<float>(), (int)x.size(0), (int)x.size(1),
+                         x.stride(0), stream()),
+        "rowdot");
+  return out;
+}
+
+void decode_step(const Tensor& sampled, const Tensor& lp, const OptTensor& ref_lp, const OptTensor& value, Tensor& step,
+                 int64_t max_new, int64_t eos_id, int64_t pad_id, Tensor& tokens_out, Tensor& logprobs_out,
+                 const OptTensor& ref_logprobs_out, const OptTensor& values_out, Tensor& finished, Tensor& resp_lens,
+                 Tensor& seq_lens, Tensor& positions, Tensor& next_tokens, Tensor& n_running) {
+  c10::cuda::CUDAGuard guard(sampled.device());
+  const int B = (int)sampled.numel();
+  check(b200_decode_step((const long long*)sampled.data_ptr<int64_t>(), lp.data_ptr<float>(), (const float*)optptr(ref_lp),
+                         (const float*)optptr(value), step.data_ptr<int>(), (int)max_new, B, eos_id, pad_id,
+                         (long long*)tokens_out.data_ptr<int64_t>(), logprobs_out.data_ptr<float>(),
+                         (float*)optptr(ref_logprobs_out), (float*)optptr(values_out), finished.data_ptr<int>(),
+                         resp_lens.data_ptr<int>(), seq_lens.data_ptr<int>(), positions.data_ptr<int>(),
+                         (long long*)next_tokens.data_ptr<int64_t>(), n_running.data_ptr<int>(), stream()),
+        "decode_step");
+}
+
+// k, v: [B, T, nkv*d] (any batch/time strides, unit inner stride)
+void paged_kv_write(const Tensor& k, const Tensor& v, Tensor& kcache, Tensor& vcache, const Tensor& block_table,
+                    const Tensor& first, const Tensor& lens, int64_t nkv, int64_t d) {
+  CHECK_BF16(k); CHECK_BF16(v);
+  TORCH_CHECK(k.dim() == 3 && k.stride(2) == 1 && v.stride(2) == 1 && k.stride(0) == v.stride(0) && k.stride(1) == v.stride(1));
+  TORCH_CHECK((nkv * d) % 8 == 0 && k.stride(0) % 8 == 0 && k.stride(1) % 8 == 0);
+  c10::cuda::CUDAGuard guard(k.device());
+  check(b200_paged_kv_write(k.data_ptr(), v.data_ptr(), kcache.data_ptr(), vcache.data_ptr(), block_table.data_ptr<int>(),
+                            first.data_ptr<int>(), lens.data_ptr<int>(), (int)k.size(0), (int)k.size(1), (int)nkv, (int)d,
+                            (int)kcache.size(1), (int)block_table.size(1), k.stride(0), k.stride(1), stream()),
+        "paged_kv_write");
+}
+
+int dtype_code(const Tensor& t) {
+  switch (t.scalar_type()) {
+    case at::kFloat: return 0;
+    case at::kBFloat16: return 1;
+    case at::kHalf: return 2;
+    default: throw std::invalid_argument("logits must be fp32 / bf16 / fp16");
+  }
+}
+
+std::vector<Tensor> logprob_from_logits(const Tensor& logits, const Tensor& labels) {
+  TORCH_CHECK(logits.is_cuda() && logits.stride(-1) == 1 && labels.scalar_type() == at::kLong);
+  c10::cuda::CUDAGuard guard(logits.device());
+  const int64_t V = logits.size(-1);
+  Tensor l2 = logits.reshape({-1, V});
+  if (l2.stride(1) != 1) l2 = l2.contiguous();
+  Tensor lab = labels.reshape({-1}).contiguous();
+  TORCH_CHECK(lab.numel() == l2.size(0));
+  auto f32 = logits.options().dtype(at::kFloat);
+  Tensor out = torch::empty({l2.size(0)}, f32), lse = torch::empty({l2.size(0)}, f32);
+  check(b200_logprob_from_logits(l2.data_ptr(), (const long long*)lab.data_ptr<int64_t>(), out.data_ptr<float>(),
+                                 lse.data_ptr<float>(), l2.size(0), (int)V, l2.stride(0), dtype_code(l2), stream()),
+        "logprob_from_logits");
+  return {out.reshape(labels.sizes()), lse.reshape(labels.sizes())};
+}
+
+void logprob_backward_inplace(Tensor& logits, const Tensor& labels, const Tensor& lse, const Tensor& grad) {
+  TORCH_CHECK(logits.dim() == 2 && logits.stride(1) == 1);
+  CHECK_F32(lse); CHECK_F32(grad);
+  c10::cuda::CUDAGuard guard(logits.device());
+  check(b200_logprob_backward_inplace(logits.data_ptr(), (const long long*)labels.data_ptr<int64_t>(), lse.data_ptr<float>(),
+                                      grad.data_ptr<float>(), logits.size(0), (int)logits.size(1), logits.stride(0),
+                                      dtype_code(logits), stream()),
+        "logprob_backward_inplace");
+}
+
+// returns (advantages, returns, stats[3] double = (count, sum, sumsq)); whitening applied unless `stats_only`
+std::vector<Tensor> gae(const Tensor& values, const Tensor& rewards, int64_t width, double gamma, double lam, bool do_whiten,
+                        bool unbiased) {
+  CHECK_F32(values); CHECK_F32(rewards);
+  TORCH_CHECK(values.dim() == 2 && values.is_contiguous() && rewards.is_contiguous() && values.sizes() == rewards.sizes());
+  c10::cuda::CUDAGuard guard(values.device());
+  const int B = (int)values.size(0), R = (int)values.size(1);
+  Tensor adv = torch::empty_like(values), ret = torch::empty_like(values);
+  Tensor stats = torch::zeros({3}, values.options().dtype(at::kDouble));
+  check(b200_gae(values.data_ptr<float>(), rewards.data_ptr<float>(), adv.data_ptr<float>(), ret.data_ptr<float>(), B, R,
+                 (int)width, R, (float)gamma, (float)lam, stats.data_ptr<double>(), stream()),
+        "gae");
+  if (do_whiten)
+    check(b200_whiten(adv.data_ptr<float>(), B, (int)width, R, stats.data_ptr<double>(), unbiased ? 1 : 0, stream()), "whiten");
+  return {adv, ret, stats};
+}
+
+void whiten_(Tensor& adv, int64_t width, const Tensor& stats, bool unbiased) {
+  CHECK_F32(adv);
+  TORCH_CHECK(stats.scalar_type() == at::kDouble);
+  c10::cuda::CUDAGuard guard(adv.device());
+  check(b200_whiten(adv.data_ptr<float>(), (int)adv.size(0), (int)width, adv.size(1), stats.data_ptr<double>(),
+                    unbiased ? 1 : 0, stream()),
+        "whiten");
+}
+
+// returns (out[O_COUNT], dlogprobs, dvalues)
+std::vector<Tensor> ppo_loss(const Tensor& logprobs, const Tensor& values, const Tensor& old_logprobs, const Tensor& old_values,
+                             const Tensor& adv, const Tensor& ret, const Tensor& mask, double clip, double clip_v,
+                             double vf_coef) {
+  for (const Tensor* t : {&logprobs, &values, &old_logprobs, &old_values, &adv, &ret, &mask}) {
+    TORCH_CHECK(t->is_cuda() && t->scalar_type() == at::kFloat && t->is_contiguous() && t->numel() == logprobs.numel(),
+                "ppo_loss: all inputs must be contiguous fp32 CUDA tensors of equal size");
+  }
+  c10::cuda::CUDAGuard guard(logprobs.device());
+  const int total = (int)logprobs.numel();
+  int nblocks = (total + 255) / 256;
+  if (nblocks > 64) nblocks = 64;
+  if (nblocks < 1) nblocks = 1;
+  auto f32 = logprobs.options();
+  Tensor ws = torch::empty({b200_ppo_loss_workspace_floats(nblocks)}, f32);
+  Tensor out = torch::empty({b200_ppo_loss_num_outputs()}, f32);
+  Tensor dlp = torch::empty_like(logprobs), dv = torch::empty_like(values);
+  check(b200_ppo_loss(logprobs.data_ptr<float>(), values.data_ptr<float>(), old_logprobs.data_ptr<float>(),
+                      old_values.data_ptr<float>(), adv.data_ptr<float>(), ret.data_ptr<float>(), mask.data_ptr<float>(),
+                      total, (float)clip, (float)clip_v, (float)vf_coef, dlp.data_ptr<float>(), dv.data_ptr<float>(),
+                      ws.data_ptr<float>(), nblocks, out.data_ptr<float>(), stream()),
+        "ppo_loss");
+  return {out, dlp, dv};
+}
+
+// returns (rewards[B,R], kl_stats double[2] = (sum of per-row KL, rows))
+std::vector<Tensor> kl_rewards(const Tensor& lp, const Tensor& ref_lp, const Tensor& resp_lens, const Tensor& scores,
+                               double kl_coef) {
+  CHECK_F32(lp); CHECK_F32(ref_lp); CHECK_F32(scores);
+  TORCH_CHECK(lp.is_contiguous() && ref_lp.is_contiguous() && resp_lens.scalar_type() == at::kInt);
+  c10::cuda::CUDAGuard guard(lp.device());
+  Tensor rewards = torch::empty_like(lp);
+  Tensor st = torch::zeros({2}, lp.options().dtype(at::kDouble));
+  check(b200_kl_rewards(lp.data_ptr<float>(), ref_lp.data_ptr<float>(), resp_lens.data_ptr<int>(), scores.data_ptr<float>(),
+                        (int)lp.size(0), (int)lp.size(1), (float)kl_coef, rewards.data_ptr<float>(), st.data_ptr<double>(),
+                        stream()),
+        "kl_rewards");
+  return {rewards, st};
+}
+
+void adamw_flat(Tensor& param, Tensor& master, const Tensor& grad, Tensor& exp_avg, Tensor& exp_avg_sq, double beta1,
+                double beta2, double eps, double weight_decay, bool decoupled, const Tensor& hyper) {
+  CHECK_BF16(param); CHECK_F32(master); CHECK_F32(exp_avg); CHECK_F32(exp_avg_sq); CHECK_F32(hyper);
+  TORCH_CHECK(grad.is_cuda() && (grad.scalar_type() == at::kFloat || grad.scalar_type() == at::kBFloat16));
+  c10::cuda::CUDAGuard guard(param.device());
+  check(b200_adamw_flat(param.data_ptr(), master.data_ptr<float>(), grad.data_ptr(), grad.scalar_type() == at::kFloat,
+                        exp_avg.data_ptr<float>(), exp_avg_sq.data_ptr<float>(), param.numel(), (float)beta1, (float)beta2,
+                        (float)eps, (float)weight_decay, decoupled ? 1 : 0, hyper.data_ptr<float>(), stream()),
+        "adamw_flat");
+}
+
+void sqnorm_(const Tensor& x, Tensor& out) {
+  TORCH_CHECK(out.scalar_type() == at::kDouble);
+  c10::cuda::CUDAGuard guard(x.device());
+  check(b200_sqnorm(x.data_ptr(), x.scalar_type() == at::kFloat, x.numel(), out.data_ptr<double>(), stream()), "sqnorm");
+}
+
+void clip_coef_(const Tensor& sqsum, double max_norm, Tensor& hyper, const OptTensor& norm_out) {
+  c10::cuda::CUDAGuard guard(hyper.device());
+  check(b200_clip_coef(sqsum.data_ptr<double>(), (float)max_norm, hyper.data_ptr<float>(), (float*)optptr(norm_out), stream()),
+        "clip_coef");
+}
+
+void signal_barrier(const std::vector<int64_t>& pads, int64_t rank, int64_t epoch) {
+  std::vector<void*> p(pads.size());
+  for (size_t i = 0; i < pads.size(); ++i) p[i] = reinterpret_cast<void*>(pads[i]);
+  check(b200_signal_barrier(p.data(), (int)rank, (int)pads.size(), (unsigned)epoch, stream()), "signal_barrier");
+}
+
+void rs_adamw_ag(const std::vector<int64_t>& grads, const std::vector<int64_t>& params, int64_t lo, int64_t n, Tensor& master,
+                 Tensor& exp_avg, Tensor& exp_avg_sq, const OptTensor& gshard, int64_t mode, double beta1, double beta2,
+                 double eps, double weight_decay, bool decoupled, const Tensor& hyper, const OptTensor& sq_out) {
+  TORCH_CHECK(grads.size() == params.size());
+  std::vector<void*> g(grads.size()), p(params.size());
+  for (size_t i = 0; i < grads.size(); ++i) { g[i] = reinterpret_cast<void*>(grads[i]); p[i] = reinterpret_cast<void*>(params[i]); }
+  c10::cuda::CUDAGuard guard(master.device());
+  check(b200_rs_adamw_ag(g.data(), p.data(), (int)grads.size(), lo, n, master.data_ptr<float>(), exp_avg.data_ptr<float>(),
+                         exp_avg_sq.data_ptr<float>(), (float*)optptr(gshard), (int)mode, (float)beta1, (float)beta2,
+                         (float)eps, (float)weight_decay, decoupled ? 1 : 0, hyper.data_ptr<float>(),
+                         (double*)optptr(sq_out), stream()),
+        "rs_adamw_ag");
+}
+
+void lerp_(Tensor& tgt, const Tensor& src, double alpha) {
+  CHECK_BF16(tgt); CHECK_BF16(src);
+  TORCH_CHECK(tgt.is_contiguous() && src.is_contiguous() && tgt.numel() == src.numel());
+  c10::cuda::CUDAGuard guard(tgt.device());
+  check(b200_lerp_bf16(tgt.data_ptr(), src.data_ptr(), tgt.numel(), (float)alpha, stream()), "lerp");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Page allocator for the paged KV cache.  Pages are fixed-size token slots shared by every layer (each layer has its
+// own [num_pages, page_size, nkv, d] tensor but the same page ids).  Sequences are identified by an integer handle.
+class PagedKVAllocator {
+ public:
+  PagedKVAllocator(int64_t num_pages, int64_t page_size) : page_size_(page_size), num_pages_(num_pages) {
+    for (int64_t i = 0; i < num_pages; ++i) free_.push_back((int32_t)i);
+  }
+  // ensure `seq` can hold `n_tokens`; returns the page ids of the sequence
+  std::vector<int32_t> reserve(int64_t seq, int64_t n_tokens) {
+    auto& pages = seqs_[seq];
+    const int64_t need = (n_tokens + page_size_ - 1) / page_size_;
+    while ((int64_t)pages.size() < need) {
+      if (free_.empty()) throw std::runtime_error("PagedKVAllocator: out of pages");
+      pages.push_back(free_.front());
+      free_.pop_front();
+    }
+    return pages;
+  }
+  void release(int64_t seq) {
+    auto it = seqs_.find(seq);
+    if (it == seqs_.end()) return;
+    for (int32_t p : it->second) free_.push_back(p);
+    seqs_.erase(it);
+  }
+  void reset() {
+    seqs_.clear();
+    free_.clear();
+    for (int64_t i = 0; i < num_pages_; ++i) free_.push_back((int32_t)i);
+  }
+  // block table for a batch of sequence handles, -1 padded: [len(seqs), max_pages] int32 (CPU tensor)
+  Tensor block_table(const std::vector<int64_t>& seqs, int64_t max_pages) {
+    Tensor t = torch::full({(int64_t)seqs.size(), max_pages}, 0, torch::dtype(torch::kInt32));
+    auto a = t.accessor<int32_t, 2>();
+    for (size_t i = 0; i < seqs.size(); ++i) {
+      auto it = seqs_.find(seqs[i]);
+      if (it == seqs_.end()) continue;
+      TORCH_CHECK((int64_t)it->second.size() <= max_pages, "block_table: max_pages too small");
+      for (size_t j = 0; j < it->second.size(); ++j) a[i][j] = it->second[j];
+    }
+    return t;
+  }
+  int64_t free_pages() const { return (int64_t)free_.size(); }
+  int64_t page_size() const { return page_size_; }
+  int64_t num_pages() const { return num_pages_; }
+
+ private:
+  int64_t page_size_, num_pages_;
+  std::deque<int32_t> free_;
+  std::unordered_map<int64_t, std::vector<int32_t>> seqs_;
+};
+
+}  // namespace
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  namespace py = pybind11;
+  m.doc() = "trlx_b200 sm_100a kernels";
+  m.def("gemm", &gemm, py::arg("x"), py::arg("w"), py::arg("bias") = py::none(), py::arg("residual") = py::none(),
+        py::arg("act") = "none", py::arg("out_f32") = false, py::arg("out") = py::none(), py::arg("col_scale") = py::none(),
+        py::arg("alpha") = 1.0, py::arg("force_bn") = 0);
+  m.def("lmhead", &lmhead, py::arg("h"), py::arg("w"), py::arg("bias") = py::none(), py::arg("labels") = py::none(),
+        py::arg("sample") = false, py::arg("temperature") = 1.0, py::arg("seed") = 0, py::arg("step") = py::none(),
+        py::arg("suppress_col") = -1, py::arg("suppress_until") = 0, py::arg("workspace") = py::none());
+  m.def("norm", &norm, py::arg("x"), py::arg("w"), py::arg("b") = py::none(), py::arg("eps") = 1e-5, py::arg("rms") = false,
+        py::arg("out") = py::none());
+  m.def("embed", &embed, py::arg("tokens"), py::arg("positions"), py::arg("wte"), py::arg("wpe") = py::none(),
+        py::arg("pos_offset") = 0, py::arg("out") = py::none());
+  m.def("decode_attention", &decode_attention, py::arg("qkv"), py::arg("kcache"), py::arg("vcache"), py::arg("block_table"),
+        py::arg("seq_lens"), py::arg("positions"), py::arg("nq"), py::arg("nkv"), py::arg("d"), py::arg("scale"),
+        py::arg("rot_dim") = 0, py::arg("rot_base") = 10000.0, py::arg("rot_interleaved") = false,
+        py::arg("alibi") = py::none(), py::arg("window") = 0, py::arg("out") = py::none());
+  m.def("rowdot", &rowdot, py::arg("x"), py::arg("w"), py::arg("bias") = py::none(), py::arg("out") = py::none());
+  m.def("decode_step", &decode_step);
+  m.def("paged_kv_write", &paged_kv_write);
+  m.def("logprob_from_logits", &logprob_from_logits);
+  m.def("logprob_backward_inplace", &logprob_backward_inplace);
+  m.def("gae", &gae, py::arg("values"), py::arg("rewards"), py::arg("width"), py::arg("gamma"), py::arg("lam"),
+        py::arg("whiten") = true, py::arg("unbiased") = true);
+  m.def("whiten_", &whiten_);
+  m.def("ppo_loss", &ppo_loss);
+  m.def("kl_rewards", &kl_rewards);
+  m.def("adamw_flat", &adamw_flat);
+  m.def("sqnorm_", &sqnorm_);
+  m.def("clip_coef_", &clip_coef_, py::arg("sqsum"), py::arg("max_norm"), py::arg("hyper"), py::arg("norm_out") = py::none());
+  m.def("signal_barrier", &signal_barrier);
+  m.def("rs_adamw_ag", &rs_adamw_ag);
+  m.def("lerp_", &lerp_);
+  m.def("ppo_loss_num_outputs", [] { return b200_ppo_loss_num_outputs(); });
+  py::class_<PagedKVAllocator>(m, "PagedKVAllocator")
+      .def(py::init<int64_t, int64_t>())
+      .def("reserve", &PagedKVAllocator::reserve)
+      .def("release", &PagedKVAllocator::release)
+      .def("reset", &PagedKVAllocator::reset)
+      .def("block_table", &PagedKVAllocator::block_table)
+      .def_property_readonly("free_pages", &PagedKVAllocator::free_pages)
+      .def_property_readonly("page_size", &PagedKVAllocator::page_size)
+      .def_property_readonly("num_pages", &PagedKVAllocator::num_pages);
+}

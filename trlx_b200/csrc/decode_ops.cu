@@ -1,0 +1,392 @@
+// Rollout / scoring support kernels (sm_100a): normalisation, embedding gather, paged-KV decode attention with fused
+// rotary + cache append, value-head row-dot, and the per-step sequence bookkeeping that keeps the whole decode loop on
+// the device (so it can live in one CUDA graph).  Replaces the per-token Python loop + dozens of aten launches of HF
+// generate() used by the reference (trlx/trainer/accelerate_base_trainer.py:256-269).
+#include "ptx.cuh"
+
+namespace b200 {
+
+// ------------------------------------------------------------------------------------------------ norms
+// One warp per row when H <= 2048 would do, but a 128-thread block per row handles any H with 16-byte loads.
+template <bool RMS>
+__global__ void __launch_bounds__(128) norm_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+                                                   const __nv_bfloat16* __restrict__ b, __nv_bfloat16* __restrict__ y,
+                                                   int H, long long ldx, long long ldy, float eps) {
+  const int row = blockIdx.x;
+  const __nv_bfloat16* xr = x + (size_t)row * ldx;
+  __nv_bfloat16* yr = y + (size_t)row * ldy;
+  __shared__ float red[2][4];
+  float s = 0.f, ss = 0.f;
+  const int nvec = H >> 3;
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+    uint4 v = *reinterpret_cast<const uint4*>(xr + i * 8);
+    const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { float f = __bfloat162float(h[j]); s += f; ss += f * f; }
+  }
+  for (int i = (nvec << 3) + threadIdx.x; i < H; i += blockDim.x) { float f = __bfloat162float(xr[i]); s += f; ss += f * f; }
+  s = warp_sum(s); ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s; red[1][threadIdx.x >> 5] = ss; }
+  __syncthreads();
+  s = red[0][0] + red[0][1] + red[0][2] + red[0][3];
+  ss = red[1][0] + red[1][1] + red[1][2] + red[1][3];
+  const float mean = RMS ? 0.f : s / H;
+  const float var = RMS ? ss / H : fmaxf(ss / H - mean * mean, 0.f);
+  const float rstd = rsqrtf(var + eps);
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+    uint4 v = *reinterpret_cast<const uint4*>(xr + i * 8);
+    uint4 wv = *reinterpret_cast<const uint4*>(w + i * 8);
+    const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&v);
+    const __nv_bfloat16* wh = reinterpret_cast<const __nv_bfloat16*>(&wv);
+    uint4 o;
+    __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(&o);
+    if (b) {
+      uint4 bv = *reinterpret_cast<const uint4*>(b + i * 8);
+      const __nv_bfloat16* bh = reinterpret_cast<const __nv_bfloat16*>(&bv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        oh[j] = __float2bfloat16((__bfloat162float(h[j]) - mean) * rstd * __bfloat162float(wh[j]) + __bfloat162float(bh[j]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) oh[j] = __float2bfloat16((__bfloat162float(h[j]) - mean) * rstd * __bfloat162float(wh[j]));
+    }
+    *reinterpret_cast<uint4*>(yr + i * 8) = o;
+  }
+  for (int i = (nvec << 3) + threadIdx.x; i < H; i += blockDim.x) {
+    float f = (__bfloat162float(xr[i]) - mean) * rstd * __bfloat162float(w[i]);
+    if (b) f += __bfloat162float(b[i]);
+    yr[i] = __float2bfloat16(f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ embedding
+// x[b,:] = wte[token[b]] + wpe[pos[b] + pos_offset]   (wpe optional)
+__global__ void embed_kernel(const long long* __restrict__ tokens, const int* __restrict__ positions,
+                             const __nv_bfloat16* __restrict__ wte, const __nv_bfloat16* __restrict__ wpe, int pos_offset,
+                             __nv_bfloat16* __restrict__ x, int H) {
+  const int b = blockIdx.x;
+  const __nv_bfloat16* te = wte + (size_t)tokens[b] * H;
+  const __nv_bfloat16* pe = wpe ? wpe + (size_t)(positions[b] + pos_offset) * H : nullptr;
+  for (int i = threadIdx.x; i < (H >> 3); i += blockDim.x) {
+    uint4 a = *reinterpret_cast<const uint4*>(te + i * 8);
+    if (pe) {
+      uint4 p = *reinterpret_cast<const uint4*>(pe + i * 8);
+      __nv_bfloat162* a2 = reinterpret_cast<__nv_bfloat162*>(&a);
+      const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&p);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) a2[j] = __hadd2(a2[j], p2[j]);
+    }
+    *reinterpret_cast<uint4*>(x + (size_t)b * H + i * 8) = a;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ decode attention
+// One block per (sequence, query head); 4 warps; each 8-lane group owns one key at a time (16-byte loads).
+// qkv       : [B, (nq + 2 nkv) * d]   current-token projections (bias already added by the GEMM epilogue)
+// k/v cache : [num_pages, page_size, nkv, d]
+// The block for query head h also appends K/V of kv-head (h / group) when h % group == 0, after applying rotary.
+// seq_lens[b] is the number of valid keys INCLUDING the current token; rows with active[b] == 0 are skipped.
+template <int MAX_D>
+__global__ void __launch_bounds__(128)
+decode_attn_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ kcache, __nv_bfloat16* __restrict__ vcache,
+                   const int* __restrict__ block_table, const int* __restrict__ seq_lens, const int* __restrict__ positions,
+                   __nv_bfloat16* __restrict__ out, int nq, int nkv, int d, int page_size, int max_pages, float scale,
+                   int rot_dim, float rot_base, int rot_interleaved, const float* __restrict__ alibi_slopes, int window) {
+  const int b = blockIdx.x, h = blockIdx.y;
+  const int group = nq / nkv, kvh = h / group;
+  const int len = seq_lens[b];
+  if (len <= 0) return;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int sub = lane >> 3, l8 = lane & 7;       // 4 key-slots per warp, 8 lanes per key
+  const int row_stride = (nq + 2 * nkv) * d;
+  const __nv_bfloat16* qp = qkv + (size_t)b * row_stride + (size_t)h * d;
+  const __nv_bfloat16* kp = qkv + (size_t)b * row_stride + (size_t)(nq + kvh) * d;
+  const __nv_bfloat16* vp = qkv + (size_t)b * row_stride + (size_t)(nq + nkv + kvh) * d;
+  const int* bt = block_table + (size_t)b * max_pages;
+  const int pos = positions ? positions[b] : len - 1;
+
+  __shared__ float q_s[MAX_D];
+  __shared__ float knew_s[MAX_D];
+  __shared__ float red_m[4 * 4], red_l[4 * 4];
+  __shared__ float acc_s[16][MAX_D + 4];
+
+  // --- load q (and the new k), apply rotary
+  for (int i = tid; i < d; i += blockDim.x) { q_s[i] = __bfloat162float(qp[i]); knew_s[i] = __bfloat162float(kp[i]); }
+  __syncthreads();
+  if (rot_dim > 0) {
+    const int half = rot_dim >> 1;
+    float qn = 0.f, kn = 0.f;
+    int i0 = -1, i1 = -1;
+    if (tid < half) {
+      const float inv = powf(rot_base, -(float)tid / (float)half);
+      float sn, cs;
+      sincosf((float)pos * inv, &sn, &cs);
+      i0 = rot_interleaved ? 2 * tid : tid;
+      i1 = rot_interleaved ? 2 * tid + 1 : tid + half;
+      const float q0 = q_s[i0], q1 = q_s[i1], k0 = knew_s[i0], k1 = knew_s[i1];
+      qn = q0 * cs - q1 * sn; kn = k0 * cs - k1 * sn;
+      const float qn1 = q1 * cs + q0 * sn, kn1 = k1 * cs + k0 * sn;
+      q_s[i0] = qn; q_s[i1] = qn1; knew_s[i0] = kn; knew_s[i1] = kn1;
+    }
+    __syncthreads();
+  }
+  // --- append the new K/V to the paged cache (one query head per kv head does it)
+  const int last = len - 1;
+  if (h % group == 0) {
+    const size_t slot = ((size_t)bt[last / page_size] * page_size + (last % page_size)) * nkv + kvh;
+    for (int i = tid; i < d; i += blockDim.x) {
+      kcache[slot * d + i] = __float2bfloat16(knew_s[i]);
+      vcache[slot * d + i] = vp[i];
+    }
+  }
+  // --- online-softmax over cached keys [lo, last) plus the new key from shared memory
+  const int lo = (window > 0 && len > window) ? len - window : 0;
+  const float slope = alibi_slopes ? alibi_slopes[h] : 0.f;
+  float m = -INFINITY, l = 0.f;
+  float acc[MAX_D / 8];
+#pragma unroll
+  for (int i = 0; i < MAX_D / 8; ++i) acc[i] = 0.f;
+  // lane (sub, l8) accumulates output dims { l8*8 + 64*c + j } for its keys
+  for (int t = lo + warp * 4 + sub; t < len; t += 16) {
+    float part = 0.f;
+    const __nv_bfloat16* kptr = nullptr;
+    const __nv_bfloat16* vptr = nullptr;
+    if (t < last) {
+      const size_t slot = ((size_t)bt[t / page_size] * page_size + (t % page_size)) * nkv + kvh;
+      kptr = kcache + slot * d;
+      vptr = vcache + slot * d;
+#pragma unroll
+      for (int c = 0; c < MAX_D / 64; ++c) {
+        const int base = l8 * 8 + 64 * c;
+        if (base < d) {
+          uint4 kv = *reinterpret_cast<const uint4*>(kptr + base);
+          const __nv_bfloat16* kh = reinterpret_cast<const __nv_bfloat16*>(&kv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) part += q_s[base + j] * __bfloat162float(kh[j]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < MAX_D / 64; ++c) {
+        const int base = l8 * 8 + 64 * c;
+        if (base < d) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) part += q_s[base + j] * knew_s[base + j];
+        }
+      }
+    }
+    part += __shfl_xor_sync(0xffffffffu, part, 1);
+    part += __shfl_xor_sync(0xffffffffu, part, 2);
+    part += __shfl_xor_sync(0xffffffffu, part, 4);
+    float sc = part * scale + slope * (float)t;
+    const float mn = fmaxf(m, sc);
+    const float corr = __expf(m - mn), p = __expf(sc - mn);
+    l = l * corr + p;
+    m = mn;
+#pragma unroll
+    for (int c = 0; c < MAX_D / 64; ++c) {
+      const int base = l8 * 8 + 64 * c;
+      if (base < d) {
+        if (t < last) {
+          uint4 vv = *reinterpret_cast<const uint4*>(vptr + base);
+          const __nv_bfloat16* vh = reinterpret_cast<const __nv_bfloat16*>(&vv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[c * 8 + j] = acc[c * 8 + j] * corr + p * __bfloat162float(vh[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[c * 8 + j] = acc[c * 8 + j] * corr + p * __bfloat162float(vp[base + j]);
+        }
+      }
+    }
+  }
+  // --- combine the 16 (warp, sub) partial softmaxes
+  const int g = warp * 4 + sub;
+  if (l8 == 0) { red_m[g] = m; red_l[g] = l; }
+  __syncthreads();
+  float gm = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) gm = fmaxf(gm, red_m[i]);
+  float gl = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) gl += red_l[i] * ((red_m[i] == -INFINITY) ? 0.f : __expf(red_m[i] - gm));
+  const float my = (m == -INFINITY) ? 0.f : __expf(m - gm);
+#pragma unroll
+  for (int c = 0; c < MAX_D / 64; ++c) {
+    const int base = l8 * 8 + 64 * c;
+    if (base < d) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc_s[g][base + j] = acc[c * 8 + j] * my;
+    }
+  }
+  __syncthreads();
+  const float inv = 1.f / gl;
+  for (int i = tid; i < d; i += blockDim.x) {
+    float o = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) o += acc_s[k][i];
+    out[(size_t)b * nq * d + (size_t)h * d + i] = __float2bfloat16(o * inv);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ value head tail
+// out[m] = dot(x[m,:], w) + bias    (the N=1 projection of the value MLP; fp32 result)
+__global__ void rowdot_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+                              const __nv_bfloat16* __restrict__ bias, float* __restrict__ out, int M, int K, long long ldx) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const __nv_bfloat16* xr = x + (size_t)row * ldx;
+  float s = 0.f;
+  for (int i = lane * 8; i + 8 <= K; i += 256) {
+    uint4 a = *reinterpret_cast<const uint4*>(xr + i), b = *reinterpret_cast<const uint4*>(w + i);
+    const __nv_bfloat16* ah = reinterpret_cast<const __nv_bfloat16*>(&a);
+    const __nv_bfloat16* bh = reinterpret_cast<const __nv_bfloat16*>(&b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += __bfloat162float(ah[j]) * __bfloat162float(bh[j]);
+  }
+  for (int i = (K & ~7) + lane; i < K; i += 32) s += __bfloat162float(xr[i]) * __bfloat162float(w[i]);
+  s = warp_sum(s);
+  if (lane == 0) out[row] = s + (bias ? __bfloat162float(bias[0]) : 0.f);
+}
+
+// ------------------------------------------------------------------------------------------------ step bookkeeping
+// After sampling at decode step `*step_ptr`: record outputs for still-running rows, retire rows that emitted EOS or
+// hit their budget, set up the next step's inputs and bump the device-side step counter.  Everything stays on the
+// device, so ONE captured CUDA graph serves every decode step.  Launched as a single block.
+//   tokens_out/logprobs_out/ref_logprobs_out/values_out : [B, max_new]
+//   finished[b] : 0/1 ; seq_lens/positions advanced for rows that keep running ; n_running counts live rows.
+__global__ void decode_step_kernel(const long long* __restrict__ sampled, const float* __restrict__ lp,
+                                   const float* __restrict__ ref_lp, const float* __restrict__ value, int* __restrict__ step_ptr,
+                                   int max_new, int B, long long eos_id, long long pad_id, long long* __restrict__ tokens_out,
+                                   float* __restrict__ logprobs_out, float* __restrict__ ref_logprobs_out,
+                                   float* __restrict__ values_out, int* __restrict__ finished, int* __restrict__ resp_lens,
+                                   int* __restrict__ seq_lens, int* __restrict__ positions, long long* __restrict__ next_tokens,
+                                   int* __restrict__ n_running) {
+  const int step = *step_ptr;
+  int retired = 0;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    if (step >= max_new) break;
+    const size_t o = (size_t)b * max_new + step;
+    if (finished[b]) {
+      tokens_out[o] = pad_id;
+      logprobs_out[o] = 0.f;
+      if (ref_logprobs_out) ref_logprobs_out[o] = 0.f;
+      if (values_out) values_out[o] = 0.f;
+      next_tokens[b] = pad_id;
+      continue;
+    }
+    const long long tok = sampled[b];
+    tokens_out[o] = tok;
+    logprobs_out[o] = lp[b];
+    if (ref_logprobs_out) ref_logprobs_out[o] = ref_lp ? ref_lp[b] : 0.f;
+    if (values_out) values_out[o] = value ? value[b] : 0.f;
+    resp_lens[b] = step + 1;
+    const bool done = (tok == eos_id) || (step + 1 >= max_new);
+    if (done) {
+      finished[b] = 1;
+      seq_lens[b] = 0;  // attention blocks for retired rows exit immediately
+      ++retired;
+    } else {
+      seq_lens[b] += 1;
+      positions[b] += 1;
+    }
+    next_tokens[b] = tok;
+  }
+  if (retired) atomicSub(n_running, retired);
+  __syncthreads();
+  if (threadIdx.x == 0) *step_ptr = step + 1;
+}
+
+// Scatter prefill K/V ([B, T, nkv, d], left- or right-padded) into the paged cache: token t of row b (valid when
+// first[b] <= t < first[b] + lens[b]) goes to logical slot t - first[b].
+__global__ void paged_kv_write_kernel(const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v,
+                                      __nv_bfloat16* __restrict__ kcache, __nv_bfloat16* __restrict__ vcache,
+                                      const int* __restrict__ block_table, const int* __restrict__ first,
+                                      const int* __restrict__ lens, int T, int nkv, int d, int page_size, int max_pages,
+                                      long long k_stride_b, long long k_stride_t) {
+  const int b = blockIdx.y, t = blockIdx.x;
+  const int s = t - first[b];
+  if (s < 0 || s >= lens[b]) return;
+  const size_t slot = (size_t)block_table[(size_t)b * max_pages + s / page_size] * page_size + (s % page_size);
+  const int row = nkv * d;
+  const __nv_bfloat16* ks = k + (size_t)b * k_stride_b + (size_t)t * k_stride_t;
+  const __nv_bfloat16* vs = v + (size_t)b * k_stride_b + (size_t)t * k_stride_t;
+  for (int i = threadIdx.x * 8; i < row; i += blockDim.x * 8) {
+    *reinterpret_cast<uint4*>(kcache + slot * row + i) = *reinterpret_cast<const uint4*>(ks + i);
+    *reinterpret_cast<uint4*>(vcache + slot * row + i) = *reinterpret_cast<const uint4*>(vs + i);
+  }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_norm_bf16(const void* x, const void* w, const void* b, void* y, int rows, int H, long long ldx,
+                              long long ldy, float eps, int rms, cudaStream_t stream) {
+  if (rows <= 0) return 0;
+  if (rms)
+    norm_kernel<true><<<rows, 128, 0, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w, nullptr,
+                                                (__nv_bfloat16*)y, H, ldx, ldy, eps);
+  else
+    norm_kernel<false><<<rows, 128, 0, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w, (const __nv_bfloat16*)b,
+                                                 (__nv_bfloat16*)y, H, ldx, ldy, eps);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int b200_embed_bf16(const long long* tokens, const int* positions, const void* wte, const void* wpe,
+                               int pos_offset, void* x, int B, int H, cudaStream_t stream) {
+  if (B <= 0) return 0;
+  embed_kernel<<<B, 128, 0, stream>>>(tokens, positions, (const __nv_bfloat16*)wte, (const __nv_bfloat16*)wpe, pos_offset,
+                                      (__nv_bfloat16*)x, H);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int b200_decode_attention_bf16(const void* qkv, void* kcache, void* vcache, const int* block_table,
+                                          const int* seq_lens, const int* positions, void* out, int B, int nq, int nkv, int d,
+                                          int page_size, int max_pages, float scale, int rot_dim, float rot_base,
+                                          int rot_interleaved, const float* alibi_slopes, int window, cudaStream_t stream) {
+  if (B <= 0) return 0;
+  if (d % 8 != 0 || d > 256) return -2;
+  dim3 grid(B, nq);
+#define LAUNCH(MD)                                                                                                       \
+  decode_attn_kernel<MD><<<grid, 128, 0, stream>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)kcache, (__nv_bfloat16*)vcache, \
+                                                   block_table, seq_lens, positions, (__nv_bfloat16*)out, nq, nkv, d,      \
+                                                   page_size, max_pages, scale, rot_dim, rot_base, rot_interleaved,        \
+                                                   alibi_slopes, window)
+  if (d <= 64) LAUNCH(64);
+  else if (d <= 128) LAUNCH(128);
+  else LAUNCH(256);
+#undef LAUNCH
+  return (int)cudaGetLastError();
+}
+
+extern "C" int b200_rowdot_bf16(const void* x, const void* w, const void* bias, float* out, int M, int K, long long ldx,
+                                cudaStream_t stream) {
+  if (M <= 0) return 0;
+  rowdot_kernel<<<(M + 3) / 4, 128, 0, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w, (const __nv_bfloat16*)bias,
+                                                 out, M, K, ldx);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int b200_decode_step(const long long* sampled, const float* lp, const float* ref_lp, const float* value,
+                                int* step_ptr, int max_new, int B, long long eos_id, long long pad_id, long long* tokens_out,
+                                float* logprobs_out, float* ref_logprobs_out, float* values_out, int* finished, int* resp_lens,
+                                int* seq_lens, int* positions, long long* next_tokens, int* n_running, cudaStream_t stream) {
+  if (B <= 0) return 0;
+  decode_step_kernel<<<1, 256, 0, stream>>>(sampled, lp, ref_lp, value, step_ptr, max_new, B, eos_id, pad_id, tokens_out,
+                                            logprobs_out, ref_logprobs_out, values_out, finished, resp_lens, seq_lens,
+                                            positions, next_tokens, n_running);
+  return (int)cudaGetLastError();
+}
+
+// k / v: [B, T, nkv*d] views with arbitrary batch / time strides (elements); nkv*d % 8 == 0.
+extern "C" int b200_paged_kv_write(const void* k, const void* v, void* kcache, void* vcache, const int* block_table,
+                                   const int* first, const int* lens, int B, int T, int nkv, int d, int page_size,
+                                   int max_pages, long long stride_b, long long stride_t, cudaStream_t stream) {
+  if (B <= 0 || T <= 0) return 0;
+  dim3 grid(T, B);
+  paged_kv_write_kernel<<<grid, 64, 0, stream>>>((const __nv_bfloat16*)k, (const __nv_bfloat16*)v, (__nv_bfloat16*)kcache,
+                                                 (__nv_bfloat16*)vcache, block_table, first, lens, T, nkv, d, page_size,
+                                                 max_pages, stride_b, stride_t);
+  return (int)cudaGetLastError();
+}

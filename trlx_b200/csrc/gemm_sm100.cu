@@ -1,0 +1,463 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a:  D[M,N] = A[M,K] · B[N,K]^T  (both operands K-major bf16, fp32 accumulate)
+//
+// One CTA computes a 128 x BN output tile:
+//   warp 0 (one lane)  : TMA producer  — cp.async.bulk.tensor tiles of A (128x64) and B (BNx64), 128B-swizzled,
+//                        into a multi-stage shared-memory ring guarded by full/empty mbarriers
+//   warp 1 (one lane)  : MMA issuer    — tcgen05.mma.cta_group::1.kind::f16, accumulator in TMEM (BN fp32 columns),
+//                        tcgen05.commit releases ring slots and finally signals the epilogue
+//   warps 2..5         : epilogue      — tcgen05.ld 32x32b (one output row per thread), fused epilogue, global store
+//
+// Two epilogues share the mainloop:
+//   * STORE   : out = act(alpha * acc [* col_scale[n]] + bias[n]) + residual[m,n]      (bf16 or fp32 out)
+//   * LMHEAD  : never writes logits.  Per (row, N-tile) it emits online-softmax partials (max, sum-exp), the
+//               logit of a given label, and (optionally) a Gumbel-max sampling candidate; a tiny second kernel
+//               merges the partials into  logsumexp / log p(label) / sampled token + its log-prob.
+//               This replaces the reference's  logits = lm_head(h); log_softmax; gather  chain
+//               (trlx/utils/modeling.py:213-219) and HF generate's softmax+multinomial.
+#include <cstdio>
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "ptx.cuh"
+
+namespace b200 {
+
+constexpr int BM = 128;
+constexpr int BK = 64;        // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+
+enum Act { ACT_NONE = 0, ACT_GELU_TANH = 1, ACT_GELU_ERF = 2, ACT_RELU = 3, ACT_SILU = 4 };
+
+struct StoreEpilogue {
+  void* out;                 // bf16 or fp32 [M, ldo]
+  const __nv_bfloat16* bias; // [N] or null
+  const __nv_bfloat16* residual;  // [M, ldr] or null
+  const float* col_scale;    // [N] or null
+  long long ldo, ldr;
+  float alpha;
+  int act;
+  int out_f32;
+};
+
+struct LMHeadEpilogue {
+  const __nv_bfloat16* bias;   // [N] or null
+  const long long* labels;     // [M] or null  (label < 0 -> ignored)
+  float* part_max;             // [M, n_tiles]
+  float* part_sum;             // [M, n_tiles]
+  float* label_logit;          // [M]   (written by the tile that owns the label)
+  // Gumbel-max sampling (enabled when samp_key != null)
+  float* samp_key;             // [M, n_tiles] best perturbed key in tile
+  float* samp_logit;           // [M, n_tiles] raw logit of that candidate
+  int* samp_idx;               // [M, n_tiles]
+  float inv_temperature;      // <= 0 -> greedy (no Gumbel noise)
+  unsigned long long seed;
+  const int* step_ptr;         // optional device step counter: mixed into the seed, gates `suppress_col`
+  int suppress_col;            // column forced to -inf while step < suppress_until (EOS before min_new_tokens), -1 = none
+  int suppress_until;
+  int n_tiles;
+};
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  switch (act) {
+    case ACT_GELU_TANH: return gelu_tanh(x);
+    case ACT_GELU_ERF: return gelu_erf(x);
+    case ACT_RELU: return fmaxf(x, 0.f);
+    case ACT_SILU: return silu(x);
+    default: return x;
+  }
+}
+
+// counter-based uniform in (0,1): splitmix64 of (seed, row, col)
+__device__ __forceinline__ float uniform01(unsigned long long seed, unsigned int row, unsigned int col) {
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (((unsigned long long)row << 32) | col);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return ((float)(z >> 40) + 0.5f) * (1.0f / 16777216.0f);
+}
+
+template <int BN, int EPI>  // EPI: 0 = store, 1 = lm-head
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M, int N, int K,
+               int stages, StoreEpilogue se, LMHeadEpilogue le) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr uint32_t A_BYTES = BM * BK * 2;
+  constexpr uint32_t B_BYTES = BN * BK * 2;
+  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+
+  // 1024-byte aligned base (dynamic smem alignment is only guaranteed to 16 B)
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)stages * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + stages;
+  uint64_t* tmem_full_bar = empty_bar + stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
+  const int nkb = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % stages;
+        const uint32_t phase = (kb / stages) & 1;
+        mbar_wait(&empty_bar[s], phase ^ 1);
+        uint8_t* a_dst = smem + (size_t)s * STAGE_BYTES;
+        uint8_t* b_dst = a_dst + A_BYTES;
+        mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+        tma_load_2d(a_dst, &map_a, &full_bar[s], kb * BK, m0);
+        tma_load_2d(b_dst, &map_b, &full_bar[s], kb * BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(1, 1, BM, BN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % stages;
+        const uint32_t phase = (kb / stages) & 1;
+        mbar_wait(&full_bar[s], phase);
+        tc_fence_after_sync();
+        const uint32_t a_addr = smem_u32(smem + (size_t)s * STAGE_BYTES);
+        const uint64_t da = umma_desc_k_sw128(a_addr);
+        const uint64_t db = umma_desc_k_sw128(a_addr + A_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+          umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    // ---------------- epilogue: 4 warps, warp (w & 3) owns TMEM lanes [32*(w&3), 32*(w&3)+32)
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + lane;
+    const bool row_ok = row < M;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after_sync();
+    const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+
+    if constexpr (EPI == 0) {
+      const bool vec_ok = ((se.ldo & 7) == 0) && (se.residual == nullptr || (se.ldr & 7) == 0);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr_row + c, r);
+        tmem_ld_wait();
+        const int col0 = n0 + c;
+        if (!row_ok || col0 >= N) continue;
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int col = col0 + j;
+          float x = __uint_as_float(r[j]) * se.alpha;
+          if (col < N) {
+            if (se.col_scale) x *= se.col_scale[col];
+            if (se.bias) x += __bfloat162float(se.bias[col]);
+          }
+          v[j] = apply_act(x, se.act);
+        }
+        const bool full = (col0 + 16 <= N);
+        if (se.residual) {
+          const __nv_bfloat16* rp = se.residual + (size_t)row * se.ldr + col0;
+          if (full && vec_ok) {
+            uint4 ra = *reinterpret_cast<const uint4*>(rp), rb = *reinterpret_cast<const uint4*>(rp + 8);
+            const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&ra);
+            const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(&rb);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { v[j] += __bfloat162float(h[j]); v[8 + j] += __bfloat162float(g[j]); }
+          } else {
+            for (int j = 0; j < 16 && col0 + j < N; ++j) v[j] += __bfloat162float(rp[j]);
+          }
+        }
+        if (se.out_f32) {
+          float* op = reinterpret_cast<float*>(se.out) + (size_t)row * se.ldo + col0;
+          if (full && (se.ldo & 3) == 0) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+            for (int j = 0; j < 16 && col0 + j < N; ++j) op[j] = v[j];
+          }
+        } else {
+          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(se.out) + (size_t)row * se.ldo + col0;
+          if (full && vec_ok) {
+            uint4 pk[2];
+            __nv_bfloat162* p2 = reinterpret_cast<__nv_bfloat162*>(pk);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) p2[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+            *reinterpret_cast<uint4*>(op) = pk[0];
+            *reinterpret_cast<uint4*>(op + 8) = pk[1];
+          } else {
+            for (int j = 0; j < 16 && col0 + j < N; ++j) op[j] = __float2bfloat16(v[j]);
+          }
+        }
+      }
+    } else {
+      const long long label = (row_ok && le.labels) ? le.labels[row] : -1;
+      float mx = -INFINITY, sum = 0.f;
+      float best_key = -INFINITY, best_logit = 0.f;
+      int best_idx = -1;
+      const bool sampling = le.samp_key != nullptr;
+      const int step = le.step_ptr ? *le.step_ptr : 0;
+      const int suppress = (le.suppress_col >= 0 && step < le.suppress_until) ? le.suppress_col : -1;
+      const unsigned long long seed = le.seed + 0x632BE59BD9B4E019ull * (unsigned long long)(step + 1);
+      const bool greedy = le.inv_temperature <= 0.f;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr_row + c, r);
+        tmem_ld_wait();
+        const int col0 = n0 + c;
+        if (!row_ok || col0 >= N) continue;
+        float z[16];
+        float cmax = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int col = col0 + j;
+          float x = -INFINITY;
+          if (col < N && col != suppress) {
+            x = __uint_as_float(r[j]);
+            if (le.bias) x += __bfloat162float(le.bias[col]);
+            if (col == label) le.label_logit[row] = x;
+          }
+          z[j] = x;
+          cmax = fmaxf(cmax, x);
+        }
+        if (cmax > mx) { sum *= __expf(mx - cmax); mx = cmax; }   // exp(-inf - finite) = 0 handles the first chunk
+        if (mx > -INFINITY) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) sum += __expf(z[j] - mx);
+        }
+        if (sampling) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (z[j] == -INFINITY) continue;
+            float key = z[j];
+            if (!greedy) key = z[j] * le.inv_temperature - __logf(-__logf(uniform01(seed, (unsigned)row, (unsigned)(col0 + j))));
+            if (key > best_key) { best_key = key; best_logit = z[j]; best_idx = col0 + j; }
+          }
+        }
+      }
+      if (row_ok) {
+        const size_t o = (size_t)row * le.n_tiles + blockIdx.x;
+        le.part_max[o] = mx;
+        le.part_sum[o] = sum;
+        if (sampling) { le.samp_key[o] = best_key; le.samp_logit[o] = best_logit; le.samp_idx[o] = best_idx; }
+      }
+    }
+    tc_fence_before_sync();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// Merge the per-tile partials of the LM-head epilogue.  One warp per row.
+__global__ void lmhead_reduce_kernel(const float* __restrict__ part_max, const float* __restrict__ part_sum,
+                                     const float* __restrict__ label_logit, const long long* __restrict__ labels,
+                                     const float* __restrict__ samp_key, const float* __restrict__ samp_logit,
+                                     const int* __restrict__ samp_idx, int M, int n_tiles, float* __restrict__ lse_out,
+                                     float* __restrict__ logprob_out, long long* __restrict__ token_out,
+                                     float* __restrict__ token_logprob_out) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const size_t base = (size_t)row * n_tiles;
+  float mx = -INFINITY;
+  for (int t = lane; t < n_tiles; t += 32) mx = fmaxf(mx, part_max[base + t]);
+  mx = warp_max(mx);
+  float s = 0.f;
+  for (int t = lane; t < n_tiles; t += 32) {
+    const float pm = part_max[base + t];
+    if (pm > -INFINITY) s += part_sum[base + t] * __expf(pm - mx);
+  }
+  s = warp_sum(s);
+  const float lse = mx + __logf(s);
+  if (lane == 0) {
+    if (lse_out) lse_out[row] = lse;
+    if (logprob_out) logprob_out[row] = (labels && labels[row] >= 0) ? label_logit[row] - lse : 0.f;
+  }
+  if (samp_key) {
+    float bk = -INFINITY, bl = 0.f;
+    int bi = -1;
+    for (int t = lane; t < n_tiles; t += 32) {
+      const float k = samp_key[base + t];
+      if (k > bk) { bk = k; bl = samp_logit[base + t]; bi = samp_idx[base + t]; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ok = __shfl_xor_sync(0xffffffffu, bk, o);
+      const float ol = __shfl_xor_sync(0xffffffffu, bl, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ok > bk || (ok == bk && oi >= 0 && (bi < 0 || oi < bi))) { bk = ok; bl = ol; bi = oi; }
+    }
+    if (lane == 0) {
+      token_out[row] = bi;
+      token_logprob_out[row] = bl - lse;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// K-major bf16 matrix [rows, cols] with row pitch ld (elements); box = box_rows x 64 elements, 128B swizzle.
+static bool make_map(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
+  using Key = std::tuple<const void*, long long, long long, long long, int>;
+  static std::map<Key, CUtensorMap> cache;
+  static std::mutex mu;
+  Key key{ptr, rows, cols, ld, box_rows};
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *map = it->second; return true; }
+  }
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return false;
+  std::lock_guard<std::mutex> g(mu);
+  if (cache.size() > 4096) cache.clear();
+  cache[key] = *map;
+  return true;
+}
+
+static int pick_bn(int M, int N) {
+  const int m_tiles = (M + BM - 1) / BM;
+  // prefer the widest tile that still yields >= ~1 wave of CTAs on 148 SMs
+  for (int bn : {128, 64, 32}) {
+    if ((long long)m_tiles * ((N + bn - 1) / bn) >= 148) return bn;
+  }
+  return 32;
+}
+
+template <int BN, int EPI>
+static cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& mb, int M, int N, int K, const StoreEpilogue& se,
+                          const LMHeadEpilogue& le, cudaStream_t stream) {
+  constexpr int stage_bytes = BM * BK * 2 + BN * BK * 2;
+  const int nkb = (K + BK - 1) / BK;
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages > nkb) stages = nkb < 2 ? 2 : nkb;
+  const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;
+  auto kern = gemm_tn_kernel<BN, EPI>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+  kern<<<grid, NUM_THREADS, smem, stream>>>(ma, mb, M, N, K, stages, se, le);
+  return cudaGetLastError();
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+// act: 0 none, 1 gelu_tanh, 2 gelu_erf, 3 relu, 4 silu.  Requirements: K % 8 == 0, lda/ldb % 8 == 0, 16B-aligned A/B.
+extern "C" int b200_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K, long long lda, long long ldb,
+                              long long ldo, const void* bias, const void* residual, long long ldr, const float* col_scale,
+                              float alpha, int act, int out_f32, int force_bn, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  const int bn = force_bn ? force_bn : pick_bn(M, N);
+  CUtensorMap ma, mb;
+  if (!make_map(&ma, A, M, K, lda, BM) || !make_map(&mb, B, N, K, ldb, bn)) return -1;
+  StoreEpilogue se{out, (const __nv_bfloat16*)bias, (const __nv_bfloat16*)residual, col_scale, ldo, ldr, alpha, act, out_f32};
+  LMHeadEpilogue le{};
+  cudaError_t e;
+  switch (bn) {
+    case 128: e = launch<128, 0>(ma, mb, M, N, K, se, le, stream); break;
+    case 64: e = launch<64, 0>(ma, mb, M, N, K, se, le, stream); break;
+    default: e = launch<32, 0>(ma, mb, M, N, K, se, le, stream); break;
+  }
+  return (int)e;
+}
+
+extern "C" int b200_lmhead_tiles(int N) { return (N + 127) / 128; }
+
+// Fused LM head.  Workspace (fp32/int32) of 5 * M * n_tiles + M elements is supplied by the caller:
+//   part_max | part_sum | samp_key | samp_logit | samp_idx(int) | label_logit[M]
+// Outputs (any may be null): lse[M], logprob[M] (of labels), token[M] + token_logprob[M] (when sample != 0).
+extern "C" int b200_lmhead_bf16(const void* H, const void* W, int M, int N, int K, long long ldh, long long ldw,
+                                const void* bias, const long long* labels, float* workspace, float* lse, float* logprob,
+                                int sample, float temperature, unsigned long long seed, const int* step_ptr,
+                                int suppress_col, int suppress_until, long long* token, float* token_logprob,
+                                cudaStream_t stream) {
+  if (M <= 0) return 0;
+  constexpr int BN = 128;
+  const int n_tiles = (N + BN - 1) / BN;
+  CUtensorMap ma, mb;
+  if (!make_map(&ma, H, M, K, ldh, BM) || !make_map(&mb, W, N, K, ldw, BN)) return -1;
+  const size_t mt = (size_t)M * n_tiles;
+  LMHeadEpilogue le{};
+  le.bias = (const __nv_bfloat16*)bias;
+  le.labels = labels;
+  le.part_max = workspace;
+  le.part_sum = workspace + mt;
+  le.samp_key = sample ? workspace + 2 * mt : nullptr;
+  le.samp_logit = workspace + 3 * mt;
+  le.samp_idx = reinterpret_cast<int*>(workspace + 4 * mt);
+  le.label_logit = workspace + 5 * mt;
+  le.inv_temperature = temperature > 0.f ? 1.0f / temperature : 0.f;
+  le.seed = seed;
+  le.step_ptr = step_ptr;
+  le.suppress_col = suppress_col;
+  le.suppress_until = suppress_until;
+  le.n_tiles = n_tiles;
+  StoreEpilogue se{};
+  cudaError_t e = launch<BN, 1>(ma, mb, M, N, K, se, le, stream);
+  if (e != cudaSuccess) return (int)e;
+  const int warps_per_block = 8;
+  lmhead_reduce_kernel<<<(M + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, stream>>>(
+      le.part_max, le.part_sum, le.label_logit, labels, le.samp_key, le.samp_logit, le.samp_idx, M, n_tiles, lse, logprob,
+      token, token_logprob);
+  return (int)cudaGetLastError();
+}

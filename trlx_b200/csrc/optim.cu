@@ -1,0 +1,217 @@
+// Partitioned AdamW for sm_100a, optionally fused with the data-parallel gradient reduce-scatter and the parameter
+// all-gather over NVLink peer memory.
+//
+// Layout: all trainable parameters of a rank live in ONE flat bf16 buffer (`param`), gradients in a matching flat bf16
+// buffer (`grad`).  Optimizer state (fp32 master copy, exp_avg, exp_avg_sq) exists only for the shard a rank owns.
+// With world > 1 the flat grad/param buffers are symmetric-memory allocations, so every rank holds device pointers to
+// every peer's copy:
+//
+//   fused_rs_adamw_ag:   g[i]   = (1/world) * sum_r peer_grad[r][i]          <- P2P loads over NVLink (reduce-scatter)
+//                        m,v,w  = AdamW(g[i])                                 <- fp32 master update of the owned shard
+//                        peer_param[r][i] = bf16(w)   for every r             <- P2P stores over NVLink (all-gather)
+//
+// which is the reference's  DDP all-reduce -> (clip) -> optimizer.step  /  ZeRO-2 reduce-scatter -> step -> all-gather
+// (accelerate_base_trainer.py:574-587) done in a single pass over the shard.  `signal_barrier` is the system-scope
+// flag handshake that orders "every rank finished backward" before and "every rank sees new params" after.
+#include "ptx.cuh"
+
+namespace b200 {
+
+constexpr int MAX_PEERS = 16;
+struct PeerPtrs { void* p[MAX_PEERS]; };
+
+// hyper[0]=lr, hyper[1]=1-beta1^t, hyper[2]=1-beta2^t, hyper[3]=grad scale (clip coefficient / loss-scale inverse)
+struct AdamArgs {
+  float beta1, beta2, eps, weight_decay;
+  int decoupled;  // 1 = AdamW (decoupled decay), 0 = Adam (L2 added to the gradient)
+};
+
+__device__ __forceinline__ float adam_update(float g, float& w, float& m, float& v, const AdamArgs& a, float lr, float bc1,
+                                             float bc2) {
+  if (!a.decoupled) g += a.weight_decay * w;
+  m = a.beta1 * m + (1.f - a.beta1) * g;
+  v = a.beta2 * v + (1.f - a.beta2) * g * g;
+  const float denom = sqrtf(v / bc2) + a.eps;
+  if (a.decoupled) w *= (1.f - lr * a.weight_decay);
+  w -= lr * (m / bc1) / denom;
+  return w;
+}
+
+// Single-GPU / already-reduced path.  grad may be bf16 (grad_f32 == 0) or fp32.
+__global__ void __launch_bounds__(256)
+adamw_flat_kernel(__nv_bfloat16* __restrict__ param, float* __restrict__ master, const void* __restrict__ grad, int grad_f32,
+                  float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq, long long n, AdamArgs a,
+                  const float* __restrict__ hyper) {
+  const float lr = hyper[0], bc1 = hyper[1], bc2 = hyper[2], gs = hyper[3];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float g = (grad_f32 ? reinterpret_cast<const float*>(grad)[i]
+                              : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(grad)[i])) * gs;
+    float w = master[i], m = exp_avg[i], v = exp_avg_sq[i];
+    adam_update(g, w, m, v, a, lr, bc1, bc2);
+    master[i] = w; exp_avg[i] = m; exp_avg_sq[i] = v;
+    param[i] = __float2bfloat16(w);
+  }
+}
+
+// sum of squares of a flat bf16/fp32 buffer -> out[0] (double, atomically accumulated; caller zeroes)
+__global__ void __launch_bounds__(256) sqnorm_kernel(const void* __restrict__ x, int is_f32, long long n, double* __restrict__ out) {
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float f = is_f32 ? reinterpret_cast<const float*>(x)[i] : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x)[i]);
+    s += f * f;
+  }
+  s = warp_sum(s);
+  __shared__ float sh[8];
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) t += sh[i];
+    atomicAdd(out, t);
+  }
+}
+
+// hyper[3] = min(1, max_norm / (sqrt(sqsum) + 1e-6))
+__global__ void clip_coef_kernel(const double* __restrict__ sqsum, float max_norm, float* __restrict__ hyper,
+                                 float* __restrict__ norm_out) {
+  const float norm = (float)sqrt(*sqsum);
+  if (norm_out) *norm_out = norm;
+  hyper[3] = fminf(1.f, max_norm / (norm + 1e-6f));
+}
+
+// System-scope barrier across `world` ranks: rank r bumps slot [r] in every peer's signal pad, then waits until all
+// slots of its own pad reach `epoch`.  One block, >= world threads.
+__global__ void signal_barrier_kernel(PeerPtrs pads, int rank, int world, uint32_t epoch) {
+  const int t = threadIdx.x;
+  __threadfence_system();
+  if (t < world) {
+    uint32_t* remote = reinterpret_cast<uint32_t*>(pads.p[t]) + rank;
+    st_release_sys(remote, epoch);
+    const uint32_t* mine = reinterpret_cast<const uint32_t*>(pads.p[rank]) + t;
+    while (ld_acquire_sys(mine) < epoch) { __nanosleep(64); }
+  }
+  __syncthreads();
+  __threadfence_system();
+}
+
+// Fused reduce-scatter + AdamW + all-gather over the owned shard [lo, lo + n).  8 bf16 (16 B) per thread-iteration.
+// lo and n must be multiples of 8.  If sq_out != null the squared norm of the averaged gradient is accumulated instead
+// of updating (phase 1 of clipped updates: the reduced gradient is parked in fp32 `gshard`).
+template <bool UPDATE>
+__global__ void __launch_bounds__(256)
+rs_adamw_ag_kernel(PeerPtrs grads, PeerPtrs params, int world, long long lo, long long n, float* __restrict__ master,
+                   float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq, float* __restrict__ gshard, int use_gshard,
+                   AdamArgs a, const float* __restrict__ hyper, double* __restrict__ sq_out) {
+  const float lr = hyper[0], bc1 = hyper[1], bc2 = hyper[2], gs = hyper[3];
+  const float inv_world = 1.f / (float)world;
+  float sq = 0.f;
+  const long long nvec = n >> 3;
+  for (long long vi = (long long)blockIdx.x * blockDim.x + threadIdx.x; vi < nvec; vi += (long long)gridDim.x * blockDim.x) {
+    const long long i = vi << 3;
+    float g[8];
+    if (use_gshard && UPDATE) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = gshard[i + j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = 0.f;
+      for (int r = 0; r < world; ++r) {
+        const int4 raw = ld_nc_v4(reinterpret_cast<const int4*>(reinterpret_cast<const __nv_bfloat16*>(grads.p[r]) + lo + i));
+        const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&raw);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] += __bfloat162float(h[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] *= inv_world;
+    }
+    if (!UPDATE) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { gshard[i + j] = g[j]; sq += g[j] * g[j]; }
+      continue;
+    }
+    uint4 packed;
+    __nv_bfloat16* ph = reinterpret_cast<__nv_bfloat16*>(&packed);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float w = master[i + j], m = exp_avg[i + j], v = exp_avg_sq[i + j];
+      adam_update(g[j] * gs, w, m, v, a, lr, bc1, bc2);
+      master[i + j] = w; exp_avg[i + j] = m; exp_avg_sq[i + j] = v;
+      ph[j] = __float2bfloat16(w);
+    }
+    for (int r = 0; r < world; ++r)
+      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(params.p[r]) + lo + i) = packed;
+  }
+  if (!UPDATE && sq_out) {
+    sq = warp_sum(sq);
+    if ((threadIdx.x & 31) == 0) atomicAdd(sq_out, (double)sq);
+  }
+}
+
+// Polyak / EMA update of target networks:  tgt = alpha * src + (1 - alpha) * tgt   (ILQL target-Q sync)
+__global__ void lerp_kernel(__nv_bfloat16* __restrict__ tgt, const __nv_bfloat16* __restrict__ src, long long n, float alpha) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    tgt[i] = __float2bfloat16(alpha * __bfloat162float(src[i]) + (1.f - alpha) * __bfloat162float(tgt[i]));
+}
+
+static int grid_for(long long n, int per_thread = 1) {
+  long long b = (n / per_thread + 255) / 256;
+  if (b < 1) b = 1;
+  if (b > 148 * 8) b = 148 * 8;
+  return (int)b;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_adamw_flat(void* param, float* master, const void* grad, int grad_f32, float* exp_avg, float* exp_avg_sq,
+                               long long n, float beta1, float beta2, float eps, float weight_decay, int decoupled,
+                               const float* hyper, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  AdamArgs a{beta1, beta2, eps, weight_decay, decoupled};
+  adamw_flat_kernel<<<grid_for(n), 256, 0, stream>>>((__nv_bfloat16*)param, master, grad, grad_f32, exp_avg, exp_avg_sq, n, a, hyper);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int b200_sqnorm(const void* x, int is_f32, long long n, double* out, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  sqnorm_kernel<<<grid_for(n), 256, 0, stream>>>(x, is_f32, n, out);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int b200_clip_coef(const double* sqsum, float max_norm, float* hyper, float* norm_out, cudaStream_t stream) {
+  clip_coef_kernel<<<1, 1, 0, stream>>>(sqsum, max_norm, hyper, norm_out);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int b200_signal_barrier(void* const* pads, int rank, int world, unsigned int epoch, cudaStream_t stream) {
+  if (world > MAX_PEERS) return -3;
+  PeerPtrs p{};
+  for (int i = 0; i < world; ++i) p.p[i] = pads[i];
+  signal_barrier_kernel<<<1, 32, 0, stream>>>(p, rank, world, epoch);
+  return (int)cudaGetLastError();
+}
+
+// mode 0: fused reduce + update + gather ; mode 1: reduce into gshard + squared norm ; mode 2: update from gshard + gather
+extern "C" int b200_rs_adamw_ag(void* const* grads, void* const* params, int world, long long lo, long long n, float* master,
+                                float* exp_avg, float* exp_avg_sq, float* gshard, int mode, float beta1, float beta2,
+                                float eps, float weight_decay, int decoupled, const float* hyper, double* sq_out,
+                                cudaStream_t stream) {
+  if (n <= 0) return 0;
+  if (world > MAX_PEERS || (lo & 7) || (n & 7)) return -3;
+  PeerPtrs g{}, p{};
+  for (int i = 0; i < world; ++i) { g.p[i] = grads[i]; p.p[i] = params[i]; }
+  AdamArgs a{beta1, beta2, eps, weight_decay, decoupled};
+  const int grid = grid_for(n, 8);
+  if (mode == 1)
+    rs_adamw_ag_kernel<false><<<grid, 256, 0, stream>>>(g, p, world, lo, n, master, exp_avg, exp_avg_sq, gshard, 1, a, hyper, sq_out);
+  else
+    rs_adamw_ag_kernel<true><<<grid, 256, 0, stream>>>(g, p, world, lo, n, master, exp_avg, exp_avg_sq, gshard, mode == 2, a, hyper, nullptr);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int b200_lerp_bf16(void* tgt, const void* src, long long n, float alpha, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  lerp_kernel<<<grid_for(n), 256, 0, stream>>>((__nv_bfloat16*)tgt, (const __nv_bfloat16*)src, n, alpha);
+  return (int)cudaGetLastError();
+}

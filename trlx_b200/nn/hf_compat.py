@@ -248,3 +248,49 @@ def branch_from_hf(spec: ArchSpec, hf_branch_sd: SD) -> SD:
         for k, v in fam.block_from_hf(spec, b).items():
             out[f"decoder_blocks.{i}.{k}"] = v
     return out
+
+
+# ---- adapter target resolution (LoRA on the fused canonical projections) -------------------------------------
+# family -> {hf leaf name: [(canonical module path inside a block, row part, hf module path inside a block)]}
+_T = lambda canon, part, hf: (canon, part, hf)  # noqa: E731
+LORA_TARGETS: Dict[str, Dict[str, List[Tuple[str, str, str]]]] = {
+    "gpt2": {"c_attn": [_T("attn.qkv", "all", "attn.c_attn")], "c_fc": [_T("mlp.up", "all", "mlp.c_fc")],
+             "c_proj": [_T("attn.out", "all", "attn.c_proj"), _T("mlp.down", "all", "mlp.c_proj")]},
+    "gpt_bigcode": {"c_attn": [_T("attn.qkv", "all", "attn.c_attn")], "c_fc": [_T("mlp.up", "all", "mlp.c_fc")],
+                    "c_proj": [_T("attn.out", "all", "attn.c_proj"), _T("mlp.down", "all", "mlp.c_proj")]},
+    "gpt_neo": {"q_proj": [_T("attn.qkv", "q", "attn.attention.q_proj")], "k_proj": [_T("attn.qkv", "k", "attn.attention.k_proj")],
+                "v_proj": [_T("attn.qkv", "v", "attn.attention.v_proj")], "out_proj": [_T("attn.out", "all", "attn.attention.out_proj")],
+                "c_fc": [_T("mlp.up", "all", "mlp.c_fc")], "c_proj": [_T("mlp.down", "all", "mlp.c_proj")]},
+    "gptj": {"q_proj": [_T("attn.qkv", "q", "attn.q_proj")], "k_proj": [_T("attn.qkv", "k", "attn.k_proj")],
+             "v_proj": [_T("attn.qkv", "v", "attn.v_proj")], "out_proj": [_T("attn.out", "all", "attn.out_proj")],
+             "fc_in": [_T("mlp.up", "all", "mlp.fc_in")], "fc_out": [_T("mlp.down", "all", "mlp.fc_out")]},
+    "gpt_neox": {"query_key_value": [_T("attn.qkv", "all_interleaved", "attention.query_key_value")],
+                 "dense": [_T("attn.out", "all", "attention.dense")],
+                 "dense_h_to_4h": [_T("mlp.up", "all", "mlp.dense_h_to_4h")], "dense_4h_to_h": [_T("mlp.down", "all", "mlp.dense_4h_to_h")]},
+    "bloom": {"query_key_value": [_T("attn.qkv", "all_interleaved", "self_attention.query_key_value")],
+              "dense": [_T("attn.out", "all", "self_attention.dense")],
+              "dense_h_to_4h": [_T("mlp.up", "all", "mlp.dense_h_to_4h")], "dense_4h_to_h": [_T("mlp.down", "all", "mlp.dense_4h_to_h")]},
+    "llama": {"q_proj": [_T("attn.qkv", "q", "self_attn.q_proj")], "k_proj": [_T("attn.qkv", "k", "self_attn.k_proj")],
+              "v_proj": [_T("attn.qkv", "v", "self_attn.v_proj")], "o_proj": [_T("attn.out", "all", "self_attn.o_proj")],
+              "gate_proj": [_T("mlp.up", "gate", "mlp.gate_proj")], "up_proj": [_T("mlp.up", "up", "mlp.up_proj")],
+              "down_proj": [_T("mlp.down", "all", "mlp.down_proj")]},
+    "opt": {"q_proj": [_T("attn.qkv", "q", "self_attn.q_proj")], "k_proj": [_T("attn.qkv", "k", "self_attn.k_proj")],
+            "v_proj": [_T("attn.qkv", "v", "self_attn.v_proj")], "out_proj": [_T("attn.out", "all", "self_attn.out_proj")],
+            "fc1": [_T("mlp.up", "all", "fc1")], "fc2": [_T("mlp.down", "all", "fc2")]},
+}
+DEFAULT_LORA_TARGETS = {"gpt2": ["c_attn"], "gpt_bigcode": ["c_attn"], "gpt_neo": ["q_proj", "v_proj"], "gptj": ["q_proj", "v_proj"],
+                        "gpt_neox": ["query_key_value"], "bloom": ["query_key_value"], "llama": ["q_proj", "v_proj"],
+                        "opt": ["q_proj", "v_proj"], "t5": ["q", "v"]}
+
+
+def row_range(spec: ArchSpec, canon: str, part: str) -> Tuple[int, int]:
+    """Rows of the fused canonical weight that belong to ``part`` of module ``canon``."""
+    if part in ("all", "all_interleaved"):
+        return 0, -1
+    if canon == "attn.qkv":
+        q, kv = spec.q_size, spec.kv_size
+        return {"q": (0, q), "k": (q, q + kv), "v": (q + kv, q + 2 * kv)}[part]
+    if canon == "mlp.up":
+        f = spec.ffn_size
+        return {"gate": (0, f), "up": (f, 2 * f)}[part]
+    raise KeyError((canon, part))

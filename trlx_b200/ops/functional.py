@@ -1,0 +1,204 @@
+"""Autograd-aware wrappers around the sm_100a kernels (CUDA bf16) with PyTorch fallbacks elsewhere."""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from trlx_b200.ops import reference
+
+_PPO_KEYS = [
+    "losses/total_loss", "losses/policy_loss", "losses/value_loss", "values/mean", "values/min", "values/max",
+    "values/std", "values/values_error", "values/values_mape_error", "values/clipfrac", "old_values/mean",
+    "old_values/min", "old_values/max", "old_values/std", "returns/mean", "returns/min", "returns/max", "returns/std",
+    "policy/approx_kl", "policy/clipfrac", "ratio", "padding_percentage",
+]
+
+
+def _ops():
+    from trlx_b200 import ops
+
+    return ops
+
+
+def _kernel_ok(x: torch.Tensor, w: torch.Tensor) -> bool:
+    if not (x.is_cuda and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16):
+        return False
+    if not _ops().available():
+        return False
+    K = x.shape[-1]
+    return K % 8 == 0 and w.stride(-1) == 1 and w.stride(0) % 8 == 0 and w.data_ptr() % 16 == 0
+
+
+def _as_2d(x: torch.Tensor) -> torch.Tensor:
+    x2 = x.reshape(-1, x.shape[-1])
+    if x2.stride(-1) != 1 or x2.stride(0) % 8 != 0 or x2.data_ptr() % 16 != 0:
+        x2 = x2.contiguous()
+    return x2
+
+
+class _Linear(torch.autograd.Function):
+    """y = x @ w.T + b (+ residual) — forward on the tcgen05 GEMM, backward on library GEMMs."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, residual):
+        C = _ops().C
+        x2 = _as_2d(x)
+        r2 = None if residual is None else _as_2d(residual)
+        y = C.gemm(x2, w, b, r2, "none")
+        ctx.save_for_backward(x2, w)
+        ctx.has_bias = b is not None
+        ctx.has_res = residual is not None
+        ctx.x_shape = x.shape
+        return y.view(*x.shape[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, gy):
+        x2, w = ctx.saved_tensors
+        g2 = gy.reshape(-1, gy.shape[-1])
+        gx = gw = gb = gr = None
+        if ctx.needs_input_grad[0]:
+            gx = (g2 @ w).view(ctx.x_shape)
+        if ctx.needs_input_grad[1]:
+            gw = g2.t() @ x2
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = g2.sum(0)
+        if ctx.has_res and ctx.needs_input_grad[3]:
+            gr = gy
+        return gx, gw, gb, gr
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor] = None, act: str = "none",
+           residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``act(x @ w.T + b) + residual``.  Activation is fused into the GEMM epilogue when no gradient is needed;
+    under autograd the pre-activation is kept and the activation runs as a separate op."""
+    if not _kernel_ok(x, w):
+        return reference.linear(x, w, b, act, residual)
+    needs_grad = torch.is_grad_enabled() and (x.requires_grad or w.requires_grad or (b is not None and b.requires_grad)
+                                              or (residual is not None and residual.requires_grad))
+    if not needs_grad:
+        C = _ops().C
+        y = C.gemm(_as_2d(x), w, b, None if residual is None else _as_2d(residual), act or "none")
+        return y.view(*x.shape[:-1], w.shape[0])
+    if act in ("none", "", None):
+        return _Linear.apply(x, w, b, residual)
+    y = reference.activation(_Linear.apply(x, w, b, None), act)
+    return y if residual is None else y + residual
+
+
+class _FusedLogprob(torch.autograd.Function):
+    """log p(label | h) through the LM head without materialising logits in the forward.
+    Backward recomputes the logits tile-free as one bf16 GEMM and overwrites them with d-logits in place."""
+
+    @staticmethod
+    def forward(ctx, h, w, b, labels):
+        C = _ops().C
+        h2 = _as_2d(h)
+        lab = labels.reshape(-1).contiguous()
+        lse, lp, _, _ = C.lmhead(h2, w, b, lab)
+        ctx.save_for_backward(h2, w, b if b is not None else h2.new_empty(0), lab, lse)
+        ctx.has_bias = b is not None
+        ctx.h_shape = h.shape
+        ctx.mark_non_differentiable(lse)
+        return lp.view(labels.shape), lse.view(labels.shape)
+
+    @staticmethod
+    def backward(ctx, g_lp, _g_lse):
+        C = _ops().C
+        h2, w, b, lab, lse = ctx.saved_tensors
+        logits = C.gemm(h2, w, b if ctx.has_bias else None, None, "none")
+        C.logprob_backward_inplace(logits, lab, lse, g_lp.reshape(-1).float().contiguous())
+        gh = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gh = (logits @ w).view(ctx.h_shape)
+        if ctx.needs_input_grad[1]:
+            gw = logits.t() @ h2
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = logits.sum(0)
+        return gh, gw, gb, None
+
+
+def fused_logprob(h, w, b, labels) -> Tuple[torch.Tensor, torch.Tensor]:
+    """``(log p(labels), logsumexp)`` of the LM head applied to ``h``; labels < 0 are ignored (0 output)."""
+    if not _kernel_ok(h, w):
+        return reference.fused_logprob(h, w, b, labels)
+    return _FusedLogprob.apply(h, w, b, labels)
+
+
+class _LogprobsFromLogits(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels):
+        lp, lse = _ops().C.logprob_from_logits(logits, labels)
+        ctx.save_for_backward(logits, labels, lse)
+        return lp
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, labels, lse = ctx.saved_tensors
+        p = torch.exp(logits.float() - lse.unsqueeze(-1))
+        onehot = torch.zeros_like(p).scatter_(-1, labels.clamp_min(0).unsqueeze(-1), 1.0)
+        return ((onehot - p) * g.unsqueeze(-1)).to(logits.dtype), None
+
+
+def logprobs_from_logits(logits: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+    return _LogprobsFromLogits.apply(logits, labels)
+
+
+def gae_and_whiten(values, rewards, width: int, gamma: float, lam: float, use_whitening: bool = True, group=None):
+    """Advantages (optionally whitened) and returns over the first ``width`` response positions.
+
+    Whitening matches the reference: unbiased variance in a single process, biased global variance across ranks
+    (``trlx/utils/modeling.py:200-210``).  On CUDA: one scan kernel + (one small all-reduce) + one whiten kernel."""
+    distributed = dist.is_available() and dist.is_initialized()
+    ops = _ops()
+    if values.is_cuda and ops.available():
+        v = values.float().contiguous()
+        r = rewards.float().contiguous()
+        if not use_whitening:
+            adv, ret, _ = ops.C.gae(v, r, width, gamma, lam, False, True)
+        elif not distributed or dist.get_world_size(group) == 1:
+            adv, ret, _ = ops.C.gae(v, r, width, gamma, lam, True, not distributed)
+        else:
+            adv, ret, stats = ops.C.gae(v, r, width, gamma, lam, False, False)
+            dist.all_reduce(stats, group=group)
+            ops.C.whiten_(adv, width, stats, False)
+        return adv[:, :width].detach(), ret[:, :width]
+    from trlx_b200.utils.modeling import whiten
+
+    adv, ret = reference.gae(values, rewards, width, gamma, lam)
+    if use_whitening:
+        adv = whiten(adv, group=group)
+    return adv.detach(), ret
+
+
+class _PPOLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logprobs, values, old_logprobs, old_values, adv, ret, mask, clip, clip_v, vf_coef):
+        C = _ops().C
+        args = [t.float().contiguous() for t in (logprobs, values, old_logprobs, old_values, adv, ret, mask)]
+        out, dlp, dv = C.ppo_loss(*args, clip, clip_v, vf_coef)
+        ctx.save_for_backward(dlp, dv)
+        ctx.shapes = (logprobs.shape, values.shape, logprobs.dtype, values.dtype)
+        ctx.mark_non_differentiable(out)
+        return out[0].clone(), out
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_out):
+        dlp, dv = ctx.saved_tensors
+        s_lp, s_v, dt_lp, dt_v = ctx.shapes
+        return ((dlp * g_loss).view(s_lp).to(dt_lp), (dv * g_loss).view(s_v).to(dt_v),
+                None, None, None, None, None, None, None, None)
+
+
+def ppo_loss(logprobs, values, old_logprobs, old_values, advantages, returns, mask, cliprange: float,
+             cliprange_value: float, vf_coef: float) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
+    """Fused PPO loss: returns ``(loss, stats)`` where ``stats`` maps the reference's flattened stat keys to 0-dim
+    DEVICE tensors (no host sync here; the trainer converts once per optimizer step)."""
+    ops = _ops()
+    if logprobs.is_cuda and ops.available():
+        loss, out = _PPOLoss.apply(logprobs, values, old_logprobs, old_values, advantages, returns, mask,
+                                   float(cliprange), float(cliprange_value), float(vf_coef))
+        return loss, {k: out[i] for i, k in enumerate(_PPO_KEYS)}
+    return reference.ppo_loss(logprobs, values, old_logprobs, old_values, advantages, returns, mask, cliprange,
+                              cliprange_value, vf_coef)
