@@ -42,7 +42,8 @@ def _merge_dicts(base: Dict, update: Dict) -> Dict:
     out = copy.deepcopy(base)
     for key, val in update.items():
         if isinstance(val, dict):
-            out[key] = _merge_dicts(out.get(key) or {}, val)
+            prev = out.get(key)
+            out[key] = _merge_dicts(prev if isinstance(prev, dict) else {}, val)
         else:
             out[key] = val
     return out

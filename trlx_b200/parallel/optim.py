@@ -1,0 +1,355 @@
+"""Optimizers.
+
+``FusedAdamW`` / ``FusedAdam`` keep every trainable parameter of a rank in ONE flat bf16 buffer (parameters and their
+``.grad`` become views into flat storage), hold fp32 master weights + Adam moments only for the shard the rank owns,
+and update with a single sm_100a kernel.  Under data parallelism the flat gradient / parameter buffers live in
+symmetric memory and the same kernel performs the gradient reduce-scatter (P2P loads from every peer), the AdamW update
+of the owned shard and the parameter all-gather (P2P stores to every peer) — see ``csrc/optim.cu``.  This is
+the B200 replacement for DDP / DeepSpeed ZeRO-1/2 + ``torch.optim.AdamW`` used by the reference
+(``trlx/trainer/accelerate_base_trainer.py:173-193,574-587``, ``configs/accelerate/zero2-bf16.yaml``).
+
+On CPU / fp32 parameters the classes fall back to the equivalent ``torch.optim`` implementation (with an explicit
+gradient all-reduce across ranks), so the trainers behave identically in gloo tests.
+
+``Adam8bit`` / ``AdamW8bit`` keep the moments block-quantised to 8 bits (256-element blocks, absmax scales) — an
+in-repo stand-in for ``bitsandbytes`` (reference: ``trlx/utils/__init__.py:104-123``).
+"""
+from __future__ import annotations
+
+import math
+from typing import Any, Dict, Iterable, List, Optional
+
+import torch
+import torch.distributed as dist
+from torch.optim import Optimizer
+
+from trlx_b200.utils import logging
+
+logger = logging.get_logger(__name__)
+
+_ALIGN = 8  # elements; keeps every shard 16-byte aligned for the vectorised kernels
+
+
+def _round_up(n: int, m: int) -> int:
+    return (n + m - 1) // m * m
+
+
+class _FlatGroup:
+    """Flat storage for one param group."""
+
+    def __init__(self, params: List[torch.nn.Parameter], world: int, rank: int, group, symmetric: bool):
+        self.params = params
+        self.device = params[0].device
+        sizes = [p.numel() for p in params]
+        self.offsets, off = [], 0
+        for n in sizes:
+            self.offsets.append(off)
+            off += _round_up(n, _ALIGN)
+        self.numel = _round_up(off, _ALIGN * max(world, 1))
+        self.world, self.rank, self.group = world, rank, group
+        self.shard = self.numel // max(world, 1)
+        self.lo = self.shard * rank
+        self.symm_param = self.symm_grad = None
+        if symmetric:
+            import torch.distributed._symmetric_memory as symm
+
+            self.flat_param = symm.empty(self.numel, dtype=torch.bfloat16, device=self.device)
+            self.flat_grad = symm.empty(self.numel, dtype=torch.bfloat16, device=self.device)
+            self.flat_param.zero_()
+            self.flat_grad.zero_()
+            name = group.group_name if group is not None else dist.group.WORLD.group_name
+            self.symm_param = symm.rendezvous(self.flat_param, name)
+            self.symm_grad = symm.rendezvous(self.flat_grad, name)
+        else:
+            self.flat_param = torch.zeros(self.numel, dtype=torch.bfloat16, device=self.device)
+            self.flat_grad = torch.zeros(self.numel, dtype=torch.bfloat16, device=self.device)
+        for p, o in zip(params, self.offsets):
+            n = p.numel()
+            self.flat_param[o:o + n].copy_(p.data.reshape(-1))
+            p.data = self.flat_param[o:o + n].view(p.shape)
+            p.grad = self.flat_grad[o:o + n].view(p.shape)
+        sl = slice(self.lo, self.lo + self.shard)
+        self.master = self.flat_param[sl].float()
+        self.exp_avg = torch.zeros(self.shard, dtype=torch.float32, device=self.device)
+        self.exp_avg_sq = torch.zeros(self.shard, dtype=torch.float32, device=self.device)
+        self.gshard: Optional[torch.Tensor] = None
+        self.hyper = torch.ones(4, dtype=torch.float32, device=self.device)
+        self.hyper_host = torch.ones(4, dtype=torch.float32).pin_memory() if self.device.type == "cuda" else torch.ones(4)
+        self.sq = torch.zeros(1, dtype=torch.float64, device=self.device)
+        self.epoch = 0
+
+    def rebind_grads(self):
+        """(Re)attach ``.grad`` views — needed after anything set them to ``None``."""
+        for p, o in zip(self.params, self.offsets):
+            if p.grad is None or p.grad.data_ptr() != self.flat_grad.data_ptr() + o * 2:
+                p.grad = self.flat_grad[o:o + p.numel()].view(p.shape)
+
+
+class FusedAdamW(Optimizer):
+    """AdamW (``decoupled=True``) with flat bf16 storage + fp32 master shard and a fused (optionally cross-GPU) update."""
+
+    decoupled = True
+
+    def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2,
+                 grad_clip: Optional[float] = None, process_group=None, **unused):
+        defaults = dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay)
+        super().__init__(params, defaults)
+        self.grad_clip = grad_clip
+        self.process_group = process_group
+        self._step_count_fused = 0
+        self._flat: Optional[List[Optional[_FlatGroup]]] = None
+        self._fallback: Optional[Optimizer] = None
+        self.last_grad_norm: Optional[torch.Tensor] = None
+
+    # -- setup ------------------------------------------------------------------------------------------------------------
+    def _world(self):
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_world_size(self.process_group), dist.get_rank(self.process_group)
+        return 1, 0
+
+    def _use_kernels(self) -> bool:
+        from trlx_b200 import ops
+
+        ps = [p for g in self.param_groups for p in g["params"] if p.requires_grad]
+        return bool(ps) and all(p.is_cuda and p.dtype == torch.bfloat16 for p in ps) and ops.available()
+
+    def _lazy_init(self):
+        if self._flat is not None or self._fallback is not None:
+            return
+        world, rank = self._world()
+        if not self._use_kernels():
+            cls = torch.optim.AdamW if self.decoupled else torch.optim.Adam
+            groups = [{**{k: v for k, v in g.items() if k != "params"}, "params": [p for p in g["params"] if p.requires_grad]}
+                      for g in self.param_groups]
+            groups = [g for g in groups if g["params"]]
+            known = ("lr", "betas", "eps", "weight_decay", "params")
+            self._fallback = cls([{k: v for k, v in g.items() if k in known} for g in groups])
+            return
+        self._flat = []
+        for g in self.param_groups:
+            ps = [p for p in g["params"] if p.requires_grad]
+            if not ps:
+                self._flat.append(None)
+                continue
+            symmetric = world > 1
+            try:
+                self._flat.append(_FlatGroup(ps, world, rank, self.process_group, symmetric))
+            except Exception as err:  # symmetric memory unavailable → replicated update after an NCCL all-reduce
+                if not symmetric:
+                    raise
+                logger.warning(f"symmetric memory unavailable ({err}); falling back to all-reduce + replicated update")
+                self._flat.append(_FlatGroup(ps, 1, 0, None, False))
+                self._flat[-1].needs_allreduce = True
+
+    def prepare(self):
+        """Flatten storage now (call once after the model is on its device, before the first backward)."""
+        self._lazy_init()
+        return self
+
+    # -- step -------------------------------------------------------------------------------------------------------------
+    def zero_grad(self, set_to_none: bool = False):
+        self._lazy_init()
+        if self._fallback is not None:
+            return self._fallback.zero_grad(set_to_none=True)
+        for fg in self._flat:
+            if fg is not None:
+                fg.flat_grad.zero_()
+                fg.rebind_grads()
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        self._lazy_init()
+        loss = closure() if closure is not None else None
+        world, rank = self._world()
+        if self._fallback is not None:
+            for g_self, g_fb in zip([g for g in self.param_groups if any(p.requires_grad for p in g["params"])],
+                                    self._fallback.param_groups):
+                g_fb["lr"] = g_self["lr"]
+            params = [p for g in self._fallback.param_groups for p in g["params"] if p.grad is not None]
+            if world > 1 and params:
+                flat = torch.cat([p.grad.reshape(-1).float() for p in params])
+                dist.all_reduce(flat, group=self.process_group)
+                flat /= world
+                off = 0
+                for p in params:
+                    p.grad.copy_(flat[off:off + p.numel()].view_as(p.grad))
+                    off += p.numel()
+            if self.grad_clip:
+                self.last_grad_norm = torch.nn.utils.clip_grad_norm_(params, self.grad_clip)
+            self._fallback.step()
+            return loss
+
+        from trlx_b200 import ops
+
+        C = ops.C
+        self._step_count_fused += 1
+        t = self._step_count_fused
+        for g, fg in zip(self.param_groups, self._flat):
+            if fg is None:
+                continue
+            b1, b2 = g["betas"]
+            fg.hyper_host[0] = float(g["lr"])
+            fg.hyper_host[1] = 1.0 - b1 ** t
+            fg.hyper_host[2] = 1.0 - b2 ** t
+            fg.hyper_host[3] = 1.0
+            fg.hyper.copy_(fg.hyper_host, non_blocking=True)
+            args = (b1, b2, g["eps"], g["weight_decay"], self.decoupled)
+            if fg.world == 1:
+                if getattr(fg, "needs_allreduce", False) and world > 1:
+                    dist.all_reduce(fg.flat_grad, group=self.process_group)
+                    fg.flat_grad.div_(world)
+                if self.grad_clip:
+                    fg.sq.zero_()
+                    C.sqnorm_(fg.flat_grad, fg.sq)
+                    norm = torch.empty(1, dtype=torch.float32, device=fg.device)
+                    C.clip_coef_(fg.sq, float(self.grad_clip), fg.hyper, norm)
+                    self.last_grad_norm = norm
+                C.adamw_flat(fg.flat_param, fg.master, fg.flat_grad, fg.exp_avg, fg.exp_avg_sq, *args, fg.hyper)
+                continue
+            # ---- data-parallel: fused reduce-scatter + AdamW + all-gather over NVLink peer memory
+            pads = list(fg.symm_grad.signal_pad_ptrs)
+            grads, params = list(fg.symm_grad.buffer_ptrs), list(fg.symm_param.buffer_ptrs)
+            fg.epoch += 1
+            C.signal_barrier(pads, fg.rank, fg.epoch)  # every rank finished accumulating gradients
+            if self.grad_clip:
+                if fg.gshard is None:
+                    fg.gshard = torch.empty(fg.shard, dtype=torch.float32, device=fg.device)
+                fg.sq.zero_()
+                C.rs_adamw_ag(grads, params, fg.lo, fg.shard, fg.master, fg.exp_avg, fg.exp_avg_sq, fg.gshard, 1, *args,
+                              fg.hyper, fg.sq)
+                dist.all_reduce(fg.sq, group=self.process_group)
+                norm = torch.empty(1, dtype=torch.float32, device=fg.device)
+                C.clip_coef_(fg.sq, float(self.grad_clip), fg.hyper, norm)
+                self.last_grad_norm = norm
+                C.rs_adamw_ag(grads, params, fg.lo, fg.shard, fg.master, fg.exp_avg, fg.exp_avg_sq, fg.gshard, 2, *args,
+                              fg.hyper, None)
+            else:
+                C.rs_adamw_ag(grads, params, fg.lo, fg.shard, fg.master, fg.exp_avg, fg.exp_avg_sq, None, 0, *args,
+                              fg.hyper, None)
+            fg.epoch += 1
+            C.signal_barrier(pads, fg.rank, fg.epoch)  # every rank's new parameters are visible everywhere
+        return loss
+
+    # -- checkpointing ------------------------------------------------------------------------------------------------------
+    def state_dict(self) -> Dict[str, Any]:
+        self._lazy_init()
+        if self._fallback is not None:
+            return {"kind": "torch", "state": self._fallback.state_dict(), "step": self._step_count_fused}
+        shards = []
+        for fg in self._flat:
+            shards.append(None if fg is None else dict(master=fg.master.cpu(), exp_avg=fg.exp_avg.cpu(),
+                                                       exp_avg_sq=fg.exp_avg_sq.cpu(), lo=fg.lo, shard=fg.shard))
+        return {"kind": "flat", "step": self._step_count_fused, "shards": shards,
+                "lrs": [g["lr"] for g in self.param_groups]}
+
+    def load_state_dict(self, sd: Dict[str, Any]) -> None:
+        self._lazy_init()
+        self._step_count_fused = sd.get("step", 0)
+        if sd["kind"] == "torch":
+            if self._fallback is not None:
+                self._fallback.load_state_dict(sd["state"])
+            return
+        if self._flat is None:
+            return
+        for fg, sh in zip(self._flat, sd["shards"]):
+            if fg is None or sh is None:
+                continue
+            if sh["lo"] != fg.lo or sh["shard"] != fg.shard:
+                raise ValueError("optimizer shard layout changed (different world size?)")
+            fg.master.copy_(sh["master"])
+            fg.exp_avg.copy_(sh["exp_avg"])
+            fg.exp_avg_sq.copy_(sh["exp_avg_sq"])
+        for g, lr in zip(self.param_groups, sd.get("lrs", [])):
+            g["lr"] = lr
+
+
+class FusedAdam(FusedAdamW):
+    """Adam with L2 regularisation folded into the gradient (``torch.optim.Adam`` semantics)."""
+
+    decoupled = False
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, **kw):
+        super().__init__(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, **kw)
+
+
+# ---- 8-bit state optimizers ---------------------------------------------------------------------------------------------
+_BLOCK = 256
+
+
+def _quantize(x: torch.Tensor, signed: bool):
+    n = x.numel()
+    pad = (-n) % _BLOCK
+    xf = torch.nn.functional.pad(x.reshape(-1).float(), (0, pad)).view(-1, _BLOCK)
+    scale = xf.abs().amax(dim=1, keepdim=True).clamp_min(1e-12)
+    if signed:
+        q = torch.round(xf / scale * 127).clamp_(-127, 127).to(torch.int8)
+    else:
+        q = torch.round(torch.sqrt(xf / scale) * 255).clamp_(0, 255).to(torch.uint8)  # sqrt companding for v ≥ 0
+    return q, scale.squeeze(1)
+
+
+def _dequantize(q: torch.Tensor, scale: torch.Tensor, n: int, signed: bool, shape):
+    if signed:
+        x = q.float() / 127 * scale[:, None]
+    else:
+        x = (q.float() / 255) ** 2 * scale[:, None]
+    return x.reshape(-1)[:n].view(shape)
+
+
+class AdamW8bit(Optimizer):
+    """AdamW whose moments are stored block-wise in 8 bits (math in fp32 per step)."""
+
+    decoupled = True
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, min_8bit_size: int = 4096, **unused):
+        super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay))
+        self.min_8bit_size = min_8bit_size
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        for g in self.param_groups:
+            b1, b2 = g["betas"]
+            for p in g["params"]:
+                if p.grad is None:
+                    continue
+                st = self.state[p]
+                grad = p.grad.float()
+                if not st:
+                    st["step"] = 0
+                    st["q8"] = p.numel() >= self.min_8bit_size and not getattr(p, "_optim_32bit", False)
+                    z = torch.zeros_like(p, dtype=torch.float32)
+                    if st["q8"]:
+                        st["m"], st["ms"] = _quantize(z, True)
+                        st["v"], st["vs"] = _quantize(z, False)
+                    else:
+                        st["m"], st["v"] = z, z.clone()
+                st["step"] += 1
+                if st["q8"]:
+                    m = _dequantize(st["m"], st["ms"], p.numel(), True, p.shape)
+                    v = _dequantize(st["v"], st["vs"], p.numel(), False, p.shape)
+                else:
+                    m, v = st["m"], st["v"]
+                w = p.data.float()
+                if not self.decoupled and g["weight_decay"]:
+                    grad = grad + g["weight_decay"] * w
+                m = m.mul(b1).add_(grad, alpha=1 - b1)
+                v = v.mul(b2).addcmul_(grad, grad, value=1 - b2)
+                bc1, bc2 = 1 - b1 ** st["step"], 1 - b2 ** st["step"]
+                if self.decoupled and g["weight_decay"]:
+                    w.mul_(1 - g["lr"] * g["weight_decay"])
+                w.addcdiv_(m / bc1, (v / bc2).sqrt_().add_(g["eps"]), value=-g["lr"])
+                p.data.copy_(w)
+                if st["q8"]:
+                    st["m"], st["ms"] = _quantize(m, True)
+                    st["v"], st["vs"] = _quantize(v, False)
+                else:
+                    st["m"], st["v"] = m, v
+        return loss
+
+
+class Adam8bit(AdamW8bit):
+    decoupled = False
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, **kw):
+        super().__init__(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, **kw)

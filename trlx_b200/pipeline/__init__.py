@@ -113,8 +113,8 @@ class MiniBatchIterator:
         out = []
         for i in range(self.num_mb):
             lo, hi = i * self.mb_size, (i + 1) * self.mb_size
-            piece = {k: v[lo:hi] for k, v in cols.items()}
-            n_rows = min((len(v) for v in piece.values()), default=0)
+            piece = {k: (v[lo:hi] if v is not None else None) for k, v in cols.items()}
+            n_rows = min((len(v) for v in piece.values() if v is not None), default=0)
             if n_rows == 0:
                 if self.num_mb > 1:
                     logger.warning(

@@ -59,9 +59,17 @@ class RolloutBlock:
     response_lens: torch.Tensor
     host_response_lens: Optional[List[int]] = None
     host_query_lens: Optional[List[int]] = None
+    trunk_hidden: Optional[torch.Tensor] = None  # [N, Q+R, H] frozen-trunk activation at the branch point (optional)
 
     def __len__(self) -> int:
         return int(self.queries.shape[0])
+
+
+@dataclass
+class PPORLBatchCached(PPORLBatch):
+    """:class:`PPORLBatch` + the cached frozen-trunk activation ``[B, Q+R, H]`` aligned with ``cat(query, response)``."""
+
+    trunk_hidden: Optional[torch.Tensor] = None
 
 
 class DeviceBatchLoader:
@@ -93,6 +101,24 @@ class DeviceBatchLoader:
         self.logprobs = torch.cat([widen(b.logprobs, R, 0.0) for b in blocks])
         self.values = torch.cat([widen(b.values, R, 0.0) for b in blocks])
         self.rewards = torch.cat([widen(b.rewards, R, 0.0) for b in blocks])
+        self.trunk = None
+        if all(b.trunk_hidden is not None for b in blocks):
+            parts = []
+            for b in blocks:
+                t = b.trunk_hidden
+                qb, rb = b.queries.shape[1], b.responses.shape[1]
+                t = t[:, : qb + rb]
+                if t.shape[1] < qb + rb:  # engines cache T-1 positions (the last token is never an input)
+                    t = torch.cat([t, t.new_zeros(t.shape[0], qb + rb - t.shape[1], t.shape[2])], 1)
+                tq, tr = t[:, :qb], t[:, qb:]
+                if qb < Q:
+                    zq = t.new_zeros(t.shape[0], Q - qb, t.shape[2])
+                    tq = torch.cat([zq, tq] if left else [tq, zq], 1)
+                if rb < R:
+                    tr = torch.cat([tr, t.new_zeros(t.shape[0], R - rb, t.shape[2])], 1)
+                parts.append(torch.cat([tq, tr], 1))
+            self.trunk = torch.cat(parts)
+        self.Q, self.R = Q, R
         self.response_lens = torch.cat([b.response_lens for b in blocks])
         self.query_lens = torch.cat([b.query_lens for b in blocks])
         self.host_rlens = sum((b.host_response_lens or b.response_lens.tolist() for b in blocks), [])
@@ -109,13 +135,20 @@ class DeviceBatchLoader:
             idx = idx_host.to(self.device, non_blocking=True)
             q, r = self.queries.index_select(0, idx), self.responses.index_select(0, idx)
             lp, v, rw = (t.index_select(0, idx) for t in (self.logprobs, self.values, self.rewards))
+            th = self.trunk.index_select(0, idx) if self.trunk is not None else None
+            qmax, rmax = self.Q, self.R
             if not self.static_shapes:
                 ids = idx_host.tolist()
                 rmax = max(max(self.host_rlens[i] for i in ids), 1)
                 qmax = max(max(self.host_qlens[i] for i in ids), 1)
                 q = q[:, q.shape[1] - qmax:] if self.left else q[:, :qmax]
                 r, lp, v, rw = r[:, :rmax], lp[:, :rmax], v[:, :rmax], rw[:, :rmax]
-            yield PPORLBatch(q, r, lp, v, rw)
+                if th is not None:
+                    th = th[:, self.Q - qmax: self.Q + rmax] if self.left else torch.cat([th[:, :qmax], th[:, self.Q: self.Q + rmax]], 1)
+            if th is not None:
+                yield PPORLBatchCached(q, r, lp, v, rw, trunk_hidden=th)
+            else:
+                yield PPORLBatch(q, r, lp, v, rw)
 
 
 class PPORolloutStorage(BaseRolloutStore):

@@ -1,0 +1,495 @@
+"""Shared training loop for PPO / ILQL / SFT / RFT.
+
+Public surface follows ``trlx/trainer/accelerate_base_trainer.py`` (class name kept as ``AccelerateRLTrainer`` so
+configs naming ``Accelerate*Trainer`` keep working): ctor bookkeeping ``:46-146``, ``setup_model/optimizer/scheduler``
+``:148-201``, ``decode`` ``:203-254``, ``generate``/``generate_eval`` ``:256-282``, ``save_pretrained`` ``:284-307``,
+``save``/``load`` ``:309-333``, ``evaluate`` ``:339-500``, ``_accumulate`` ``:502-516``, ``learn`` ``:518-652``.
+
+What is different underneath: there is no Accelerate/DeepSpeed.  :class:`trlx_b200.parallel.runtime.Runtime` owns the
+process groups and trackers; the optimizer is the flat, partitioned :class:`~trlx_b200.parallel.optim.FusedAdamW`
+whose ``step()`` *is* the gradient synchronisation (fused reduce-scatter + update + all-gather), so gradient
+accumulation needs no ``no_sync`` dance; statistics stay on the device and are fetched with ONE transfer per
+optimizer step; phase timings are device-timed.
+"""
+from __future__ import annotations
+
+import contextlib
+import json
+import os
+import sys
+from abc import abstractmethod
+from contextlib import contextmanager
+from time import time
+from typing import Any, Dict, List, Optional, Tuple
+
+import torch
+
+from trlx_b200.data.configs import TRLConfig
+from trlx_b200.parallel.runtime import Runtime
+from trlx_b200.pipeline import MiniBatchIterator
+from trlx_b200.trainer import BaseRLTrainer, register_trainer
+from trlx_b200.utils import (filter_non_scalars, get_distributed_config, get_git_tag, get_optimizer_class,
+                             get_scheduler_class, logging, significant)
+from trlx_b200.utils.modeling import (flatten_dict, freeze_bottom_causal_layers, freeze_bottom_seq2seq_layers,
+                                      gather_dict)
+from trlx_b200.utils.tokenizer import load_tokenizer
+
+logger = logging.get_logger(__name__)
+
+
+def _materialise(stats: Dict[str, Any]) -> Dict[str, Any]:
+    """Turn 0-dim device tensors into python floats with a single device→host transfer."""
+    keys = [k for k, v in stats.items() if isinstance(v, torch.Tensor) and v.numel() == 1]
+    if keys:
+        dev = [stats[k].detach().float().reshape(()) for k in keys]
+        vals = torch.stack(dev).tolist() if dev[0].is_cuda else [float(v) for v in dev]
+        stats = dict(stats)
+        stats.update(zip(keys, vals))
+    return stats
+
+
+@register_trainer
+class AccelerateRLTrainer(BaseRLTrainer):
+    """Abstract trainer on the B200 runtime."""
+
+    def __init__(self, config: TRLConfig, **kwargs):
+        super().__init__(config, **kwargs)
+        self.max_length = config.train.seq_length
+        if config.train.minibatch_size:
+            assert config.train.batch_size % config.train.minibatch_size == 0, "Minibatch size must divide batch size"
+            self.mb_size = config.train.minibatch_size
+        else:
+            self.mb_size = config.train.batch_size
+        self.num_mb = config.train.batch_size // self.mb_size
+        self.mb_count = 0
+        self.gradient_accumulation_steps = 1
+
+        self.runtime = Runtime(config.train.parallel)
+        self.accelerator = self.runtime  # attribute name kept for user code written against the reference
+        self.runtime.barrier()
+
+        self.tokenizer = load_tokenizer(config.tokenizer.tokenizer_path, **config.tokenizer.tokenizer_extra_configs)
+        self.tokenizer.padding_side = config.tokenizer.padding_side
+        self.tokenizer.truncation_side = config.tokenizer.truncation_side
+        self.tokenizer.sep_token = "<sep>"
+        if self.tokenizer.pad_token is None:
+            self.tokenizer.pad_token = "<|padding|>"
+
+        self.model = self.setup_model()
+        self.opt = self.setup_optimizer()
+        self.scheduler = self.setup_scheduler()
+
+        script_name = os.path.basename(sys.argv[0]).rsplit(".", 1)[0]
+        mp = config.model.model_path
+        model_name = mp.split("/")[-1] if isinstance(mp, str) else (mp.get("model_type", "model") if isinstance(mp, dict)
+                                                                     else type(mp).__name__)
+        num_gpus = "1gpu" if self.runtime.num_processes == 1 else f"{self.runtime.num_processes}gpus"
+        run_name = config.train.run_name or "/".join([script_name, model_name, num_gpus]) + f":{get_git_tag()[0]}"
+        self.run_name = run_name
+        if self.runtime.is_main_process:
+            cfg_dict = self.config.to_dict()
+            cfg_dict["distributed"] = get_distributed_config(self.runtime)
+            if cfg_dict["model"].get("peft_config") is not None:
+                pc = cfg_dict["model"]["peft_config"]
+                cfg_dict["model"]["peft_config"] = pc if isinstance(pc, dict) else str(pc)
+            if not isinstance(cfg_dict["model"]["model_path"], str):
+                cfg_dict["model"]["model_path"] = str(cfg_dict["model"]["model_path"])
+            init_kwargs = {}
+            if config.train.tracker == "wandb":
+                init_kwargs = dict(entity=config.train.entity_name, group=config.train.group_name,
+                                   tags=(config.train.tags or []) + ["/".join(get_git_tag())],
+                                   mode="disabled" if os.environ.get("debug", False) else "online")
+            self.runtime.init_tracker(config.train.tracker, config.train.project_name, flatten_dict(cfg_dict), run_name,
+                                      logging_dir=config.train.logging_dir, **init_kwargs)
+
+        self.nth_evaluation = 0
+        self.iter_count = 0
+        self.generate_sweep_kwarg = None
+        self.generate_kwargs = dict(getattr(self, "generate_kwargs", None) or config.method.gen_kwargs)
+        for k, v in config.method.gen_kwargs.items():
+            if isinstance(v, list):
+                if self.generate_sweep_kwarg is not None:
+                    logger.info(f"Only a single sweep is allowed, {k} is going to be set to {v[0]}")
+                    self.generate_kwargs[k] = v[0]
+                else:
+                    self.generate_sweep_kwarg = (k, v)
+
+    # ---- setup --------------------------------------------------------------------------------------------------------
+    def setup_model(self):
+        logger.info(f"Initializing model: {self.config.model.model_path}")
+        model = self.get_arch(self.config)
+        if self.config.model.peft_config is None:
+            if self.config.model.model_arch_type == "seq2seq":
+                freeze_bottom_seq2seq_layers(model.base_model, self.config.model.num_layers_unfrozen)
+            else:
+                freeze_bottom_causal_layers(model.base_model, self.config.model.num_layers_unfrozen)
+        elif self.config.model.num_layers_unfrozen >= 0:
+            logger.warning("The argument num_layers_unfrozen is ignored when using peft, to prevent unexpected behaviour."
+                           "For Lora, use the `LoraConfig` argument `modules_to_save` instead.")
+        model = model.to(self.runtime.device)
+        if self.runtime.cuda and self.runtime.dtype != torch.float32:
+            model = model.to(self.runtime.dtype)
+        model.eval()
+        return model
+
+    def setup_optimizer(self):
+        optimizer_class = get_optimizer_class(self.config.optimizer.name)
+        kwargs = dict(self.config.optimizer.kwargs)
+        from trlx_b200.parallel.optim import FusedAdamW
+
+        if issubclass(optimizer_class, FusedAdamW):
+            kwargs.setdefault("grad_clip", self.config.train.parallel.grad_clip)
+            kwargs.setdefault("process_group", self.runtime.dp_group)
+        params = [p for p in self.model.parameters() if p.requires_grad]
+        opt = optimizer_class(params, **kwargs)
+        if hasattr(opt, "prepare"):
+            opt.prepare()
+        if "8bit" in optimizer_class.__name__:
+            for module in self.model.modules():  # keep embedding state in 32 bits (reference: :183-191)
+                if isinstance(module, torch.nn.Embedding):
+                    module.weight._optim_32bit = True
+        return opt
+
+    def setup_scheduler(self):
+        scheduler_class = get_scheduler_class(self.config.scheduler.name)
+        return scheduler_class(self.opt, **self.config.scheduler.kwargs)
+
+    # ---- text <-> tokens ------------------------------------------------------------------------------------------------
+    def decode(self, prompts, samples, prompt_sizes=None, append_eos_token: bool = False) -> Tuple[List[str], List[str], List[str]]:
+        """Token tensors → ``(samples, prompts, outputs)`` strings; trims at ``stop_sequences`` and restores a
+        trailing EOS when the generation ended by itself (or was trimmed)."""
+        if prompt_sizes is None:
+            prompt_sizes = [prompts.shape[1]] * len(prompts)  # left-padded prompts
+        seq2seq = self.config.model.model_arch_type == "seq2seq"
+        tok = self.tokenizer
+        str_samples, str_prompts, str_outputs = [], [], []
+        for prompt, sample, prompt_size in zip(prompts, samples, prompt_sizes):
+            prompt_size = int(prompt_size)
+            start = 0 if seq2seq else prompt_size
+            str_prompt = tok.decode(prompt[:prompt_size], skip_special_tokens=True)
+            str_output = tok.decode(sample[start:], skip_special_tokens=True)
+            trimmed = False
+            for stop in self.stop_sequences or []:
+                ix = str_output.find(stop)
+                if ix >= 0:
+                    str_output = str_output[:ix].rstrip()
+                    trimmed = True
+            last = int(sample[-1]) if len(sample) else None
+            if append_eos_token and (trimmed or last == tok.eos_token_id or last == tok.pad_token_id):
+                str_output += tok.eos_token
+            str_prompts.append(str_prompt)
+            str_outputs.append(str_output)
+            str_samples.append(str_prompt + (tok.sep_token if seq2seq else "") + str_output)
+        return str_samples, str_prompts, str_outputs
+
+    def generate(self, input_ids, attention_mask=None, **kwargs):
+        """Sample with the experience-generation kwargs (falls back to ``gen_kwargs``)."""
+        base = getattr(self, "generate_experience_kwargs", None) or self.generate_kwargs
+        return self._generate(input_ids, attention_mask, dict(base, **kwargs))
+
+    def generate_eval(self, input_ids, attention_mask=None, **kwargs):
+        """Sample with the evaluation ``gen_kwargs``."""
+        return self._generate(input_ids, attention_mask, dict(self.generate_kwargs, **kwargs))
+
+    def _generate(self, input_ids, attention_mask, kwargs):
+        input_ids = input_ids.to(self.runtime.device)
+        if attention_mask is not None:
+            attention_mask = attention_mask.to(self.runtime.device)
+        with torch.no_grad():
+            return self.model.generate(input_ids=input_ids, attention_mask=attention_mask, **kwargs)
+
+    # ---- persistence ------------------------------------------------------------------------------------------------------
+    def save_pretrained(self, directory: Optional[str] = None, **kwargs):
+        """HF-layout export (``config.json`` + weights + tokenizer) of the wrapped model."""
+        if directory is None:
+            directory = os.path.join(self.config.train.checkpoint_dir, "hf_model")
+        self.runtime.barrier()
+        if self.runtime.is_main_process:
+            self.model.save_pretrained(directory, **kwargs)
+            try:
+                self.tokenizer.save_pretrained(directory)
+            except Exception as err:  # pragma: no cover
+                logger.warning(f"could not save tokenizer: {err}")
+        self.runtime.barrier()
+
+    def _extra_state(self) -> Dict[str, Any]:
+        return {}
+
+    def _load_extra_state(self, state: Dict[str, Any]) -> None:
+        pass
+
+    def save(self, directory: Optional[str] = None, **kwargs):
+        """Full training state: raw model tensors, optimizer shard of every rank, scheduler, RNG, counters."""
+        directory = directory or self.config.train.checkpoint_dir
+        os.makedirs(directory, exist_ok=True)
+        rank = self.runtime.rank
+        if self.runtime.is_main_process:
+            torch.save({k: v.detach().cpu() for k, v in self.model.raw_state_dict().items()},
+                       os.path.join(directory, "model_state.pt"))
+            with open(os.path.join(directory, "state.json"), "w") as fh:
+                json.dump({"iter_count": self.iter_count, "nth_evaluation": self.nth_evaluation,
+                           "world_size": self.runtime.world_size}, fh)
+        torch.save({"optimizer": self.opt.state_dict(), "scheduler": self.scheduler.state_dict(),
+                    "rng": {"torch": torch.get_rng_state(),
+                            "cuda": torch.cuda.get_rng_state() if self.runtime.cuda else None},
+                    "extra": self._extra_state()},
+                   os.path.join(directory, f"trainer_state_rank{rank}.pt"))
+        if self.model.peft_type and self.runtime.is_main_process:
+            self.model.save_pretrained(directory)
+        self.runtime.barrier()
+
+    def load(self, directory: Optional[str] = None, **kwargs):
+        """Restore what :meth:`save` wrote (or, for a plain ``hf_model`` export, just the weights)."""
+        directory = directory or self.config.train.checkpoint_dir
+        path = os.path.join(directory, "model_state.pt")
+        if os.path.exists(path):
+            sd = torch.load(path, map_location="cpu", weights_only=True)
+            own = self.model.raw_state_dict()
+            with torch.no_grad():
+                for k, v in sd.items():
+                    if k in own:
+                        own[k].copy_(v.to(own[k].dtype))
+        st_path = os.path.join(directory, f"trainer_state_rank{self.runtime.rank}.pt")
+        if os.path.exists(st_path):
+            st = torch.load(st_path, map_location="cpu", weights_only=False)
+            self.opt.load_state_dict(st["optimizer"])
+            self.scheduler.load_state_dict(st["scheduler"])
+            torch.set_rng_state(st["rng"]["torch"])
+            if self.runtime.cuda and st["rng"]["cuda"] is not None:
+                torch.cuda.set_rng_state(st["rng"]["cuda"])
+            self._load_extra_state(st.get("extra", {}))
+        js = os.path.join(directory, "state.json")
+        if os.path.exists(js):
+            with open(js) as fh:
+                state = json.load(fh)
+            self.iter_count = state.get("iter_count", 0)
+            self.nth_evaluation = state.get("nth_evaluation", 0)
+        self._after_weights_changed()
+        self.runtime.barrier()
+
+    def _after_weights_changed(self):
+        """Hook: engines holding derived weight copies refresh here."""
+
+    # ---- evaluation -------------------------------------------------------------------------------------------------------
+    def add_eval_pipeline(self, eval_pipeline):
+        self.eval_pipeline = eval_pipeline
+
+    def evaluate(self):  # noqa: C901
+        """Generate on ``eval_pipeline``, score with ``reward_fn`` / ``metric_fn`` (main process), tabulate."""
+        logger.info("Evaluating model")
+        sweep_arg, sweep_values = self.generate_sweep_kwarg if self.generate_sweep_kwarg is not None else (None, [None])
+        stats: Dict[str, Any] = {}
+        table: List[List[tuple]] = []
+        columns: List[str] = []
+        seq2seq = self.config.model.model_arch_type == "seq2seq"
+        pad_id = self.tokenizer.pad_token_id
+        total = len(self.eval_dataloader) * len(sweep_values)
+        tbar = logging.tqdm(total=total, desc="[eval]", disable=not self.runtime.is_main_process, position=0, leave=True)
+
+        for i_sweep, sweep_value in enumerate(sweep_values):
+            suffix = f"@{sweep_arg}={sweep_value}" if sweep_value is not None else ""
+            all_samples, all_prompts, all_sizes, all_meta = [], [], [], []
+            t0 = time()
+            world, rank = self.runtime.world_size, self.runtime.rank
+            for i_prompt, prompts in enumerate(self.eval_dataloader):
+                tbar.set_description(f"[generation sweep {i_sweep + 1}/{len(sweep_values)} | eval batch {i_prompt + 1}/{len(self.eval_dataloader)}]")
+                tbar.update()
+                if i_prompt % world != rank:  # eval batches are dealt round-robin to the ranks
+                    continue
+                metadata = {k: v for k, v in prompts.items() if k not in ("input_ids", "attention_mask")}
+                extra = {sweep_arg: sweep_value} if self.generate_sweep_kwarg else {}
+                samples = self.generate_eval(prompts["input_ids"], prompts["attention_mask"], **extra)
+                if seq2seq:
+                    samples = samples[:, 1:].contiguous()
+                all_samples.extend(samples.tolist())
+                all_prompts.extend(prompts["input_ids"].tolist())
+                all_sizes.extend([prompts["input_ids"].shape[1]] * len(prompts["input_ids"]))
+                all_meta.append(metadata)
+            if self.runtime.distributed:  # one pickled gather per sweep value instead of collectives per batch
+                shards = self.runtime.gather_objects((all_samples, all_prompts, all_sizes, all_meta))
+                all_samples = sum((sh[0] for sh in shards), [])
+                all_prompts = sum((sh[1] for sh in shards), [])
+                all_sizes = sum((sh[2] for sh in shards), [])
+                all_meta = sum((sh[3] for sh in shards), [])
+            stats["time/generate"] = time() - t0
+
+            if self.runtime.is_main_process:
+                str_samples, str_prompts, str_outputs = self.decode(all_prompts, all_samples, all_sizes)
+                columns = ["prompt", "output"]
+                columns_data = [str_prompts, str_outputs]
+                metadata = {}
+                for m in all_meta:
+                    for k, v in m.items():
+                        metadata.setdefault(k, []).extend(v)
+                if self.reward_fn:
+                    logger.info("Computing rewards")
+                    rewards = self.reward_fn(samples=str_samples, prompts=str_prompts, outputs=str_outputs,
+                                             tokenizer=self.tokenizer, **metadata)
+                    if len(rewards) and isinstance(rewards[0], torch.Tensor):
+                        rewards = torch.tensor([float(r.sum()) for r in rewards], dtype=torch.float64)
+                    elif len(rewards) and isinstance(rewards[0], list):
+                        rewards = torch.tensor([sum(r) for r in rewards], dtype=torch.float64)
+                    else:
+                        rewards = torch.as_tensor(rewards, dtype=torch.float64)
+                    stats[f"reward/mean{suffix}"] = rewards.mean().item()
+                    columns.append("reward")
+                    columns_data.append(rewards.tolist())
+                if self.metric_fn:
+                    logger.info("Computing metrics")
+                    t1 = time()
+                    metrics = self.metric_fn(samples=str_samples, prompts=str_prompts, outputs=str_outputs, **metadata)
+                    stats["time/metric"] = time() - t1
+                    for k, xs in metrics.items():
+                        stats[f"metrics/{k}{suffix}"] = torch.as_tensor(xs, dtype=torch.float64).mean(-1).item()
+                        if isinstance(xs, float):
+                            continue
+                        columns.append(k)
+                        columns_data.append(xs if isinstance(xs, list) else torch.as_tensor(xs).tolist())
+                if self.generate_sweep_kwarg:
+                    columns.insert(0, sweep_arg)
+                    columns_data.insert(0, [sweep_value] * len(str_samples))
+                table.append(list(zip(*columns_data)))
+        tbar.close()
+
+        logger.info("Summarizing evaluation")
+        if self.runtime.is_main_process and table:
+            rows = sum(list(map(list, zip(*table))), [])
+            title = f"Evaluation #{self.nth_evaluation}"
+            for k, x in stats.items():
+                if k.startswith("reward") or k.startswith("metrics"):
+                    title += f" {k}: {significant(x)}"
+            try:
+                from rich.console import Console
+                from rich.table import Table
+
+                rich_table = Table(*columns, title=title, show_lines=True)
+                for ix in range(min(max(min(3, len(rows)), len(sweep_values)), len(rows))):
+                    rich_table.add_row(*[str(significant(x)) for x in rows[ix]])
+                Console().print(rich_table)
+            except Exception:  # pragma: no cover - rich missing
+                logger.info(title)
+            if self.runtime._tracker_kind == "wandb":
+                import wandb
+
+                stats["samples"] = wandb.Table(columns, rows)
+        self.nth_evaluation += 1
+        return stats
+
+    # ---- optimisation loop ------------------------------------------------------------------------------------------------
+    @contextmanager
+    def _accumulate(self):
+        """Micro-batch bookkeeping.  Gradient synchronisation happens inside ``opt.step()`` (fused reduce-scatter), so
+        unlike the reference (``:502-516``) no ``no_sync`` context is required while accumulating."""
+        self.mb_count += 1
+        assert self.mb_count // self.num_mb <= self.config.train.total_steps, "Beyond total steps, something is wrong"
+        with contextlib.nullcontext():
+            yield
+
+    def _checkpoint_name(self) -> str:
+        return f"checkpoint_{self.iter_count:0{len(str(self.total_steps))}d}"
+
+    def _save_checkpoint(self, directory: str):
+        if self.config.train.save_optimizer:
+            logger.info(f"Saving intermediate optimizer & model checkpoint into {directory}")
+            self.save(directory)
+        pretrained = os.path.join(directory, "hf_model")
+        logger.info(f"Saving pretrained model into {pretrained}")
+        self.save_pretrained(pretrained)
+
+    def train_step(self, minibatch) -> Dict[str, Any]:
+        """One optimizer step over the micro-batches of ``minibatch`` → (device-resident) stats."""
+        times: Dict[str, float] = {}
+        stats_accum = []
+        fwd = bwd = 0.0
+        for microbatch in minibatch:
+            with self._accumulate():
+                with self.runtime.phase("forward", times):
+                    loss, stats = self.loss(microbatch)
+                fwd += times["forward"]
+                with self.runtime.phase("backward", times):
+                    self.model.train()
+                    loss.backward()
+                    self.model.eval()
+                bwd += times["backward"]
+                stats_accum.append(stats)
+        n = len(stats_accum)
+        stats = {k: sum(s[k] for s in stats_accum) / self.num_mb for k in stats_accum[0]}
+        self.opt.step()
+        self.opt.zero_grad()
+        self.scheduler.step()
+        self.iter_count += 1
+        self._after_weights_changed()
+        stats["time/forward"] = fwd / self.num_mb
+        stats["time/backward"] = bwd / self.num_mb
+        return stats
+
+    def learn(self):  # noqa: C901
+        """Train from ``self.store``; checkpoint / evaluate on their intervals; returns the last eval results."""
+        logger.info("Starting training")
+        self.prepare_learning()
+        self.iter_count = getattr(self, "_resumed_iter", 0) or self.iter_count
+        self.nth_evaluation = 0
+        results = self.evaluate()
+        self.runtime.log(filter_non_scalars(results) if self.runtime._tracker_kind != "wandb" else results, step=self.iter_count)
+
+        tbar = logging.tqdm(initial=self.iter_count, total=self.total_steps, disable=not self.runtime.is_main_process,
+                            position=0, leave=True)
+        best_reward = -float("inf")
+        for _ in range(self.config.train.epochs):
+            for _ in range(self.n_inner_epochs):
+                train_dataloader = self.create_train_dataloader()
+                for minibatch in MiniBatchIterator(train_dataloader, self.mb_size, self.num_mb):
+                    stats = self.train_step(minibatch)
+                    if self.iter_count % self.config.train.checkpoint_interval == 0 or self.iter_count >= self.total_steps:
+                        self._save_checkpoint(os.path.join(self.config.train.checkpoint_dir, self._checkpoint_name()))
+                    for gi, lr in enumerate(self.scheduler.get_last_lr()):
+                        stats[f"learning_rate_group_{gi}"] = lr
+                    stats = _materialise(stats)
+                    if self.iter_count % self.config.train.eval_interval == 0 or self.iter_count >= self.total_steps:
+                        results = self.evaluate()
+                        stats.update(results)
+                        if self.config.train.save_best:
+                            if stats.get("reward/mean", -float("inf")) > best_reward:
+                                best_reward, do_save = stats.get("reward/mean"), True
+                            elif stats.get("metrics/reward", -float("inf")) > best_reward:
+                                best_reward, do_save = stats.get("metrics/reward"), True
+                            else:
+                                do_save = False
+                            flag = torch.tensor(int(do_save), device=self.runtime.device)
+                            self.runtime.all_reduce(flag, "max")
+                            if bool(flag.item()):
+                                self._save_checkpoint(os.path.join(self.config.train.checkpoint_dir, "best_checkpoint"))
+                    desc = " | ".join(f"{k}: {v:.2f}" for k, v in stats.items() if k.startswith("loss"))
+                    tbar.set_description(f"[{desc}]")
+                    tbar.update()
+                    self.runtime.log(stats, step=self.iter_count)
+                    if self.iter_count >= self.total_steps:
+                        tbar.close()
+                        return results
+                self.post_backward_callback()
+            self.post_epoch_callback()
+        tbar.close()
+        return results
+
+    # ---- hooks ------------------------------------------------------------------------------------------------------------
+    @abstractmethod
+    def create_train_dataloader(self):
+        """New dataloader (fresh shuffle) for one inner epoch."""
+
+    @abstractmethod
+    def get_arch(self, config: TRLConfig):
+        """Build the wrapped model for this method."""
+
+    @abstractmethod
+    def loss(self, batch) -> Tuple[torch.Tensor, Dict]:
+        """Loss and statistics of one micro-batch."""
+
+    @abstractmethod
+    def prepare_learning(self):
+        """Set ``eval_dataloader``, ``total_steps``, ``n_inner_epochs`` … before training."""
+
+    def post_backward_callback(self):
+        """After each pass over the store."""
+
+    def post_epoch_callback(self):
+        """After each outer epoch."""
