@@ -1,0 +1,8 @@
+#!/bin/bash
+# run each GPU kernel test function in its own process so a device-side hang is attributed to one group
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
+for t in test_decode_attention test_logprob_from_logits test_gae_whiten test_ppo_loss_and_grads test_kl_rewards test_adamw_flat test_linear_autograd test_fused_logprob_autograd test_lmhead_greedy_and_sampling test_embed_rowdot test_norm; do
+  echo "=== $t"
+  timeout 100 python -m pytest tests/test_kernels_gpu.py -m gpu -q -x -k "$t" --timeout=45 --timeout-method=thread -p no:cacheprovider 2>&1 | tail -25
+  echo "rc=$?"
+done

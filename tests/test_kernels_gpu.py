@@ -261,7 +261,8 @@ def test_linear_autograd():
     yr.float().pow(2).sum().backward()
     torch.testing.assert_close(y.float(), yr.float(), atol=5e-2, rtol=3e-2)
     for a, bb in ((gx, x.grad), (gw, w.grad), (gb, b.grad), (gr, r.grad)):
-        torch.testing.assert_close(a.float(), bb.float(), atol=0.5, rtol=5e-2)
+        scale = bb.float().abs().max().item()
+        torch.testing.assert_close(a.float(), bb.float(), atol=2e-2 * scale, rtol=5e-2)
 
 
 def test_fused_logprob_autograd():
@@ -279,5 +280,5 @@ def test_fused_logprob_autograd():
     ref = torch.log_softmax(F.linear(h.float(), w.float()), -1).gather(-1, labels[:, None]).squeeze(-1)
     (ref * torch.arange(M, device="cuda")).sum().backward()
     torch.testing.assert_close(lp, ref, atol=3e-3, rtol=1e-3)
-    torch.testing.assert_close(gh.float(), h.grad.float(), atol=0.3, rtol=5e-2)
-    torch.testing.assert_close(gw.float(), w.grad.float(), atol=0.5, rtol=5e-2)
+    torch.testing.assert_close(gh.float(), h.grad.float(), atol=2e-2 * h.grad.float().abs().max().item(), rtol=5e-2)
+    torch.testing.assert_close(gw.float(), w.grad.float(), atol=2e-2 * w.grad.float().abs().max().item(), rtol=5e-2)

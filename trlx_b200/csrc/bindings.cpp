@@ -19,7 +19,8 @@ int b200_gemm_bf16(const void*, const void*, void*, int, int, int, long long, lo
                    long long, const float*, float, int, int, int, cudaStream_t);
 int b200_lmhead_tiles(int);
 int b200_lmhead_bf16(const void*, const void*, int, int, int, long long, long long, const void*, const long long*, float*,
-                     float*, float*, int, float, unsigned long long, const int*, int, int, long long*, float*, cudaStream_t);
+                     float*, float*, int, float, unsigned long long, const long long*, const int*, int, int, long long*, float*,
+                     cudaStream_t);
 int b200_norm_bf16(const void*, const void*, const void*, void*, int, int, long long, long long, float, int, cudaStream_t);
 int b200_embed_bf16(const long long*, const int*, const void*, const void*, int, void*, int, int, cudaStream_t);
 int b200_decode_attention_bf16(const void*, void*, void*, const int*, const int*, const int*, void*, int, int, int, int, int,
@@ -101,7 +102,7 @@ Tensor gemm(const Tensor& x, const Tensor& w, const OptTensor& bias, const OptTe
 // Fused LM head: returns (lse[M], logprob[M], token[M], token_logprob[M]); unused outputs are empty tensors.
 std::vector<Tensor> lmhead(const Tensor& h, const Tensor& w, const OptTensor& bias, const OptTensor& labels, bool sample,
                            double temperature, int64_t seed, const OptTensor& step, int64_t suppress_col,
-                           int64_t suppress_until, const OptTensor& workspace_) {
+                           int64_t suppress_until, const OptTensor& workspace_, const OptTensor& seed_tensor) {
   CHECK_BF16(h); CHECK_BF16(w);
   TORCH_CHECK(h.dim() == 2 && w.dim() == 2 && h.size(1) == w.size(1) && h.stride(1) == 1 && w.stride(1) == 1);
   const int64_t M = h.size(0), N = w.size(0), K = h.size(1);
@@ -116,11 +117,13 @@ std::vector<Tensor> lmhead(const Tensor& h, const Tensor& w, const OptTensor& bi
   Tensor tlp = sample ? torch::empty({M}, f32) : Tensor();
   const long long* lab = nullptr;
   if (labels.has_value()) { TORCH_CHECK(labels->scalar_type() == at::kLong && labels->numel() == M && labels->is_contiguous()); lab = labels->data_ptr<int64_t>() ? (const long long*)labels->data_ptr<int64_t>() : nullptr; }
+  const long long* seedp = nullptr;
+  if (seed_tensor.has_value()) { TORCH_CHECK(seed_tensor->scalar_type() == at::kLong && seed_tensor->is_cuda()); seedp = (const long long*)seed_tensor->data_ptr<int64_t>(); }
   const int* sp = nullptr;
   if (step.has_value()) { TORCH_CHECK(step->scalar_type() == at::kInt); sp = step->data_ptr<int>(); }
   check(b200_lmhead_bf16(h.data_ptr(), w.data_ptr(), (int)M, (int)N, (int)K, h.stride(0), w.stride(0), optptr(bias), lab,
                          ws.data_ptr<float>(), lse.data_ptr<float>(), lp.data_ptr<float>(), sample ? 1 : 0,
-                         (float)temperature, (unsigned long long)seed, sp, (int)suppress_col, (int)suppress_until,
+                         (float)temperature, (unsigned long long)seed, seedp, sp, (int)suppress_col, (int)suppress_until,
                          sample ? (long long*)tok.data_ptr<int64_t>() : nullptr, sample ? tlp.data_ptr<float>() : nullptr,
                          stream()),
         "lmhead");
@@ -421,7 +424,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("alpha") = 1.0, py::arg("force_bn") = 0);
   m.def("lmhead", &lmhead, py::arg("h"), py::arg("w"), py::arg("bias") = py::none(), py::arg("labels") = py::none(),
         py::arg("sample") = false, py::arg("temperature") = 1.0, py::arg("seed") = 0, py::arg("step") = py::none(),
-        py::arg("suppress_col") = -1, py::arg("suppress_until") = 0, py::arg("workspace") = py::none());
+        py::arg("suppress_col") = -1, py::arg("suppress_until") = 0, py::arg("workspace") = py::none(),
+        py::arg("seed_tensor") = py::none());
   m.def("norm", &norm, py::arg("x"), py::arg("w"), py::arg("b") = py::none(), py::arg("eps") = 1e-5, py::arg("rms") = false,
         py::arg("out") = py::none());
   m.def("embed", &embed, py::arg("tokens"), py::arg("positions"), py::arg("wte"), py::arg("wpe") = py::none(),

@@ -147,11 +147,15 @@ decode_attn_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restr
 #pragma unroll
   for (int i = 0; i < MAX_D / 8; ++i) acc[i] = 0.f;
   // lane (sub, l8) accumulates output dims { l8*8 + 64*c + j } for its keys
-  for (int t = lo + warp * 4 + sub; t < len; t += 16) {
+  // NOTE: the trip count is warp-uniform (`base`), lanes whose key index falls past `len` stay in the loop so the
+  // full-mask shuffles below are executed by every lane.
+  for (int base_t = lo + warp * 4; base_t < len; base_t += 16) {
+    const int t = base_t + sub;
+    const bool valid = t < len;
     float part = 0.f;
     const __nv_bfloat16* kptr = nullptr;
     const __nv_bfloat16* vptr = nullptr;
-    if (t < last) {
+    if (valid && t < last) {
       const size_t slot = ((size_t)bt[t / page_size] * page_size + (t % page_size)) * nkv + kvh;
       kptr = kcache + slot * d;
       vptr = vcache + slot * d;
@@ -165,7 +169,7 @@ decode_attn_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restr
           for (int j = 0; j < 8; ++j) part += q_s[base + j] * __bfloat162float(kh[j]);
         }
       }
-    } else {
+    } else if (valid) {
 #pragma unroll
       for (int c = 0; c < MAX_D / 64; ++c) {
         const int base = l8 * 8 + 64 * c;
@@ -178,6 +182,7 @@ decode_attn_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restr
     part += __shfl_xor_sync(0xffffffffu, part, 1);
     part += __shfl_xor_sync(0xffffffffu, part, 2);
     part += __shfl_xor_sync(0xffffffffu, part, 4);
+    if (!valid) continue;
     float sc = part * scale + slope * (float)t;
     const float mn = fmaxf(m, sc);
     const float corr = __expf(m - mn), p = __expf(sc - mn);

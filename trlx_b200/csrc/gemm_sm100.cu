@@ -53,6 +53,7 @@ struct LMHeadEpilogue {
   int* samp_idx;               // [M, n_tiles]
   float inv_temperature;      // <= 0 -> greedy (no Gumbel noise)
   unsigned long long seed;
+  const long long* seed_ptr;   // optional device-side seed offset (lets a captured CUDA graph draw fresh noise per call)
   const int* step_ptr;         // optional device step counter: mixed into the seed, gates `suppress_col`
   int suppress_col;            // column forced to -inf while step < suppress_until (EOS before min_new_tokens), -1 = none
   int suppress_until;
@@ -223,7 +224,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const bool sampling = le.samp_key != nullptr;
       const int step = le.step_ptr ? *le.step_ptr : 0;
       const int suppress = (le.suppress_col >= 0 && step < le.suppress_until) ? le.suppress_col : -1;
-      const unsigned long long seed = le.seed + 0x632BE59BD9B4E019ull * (unsigned long long)(step + 1);
+      const unsigned long long seed = le.seed + (le.seed_ptr ? (unsigned long long)(*le.seed_ptr) : 0ull) +
+                                      0x632BE59BD9B4E019ull * (unsigned long long)(step + 1);
       const bool greedy = le.inv_temperature <= 0.f;
 #pragma unroll 1
       for (int c = 0; c < BN; c += 16) {
@@ -428,7 +430,8 @@ extern "C" int b200_lmhead_tiles(int N) { return (N + 127) / 128; }
 // Outputs (any may be null): lse[M], logprob[M] (of labels), token[M] + token_logprob[M] (when sample != 0).
 extern "C" int b200_lmhead_bf16(const void* H, const void* W, int M, int N, int K, long long ldh, long long ldw,
                                 const void* bias, const long long* labels, float* workspace, float* lse, float* logprob,
-                                int sample, float temperature, unsigned long long seed, const int* step_ptr,
+                                int sample, float temperature, unsigned long long seed, const long long* seed_ptr,
+                                const int* step_ptr,
                                 int suppress_col, int suppress_until, long long* token, float* token_logprob,
                                 cudaStream_t stream) {
   if (M <= 0) return 0;
@@ -448,6 +451,7 @@ extern "C" int b200_lmhead_bf16(const void* H, const void* W, int M, int N, int 
   le.label_logit = workspace + 5 * mt;
   le.inv_temperature = temperature > 0.f ? 1.0f / temperature : 0.f;
   le.seed = seed;
+  le.seed_ptr = seed_ptr;
   le.step_ptr = step_ptr;
   le.suppress_col = suppress_col;
   le.suppress_until = suppress_until;

@@ -1,0 +1,344 @@
+"""CUDA rollout engine: batched sampling for PPO on the sm_100a kernels, one CUDA graph per decode step.
+
+What the reference does per chunk of prompts: HF ``generate`` (python loop, dozens of launches per
+token) → a second full forward for log-probs and values → ``forward_hydra`` which runs the trunk a third time for the
+reference log-probs → ``[B,T,V]`` fp32 logits twice → ``.cpu()``.  Here:
+
+* prompts are prefilled once (tcgen05 GEMMs) and their K/V scattered into a **paged KV cache**
+  (``csrc/bindings.cpp::PagedKVAllocator`` hands out pages; every layer owns a ``[pages, page, kv_heads, d]`` tensor);
+* each decode step is ONE captured CUDA graph: embedding → per layer {norm, QKV GEMM, paged attention with fused
+  rotary + cache append, out-proj GEMM (+residual), norm, MLP GEMMs (+bias+act, +residual)} → the fused LM-head
+  kernel samples by Gumbel-max inside the GEMM epilogue and returns the token and its log-prob without ever
+  writing logits → value head → the frozen *reference branch* runs from the shared trunk activation and scores
+  the same token → a bookkeeping kernel records (token, log-prob, ref log-prob, value), retires finished rows and
+  prepares the next step — all on the device;
+* the trunk activation at the branch point is kept per position so PPO updates never recompute the frozen trunk.
+
+The result has exactly the tensors ``AcceleratePPOTrainer.make_experience`` needs (``logprobs``, ``ref_logprobs``,
+``values`` over ``T-1`` positions, ``mask``, ``start``), so the reference's re-scoring passes are simply not run.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Any, Dict, List, Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from trlx_b200 import ops
+from trlx_b200.models.modeling_base import base_lm
+from trlx_b200.nn.transformer import alibi_slopes, build_attn_context
+from trlx_b200.utils import logging
+
+logger = logging.get_logger(__name__)
+
+PAGE = 16
+
+
+@dataclass
+class _LayerW:
+    n1w: torch.Tensor
+    n1b: Optional[torch.Tensor]
+    n2w: Optional[torch.Tensor]
+    n2b: Optional[torch.Tensor]
+    qkv_w: torch.Tensor
+    qkv_b: Optional[torch.Tensor]
+    out_w: torch.Tensor
+    out_b: Optional[torch.Tensor]
+    up_w: torch.Tensor
+    up_b: Optional[torch.Tensor]
+    down_w: torch.Tensor
+    down_b: Optional[torch.Tensor]
+    window: int
+
+
+def _layer_weights(block, spec, idx: int) -> _LayerW:
+    n2 = block.norm2
+    return _LayerW(block.norm1.weight, block.norm1.bias, n2.weight if n2 is not None else None,
+                   n2.bias if n2 is not None else None, block.attn.qkv.weight, block.attn.qkv.bias, block.attn.out.weight,
+                   block.attn.out.bias, block.mlp.up.weight, block.mlp.up.bias, block.mlp.down.weight, block.mlp.down.bias,
+                   spec.local_window if idx in spec.local_layers else 0)
+
+
+class RolloutEngine:
+    @staticmethod
+    def supports(model, gen_kwargs: Dict[str, Any], config=None, stop_sequences=None) -> bool:
+        """Decoder-only hydra model with a frozen reference branch, bf16 on CUDA, plain (temperature) sampling."""
+        try:
+            if not ops.available():
+                return False
+        except ops.ExtensionMissing:
+            raise
+        if stop_sequences:
+            return False  # trimming + re-tokenisation changes token ids → reference-faithful PyTorch path
+        if getattr(model, "peft_type", None) or getattr(model, "frozen_head", None) is None:
+            return False
+        if getattr(model, "num_value_layers_unfrozen", 0) != 0:
+            return False
+        lm = base_lm(model.base_model)
+        spec = lm.config
+        if not hasattr(lm, "transformer") or lm.dtype != torch.bfloat16 or not lm.device.type == "cuda":
+            return False
+        if spec.head_dim % 8 or spec.hidden_size % 8 or spec.head_dim > 256 or spec.ffn_size % 8:
+            return False
+        g = gen_kwargs or {}
+        if g.get("top_k") not in (0, None) or g.get("top_p") not in (1.0, 1, None):
+            return False
+        if g.get("num_beams", 1) not in (1, None) or g.get("repetition_penalty") not in (None, 1.0):
+            return False
+        if any(isinstance(v, list) for v in g.values()):
+            return False
+        return True
+
+    def __init__(self, model, pad_token_id: int, eos_token_id: int, gen_kwargs: Dict[str, Any], cache_trunk: bool = True,
+                 seed: int = 0, use_cuda_graph: bool = True):
+        self.model = model
+        self.lm = base_lm(model.base_model)
+        self.spec = self.lm.config
+        self.pad, self.eos = int(pad_token_id), int(eos_token_id if eos_token_id is not None else -1)
+        self.gen = dict(gen_kwargs)
+        self.cache_trunk = cache_trunk
+        self.seed = int(seed)
+        self.calls = 0
+        self.use_cuda_graph = use_cuda_graph
+        self.device = self.lm.device
+        self.branch = model.branch_layer
+        spec = self.spec
+        self.layers = [_layer_weights(b, spec, i) for i, b in enumerate(self.lm.transformer.h)]
+        fh = model.frozen_head
+        self.ref_layers = [_layer_weights(b, spec, self.branch + j) for j, b in enumerate(fh.decoder_blocks)]
+        self.scale = spec.attn_scale if spec.attn_scale is not None else 1.0 / math.sqrt(spec.head_dim)
+        self.alibi = alibi_slopes(spec.num_heads).to(self.device) if spec.pos == "alibi" else None
+        self.rot_dim = spec.rotary_dim if spec.pos == "rotary" else 0
+        self._state = None  # (B, P) → static buffers + graph
+        do_sample = bool(self.gen.get("do_sample", False))
+        t = self.gen.get("temperature", 1.0)
+        self.temperature = float(t if t is not None else 1.0) if do_sample else 0.0
+        self.launches_per_step = 0
+
+    # ------------------------------------------------------------------------------------------------ kernels per layer
+    def _layer(self, x, W: _LayerW, kc, vc, st):
+        C, spec = ops.C, self.spec
+        rms = spec.norm == "rmsnorm"
+        h = C.norm(x, W.n1w, W.n1b, spec.norm_eps, rms)
+        qkv = C.gemm(h, W.qkv_w, W.qkv_b)
+        a = C.decode_attention(qkv, kc, vc, st["block_table"], st["seq_lens"], st["positions"], spec.num_heads,
+                               spec.num_kv_heads, spec.head_dim, self.scale, self.rot_dim, spec.rotary_base,
+                               spec.rotary_interleaved, self.alibi, W.window)
+        if spec.parallel_residual:
+            h2 = h if W.n2w is None else C.norm(x, W.n2w, W.n2b, spec.norm_eps, rms)
+            t = C.gemm(a, W.out_w, W.out_b, x)
+            return C.gemm(self._mlp_mid(h2, W), W.down_w, W.down_b, t)
+        x = C.gemm(a, W.out_w, W.out_b, x)
+        h2 = C.norm(x, W.n2w, W.n2b, spec.norm_eps, rms)
+        return C.gemm(self._mlp_mid(h2, W), W.down_w, W.down_b, x)
+
+    def _mlp_mid(self, h, W: _LayerW):
+        C, spec = ops.C, self.spec
+        if spec.gated_mlp:
+            g, u = C.gemm(h, W.up_w, W.up_b).chunk(2, dim=-1)
+            return (F.silu(g) * u).contiguous() if spec.activation in ("silu", "swish") else (F.gelu(g, approximate="tanh") * u).contiguous()
+        return C.gemm(h, W.up_w, W.up_b, None, spec.activation)
+
+    def _decode_step(self, st):
+        """One token for every running row; pure device work (captured into a CUDA graph)."""
+        C, spec, lm, model = ops.C, self.spec, self.lm, self.model
+        tr = lm.transformer
+        x = C.embed(st["next_tokens"], st["positions"], tr.wte.weight, tr.wpe.weight if tr.wpe is not None else None,
+                    spec.pos_offset)
+        if tr.emb_norm is not None:
+            x = C.norm(x, tr.emb_norm.weight, tr.emb_norm.bias, spec.norm_eps, spec.norm == "rmsnorm")
+        trunk_x = x
+        for i, W in enumerate(self.layers):
+            if i == self.branch:
+                trunk_x = x
+            x = self._layer(x, W, st["kc"][i], st["vc"][i], st)
+        if self.cache_trunk:
+            st["trunk_decode"].index_copy_(1, st["step64"], trunk_x.unsqueeze(1))
+        rms = spec.norm == "rmsnorm"
+        hf = C.norm(x, tr.ln_f.weight, tr.ln_f.bias, spec.norm_eps, rms)
+        _, _, tok, tlp = C.lmhead(hf, lm.lm_head.weight, lm.lm_head.bias, None, True, self.temperature, self.seed,
+                                  st["step"], self.eos if st["min_new"] > 0 else -1, st["min_new"], st["ws"], st["seed_dev"])
+        vh = model.v_head
+        h1 = C.gemm(hf, vh[0].weight, vh[0].bias, None, "relu")
+        val = C.rowdot(h1, vh[2].weight.view(-1), vh[2].bias)
+        fh = model.frozen_head
+        y = trunk_x
+        L = len(self.layers)
+        for j, W in enumerate(self.ref_layers):
+            y = self._layer(y, W, st["kc"][L + j], st["vc"][L + j], st)
+        rf = C.norm(y, fh.final_norm.weight, fh.final_norm.bias, spec.norm_eps, rms)
+        _, ref_lp, _, _ = C.lmhead(rf, fh.lm_head.weight, fh.lm_head.bias, tok, False, 1.0, 0, None, -1, 0, st["ws_ref"])
+        C.decode_step(tok, tlp, ref_lp, val, st["step"], st["R"], self.eos, self.pad, st["tokens_out"], st["lp_out"],
+                      st["ref_lp_out"], st["val_out"], st["finished"], st["resp_lens"], st["seq_lens"], st["positions"],
+                      st["next_tokens"], st["n_running"])
+        st["step64"].add_(1)
+
+    # ------------------------------------------------------------------------------------------------ state / graph
+    def _build_state(self, B: int, Q: int, R: int):
+        spec, dev = self.spec, self.device
+        P = (Q + R + PAGE - 1) // PAGE
+        n_layers = len(self.layers) + len(self.ref_layers)
+        i32 = dict(dtype=torch.int32, device=dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        V = spec.vocab_size
+        n_tiles = (V + 127) // 128
+        st = dict(
+            B=B, Q=Q, R=R, P=P,
+            allocator=ops.C.PagedKVAllocator(B * P, PAGE),
+            kc=[torch.zeros(B * P, PAGE, spec.num_kv_heads, spec.head_dim, dtype=torch.bfloat16, device=dev) for _ in range(n_layers)],
+            vc=[torch.zeros(B * P, PAGE, spec.num_kv_heads, spec.head_dim, dtype=torch.bfloat16, device=dev) for _ in range(n_layers)],
+            block_table=torch.zeros(B, P, **i32), seq_lens=torch.zeros(B, **i32), positions=torch.zeros(B, **i32),
+            next_tokens=torch.zeros(B, dtype=torch.long, device=dev), finished=torch.zeros(B, **i32),
+            resp_lens=torch.zeros(B, **i32), step=torch.zeros(1, **i32), step64=torch.zeros(1, dtype=torch.long, device=dev),
+            n_running=torch.zeros(1, **i32),
+            tokens_out=torch.full((B, R), self.pad, dtype=torch.long, device=dev), lp_out=torch.zeros(B, R, **f32),
+            ref_lp_out=torch.zeros(B, R, **f32), val_out=torch.zeros(B, R, **f32),
+            ws=torch.empty(5 * B * n_tiles + B, **f32), ws_ref=torch.empty(5 * B * n_tiles + B, **f32),
+            trunk_decode=(torch.zeros(B, R, spec.hidden_size, dtype=torch.bfloat16, device=dev) if self.cache_trunk else None),
+            seed_dev=torch.zeros(1, dtype=torch.long, device=dev), min_new=0, graph=None,
+        )
+        return st
+
+    def _ensure_state(self, B, Q, R):
+        st = self._state
+        if st is None or st["B"] != B or st["R"] != R or st["P"] < (Q + R + PAGE - 1) // PAGE:
+            self._state = st = self._build_state(B, Q, R)
+        return st
+
+    def _reset(self, st, q_lens: torch.Tensor, last_tokens: torch.Tensor):
+        B, P = st["B"], st["P"]
+        alloc = st["allocator"]
+        alloc.reset()
+        for b in range(B):
+            alloc.reserve(b, P * PAGE)
+        st["block_table"].copy_(alloc.block_table(list(range(B)), P), non_blocking=True)
+        st["seq_lens"].copy_(q_lens.to(torch.int32))
+        st["positions"].copy_((q_lens - 1).to(torch.int32))
+        st["next_tokens"].copy_(last_tokens)
+        st["finished"].zero_()
+        st["resp_lens"].zero_()
+        st["step"].zero_()
+        st["step64"].zero_()
+        st["n_running"].fill_(B)
+        st["tokens_out"].fill_(self.pad)
+        for k in ("lp_out", "ref_lp_out", "val_out"):
+            st[k].zero_()
+
+    # ------------------------------------------------------------------------------------------------ prefill
+    @torch.no_grad()
+    def _prefill(self, st, prompt: torch.Tensor, mask: torch.Tensor):
+        """Forward the first Q-1 prompt tokens, fill the paged caches, return prompt-position scores."""
+        C, lm, model, spec = ops.C, self.lm, self.model, self.spec
+        B, Q = prompt.shape
+        T = Q - 1
+        H = spec.hidden_size
+        dev = self.device
+        if T == 0:
+            z = torch.zeros(B, 0, device=dev)
+            return z, z.clone(), z.clone(), torch.zeros(B, 0, H, dtype=torch.bfloat16, device=dev)
+        ids, am = prompt[:, :T], mask[:, :T]
+        pos = (am.long().cumsum(-1) - 1).clamp_min(0)
+        out = lm(input_ids=ids, attention_mask=am, position_ids=pos, use_cache=True, output_hidden_states=True,
+                 compute_logits=False)
+        first = (Q - mask.long().sum(1)).to(torch.int32)  # left padding
+        lens = (mask.long().sum(1) - 1).to(torch.int32)
+
+        def scatter(layer_idx, kv):
+            k, v = kv
+            k2 = k.transpose(1, 2).reshape(B, T, -1)
+            v2 = v.transpose(1, 2).reshape(B, T, -1)
+            C.paged_kv_write(k2, v2, st["kc"][layer_idx], st["vc"][layer_idx], st["block_table"], first, lens,
+                             spec.num_kv_heads, spec.head_dim)
+
+        for i, kv in enumerate(out.past_key_values):
+            scatter(i, kv)
+        trunk = out.hidden_states[self.branch]
+        final = out.last_hidden_state
+        labels = prompt[:, 1:Q]
+        lp, _ = ops.fused_logprob(final, lm.lm_head.weight, lm.lm_head.bias, labels)
+        # reference branch on the shared trunk activation
+        fh = model.frozen_head
+        ctx = build_attn_context(spec, am, pos, T, 0, trunk.dtype, dev)
+        y = trunk
+        L = len(self.layers)
+        for j, blk in enumerate(fh.decoder_blocks):
+            y, present = blk(y, ctx, None, True)
+            scatter(L + j, present)
+        y = fh.final_norm(y)
+        ref_lp, _ = ops.fused_logprob(y, fh.lm_head.weight, fh.lm_head.bias, labels)
+        vals = torch.zeros(B, T, device=dev)
+        return lp.float(), ref_lp.float(), vals, trunk
+
+    # ------------------------------------------------------------------------------------------------ public API
+    @torch.no_grad()
+    def rollout(self, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor] = None) -> Dict[str, Any]:
+        dev = self.device
+        prompt = input_ids.to(dev, non_blocking=True)
+        mask = (attention_mask if attention_mask is not None else torch.ones_like(input_ids)).to(dev, non_blocking=True).long()
+        B, Q = prompt.shape
+        g = self.gen
+        R = g.get("max_new_tokens")
+        if R is None:
+            R = max(int(g.get("max_length", Q + 20)) - Q, 1)
+        R = int(R)
+        st = self._ensure_state(B, Q, R)
+        q_lens = mask.sum(1)
+        self._reset(st, q_lens, prompt[:, -1])
+        self.calls += 1
+        st["seed_dev"].fill_((self.calls * 0x9E3779B1) & 0x7FFFFFFFFFFF)
+        st["min_new"] = max(int(g.get("min_new_tokens") or 0), int(g.get("min_length") or 0) - Q, 0)
+
+        lp_p, ref_lp_p, val_p, trunk_p = self._prefill(st, prompt, mask)
+
+        if self.use_cuda_graph:
+            if st["graph"] is None or st.get("graph_key_min_new") != st["min_new"]:
+                # warm-up on a side stream (also loads kernels / sets attributes), then capture
+                snap = {k: st[k].clone() for k in ("seq_lens", "positions", "next_tokens", "finished", "resp_lens", "step",
+                                                   "step64", "n_running")}
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                before = ops.launch_count()
+                with torch.cuda.stream(s):
+                    self._decode_step(st)
+                self.launches_per_step = ops.launch_count() - before
+                torch.cuda.current_stream().wait_stream(s)
+                for k, v in snap.items():
+                    st[k].copy_(v)
+                st["tokens_out"].fill_(self.pad)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    self._decode_step(st)
+                for k, v in snap.items():
+                    st[k].copy_(v)
+                st["tokens_out"].fill_(self.pad)
+                for k2 in ("lp_out", "ref_lp_out", "val_out"):
+                    st[k2].zero_()
+                st["graph"], st["graph_key_min_new"] = graph, st["min_new"]
+                # the sampling noise varies per step (device step counter) and per call (device seed offset)
+            for s_i in range(R):
+                st["graph"].replay()
+                ops.add_launches(self.launches_per_step)
+                if (s_i & 7) == 7 and s_i + 1 < R and int(st["n_running"].item()) == 0:
+                    break
+        else:
+            for s_i in range(R):
+                self._decode_step(st)
+                if (s_i & 7) == 7 and s_i + 1 < R and int(st["n_running"].item()) == 0:
+                    break
+
+        resp_lens = st["resp_lens"].clone()
+        r_max = max(int(resp_lens.max().item()), 1)
+        sample_outputs = st["tokens_out"][:, :r_max].clone()
+        logprobs = torch.cat([lp_p, st["lp_out"][:, :r_max]], 1)
+        ref_logprobs = torch.cat([ref_lp_p, st["ref_lp_out"][:, :r_max]], 1)
+        values = torch.cat([val_p, st["val_out"][:, :r_max]], 1)
+        all_tokens = torch.cat([prompt, sample_outputs], 1)
+        full_mask = all_tokens.not_equal(self.pad).long()
+        trunk = None
+        if self.cache_trunk:
+            trunk = torch.cat([trunk_p, st["trunk_decode"][:, :r_max]], 1)
+        return dict(samples=all_tokens, prompt_tensors=prompt, sample_outputs=sample_outputs, logprobs=logprobs,
+                    ref_logprobs=ref_logprobs, values=values, mask=full_mask, start=Q - 1, trunk=trunk)

@@ -37,6 +37,19 @@ class CausalLMOutput:
         return tuple(v for v in (self.loss, self.logits, self.past_key_values, self.hidden_states) if v is not None)[i]
 
 
+def project(module: nn.Module, x: torch.Tensor, act: str = "none", residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``act(x @ W.T + b) (+ residual)`` for an ``nn.Linear`` — on CUDA/bf16 this is the tcgen05 GEMM with the bias /
+    activation / residual fused into its epilogue; adapter-wrapped projections (LoRA) keep their own forward."""
+    if type(module) is nn.Linear and x.is_cuda and x.dtype == torch.bfloat16:
+        from trlx_b200 import ops
+
+        return ops.linear(x, module.weight, module.bias, act, residual)
+    y = module(x)
+    if act not in ("none", "", None):
+        y = activation_fn(act)(y)
+    return y if residual is None else y + residual
+
+
 def activation_fn(name: str):
     if name in ("gelu_new", "gelu_pytorch_tanh", "gelu_fast", "gelu_tanh"):
         return lambda x: F.gelu(x, approximate="tanh")
@@ -122,7 +135,7 @@ class Attention(nn.Module):
     def forward(self, x, ctx: AttnContext, past=None, use_cache=False):
         s = self.spec
         B, T, _ = x.shape
-        qkv = self.qkv(x)
+        qkv = project(self.qkv, x)
         q, k, v = qkv.split([s.q_size, s.kv_size, s.kv_size], dim=-1)
         q = q.view(B, T, s.num_heads, s.head_dim).transpose(1, 2)
         k = k.view(B, T, s.num_kv_heads, s.head_dim).transpose(1, 2)
@@ -144,7 +157,7 @@ class Attention(nn.Module):
         else:
             o = F.scaled_dot_product_attention(q, k, v, attn_mask=bias.to(q.dtype), scale=self.scale)
         o = o.transpose(1, 2).reshape(B, T, s.q_size)
-        return self.out(o), present
+        return project(self.out, o), present
 
 
 class MLP(nn.Module):
@@ -154,15 +167,15 @@ class MLP(nn.Module):
         self.up = nn.Linear(spec.hidden_size, spec.ffn_size * (2 if spec.gated_mlp else 1), bias=spec.mlp_bias, dtype=dtype)
         self.down = nn.Linear(spec.ffn_size, spec.hidden_size, bias=spec.mlp_bias, dtype=dtype)
         self.act = activation_fn(spec.activation)
+        self.act_name = spec.activation
 
     def forward(self, x):
-        h = self.up(x)
         if self.gated:
-            g, u = h.chunk(2, dim=-1)
+            g, u = project(self.up, x).chunk(2, dim=-1)
             h = self.act(g) * u
         else:
-            h = self.act(h)
-        return self.down(h)
+            h = project(self.up, x, self.act_name)
+        return project(self.down, h)
 
 
 class Block(nn.Module):
@@ -328,7 +341,7 @@ class CausalLM(nn.Module):
             x = trunk.ln_f(x)
         if hiddens is not None:
             hiddens.append(x)
-        logits = self.lm_head(x) if (final and compute_logits) else None
+        logits = project(self.lm_head, x) if (final and compute_logits) else None
         loss = None
         if labels is not None and logits is not None:
             loss = F.cross_entropy(logits[:, :-1].reshape(-1, logits.shape[-1]).float(), labels[:, 1:].reshape(-1),

@@ -44,9 +44,49 @@ def extension():
     return mod
 
 
+# kernels launched per binding call (used for the launch counter that bench.py reports as ``gpu_launches``)
+_KERNELS_PER_CALL = {"lmhead": 2, "ppo_loss": 3, "gae": 2}
+_launches = 0
+
+
+def reset_launch_count() -> None:
+    global _launches
+    _launches = 0
+
+
+def launch_count() -> int:
+    """Number of hand-written kernels launched (graph replays included) since :func:`reset_launch_count`."""
+    return _launches
+
+
+def add_launches(n: int) -> None:
+    global _launches
+    _launches += int(n)
+
+
 class _Lazy:
+    """Attribute proxy for the extension; kernel entry points are wrapped to count launches."""
+
+    def __init__(self):
+        self._cache = {}
+
     def __getattr__(self, name):
-        return getattr(extension(), name)
+        fn = self._cache.get(name)
+        if fn is not None:
+            return fn
+        raw = getattr(extension(), name)
+        if not callable(raw) or isinstance(raw, type) or name in ("ppo_loss_num_outputs",):
+            return raw
+        per_call = _KERNELS_PER_CALL.get(name, 1)
+
+        def counted(*a, __raw=raw, __n=per_call, **k):
+            global _launches
+            _launches += __n
+            return __raw(*a, **k)
+
+        counted.__name__ = name
+        self._cache[name] = counted
+        return counted
 
 
 C = _Lazy()
@@ -55,7 +95,7 @@ C = _Lazy()
 @functools.lru_cache(maxsize=1)
 def available() -> bool:
     """CUDA device present and extension importable.  Raises on a GPU box without the extension."""
-    if not torch.cuda.is_available():
+    if not torch.cuda.is_available() or os.environ.get("TRLX_B200_DISABLE_KERNELS", "0") == "1":
         return False
     mod, err = _load()
     if mod is None:

@@ -282,17 +282,27 @@ def _quantize(x: torch.Tensor, signed: bool):
     xf = torch.nn.functional.pad(x.reshape(-1).float(), (0, pad)).view(-1, _BLOCK)
     scale = xf.abs().amax(dim=1, keepdim=True).clamp_min(1e-12)
     if signed:
-        q = torch.round(xf / scale * 127).clamp_(-127, 127).to(torch.int8)
+        # sign + log-magnitude (1/4-octave steps, 2^-31 … 1 of the block max): Adam's update m/sqrt(v) is scale free per
+        # element, so small entries need *relative* precision, which linear int8 cannot give
+        lg = torch.log2((xf.abs() / scale).clamp_min(2.0 ** -40))
+        mag = torch.round(127 + 4 * lg).clamp_(1, 127)
+        q = torch.where(xf == 0, torch.zeros_like(mag), mag * torch.sign(xf)).to(torch.int8)
     else:
-        q = torch.round(torch.sqrt(xf / scale) * 255).clamp_(0, 255).to(torch.uint8)  # sqrt companding for v ≥ 0
+        # second moments span many orders of magnitude inside a block: store log2(v / blockmax) with 1/8-octave steps
+        # (covers 2^-31 … 1; code 0 means exactly zero) so that tiny entries never collapse to 0 and blow up m/sqrt(v)
+        lg = torch.log2((xf / scale).clamp_min(2.0 ** -40))
+        q = torch.round(255 + 8 * lg).clamp_(1, 255)
+        q = torch.where(xf <= 0, torch.zeros_like(q), q).to(torch.uint8)
     return q, scale.squeeze(1)
 
 
 def _dequantize(q: torch.Tensor, scale: torch.Tensor, n: int, signed: bool, shape):
     if signed:
-        x = q.float() / 127 * scale[:, None]
+        qf = q.float()
+        x = torch.where(qf != 0, torch.exp2((qf.abs() - 127) / 4) * torch.sign(qf), torch.zeros_like(qf)) * scale[:, None]
     else:
-        x = (q.float() / 255) ** 2 * scale[:, None]
+        qf = q.float()
+        x = torch.where(qf > 0, torch.exp2((qf - 255) / 8), torch.zeros_like(qf)) * scale[:, None]
     return x.reshape(-1)[:n].view(shape)
 
 

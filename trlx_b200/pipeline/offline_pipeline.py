@@ -178,7 +178,14 @@ class PromptPipeline(BasePipeline):
                     out[key] = [x[key] for x in xs]
             return out
 
-        return DataLoader(self, batch_size=batch_size, collate_fn=collate, shuffle=shuffle if sampler is None else False,
+        def collate_pinned(xs):
+            out = collate(xs)
+            if torch.cuda.is_available():  # prompts are staged in pinned host memory → async H2D in the trainers
+                for k in ("input_ids", "attention_mask"):
+                    out[k] = out[k].pin_memory()
+            return out
+
+        return DataLoader(self, batch_size=batch_size, collate_fn=collate_pinned, shuffle=shuffle if sampler is None else False,
                           sampler=sampler, num_workers=0, drop_last=drop_last)
 
 

@@ -160,6 +160,12 @@ class AccelerateRLTrainer(BaseRLTrainer):
         trailing EOS when the generation ended by itself (or was trimmed)."""
         if prompt_sizes is None:
             prompt_sizes = [prompts.shape[1]] * len(prompts)  # left-padded prompts
+        if isinstance(prompts, torch.Tensor) and prompts.is_cuda:
+            prompts = prompts.cpu()
+        if isinstance(samples, torch.Tensor) and samples.is_cuda:
+            samples = samples.cpu()
+        if isinstance(prompt_sizes, torch.Tensor):
+            prompt_sizes = prompt_sizes.tolist()
         seq2seq = self.config.model.model_arch_type == "seq2seq"
         tok = self.tokenizer
         str_samples, str_prompts, str_outputs = [], [], []

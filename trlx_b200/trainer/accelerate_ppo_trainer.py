@@ -325,6 +325,7 @@ class AcceleratePPOTrainer(AccelerateRLTrainer):
         while collected < num_rollouts:
             stats: Dict[str, Any] = {}
             batch = next(self.prompt_iterator)
+            self._last_prompt_width = int(batch["input_ids"].shape[1])
             metadata = {k: v for k, v in batch.items() if k not in ("input_ids", "attention_mask")}
             t_gen = time()
             if engine is not None:
