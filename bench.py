@@ -246,6 +246,40 @@ def main():
                 "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),
     }
+    if os.environ.get("BENCH_BREAKDOWN") and rank == 0:
+        # coarse per-phase wall-clock (synchronised) for one more iteration — diagnostic only, not part of the metric
+        import collections
+
+        acc = collections.OrderedDict()
+
+        def timed(name, fn, *a, **k):
+            torch.cuda.synchronize()
+            t = time.perf_counter()
+            r = fn(*a, **k)
+            torch.cuda.synchronize()
+            acc[name] = acc.get(name, 0.0) + (time.perf_counter() - t) * 1e3
+            return r
+
+        from trlx_b200.pipeline import MiniBatchIterator
+
+        eng = trainer._engine
+        if eng is not None:
+            orig_prefill, orig_rollout = eng._prefill, eng.rollout
+            eng._prefill = lambda *a, **k: timed("engine.prefill", orig_prefill, *a, **k)
+            eng.rollout = lambda *a, **k: timed("engine.rollout(total)", orig_rollout, *a, **k)
+        orig_decode = trainer.decode
+        trainer.decode = lambda *a, **k: timed("decode(strings)", orig_decode, *a, **k)
+        trainer.store.clear_history()
+        timed("make_experience(total)", trainer.make_experience, cfg.method.num_rollouts, 0)
+        for _ in range(trainer.n_inner_epochs):
+            loader = timed("create_loader", trainer.create_train_dataloader)
+            for minibatch in MiniBatchIterator(loader, trainer.mb_size, trainer.num_mb):
+                for mb in minibatch:
+                    loss, _ = timed("loss(fwd)", trainer.loss, mb)
+                    timed("backward", loss.backward)
+                timed("opt.step", trainer.opt.step)
+                timed("zero_grad", trainer.opt.zero_grad)
+        print("BREAKDOWN_MS " + json.dumps({k: round(v, 2) for k, v in acc.items()}), file=sys.stderr)
     if rank == 0:
         print(json.dumps(out))
     if dist.is_initialized():

@@ -155,16 +155,25 @@ def test_freezing_rules():
     assert len(trainable(-1)) == len(list(CausalLM(spec).named_parameters()))
 
 
-def test_logging_rank_filter(monkeypatch, capsys):
+def test_logging_rank_filter():
+    import io
+    import logging as pylogging
+
     from trlx_b200.utils import logging
 
-    logger = logging.get_logger("trlx_b200.test")
-    logging.set_verbosity(logging.INFO)
-    logger.info("shown")
-    logger.info("hidden", ranks=["3"])
-    logger.info("everywhere", ranks=[])
-    err = capsys.readouterr().err
-    assert "[RANK 0] shown" in err and "hidden" not in err and "everywhere" in err
+    stream = io.StringIO()
+    handler = pylogging.StreamHandler(stream)
+    logging.add_handler(handler)
+    try:
+        logger = logging.get_logger("trlx_b200.test")
+        logging.set_verbosity(logging.INFO)
+        logger.info("shown")
+        logger.info("hidden", ranks=["3"])
+        logger.info("everywhere", ranks=[])
+    finally:
+        logging.remove_handler(handler)
+    out = stream.getvalue()
+    assert "[RANK 0] shown" in out and "hidden" not in out and "everywhere" in out
     logging.disable_progress_bar()
     assert not logging.is_progress_bar_enabled() and list(logging.tqdm([1, 2])) == [1, 2]
     logging.enable_progress_bar()

@@ -37,11 +37,14 @@ def merge(base: Dict, update: Dict, updated: Set) -> Dict:
     return base
 
 
+_ATOMIC_KEYS = ("model_path", "tokenizer_path", "peft_config")  # dict-valued fields that are replaced, never merged
+
+
 def _merge_dicts(base: Dict, update: Dict) -> Dict:
     """Pure recursive union (new keys allowed); returns a fresh dict."""
     out = copy.deepcopy(base)
     for key, val in update.items():
-        if isinstance(val, dict):
+        if isinstance(val, dict) and key not in _ATOMIC_KEYS:
             prev = out.get(key)
             out[key] = _merge_dicts(prev if isinstance(prev, dict) else {}, val)
         else:

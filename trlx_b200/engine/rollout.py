@@ -248,8 +248,8 @@ class RolloutEngine:
 
         def scatter(layer_idx, kv):
             k, v = kv
-            k2 = k.transpose(1, 2).reshape(B, T, -1)
-            v2 = v.transpose(1, 2).reshape(B, T, -1)
+            k2 = k.transpose(1, 2).reshape(B, T, -1).contiguous()
+            v2 = v.transpose(1, 2).reshape(B, T, -1).contiguous()
             C.paged_kv_write(k2, v2, st["kc"][layer_idx], st["vc"][layer_idx], st["block_table"], first, lens,
                              spec.num_kv_heads, spec.head_dim)
 

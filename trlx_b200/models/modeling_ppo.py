@@ -469,7 +469,7 @@ class AutoModelForCausalLMWithHydraValueHead(AutoModelForCausalLMWithValueHead):
         state_dict = state_dict or {}
         if not self.peft_type and self.frozen_head is None:
             for k in state_dict:
-                m = re.search(r"^frozen_head\..+\.(\d+)\.", k)
+                m = re.search(r"^frozen_head\.decoder_blocks\.(\d+)\.", k)
                 if m:
                     self.num_layers_unfrozen = max(self.num_layers_unfrozen, int(m.group(1)) + 1)
             if self.num_layers_unfrozen > 0 and any(k.startswith("frozen_head.") for k in state_dict):
@@ -634,7 +634,7 @@ class AutoModelForSeq2SeqLMWithHydraValueHead(AutoModelForSeq2SeqLMWithValueHead
         state_dict = state_dict or {}
         if not self.peft_type and self.frozen_head is None:
             for k in state_dict:
-                m = re.search(r"^frozen_head\..+\.(\d+)\.", k)
+                m = re.search(r"^frozen_head\.decoder_blocks\.(\d+)\.", k)
                 if m:
                     self.num_layers_unfrozen = max(self.num_layers_unfrozen, int(m.group(1)) + 1)
             if self.num_layers_unfrozen > 0 and any(k.startswith("frozen_head.") for k in state_dict):

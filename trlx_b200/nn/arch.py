@@ -141,7 +141,12 @@ def spec_from_hf_config(cfg) -> ArchSpec:
                         activation=_get(cfg, "activation_function", default="gelu_pytorch_tanh"),
                         tie_word_embeddings=_get(cfg, "tie_word_embeddings", default=True), **common)
     if mt == "gpt_neo":
-        layers = _get(cfg, "attention_layers", default=["global"] * L)
+        layers = _get(cfg, "attention_layers")
+        if layers is None:
+            layers = []
+            for pattern, repeat in (_get(cfg, "attention_types") or [[["global"], L]]):
+                layers += list(pattern) * int(repeat)
+            layers = (layers + ["global"] * L)[:L]
         return ArchSpec(family="gpt_neo", num_kv_heads=nh, head_dim=d, ffn_size=_get(cfg, "intermediate_size", default=4 * H),
                         max_positions=_get(cfg, "max_position_embeddings", default=2048),
                         norm_eps=_get(cfg, "layer_norm_epsilon", default=1e-5),

@@ -142,9 +142,11 @@ class DeviceBatchLoader:
                 rmax = max(max(self.host_rlens[i] for i in ids), 1)
                 qmax = max(max(self.host_qlens[i] for i in ids), 1)
                 q = q[:, q.shape[1] - qmax:] if self.left else q[:, :qmax]
-                r, lp, v, rw = r[:, :rmax], lp[:, :rmax], v[:, :rmax], rw[:, :rmax]
+                # responses keep one token more than the longest scored slice: position i is scored against token i+1
+                rtok = min(rmax + 1, self.R)
+                r, lp, v, rw = r[:, :rtok], lp[:, :rmax], v[:, :rmax], rw[:, :rmax]
                 if th is not None:
-                    th = th[:, self.Q - qmax: self.Q + rmax] if self.left else torch.cat([th[:, :qmax], th[:, self.Q: self.Q + rmax]], 1)
+                    th = th[:, self.Q - qmax: self.Q + rtok] if self.left else torch.cat([th[:, :qmax], th[:, self.Q: self.Q + rtok]], 1)
             if th is not None:
                 yield PPORLBatchCached(q, r, lp, v, rw, trunk_hidden=th)
             else:
