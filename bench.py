@@ -274,11 +274,7 @@ def main():
         for _ in range(trainer.n_inner_epochs):
             loader = timed("create_loader", trainer.create_train_dataloader)
             for minibatch in MiniBatchIterator(loader, trainer.mb_size, trainer.num_mb):
-                for mb in minibatch:
-                    loss, _ = timed("loss(fwd)", trainer.loss, mb)
-                    timed("backward", loss.backward)
-                timed("opt.step", trainer.opt.step)
-                timed("zero_grad", trainer.opt.zero_grad)
+                timed("train_step(16x)", trainer.train_step, minibatch)
         print("BREAKDOWN_MS " + json.dumps({k: round(v, 2) for k, v in acc.items()}), file=sys.stderr)
     if rank == 0:
         print(json.dumps(out))

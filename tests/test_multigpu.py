@@ -1,0 +1,150 @@
+"""Multi-GPU tests (need >= 2 B200s on one node; run with `gpurun --gpus 2 -- pytest tests/test_multigpu.py -m gpu`)."""
+import os
+import socket
+import tempfile
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
+
+
+def _need(n):
+    if torch.cuda.device_count() < n:
+        pytest.skip(f"needs {n} GPUs")
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, fn, out_dir, args):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        res = fn(rank, world, *args)
+        torch.cuda.synchronize()
+        torch.save(res, os.path.join(out_dir, f"r{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def run(fn, world=2, args=()):
+    out = tempfile.mkdtemp()
+    mp.spawn(_worker, args=(world, _free_port(), fn, out, args), nprocs=world, join=True)
+    return [torch.load(os.path.join(out, f"r{r}.pt"), weights_only=False) for r in range(world)]
+
+
+# ---- fused reduce-scatter + AdamW + all-gather ----------------------------------------------------------------------------
+def _dp_optim_job(rank, world, clip):
+    from trlx_b200.parallel.optim import FusedAdamW
+
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.randn(n, device="cuda").to(torch.bfloat16)) for n in (1000, 37, 4096, 515)]
+    init = [p.detach().float().clone() for p in params]
+    opt = FusedAdamW(params, lr=1e-2, betas=(0.9, 0.95), weight_decay=0.01, grad_clip=clip).prepare()
+    grads_log = []
+    for step in range(3):
+        torch.manual_seed(100 * step + rank)
+        gs = [torch.randn_like(p) for p in params]
+        for p, g in zip(params, gs):
+            p.grad.copy_(g)
+        grads_log.append([g.float().cpu() for g in gs])
+        opt.step()
+        opt.zero_grad()
+    return dict(params=[p.detach().float().cpu() for p in params], init=[i.cpu() for i in init], grads=grads_log,
+                symmetric=opt._flat[0].symm_grad is not None)
+
+
+@pytest.mark.parametrize("clip", [None, 1.0])
+def test_fused_dp_adamw_matches_reference(clip):
+    _need(2)
+    from trlx_b200.ops import reference
+
+    res = run(_dp_optim_job, 2, args=(clip,))
+    assert all(r["symmetric"] for r in res), "the NVLink symmetric-memory path must be the one that ran"
+    for a, b in zip(res[0]["params"], res[1]["params"]):
+        assert torch.equal(a, b)  # all-gather leaves identical replicas
+    w = [i.clone() for i in res[0]["init"]]
+    m, v = [torch.zeros_like(x) for x in w], [torch.zeros_like(x) for x in w]
+    for step in range(3):
+        g = [(res[0]["grads"][step][i].to(torch.bfloat16).float() + res[1]["grads"][step][i].to(torch.bfloat16).float()) / 2 for i in range(len(w))]
+        if clip:
+            norm = torch.sqrt(sum((x ** 2).sum() for x in g))
+            coef = min(1.0, clip / (norm.item() + 1e-6))
+            g = [x * coef for x in g]
+        for i in range(len(w)):
+            reference.adamw_step(w[i], g[i], m[i], v[i], step + 1, 1e-2, 0.9, 0.95, 1e-8, 0.01)
+    for got, ref in zip(res[0]["params"], w):
+        torch.testing.assert_close(got, ref, atol=2e-2, rtol=2e-2)
+
+
+# ---- fused TP GEMM <-> collective kernels -------------------------------------------------------------------------------------
+def _tp_kernels_job(rank, world):
+    from trlx_b200.parallel.fused_tp import FusedTP
+
+    fused = FusedTP(None, rank, world, torch.device("cuda", rank))
+    torch.manual_seed(1)
+    m, K, N = 256, 512, 384  # rows per rank, hidden, out
+    x_all = (torch.randn(world, m, K, device="cuda") * 0.5).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda") * K ** -0.5).to(torch.bfloat16)
+    b = torch.randn(N, device="cuda").to(torch.bfloat16)
+    out = fused.allgather_gemm(x_all[rank].contiguous(), w, b, "gelu_new")
+    out2 = fused.allgather_gemm(x_all[rank].contiguous(), w, b, "gelu_new")  # buffer reuse
+    ref = torch.nn.functional.gelu(x_all.reshape(world * m, K).float() @ w.float().t() + b.float(), approximate="tanh")
+    # row-parallel: K split over ranks
+    M = world * 128
+    xs = (torch.randn(M, K, device="cuda") * 0.5).to(torch.bfloat16)
+    ws = (torch.randn(N, K, device="cuda") * K ** -0.5).to(torch.bfloat16)
+    kl = K // world
+    res = (torch.randn(M // world, N, device="cuda")).to(torch.bfloat16)
+    y = fused.gemm_reduce_scatter(xs[:, rank * kl:(rank + 1) * kl].contiguous(), ws[:, rank * kl:(rank + 1) * kl].contiguous(),
+                                  b if rank == 0 else None, res)
+    full = xs.float() @ ws.float().t() + b.float()
+    rows = M // world
+    ref_y = full[rank * rows:(rank + 1) * rows] + res.float()
+    return dict(ag_err=(out.float() - ref).abs().max().item(), ag2_err=(out2.float() - ref).abs().max().item(),
+                rs_err=(y.float() - ref_y).abs().max().item())
+
+
+def test_fused_tp_gemm_collectives():
+    _need(2)
+    for r in run(_tp_kernels_job, 2):
+        assert r["ag_err"] < 5e-2 and r["ag2_err"] < 5e-2 and r["rs_err"] < 6e-2, r
+
+
+# ---- TP/SP model on GPUs with the fused kernels ------------------------------------------------------------------------------------
+def _tp_model_job(rank, world, sp):
+    from trlx_b200.models.modeling_ppo import AutoModelForCausalLMWithHydraValueHead
+    from trlx_b200.parallel.tensor_parallel import apply_tensor_parallel
+
+    cfg = dict(model_type="gpt_neox", vocab_size=512, hidden_size=256, num_hidden_layers=3, num_attention_heads=4,
+               intermediate_size=1024, max_position_embeddings=512)
+    torch.manual_seed(0)
+    model = AutoModelForCausalLMWithHydraValueHead.from_config(cfg, num_layers_unfrozen=1).cuda().to(torch.bfloat16).eval()
+    torch.manual_seed(1)
+    ids = torch.randint(0, 512, (2, 256), device="cuda")
+    mask = torch.ones_like(ids)
+    with torch.no_grad():
+        ref = model(ids, mask, return_dict=True).logits.float()
+    tp = apply_tensor_parallel(model, None, rank, world, sequence_parallel=sp)
+    out = model(ids, mask, return_dict=True)
+    out.logits.float().pow(2).mean().backward()
+    g = model.base_model.transformer.h[-1].mlp.down.weight.grad
+    return dict(err=(out.logits.float() - ref).abs().max().item(), scale=ref.abs().max().item(), fused=tp.fused is not None,
+                grad_finite=bool(torch.isfinite(g).all()))
+
+
+@pytest.mark.parametrize("sp", [False, True])
+def test_tensor_parallel_model_on_gpus(sp):
+    _need(2)
+    for r in run(_tp_model_job, 2, args=(sp,)):
+        assert r["err"] < 0.05 * max(r["scale"], 1.0) and r["grad_finite"], r
+        assert r["fused"] == sp

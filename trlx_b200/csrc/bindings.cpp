@@ -33,21 +33,30 @@ int b200_paged_kv_write(const void*, const void*, void*, void*, const int*, cons
 int b200_logprob_from_logits(const void*, const long long*, float*, float*, long long, int, long long, int, cudaStream_t);
 int b200_logprob_backward_inplace(void*, const long long*, const float*, const float*, long long, int, long long, int,
                                   cudaStream_t);
-int b200_gae(const float*, const float*, float*, float*, int, int, int, long long, float, float, double*, cudaStream_t);
-int b200_whiten(float*, int, int, long long, const double*, int, cudaStream_t);
+int b200_gae(const float*, const float*, float*, float*, int, int, int, const int*, long long, float, float, double*,
+             cudaStream_t);
+int b200_whiten(float*, int, int, const int*, long long, const double*, int, cudaStream_t);
 int b200_ppo_loss_num_outputs();
 int b200_ppo_loss_workspace_floats(int);
 int b200_ppo_loss(const float*, const float*, const float*, const float*, const float*, const float*, const float*, int, float,
-                  float, float, float*, float*, float*, int, float*, cudaStream_t);
+                  float, float, float*, float*, float*, int, float*, int, const int*, cudaStream_t);
 int b200_kl_rewards(const float*, const float*, const int*, const float*, int, int, float, float*, double*, cudaStream_t);
 int b200_adamw_flat(void*, float*, const void*, int, float*, float*, long long, float, float, float, float, int, const float*,
                     cudaStream_t);
 int b200_sqnorm(const void*, int, long long, double*, cudaStream_t);
 int b200_clip_coef(const double*, float, float*, float*, cudaStream_t);
-int b200_signal_barrier(void* const*, int, int, unsigned int, cudaStream_t);
+int b200_signal_barrier(void* const*, int, int, unsigned int*, cudaStream_t);
 int b200_rs_adamw_ag(void* const*, void* const*, int, long long, long long, float*, float*, float*, float*, int, float, float,
                      float, float, int, const float*, double*, cudaStream_t);
 int b200_lerp_bf16(void*, const void*, long long, float, cudaStream_t);
+void b200_set_pdl(int);
+int b200_get_pdl();
+int b200_gemm_allgather_bf16(void* const*, int, const void*, void*, int, int, int, long long, long long, long long, const void*,
+                             int, cudaStream_t);
+int b200_gemm_reduce_scatter_bf16(const void*, const void*, float* const*, int, int, int, int, long long, long long, long long,
+                                  const void*, cudaStream_t);
+int b200_rs_finalize(const float*, const void*, const void*, void*, long long, int, long long, long long, long long,
+                     cudaStream_t);
 }
 
 namespace {
@@ -248,7 +257,9 @@ void logprob_backward_inplace(Tensor& logits, const Tensor& labels, const Tensor
 
 // returns (advantages, returns, stats[3] double = (count, sum, sumsq)); whitening applied unless `stats_only`
 std::vector<Tensor> gae(const Tensor& values, const Tensor& rewards, int64_t width, double gamma, double lam, bool do_whiten,
-                        bool unbiased) {
+                        bool unbiased, const OptTensor& width_tensor) {
+  const int* wp = nullptr;
+  if (width_tensor.has_value()) { TORCH_CHECK(width_tensor->scalar_type() == at::kInt && width_tensor->is_cuda()); wp = width_tensor->data_ptr<int>(); }
   CHECK_F32(values); CHECK_F32(rewards);
   TORCH_CHECK(values.dim() == 2 && values.is_contiguous() && rewards.is_contiguous() && values.sizes() == rewards.sizes());
   c10::cuda::CUDAGuard guard(values.device());
@@ -256,18 +267,19 @@ std::vector<Tensor> gae(const Tensor& values, const Tensor& rewards, int64_t wid
   Tensor adv = torch::empty_like(values), ret = torch::empty_like(values);
   Tensor stats = torch::zeros({3}, values.options().dtype(at::kDouble));
   check(b200_gae(values.data_ptr<float>(), rewards.data_ptr<float>(), adv.data_ptr<float>(), ret.data_ptr<float>(), B, R,
-                 (int)width, R, (float)gamma, (float)lam, stats.data_ptr<double>(), stream()),
+                 (int)width, wp, R, (float)gamma, (float)lam, stats.data_ptr<double>(), stream()),
         "gae");
   if (do_whiten)
-    check(b200_whiten(adv.data_ptr<float>(), B, (int)width, R, stats.data_ptr<double>(), unbiased ? 1 : 0, stream()), "whiten");
+    check(b200_whiten(adv.data_ptr<float>(), B, (int)width, wp, R, stats.data_ptr<double>(), unbiased ? 1 : 0, stream()), "whiten");
   return {adv, ret, stats};
 }
 
-void whiten_(Tensor& adv, int64_t width, const Tensor& stats, bool unbiased) {
+void whiten_(Tensor& adv, int64_t width, const Tensor& stats, bool unbiased, const OptTensor& width_tensor) {
   CHECK_F32(adv);
   TORCH_CHECK(stats.scalar_type() == at::kDouble);
   c10::cuda::CUDAGuard guard(adv.device());
-  check(b200_whiten(adv.data_ptr<float>(), (int)adv.size(0), (int)width, adv.size(1), stats.data_ptr<double>(),
+  const int* wp = width_tensor.has_value() ? width_tensor->data_ptr<int>() : nullptr;
+  check(b200_whiten(adv.data_ptr<float>(), (int)adv.size(0), (int)width, wp, adv.size(1), stats.data_ptr<double>(),
                     unbiased ? 1 : 0, stream()),
         "whiten");
 }
@@ -275,7 +287,7 @@ void whiten_(Tensor& adv, int64_t width, const Tensor& stats, bool unbiased) {
 // returns (out[O_COUNT], dlogprobs, dvalues)
 std::vector<Tensor> ppo_loss(const Tensor& logprobs, const Tensor& values, const Tensor& old_logprobs, const Tensor& old_values,
                              const Tensor& adv, const Tensor& ret, const Tensor& mask, double clip, double clip_v,
-                             double vf_coef) {
+                             double vf_coef, const OptTensor& width_tensor) {
   for (const Tensor* t : {&logprobs, &values, &old_logprobs, &old_values, &adv, &ret, &mask}) {
     TORCH_CHECK(t->is_cuda() && t->scalar_type() == at::kFloat && t->is_contiguous() && t->numel() == logprobs.numel(),
                 "ppo_loss: all inputs must be contiguous fp32 CUDA tensors of equal size");
@@ -292,7 +304,8 @@ std::vector<Tensor> ppo_loss(const Tensor& logprobs, const Tensor& values, const
   check(b200_ppo_loss(logprobs.data_ptr<float>(), values.data_ptr<float>(), old_logprobs.data_ptr<float>(),
                       old_values.data_ptr<float>(), adv.data_ptr<float>(), ret.data_ptr<float>(), mask.data_ptr<float>(),
                       total, (float)clip, (float)clip_v, (float)vf_coef, dlp.data_ptr<float>(), dv.data_ptr<float>(),
-                      ws.data_ptr<float>(), nblocks, out.data_ptr<float>(), stream()),
+                      ws.data_ptr<float>(), nblocks, out.data_ptr<float>(), (int)logprobs.size(0),
+                      width_tensor.has_value() ? width_tensor->data_ptr<int>() : nullptr, stream()),
         "ppo_loss");
   return {out, dlp, dv};
 }
@@ -335,10 +348,14 @@ void clip_coef_(const Tensor& sqsum, double max_norm, Tensor& hyper, const OptTe
         "clip_coef");
 }
 
-void signal_barrier(const std::vector<int64_t>& pads, int64_t rank, int64_t epoch) {
+// `epoch` is a 1-element int32 CUDA tensor owned by the caller (zero-initialised); every call increments it on the device
+void signal_barrier(const std::vector<int64_t>& pads, int64_t rank, Tensor& epoch) {
+  TORCH_CHECK(epoch.is_cuda() && epoch.scalar_type() == at::kInt && epoch.numel() == 1);
+  c10::cuda::CUDAGuard guard(epoch.device());
   std::vector<void*> p(pads.size());
   for (size_t i = 0; i < pads.size(); ++i) p[i] = reinterpret_cast<void*>(pads[i]);
-  check(b200_signal_barrier(p.data(), (int)rank, (int)pads.size(), (unsigned)epoch, stream()), "signal_barrier");
+  check(b200_signal_barrier(p.data(), (int)rank, (int)pads.size(), reinterpret_cast<unsigned int*>(epoch.data_ptr<int>()), stream()),
+        "signal_barrier");
 }
 
 void rs_adamw_ag(const std::vector<int64_t>& grads, const std::vector<int64_t>& params, int64_t lo, int64_t n, Tensor& master,
@@ -360,6 +377,49 @@ void lerp_(Tensor& tgt, const Tensor& src, double alpha) {
   TORCH_CHECK(tgt.is_contiguous() && src.is_contiguous() && tgt.numel() == src.numel());
   c10::cuda::CUDAGuard guard(tgt.device());
   check(b200_lerp_bf16(tgt.data_ptr(), src.data_ptr(), tgt.numel(), (float)alpha, stream()), "lerp");
+}
+
+// out[M, N] = act(concat_r A_r . w^T + bias) where A_r ([M/world, K], row pitch lda) lives at device address peers[r]
+Tensor gemm_allgather(const std::vector<int64_t>& peers, int64_t rows_per_rank, int64_t K, int64_t lda, const Tensor& w,
+                      const OptTensor& bias, const std::string& act, const OptTensor& out_) {
+  CHECK_BF16(w);
+  TORCH_CHECK(w.dim() == 2 && w.size(1) == K && w.stride(1) == 1 && K % 8 == 0 && lda % 8 == 0);
+  c10::cuda::CUDAGuard guard(w.device());
+  const int64_t world = (int64_t)peers.size(), M = rows_per_rank * world, N = w.size(0);
+  std::vector<void*> p(world);
+  for (int64_t i = 0; i < world; ++i) p[i] = reinterpret_cast<void*>(peers[i]);
+  Tensor out = out_.has_value() ? *out_ : torch::empty({M, N}, w.options());
+  check(b200_gemm_allgather_bf16(p.data(), (int)world, w.data_ptr(), out.data_ptr(), (int)M, (int)N, (int)K, lda, w.stride(0),
+                                 out.stride(0), optptr(bias), act_code(act), stream()),
+        "gemm_allgather");
+  return out;
+}
+
+// adds this rank's partial product x[M, K_local] . w[N, K_local]^T into the peers' fp32 accumulators (row-blocks by owner)
+void gemm_reduce_scatter(const Tensor& x, const Tensor& w, const std::vector<int64_t>& acc_peers, int64_t ldacc,
+                         const OptTensor& bias) {
+  CHECK_BF16(x); CHECK_BF16(w);
+  TORCH_CHECK(x.dim() == 2 && w.dim() == 2 && x.size(1) == w.size(1) && x.stride(1) == 1 && w.stride(1) == 1);
+  TORCH_CHECK(x.size(1) % 8 == 0 && x.stride(0) % 8 == 0 && w.stride(0) % 8 == 0);
+  c10::cuda::CUDAGuard guard(x.device());
+  std::vector<float*> p(acc_peers.size());
+  for (size_t i = 0; i < acc_peers.size(); ++i) p[i] = reinterpret_cast<float*>(acc_peers[i]);
+  check(b200_gemm_reduce_scatter_bf16(x.data_ptr(), w.data_ptr(), p.data(), (int)p.size(), (int)x.size(0), (int)w.size(0),
+                                      (int)x.size(1), x.stride(0), w.stride(0), ldacc, optptr(bias), stream()),
+        "gemm_reduce_scatter");
+}
+
+Tensor rs_finalize(const Tensor& acc, const OptTensor& bias, const OptTensor& residual, const OptTensor& out_) {
+  CHECK_F32(acc);
+  TORCH_CHECK(acc.dim() == 2 && acc.stride(1) == 1);
+  c10::cuda::CUDAGuard guard(acc.device());
+  Tensor out = out_.has_value() ? *out_ : torch::empty({acc.size(0), acc.size(1)}, acc.options().dtype(at::kBFloat16));
+  long long ldr = 0;
+  if (residual.has_value()) { CHECK_BF16(*residual); TORCH_CHECK(residual->stride(1) == 1); ldr = residual->stride(0); }
+  check(b200_rs_finalize(acc.data_ptr<float>(), optptr(bias), optptr(residual), out.data_ptr(), acc.size(0), (int)acc.size(1),
+                         acc.stride(0), ldr, out.stride(0), stream()),
+        "rs_finalize");
+  return out;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -440,9 +500,12 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("logprob_from_logits", &logprob_from_logits);
   m.def("logprob_backward_inplace", &logprob_backward_inplace);
   m.def("gae", &gae, py::arg("values"), py::arg("rewards"), py::arg("width"), py::arg("gamma"), py::arg("lam"),
-        py::arg("whiten") = true, py::arg("unbiased") = true);
-  m.def("whiten_", &whiten_);
-  m.def("ppo_loss", &ppo_loss);
+        py::arg("whiten") = true, py::arg("unbiased") = true, py::arg("width_tensor") = py::none());
+  m.def("whiten_", &whiten_, py::arg("adv"), py::arg("width"), py::arg("stats"), py::arg("unbiased"),
+        py::arg("width_tensor") = py::none());
+  m.def("ppo_loss", &ppo_loss, py::arg("logprobs"), py::arg("values"), py::arg("old_logprobs"), py::arg("old_values"),
+        py::arg("adv"), py::arg("ret"), py::arg("mask"), py::arg("clip"), py::arg("clip_v"), py::arg("vf_coef"),
+        py::arg("width_tensor") = py::none());
   m.def("kl_rewards", &kl_rewards);
   m.def("adamw_flat", &adamw_flat);
   m.def("sqnorm_", &sqnorm_);
@@ -450,7 +513,15 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("signal_barrier", &signal_barrier);
   m.def("rs_adamw_ag", &rs_adamw_ag);
   m.def("lerp_", &lerp_);
+  m.def("gemm_allgather", &gemm_allgather, py::arg("peers"), py::arg("rows_per_rank"), py::arg("K"), py::arg("lda"),
+        py::arg("w"), py::arg("bias") = py::none(), py::arg("act") = "none", py::arg("out") = py::none());
+  m.def("gemm_reduce_scatter", &gemm_reduce_scatter, py::arg("x"), py::arg("w"), py::arg("acc_peers"), py::arg("ldacc"),
+        py::arg("bias") = py::none());
+  m.def("rs_finalize", &rs_finalize, py::arg("acc"), py::arg("bias") = py::none(), py::arg("residual") = py::none(),
+        py::arg("out") = py::none());
   m.def("ppo_loss_num_outputs", [] { return b200_ppo_loss_num_outputs(); });
+  m.def("set_pdl", [](bool on) { b200_set_pdl(on ? 1 : 0); }, "enable/disable programmatic dependent launch for the kernels");
+  m.def("get_pdl", [] { return b200_get_pdl() != 0; });
   py::class_<PagedKVAllocator>(m, "PagedKVAllocator")
       .def(py::init<int64_t, int64_t>())
       .def("reserve", &PagedKVAllocator::reserve)

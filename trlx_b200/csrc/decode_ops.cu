@@ -12,6 +12,8 @@ template <bool RMS>
 __global__ void __launch_bounds__(128) norm_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
                                                    const __nv_bfloat16* __restrict__ b, __nv_bfloat16* __restrict__ y,
                                                    int H, long long ldx, long long ldy, float eps) {
+  griddep_wait();
+  griddep_launch();
   const int row = blockIdx.x;
   const __nv_bfloat16* xr = x + (size_t)row * ldx;
   __nv_bfloat16* yr = y + (size_t)row * ldy;
@@ -64,6 +66,8 @@ __global__ void __launch_bounds__(128) norm_kernel(const __nv_bfloat16* __restri
 __global__ void embed_kernel(const long long* __restrict__ tokens, const int* __restrict__ positions,
                              const __nv_bfloat16* __restrict__ wte, const __nv_bfloat16* __restrict__ wpe, int pos_offset,
                              __nv_bfloat16* __restrict__ x, int H) {
+  griddep_wait();
+  griddep_launch();
   const int b = blockIdx.x;
   const __nv_bfloat16* te = wte + (size_t)tokens[b] * H;
   const __nv_bfloat16* pe = wpe ? wpe + (size_t)(positions[b] + pos_offset) * H : nullptr;
@@ -92,6 +96,8 @@ decode_attn_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restr
                    const int* __restrict__ block_table, const int* __restrict__ seq_lens, const int* __restrict__ positions,
                    __nv_bfloat16* __restrict__ out, int nq, int nkv, int d, int page_size, int max_pages, float scale,
                    int rot_dim, float rot_base, int rot_interleaved, const float* __restrict__ alibi_slopes, int window) {
+  griddep_wait();
+  griddep_launch();
   const int b = blockIdx.x, h = blockIdx.y;
   const int group = nq / nkv, kvh = h / group;
   const int len = seq_lens[b];
@@ -237,6 +243,8 @@ decode_attn_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restr
 // out[m] = dot(x[m,:], w) + bias    (the N=1 projection of the value MLP; fp32 result)
 __global__ void rowdot_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
                               const __nv_bfloat16* __restrict__ bias, float* __restrict__ out, int M, int K, long long ldx) {
+  griddep_wait();
+  griddep_launch();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -267,6 +275,8 @@ __global__ void decode_step_kernel(const long long* __restrict__ sampled, const 
                                    float* __restrict__ values_out, int* __restrict__ finished, int* __restrict__ resp_lens,
                                    int* __restrict__ seq_lens, int* __restrict__ positions, long long* __restrict__ next_tokens,
                                    int* __restrict__ n_running) {
+  griddep_wait();
+  griddep_launch();
   const int step = *step_ptr;
   int retired = 0;
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
@@ -330,20 +340,17 @@ extern "C" int b200_norm_bf16(const void* x, const void* w, const void* b, void*
                               long long ldy, float eps, int rms, cudaStream_t stream) {
   if (rows <= 0) return 0;
   if (rms)
-    norm_kernel<true><<<rows, 128, 0, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w, nullptr,
-                                                (__nv_bfloat16*)y, H, ldx, ldy, eps);
-  else
-    norm_kernel<false><<<rows, 128, 0, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w, (const __nv_bfloat16*)b,
-                                                 (__nv_bfloat16*)y, H, ldx, ldy, eps);
-  return (int)cudaGetLastError();
+    return (int)launch_kernel(norm_kernel<true>, dim3(rows), dim3(128), 0, stream, (const __nv_bfloat16*)x,
+                              (const __nv_bfloat16*)w, (const __nv_bfloat16*)nullptr, (__nv_bfloat16*)y, H, ldx, ldy, eps);
+  return (int)launch_kernel(norm_kernel<false>, dim3(rows), dim3(128), 0, stream, (const __nv_bfloat16*)x,
+                            (const __nv_bfloat16*)w, (const __nv_bfloat16*)b, (__nv_bfloat16*)y, H, ldx, ldy, eps);
 }
 
 extern "C" int b200_embed_bf16(const long long* tokens, const int* positions, const void* wte, const void* wpe,
                                int pos_offset, void* x, int B, int H, cudaStream_t stream) {
   if (B <= 0) return 0;
-  embed_kernel<<<B, 128, 0, stream>>>(tokens, positions, (const __nv_bfloat16*)wte, (const __nv_bfloat16*)wpe, pos_offset,
-                                      (__nv_bfloat16*)x, H);
-  return (int)cudaGetLastError();
+  return (int)launch_kernel(embed_kernel, dim3(B), dim3(128), 0, stream, tokens, positions, (const __nv_bfloat16*)wte,
+                            (const __nv_bfloat16*)wpe, pos_offset, (__nv_bfloat16*)x, H);
 }
 
 extern "C" int b200_decode_attention_bf16(const void* qkv, void* kcache, void* vcache, const int* block_table,
@@ -353,24 +360,22 @@ extern "C" int b200_decode_attention_bf16(const void* qkv, void* kcache, void* v
   if (B <= 0) return 0;
   if (d % 8 != 0 || d > 256) return -2;
   dim3 grid(B, nq);
-#define LAUNCH(MD)                                                                                                       \
-  decode_attn_kernel<MD><<<grid, 128, 0, stream>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)kcache, (__nv_bfloat16*)vcache, \
-                                                   block_table, seq_lens, positions, (__nv_bfloat16*)out, nq, nkv, d,      \
-                                                   page_size, max_pages, scale, rot_dim, rot_base, rot_interleaved,        \
-                                                   alibi_slopes, window)
-  if (d <= 64) LAUNCH(64);
-  else if (d <= 128) LAUNCH(128);
-  else LAUNCH(256);
+#define LAUNCH(MD)                                                                                                        \
+  return (int)launch_kernel(decode_attn_kernel<MD>, grid, dim3(128), 0, stream, (const __nv_bfloat16*)qkv,                 \
+                            (__nv_bfloat16*)kcache, (__nv_bfloat16*)vcache, block_table, seq_lens, positions,               \
+                            (__nv_bfloat16*)out, nq, nkv, d, page_size, max_pages, scale, rot_dim, rot_base, rot_interleaved, \
+                            alibi_slopes, window)
+  if (d <= 64) { LAUNCH(64); }
+  else if (d <= 128) { LAUNCH(128); }
+  else { LAUNCH(256); }
 #undef LAUNCH
-  return (int)cudaGetLastError();
 }
 
 extern "C" int b200_rowdot_bf16(const void* x, const void* w, const void* bias, float* out, int M, int K, long long ldx,
                                 cudaStream_t stream) {
   if (M <= 0) return 0;
-  rowdot_kernel<<<(M + 3) / 4, 128, 0, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w, (const __nv_bfloat16*)bias,
-                                                 out, M, K, ldx);
-  return (int)cudaGetLastError();
+  return (int)launch_kernel(rowdot_kernel, dim3((M + 3) / 4), dim3(128), 0, stream, (const __nv_bfloat16*)x,
+                            (const __nv_bfloat16*)w, (const __nv_bfloat16*)bias, out, M, K, ldx);
 }
 
 extern "C" int b200_decode_step(const long long* sampled, const float* lp, const float* ref_lp, const float* value,
@@ -378,10 +383,9 @@ extern "C" int b200_decode_step(const long long* sampled, const float* lp, const
                                 float* logprobs_out, float* ref_logprobs_out, float* values_out, int* finished, int* resp_lens,
                                 int* seq_lens, int* positions, long long* next_tokens, int* n_running, cudaStream_t stream) {
   if (B <= 0) return 0;
-  decode_step_kernel<<<1, 256, 0, stream>>>(sampled, lp, ref_lp, value, step_ptr, max_new, B, eos_id, pad_id, tokens_out,
-                                            logprobs_out, ref_logprobs_out, values_out, finished, resp_lens, seq_lens,
-                                            positions, next_tokens, n_running);
-  return (int)cudaGetLastError();
+  return (int)launch_kernel(decode_step_kernel, dim3(1), dim3(256), 0, stream, sampled, lp, ref_lp, value, step_ptr, max_new,
+                            B, eos_id, pad_id, tokens_out, logprobs_out, ref_logprobs_out, values_out, finished, resp_lens,
+                            seq_lens, positions, next_tokens, n_running);
 }
 
 // k / v: [B, T, nkv*d] views with arbitrary batch / time strides (elements); nkv*d % 8 == 0.

@@ -41,6 +41,18 @@ struct StoreEpilogue {
   int out_f32;
 };
 
+constexpr int MAX_TP = 8;
+// A-operand tensor maps, one per tensor-parallel peer (all-gather -> GEMM reads row-block r of A from peer r's HBM)
+struct MapArray { CUtensorMap m[MAX_TP]; };
+
+// GEMM -> reduce-scatter epilogue: rows [r*rows_per_rank, (r+1)*rows_per_rank) of the partial product are added
+// (NVLink red.add.f32) into peer r's fp32 accumulation buffer [rows_per_rank, ldacc].
+struct ReduceScatterEpilogue {
+  float* acc[MAX_TP];
+  long long ldacc;
+  int rows_per_rank;
+};
+
 struct LMHeadEpilogue {
   const __nv_bfloat16* bias;   // [N] or null
   const long long* labels;     // [M] or null  (label < 0 -> ignored)
@@ -79,10 +91,14 @@ __device__ __forceinline__ float uniform01(unsigned long long seed, unsigned int
   return ((float)(z >> 40) + 0.5f) * (1.0f / 16777216.0f);
 }
 
-template <int BN, int EPI>  // EPI: 0 = store, 1 = lm-head
+__device__ __forceinline__ void red_add_v4_f32(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int BN, int EPI>  // EPI: 0 = store, 1 = lm-head, 2 = reduce-scatter into peer accumulators
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M, int N, int K,
-               int stages, StoreEpilogue se, LMHeadEpilogue le) {
+gemm_tn_kernel(const __grid_constant__ MapArray maps_a, const __grid_constant__ CUtensorMap map_b, int M, int N, int K,
+               int stages, int rows_per_map, StoreEpilogue se, LMHeadEpilogue le, ReduceScatterEpilogue re) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr uint32_t A_BYTES = BM * BK * 2;
   constexpr uint32_t B_BYTES = BN * BK * 2;
@@ -99,9 +115,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
   const int nkb = (K + BK - 1) / BK;
+  // which peer's copy of A holds this M-tile (all-gather -> GEMM); plain GEMMs have a single map
+  const int a_map = m0 / rows_per_map;
+  const int a_row = m0 - a_map * rows_per_map;
+  const CUtensorMap* map_a_ptr = &maps_a.m[a_map];
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(map_a_ptr);
     tma_prefetch_desc(&map_b);
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -118,6 +138,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped with the tail of the previous
+  // kernel; from here on we touch memory it produced.  Let our own successor start its prologue right away.
+  griddep_wait();
+  griddep_launch();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -128,7 +152,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         uint8_t* a_dst = smem + (size_t)s * STAGE_BYTES;
         uint8_t* b_dst = a_dst + A_BYTES;
         mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
-        tma_load_2d(a_dst, &map_a, &full_bar[s], kb * BK, m0);
+        tma_load_2d(a_dst, map_a_ptr, &full_bar[s], kb * BK, a_row);
         tma_load_2d(b_dst, &map_b, &full_bar[s], kb * BK, n0);
       }
     }
@@ -216,6 +240,29 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
         }
       }
+    } else if constexpr (EPI == 2) {
+      const int owner = row_ok ? row / re.rows_per_rank : 0;
+      float* dst_row = row_ok ? re.acc[owner] + (size_t)(row - owner * re.rows_per_rank) * re.ldacc : nullptr;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr_row + c, r);
+        tmem_ld_wait();
+        const int col0 = n0 + c;
+        if (!row_ok || col0 >= N) continue;
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          v[j] = __uint_as_float(r[j]);
+          if (se.bias && col0 + j < N) v[j] += __bfloat162float(se.bias[col0 + j]);  // only the rank that owns the bias passes it
+        }
+        if (col0 + 16 <= N && (re.ldacc & 3) == 0) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) red_add_v4_f32(dst_row + col0 + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+          for (int j = 0; j < 16 && col0 + j < N; ++j) atomicAdd(dst_row + col0 + j, v[j]);
+        }
+      }
     } else {
       const long long label = (row_ok && le.labels) ? le.labels[row] : -1;
       float mx = -INFINITY, sum = 0.f;
@@ -286,6 +333,8 @@ __global__ void lmhead_reduce_kernel(const float* __restrict__ part_max, const f
                                      const int* __restrict__ samp_idx, int M, int n_tiles, float* __restrict__ lse_out,
                                      float* __restrict__ logprob_out, long long* __restrict__ token_out,
                                      float* __restrict__ token_logprob_out) {
+  griddep_wait();
+  griddep_launch();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -380,8 +429,9 @@ static int pick_bn(int M, int N) {
 }
 
 template <int BN, int EPI>
-static cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& mb, int M, int N, int K, const StoreEpilogue& se,
-                          const LMHeadEpilogue& le, cudaStream_t stream) {
+static cudaError_t launch(const MapArray& ma, const CUtensorMap& mb, int M, int N, int K, int rows_per_map,
+                          const StoreEpilogue& se, const LMHeadEpilogue& le, const ReduceScatterEpilogue& re,
+                          cudaStream_t stream) {
   constexpr int stage_bytes = BM * BK * 2 + BN * BK * 2;
   const int nkb = (K + BK - 1) / BK;
   int stages = (200 * 1024) / stage_bytes;
@@ -396,13 +446,19 @@ static cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& mb, int M, i
     configured = true;
   }
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
-  kern<<<grid, NUM_THREADS, smem, stream>>>(ma, mb, M, N, K, stages, se, le);
-  return cudaGetLastError();
+  return launch_kernel(kern, grid, dim3(NUM_THREADS), smem, stream, ma, mb, M, N, K, stages, rows_per_map, se, le, re);
 }
+
+static bool g_pdl = true;
+bool pdl_enabled() { return g_pdl; }
+void set_pdl_enabled(bool on) { g_pdl = on; }
 
 }  // namespace b200
 
 using namespace b200;
+
+extern "C" void b200_set_pdl(int on) { set_pdl_enabled(on != 0); }
+extern "C" int b200_get_pdl() { return pdl_enabled() ? 1 : 0; }
 
 // act: 0 none, 1 gelu_tanh, 2 gelu_erf, 3 relu, 4 silu.  Requirements: K % 8 == 0, lda/ldb % 8 == 0, 16B-aligned A/B.
 extern "C" int b200_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K, long long lda, long long ldb,
@@ -410,17 +466,98 @@ extern "C" int b200_gemm_bf16(const void* A, const void* B, void* out, int M, in
                               float alpha, int act, int out_f32, int force_bn, cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   const int bn = force_bn ? force_bn : pick_bn(M, N);
-  CUtensorMap ma, mb;
-  if (!make_map(&ma, A, M, K, lda, BM) || !make_map(&mb, B, N, K, ldb, bn)) return -1;
+  MapArray ma{};
+  CUtensorMap mb;
+  if (!make_map(&ma.m[0], A, M, K, lda, BM) || !make_map(&mb, B, N, K, ldb, bn)) return -1;
   StoreEpilogue se{out, (const __nv_bfloat16*)bias, (const __nv_bfloat16*)residual, col_scale, ldo, ldr, alpha, act, out_f32};
   LMHeadEpilogue le{};
+  ReduceScatterEpilogue re{};
+  const int rpm = 1 << 30;
   cudaError_t e;
   switch (bn) {
-    case 128: e = launch<128, 0>(ma, mb, M, N, K, se, le, stream); break;
-    case 64: e = launch<64, 0>(ma, mb, M, N, K, se, le, stream); break;
-    default: e = launch<32, 0>(ma, mb, M, N, K, se, le, stream); break;
+    case 128: e = launch<128, 0>(ma, mb, M, N, K, rpm, se, le, re, stream); break;
+    case 64: e = launch<64, 0>(ma, mb, M, N, K, rpm, se, le, re, stream); break;
+    default: e = launch<32, 0>(ma, mb, M, N, K, rpm, se, le, re, stream); break;
   }
   return (int)e;
+}
+
+// all-gather -> GEMM: A is sharded by rows over `world` peers (A_peers[r] = peer r's [M/world, K] shard, any of them may
+// be a remote NVLink-mapped pointer); out[M, N] = act(concat_r(A_r) . B^T + bias).  rows_per_rank % 128 == 0.
+extern "C" int b200_gemm_allgather_bf16(void* const* A_peers, int world, const void* B, void* out, int M, int N, int K,
+                                        long long lda, long long ldb, long long ldo, const void* bias, int act,
+                                        cudaStream_t stream) {
+  if (world < 1 || world > MAX_TP || M % world) return -3;
+  const int rows = M / world;
+  if (rows % BM) return -3;
+  const int bn = pick_bn(M, N);
+  MapArray ma{};
+  CUtensorMap mb;
+  for (int r = 0; r < world; ++r)
+    if (!make_map(&ma.m[r], A_peers[r], rows, K, lda, BM)) return -1;
+  if (!make_map(&mb, B, N, K, ldb, bn)) return -1;
+  StoreEpilogue se{out, (const __nv_bfloat16*)bias, nullptr, nullptr, ldo, 0, 1.0f, act, 0};
+  LMHeadEpilogue le{};
+  ReduceScatterEpilogue re{};
+  cudaError_t e;
+  switch (bn) {
+    case 128: e = launch<128, 0>(ma, mb, M, N, K, rows, se, le, re, stream); break;
+    case 64: e = launch<64, 0>(ma, mb, M, N, K, rows, se, le, re, stream); break;
+    default: e = launch<32, 0>(ma, mb, M, N, K, rows, se, le, re, stream); break;
+  }
+  return (int)e;
+}
+
+// GEMM -> reduce-scatter: every rank computes its partial product A[M, K_local] . B[N, K_local]^T and adds rows
+// [r*M/world, (r+1)*M/world) into peer r's fp32 accumulator acc_peers[r] ([M/world, ldacc]) straight from the epilogue.
+extern "C" int b200_gemm_reduce_scatter_bf16(const void* A, const void* B, float* const* acc_peers, int world, int M, int N,
+                                             int K, long long lda, long long ldb, long long ldacc, const void* bias,
+                                             cudaStream_t stream) {
+  if (world < 1 || world > MAX_TP || M % world) return -3;
+  const int bn = pick_bn(M, N);
+  MapArray ma{};
+  CUtensorMap mb;
+  if (!make_map(&ma.m[0], A, M, K, lda, BM) || !make_map(&mb, B, N, K, ldb, bn)) return -1;
+  StoreEpilogue se{};
+  se.bias = (const __nv_bfloat16*)bias;
+  LMHeadEpilogue le{};
+  ReduceScatterEpilogue re{};
+  for (int r = 0; r < world; ++r) re.acc[r] = acc_peers[r];
+  re.ldacc = ldacc;
+  re.rows_per_rank = M / world;
+  const int rpm = 1 << 30;
+  cudaError_t e;
+  switch (bn) {
+    case 128: e = launch<128, 2>(ma, mb, M, N, K, rpm, se, le, re, stream); break;
+    case 64: e = launch<64, 2>(ma, mb, M, N, K, rpm, se, le, re, stream); break;
+    default: e = launch<32, 2>(ma, mb, M, N, K, rpm, se, le, re, stream); break;
+  }
+  return (int)e;
+}
+
+// fp32 accumulator -> bf16 (+ bias + residual) after the reduce-scatter has completed on every peer
+__global__ void rs_finalize_kernel(const float* __restrict__ acc, const __nv_bfloat16* __restrict__ bias,
+                                   const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ out, long long rows,
+                                   int N, long long ldacc, long long ldr, long long ldo) {
+  const long long total = rows * N;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / N;
+    const int c = (int)(i - r * N);
+    float v = acc[r * ldacc + c];
+    if (bias) v += __bfloat162float(bias[c]);
+    if (residual) v += __bfloat162float(residual[r * ldr + c]);
+    out[r * ldo + c] = __float2bfloat16(v);
+  }
+}
+
+extern "C" int b200_rs_finalize(const float* acc, const void* bias, const void* residual, void* out, long long rows, int N,
+                                long long ldacc, long long ldr, long long ldo, cudaStream_t stream) {
+  if (rows <= 0) return 0;
+  long long blocks = (rows * N + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  rs_finalize_kernel<<<(int)blocks, 256, 0, stream>>>(acc, (const __nv_bfloat16*)bias, (const __nv_bfloat16*)residual,
+                                                     (__nv_bfloat16*)out, rows, N, ldacc, ldr, ldo);
+  return (int)cudaGetLastError();
 }
 
 extern "C" int b200_lmhead_tiles(int N) { return (N + 127) / 128; }
@@ -437,8 +574,9 @@ extern "C" int b200_lmhead_bf16(const void* H, const void* W, int M, int N, int 
   if (M <= 0) return 0;
   constexpr int BN = 128;
   const int n_tiles = (N + BN - 1) / BN;
-  CUtensorMap ma, mb;
-  if (!make_map(&ma, H, M, K, ldh, BM) || !make_map(&mb, W, N, K, ldw, BN)) return -1;
+  MapArray ma{};
+  CUtensorMap mb;
+  if (!make_map(&ma.m[0], H, M, K, ldh, BM) || !make_map(&mb, W, N, K, ldw, BN)) return -1;
   const size_t mt = (size_t)M * n_tiles;
   LMHeadEpilogue le{};
   le.bias = (const __nv_bfloat16*)bias;
@@ -457,11 +595,12 @@ extern "C" int b200_lmhead_bf16(const void* H, const void* W, int M, int N, int 
   le.suppress_until = suppress_until;
   le.n_tiles = n_tiles;
   StoreEpilogue se{};
-  cudaError_t e = launch<BN, 1>(ma, mb, M, N, K, se, le, stream);
+  ReduceScatterEpilogue re{};
+  cudaError_t e = launch<BN, 1>(ma, mb, M, N, K, 1 << 30, se, le, re, stream);
   if (e != cudaSuccess) return (int)e;
   const int warps_per_block = 8;
-  lmhead_reduce_kernel<<<(M + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, stream>>>(
-      le.part_max, le.part_sum, le.label_logit, labels, le.samp_key, le.samp_logit, le.samp_idx, M, n_tiles, lse, logprob,
-      token, token_logprob);
-  return (int)cudaGetLastError();
+  return (int)launch_kernel(lmhead_reduce_kernel, dim3((M + warps_per_block - 1) / warps_per_block),
+                            dim3(warps_per_block * 32), 0, stream, (const float*)le.part_max, (const float*)le.part_sum,
+                            (const float*)le.label_logit, labels, (const float*)le.samp_key, (const float*)le.samp_logit,
+                            (const int*)le.samp_idx, M, n_tiles, lse, logprob, token, token_logprob);
 }

@@ -81,8 +81,13 @@ __global__ void clip_coef_kernel(const double* __restrict__ sqsum, float max_nor
 
 // System-scope barrier across `world` ranks: rank r bumps slot [r] in every peer's signal pad, then waits until all
 // slots of its own pad reach `epoch`.  One block, >= world threads.
-__global__ void signal_barrier_kernel(PeerPtrs pads, int rank, int world, uint32_t epoch) {
+__global__ void signal_barrier_kernel(PeerPtrs pads, int rank, int world, uint32_t* __restrict__ epoch_ptr) {
+  // the epoch lives on the device and is bumped by every launch, so the barrier can sit inside a replayed CUDA graph
+  // (all ranks launch barriers in the same order, which keeps their counters in lock-step)
   const int t = threadIdx.x;
+  const uint32_t epoch = *epoch_ptr + 1;
+  __syncthreads();
+  if (t == 0) *epoch_ptr = epoch;
   __threadfence_system();
   if (t < world) {
     uint32_t* remote = reinterpret_cast<uint32_t*>(pads.p[t]) + rank;
@@ -184,11 +189,11 @@ extern "C" int b200_clip_coef(const double* sqsum, float max_norm, float* hyper,
   return (int)cudaGetLastError();
 }
 
-extern "C" int b200_signal_barrier(void* const* pads, int rank, int world, unsigned int epoch, cudaStream_t stream) {
+extern "C" int b200_signal_barrier(void* const* pads, int rank, int world, unsigned int* epoch_ptr, cudaStream_t stream) {
   if (world > MAX_PEERS) return -3;
   PeerPtrs p{};
   for (int i = 0; i < world; ++i) p.p[i] = pads[i];
-  signal_barrier_kernel<<<1, 32, 0, stream>>>(p, rank, world, epoch);
+  signal_barrier_kernel<<<1, 32, 0, stream>>>(p, rank, world, epoch_ptr);
   return (int)cudaGetLastError();
 }
 

@@ -160,6 +160,12 @@ __device__ __forceinline__ int4 ld_relaxed_sys_v4(const int4* p) {
   return r;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// griddep_wait(): block until every kernel this one depends on has completed and flushed (no-op without PDL).
+// griddep_launch(): allow the next kernel in the stream to start its prologue while this one is still running.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- misc math
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -178,5 +184,25 @@ __device__ __forceinline__ float gelu_tanh(float x) {
 }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.7071067811865476f)); }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+
+// Host-side launcher: same as <<<>>> but optionally marks the launch as programmatically dependent on its predecessor.
+bool pdl_enabled();
+void set_pdl_enabled(bool on);
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 }  // namespace b200

@@ -81,8 +81,11 @@ __global__ void __launch_bounds__(256) logprob_bwd_kernel(T* __restrict__ logits
 // ----------------------------------------------------------------------------- GAE + whitening
 // stats (double[3]) accumulates (count, sum, sum of squares) of the advantages over [B, width].
 __global__ void gae_kernel(const float* __restrict__ values, const float* __restrict__ rewards, float* __restrict__ adv,
-                           float* __restrict__ ret, int B, int R, int width, long long ld, float gamma, float lam,
-                           double* __restrict__ stats) {
+                           float* __restrict__ ret, int B, int R, int width_arg, const int* __restrict__ width_ptr,
+                           long long ld, float gamma, float lam, double* __restrict__ stats) {
+  // the effective width may live on the device so that one captured CUDA graph serves batches of different widths
+  int width = width_ptr ? *width_ptr : width_arg;
+  if (width > R) width = R;
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   double s = 0.0, ss = 0.0;
   if (b < B) {
@@ -111,17 +114,21 @@ __global__ void gae_kernel(const float* __restrict__ values, const float* __rest
 }
 
 // adv <- (adv - mean) * rsqrt(var + 1e-8); var is unbiased when `unbiased` (single-process torch.var_mean semantics)
-__global__ void whiten_kernel(float* __restrict__ adv, int B, int width, long long ld, const double* __restrict__ stats,
-                              int unbiased) {
+__global__ void whiten_kernel(float* __restrict__ adv, int B, int width_arg, const int* __restrict__ width_ptr, long long ld,
+                              const double* __restrict__ stats, int unbiased) {
+  int width = width_ptr ? *width_ptr : width_arg;
+  if (width > (int)ld) width = (int)ld;
   const double n = stats[0];
   const double mean = stats[1] / n;
   double var = stats[2] / n - mean * mean;
   if (var < 0) var = 0;
   if (unbiased && n > 1) var = var * n / (n - 1);
   const float fm = (float)mean, fr = rsqrtf((float)var + 1e-8f);
+  const int span = width_ptr ? (int)ld : width;  // threads are laid out over the launch-time span
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B * width) return;
-  const int b = i / width, t = i % width;
+  if (i >= B * span) return;
+  const int b = i / span, t = i % span;
+  if (t >= width) return;
   float* p = adv + (size_t)b * ld + t;
   *p = (*p - fm) * fr;
 }
@@ -190,8 +197,10 @@ ppo_loss_partial_kernel(const float* __restrict__ logprobs, const float* __restr
 
 // single block: reduce partials, emit the stats vector and scale the gradients by 1/n (policy) and vf_coef/n (value)
 __global__ void __launch_bounds__(256)
-ppo_loss_finalize_kernel(const float* __restrict__ part, const float* __restrict__ ext, int nblocks, int total,
-                         float vf_coef, float* __restrict__ out) {
+ppo_loss_finalize_kernel(const float* __restrict__ part, const float* __restrict__ ext, int nblocks, int total_arg,
+                         int rows, const int* __restrict__ width_ptr, float vf_coef, float* __restrict__ out) {
+  // number of (row, position) cells the unmasked means (approx_kl, padding_percentage) are taken over
+  const int total = width_ptr ? rows * (*width_ptr) : total_arg;
   __shared__ double acc[A_COUNT];
   __shared__ float mm[6];
   if (threadIdx.x < A_COUNT) {
@@ -284,17 +293,17 @@ extern "C" int b200_logprob_backward_inplace(void* logits, const long long* labe
 
 // stats must be zeroed by the caller (double[3]).
 extern "C" int b200_gae(const float* values, const float* rewards, float* adv, float* ret, int B, int R, int width,
-                        long long ld, float gamma, float lam, double* stats, cudaStream_t stream) {
+                        const int* width_ptr, long long ld, float gamma, float lam, double* stats, cudaStream_t stream) {
   if (B <= 0) return 0;
-  gae_kernel<<<(B + 63) / 64, 64, 0, stream>>>(values, rewards, adv, ret, B, R, width, ld, gamma, lam, stats);
+  gae_kernel<<<(B + 63) / 64, 64, 0, stream>>>(values, rewards, adv, ret, B, R, width, width_ptr, ld, gamma, lam, stats);
   return (int)cudaGetLastError();
 }
 
-extern "C" int b200_whiten(float* adv, int B, int width, long long ld, const double* stats, int unbiased,
-                           cudaStream_t stream) {
-  const int total = B * width;
+extern "C" int b200_whiten(float* adv, int B, int width, const int* width_ptr, long long ld, const double* stats,
+                           int unbiased, cudaStream_t stream) {
+  const int total = B * (width_ptr ? (int)ld : width);  // launch for the widest case when the width is device-side
   if (total <= 0) return 0;
-  whiten_kernel<<<(total + 255) / 256, 256, 0, stream>>>(adv, B, width, ld, stats, unbiased);
+  whiten_kernel<<<(total + 255) / 256, 256, 0, stream>>>(adv, B, width, width_ptr, ld, stats, unbiased);
   return (int)cudaGetLastError();
 }
 
@@ -305,13 +314,13 @@ extern "C" int b200_ppo_loss_workspace_floats(int nblocks) { return nblocks * (A
 extern "C" int b200_ppo_loss(const float* logprobs, const float* values, const float* old_logprobs, const float* old_values,
                              const float* adv, const float* ret, const float* mask, int total, float clip, float clip_v,
                              float vf_coef, float* dlogprobs, float* dvalues, float* workspace, int nblocks, float* out,
-                             cudaStream_t stream) {
+                             int rows, const int* width_ptr, cudaStream_t stream) {
   if (total <= 0) return 0;
   float* part = workspace;
   float* ext = workspace + (size_t)nblocks * A_COUNT;
   ppo_loss_partial_kernel<<<nblocks, 256, 0, stream>>>(logprobs, values, old_logprobs, old_values, adv, ret, mask, total, clip,
                                                        clip_v, dlogprobs, dvalues, part, ext);
-  ppo_loss_finalize_kernel<<<1, 256, 0, stream>>>(part, ext, nblocks, total, vf_coef, out);
+  ppo_loss_finalize_kernel<<<1, 256, 0, stream>>>(part, ext, nblocks, total, rows, width_ptr, vf_coef, out);
   ppo_grad_scale_kernel<<<(total + 255) / 256, 256, 0, stream>>>(dlogprobs, dvalues, total, out, vf_coef);
   return (int)cudaGetLastError();
 }

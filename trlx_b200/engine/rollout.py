@@ -117,6 +117,11 @@ class RolloutEngine:
         t = self.gen.get("temperature", 1.0)
         self.temperature = float(t if t is not None else 1.0) if do_sample else 0.0
         self.launches_per_step = 0
+        import os
+
+        self.parallel_branches = os.environ.get("TRLX_B200_PARALLEL_BRANCHES", "1") == "1" and self.branch < len(self.layers)
+        self.side = torch.cuda.Stream(device=self.device) if self.parallel_branches else None
+        ops.C.set_pdl(os.environ.get("TRLX_B200_PDL", "1") == "1")
 
     # ------------------------------------------------------------------------------------------------ kernels per layer
     def _layer(self, x, W: _LayerW, kc, vc, st):
@@ -151,25 +156,42 @@ class RolloutEngine:
         if tr.emb_norm is not None:
             x = C.norm(x, tr.emb_norm.weight, tr.emb_norm.bias, spec.norm_eps, spec.norm == "rmsnorm")
         trunk_x = x
+        rms = spec.norm == "rmsnorm"
+        fh = model.frozen_head
+        L = len(self.layers)
+        main = torch.cuda.current_stream()
+        rf = None
         for i, W in enumerate(self.layers):
             if i == self.branch:
                 trunk_x = x
+                if self.parallel_branches:
+                    # the frozen reference branch only depends on the trunk activation: run it on a second stream so the
+                    # graph has two independent chains (policy top blocks || reference blocks) instead of one long one
+                    self.side.wait_stream(main)
+                    with torch.cuda.stream(self.side):
+                        y = trunk_x
+                        for j, Wr in enumerate(self.ref_layers):
+                            y = self._layer(y, Wr, st["kc"][L + j], st["vc"][L + j], st)
+                        rf = C.norm(y, fh.final_norm.weight, fh.final_norm.bias, spec.norm_eps, rms)
+                        if self.cache_trunk:
+                            st["trunk_decode"].index_copy_(1, st["step64"], trunk_x.unsqueeze(1))
             x = self._layer(x, W, st["kc"][i], st["vc"][i], st)
-        if self.cache_trunk:
+        if self.cache_trunk and not self.parallel_branches:
             st["trunk_decode"].index_copy_(1, st["step64"], trunk_x.unsqueeze(1))
-        rms = spec.norm == "rmsnorm"
         hf = C.norm(x, tr.ln_f.weight, tr.ln_f.bias, spec.norm_eps, rms)
         _, _, tok, tlp = C.lmhead(hf, lm.lm_head.weight, lm.lm_head.bias, None, True, self.temperature, self.seed,
                                   st["step"], self.eos if st["min_new"] > 0 else -1, st["min_new"], st["ws"], st["seed_dev"])
         vh = model.v_head
         h1 = C.gemm(hf, vh[0].weight, vh[0].bias, None, "relu")
         val = C.rowdot(h1, vh[2].weight.view(-1), vh[2].bias)
-        fh = model.frozen_head
-        y = trunk_x
-        L = len(self.layers)
-        for j, W in enumerate(self.ref_layers):
-            y = self._layer(y, W, st["kc"][L + j], st["vc"][L + j], st)
-        rf = C.norm(y, fh.final_norm.weight, fh.final_norm.bias, spec.norm_eps, rms)
+        if rf is None:
+            y = trunk_x
+            for j, W in enumerate(self.ref_layers):
+                y = self._layer(y, W, st["kc"][L + j], st["vc"][L + j], st)
+            rf = C.norm(y, fh.final_norm.weight, fh.final_norm.bias, spec.norm_eps, rms)
+        else:
+            main.wait_stream(self.side)
+            rf.record_stream(main)
         _, ref_lp, _, _ = C.lmhead(rf, fh.lm_head.weight, fh.lm_head.bias, tok, False, 1.0, 0, None, -1, 0, st["ws_ref"])
         C.decode_step(tok, tlp, ref_lp, val, st["step"], st["R"], self.eos, self.pad, st["tokens_out"], st["lp_out"],
                       st["ref_lp_out"], st["val_out"], st["finished"], st["resp_lens"], st["seq_lens"], st["positions"],

@@ -101,16 +101,18 @@ class PPOConfig(MethodConfig):
     num_value_layers_unfrozen: int = 0
 
     def get_advantages_and_returns(self, values: torch.Tensor, rewards: torch.Tensor, response_length: int,
-                                   use_whitening: Optional[bool] = True) -> Tuple[torch.Tensor, torch.Tensor]:
+                                   use_whitening: Optional[bool] = True, width_tensor: Optional[torch.Tensor] = None
+                                   ) -> Tuple[torch.Tensor, torch.Tensor]:
         """GAE: ``δ_t = r_t + γV_{t+1} − V_t``, ``A_t = δ_t + γλA_{t+1}``, ``returns = A + V``; advantages are whitened
         (globally across ranks) and detached.  Runs as one scan kernel + one whiten kernel on CUDA."""
-        return ops.gae_and_whiten(values, rewards, response_length, self.gamma, self.lam, bool(use_whitening))
+        return ops.gae_and_whiten(values, rewards, response_length, self.gamma, self.lam, bool(use_whitening),
+                                  width_tensor=width_tensor)
 
-    def loss(self, logprobs, values, old_logprobs, old_values, advantages, returns, mask):
+    def loss(self, logprobs, values, old_logprobs, old_values, advantages, returns, mask, width_tensor=None):
         """Clipped PPO objective → ``(loss, flat stats dict)``.  On CUDA the loss, its ~20 statistics and
         both gradients come out of one fused pass; stats stay on the device (no ``.item()`` syncs here)."""
         return ops.ppo_loss(logprobs, values, old_logprobs, old_values, advantages, returns, mask, self.cliprange,
-                            self.cliprange_value, self.vf_coef)
+                            self.cliprange_value, self.vf_coef, width_tensor=width_tensor)
 
 
 # ---- outputs ----------------------------------------------------------------------------------------------------------
@@ -190,6 +192,10 @@ class ModelBranch(nn.Module):
 
     def run_blocks(self, hidden_states, attention_mask=None, position_ids=None):
         B, T = hidden_states.shape[:2]
+        if attention_mask is not None:  # hidden states may be sequence-sharded (sequence parallelism)
+            T = attention_mask.shape[1]
+        elif position_ids is not None:
+            T = position_ids.shape[1]
         if position_ids is None:
             if attention_mask is not None:
                 position_ids = (attention_mask.long().cumsum(-1) - 1).clamp_min(0)

@@ -306,6 +306,11 @@ class CausalLM(nn.Module):
         B, T = ref.shape[0], ref.shape[1]
         device = ref.device
         past_len = past_key_values[0][0].shape[2] if past_key_values else 0
+        if hidden_in is not None:  # a (possibly sequence-sharded) cached activation: the true length comes from the mask
+            if attention_mask is not None:
+                T = attention_mask.shape[1] - past_len
+            elif position_ids is not None:
+                T = position_ids.shape[1]
         if position_ids is None:
             if attention_mask is not None:
                 position_ids = (attention_mask.long().cumsum(-1) - 1).clamp_min(0)[:, -T:]

@@ -145,7 +145,8 @@ def logprobs_from_logits(logits: torch.Tensor, labels: torch.Tensor) -> torch.Te
     return _LogprobsFromLogits.apply(logits, labels)
 
 
-def gae_and_whiten(values, rewards, width: int, gamma: float, lam: float, use_whitening: bool = True, group=None):
+def gae_and_whiten(values, rewards, width: int, gamma: float, lam: float, use_whitening: bool = True, group=None,
+                   width_tensor: Optional[torch.Tensor] = None):
     """Advantages (optionally whitened) and returns over the first ``width`` response positions.
 
     Whitening matches the reference: unbiased variance in a single process, biased global variance across ranks
@@ -155,14 +156,16 @@ def gae_and_whiten(values, rewards, width: int, gamma: float, lam: float, use_wh
     if values.is_cuda and ops.available():
         v = values.float().contiguous()
         r = rewards.float().contiguous()
+        # ``width_tensor`` (int32, device) overrides ``width`` inside the kernels: a captured CUDA graph then serves
+        # batches whose longest response differs (the tensors keep their static full width)
         if not use_whitening:
-            adv, ret, _ = ops.C.gae(v, r, width, gamma, lam, False, True)
+            adv, ret, _ = ops.C.gae(v, r, width, gamma, lam, False, True, width_tensor)
         elif not distributed or dist.get_world_size(group) == 1:
-            adv, ret, _ = ops.C.gae(v, r, width, gamma, lam, True, not distributed)
+            adv, ret, _ = ops.C.gae(v, r, width, gamma, lam, True, not distributed, width_tensor)
         else:
-            adv, ret, stats = ops.C.gae(v, r, width, gamma, lam, False, False)
+            adv, ret, stats = ops.C.gae(v, r, width, gamma, lam, False, False, width_tensor)
             dist.all_reduce(stats, group=group)
-            ops.C.whiten_(adv, width, stats, False)
+            ops.C.whiten_(adv, width, stats, False, width_tensor)
         return adv[:, :width].detach(), ret[:, :width]
     from trlx_b200.utils.modeling import whiten
 
@@ -174,10 +177,10 @@ def gae_and_whiten(values, rewards, width: int, gamma: float, lam: float, use_wh
 
 class _PPOLoss(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, logprobs, values, old_logprobs, old_values, adv, ret, mask, clip, clip_v, vf_coef):
+    def forward(ctx, logprobs, values, old_logprobs, old_values, adv, ret, mask, clip, clip_v, vf_coef, width_tensor):
         C = _ops().C
         args = [t.float().contiguous() for t in (logprobs, values, old_logprobs, old_values, adv, ret, mask)]
-        out, dlp, dv = C.ppo_loss(*args, clip, clip_v, vf_coef)
+        out, dlp, dv = C.ppo_loss(*args, clip, clip_v, vf_coef, width_tensor)
         ctx.save_for_backward(dlp, dv)
         ctx.shapes = (logprobs.shape, values.shape, logprobs.dtype, values.dtype)
         ctx.mark_non_differentiable(out)
@@ -188,17 +191,18 @@ class _PPOLoss(torch.autograd.Function):
         dlp, dv = ctx.saved_tensors
         s_lp, s_v, dt_lp, dt_v = ctx.shapes
         return ((dlp * g_loss).view(s_lp).to(dt_lp), (dv * g_loss).view(s_v).to(dt_v),
-                None, None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None)
 
 
 def ppo_loss(logprobs, values, old_logprobs, old_values, advantages, returns, mask, cliprange: float,
-             cliprange_value: float, vf_coef: float) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
+             cliprange_value: float, vf_coef: float, width_tensor: Optional[torch.Tensor] = None
+             ) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
     """Fused PPO loss: returns ``(loss, stats)`` where ``stats`` maps the reference's flattened stat keys to 0-dim
     DEVICE tensors (no host sync here; the trainer converts once per optimizer step)."""
     ops = _ops()
     if logprobs.is_cuda and ops.available():
         loss, out = _PPOLoss.apply(logprobs, values, old_logprobs, old_values, advantages, returns, mask,
-                                   float(cliprange), float(cliprange_value), float(vf_coef))
+                                   float(cliprange), float(cliprange_value), float(vf_coef), width_tensor)
         return loss, {k: out[i] for i, k in enumerate(_PPO_KEYS)}
     return reference.ppo_loss(logprobs, values, old_logprobs, old_values, advantages, returns, mask, cliprange,
                               cliprange_value, vf_coef)

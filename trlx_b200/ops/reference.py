@@ -53,7 +53,7 @@ def gae(values: torch.Tensor, rewards: torch.Tensor, width: int, gamma: float, l
 
 
 def ppo_loss(logprobs, values, old_logprobs, old_values, advantages, returns, mask, cliprange, cliprange_value,
-             vf_coef) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
+             vf_coef, width_tensor=None) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
     """Clipped PPO objective + statistics (``trlx/models/modeling_ppo.py:189-238``), differentiable."""
     from trlx_b200.utils.modeling import get_tensor_stats
 

@@ -1,0 +1,141 @@
+"""Fused tensor-parallel GEMM ↔ collective operations over NVLink peer memory.
+
+* :meth:`FusedTP.allgather_gemm` — the sequence-sharded activation of every rank lives in a symmetric buffer; ONE kernel
+  computes ``concat_r(x_r) · Wᵀ`` by streaming the A-operand tiles of row-block ``r`` straight out of peer ``r``'s HBM
+  with TMA into the tcgen05 pipeline (no materialised all-gather).
+* :meth:`FusedTP.gemm_reduce_scatter` — every rank's partial product tile is added from the GEMM epilogue into the fp32
+  accumulator of the rank that owns those rows with ``red.global.add.v4.f32`` over NVLink (no separate reduce-scatter).
+
+Ordering between ranks uses the device-side flag barrier of ``csrc/optim.cu`` on the buffers' signal pads.  Backward
+passes use ``torch.distributed`` collectives (library path).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from trlx_b200 import ops
+
+
+class FusedTP:
+    def __init__(self, group, rank: int, size: int, device: torch.device):
+        self.group, self.rank, self.size, self.device = group, rank, size, device
+        self._bufs: Dict[Tuple, Tuple[torch.Tensor, object]] = {}
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
+        self._pads = None
+
+    def _symm(self, key: Tuple, shape, dtype):
+        if key not in self._bufs:
+            import torch.distributed._symmetric_memory as symm
+
+            t = symm.empty(*shape, dtype=dtype, device=self.device)
+            name = self.group.group_name if self.group is not None else dist.group.WORLD.group_name
+            hdl = symm.rendezvous(t, name)
+            self._bufs[key] = (t, hdl)
+            if self._pads is None:
+                self._pads = list(hdl.signal_pad_ptrs)
+        return self._bufs[key]
+
+    def barrier(self):
+        ops.C.signal_barrier(self._pads, self.rank, self.epoch)
+
+    @staticmethod
+    def usable(rows_per_rank: int, k: int, n: int) -> bool:
+        return rows_per_rank % 128 == 0 and k % 8 == 0 and n % 8 == 0
+
+    def allgather_gemm(self, x_local: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act: str = "none"):
+        """``x_local`` ``[m, K]`` (this rank's sequence shard) → ``[m·size, N]`` = act(all_gather(x) · wᵀ + bias)."""
+        m, K = x_local.shape
+        buf, hdl = self._symm(("ag", m, K), (m, K), torch.bfloat16)
+        buf.copy_(x_local)
+        self.barrier()  # every rank's shard is in place
+        out = ops.C.gemm_allgather(list(hdl.buffer_ptrs), m, K, K, w, bias, act)
+        self.barrier()  # all peers finished reading before the buffer is reused
+        return out
+
+    def gemm_reduce_scatter(self, x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
+                            residual: Optional[torch.Tensor] = None):
+        """``x`` ``[M, K_local]``, ``w`` ``[N, K_local]`` → this rank's ``[M/size, N]`` rows of Σ_ranks x·wᵀ (+bias) (+residual)."""
+        M, N = x.shape[0], w.shape[0]
+        rows = M // self.size
+        acc, hdl = self._symm(("rs", rows, N), (rows, N), torch.float32)
+        acc.zero_()
+        self.barrier()  # accumulators are clean everywhere
+        ops.C.gemm_reduce_scatter(x, w, list(hdl.buffer_ptrs), N, bias)
+        self.barrier()  # every partial sum has landed
+        return ops.C.rs_finalize(acc, None, residual)
+
+
+class _ColumnLinearFused(torch.autograd.Function):
+    """AG→GEMM forward (fused kernel); backward via NCCL: dX = RS(dY·W), dW = dYᵀ·AG(x)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, fused: FusedTP):
+        B, t, K = x.shape
+        y = fused.allgather_gemm(x.reshape(B * t, K).contiguous(), w, b)
+        ctx.save_for_backward(x, w)
+        ctx.fused, ctx.has_bias = fused, b is not None
+        # rows are ordered rank-major ([rank][batch][time]) → back to [B, T, N]
+        return y.view(fused.size, B, t, -1).permute(1, 0, 2, 3).reshape(B, fused.size * t, -1)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        fused = ctx.fused
+        B, t, K = x.shape
+        g = gy.reshape(B, fused.size, t, -1).permute(1, 0, 2, 3).reshape(fused.size * B * t, -1).contiguous()
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            full = g @ w
+            out = torch.empty(B * t, K, dtype=full.dtype, device=full.device)
+            dist.reduce_scatter_tensor(out, full, group=fused.group)
+            gx = out.view(B, t, K)
+        if ctx.needs_input_grad[1]:
+            xs = torch.empty(fused.size * B * t, K, dtype=x.dtype, device=x.device)
+            dist.all_gather_into_tensor(xs, x.reshape(B * t, K).contiguous(), group=fused.group)
+            gw = g.t() @ xs
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = g.sum(0)
+        return gx, gw, gb, None
+
+
+class _RowLinearFused(torch.autograd.Function):
+    """GEMM→RS forward (fused kernel); backward via NCCL: dY_full = AG(dy), dX = dY_full·W, dW = dY_fullᵀ·x."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, fused: FusedTP):
+        B, T, K = x.shape
+        t = T // fused.size
+        xr = x.reshape(B, fused.size, t, K).permute(1, 0, 2, 3).reshape(fused.size * B * t, K).contiguous()  # rank-major rows
+        y = fused.gemm_reduce_scatter(xr, w, b)
+        ctx.save_for_backward(xr, w)
+        ctx.fused, ctx.has_bias, ctx.shape = fused, b is not None, (B, T, K)
+        return y.view(B, t, -1)
+
+    @staticmethod
+    def backward(ctx, gy):
+        xr, w = ctx.saved_tensors
+        fused = ctx.fused
+        B, T, K = ctx.shape
+        t = T // fused.size
+        g_local = gy.reshape(B * t, -1).contiguous()
+        g = torch.empty(fused.size * B * t, g_local.shape[1], dtype=g_local.dtype, device=g_local.device)
+        dist.all_gather_into_tensor(g, g_local, group=fused.group)
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = (g @ w).view(fused.size, B, t, K).permute(1, 0, 2, 3).reshape(B, T, K)
+        if ctx.needs_input_grad[1]:
+            gw = g.t() @ xr
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = g.sum(0)
+        return gx, gw, gb, None
+
+
+def column_linear(fused: FusedTP, linear, x):
+    return _ColumnLinearFused.apply(x, linear.weight, linear.bias, fused)
+
+
+def row_linear(fused: FusedTP, linear, x):
+    return _RowLinearFused.apply(x, linear.weight, linear.bias if fused.rank == 0 else None, fused)

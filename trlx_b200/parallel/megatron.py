@@ -29,6 +29,13 @@ class MegatronMixin:
             apply_pipeline_parallel(model, rt.pp_group, rt.pp_rank, rt.pp_size)
         return model
 
+    def _pre_optimizer_step(self):
+        rt = self.runtime
+        if rt.tp_size > 1 and self.config.train.parallel.sequence_parallel:
+            from trlx_b200.parallel.tensor_parallel import allreduce_sequence_parallel_grads
+
+            allreduce_sequence_parallel_grads(self.model, rt.tp_group)
+
     def save_pretrained(self, directory: Optional[str] = None, **kwargs):
         """``<dir>/mp_rank_XX/model_weights.ckpt`` per tensor-parallel rank (single file when TP == 1)."""
         rt = self.runtime

@@ -76,7 +76,8 @@ class _FlatGroup:
         self.hyper = torch.ones(4, dtype=torch.float32, device=self.device)
         self.hyper_host = torch.ones(4, dtype=torch.float32).pin_memory() if self.device.type == "cuda" else torch.ones(4)
         self.sq = torch.zeros(1, dtype=torch.float64, device=self.device)
-        self.epoch = 0
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=self.device)  # device-side barrier epoch
+        self.norm = torch.zeros(1, dtype=torch.float32, device=self.device)
 
     def rebind_grads(self):
         """(Re)attach ``.grad`` views — needed after anything set them to ``None``."""
@@ -179,12 +180,16 @@ class FusedAdamW(Optimizer):
             self._fallback.step()
             return loss
 
-        from trlx_b200 import ops
+        self.host_prepare()
+        self.device_step()
+        return loss
 
-        C = ops.C
+    def host_prepare(self):
+        """Host half of a fused step: advance the step count and stage (lr, bias corrections) in pinned memory."""
+        self._lazy_init()
         self._step_count_fused += 1
         t = self._step_count_fused
-        for g, fg in zip(self.param_groups, self._flat):
+        for g, fg in zip(self.param_groups, self._flat or []):
             if fg is None:
                 continue
             b1, b2 = g["betas"]
@@ -192,6 +197,18 @@ class FusedAdamW(Optimizer):
             fg.hyper_host[1] = 1.0 - b1 ** t
             fg.hyper_host[2] = 1.0 - b2 ** t
             fg.hyper_host[3] = 1.0
+
+    def device_step(self):
+        """Device half: everything here is stream work only (H2D of the staged scalars + kernels), so it can be
+        captured in a CUDA graph and replayed after :meth:`host_prepare`."""
+        from trlx_b200 import ops
+
+        C = ops.C
+        world, rank = self._world()
+        for g, fg in zip(self.param_groups, self._flat):
+            if fg is None:
+                continue
+            b1, b2 = g["betas"]
             fg.hyper.copy_(fg.hyper_host, non_blocking=True)
             args = (b1, b2, g["eps"], g["weight_decay"], self.decoupled)
             if fg.world == 1:
@@ -201,15 +218,13 @@ class FusedAdamW(Optimizer):
                 if self.grad_clip:
                     fg.sq.zero_()
                     C.sqnorm_(fg.flat_grad, fg.sq)
-                    norm = torch.empty(1, dtype=torch.float32, device=fg.device)
-                    C.clip_coef_(fg.sq, float(self.grad_clip), fg.hyper, norm)
-                    self.last_grad_norm = norm
+                    C.clip_coef_(fg.sq, float(self.grad_clip), fg.hyper, fg.norm)
+                    self.last_grad_norm = fg.norm
                 C.adamw_flat(fg.flat_param, fg.master, fg.flat_grad, fg.exp_avg, fg.exp_avg_sq, *args, fg.hyper)
                 continue
             # ---- data-parallel: fused reduce-scatter + AdamW + all-gather over NVLink peer memory
             pads = list(fg.symm_grad.signal_pad_ptrs)
             grads, params = list(fg.symm_grad.buffer_ptrs), list(fg.symm_param.buffer_ptrs)
-            fg.epoch += 1
             C.signal_barrier(pads, fg.rank, fg.epoch)  # every rank finished accumulating gradients
             if self.grad_clip:
                 if fg.gshard is None:
@@ -218,17 +233,37 @@ class FusedAdamW(Optimizer):
                 C.rs_adamw_ag(grads, params, fg.lo, fg.shard, fg.master, fg.exp_avg, fg.exp_avg_sq, fg.gshard, 1, *args,
                               fg.hyper, fg.sq)
                 dist.all_reduce(fg.sq, group=self.process_group)
-                norm = torch.empty(1, dtype=torch.float32, device=fg.device)
-                C.clip_coef_(fg.sq, float(self.grad_clip), fg.hyper, norm)
-                self.last_grad_norm = norm
+                C.clip_coef_(fg.sq, float(self.grad_clip), fg.hyper, fg.norm)
+                self.last_grad_norm = fg.norm
                 C.rs_adamw_ag(grads, params, fg.lo, fg.shard, fg.master, fg.exp_avg, fg.exp_avg_sq, fg.gshard, 2, *args,
                               fg.hyper, None)
             else:
                 C.rs_adamw_ag(grads, params, fg.lo, fg.shard, fg.master, fg.exp_avg, fg.exp_avg_sq, None, 0, *args,
                               fg.hyper, None)
-            fg.epoch += 1
             C.signal_barrier(pads, fg.rank, fg.epoch)  # every rank's new parameters are visible everywhere
-        return loss
+
+    @property
+    def graph_capturable(self) -> bool:
+        """True when ``device_step`` is pure stream work on the fused kernels (no torch.optim fallback)."""
+        self._lazy_init()
+        return self._flat is not None
+
+    def snapshot(self):
+        """Clone of all mutable optimizer/parameter storage (used to undo CUDA-graph warm-up steps)."""
+        self._lazy_init()
+        snap = {"step": self._step_count_fused, "groups": []}
+        for fg in self._flat or []:
+            snap["groups"].append(None if fg is None else [t.clone() for t in (fg.flat_param, fg.master, fg.exp_avg, fg.exp_avg_sq)])
+        return snap
+
+    def restore(self, snap):
+        self._step_count_fused = snap["step"]
+        for fg, saved in zip(self._flat or [], snap["groups"]):
+            if fg is None:
+                continue
+            for dst, src in zip((fg.flat_param, fg.master, fg.exp_avg, fg.exp_avg_sq), saved):
+                dst.copy_(src)
+            fg.flat_grad.zero_()
 
     # -- checkpointing ------------------------------------------------------------------------------------------------------
     def state_dict(self) -> Dict[str, Any]:

@@ -137,9 +137,10 @@ class DeviceBatchLoader:
             lp, v, rw = (t.index_select(0, idx) for t in (self.logprobs, self.values, self.rewards))
             th = self.trunk.index_select(0, idx) if self.trunk is not None else None
             qmax, rmax = self.Q, self.R
+            ids = idx_host.tolist()
+            width = min(max(max(self.host_rlens[i] for i in ids), 1), self.R)  # widest scored response of this batch
             if not self.static_shapes:
-                ids = idx_host.tolist()
-                rmax = max(max(self.host_rlens[i] for i in ids), 1)
+                rmax = width
                 qmax = max(max(self.host_qlens[i] for i in ids), 1)
                 q = q[:, q.shape[1] - qmax:] if self.left else q[:, :qmax]
                 # responses keep one token more than the longest scored slice: position i is scored against token i+1
@@ -147,10 +148,9 @@ class DeviceBatchLoader:
                 r, lp, v, rw = r[:, :rtok], lp[:, :rmax], v[:, :rmax], rw[:, :rmax]
                 if th is not None:
                     th = th[:, self.Q - qmax: self.Q + rtok] if self.left else torch.cat([th[:, :qmax], th[:, self.Q: self.Q + rtok]], 1)
-            if th is not None:
-                yield PPORLBatchCached(q, r, lp, v, rw, trunk_hidden=th)
-            else:
-                yield PPORLBatch(q, r, lp, v, rw)
+            batch = PPORLBatchCached(q, r, lp, v, rw, trunk_hidden=th) if th is not None else PPORLBatch(q, r, lp, v, rw)
+            batch.width = width  # python int: in static-shape mode the kernels take it through a device scalar
+            yield batch
 
 
 class PPORolloutStorage(BaseRolloutStore):

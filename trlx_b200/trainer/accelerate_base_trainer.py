@@ -37,6 +37,22 @@ from trlx_b200.utils.tokenizer import load_tokenizer
 logger = logging.get_logger(__name__)
 
 
+class EventTimer:
+    """Device-timed interval whose value is read lazily (after the step's single synchronising transfer)."""
+
+    def __init__(self):
+        self.start, self.end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.start.record()
+
+    def stop(self):
+        self.end.record()
+        return self
+
+    def __float__(self):
+        self.end.synchronize()
+        return self.start.elapsed_time(self.end) / 1e3
+
+
 def _materialise(stats: Dict[str, Any]) -> Dict[str, Any]:
     """Turn 0-dim device tensors into python floats with a single device→host transfer."""
     keys = [k for k, v in stats.items() if isinstance(v, torch.Tensor) and v.numel() == 1]
@@ -45,6 +61,9 @@ def _materialise(stats: Dict[str, Any]) -> Dict[str, Any]:
         vals = torch.stack(dev).tolist() if dev[0].is_cuda else [float(v) for v in dev]
         stats = dict(stats)
         stats.update(zip(keys, vals))
+    for k, v in list(stats.items()):
+        if isinstance(v, EventTimer):
+            stats[k] = float(v)
     return stats
 
 
@@ -273,6 +292,9 @@ class AccelerateRLTrainer(BaseRLTrainer):
         self._after_weights_changed()
         self.runtime.barrier()
 
+    def _pre_optimizer_step(self):
+        """Hook between the last backward and ``opt.step()`` (tensor-parallel gradient fix-ups live here)."""
+
     def _after_weights_changed(self):
         """Hook: engines holding derived weight copies refresh here."""
 
@@ -420,6 +442,7 @@ class AccelerateRLTrainer(BaseRLTrainer):
                 stats_accum.append(stats)
         n = len(stats_accum)
         stats = {k: sum(s[k] for s in stats_accum) / self.num_mb for k in stats_accum[0]}
+        self._pre_optimizer_step()
         self.opt.step()
         self.opt.zero_grad()
         self.scheduler.step()

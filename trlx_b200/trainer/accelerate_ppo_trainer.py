@@ -93,6 +93,7 @@ class AcceleratePPOTrainer(AccelerateRLTrainer):
         self.cache_trunk = bool(config.train.trainer_kwargs.get("cache_trunk", True))
         self._engine = None
         self._engine_failed = False
+        self._graphed_steps = {}
 
     # ---- model ------------------------------------------------------------------------------------------------------------
     def get_arch(self, config: TRLConfig):
@@ -110,7 +111,9 @@ class AcceleratePPOTrainer(AccelerateRLTrainer):
         query, response = batch.query_tensors.to(dev), batch.response_tensors.to(dev)
         old_logprobs, old_values, old_rewards = batch.logprobs.to(dev), batch.values.to(dev), batch.rewards.to(dev)
         response_length = old_rewards.shape[1]
-        advantages, returns = self.config.method.get_advantages_and_returns(old_values, old_rewards, response_length)
+        width_tensor = getattr(batch, "width_tensor", None)  # device-side effective width (CUDA-graph replay)
+        advantages, returns = self.config.method.get_advantages_and_returns(old_values, old_rewards, response_length,
+                                                                            width_tensor=width_tensor)
 
         if self.config.model.model_arch_type == "seq2seq":
             attention_mask = query.ne(pad).long()
@@ -144,7 +147,8 @@ class AcceleratePPOTrainer(AccelerateRLTrainer):
             mask = attention_mask[:, start + 1:end + 1]
 
         return self.config.method.loss(logprobs=logprobs.float(), values=values_pred.float(), old_logprobs=old_logprobs,
-                                       old_values=old_values, advantages=advantages, returns=returns, mask=mask.float())
+                                       old_values=old_values, advantages=advantages, returns=returns, mask=mask.float(),
+                                       width_tensor=width_tensor)
 
     # ---- bookkeeping ------------------------------------------------------------------------------------------------------
     def setup_rollout_logging(self, config):
@@ -165,8 +169,41 @@ class AcceleratePPOTrainer(AccelerateRLTrainer):
     def post_backward_callback(self):
         self.kl_ctl.update(self.mean_kl, n_steps=self.config.train.batch_size)
 
+    def _graphs_enabled(self) -> bool:
+        """Whole-step CUDA graphs: CUDA, fused optimizer, one micro-batch per step, decoder-only hydra with shared trunk."""
+        return bool(self.runtime.cuda and self.config.train.parallel.cuda_graphs and self.num_mb == 1
+                    and getattr(self.opt, "graph_capturable", False) and self.config.model.model_arch_type != "seq2seq"
+                    and hasattr(self.model, "can_share_trunk") and self.model.can_share_trunk()
+                    and not self.config.train.trainer_kwargs.get("no_train_graph", False)
+                    and os.environ.get("TRLX_B200_TRAIN_GRAPH", "1") == "1")
+
     def create_train_dataloader(self):
-        return self.store.create_loader(self.config.train.batch_size, shuffle=True)
+        return self.store.create_loader(self.config.train.batch_size, shuffle=True, static_shapes=self._graphs_enabled())
+
+    def train_step(self, minibatch):
+        """One optimizer step; replayed from a captured CUDA graph when the shapes allow it."""
+        batch = minibatch[0] if len(minibatch) == 1 else None
+        if batch is None or not self._graphs_enabled() or not hasattr(batch, "width") or not batch.query_tensors.is_cuda:
+            return super().train_step(minibatch)
+        from trlx_b200.trainer.accelerate_base_trainer import EventTimer
+        from trlx_b200.trainer.graphed_step import GraphedPPOStep
+
+        key = GraphedPPOStep.shape_key(batch)
+        step = self._graphed_steps.get(key)
+        if step is None:
+            if len(self._graphed_steps) >= 8:  # shapes keep changing → not worth capturing
+                return super().train_step(minibatch)
+            step = self._graphed_steps[key] = GraphedPPOStep(self, batch)
+        self.mb_count += 1
+        timer = EventTimer()
+        stats = step.run(batch, batch.width)
+        stats["time/step"] = timer.stop()
+        stats["time/forward"] = 0.0  # not separable inside one graph; see time/step
+        stats["time/backward"] = 0.0
+        self.scheduler.step()
+        self.iter_count += 1
+        self._after_weights_changed()
+        return stats
 
     def prepare_learning(self):
         self.eval_dataloader = self.eval_pipeline.create_loader(self.config.method.chunk_size)
@@ -329,7 +366,14 @@ class AcceleratePPOTrainer(AccelerateRLTrainer):
             metadata = {k: v for k, v in batch.items() if k not in ("input_ids", "attention_mask")}
             t_gen = time()
             if engine is not None:
-                ro = engine.rollout(batch["input_ids"], batch["attention_mask"])
+                ids, am = batch["input_ids"], batch["attention_mask"]
+                bucket = int(self.config.train.trainer_kwargs.get("prompt_bucket", 16))
+                width = -(-ids.shape[1] // bucket) * bucket
+                if width != ids.shape[1] and self.tokenizer.padding_side == "left":
+                    # bucket the (left-padded) prompt width so decode / train-step CUDA graphs see few distinct shapes
+                    ids = F.pad(ids, (width - ids.shape[1], 0), value=pad)
+                    am = F.pad(am, (width - am.shape[1], 0), value=0)
+                ro = engine.rollout(ids, am)
             else:
                 ro = self._rollout_torch(batch, device)
             stats["time/rollout_generate"] = time() - t_gen
