@@ -213,6 +213,8 @@ def _ilql_sample(logits, qs, vs, beta, top_k, temperature, logit_mask_row=None):
     """π ∝ softmax(topk(log_softmax(logits) + β·(Q − V)) / T)  (SURVEY A.6)."""
     logits = logits.float()
     if logit_mask_row is not None:
+        if logit_mask_row.shape[-1] < logits.shape[-1]:  # masks may cover only the task's own tokens
+            logit_mask_row = F.pad(logit_mask_row, (0, logits.shape[-1] - logit_mask_row.shape[-1]), value=False)
         logits = logits.masked_fill(logit_mask_row, float("-inf"))
     pi_beta = F.log_softmax(logits, -1)
     shifted = topk_mask(pi_beta + beta * (qs.float() - vs.float()), top_k)
@@ -291,7 +293,9 @@ class AutoModelForCausalLMWithILQLHeads(PreTrainedModelWrapper):
             qs = torch.minimum(target_qs[0][:, -1], target_qs[1][:, -1]) if self.two_qs else target_qs[0][:, -1]
             mask_row = None
             if logit_mask is not None:
-                mask_row = logit_mask[input_ids[:, -1].to(logit_mask.device)].to(logits.device).bool()
+                last = input_ids[:, -1].to(logit_mask.device)
+                rows = logit_mask[last.clamp_max(logit_mask.shape[0] - 1)].to(logits.device).bool()
+                mask_row = rows & (last < logit_mask.shape[0]).to(rows.device).unsqueeze(-1)
             nxt = _ilql_sample(logits[:, -1], qs, vs[:, -1], beta, top_k, temperature, mask_row)
             nxt = (1 - finished) * nxt + finished * eos_token_id
             finished = (nxt == eos_token_id).long()

@@ -83,7 +83,9 @@ def tokenize_dialogue(dialogue: Union[str, Iterable[str]], tokenizer, max_length
                 out[0].tokens = out[0].tokens[1:]
             else:
                 out[-1].tokens = out[-1].tokens[:-1]
-        out.insert(0, DialogMessage(False, (tokenizer.bos_token_id,)))
+            out = [m for m in out if len(m.tokens) > 0]  # the trimmed message may have had a single token
+        if out and out[0].is_output:
+            out.insert(0, DialogMessage(False, (tokenizer.bos_token_id,)))
     return out
 
 
