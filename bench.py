@@ -276,6 +276,33 @@ def main():
             for minibatch in MiniBatchIterator(loader, trainer.mb_size, trainer.num_mb):
                 timed("train_step(16x)", trainer.train_step, minibatch)
         print("BREAKDOWN_MS " + json.dumps({k: round(v, 2) for k, v in acc.items()}), file=sys.stderr)
+    if os.environ.get("BENCH_PROFILE") and rank == 0:
+        # per-kernel device time of the two phases (torch.profiler/CUPTI; diagnostic only — never a bench number)
+        from torch.profiler import ProfilerActivity, profile
+
+        from trlx_b200.pipeline import MiniBatchIterator
+
+        os.environ["TRLX_B200_TRAIN_GRAPH"] = "0"  # kernels inside a replayed graph are attributed per kernel anyway,
+        trainer._graphed_steps = {}                 # but the eager step also shows which autograd node launched them
+        os.makedirs("gpurun_out", exist_ok=True)
+        for phase in ("train", "rollout"):
+            trainer.store.clear_history()
+            if phase == "train":
+                trainer.make_experience(cfg.method.num_rollouts, 0)
+                loader = trainer.create_train_dataloader()
+                batches = list(MiniBatchIterator(loader, trainer.mb_size, trainer.num_mb))
+                trainer.train_step(batches[0])
+            torch.cuda.synchronize()
+            with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+                if phase == "train":
+                    for mb in batches[1:5]:
+                        trainer.train_step(mb)
+                else:
+                    trainer.make_experience(cfg.method.num_rollouts, 0)
+                torch.cuda.synchronize()
+            table = prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=70)
+            with open(f"gpurun_out/profile_{phase}.txt", "w") as fh:
+                fh.write(table)
     if rank == 0:
         print(json.dumps(out))
     if dist.is_initialized():

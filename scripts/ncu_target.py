@@ -1,0 +1,37 @@
+"""Short kernel driver for `ncu --set full` captures (profiles/README.md): a few launches of each hot kernel at the
+shapes the PPO benchmark uses, plus a large square GEMM for the roofline comparison."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from trlx_b200 import ops
+
+C = ops.C
+dev = "cuda"
+torch.manual_seed(0)
+
+
+def t(*shape):
+    return (torch.randn(*shape, device=dev) * 0.05).to(torch.bfloat16)
+
+
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+if which in ("all", "gemm"):
+    a, w = t(8192, 8192), t(8192, 8192)          # roofline shape
+    for _ in range(3):
+        C.gemm(a, w, None, None, "none")
+    a, w, b = t(128, 768), t(2304, 768), t(2304)  # decode QKV (launch/latency bound)
+    for _ in range(3):
+        C.gemm(a, w, b, None, "none")
+    a, w, b = t(1792, 768), t(3072, 768), t(3072)  # training MLP up-projection + GELU
+    for _ in range(3):
+        C.gemm(a, w, b, None, "gelu_tanh")
+if which in ("all", "lmhead"):
+    h, w = t(1280, 768), t(50257, 768)
+    lab = torch.randint(0, 50257, (1280,), device=dev)
+    for _ in range(3):
+        C.lmhead(h, w, None, lab)
+torch.cuda.synchronize()

@@ -165,3 +165,120 @@ def test_tp_state_dict_resharding_roundtrip():
     back = unshard_state_dicts(spec, shards)
     for k, v in sd.items():
         torch.testing.assert_close(back[k], v)
+
+
+# ---- pipeline parallelism -------------------------------------------------------------------------------------------------
+def _pp_job(rank, world, family, tied):
+    import copy
+
+    from trlx_b200.nn.arch import spec_from_hf_config
+    from trlx_b200.nn.transformer import CausalLM
+    from trlx_b200.parallel import pipeline_parallel as pp
+
+    cfgs = {
+        "gpt2": dict(model_type="gpt2", vocab_size=61, n_embd=32, n_layer=4, n_head=4, n_positions=64),
+        "llama": dict(model_type="llama", vocab_size=61, hidden_size=32, num_hidden_layers=4, num_attention_heads=4,
+                      num_key_value_heads=2, intermediate_size=64, max_position_embeddings=64),
+    }
+    torch.manual_seed(0)
+    spec = spec_from_hf_config(dict(cfgs[family], tie_word_embeddings=tied))
+    assert spec.tie_word_embeddings == tied
+    full = CausalLM(spec).float()
+    staged = copy.deepcopy(full)
+    stage = pp.apply_pipeline_parallel(staged, None, rank, world)
+    M = 5
+    g = torch.Generator().manual_seed(1)
+    mbs = []
+    for i in range(M):
+        T = 6 + (i % 3)  # the activation shape changes between micro-batches
+        ids = torch.randint(0, 61, (2, T), generator=g)
+        mask = torch.ones_like(ids)
+        mask[0, :i % 2] = 0
+        mbs.append(dict(input_ids=ids, attention_mask=mask, labels=ids))
+
+    # oracle: the unpartitioned model
+    ref_losses = []
+    for mb in mbs:
+        out = full(**mb)
+        out.loss.backward()
+        ref_losses.append(out.loss.detach())
+    ref_grads = {n: p.grad.clone() for n, p in full.named_parameters() if p.grad is not None}
+
+    # (1) differentiable relay, one micro-batch at a time
+    relay_losses = []
+    for mb in mbs:
+        out = staged(**mb)
+        out.loss.backward()
+        relay_losses.append(out.loss.detach())
+    pp.allreduce_tied_embedding_grads(stage)
+    relay_grads = {n: p.grad.clone() for n, p in staged.named_parameters() if p.grad is not None and p.numel()}
+    staged.zero_grad()
+
+    # (2) 1F1B schedule
+    def loss_fn(mb):
+        out = staged(**mb)
+        return out.loss, {"loss": out.loss.detach()}
+
+    stats = pp.run_1f1b(stage, mbs, loss_fn, torch.device("cpu"))
+    pp.allreduce_tied_embedding_grads(stage)
+    sched_grads = {n: p.grad.clone() for n, p in staged.named_parameters() if p.grad is not None and p.numel()}
+    shared = pp.broadcast_stats(stage, {"loss": sum(s["loss"] for s in stats) / M} if stage.last else None, torch.device("cpu"))
+
+    # (3) inference relay with a KV cache: every stage sees the same logits as the full model
+    with torch.no_grad():
+        ids = mbs[0]["input_ids"]
+        a = staged(input_ids=ids[:, :4], use_cache=True)
+        b = staged(input_ids=ids[:, 4:5], past_key_values=a.past_key_values, use_cache=True)
+        fa = full(input_ids=ids[:, :5])
+    return dict(ref_losses=ref_losses, relay_losses=relay_losses, ref_grads=ref_grads, relay_grads=relay_grads,
+                sched_grads=sched_grads, mean_loss=shared["loss"], step_logits=b.logits[:, -1], full_logits=fa.logits[:, -1],
+                owned=(stage.lo, stage.hi))
+
+
+@pytest.mark.parametrize("world,family,tied", [(2, "gpt2", True), (3, "llama", False)])
+def test_pipeline_parallel_matches_single_rank(world, family, tied):
+    res = run_distributed(_pp_job, world, (family, tied))
+    ref = res[0]["ref_grads"]
+    seen = set()
+    for r in res:
+        for a, b in zip(r["relay_losses"], r["ref_losses"]):  # every stage reports the true loss in relay mode
+            torch.testing.assert_close(a, b, atol=1e-5, rtol=1e-5)
+        torch.testing.assert_close(r["mean_loss"], sum(r["ref_losses"]) / len(r["ref_losses"]), atol=1e-5, rtol=1e-5)
+        torch.testing.assert_close(r["step_logits"], r["full_logits"], atol=1e-4, rtol=1e-4)
+        for kind in ("relay_grads", "sched_grads"):
+            for n, g in r[kind].items():
+                torch.testing.assert_close(g, ref[n], atol=2e-5, rtol=1e-4, msg=lambda m: f"{kind} {n}: {m}")
+                seen.add(n)
+    assert seen == set(ref), f"parameters without a gradient on any stage: {set(ref) - seen}"
+
+
+def _pp_trainer_job(rank, world, kind, tmp):
+    import trlx_b200 as trlx
+    from trlx_b200.data.default_configs import default_ppo_config, default_sft_config
+
+    gpt2 = dict(model_type="gpt2", vocab_size=257, n_embd=32, n_layer=4, n_head=2, n_positions=64, eos_token_id=256, bos_token_id=256)
+    common = dict(seq_length=16, batch_size=4, minibatch_size=1, total_steps=3, epochs=4, checkpoint_interval=100, eval_interval=3,
+                  tracker=None, checkpoint_dir=tmp, seed=3, parallel=dict(pipeline_parallel=world))
+    prompts = ["hello a", "what is", "b", "count the a", "zz", "dog dog", "a dog", "the"]
+    if kind == "ppo":
+        cfg = default_ppo_config().evolve(
+            train=dict(common, trainer="NeMoPPOTrainer"), model=dict(model_path=gpt2, num_layers_unfrozen=-1),
+            tokenizer=dict(tokenizer_path="toy://bytes"),
+            method=dict(num_rollouts=4, chunk_size=4, ppo_epochs=1, gen_kwargs=dict(max_new_tokens=5, top_k=0, top_p=1.0, do_sample=True)))
+        trainer = trlx.train(reward_fn=lambda samples, **kw: [float(s.count("a")) for s in samples], prompts=prompts,
+                             eval_prompts=prompts[:2], config=cfg)
+    else:
+        cfg = default_sft_config().evolve(
+            train=dict(common, trainer="NeMoSFTTrainer"), model=dict(model_path=gpt2),
+            tokenizer=dict(tokenizer_path="toy://bytes"), method=dict(gen_kwargs=dict(max_new_tokens=4, do_sample=False)))
+        trainer = trlx.train(samples=[[p, " yes a"] for p in prompts], eval_prompts=prompts[:2], config=cfg)
+    lm = trainer.model.base_model
+    owned = [i for i, blk in enumerate(lm.transformer.h) if sum(p.numel() for p in blk.parameters()) > 0]
+    return dict(iters=trainer.iter_count, owned=owned)
+
+
+@pytest.mark.parametrize("kind", ["sft", "ppo"])
+def test_pipeline_parallel_trainers_run(kind, tmp_path):
+    res = run_distributed(_pp_trainer_job, 2, (kind, str(tmp_path)))
+    assert [r["iters"] for r in res] == [3, 3]
+    assert res[0]["owned"] == [0, 1] and res[1]["owned"] == [2, 3]

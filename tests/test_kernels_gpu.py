@@ -21,7 +21,7 @@ def _bf(*shape, scale=1.0):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 2304, 768), (1600, 3072, 768), (100, 776, 3072), (257, 50257, 768), (32, 768, 64)])
-@pytest.mark.parametrize("bn", [0, 32, 64, 128])
+@pytest.mark.parametrize("bn", [0, 32, 64, 128, 256])
 def test_gemm_matches_fp32(C, M, N, K, bn):
     torch.manual_seed(0)
     x, w = _bf(M, K), _bf(N, K, scale=K ** -0.5)
@@ -30,6 +30,37 @@ def test_gemm_matches_fp32(C, M, N, K, bn):
     torch.testing.assert_close(out, ref, atol=2e-3, rtol=2e-3)
     out16 = C.gemm(x, w, force_bn=bn)
     torch.testing.assert_close(out16.float(), ref, atol=3e-2, rtol=3e-2)
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(2048, 4096, 512, 128), (4096, 8192, 256, 256), (1300, 20000, 192, 0), (9000, 300, 128, 32)])
+def test_gemm_persistent_many_tiles(C, M, N, K, bn):
+    """More tiles than SMs: every CTA walks several tiles through the double-buffered TMEM accumulator."""
+    torch.manual_seed(M + N)
+    x = (torch.randn(M, K, device="cuda") * 0.5).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda") * 0.5).to(torch.bfloat16)
+    y = C.gemm(x, w, None, None, "none", force_bn=bn)
+    ref = x.float() @ w.float().t()
+    err = (y.float() - ref).abs().max().item()
+    assert err <= 2e-2 * ref.abs().max().item(), err
+
+
+def test_lmhead_dlogits(C):
+    torch.manual_seed(5)
+    M, V, K = 300, 50257, 256
+    h = (torch.randn(M, K, device="cuda") * 0.3).to(torch.bfloat16)
+    w = (torch.randn(V, K, device="cuda") * 0.3).to(torch.bfloat16)
+    b = (torch.randn(V, device="cuda") * 0.1).to(torch.bfloat16)
+    lab = torch.randint(0, V, (M,), device="cuda")
+    lab[::7] = -1
+    g = torch.randn(M, device="cuda")
+    logits = h.float() @ w.float().t() + b.float()
+    lse = torch.logsumexp(logits, -1)
+    onehot = torch.zeros_like(logits).scatter_(1, lab.clamp_min(0)[:, None], 1.0)
+    ref = (onehot - torch.exp(logits - lse[:, None])) * g[:, None]
+    ref[lab < 0] = 0
+    d = C.lmhead_dlogits(h, w, b, lab, lse, g)
+    assert d.shape == (M, V) and d.stride(0) % 64 == 0
+    assert (d.float() - ref).abs().max().item() < 2e-2 * max(ref.abs().max().item(), 1e-3) + 1e-3
 
 
 @pytest.mark.parametrize("act", ["none", "gelu_new", "gelu", "relu", "silu"])

@@ -31,6 +31,8 @@ int b200_decode_step(const long long*, const float*, const float*, const float*,
 int b200_paged_kv_write(const void*, const void*, void*, void*, const int*, const int*, const int*, int, int, int, int, int,
                         int, long long, long long, cudaStream_t);
 int b200_logprob_from_logits(const void*, const long long*, float*, float*, long long, int, long long, int, cudaStream_t);
+int b200_lmhead_dlogits_bf16(const void*, const void*, void*, int, int, int, long long, long long, long long, const void*,
+                             const long long*, const float*, const float*, cudaStream_t);
 int b200_logprob_backward_inplace(void*, const long long*, const float*, const float*, long long, int, long long, int,
                                   cudaStream_t);
 int b200_gae(const float*, const float*, float*, float*, int, int, int, const int*, long long, float, float, double*,
@@ -106,6 +108,27 @@ Tensor gemm(const Tensor& x, const Tensor& w, const OptTensor& bias, const OptTe
                        act_code(act), out.scalar_type() == at::kFloat, (int)force_bn, stream()),
         "gemm");
   return out;
+}
+
+// LM-head backward: d-logits[M, N] (bf16, row pitch padded to a multiple of 64 so every consumer is vectorised) from
+// h[M,K], w[N,K], the saved logsumexp and the incoming gradient of log p(label).
+Tensor lmhead_dlogits(const Tensor& h, const Tensor& w, const OptTensor& bias, const Tensor& labels, const Tensor& lse,
+                      const Tensor& grad) {
+  CHECK_BF16(h); CHECK_BF16(w); CHECK_F32(lse); CHECK_F32(grad);
+  TORCH_CHECK(h.dim() == 2 && w.dim() == 2 && h.size(1) == w.size(1) && h.stride(1) == 1 && w.stride(1) == 1);
+  const int64_t M = h.size(0), N = w.size(0), K = h.size(1);
+  TORCH_CHECK(K % 8 == 0 && h.stride(0) % 8 == 0 && w.stride(0) % 8 == 0);
+  TORCH_CHECK(labels.scalar_type() == at::kLong && labels.numel() == M && labels.is_contiguous());
+  TORCH_CHECK(lse.numel() == M && grad.numel() == M && lse.is_contiguous() && grad.is_contiguous());
+  c10::cuda::CUDAGuard guard(h.device());
+  const int64_t ld = (N + 63) / 64 * 64;
+  Tensor buf = torch::empty({M, ld}, h.options());
+  if (ld != N) buf.slice(1, N, ld).zero_();
+  check(b200_lmhead_dlogits_bf16(h.data_ptr(), w.data_ptr(), buf.data_ptr(), (int)M, (int)N, (int)K, h.stride(0), w.stride(0),
+                                 ld, optptr(bias), (const long long*)labels.data_ptr<int64_t>(), lse.data_ptr<float>(),
+                                 grad.data_ptr<float>(), stream()),
+        "lmhead_dlogits");
+  return buf.slice(1, 0, N);
 }
 
 // Fused LM head: returns (lse[M], logprob[M], token[M], token_logprob[M]); unused outputs are empty tensors.
@@ -486,6 +509,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("sample") = false, py::arg("temperature") = 1.0, py::arg("seed") = 0, py::arg("step") = py::none(),
         py::arg("suppress_col") = -1, py::arg("suppress_until") = 0, py::arg("workspace") = py::none(),
         py::arg("seed_tensor") = py::none());
+  m.def("lmhead_tiles", [](int64_t n) { return (int64_t)b200_lmhead_tiles((int)n); }, py::arg("vocab"));
+  m.def("lmhead_dlogits", &lmhead_dlogits, py::arg("h"), py::arg("w"), py::arg("bias"), py::arg("labels"), py::arg("lse"),
+        py::arg("grad"));
   m.def("norm", &norm, py::arg("x"), py::arg("w"), py::arg("b") = py::none(), py::arg("eps") = 1e-5, py::arg("rms") = false,
         py::arg("out") = py::none());
   m.def("embed", &embed, py::arg("tokens"), py::arg("positions"), py::arg("wte"), py::arg("wpe") = py::none(),

@@ -15,6 +15,7 @@
 //               This replaces the reference's  logits = lm_head(h); log_softmax; gather  chain
 //               (trlx/utils/modeling.py:213-219) and HF generate's softmax+multinomial.
 #include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -26,7 +27,8 @@ namespace b200 {
 constexpr int BM = 128;
 constexpr int BK = 64;        // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
 
 enum Act { ACT_NONE = 0, ACT_GELU_TANH = 1, ACT_GELU_ERF = 2, ACT_RELU = 3, ACT_SILU = 4 };
 
@@ -39,6 +41,11 @@ struct StoreEpilogue {
   float alpha;
   int act;
   int out_f32;
+  // d-logits mode (LM-head backward, all three set): out = ((col == label) - exp(x - lse[row])) * grad[row]
+  const float* dl_lse;
+  const float* dl_grad;
+  const long long* dl_labels;
+  int debug_nostore;
 };
 
 constexpr int MAX_TP = 8;
@@ -95,6 +102,164 @@ __device__ __forceinline__ void red_add_v4_f32(float* addr, float a, float b, fl
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// Epilogue bodies: one output row per thread, columns [c_lo, c_hi) of the current tile's accumulator.
+template <int EPI>
+__device__ __forceinline__ void epilogue_cols(uint32_t taddr_row, int row, bool row_ok, int n0, int c_lo, int c_hi, int N,
+                                              int part_idx, const StoreEpilogue& se, const LMHeadEpilogue& le,
+                                              const ReduceScatterEpilogue& re) {
+  if constexpr (EPI == 0) {
+    const bool vec_ok = ((se.ldo & 7) == 0) && (se.residual == nullptr || (se.ldr & 7) == 0);
+    // d-logits mode (LM-head backward): out = ((col == label) - exp(logit - lse[row])) * grad[row]
+    const bool dl = se.dl_lse != nullptr;
+    float dl_l = 0.f, dl_g = 0.f;
+    long long dl_lab = -1;
+    if (dl && row_ok) { dl_l = se.dl_lse[row]; dl_g = se.dl_grad[row]; dl_lab = se.dl_labels[row]; }
+#pragma unroll 1
+    for (int c = c_lo; c < c_hi; c += 16) {
+      uint32_t r[16];
+      tmem_ld16(taddr_row + c, r);
+      tmem_ld_wait();
+      const int col0 = n0 + c;
+      if (!row_ok || col0 >= N) continue;
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int col = col0 + j;
+        float x = __uint_as_float(r[j]) * se.alpha;
+        if (col < N) {
+          if (se.col_scale) x *= se.col_scale[col];
+          if (se.bias) x += __bfloat162float(se.bias[col]);
+        }
+        if (dl) {
+          const float pr = __expf(x - dl_l);
+          x = (dl_lab < 0) ? 0.f : (((long long)col == dl_lab ? 1.f : 0.f) - pr) * dl_g;
+        }
+        v[j] = apply_act(x, se.act);
+      }
+      const bool full = (col0 + 16 <= N);
+      if (se.debug_nostore) {  // experiment: keep the math, drop the global stores
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc += v[j];
+        if (acc == 1.2345e-30f) reinterpret_cast<float*>(se.out)[0] = acc;
+        continue;
+      }
+      if (se.residual) {
+        const __nv_bfloat16* rp = se.residual + (size_t)row * se.ldr + col0;
+        if (full && vec_ok) {
+          uint4 ra = *reinterpret_cast<const uint4*>(rp), rb = *reinterpret_cast<const uint4*>(rp + 8);
+          const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&ra);
+          const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(&rb);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { v[j] += __bfloat162float(h[j]); v[8 + j] += __bfloat162float(g[j]); }
+        } else {
+          for (int j = 0; j < 16 && col0 + j < N; ++j) v[j] += __bfloat162float(rp[j]);
+        }
+      }
+      if (se.out_f32) {
+        float* op = reinterpret_cast<float*>(se.out) + (size_t)row * se.ldo + col0;
+        if (full && (se.ldo & 3) == 0) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+          for (int j = 0; j < 16 && col0 + j < N; ++j) op[j] = v[j];
+        }
+      } else {
+        __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(se.out) + (size_t)row * se.ldo + col0;
+        if (full && vec_ok) {
+          uint4 pk[2];
+          __nv_bfloat162* p2 = reinterpret_cast<__nv_bfloat162*>(pk);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) p2[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+          *reinterpret_cast<uint4*>(op) = pk[0];
+          *reinterpret_cast<uint4*>(op + 8) = pk[1];
+        } else {
+          for (int j = 0; j < 16 && col0 + j < N; ++j) op[j] = __float2bfloat16(v[j]);
+        }
+      }
+    }
+  } else if constexpr (EPI == 2) {
+    const int owner = row_ok ? row / re.rows_per_rank : 0;
+    float* dst_row = row_ok ? re.acc[owner] + (size_t)(row - owner * re.rows_per_rank) * re.ldacc : nullptr;
+#pragma unroll 1
+    for (int c = c_lo; c < c_hi; c += 16) {
+      uint32_t r[16];
+      tmem_ld16(taddr_row + c, r);
+      tmem_ld_wait();
+      const int col0 = n0 + c;
+      if (!row_ok || col0 >= N) continue;
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        v[j] = __uint_as_float(r[j]);
+        if (se.bias && col0 + j < N) v[j] += __bfloat162float(se.bias[col0 + j]);  // only the rank that owns the bias passes it
+      }
+      if (col0 + 16 <= N && (re.ldacc & 3) == 0) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) red_add_v4_f32(dst_row + col0 + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+      } else {
+        for (int j = 0; j < 16 && col0 + j < N; ++j) atomicAdd(dst_row + col0 + j, v[j]);
+      }
+    }
+  } else {
+    const long long label = (row_ok && le.labels) ? le.labels[row] : -1;
+    float mx = -INFINITY, sum = 0.f;
+    float best_key = -INFINITY, best_logit = 0.f;
+    int best_idx = -1;
+    const bool sampling = le.samp_key != nullptr;
+    const int step = le.step_ptr ? *le.step_ptr : 0;
+    const int suppress = (le.suppress_col >= 0 && step < le.suppress_until) ? le.suppress_col : -1;
+    const unsigned long long seed = le.seed + (le.seed_ptr ? (unsigned long long)(*le.seed_ptr) : 0ull) +
+                                    0x632BE59BD9B4E019ull * (unsigned long long)(step + 1);
+    const bool greedy = le.inv_temperature <= 0.f;
+#pragma unroll 1
+    for (int c = c_lo; c < c_hi; c += 16) {
+      uint32_t r[16];
+      tmem_ld16(taddr_row + c, r);
+      tmem_ld_wait();
+      const int col0 = n0 + c;
+      if (!row_ok || col0 >= N) continue;
+      float z[16];
+      float cmax = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int col = col0 + j;
+        float x = -INFINITY;
+        if (col < N && col != suppress) {
+          x = __uint_as_float(r[j]);
+          if (le.bias) x += __bfloat162float(le.bias[col]);
+          if (col == label) le.label_logit[row] = x;
+        }
+        z[j] = x;
+        cmax = fmaxf(cmax, x);
+      }
+      if (cmax > mx) { sum *= __expf(mx - cmax); mx = cmax; }   // exp(-inf - finite) = 0 handles the first chunk
+      if (mx > -INFINITY) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) sum += __expf(z[j] - mx);
+      }
+      if (sampling) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (z[j] == -INFINITY) continue;
+          float key = z[j];
+          if (!greedy) key = z[j] * le.inv_temperature - __logf(-__logf(uniform01(seed, (unsigned)row, (unsigned)(col0 + j))));
+          if (key > best_key) { best_key = key; best_logit = z[j]; best_idx = col0 + j; }
+        }
+      }
+    }
+    if (row_ok) {
+      const size_t o = (size_t)row * le.n_tiles + part_idx;
+      le.part_max[o] = mx;
+      le.part_sum[o] = sum;
+      if (sampling) { le.samp_key[o] = best_key; le.samp_logit[o] = best_logit; le.samp_idx[o] = best_idx; }
+    }
+  }
+}
+
+// Persistent, warp-specialised kernel.  Each CTA walks output tiles  t = blockIdx.x, blockIdx.x + gridDim.x, ...
+// (M-fastest order: CTAs that run concurrently share the same B panel in L2).  The accumulator is double-buffered in
+// TMEM (2 x BN fp32 columns), so the epilogue of tile i overlaps the TMA/MMA mainloop of tile i+1.
 template <int BN, int EPI>  // EPI: 0 = store, 1 = lm-head, 2 = reduce-scatter into peer accumulators
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ MapArray maps_a, const __grid_constant__ CUtensorMap map_b, int M, int N, int K,
@@ -103,31 +268,35 @@ gemm_tn_kernel(const __grid_constant__ MapArray maps_a, const __grid_constant__ 
   constexpr uint32_t A_BYTES = BM * BK * 2;
   constexpr uint32_t B_BYTES = BN * BK * 2;
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  constexpr uint32_t ACC_COLS = BN < 32 ? 32 : BN;   // TMEM columns of one accumulator buffer
+  constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;
+  constexpr int HALF = BN >= 32 ? BN / 2 : BN;        // columns per epilogue warp (two warps share a TMEM lane quadrant)
 
   // 1024-byte aligned base (dynamic smem alignment is only guaranteed to 16 B)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)stages * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + stages;
-  uint64_t* tmem_full_bar = empty_bar + stages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + stages;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
   const int nkb = (K + BK - 1) / BK;
-  // which peer's copy of A holds this M-tile (all-gather -> GEMM); plain GEMMs have a single map
-  const int a_map = m0 / rows_per_map;
-  const int a_row = m0 - a_map * rows_per_map;
-  const CUtensorMap* map_a_ptr = &maps_a.m[a_map];
+  const int m_tiles = (M + BM - 1) / BM;
+  const int n_tiles = (N + BN - 1) / BN;
+  const int total_tiles = m_tiles * n_tiles;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(map_a_ptr);
+    tma_prefetch_desc(&maps_a.m[0]);
     tma_prefetch_desc(&map_b);
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], NUM_EPI_WARPS);
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -145,180 +314,75 @@ gemm_tn_kernel(const __grid_constant__ MapArray maps_a, const __grid_constant__ 
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % stages;
-        const uint32_t phase = (kb / stages) & 1;
-        mbar_wait(&empty_bar[s], phase ^ 1);
-        uint8_t* a_dst = smem + (size_t)s * STAGE_BYTES;
-        uint8_t* b_dst = a_dst + A_BYTES;
-        mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
-        tma_load_2d(a_dst, map_a_ptr, &full_bar[s], kb * BK, a_row);
-        tma_load_2d(b_dst, &map_b, &full_bar[s], kb * BK, n0);
+      uint32_t it = 0;  // k-block counter across all of this CTA's tiles (ring position)
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m0 = (tile % m_tiles) * BM, n0 = (tile / m_tiles) * BN;
+        // which peer's copy of A holds this M-tile (all-gather -> GEMM); plain GEMMs have a single map
+        const int a_map = m0 / rows_per_map;
+        const int a_row = m0 - a_map * rows_per_map;
+        const CUtensorMap* map_a_ptr = &maps_a.m[a_map];
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % stages;
+          const uint32_t phase = (it / stages) & 1;
+          mbar_wait(&empty_bar[s], phase ^ 1);
+          uint8_t* a_dst = smem + (size_t)s * STAGE_BYTES;
+          uint8_t* b_dst = a_dst + A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+          tma_load_2d(a_dst, map_a_ptr, &full_bar[s], kb * BK, a_row);
+          tma_load_2d(b_dst, &map_b, &full_bar[s], kb * BK, n0);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc(1, 1, BM, BN);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % stages;
-        const uint32_t phase = (kb / stages) & 1;
-        mbar_wait(&full_bar[s], phase);
+      uint32_t it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+        const uint32_t as = tcount & 1, aphase = (tcount >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[as], aphase ^ 1);  // epilogue drained this accumulator buffer
         tc_fence_after_sync();
-        const uint32_t a_addr = smem_u32(smem + (size_t)s * STAGE_BYTES);
-        const uint64_t da = umma_desc_k_sw128(a_addr);
-        const uint64_t db = umma_desc_k_sw128(a_addr + A_BYTES);
+        const uint32_t tmem_acc = tmem_base + as * ACC_COLS;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % stages;
+          const uint32_t phase = (it / stages) & 1;
+          mbar_wait(&full_bar[s], phase);
+          tc_fence_after_sync();
+          const uint32_t a_addr = smem_u32(smem + (size_t)s * STAGE_BYTES);
+          const uint64_t da = umma_desc_k_sw128(a_addr);
+          const uint64_t db = umma_desc_k_sw128(a_addr + A_BYTES);
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-          umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+            umma_bf16(tmem_acc, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
         }
-        umma_commit(&empty_bar[s]);
+        umma_commit(&tmem_full_bar[as]);
       }
-      umma_commit(tmem_full_bar);
     }
   } else {
-    // ---------------- epilogue: 4 warps, warp (w & 3) owns TMEM lanes [32*(w&3), 32*(w&3)+32)
+    // ---------------- epilogue: 8 warps; warp w may only touch TMEM lanes [32*(w&3), 32*(w&3)+32), and the two warps of
+    // a quadrant split the tile's columns
     const int q = warp & 3;
-    const int row = m0 + q * 32 + lane;
-    const bool row_ok = row < M;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after_sync();
-    const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-
-    if constexpr (EPI == 0) {
-      const bool vec_ok = ((se.ldo & 7) == 0) && (se.residual == nullptr || (se.ldr & 7) == 0);
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 16) {
-        uint32_t r[16];
-        tmem_ld16(taddr_row + c, r);
-        tmem_ld_wait();
-        const int col0 = n0 + c;
-        if (!row_ok || col0 >= N) continue;
-        float v[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int col = col0 + j;
-          float x = __uint_as_float(r[j]) * se.alpha;
-          if (col < N) {
-            if (se.col_scale) x *= se.col_scale[col];
-            if (se.bias) x += __bfloat162float(se.bias[col]);
-          }
-          v[j] = apply_act(x, se.act);
-        }
-        const bool full = (col0 + 16 <= N);
-        if (se.residual) {
-          const __nv_bfloat16* rp = se.residual + (size_t)row * se.ldr + col0;
-          if (full && vec_ok) {
-            uint4 ra = *reinterpret_cast<const uint4*>(rp), rb = *reinterpret_cast<const uint4*>(rp + 8);
-            const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&ra);
-            const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(&rb);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { v[j] += __bfloat162float(h[j]); v[8 + j] += __bfloat162float(g[j]); }
-          } else {
-            for (int j = 0; j < 16 && col0 + j < N; ++j) v[j] += __bfloat162float(rp[j]);
-          }
-        }
-        if (se.out_f32) {
-          float* op = reinterpret_cast<float*>(se.out) + (size_t)row * se.ldo + col0;
-          if (full && (se.ldo & 3) == 0) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-            for (int j = 0; j < 16 && col0 + j < N; ++j) op[j] = v[j];
-          }
-        } else {
-          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(se.out) + (size_t)row * se.ldo + col0;
-          if (full && vec_ok) {
-            uint4 pk[2];
-            __nv_bfloat162* p2 = reinterpret_cast<__nv_bfloat162*>(pk);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) p2[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-            *reinterpret_cast<uint4*>(op) = pk[0];
-            *reinterpret_cast<uint4*>(op + 8) = pk[1];
-          } else {
-            for (int j = 0; j < 16 && col0 + j < N; ++j) op[j] = __float2bfloat16(v[j]);
-          }
-        }
-      }
-    } else if constexpr (EPI == 2) {
-      const int owner = row_ok ? row / re.rows_per_rank : 0;
-      float* dst_row = row_ok ? re.acc[owner] + (size_t)(row - owner * re.rows_per_rank) * re.ldacc : nullptr;
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 16) {
-        uint32_t r[16];
-        tmem_ld16(taddr_row + c, r);
-        tmem_ld_wait();
-        const int col0 = n0 + c;
-        if (!row_ok || col0 >= N) continue;
-        float v[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          v[j] = __uint_as_float(r[j]);
-          if (se.bias && col0 + j < N) v[j] += __bfloat162float(se.bias[col0 + j]);  // only the rank that owns the bias passes it
-        }
-        if (col0 + 16 <= N && (re.ldacc & 3) == 0) {
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) red_add_v4_f32(dst_row + col0 + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
-        } else {
-          for (int j = 0; j < 16 && col0 + j < N; ++j) atomicAdd(dst_row + col0 + j, v[j]);
-        }
-      }
-    } else {
-      const long long label = (row_ok && le.labels) ? le.labels[row] : -1;
-      float mx = -INFINITY, sum = 0.f;
-      float best_key = -INFINITY, best_logit = 0.f;
-      int best_idx = -1;
-      const bool sampling = le.samp_key != nullptr;
-      const int step = le.step_ptr ? *le.step_ptr : 0;
-      const int suppress = (le.suppress_col >= 0 && step < le.suppress_until) ? le.suppress_col : -1;
-      const unsigned long long seed = le.seed + (le.seed_ptr ? (unsigned long long)(*le.seed_ptr) : 0ull) +
-                                      0x632BE59BD9B4E019ull * (unsigned long long)(step + 1);
-      const bool greedy = le.inv_temperature <= 0.f;
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 16) {
-        uint32_t r[16];
-        tmem_ld16(taddr_row + c, r);
-        tmem_ld_wait();
-        const int col0 = n0 + c;
-        if (!row_ok || col0 >= N) continue;
-        float z[16];
-        float cmax = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int col = col0 + j;
-          float x = -INFINITY;
-          if (col < N && col != suppress) {
-            x = __uint_as_float(r[j]);
-            if (le.bias) x += __bfloat162float(le.bias[col]);
-            if (col == label) le.label_logit[row] = x;
-          }
-          z[j] = x;
-          cmax = fmaxf(cmax, x);
-        }
-        if (cmax > mx) { sum *= __expf(mx - cmax); mx = cmax; }   // exp(-inf - finite) = 0 handles the first chunk
-        if (mx > -INFINITY) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) sum += __expf(z[j] - mx);
-        }
-        if (sampling) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            if (z[j] == -INFINITY) continue;
-            float key = z[j];
-            if (!greedy) key = z[j] * le.inv_temperature - __logf(-__logf(uniform01(seed, (unsigned)row, (unsigned)(col0 + j))));
-            if (key > best_key) { best_key = key; best_logit = z[j]; best_idx = col0 + j; }
-          }
-        }
-      }
-      if (row_ok) {
-        const size_t o = (size_t)row * le.n_tiles + blockIdx.x;
-        le.part_max[o] = mx;
-        le.part_sum[o] = sum;
-        if (sampling) { le.samp_key[o] = best_key; le.samp_logit[o] = best_logit; le.samp_idx[o] = best_idx; }
-      }
+    const int half = (warp - 2) >> 2;
+    const int c_lo = (BN >= 32) ? half * HALF : 0;
+    const int c_hi = (BN >= 32) ? c_lo + HALF : ((half == 0) ? BN : 0);
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      const uint32_t as = tcount & 1, aphase = (tcount >> 1) & 1;
+      const int m_idx = tile % m_tiles, n_idx = tile / m_tiles;
+      const int row = m_idx * BM + q * 32 + lane;
+      const bool row_ok = row < M;
+      mbar_wait(&tmem_full_bar[as], aphase);
+      tc_fence_after_sync();
+      const uint32_t taddr_row = tmem_base + as * ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
+      epilogue_cols<EPI>(taddr_row, row, row_ok, n_idx * BN, c_lo, c_hi, N, n_idx * 2 + half, se, le, re);
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
     }
-    tc_fence_before_sync();
   }
+  tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after_sync();
@@ -419,11 +483,24 @@ static bool make_map(CUtensorMap* map, const void* ptr, long long rows, long lon
   return true;
 }
 
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
 static int pick_bn(int M, int N) {
-  const int m_tiles = (M + BM - 1) / BM;
-  // prefer the widest tile that still yields >= ~1 wave of CTAs on 148 SMs
+  const long long m_tiles = (M + BM - 1) / BM;
+  const int sms = num_sms();
+  // 128x256 tiles halve the L2->SMEM traffic per flop; worth it once there are a few waves of them
+  if (m_tiles * ((N + 255) / 256) >= 3LL * sms) return 256;
+  // otherwise the widest tile that still gives every SM a tile
   for (int bn : {128, 64, 32}) {
-    if ((long long)m_tiles * ((N + bn - 1) / bn) >= 148) return bn;
+    if (m_tiles * ((N + bn - 1) / bn) >= sms) return bn;
   }
   return 32;
 }
@@ -437,7 +514,7 @@ static cudaError_t launch(const MapArray& ma, const CUtensorMap& mb, int M, int 
   int stages = (200 * 1024) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages > nkb) stages = nkb < 2 ? 2 : nkb;
-  const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;
+  const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 4) * 8 + 16 + 1024;
   auto kern = gemm_tn_kernel<BN, EPI>;
   static bool configured = false;
   if (!configured) {
@@ -445,7 +522,8 @@ static cudaError_t launch(const MapArray& ma, const CUtensorMap& mb, int M, int 
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+  const long long tiles = (long long)((N + BN - 1) / BN) * ((M + BM - 1) / BM);
+  dim3 grid((unsigned)(tiles < num_sms() ? tiles : num_sms()));  // persistent: one CTA per SM walks the tile list
   return launch_kernel(kern, grid, dim3(NUM_THREADS), smem, stream, ma, mb, M, N, K, stages, rows_per_map, se, le, re);
 }
 
@@ -470,11 +548,38 @@ extern "C" int b200_gemm_bf16(const void* A, const void* B, void* out, int M, in
   CUtensorMap mb;
   if (!make_map(&ma.m[0], A, M, K, lda, BM) || !make_map(&mb, B, N, K, ldb, bn)) return -1;
   StoreEpilogue se{out, (const __nv_bfloat16*)bias, (const __nv_bfloat16*)residual, col_scale, ldo, ldr, alpha, act, out_f32};
+  static const bool nostore = getenv("B200_GEMM_NOSTORE") != nullptr;
+  se.debug_nostore = nostore ? 1 : 0;
   LMHeadEpilogue le{};
   ReduceScatterEpilogue re{};
   const int rpm = 1 << 30;
   cudaError_t e;
   switch (bn) {
+    case 256: e = launch<256, 0>(ma, mb, M, N, K, rpm, se, le, re, stream); break;
+    case 128: e = launch<128, 0>(ma, mb, M, N, K, rpm, se, le, re, stream); break;
+    case 64: e = launch<64, 0>(ma, mb, M, N, K, rpm, se, le, re, stream); break;
+    default: e = launch<32, 0>(ma, mb, M, N, K, rpm, se, le, re, stream); break;
+  }
+  return (int)e;
+}
+
+// LM-head backward, fused: out[M, N] (bf16, row pitch ldo) = ((n == labels[m]) - exp(A.B^T + bias - lse[m])) * grad[m].
+// The logits are recomputed tile by tile and turned into d-logits in the epilogue (never stored as logits).
+extern "C" int b200_lmhead_dlogits_bf16(const void* A, const void* B, void* out, int M, int N, int K, long long lda,
+                                        long long ldb, long long ldo, const void* bias, const long long* labels,
+                                        const float* lse, const float* grad, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  const int bn = pick_bn(M, N);
+  MapArray ma{};
+  CUtensorMap mb;
+  if (!make_map(&ma.m[0], A, M, K, lda, BM) || !make_map(&mb, B, N, K, ldb, bn)) return -1;
+  StoreEpilogue se{out, (const __nv_bfloat16*)bias, nullptr, nullptr, ldo, 0, 1.0f, ACT_NONE, 0, lse, grad, labels};
+  LMHeadEpilogue le{};
+  ReduceScatterEpilogue re{};
+  const int rpm = 1 << 30;
+  cudaError_t e;
+  switch (bn) {
+    case 256: e = launch<256, 0>(ma, mb, M, N, K, rpm, se, le, re, stream); break;
     case 128: e = launch<128, 0>(ma, mb, M, N, K, rpm, se, le, re, stream); break;
     case 64: e = launch<64, 0>(ma, mb, M, N, K, rpm, se, le, re, stream); break;
     default: e = launch<32, 0>(ma, mb, M, N, K, rpm, se, le, re, stream); break;
@@ -501,6 +606,7 @@ extern "C" int b200_gemm_allgather_bf16(void* const* A_peers, int world, const v
   ReduceScatterEpilogue re{};
   cudaError_t e;
   switch (bn) {
+    case 256: e = launch<256, 0>(ma, mb, M, N, K, rows, se, le, re, stream); break;
     case 128: e = launch<128, 0>(ma, mb, M, N, K, rows, se, le, re, stream); break;
     case 64: e = launch<64, 0>(ma, mb, M, N, K, rows, se, le, re, stream); break;
     default: e = launch<32, 0>(ma, mb, M, N, K, rows, se, le, re, stream); break;
@@ -514,7 +620,8 @@ extern "C" int b200_gemm_reduce_scatter_bf16(const void* A, const void* B, float
                                              int K, long long lda, long long ldb, long long ldacc, const void* bias,
                                              cudaStream_t stream) {
   if (world < 1 || world > MAX_TP || M % world) return -3;
-  const int bn = pick_bn(M, N);
+  int bn = pick_bn(M, N);
+  if (bn > 128) bn = 128;
   MapArray ma{};
   CUtensorMap mb;
   if (!make_map(&ma.m[0], A, M, K, lda, BM) || !make_map(&mb, B, N, K, ldb, bn)) return -1;
@@ -560,7 +667,8 @@ extern "C" int b200_rs_finalize(const float* acc, const void* bias, const void* 
   return (int)cudaGetLastError();
 }
 
-extern "C" int b200_lmhead_tiles(int N) { return (N + 127) / 128; }
+// number of (row, column-range) partials the fused LM head emits per row: two epilogue warps split every 128-wide tile
+extern "C" int b200_lmhead_tiles(int N) { return 2 * ((N + 127) / 128); }
 
 // Fused LM head.  Workspace (fp32/int32) of 5 * M * n_tiles + M elements is supplied by the caller:
 //   part_max | part_sum | samp_key | samp_logit | samp_idx(int) | label_logit[M]
@@ -573,7 +681,7 @@ extern "C" int b200_lmhead_bf16(const void* H, const void* W, int M, int N, int 
                                 cudaStream_t stream) {
   if (M <= 0) return 0;
   constexpr int BN = 128;
-  const int n_tiles = (N + BN - 1) / BN;
+  const int n_tiles = b200_lmhead_tiles(N);
   MapArray ma{};
   CUtensorMap mb;
   if (!make_map(&ma.m[0], H, M, K, ldh, BM) || !make_map(&mb, W, N, K, ldw, BN)) return -1;

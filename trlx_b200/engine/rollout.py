@@ -206,7 +206,7 @@ class RolloutEngine:
         i32 = dict(dtype=torch.int32, device=dev)
         f32 = dict(dtype=torch.float32, device=dev)
         V = spec.vocab_size
-        n_tiles = (V + 127) // 128
+        n_tiles = int(ops.C.lmhead_tiles(V))  # partials per row emitted by the fused LM-head epilogue
         st = dict(
             B=B, Q=Q, R=R, P=P,
             allocator=ops.C.PagedKVAllocator(B * P, PAGE),

@@ -41,6 +41,26 @@ def sample_next(logits: torch.Tensor, do_sample: bool, temperature: float = 1.0,
     return torch.multinomial(torch.softmax(logits, -1), 1, generator=generator).squeeze(-1)
 
 
+def sample_sync_groups(model) -> list:
+    """``[(group, src)]`` of the model-parallel groups that must agree on sampled tokens (tensor / pipeline parallel
+    replicas of one model); empty for plain data parallelism."""
+    for m in model.modules():
+        groups = getattr(m, "_sample_sync", None)
+        if groups:
+            return list(groups)
+    return []
+
+
+def sync_tokens(tokens: torch.Tensor, groups: list) -> torch.Tensor:
+    if groups:
+        import torch.distributed as dist
+
+        tokens = tokens.contiguous()
+        for group, src in groups:
+            dist.broadcast(tokens, src=src, group=group)
+    return tokens
+
+
 def _ids(x) -> List[int]:
     if x is None:
         return []
@@ -83,6 +103,7 @@ def generate(model, input_ids: Optional[torch.Tensor] = None, attention_mask: Op
     min_new = max(int(min_new_tokens or 0), int(min_length or 0) - (1 if seq2seq else Q), 0)
 
     finished = torch.zeros(B, dtype=torch.bool, device=device)
+    sync = sample_sync_groups(model)
     eos_t = torch.tensor(eos_ids, device=device, dtype=torch.long) if eos_ids else None
 
     if seq2seq:
@@ -102,7 +123,7 @@ def generate(model, input_ids: Optional[torch.Tensor] = None, attention_mask: Op
                 logits[:, eos_ids] = float("-inf")
             for proc in logits_processor or []:
                 logits = proc(seqs, logits)
-            nxt = sample_next(logits, do_sample, temperature, top_k, top_p, generator)
+            nxt = sync_tokens(sample_next(logits, do_sample, temperature, top_k, top_p, generator), sync)
             nxt = torch.where(finished, torch.full_like(nxt, pad_token_id), nxt)
             seqs = torch.cat([seqs, nxt[:, None]], 1)
             if eos_t is not None:
@@ -129,7 +150,7 @@ def generate(model, input_ids: Optional[torch.Tensor] = None, attention_mask: Op
             logits[:, eos_ids] = float("-inf")
         for proc in logits_processor or []:
             logits = proc(seqs, logits)
-        nxt = sample_next(logits, do_sample, temperature, top_k, top_p, generator)
+        nxt = sync_tokens(sample_next(logits, do_sample, temperature, top_k, top_p, generator), sync)
         nxt = torch.where(finished, torch.full_like(nxt, pad_token_id), nxt)
         seqs = torch.cat([seqs, nxt[:, None]], 1)
         if eos_t is not None:

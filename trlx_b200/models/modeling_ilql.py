@@ -27,6 +27,7 @@ import torch.nn.functional as F
 from trlx_b200 import ops
 from trlx_b200.data.ilql_types import ILQLBatch
 from trlx_b200.data.method_configs import MethodConfig, register_method
+from trlx_b200.models.generation import sample_sync_groups, sync_tokens
 from trlx_b200.models.modeling_base import PreTrainedModelWrapper, base_lm, export_base_state_dict
 from trlx_b200.models.peft import PeftModel
 from trlx_b200.utils.modeling import flatten_dict, get_tensor_stats, make_head
@@ -297,6 +298,7 @@ class AutoModelForCausalLMWithILQLHeads(PreTrainedModelWrapper):
                 rows = logit_mask[last.clamp_max(logit_mask.shape[0] - 1)].to(logits.device).bool()
                 mask_row = rows & (last < logit_mask.shape[0]).to(rows.device).unsqueeze(-1)
             nxt = _ilql_sample(logits[:, -1], qs, vs[:, -1], beta, top_k, temperature, mask_row)
+            nxt = sync_tokens(nxt, sample_sync_groups(self))
             nxt = (1 - finished) * nxt + finished * eos_token_id
             finished = (nxt == eos_token_id).long()
             samples = torch.hstack((samples, nxt))

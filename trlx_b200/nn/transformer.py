@@ -301,6 +301,12 @@ class CausalLM(nn.Module):
                 inputs_embeds=None, use_cache=False, output_hidden_states=False, return_dict=True, labels=None,
                 hidden_in=None, start_layer: int = 0, stop_layer: Optional[int] = None, compute_logits: bool = True,
                 **_ignored):
+        pp = getattr(self, "_pp", None)
+        if pp is not None:  # this LM holds one pipeline stage (parallel/pipeline_parallel.py)
+            return pp.forward(input_ids=input_ids, attention_mask=attention_mask, position_ids=position_ids,
+                              past_key_values=past_key_values, inputs_embeds=inputs_embeds, use_cache=use_cache,
+                              output_hidden_states=output_hidden_states, labels=labels, compute_logits=compute_logits,
+                              hidden_in=hidden_in, start_layer=start_layer, stop_layer=stop_layer)
         spec, trunk = self.config, self.transformer
         ref = hidden_in if hidden_in is not None else (inputs_embeds if inputs_embeds is not None else input_ids)
         B, T = ref.shape[0], ref.shape[1]

@@ -89,7 +89,8 @@ def linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor] = None, a
 
 class _FusedLogprob(torch.autograd.Function):
     """log p(label | h) through the LM head without materialising logits in the forward.
-    Backward recomputes the logits tile-free as one bf16 GEMM and overwrites them with d-logits in place."""
+    Backward: one tcgen05 GEMM recomputes the logits tile by tile and emits d-logits straight from its epilogue
+    (``(onehot − softmax) · g``, bf16, row pitch padded to 64 so the two library GEMMs that consume it are aligned)."""
 
     @staticmethod
     def forward(ctx, h, w, b, labels):
@@ -107,8 +108,7 @@ class _FusedLogprob(torch.autograd.Function):
     def backward(ctx, g_lp, _g_lse):
         C = _ops().C
         h2, w, b, lab, lse = ctx.saved_tensors
-        logits = C.gemm(h2, w, b if ctx.has_bias else None, None, "none")
-        C.logprob_backward_inplace(logits, lab, lse, g_lp.reshape(-1).float().contiguous())
+        logits = C.lmhead_dlogits(h2, w, b if ctx.has_bias else None, lab, lse, g_lp.reshape(-1).float().contiguous())
         gh = gw = gb = None
         if ctx.needs_input_grad[0]:
             gh = (logits @ w).view(ctx.h_shape)
@@ -152,6 +152,10 @@ def gae_and_whiten(values, rewards, width: int, gamma: float, lam: float, use_wh
     Whitening matches the reference: unbiased variance in a single process, biased global variance across ranks
     (``trlx/utils/modeling.py:200-210``).  On CUDA: one scan kernel + (one small all-reduce) + one whiten kernel."""
     distributed = dist.is_available() and dist.is_initialized()
+    if distributed and group is None:
+        from trlx_b200.utils.modeling import statistics_group
+
+        group = statistics_group()
     ops = _ops()
     if values.is_cuda and ops.available():
         v = values.float().contiguous()

@@ -12,7 +12,31 @@ logger = logging.get_logger(__name__)
 
 
 class MegatronMixin:
-    """Overrides model setup (shard after construction) and checkpoint IO (``mp_rank_XX`` layout)."""
+    """Overrides model setup (shard after construction), the optimizer step under pipeline parallelism (1F1B over the
+    micro-batches) and checkpoint IO (``mp_rank_XX`` layout)."""
+
+    def __init__(self, config, **kwargs):
+        pp = int(getattr(config.train.parallel, "pipeline_parallel", 1) or 1)
+        if pp > 1:
+            if config.model.model_arch_type == "seq2seq":
+                raise NotImplementedError("pipeline parallelism covers decoder-only models")
+            if config.model.num_layers_unfrozen > 0:
+                logger.warning("pipeline parallelism: the hydra reference branch is replaced by a separate, equally "
+                               "partitioned reference model (num_layers_unfrozen → -1)")
+                config = config.evolve(model=dict(num_layers_unfrozen=-1))
+        super().__init__(config, **kwargs)
+        self._pp_stage = getattr(self, "_pp_stage", None)
+        ref = getattr(self, "ref_model", None)
+        if self._pp_stage is not None and ref is not None:
+            from trlx_b200.parallel.pipeline_parallel import apply_pipeline_parallel
+
+            rt = self.runtime
+            if rt.tp_size > 1:
+                from trlx_b200.parallel.tensor_parallel import apply_tensor_parallel
+
+                apply_tensor_parallel(ref, rt.tp_group, rt.tp_rank, rt.tp_size,
+                                      sequence_parallel=bool(self.config.train.parallel.sequence_parallel))
+            apply_pipeline_parallel(ref, rt.pp_group, rt.pp_rank, rt.pp_size)
 
     def setup_model(self):
         model = super().setup_model()
@@ -26,36 +50,79 @@ class MegatronMixin:
         if rt.pp_size > 1:
             from trlx_b200.parallel.pipeline_parallel import apply_pipeline_parallel
 
-            apply_pipeline_parallel(model, rt.pp_group, rt.pp_rank, rt.pp_size)
+            self._pp_stage = apply_pipeline_parallel(model, rt.pp_group, rt.pp_rank, rt.pp_size)
         return model
+
+    # ---- pipeline-parallel optimizer step -------------------------------------------------------------------------------
+    def train_step(self, minibatch):
+        stage = getattr(self, "_pp_stage", None)
+        if stage is None:
+            return super().train_step(minibatch)
+        from trlx_b200.parallel import pipeline_parallel as pp
+
+        microbatches = list(minibatch)
+        for _ in microbatches:
+            self.mb_count += 1
+        per_mb = pp.run_1f1b(stage, microbatches, self.loss, self.runtime.device,
+                             before_backward=self.model.train, after_backward=self.model.eval)
+        stats = None
+        if stage.last:
+            stats = {k: sum(s[k] for s in per_mb) / self.num_mb for k in per_mb[0]}
+        stats = pp.broadcast_stats(stage, stats, self.runtime.device)
+        self._pre_optimizer_step()
+        self.opt.step()
+        self.opt.zero_grad()
+        self.scheduler.step()
+        self.iter_count += 1
+        self._after_weights_changed()
+        stats["time/forward"] = 0.0
+        stats["time/backward"] = 0.0
+        return stats
+
+    def _after_weights_changed(self):
+        super()._after_weights_changed()
+        stage = getattr(self, "_pp_stage", None)
+        if stage is not None:
+            from trlx_b200.parallel.pipeline_parallel import broadcast_module_from_last
+
+            heads = [getattr(self.model, n) for n in ("v_head", "ilql_heads") if getattr(self.model, n, None) is not None]
+            broadcast_module_from_last(stage, heads)
 
     def _pre_optimizer_step(self):
         rt = self.runtime
+        stage = getattr(self, "_pp_stage", None)
+        if stage is not None:
+            from trlx_b200.parallel.pipeline_parallel import allreduce_tied_embedding_grads
+
+            allreduce_tied_embedding_grads(stage)
         if rt.tp_size > 1 and self.config.train.parallel.sequence_parallel:
             from trlx_b200.parallel.tensor_parallel import allreduce_sequence_parallel_grads
 
             allreduce_sequence_parallel_grads(self.model, rt.tp_group)
 
+    def _mp_subdir(self) -> str:
+        """Megatron naming: ``mp_rank_<tp>`` and, with pipeline stages, ``mp_rank_<tp>_<pp>``."""
+        rt = self.runtime
+        return f"mp_rank_{rt.tp_rank:02d}" + (f"_{rt.pp_rank:03d}" if rt.pp_size > 1 else "")
+
     def save_pretrained(self, directory: Optional[str] = None, **kwargs):
-        """``<dir>/mp_rank_XX/model_weights.ckpt`` per tensor-parallel rank (single file when TP == 1)."""
+        """``<dir>/mp_rank_XX[_YYY]/model_weights.ckpt`` per model-parallel rank (single file when TP == PP == 1).
+        The reference refuses to save with PP > 1 (``modeling_nemo_ppo.py:448-450``); here every stage writes its slice."""
         rt = self.runtime
         if rt.tp_size == 1 and rt.pp_size == 1:
             return super().save_pretrained(directory, **kwargs)
-        if rt.pp_size > 1:
-            raise NotImplementedError("saving with pipeline parallelism > 1 is not supported (same as the reference, "
-                                      "modeling_nemo_ppo.py:448-450); gather to PP=1 first")
         directory = directory or os.path.join(self.config.train.checkpoint_dir, "hf_model")
         rt.barrier()
         if rt.dp_rank == 0:
-            sub = os.path.join(directory, f"mp_rank_{rt.tp_rank:02d}")
+            sub = os.path.join(directory, self._mp_subdir())
             os.makedirs(sub, exist_ok=True)
-            torch.save({k: v.detach().cpu() for k, v in self.model.raw_state_dict().items()},
+            torch.save({k: v.detach().cpu() for k, v in self.model.raw_state_dict().items() if v.numel()},
                        os.path.join(sub, "model_weights.ckpt"))
         rt.barrier()
 
     def load_from_pretrained(self, directory: str):
         rt = self.runtime
-        sub = os.path.join(directory, f"mp_rank_{rt.tp_rank:02d}") if rt.tp_size > 1 else directory
+        sub = os.path.join(directory, self._mp_subdir()) if (rt.tp_size > 1 or rt.pp_size > 1) else directory
         sd = torch.load(os.path.join(sub, "model_weights.ckpt"), map_location="cpu", weights_only=True)
         own = self.model.raw_state_dict()
         with torch.no_grad():

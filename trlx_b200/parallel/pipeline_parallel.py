@@ -1,0 +1,406 @@
+"""Pipeline parallelism for the generic decoder (:class:`trlx_b200.nn.transformer.CausalLM`).
+
+Reference counterpart: the NeMo/Megatron path (``trlx/models/modeling_nemo_ppo.py:560-700`` drives Apex's
+``forward_backward_pipelining_without_interleaving``; configs ``configs/nemo_configs/*.yaml`` carry
+``pipeline_model_parallel_size``).  That path cannot be imported in the reference snapshot; this is a from-scratch design
+around the one-process-per-GPU runtime:
+
+* :func:`apply_pipeline_parallel` keeps a contiguous slice of the blocks on each stage (embeddings on the first, final
+  norm + LM head on the last; a tied embedding lives on both and its gradient is summed across the two before the
+  optimizer step) and installs a :class:`PipelineStage` on the LM.  The wrappers (value head, ILQL heads) and the
+  trainers' ``loss`` functions are unchanged.
+* **Inference / scoring** (no schedule active): a forward call relays the activation stage to stage with point-to-point
+  NCCL transfers over NVLink and the last stage broadcasts ``(final hidden, logits)`` to its pipeline group, so every
+  rank sees complete outputs (generation and ``make_experience`` run as-is).  With autograd enabled the relay is
+  differentiable: the send records a node whose backward *receives* the activation gradient from the next stage, so a
+  plain ``loss.backward()`` on every stage trains correctly (one micro-batch in flight).
+* **Training** (:func:`run_1f1b`): the non-interleaved one-forward-one-backward schedule over the micro-batches of an
+  optimizer step.  A stage runs the trainer's own ``loss(microbatch)``; on every stage but the last the LM raises
+  :class:`StageBoundary` as soon as its blocks are done, which hands the boundary activation to the schedule.  Steady
+  state uses grouped send/recv pairs (``batch_isend_irecv``) so that neighbouring stages, which are sending to each other
+  at the same moment, cannot deadlock.  The shape of the activation to receive is found by *probing* the loss function
+  (it is run up to the LM call with the stage in probe mode), so no shape handshake is exchanged.
+"""
+from __future__ import annotations
+
+from collections import deque
+from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from trlx_b200.utils import logging
+
+logger = logging.get_logger(__name__)
+
+
+class StageBoundary(Exception):
+    """Raised by a non-final stage's LM forward while a schedule is active (control flow, not an error)."""
+
+
+class _Hole(nn.Module):
+    """Stands in for a block owned by another stage (keeps ``transformer.h`` indices stable)."""
+
+    def forward(self, *a, **k):  # pragma: no cover - never called
+        raise RuntimeError("this block lives on another pipeline stage")
+
+
+def partition_layers(num_layers: int, stages: int) -> List[Tuple[int, int]]:
+    """Balanced contiguous split; earlier stages take the remainder (the last stage also carries the LM head)."""
+    base, rem = divmod(num_layers, stages)
+    out, lo = [], 0
+    for s in range(stages):
+        n = base + (1 if s < rem else 0)
+        out.append((lo, lo + n))
+        lo += n
+    return out
+
+
+# ---- differentiable relay ops (sequential mode) ---------------------------------------------------------------------------
+class _RecvFromPrev(torch.autograd.Function):
+    """forward: receive the activation from the previous stage; backward: send its gradient back."""
+
+    @staticmethod
+    def forward(ctx, anchor: torch.Tensor, stage: "PipelineStage", shape, dtype):
+        ctx.stage = stage
+        buf = torch.empty(shape, dtype=dtype, device=anchor.device)
+        dist.recv(buf, src=stage.prev_global, group=stage.group)
+        return buf
+
+    @staticmethod
+    def backward(ctx, grad):
+        dist.send(grad.contiguous(), dst=ctx.stage.prev_global, group=ctx.stage.group)
+        return None, None, None, None
+
+
+class _SendToNext(torch.autograd.Function):
+    """forward: send the activation on, return a zero scalar tied to the graph; backward: ignore the incoming (zero)
+    gradient, *receive* the real activation gradient from the next stage and return it."""
+
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, stage: "PipelineStage"):
+        ctx.stage, ctx.shape, ctx.dtype = stage, x.shape, x.dtype
+        dist.send(x.contiguous(), dst=stage.next_global, group=stage.group)
+        return x.new_zeros(())
+
+    @staticmethod
+    def backward(ctx, _):
+        g = torch.empty(ctx.shape, dtype=ctx.dtype, device=_.device)
+        dist.recv(g, src=ctx.stage.next_global, group=ctx.stage.group)
+        return g, None
+
+
+class PipelineStage:
+    """Per-LM pipeline state + the stage-local forward."""
+
+    def __init__(self, lm, group, rank: int, size: int):
+        self.lm, self.group, self.rank, self.size = lm, group, rank, size
+        self.first, self.last = rank == 0, rank == size - 1
+        ranks = dist.get_process_group_ranks(group) if group is not None else list(range(size))
+        self.global_ranks = ranks
+        self.prev_global = ranks[rank - 1] if rank > 0 else None
+        self.next_global = ranks[rank + 1] if rank < size - 1 else None
+        self.last_global = ranks[-1]
+        self.lo, self.hi = partition_layers(len(lm.transformer.h), size)[rank]
+        # schedule hand-off
+        self.mode = "relay"  # "relay" | "schedule" | "probe"
+        self.input_tensor: Optional[torch.Tensor] = None
+        self.output_tensor: Optional[torch.Tensor] = None
+        self.probe_shape: Optional[Tuple[int, ...]] = None
+
+    # -- forward ----------------------------------------------------------------------------------------------------------
+    def forward(self, input_ids=None, attention_mask=None, position_ids=None, past_key_values=None, inputs_embeds=None,
+                use_cache=False, output_hidden_states=False, labels=None, compute_logits: bool = True,
+                hidden_in=None, start_layer: int = 0, stop_layer: Optional[int] = None, **_ignored):
+        from trlx_b200.nn.transformer import CausalLMOutput, build_attn_context, project
+
+        if hidden_in is not None or start_layer or stop_layer is not None:
+            raise NotImplementedError("layer-sliced forwards (hydra / trunk cache) are not available under pipeline parallelism")
+        lm, spec, trunk = self.lm, self.lm.config, self.lm.transformer
+        ref = inputs_embeds if inputs_embeds is not None else input_ids
+        B, T = ref.shape[0], ref.shape[1]
+        device, dtype = ref.device, self.param_dtype()
+        hshape = (B, T, spec.hidden_size)
+        if self.mode == "probe":
+            self.probe_shape = hshape
+            raise StageBoundary()
+        past_len = past_key_values[0][0].shape[2] if past_key_values else 0
+        if position_ids is None:
+            if attention_mask is not None:
+                position_ids = (attention_mask.long().cumsum(-1) - 1).clamp_min(0)[:, -T:]
+            else:
+                position_ids = torch.arange(past_len, past_len + T, device=device).unsqueeze(0).expand(B, T)
+        grad_mode = torch.is_grad_enabled()
+
+        if self.first:
+            if inputs_embeds is not None:
+                x = inputs_embeds
+                if trunk.wpe is not None:
+                    x = x + trunk.wpe(position_ids + spec.pos_offset)
+                if trunk.emb_norm is not None:
+                    x = trunk.emb_norm(x)
+            else:
+                x = trunk.embed(input_ids, position_ids)
+        elif self.mode == "schedule":
+            x = self.input_tensor
+            assert x is not None and tuple(x.shape) == hshape, "pipeline schedule handed over a mismatched activation"
+        elif grad_mode:
+            anchor = torch.zeros((), device=device, requires_grad=True)
+            x = _RecvFromPrev.apply(anchor, self, hshape, dtype)
+        else:
+            x = torch.empty(hshape, dtype=dtype, device=device)
+            dist.recv(x, src=self.prev_global, group=self.group)
+
+        ctx = build_attn_context(spec, attention_mask, position_ids, T, past_len, x.dtype, device)
+        presents = [] if use_cache else None
+        for j, i in enumerate(range(self.lo, self.hi)):
+            past = past_key_values[j] if past_key_values else None
+            x, present = trunk.h[i](x, ctx, past, use_cache)
+            if presents is not None:
+                presents.append(present)
+        if use_cache and not presents:  # a stage without blocks still has to report the cache length
+            presents = [(x.new_zeros(B, 1, past_len + T, 1), x.new_zeros(B, 1, past_len + T, 1))]
+
+        if self.mode == "schedule" and not self.last:
+            self.output_tensor = x
+            raise StageBoundary()
+
+        logits = None
+        if self.last:
+            x = trunk.ln_f(x)
+            if compute_logits:
+                logits = project(lm.lm_head, x)
+            if self.mode == "relay":
+                self._broadcast_outputs(x, logits, compute_logits)
+        else:  # relay, non-final stage
+            phantom = None
+            if grad_mode:
+                if not x.requires_grad:  # fully frozen stage: the next stage still returns a gradient, consume it
+                    x = x.detach().requires_grad_(True)
+                phantom = _SendToNext.apply(x, self)
+            else:
+                dist.send(x.contiguous(), dst=self.next_global, group=self.group)
+            x = torch.empty(hshape, dtype=dtype, device=device)
+            logits = torch.empty((B, T, spec.vocab_size), dtype=dtype, device=device) if compute_logits else None
+            self._broadcast_outputs(x, logits, compute_logits)
+            if phantom is not None:  # ties the (complete, but constant) outputs to this stage's graph
+                x = x + phantom.to(x.dtype)
+                if logits is not None:
+                    logits = logits + phantom.to(logits.dtype)
+        loss = None
+        if labels is not None and logits is not None:
+            import torch.nn.functional as F
+
+            loss = F.cross_entropy(logits[:, :-1].reshape(-1, logits.shape[-1]).float(), labels[:, 1:].reshape(-1),
+                                   ignore_index=-100)
+        return CausalLMOutput(logits=logits, past_key_values=presents,
+                              hidden_states=(x,) if output_hidden_states else None, loss=loss, last_hidden_state=x)
+
+    def param_dtype(self):
+        for p in self.lm.parameters():
+            return p.dtype
+        return torch.float32
+
+    def _broadcast_outputs(self, x, logits, with_logits: bool):
+        dist.broadcast(x.detach() if self.last else x, src=self.last_global, group=self.group)
+        if with_logits:
+            dist.broadcast(logits.detach() if self.last else logits, src=self.last_global, group=self.group)
+
+
+# ---- installation ----------------------------------------------------------------------------------------------------------
+def _find_lm(model):
+    from trlx_b200.nn.transformer import CausalLM
+
+    if isinstance(model, CausalLM):
+        return model
+    for m in model.modules():
+        if isinstance(m, CausalLM):
+            return m
+    raise TypeError("pipeline parallelism needs a decoder-only CausalLM inside the model")
+
+
+def apply_pipeline_parallel(model, group, rank: int, size: int) -> PipelineStage:
+    """Keep this stage's slice of ``model``'s decoder, free the rest, install the stage forward."""
+    lm = _find_lm(model)
+    if getattr(lm, "_pp", None) is not None:
+        return lm._pp
+    stage = PipelineStage(lm, group, rank, size)
+    trunk = lm.transformer
+    for i in range(len(trunk.h)):
+        if not (stage.lo <= i < stage.hi):
+            trunk.h[i] = _Hole()
+    tied = lm.lm_head.weight is trunk.wte.weight
+    stage.tied = tied
+    if not stage.first and not (tied and stage.last):
+        trunk.wte.weight.requires_grad_(False)
+        trunk.wte.weight.data = trunk.wte.weight.data.new_empty(0)
+    if not stage.first:
+        if trunk.wpe is not None:
+            trunk.wpe.weight.requires_grad_(False)
+            trunk.wpe.weight.data = trunk.wpe.weight.data.new_empty(0)
+        if trunk.emb_norm is not None:
+            for p in trunk.emb_norm.parameters():
+                p.requires_grad_(False)
+    if not stage.last:
+        for p in trunk.ln_f.parameters():
+            p.requires_grad_(False)
+        if not tied:
+            lm.lm_head.weight.requires_grad_(False)
+            lm.lm_head.weight.data = lm.lm_head.weight.data.new_empty(0)
+            if lm.lm_head.bias is not None:
+                lm.lm_head.bias.requires_grad_(False)
+    lm._pp = stage
+    if size > 1:  # every stage continues a generation with the token the last stage sampled (generation.sync_tokens)
+        lm._sample_sync = getattr(lm, "_sample_sync", []) + [(group, stage.last_global)]
+    logger.info(f"pipeline stage {rank}/{size}: blocks [{stage.lo}, {stage.hi}) of {len(trunk.h)}"
+                f"{' +embeddings' if stage.first else ''}{' +lm_head' if stage.last else ''}")
+    return stage
+
+
+def allreduce_tied_embedding_grads(stage: PipelineStage):
+    """A tied embedding is used by the first stage (lookup) and the last (LM head): sum the two gradients."""
+    if not getattr(stage, "tied", False) or stage.size == 1:
+        return
+    w = stage.lm.transformer.wte.weight
+    if stage.first or stage.last:
+        g = w.grad if w.grad is not None else torch.zeros_like(w)
+    else:
+        g = None
+    # the whole pipeline group takes part (cheap, and avoids building a {first,last} sub-group): middle stages add zeros
+    if g is None:
+        H = stage.lm.config.hidden_size
+        g = torch.zeros(stage.lm.config.vocab_size, H, dtype=stage.param_dtype(), device=next(stage.lm.parameters()).device)
+    dist.all_reduce(g, group=stage.group)
+    if stage.first or stage.last:
+        w.grad = g
+
+
+# ---- point-to-point helpers for the schedule --------------------------------------------------------------------------------
+def _exchange(stage: PipelineStage, send_next=None, send_prev=None, recv_prev_shape=None, recv_next_shape=None,
+              dtype=None, device=None):
+    """One grouped round of point-to-point transfers with the neighbours.  Returns ``(from_prev, from_next)``."""
+    ops, from_prev, from_next = [], None, None
+    if send_prev is not None:
+        ops.append(dist.P2POp(dist.isend, send_prev.contiguous(), stage.prev_global, stage.group))
+    if recv_prev_shape is not None:
+        from_prev = torch.empty(recv_prev_shape, dtype=dtype, device=device)
+        ops.append(dist.P2POp(dist.irecv, from_prev, stage.prev_global, stage.group))
+    if send_next is not None:
+        ops.append(dist.P2POp(dist.isend, send_next.contiguous(), stage.next_global, stage.group))
+    if recv_next_shape is not None:
+        from_next = torch.empty(recv_next_shape, dtype=dtype, device=device)
+        ops.append(dist.P2POp(dist.irecv, from_next, stage.next_global, stage.group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return from_prev, from_next
+
+
+def run_1f1b(stage: PipelineStage, microbatches: Sequence[Any], loss_fn: Callable[[Any], Tuple[torch.Tensor, Dict]],
+             device, loss_scale: float = 1.0, before_backward: Optional[Callable] = None,
+             after_backward: Optional[Callable] = None) -> List[Optional[Dict]]:
+    """Non-interleaved 1F1B over ``microbatches``.  ``loss_fn(mb) → (loss, stats)`` is the trainer's loss; gradients
+    accumulate into ``.grad``.  Returns the per-micro-batch stats on the last stage (``None`` elsewhere)."""
+    M, P, r = len(microbatches), stage.size, stage.rank
+    dtype = stage.param_dtype()
+    warm = min(P - 1 - r, M)
+    steady = M - warm
+    pending: deque = deque()  # (input leaf, output) in forward order
+    stats: List[Optional[Dict]] = []
+
+    def probe(mb):
+        if stage.first:
+            return None
+        stage.mode = "probe"
+        try:
+            with torch.no_grad():
+                loss_fn(mb)
+            raise RuntimeError("the loss function never called the language model")
+        except StageBoundary:
+            return stage.probe_shape
+        finally:
+            stage.mode = "relay"
+
+    def forward(mb, x):
+        if x is not None:
+            x.requires_grad_(True)
+        stage.mode, stage.input_tensor, stage.output_tensor = "schedule", x, None
+        try:
+            loss, st = loss_fn(mb)
+            if not stage.last:
+                raise RuntimeError("a non-final stage completed its loss function; the LM was not called")
+            out = loss * loss_scale
+            stats.append(st)
+        except StageBoundary:
+            out = stage.output_tensor
+            stats.append(None)
+        finally:
+            stage.mode, stage.input_tensor = "relay", None
+        pending.append((x, out))
+        return out
+
+    def backward(gy):
+        x, y = pending.popleft()
+        if before_backward is not None:
+            before_backward()
+        if stage.last:
+            y.backward()
+        elif y.requires_grad:  # (a fully frozen first stage has nothing to differentiate)
+            torch.autograd.backward(y, gy)
+        if after_backward is not None:
+            after_backward()
+        return None if x is None else x.grad
+
+    kw = dict(dtype=dtype, device=device)
+    # warm-up: forwards only
+    for k in range(warm):
+        x, _ = _exchange(stage, recv_prev_shape=probe(microbatches[k]), **kw)
+        y = forward(microbatches[k], x)
+        _exchange(stage, send_next=y.detach(), **kw)
+    x = None
+    if steady > 0:
+        x, _ = _exchange(stage, recv_prev_shape=probe(microbatches[warm]), **kw)
+    # steady state: one forward, one backward
+    for i in range(steady):
+        k = warm + i
+        y = forward(microbatches[k], x)
+        gy = None
+        if not stage.last:
+            _, gy = _exchange(stage, send_next=y.detach(), recv_next_shape=tuple(pending[0][1].shape), **kw)
+        gx = backward(gy)
+        nxt_shape = probe(microbatches[k + 1]) if i < steady - 1 else None
+        if stage.first:
+            x = None
+        else:
+            x, _ = _exchange(stage, send_prev=gx, recv_prev_shape=nxt_shape, **kw)
+    # cool-down: remaining backwards
+    for _ in range(warm):
+        y = pending[0][1]
+        _, gy = _exchange(stage, recv_next_shape=tuple(y.shape), **kw)
+        gx = backward(gy)
+        if not stage.first:
+            _exchange(stage, send_prev=gx, **kw)
+    return stats
+
+
+def broadcast_stats(stage: PipelineStage, stats: Optional[Dict[str, Any]], device) -> Dict[str, Any]:
+    """Ship the last stage's (scalar) statistics to the whole pipeline group."""
+    keys = [sorted(stats.keys())] if stage.last else [None]
+    dist.broadcast_object_list(keys, src=stage.last_global, group=stage.group)
+    names = keys[0]
+    if stage.last:
+        vals = torch.stack([torch.as_tensor(stats[k], dtype=torch.float32, device=device).reshape(()) for k in names])
+    else:
+        vals = torch.empty(len(names), dtype=torch.float32, device=device)
+    dist.broadcast(vals, src=stage.last_global, group=stage.group)
+    return {k: vals[i] for i, k in enumerate(names)}
+
+
+def broadcast_module_from_last(stage: PipelineStage, modules: Sequence[nn.Module]):
+    """Heads (value / Q heads) are trained on the last stage only; refresh the replicas the other stages use when they
+    score samples."""
+    for m in modules:
+        for p in m.parameters():
+            if p.numel():
+                dist.broadcast(p.data, src=stage.last_global, group=stage.group)

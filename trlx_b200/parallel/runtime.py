@@ -69,6 +69,9 @@ class Runtime:
         self.dp_rank = (self.rank // tp) % self.dp_size
         self.pp_rank = self.rank // (tp * self.dp_size)
         self.tp_group = self.dp_group = self.pp_group = None
+        from trlx_b200.utils.modeling import set_statistics_group
+
+        set_statistics_group(None)
         if not self.distributed or (tp == 1 and pp == 1):
             self.dp_group = None  # WORLD
             return
@@ -90,6 +93,12 @@ class Runtime:
                 g = dist.new_group(ranks)
                 if self.rank in ranks:
                     self.pp_group = g
+        set_statistics_group(self.dp_group)  # model-parallel peers hold identical data: statistics span DP only
+
+    @property
+    def is_replica_leader(self) -> bool:
+        """One rank per model replica (first tensor-parallel rank of the first pipeline stage)."""
+        return self.tp_rank == 0 and self.pp_rank == 0
 
     @property
     def is_main_process(self) -> bool:

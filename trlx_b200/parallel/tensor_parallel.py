@@ -322,6 +322,8 @@ def apply_tensor_parallel(model, group, rank: int, size: int, sequence_parallel:
             if branch is not None and hasattr(branch, "final_norm"):
                 _gather_before(branch.final_norm, tp)
     model.tp_context = tp
+    if group is not None and size > 1:  # sampled tokens are taken from the group's first rank (generation.sync_tokens)
+        lm._sample_sync = getattr(lm, "_sample_sync", []) + [(group, dist.get_process_group_ranks(group)[0])]
     tp.enable_fused_kernels(next(lm.parameters()).device)
     return tp
 

@@ -148,8 +148,22 @@ class AccelerateRLTrainer(BaseRLTrainer):
         model = model.to(self.runtime.device)
         if self.runtime.cuda and self.runtime.dtype != torch.float32:
             model = model.to(self.runtime.dtype)
+        self._sync_initial_weights(model)
         model.eval()
         return model
+
+    def _sync_initial_weights(self, model):
+        """Every rank starts from rank 0's weights (randomly initialised heads / from-config models are seeded per data-
+        parallel rank).  The reference gets this from DDP's constructor broadcast inside ``accelerator.prepare``
+        (``accelerate_base_trainer.py:71``); here it also guarantees identical full weights before TP/PP sharding."""
+        if not self.runtime.distributed:
+            return
+        import torch.distributed as dist
+
+        with torch.no_grad():
+            for t in list(model.parameters()) + list(model.buffers()):
+                if t.numel():
+                    dist.broadcast(t.data, src=0)
 
     def setup_optimizer(self):
         optimizer_class = get_optimizer_class(self.config.optimizer.name)
@@ -318,11 +332,12 @@ class AccelerateRLTrainer(BaseRLTrainer):
             suffix = f"@{sweep_arg}={sweep_value}" if sweep_value is not None else ""
             all_samples, all_prompts, all_sizes, all_meta = [], [], [], []
             t0 = time()
-            world, rank = self.runtime.world_size, self.runtime.rank
+            # eval batches are dealt round-robin to the model replicas (all TP/PP ranks of a replica run the same batch)
+            world, rank = self.runtime.dp_size, self.runtime.dp_rank
             for i_prompt, prompts in enumerate(self.eval_dataloader):
                 tbar.set_description(f"[generation sweep {i_sweep + 1}/{len(sweep_values)} | eval batch {i_prompt + 1}/{len(self.eval_dataloader)}]")
                 tbar.update()
-                if i_prompt % world != rank:  # eval batches are dealt round-robin to the ranks
+                if i_prompt % world != rank:
                     continue
                 metadata = {k: v for k, v in prompts.items() if k not in ("input_ids", "attention_mask")}
                 extra = {sweep_arg: sweep_value} if self.generate_sweep_kwarg else {}
@@ -334,6 +349,8 @@ class AccelerateRLTrainer(BaseRLTrainer):
                 all_sizes.extend([prompts["input_ids"].shape[1]] * len(prompts["input_ids"]))
                 all_meta.append(metadata)
             if self.runtime.distributed:  # one pickled gather per sweep value instead of collectives per batch
+                if not self.runtime.is_replica_leader:  # model-parallel peers hold duplicates of their leader's samples
+                    all_samples, all_prompts, all_sizes, all_meta = [], [], [], []
                 shards = self.runtime.gather_objects((all_samples, all_prompts, all_sizes, all_meta))
                 all_samples = sum((sh[0] for sh in shards), [])
                 all_prompts = sum((sh[1] for sh in shards), [])

@@ -69,7 +69,7 @@ class AcceleratePPOTrainer(AccelerateRLTrainer):
             self.ref_model = self.get_arch(self.config).to(self.runtime.device)
             if self.runtime.cuda and self.runtime.dtype != torch.float32:
                 self.ref_model = self.ref_model.to(self.runtime.dtype)
-            self.ref_model.load_state_dict(self.model.raw_state_dict(), strict=False)
+            self.ref_model.load_state_dict({k: v for k, v in self.model.raw_state_dict().items() if v.numel()}, strict=False)
             self.ref_model.eval().requires_grad_(False)
 
         if config.method.target is not None:

@@ -48,7 +48,7 @@ def train(  # noqa: C901
         else:
             config = default_sft_config()
 
-    set_seed(config.train.seed)
+    set_seed(config.train.seed, config.train.parallel)
 
     if dataset:
         warnings.warn("the `dataset` argument is being depreciated, split it into `samples` and `rewards` instead")

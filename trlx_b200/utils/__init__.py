@@ -60,9 +60,16 @@ def significant(x: Any, ndigits: int = 2) -> Any:
     return round(x, ndigits - magnitude)
 
 
-def set_seed(seed: int) -> None:
-    """Seed python / numpy / torch with ``seed + RANK`` (so DP ranks sample different rollouts)."""
-    seed = int(seed) + rank()
+def set_seed(seed: int, parallel=None) -> None:
+    """Seed python / numpy / torch with ``seed + data-parallel rank``: DP replicas sample different rollouts, while the
+    tensor/pipeline-parallel ranks of one replica share a stream (``rank = (pp·DP + dp)·TP + tp``, parallel/runtime.py)."""
+    r = rank()
+    if parallel is not None:
+        tp = max(int(getattr(parallel, "tensor_parallel", 1) or 1), 1)
+        pp = max(int(getattr(parallel, "pipeline_parallel", 1) or 1), 1)
+        dp = max(int(os.environ.get("WORLD_SIZE", "1")) // (tp * pp), 1)
+        r = (r // tp) % dp
+    seed = int(seed) + r
     random.seed(seed)
     np.random.seed(seed % (2**32))
     torch.manual_seed(seed)

@@ -149,8 +149,24 @@ def _merge_moments(stats: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, tor
     return mean, m2 / tot.clamp_min(1e-24), tot
 
 
+_STATS_GROUP = None
+
+
+def set_statistics_group(group) -> None:
+    """Default process group of the global statistics (whitening, running moments).  The runtime points it at the
+    data-parallel group when tensor/pipeline-parallel peers (which hold *identical* data, and under a pipeline schedule
+    are at different micro-batches at any moment) share the world."""
+    global _STATS_GROUP
+    _STATS_GROUP = group
+
+
+def statistics_group(group=None):
+    return _STATS_GROUP if group is None else group
+
+
 def get_global_statistics(xs: torch.Tensor, group=None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """Global ``(mean, biased variance, count)`` of ``xs`` over ``group`` in one collective."""
+    group = statistics_group(group)
     local = _local_moments(xs)
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         bucket = local.new_empty((dist.get_world_size(group), 3))
