@@ -29,6 +29,10 @@ if which in ("all", "gemm"):
     a, w, b = t(1792, 768), t(3072, 768), t(3072)  # training MLP up-projection + GELU
     for _ in range(3):
         C.gemm(a, w, b, None, "gelu_tanh")
+if which in ("all", "dlogits"):
+    a, w = t(1280, 768), t(50304, 768)            # LM-head backward recompute shape (short K, huge N)
+    for _ in range(2):
+        C.gemm(a, w, None, None, "none")
 if which in ("all", "lmhead"):
     h, w = t(1280, 768), t(50257, 768)
     lab = torch.randint(0, 50257, (1280,), device=dev)

@@ -29,6 +29,7 @@ constexpr int BK = 64;        // bf16 elements per k-block = one 128-byte swizzl
 constexpr int UMMA_K = 16;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
+constexpr int STG_BYTES = 4096;   // per epilogue warp: 32 rows x 128 B staging for the TMA-store epilogue
 
 enum Act { ACT_NONE = 0, ACT_GELU_TANH = 1, ACT_GELU_ERF = 2, ACT_RELU = 3, ACT_SILU = 4 };
 
@@ -46,6 +47,7 @@ struct StoreEpilogue {
   const float* dl_grad;
   const long long* dl_labels;
   int debug_nostore;
+  int tma_store;              // bf16 output goes through shared memory + cp.async.bulk.tensor (needs ldo % 8 == 0)
 };
 
 constexpr int MAX_TP = 8;
@@ -103,10 +105,33 @@ __device__ __forceinline__ void red_add_v4_f32(float* addr, float a, float b, fl
 }
 
 // Epilogue bodies: one output row per thread, columns [c_lo, c_hi) of the current tile's accumulator.
-template <int EPI>
+// v[j] = act(alpha * acc * col_scale + bias)  (or the d-logits transform) for 16 consecutive columns starting at col0
+__device__ __forceinline__ void store_values(const uint32_t (&r)[16], float (&v)[16], int col0, int N, const StoreEpilogue& se,
+                                             bool dl, float dl_l, float dl_g, long long dl_lab) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int col = col0 + j;
+    float x = __uint_as_float(r[j]) * se.alpha;
+    if (col < N) {
+      if (se.col_scale) x *= se.col_scale[col];
+      if (se.bias) x += __bfloat162float(se.bias[col]);
+    }
+    if (dl) {
+      const float pr = __expf(x - dl_l);
+      x = (dl_lab < 0) ? 0.f : (((long long)col == dl_lab ? 1.f : 0.f) - pr) * dl_g;
+    }
+    v[j] = apply_act(x, se.act);
+  }
+}
+
+// Epilogue bodies: one output row per thread, columns [c_lo, c_hi) of the current tile's accumulator.
+//   stg      : this warp's 4 KB shared-memory staging buffer (TMA-store path)
+//   map_out  : tensor map of the bf16 output (TMA-store path; box = CW columns x 32 rows, swizzle = CW*2 bytes)
+template <int EPI, int CW>
 __device__ __forceinline__ void epilogue_cols(uint32_t taddr_row, int row, bool row_ok, int n0, int c_lo, int c_hi, int N,
                                               int part_idx, const StoreEpilogue& se, const LMHeadEpilogue& le,
-                                              const ReduceScatterEpilogue& re) {
+                                              const ReduceScatterEpilogue& re, uint8_t* stg, const CUtensorMap* map_out,
+                                              int row0_warp, int lane) {
   if constexpr (EPI == 0) {
     const bool vec_ok = ((se.ldo & 7) == 0) && (se.residual == nullptr || (se.ldr & 7) == 0);
     // d-logits mode (LM-head backward): out = ((col == label) - exp(logit - lse[row])) * grad[row]
@@ -114,6 +139,59 @@ __device__ __forceinline__ void epilogue_cols(uint32_t taddr_row, int row, bool 
     float dl_l = 0.f, dl_g = 0.f;
     long long dl_lab = -1;
     if (dl && row_ok) { dl_l = se.dl_lse[row]; dl_g = se.dl_grad[row]; dl_lab = se.dl_labels[row]; }
+    if (se.tma_store) {
+      // registers -> (swizzled) shared memory -> one bulk tensor store per 32 x CW chunk: full-line, coalesced global
+      // writes instead of 32 scattered 32-byte row fragments per warp instruction; TMA clips rows >= M / cols >= N.
+      constexpr int ROWB = CW * 2;                                  // bytes per staged row: 128 / 64 / 32
+      constexpr uint32_t SW_MASK = ROWB == 128 ? 7u : (ROWB == 64 ? 3u : 1u);
+      const uint32_t stg_u32 = smem_u32(stg);
+#pragma unroll 1
+      for (int c = c_lo; c < c_hi; c += CW) {
+        if (lane == 0) tma_store_wait_read();   // the previous chunk's store has drained the staging buffer
+        __syncwarp();
+        if (n0 + c >= N) continue;
+#pragma unroll
+        for (int cc = 0; cc < CW; cc += 16) {
+          uint32_t r[16];
+          tmem_ld16(taddr_row + c + cc, r);
+          tmem_ld_wait();
+          const int col0 = n0 + c + cc;
+          float v[16];
+          store_values(r, v, col0, N, se, dl, dl_l, dl_g, dl_lab);
+          if (se.residual && row_ok) {
+            const __nv_bfloat16* rp = se.residual + (size_t)row * se.ldr + col0;
+            if (col0 + 16 <= N && vec_ok) {
+              uint4 ra = *reinterpret_cast<const uint4*>(rp), rb = *reinterpret_cast<const uint4*>(rp + 8);
+              const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&ra);
+              const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(&rb);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { v[j] += __bfloat162float(h[j]); v[8 + j] += __bfloat162float(g[j]); }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (col0 + j < N) v[j] += __bfloat162float(rp[j]);
+            }
+          }
+          uint4 pk[2];
+          __nv_bfloat162* p2 = reinterpret_cast<__nv_bfloat162*>(pk);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) p2[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t off = (uint32_t)lane * ROWB + (uint32_t)(cc * 2 + h * 16);
+            off ^= ((off >> 7) & SW_MASK) << 4;                     // the TMA swizzle: 16-byte unit ^= (128-byte row index)
+            st_shared_v4(stg_u32 + off, pk[h]);
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(map_out, stg, n0 + c, row0_warp);
+          tma_store_commit();
+        }
+      }
+      return;
+    }
 #pragma unroll 1
     for (int c = c_lo; c < c_hi; c += 16) {
       uint32_t r[16];
@@ -122,20 +200,7 @@ __device__ __forceinline__ void epilogue_cols(uint32_t taddr_row, int row, bool 
       const int col0 = n0 + c;
       if (!row_ok || col0 >= N) continue;
       float v[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int col = col0 + j;
-        float x = __uint_as_float(r[j]) * se.alpha;
-        if (col < N) {
-          if (se.col_scale) x *= se.col_scale[col];
-          if (se.bias) x += __bfloat162float(se.bias[col]);
-        }
-        if (dl) {
-          const float pr = __expf(x - dl_l);
-          x = (dl_lab < 0) ? 0.f : (((long long)col == dl_lab ? 1.f : 0.f) - pr) * dl_g;
-        }
-        v[j] = apply_act(x, se.act);
-      }
+      store_values(r, v, col0, N, se, dl, dl_l, dl_g, dl_lab);
       const bool full = (col0 + 16 <= N);
       if (se.debug_nostore) {  // experiment: keep the math, drop the global stores
         float acc = 0.f;
@@ -153,7 +218,9 @@ __device__ __forceinline__ void epilogue_cols(uint32_t taddr_row, int row, bool 
 #pragma unroll
           for (int j = 0; j < 8; ++j) { v[j] += __bfloat162float(h[j]); v[8 + j] += __bfloat162float(g[j]); }
         } else {
-          for (int j = 0; j < 16 && col0 + j < N; ++j) v[j] += __bfloat162float(rp[j]);
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (col0 + j < N) v[j] += __bfloat162float(rp[j]);
         }
       }
       if (se.out_f32) {
@@ -162,7 +229,9 @@ __device__ __forceinline__ void epilogue_cols(uint32_t taddr_row, int row, bool 
 #pragma unroll
           for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         } else {
-          for (int j = 0; j < 16 && col0 + j < N; ++j) op[j] = v[j];
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (col0 + j < N) op[j] = v[j];
         }
       } else {
         __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(se.out) + (size_t)row * se.ldo + col0;
@@ -174,7 +243,9 @@ __device__ __forceinline__ void epilogue_cols(uint32_t taddr_row, int row, bool 
           *reinterpret_cast<uint4*>(op) = pk[0];
           *reinterpret_cast<uint4*>(op + 8) = pk[1];
         } else {
-          for (int j = 0; j < 16 && col0 + j < N; ++j) op[j] = __float2bfloat16(v[j]);
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (col0 + j < N) op[j] = __float2bfloat16(v[j]);
         }
       }
     }
@@ -262,19 +333,22 @@ __device__ __forceinline__ void epilogue_cols(uint32_t taddr_row, int row, bool 
 // TMEM (2 x BN fp32 columns), so the epilogue of tile i overlaps the TMA/MMA mainloop of tile i+1.
 template <int BN, int EPI>  // EPI: 0 = store, 1 = lm-head, 2 = reduce-scatter into peer accumulators
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tn_kernel(const __grid_constant__ MapArray maps_a, const __grid_constant__ CUtensorMap map_b, int M, int N, int K,
-               int stages, int rows_per_map, StoreEpilogue se, LMHeadEpilogue le, ReduceScatterEpilogue re) {
+gemm_tn_kernel(const __grid_constant__ MapArray maps_a, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ CUtensorMap map_out, int M, int N, int K, int stages, int rows_per_map,
+               StoreEpilogue se, LMHeadEpilogue le, ReduceScatterEpilogue re) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr uint32_t A_BYTES = BM * BK * 2;
   constexpr uint32_t B_BYTES = BN * BK * 2;
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t ACC_COLS = BN < 32 ? 32 : BN;   // TMEM columns of one accumulator buffer
   constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;
-  constexpr int HALF = BN >= 32 ? BN / 2 : BN;        // columns per epilogue warp (two warps share a TMEM lane quadrant)
+  constexpr int HALF = BN / 2;                        // columns per epilogue warp (two warps share a TMEM lane quadrant)
 
   // 1024-byte aligned base (dynamic smem alignment is only guaranteed to 16 B)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)stages * STAGE_BYTES);
+  constexpr int CW = HALF < 64 ? HALF : 64;           // columns per staged output chunk (TMA-store epilogue)
+  uint8_t* stage_out = smem + (size_t)stages * STAGE_BYTES;  // NUM_EPI_WARPS x 4 KB, 1024-byte aligned
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_out + NUM_EPI_WARPS * STG_BYTES);
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* tmem_full_bar = empty_bar + stages;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
@@ -289,6 +363,7 @@ gemm_tn_kernel(const __grid_constant__ MapArray maps_a, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps_a.m[0]);
     tma_prefetch_desc(&map_b);
+    if (EPI == 0 && se.tma_store) tma_prefetch_desc(&map_out);
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -365,8 +440,8 @@ gemm_tn_kernel(const __grid_constant__ MapArray maps_a, const __grid_constant__ 
     // a quadrant split the tile's columns
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
-    const int c_lo = (BN >= 32) ? half * HALF : 0;
-    const int c_hi = (BN >= 32) ? c_lo + HALF : ((half == 0) ? BN : 0);
+    const int c_lo = half * HALF, c_hi = c_lo + HALF;
+    uint8_t* stg = stage_out + (size_t)(warp - 2) * STG_BYTES;
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
       const uint32_t as = tcount & 1, aphase = (tcount >> 1) & 1;
@@ -376,11 +451,13 @@ gemm_tn_kernel(const __grid_constant__ MapArray maps_a, const __grid_constant__ 
       mbar_wait(&tmem_full_bar[as], aphase);
       tc_fence_after_sync();
       const uint32_t taddr_row = tmem_base + as * ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
-      epilogue_cols<EPI>(taddr_row, row, row_ok, n_idx * BN, c_lo, c_hi, N, n_idx * 2 + half, se, le, re);
+      epilogue_cols<EPI, CW>(taddr_row, row, row_ok, n_idx * BN, c_lo, c_hi, N, n_idx * 2 + half, se, le, re, stg, &map_out,
+                             m_idx * BM + q * 32, lane);
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
     }
+    if (EPI == 0 && se.tma_store && lane == 0) tma_store_wait_all();  // bulk stores must land before the CTA retires
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -456,12 +533,14 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// K-major bf16 matrix [rows, cols] with row pitch ld (elements); box = box_rows x 64 elements, 128B swizzle.
-static bool make_map(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
-  using Key = std::tuple<const void*, long long, long long, long long, int>;
+// Row-major bf16 matrix [rows, cols] with row pitch ld (elements); box = box_rows x box_cols elements, swizzle span =
+// box_cols * 2 bytes (128 / 64 / 32).  Operand loads use 64-column (128-byte) boxes.
+static bool make_map(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_rows,
+                     int box_cols = BK) {
+  using Key = std::tuple<const void*, long long, long long, long long, int, int>;
   static std::map<Key, CUtensorMap> cache;
   static std::mutex mu;
-  Key key{ptr, rows, cols, ld, box_rows};
+  Key key{ptr, rows, cols, ld, box_rows, box_cols};
   {
     std::lock_guard<std::mutex> g(mu);
     auto it = cache.find(key);
@@ -471,11 +550,12 @@ static bool make_map(CUtensorMap* map, const void* ptr, long long rows, long lon
   if (!fn) return false;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapSwizzle sw = box_cols >= 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : (box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return false;
   std::lock_guard<std::mutex> g(mu);
   if (cache.size() > 4096) cache.clear();
@@ -506,15 +586,16 @@ static int pick_bn(int M, int N) {
 }
 
 template <int BN, int EPI>
-static cudaError_t launch(const MapArray& ma, const CUtensorMap& mb, int M, int N, int K, int rows_per_map,
-                          const StoreEpilogue& se, const LMHeadEpilogue& le, const ReduceScatterEpilogue& re,
-                          cudaStream_t stream) {
+static cudaError_t launch(const MapArray& ma, const CUtensorMap& mb, const CUtensorMap& mo, int M, int N, int K,
+                          int rows_per_map, const StoreEpilogue& se, const LMHeadEpilogue& le,
+                          const ReduceScatterEpilogue& re, cudaStream_t stream) {
   constexpr int stage_bytes = BM * BK * 2 + BN * BK * 2;
+  constexpr int fixed_bytes = NUM_EPI_WARPS * STG_BYTES + 1024 /*alignment slack*/ + 512 /*barriers*/;
   const int nkb = (K + BK - 1) / BK;
-  int stages = (200 * 1024) / stage_bytes;
+  int stages = (227 * 1024 - fixed_bytes) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages > nkb) stages = nkb < 2 ? 2 : nkb;
-  const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 4) * 8 + 16 + 1024;
+  const size_t smem = (size_t)stages * stage_bytes + fixed_bytes;
   auto kern = gemm_tn_kernel<BN, EPI>;
   static bool configured = false;
   if (!configured) {
@@ -524,7 +605,18 @@ static cudaError_t launch(const MapArray& ma, const CUtensorMap& mb, int M, int 
   }
   const long long tiles = (long long)((N + BN - 1) / BN) * ((M + BM - 1) / BM);
   dim3 grid((unsigned)(tiles < num_sms() ? tiles : num_sms()));  // persistent: one CTA per SM walks the tile list
-  return launch_kernel(kern, grid, dim3(NUM_THREADS), smem, stream, ma, mb, M, N, K, stages, rows_per_map, se, le, re);
+  return launch_kernel(kern, grid, dim3(NUM_THREADS), smem, stream, ma, mb, mo, M, N, K, stages, rows_per_map, se, le, re);
+}
+
+// Route a bf16 [M, N] output (row pitch ldo) through the TMA-store epilogue when the pitch allows a tensor map.
+static bool setup_tma_store(StoreEpilogue& se, CUtensorMap* mo, int M, int N, int bn) {
+  static const bool disabled = getenv("B200_GEMM_DIRECT_STORE") != nullptr;
+  se.tma_store = 0;
+  if (disabled || se.out_f32 || se.debug_nostore || (se.ldo & 7) || (reinterpret_cast<uintptr_t>(se.out) & 15)) return true;
+  const int cw = bn / 2 < 64 ? bn / 2 : 64;
+  if (!make_map(mo, se.out, M, N, se.ldo, 32, cw)) return false;
+  se.tma_store = 1;
+  return true;
 }
 
 static bool g_pdl = true;
@@ -550,15 +642,17 @@ extern "C" int b200_gemm_bf16(const void* A, const void* B, void* out, int M, in
   StoreEpilogue se{out, (const __nv_bfloat16*)bias, (const __nv_bfloat16*)residual, col_scale, ldo, ldr, alpha, act, out_f32};
   static const bool nostore = getenv("B200_GEMM_NOSTORE") != nullptr;
   se.debug_nostore = nostore ? 1 : 0;
+  CUtensorMap mo{};
+  if (!setup_tma_store(se, &mo, M, N, bn)) return -1;
   LMHeadEpilogue le{};
   ReduceScatterEpilogue re{};
   const int rpm = 1 << 30;
   cudaError_t e;
   switch (bn) {
-    case 256: e = launch<256, 0>(ma, mb, M, N, K, rpm, se, le, re, stream); break;
-    case 128: e = launch<128, 0>(ma, mb, M, N, K, rpm, se, le, re, stream); break;
-    case 64: e = launch<64, 0>(ma, mb, M, N, K, rpm, se, le, re, stream); break;
-    default: e = launch<32, 0>(ma, mb, M, N, K, rpm, se, le, re, stream); break;
+    case 256: e = launch<256, 0>(ma, mb, mo, M, N, K, rpm, se, le, re, stream); break;
+    case 128: e = launch<128, 0>(ma, mb, mo, M, N, K, rpm, se, le, re, stream); break;
+    case 64: e = launch<64, 0>(ma, mb, mo, M, N, K, rpm, se, le, re, stream); break;
+    default: e = launch<32, 0>(ma, mb, mo, M, N, K, rpm, se, le, re, stream); break;
   }
   return (int)e;
 }
@@ -574,15 +668,17 @@ extern "C" int b200_lmhead_dlogits_bf16(const void* A, const void* B, void* out,
   CUtensorMap mb;
   if (!make_map(&ma.m[0], A, M, K, lda, BM) || !make_map(&mb, B, N, K, ldb, bn)) return -1;
   StoreEpilogue se{out, (const __nv_bfloat16*)bias, nullptr, nullptr, ldo, 0, 1.0f, ACT_NONE, 0, lse, grad, labels};
+  CUtensorMap mo{};
+  if (!setup_tma_store(se, &mo, M, N, bn)) return -1;
   LMHeadEpilogue le{};
   ReduceScatterEpilogue re{};
   const int rpm = 1 << 30;
   cudaError_t e;
   switch (bn) {
-    case 256: e = launch<256, 0>(ma, mb, M, N, K, rpm, se, le, re, stream); break;
-    case 128: e = launch<128, 0>(ma, mb, M, N, K, rpm, se, le, re, stream); break;
-    case 64: e = launch<64, 0>(ma, mb, M, N, K, rpm, se, le, re, stream); break;
-    default: e = launch<32, 0>(ma, mb, M, N, K, rpm, se, le, re, stream); break;
+    case 256: e = launch<256, 0>(ma, mb, mo, M, N, K, rpm, se, le, re, stream); break;
+    case 128: e = launch<128, 0>(ma, mb, mo, M, N, K, rpm, se, le, re, stream); break;
+    case 64: e = launch<64, 0>(ma, mb, mo, M, N, K, rpm, se, le, re, stream); break;
+    default: e = launch<32, 0>(ma, mb, mo, M, N, K, rpm, se, le, re, stream); break;
   }
   return (int)e;
 }
@@ -602,14 +698,16 @@ extern "C" int b200_gemm_allgather_bf16(void* const* A_peers, int world, const v
     if (!make_map(&ma.m[r], A_peers[r], rows, K, lda, BM)) return -1;
   if (!make_map(&mb, B, N, K, ldb, bn)) return -1;
   StoreEpilogue se{out, (const __nv_bfloat16*)bias, nullptr, nullptr, ldo, 0, 1.0f, act, 0};
+  CUtensorMap mo{};
+  if (!setup_tma_store(se, &mo, M, N, bn)) return -1;
   LMHeadEpilogue le{};
   ReduceScatterEpilogue re{};
   cudaError_t e;
   switch (bn) {
-    case 256: e = launch<256, 0>(ma, mb, M, N, K, rows, se, le, re, stream); break;
-    case 128: e = launch<128, 0>(ma, mb, M, N, K, rows, se, le, re, stream); break;
-    case 64: e = launch<64, 0>(ma, mb, M, N, K, rows, se, le, re, stream); break;
-    default: e = launch<32, 0>(ma, mb, M, N, K, rows, se, le, re, stream); break;
+    case 256: e = launch<256, 0>(ma, mb, mo, M, N, K, rows, se, le, re, stream); break;
+    case 128: e = launch<128, 0>(ma, mb, mo, M, N, K, rows, se, le, re, stream); break;
+    case 64: e = launch<64, 0>(ma, mb, mo, M, N, K, rows, se, le, re, stream); break;
+    default: e = launch<32, 0>(ma, mb, mo, M, N, K, rows, se, le, re, stream); break;
   }
   return (int)e;
 }
@@ -626,6 +724,7 @@ extern "C" int b200_gemm_reduce_scatter_bf16(const void* A, const void* B, float
   CUtensorMap mb;
   if (!make_map(&ma.m[0], A, M, K, lda, BM) || !make_map(&mb, B, N, K, ldb, bn)) return -1;
   StoreEpilogue se{};
+  CUtensorMap mo{};
   se.bias = (const __nv_bfloat16*)bias;
   LMHeadEpilogue le{};
   ReduceScatterEpilogue re{};
@@ -635,9 +734,9 @@ extern "C" int b200_gemm_reduce_scatter_bf16(const void* A, const void* B, float
   const int rpm = 1 << 30;
   cudaError_t e;
   switch (bn) {
-    case 128: e = launch<128, 2>(ma, mb, M, N, K, rpm, se, le, re, stream); break;
-    case 64: e = launch<64, 2>(ma, mb, M, N, K, rpm, se, le, re, stream); break;
-    default: e = launch<32, 2>(ma, mb, M, N, K, rpm, se, le, re, stream); break;
+    case 128: e = launch<128, 2>(ma, mb, mo, M, N, K, rpm, se, le, re, stream); break;
+    case 64: e = launch<64, 2>(ma, mb, mo, M, N, K, rpm, se, le, re, stream); break;
+    default: e = launch<32, 2>(ma, mb, mo, M, N, K, rpm, se, le, re, stream); break;
   }
   return (int)e;
 }
@@ -703,8 +802,9 @@ extern "C" int b200_lmhead_bf16(const void* H, const void* W, int M, int N, int 
   le.suppress_until = suppress_until;
   le.n_tiles = n_tiles;
   StoreEpilogue se{};
+  CUtensorMap mo{};
   ReduceScatterEpilogue re{};
-  cudaError_t e = launch<BN, 1>(ma, mb, M, N, K, 1 << 30, se, le, re, stream);
+  cudaError_t e = launch<BN, 1>(ma, mb, mo, M, N, K, 1 << 30, se, le, re, stream);
   if (e != cudaSuccess) return (int)e;
   const int warps_per_block = 8;
   return (int)launch_kernel(lmhead_reduce_kernel, dim3((M + warps_per_block - 1) / warps_per_block),

@@ -1,0 +1,295 @@
+"""Hyper-parameter sweeps:  ``python -m trlx_b200.sweep --config configs/sweeps/ppo_sweep.yml examples/ppo_sentiments.py``
+
+Reference counterpart: ``trlx/sweep.py`` (Ray Tune + W&B reports): parameter-space strategies ``:16-98``, search
+algorithms / schedulers ``:103-176``, the report ``:178-265``, the CLI ``:268-348``.  Same YAML schema and CLI, but no Ray
+and no W&B dependency: trials are plain subprocesses (``python -m torch.distributed.run`` when a trial uses several GPUs)
+scheduled over the node's GPUs, each logging through the ``jsonl`` tracker; the sweep reads the target metric back from
+those logs, supports ``random`` and grid search with ``fifo`` or successive-halving (``asha`` / ``hyperband`` names)
+scheduling, and writes ``sweep_results.json`` + a Markdown report (best trials, parameter table) instead of a W&B report.
+
+An example script only has to expose ``main(hparams: dict)`` (every script under ``examples/`` does).
+"""
+from __future__ import annotations
+
+import argparse
+import itertools
+import json
+import math
+import os
+import random
+import subprocess
+import sys
+import time
+from datetime import datetime
+from typing import Any, Dict, Iterator, List, Optional, Tuple
+
+import yaml
+
+STRATEGIES = ("uniform", "quniform", "loguniform", "qloguniform", "randn", "qrandn", "randint", "qrandint", "lograndint",
+              "qlograndint", "choice", "grid_search", "grid")
+
+
+def _quantize(x: float, q: float) -> float:
+    return round(x / q) * q
+
+
+def sample_value(spec: Dict[str, Any], rng: random.Random):
+    """One draw from a ``{strategy, values}`` entry (grid strategies are expanded by :func:`iter_trials`)."""
+    strategy, v = spec["strategy"], spec["values"]
+    if strategy not in STRATEGIES:
+        raise ValueError(f"unknown search strategy `{strategy}`; expected one of {STRATEGIES}")
+    if strategy == "uniform":
+        lo, hi = v
+        return rng.uniform(lo, hi)
+    if strategy == "quniform":
+        lo, hi, q = v
+        return _quantize(rng.uniform(lo, hi), q)
+    if strategy in ("loguniform", "qloguniform"):
+        lo, hi = v[0], v[1]
+        base = v[2] if strategy == "loguniform" and len(v) > 2 else 10
+        x = base ** rng.uniform(math.log(lo, base), math.log(hi, base))
+        return _quantize(x, v[2]) if strategy == "qloguniform" else x
+    if strategy == "randn":
+        mean, sd = v
+        return rng.gauss(mean, sd)
+    if strategy == "qrandn":
+        mean, sd, q = v
+        return _quantize(rng.gauss(mean, sd), q)
+    if strategy == "randint":
+        lo, hi = v
+        return rng.randrange(int(lo), int(hi))
+    if strategy == "qrandint":
+        lo, hi, q = v
+        return int(_quantize(rng.randrange(int(lo), int(hi) + 1), q))
+    if strategy in ("lograndint", "qlograndint"):
+        lo, hi = v[0], v[1]
+        x = int(math.exp(rng.uniform(math.log(lo), math.log(hi))))
+        return int(_quantize(x, v[2])) if strategy == "qlograndint" else x
+    if strategy == "choice":
+        return rng.choice(list(v))
+    return rng.choice(list(v))  # grid entries sampled at random when a random search touches them
+
+
+def get_param_space(config: Dict[str, Any]) -> Dict[str, Dict[str, Any]]:
+    """Validate and return ``{dotted.key: {strategy, values}}`` (everything but ``tune_config``)."""
+    space = {}
+    for key, spec in config.items():
+        if key == "tune_config":
+            continue
+        if not isinstance(spec, dict) or "strategy" not in spec or "values" not in spec:
+            raise ValueError(f"sweep entry `{key}` must be a mapping with `strategy` and `values`")
+        if spec["strategy"] not in STRATEGIES:
+            raise ValueError(f"sweep entry `{key}`: unknown strategy `{spec['strategy']}`")
+        if not isinstance(spec["values"], list):
+            raise ValueError(f"sweep entry `{key}`: `values` must be a list")
+        space[key] = spec
+    return space
+
+
+def iter_trials(space: Dict[str, Dict[str, Any]], tune_config: Dict[str, Any], seed: int = 0) -> Iterator[Dict[str, Any]]:
+    """Grid entries are enumerated exhaustively; the remaining entries are re-sampled ``num_samples`` times per grid point
+    (Ray Tune semantics)."""
+    rng = random.Random(seed)
+    grid_keys = [k for k, s in space.items() if s["strategy"] in ("grid_search", "grid")]
+    other = [k for k in space if k not in grid_keys]
+    num_samples = int(tune_config.get("num_samples", 1))
+    search = str(tune_config.get("search_alg", "random")).lower()
+    if search not in ("random", "grid"):
+        print(f"[sweep] search_alg `{search}` needs a Bayesian-optimisation package that is not bundled; using random search")
+    grids = itertools.product(*[space[k]["values"] for k in grid_keys]) if grid_keys else [()]
+    for point in grids:
+        for _ in range(num_samples):
+            hp = dict(zip(grid_keys, point))
+            for k in other:
+                hp[k] = sample_value(space[k], rng)
+            yield hp
+
+
+# ---- running trials ------------------------------------------------------------------------------------------------------------
+_TRIAL_SNIPPET = """
+import importlib.util, json, sys
+spec = importlib.util.spec_from_file_location("sweep_target", sys.argv[1])
+mod = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(mod)
+mod.main(json.loads(sys.argv[2]))
+"""
+
+
+def launch_trial(script: str, hparams: Dict[str, Any], trial_dir: str, gpus: List[int], budget_steps: Optional[int],
+                 default_config: Optional[str]) -> subprocess.Popen:
+    os.makedirs(trial_dir, exist_ok=True)
+    hp = dict(hparams)
+    hp.setdefault("train.tracker", "jsonl")
+    hp.setdefault("train.logging_dir", trial_dir)
+    hp.setdefault("train.checkpoint_dir", os.path.join(trial_dir, "ckpts"))
+    if budget_steps is not None:
+        hp["train.total_steps"] = int(budget_steps)
+    env = dict(os.environ)
+    if gpus:
+        env["CUDA_VISIBLE_DEVICES"] = ",".join(str(g) for g in gpus)
+    if default_config:
+        env["TRLX_B200_DEFAULT_CONFIG"] = default_config
+    with open(os.path.join(trial_dir, "hparams.json"), "w") as fh:
+        json.dump(hparams, fh, indent=2, default=str)
+    runner = os.path.join(trial_dir, "_run_trial.py")
+    with open(runner, "w") as fh:
+        fh.write(_TRIAL_SNIPPET)
+    if len(gpus) > 1:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={len(gpus)}", "--standalone",
+               "--local-addr", "127.0.0.1", runner, script, json.dumps(hp)]
+    else:
+        cmd = [sys.executable, runner, script, json.dumps(hp)]
+    log = open(os.path.join(trial_dir, "stdout.log"), "w")
+    return subprocess.Popen(cmd, env=env, stdout=log, stderr=subprocess.STDOUT)
+
+
+def read_metric(trial_dir: str, metric: str, mode: str) -> Tuple[Optional[float], Optional[float], int]:
+    """``(best, last, n_points)`` of ``metric`` over every jsonl log of a trial."""
+    values: List[float] = []
+    for name in sorted(os.listdir(trial_dir)):
+        if not name.endswith(".jsonl"):
+            continue
+        with open(os.path.join(trial_dir, name)) as fh:
+            for line in fh:
+                try:
+                    rec = json.loads(line)
+                except json.JSONDecodeError:
+                    continue
+                if metric in rec and isinstance(rec[metric], (int, float)) and math.isfinite(rec[metric]):
+                    values.append(float(rec[metric]))
+    if not values:
+        return None, None, 0
+    return (max(values) if mode == "max" else min(values)), values[-1], len(values)
+
+
+def run_sweep(script: str, sweep_config: Dict[str, Any], out_dir: str, num_gpus: int = 1, gpu_ids: Optional[List[int]] = None,
+              default_config: Optional[str] = None, seed: int = 0, poll: float = 1.0) -> List[Dict[str, Any]]:
+    tune_config = dict(sweep_config.get("tune_config", {}))
+    metric, mode = tune_config.get("metric", "reward/mean"), tune_config.get("mode", "max")
+    scheduler = str(tune_config.get("scheduler", "fifo")).lower()
+    space = get_param_space(sweep_config)
+    trials = [dict(id=i, hparams=hp) for i, hp in enumerate(iter_trials(space, tune_config, seed))]
+    os.makedirs(out_dir, exist_ok=True)
+    if gpu_ids is None:
+        try:
+            import torch
+
+            gpu_ids = list(range(torch.cuda.device_count()))
+        except Exception:  # pragma: no cover
+            gpu_ids = []
+    slots: List[List[int]] = ([gpu_ids[i:i + num_gpus] for i in range(0, len(gpu_ids) - num_gpus + 1, num_gpus)]
+                              if gpu_ids and num_gpus > 0 else [[]])
+    max_conc = int(tune_config.get("max_concurrent_trials", len(slots)))
+    if slots == [[]]:  # CPU-only node: concurrency is bounded by the config alone
+        slots = [[] for _ in range(max(max_conc, 1))]
+    slots = slots[:max(max_conc, 1)]
+
+    # successive halving ("asha"/"hyperband"/"bohb" schedulers): rungs of growing step budget, keep the top 1/eta
+    if scheduler in ("hyperband", "asha", "bohb", "median"):
+        max_t = int(tune_config.get("max_t", tune_config.get("max_steps", 0)) or 0)
+        eta = int(tune_config.get("reduction_factor", 3))
+        grace = int(tune_config.get("grace_period", max(max_t // (eta ** 2), 1))) if max_t else None
+        rungs = []
+        t = grace
+        while max_t and t < max_t:
+            rungs.append(t)
+            t *= eta
+        rungs.append(max_t if max_t else None)
+    else:
+        if scheduler != "fifo":
+            print(f"[sweep] unknown scheduler `{scheduler}`; running every trial to completion (fifo)")
+        rungs, eta = [None], 1
+
+    alive = trials
+    for rung_i, budget in enumerate(rungs):
+        pending = list(alive)
+        running: List[Tuple[Dict[str, Any], subprocess.Popen, List[int]]] = []
+        free = list(slots)
+        while pending or running:
+            while pending and free:
+                tr = pending.pop(0)
+                slot = free.pop(0)
+                tdir = os.path.join(out_dir, f"trial_{tr['id']:04d}", f"rung_{rung_i}")
+                tr["dir"] = tdir
+                proc = launch_trial(script, tr["hparams"], tdir, slot, budget, default_config)
+                running.append((tr, proc, slot))
+                print(f"[sweep] trial {tr['id']} (rung {rung_i}, budget {budget}) started on gpus {slot}: {tr['hparams']}")
+            time.sleep(poll)
+            for item in list(running):
+                tr, proc, slot = item
+                rc = proc.poll()
+                if rc is None:
+                    continue
+                running.remove(item)
+                free.append(slot)
+                best, last, n = read_metric(tr["dir"], metric, mode)
+                tr.update(returncode=rc, best=best, last=last, points=n, budget=budget)
+                print(f"[sweep] trial {tr['id']} finished rc={rc} {metric}: best={best} last={last}")
+        if rung_i < len(rungs) - 1:
+            scored = [t for t in alive if t.get("best") is not None]
+            scored.sort(key=lambda t: t["best"], reverse=(mode == "max"))
+            alive = scored[:max(len(scored) // eta, 1)]
+    results = sorted(trials, key=lambda t: (t.get("best") is None, -(t.get("best") or 0) if mode == "max" else (t.get("best") or 0)))
+    with open(os.path.join(out_dir, "sweep_results.json"), "w") as fh:
+        json.dump(dict(metric=metric, mode=mode, script=script, trials=results), fh, indent=2, default=str)
+    write_report(results, space, metric, mode, script, os.path.join(out_dir, "report.md"))
+    return results
+
+
+def write_report(results, space, metric: str, mode: str, script: str, path: str) -> None:
+    """Markdown stand-in for the reference's W&B report: best configuration, full trial table, per-parameter view."""
+    keys = list(space)
+    lines = [f"# Sweep report — `{script}`", "", f"Target metric: `{metric}` ({mode}); {len(results)} trials; "
+             f"generated {datetime.now().isoformat(timespec='seconds')}", ""]
+    done = [r for r in results if r.get("best") is not None]
+    if done:
+        best = done[0]
+        lines += ["## Best configuration", "", "```json", json.dumps(best["hparams"], indent=2, default=str), "```",
+                  f"`{metric}` = {best['best']:.6g}", ""]
+    lines += ["## Trials", "", "| trial | " + " | ".join(keys) + f" | best {metric} | last | points | rc |",
+              "|---|" + "---|" * (len(keys) + 4)]
+    for r in results:
+        vals = " | ".join(f"{r['hparams'].get(k):.4g}" if isinstance(r["hparams"].get(k), float) else str(r["hparams"].get(k))
+                          for k in keys)
+        b = "-" if r.get("best") is None else f"{r['best']:.5g}"
+        la = "-" if r.get("last") is None else f"{r['last']:.5g}"
+        lines.append(f"| {r['id']} | {vals} | {b} | {la} | {r.get('points', 0)} | {r.get('returncode')} |")
+    if done:
+        lines += ["", "## Parameter view (trials sorted by each parameter)", ""]
+        for k in keys:
+            pts = sorted(((r["hparams"].get(k), r["best"]) for r in done), key=lambda p: str(p[0]))
+            lines.append(f"* `{k}`: " + ", ".join(f"{v if not isinstance(v, float) else format(v, '.3g')}→{b:.4g}" for v, b in pts))
+    with open(path, "w") as fh:
+        fh.write("\n".join(lines) + "\n")
+
+
+def main(argv: Optional[List[str]] = None) -> int:
+    parser = argparse.ArgumentParser(description=__doc__.split("\n")[0])
+    parser.add_argument("script", type=str, help="Path to the example script (must define main(hparams))")
+    parser.add_argument("--config", type=str, required=True, help="Param-space YAML (configs/sweeps/*.yml)")
+    parser.add_argument("--default_config", type=str, default=None, help="Default TRLConfig YAML for the script")
+    parser.add_argument("--num_gpus", type=int, default=1, help="GPUs (ranks) per trial")
+    parser.add_argument("--num_cpus", type=int, default=4, help="Accepted for CLI compatibility (unused)")
+    parser.add_argument("--output_dir", type=str, default=None, help="Where trial logs and the report go")
+    parser.add_argument("--seed", type=int, default=0)
+    parser.add_argument("-y", "--assume_yes", action="store_true", help="Don't ask for confirmation")
+    parser.add_argument("--server_address", type=str, default=None, help="Accepted for CLI compatibility (no Ray cluster)")
+    args = parser.parse_args(argv)
+    with open(args.config) as fh:
+        sweep_config = yaml.safe_load(fh)
+    out = args.output_dir or os.path.join("sweeps", os.path.splitext(os.path.basename(args.script))[0] + "_"
+                                          + datetime.now().strftime("%Y%m%d_%H%M%S"))
+    print(f'Running `main(hparams)` of "{args.script}" for every trial; results in {out}')
+    if not args.assume_yes and sys.stdin.isatty():
+        if input("Proceed? [y/N] ").strip().lower() not in ("y", "yes"):
+            return 1
+    results = run_sweep(args.script, sweep_config, out, num_gpus=args.num_gpus, default_config=args.default_config,
+                        seed=args.seed)
+    ok = [r for r in results if r.get("best") is not None]
+    print(f"[sweep] {len(ok)}/{len(results)} trials reported `{sweep_config.get('tune_config', {}).get('metric')}`; "
+          f"report: {os.path.join(out, 'report.md')}")
+    return 0 if ok else 2
+
+
+if __name__ == "__main__":
+    sys.exit(main())
