@@ -259,16 +259,16 @@ class TRLConfig:
         """
         nested: Dict[str, Any] = {}
         for dotted, value in config.items():
-            if isinstance(value, dict):
-                nested[dotted] = _merge_dicts(nested.get(dotted, {}), value)
-                continue
             *parents, leaf = dotted.split(".")
-            if not parents:
+            if not parents and not isinstance(value, dict):
                 continue  # a bare scalar at top level carries no section → ignored like the reference
             cursor = nested
             for p in parents:
                 cursor = cursor.setdefault(p, {})
-            cursor[leaf] = value
+            if isinstance(value, dict) and isinstance(cursor.get(leaf), dict) and leaf not in _ATOMIC_KEYS:
+                cursor[leaf] = _merge_dicts(cursor[leaf], value)
+            else:
+                cursor[leaf] = value
 
         base = baseconfig if isinstance(baseconfig, dict) else baseconfig.to_dict()
         base = copy.deepcopy(base)
@@ -290,7 +290,7 @@ def _assert_all_consumed(update: Dict, merged: Dict, path: str) -> None:
         if isinstance(val, dict) and isinstance(merged[key], dict):
             # free-form dict fields (kwargs, gen_kwargs, peft_config…) may gain new keys
             if key in ("kwargs", "gen_kwargs", "trainer_kwargs", "peft_config", "model_extra_configs",
-                       "tokenizer_extra_configs"):
+                       "tokenizer_extra_configs") or key in _ATOMIC_KEYS:
                 merged[key].update(val)
                 continue
             _assert_all_consumed(val, merged[key], where + ".")

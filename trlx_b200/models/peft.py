@@ -88,6 +88,32 @@ class PeftConfig:
             return cls.from_dict(json.load(fh))
 
 
+class TaskType:
+    """Task identifiers (same strings as the `peft` package)."""
+
+    CAUSAL_LM = "CAUSAL_LM"
+    SEQ_2_SEQ_LM = "SEQ_2_SEQ_LM"
+
+
+class PeftType:
+    LORA = "LORA"
+    PROMPT_TUNING = "PROMPT_TUNING"
+    PREFIX_TUNING = "PREFIX_TUNING"
+
+
+def LoraConfig(**kw) -> PeftConfig:
+    """`peft.LoraConfig(...)`-style constructor."""
+    return PeftConfig(peft_type=PeftType.LORA, **kw)
+
+
+def PromptTuningConfig(**kw) -> PeftConfig:
+    return PeftConfig(peft_type=PeftType.PROMPT_TUNING, **kw)
+
+
+def PrefixTuningConfig(**kw) -> PeftConfig:
+    return PeftConfig(peft_type=PeftType.PREFIX_TUNING, **kw)
+
+
 def get_peft_config(config: Union[Dict[str, Any], PeftConfig, Any]) -> PeftConfig:
     """Accepts our :class:`PeftConfig`, a plain dict, or a foreign (``peft``) config object with ``to_dict``."""
     if isinstance(config, PeftConfig):

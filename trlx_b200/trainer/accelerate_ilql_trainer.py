@@ -159,6 +159,11 @@ class AccelerateILQLTrainer(AccelerateRLTrainer):
         logger.info("Collecting rollouts")
         if self.tokenizer:
             samples = [tokenize_dialogue(s, self.tokenizer, max_length) for s in samples]
+            keep = [i for i, s in enumerate(samples) if len(s) >= 2 and len(s[1].tokens) > 1]
+            if len(keep) != len(samples):  # truncation left no room for an output (the reference would raise IndexError)
+                logger.warning(f"dropping {len(samples) - len(keep)} samples whose output was truncated away "
+                               f"(max_length={max_length})")
+                samples, rewards = [samples[i] for i in keep], [rewards[i] for i in keep]
         all_input_ids, all_output_ids, all_actions, all_states, all_dones = [], [], [], [], []
         for sample in samples:
             all_input_ids.append(torch.tensor(sample[0].tokens, dtype=torch.long))
