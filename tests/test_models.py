@@ -223,3 +223,47 @@ def test_ilql_wrappers_generate_and_save(tmp_path):
     s2s = AutoModelForSeq2SeqLMWithILQLHeads.from_config(T5, two_qs=False).eval()
     gen = s2s.generate(ids, mask, max_new_tokens=3, eos_token_id=1, pad_token_id=0)
     assert gen.shape[0] == 3 and gen.shape[1] <= 4
+
+
+def test_beam_search_exact_when_width_covers_vocab_and_never_worse_than_greedy():
+    from trlx_b200.models.generation import generate
+    from trlx_b200.nn.arch import spec_from_hf_config
+    from trlx_b200.nn.transformer import CausalLM
+
+    torch.manual_seed(0)
+    V = 30
+    spec = spec_from_hf_config(dict(model_type="gpt2", vocab_size=V, n_embd=32, n_layer=2, n_head=2, n_positions=64, eos_token_id=V - 1))
+    m = CausalLM(spec).eval()
+    ids = torch.randint(0, V - 2, (3, 5))
+    mask = torch.ones_like(ids)
+    mask[0, :2] = 0
+
+    def seq_logprob(seq, rows=slice(None)):
+        am = torch.cat([mask[rows], torch.ones(seq.shape[0], seq.shape[1] - 5, dtype=torch.long)], 1)
+        lp = torch.log_softmax(m(input_ids=seq, attention_mask=am).logits[:, :-1].float(), -1)
+        return lp.gather(-1, seq[:, 1:, None]).squeeze(-1)[:, 4:].sum(-1)
+
+    with torch.no_grad():
+        greedy = generate(m, ids, mask, max_new_tokens=5, do_sample=False, eos_token_id=None, pad_token_id=0)
+        beam = generate(m, ids, mask, max_new_tokens=5, num_beams=4, eos_token_id=None, pad_token_id=0)
+        assert beam.shape == greedy.shape and (seq_logprob(beam) >= seq_logprob(greedy) - 1e-4).all()
+        # beam width = vocabulary size makes a 2-step search exhaustive
+        wide = generate(m, ids[:1], mask[:1], max_new_tokens=2, num_beams=V, eos_token_id=None, pad_token_id=0)
+        best = max(((seq_logprob(torch.cat([ids[:1], torch.tensor([[a, b]])], 1), slice(0, 1)).item(), a, b)
+                    for a in range(V) for b in range(V)))
+        assert wide[0, -2:].tolist() == [best[1], best[2]]
+
+
+def test_beam_search_seq2seq_runs_and_pads_after_eos():
+    from trlx_b200.models.generation import generate
+    from trlx_b200.models.modeling_base import build_base_model
+
+    torch.manual_seed(0)
+    t5 = build_base_model(dict(model_type="t5", vocab_size=40, d_model=32, d_kv=8, d_ff=64, num_layers=2, num_heads=4, eos_token_id=1,
+                               pad_token_id=0, decoder_start_token_id=0), "seq2seq").eval()
+    ids = torch.randint(2, 40, (2, 6))
+    out = generate(t5, ids, torch.ones_like(ids), max_new_tokens=8, num_beams=3, eos_token_id=1, pad_token_id=0)
+    assert out.shape[0] == 2 and out[:, 0].eq(0).all()
+    for row in out.tolist():
+        if 1 in row:
+            assert all(t == 0 for t in row[row.index(1) + 1:])

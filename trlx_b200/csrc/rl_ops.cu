@@ -215,7 +215,7 @@ ppo_loss_finalize_kernel(const float* __restrict__ part, const float* __restrict
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    const double n = acc[A_N];
+    const double n = acc[A_N] > 0 ? acc[A_N] : 1.0;  // an all-padding batch yields zero loss/gradients, not NaN
     const double pg = acc[A_PG] / n, vf = 0.5 * acc[A_VF] / n;
     out[O_LOSS] = (float)(pg + vf_coef * vf);
     out[O_PG] = (float)pg;
@@ -237,7 +237,7 @@ ppo_loss_finalize_kernel(const float* __restrict__ part, const float* __restrict
 
 __global__ void ppo_grad_scale_kernel(float* __restrict__ dlogprobs, float* __restrict__ dvalues, int total,
                                       const float* __restrict__ out, float vf_coef) {
-  const float inv_n = 1.f / out[O_N];
+  const float inv_n = 1.f / fmaxf(out[O_N], 1.f);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < total) { dlogprobs[i] *= inv_n; dvalues[i] *= vf_coef * inv_n; }
 }

@@ -59,7 +59,7 @@ def ppo_loss(logprobs, values, old_logprobs, old_values, advantages, returns, ma
 
     mask = mask.float()
     values_clipped = torch.clamp(values, old_values - cliprange_value, old_values + cliprange_value)
-    n = mask.sum()
+    n = mask.sum().clamp_min(1)  # an all-padding batch yields zero loss/gradients, not NaN
     vf1, vf2 = (values - returns) ** 2, (values_clipped - returns) ** 2
     vf_loss = 0.5 * torch.sum(torch.max(vf1, vf2) * mask) / n
     vf_clipfrac = torch.sum((vf2 > vf1).float() * mask) / n

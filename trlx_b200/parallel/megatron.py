@@ -16,6 +16,14 @@ class MegatronMixin:
     micro-batches) and checkpoint IO (``mp_rank_XX`` layout)."""
 
     def __init__(self, config, **kwargs):
+        tk = dict(config.train.trainer_kwargs or {})
+        for key in ("megatron_cfg", "pretrained_model"):  # reference-style trainer kwargs are consumed here
+            if key in kwargs:
+                tk.setdefault(key, kwargs.pop(key))
+        if tk.get("megatron_cfg") is not None:  # NeMo-style recipe (reference trainer_kwargs): layout, architecture, optimizer
+            from trlx_b200.parallel.megatron_cfg import apply_megatron_cfg
+
+            config = apply_megatron_cfg(config, tk["megatron_cfg"], tk.get("pretrained_model"))
         pp = int(getattr(config.train.parallel, "pipeline_parallel", 1) or 1)
         if pp > 1:
             if config.model.model_arch_type == "seq2seq":

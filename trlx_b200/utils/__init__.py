@@ -92,6 +92,7 @@ class OptimizerName(str, Enum):
     ADAM_8BIT_BNB = "adam_8bit_bnb"
     ADAMW_8BIT_BNB = "adamw_8bit_bnb"
     SGD = "sgd"
+    DISTRIBUTED_FUSED_ADAM = "distributed_fused_adam"  # NeMo/Apex name: the sharded fused AdamW is exactly that here
 
 
 def get_optimizer_class(name):
@@ -105,6 +106,7 @@ def get_optimizer_class(name):
         OptimizerName.ADAM_8BIT_BNB.value: _optim.Adam8bit,
         OptimizerName.ADAMW_8BIT_BNB.value: _optim.AdamW8bit,
         OptimizerName.SGD.value: torch.optim.SGD,
+        OptimizerName.DISTRIBUTED_FUSED_ADAM.value: _optim.FusedAdamW,
     }
     if key not in table:
         supported = [o.value for o in OptimizerName]
@@ -115,13 +117,38 @@ def get_optimizer_class(name):
 class SchedulerName(str, Enum):
     COSINE_ANNEALING = "cosine_annealing"
     LINEAR = "linear"
+    NEMO_COSINE_ANNEALING = "CosineAnnealing"  # NeMo's warmup → cosine → constant schedule (nemo_* examples)
+
+
+class WarmupCosineAnnealing(torch.optim.lr_scheduler.LambdaLR):
+    """``warmup_steps`` linear warm-up, cosine decay to ``min_lr`` until ``max_steps - constant_steps``, then constant
+    (the schedule the reference's NeMo examples configure: ``examples/nemo_ppo_sentiments.py:69-72``)."""
+
+    def __init__(self, optimizer, warmup_steps: int = 0, constant_steps: float = 0, min_lr: float = 0.0,
+                 max_steps: float = 1e12, last_epoch: int = -1, **unused):
+        import math
+
+        base = [g["lr"] for g in optimizer.param_groups]
+        decay_steps = max(float(max_steps) - float(constant_steps) - warmup_steps, 1.0)
+
+        def factor(base_lr):
+            def f(step):
+                if warmup_steps and step < warmup_steps:
+                    return (step + 1) / (warmup_steps + 1)
+                t = min((step - warmup_steps) / decay_steps, 1.0)
+                lr = min_lr + 0.5 * (base_lr - min_lr) * (1 + math.cos(math.pi * t))
+                return lr / base_lr if base_lr else 1.0
+            return f
+
+        super().__init__(optimizer, [factor(b) for b in base], last_epoch=last_epoch)
 
 
 def get_scheduler_class(name):
     key = name.value if isinstance(name, SchedulerName) else str(name)
     from torch.optim.lr_scheduler import CosineAnnealingLR, LinearLR
 
-    table = {SchedulerName.COSINE_ANNEALING.value: CosineAnnealingLR, SchedulerName.LINEAR.value: LinearLR}
+    table = {SchedulerName.COSINE_ANNEALING.value: CosineAnnealingLR, SchedulerName.LINEAR.value: LinearLR,
+             SchedulerName.NEMO_COSINE_ANNEALING.value: WarmupCosineAnnealing}
     if key not in table:
         supported = [s.value for s in SchedulerName]
         raise ValueError(f"`{name}` is not a supported scheduler. Supported schedulers are: {supported}")
