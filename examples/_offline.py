@@ -138,6 +138,7 @@ def offline_model(name: str, fallback: dict) -> object:
 
 GPT2_SMALL = dict(model_type="gpt2", vocab_size=50257, n_embd=768, n_layer=12, n_head=12, n_positions=1024)
 GPT2_TINY = dict(model_type="gpt2", vocab_size=50257, n_embd=128, n_layer=4, n_head=4, n_positions=1024)
+GPTJ_TINY = dict(model_type="gptj", vocab_size=50400, n_embd=128, n_layer=4, n_head=4, n_positions=2048, rotary_dim=16)
 T5_TINY = dict(model_type="t5", vocab_size=32128, d_model=128, d_kv=32, d_ff=256, num_layers=2, num_heads=4,
                decoder_start_token_id=0, pad_token_id=0, eos_token_id=1)
 LLAMA_TINY = dict(model_type="llama", vocab_size=32000, hidden_size=256, num_hidden_layers=4, num_attention_heads=8,

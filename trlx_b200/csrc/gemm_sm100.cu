@@ -104,24 +104,125 @@ __device__ __forceinline__ void red_add_v4_f32(float* addr, float a, float b, fl
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-// Epilogue bodies: one output row per thread, columns [c_lo, c_hi) of the current tile's accumulator.
-// v[j] = act(alpha * acc * col_scale + bias)  (or the d-logits transform) for 16 consecutive columns starting at col0
-__device__ __forceinline__ void store_values(const uint32_t (&r)[16], float (&v)[16], int col0, int N, const StoreEpilogue& se,
-                                             bool dl, float dl_l, float dl_g, long long dl_lab) {
+// ---------------------------------------------------------------------------------------------------- epilogues
+// Code size matters here: the epilogue warps of all 148 CTAs stream this code continuously, and an earlier version that
+// unrolled per-element bounds / bias / activation branches grew to ~190 KB of SASS and spent half of its issue slots in
+// `stall_no_inst` (instruction-cache misses; profiles/ncu_gemm_v3_icache.md).  So: one branch-free hot path for full
+// 16-column chunks (vector loads of bias / scale / residual, the activation switch hoisted out of the element loop) and a
+// rolled scalar path for the ragged last chunk of a row.
+
+__device__ __forceinline__ void load16_bf16(const __nv_bfloat16* p, float (&o)[16]) {
+  const uint4 a = *reinterpret_cast<const uint4*>(p), b = *reinterpret_cast<const uint4*>(p + 8);
+  const __nv_bfloat162* x = reinterpret_cast<const __nv_bfloat162*>(&a);
+  const __nv_bfloat162* y = reinterpret_cast<const __nv_bfloat162*>(&b);
 #pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = __bfloat1622float2(x[j]), g = __bfloat1622float2(y[j]);
+    o[2 * j] = f.x; o[2 * j + 1] = f.y; o[8 + 2 * j] = g.x; o[8 + 2 * j + 1] = g.y;
+  }
+}
+
+__device__ __forceinline__ void activate16(float (&v)[16], int act) {
+  switch (act) {  // hoisted: one compact loop per activation, only the one in use is ever fetched
+    case ACT_GELU_TANH:
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = gelu_tanh(v[j]);
+      break;
+    case ACT_GELU_ERF:
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
+      break;
+    case ACT_RELU:
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+      break;
+    case ACT_SILU:
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = silu(v[j]);
+      break;
+    default: break;
+  }
+}
+
+struct RowCtx {      // per-thread (= per output row) constants of the store epilogue
+  bool dl;
+  float dl_l, dl_g;
+  long long dl_lab;
+};
+
+// v = act(alpha * acc [* col_scale] [+ bias])  (or the d-logits transform)  [+ residual]   for a FULL 16-column chunk
+__device__ __forceinline__ void store_values_full(const uint32_t (&r)[16], float (&v)[16], int row, int col0,
+                                                  const StoreEpilogue& se, const RowCtx& rc, bool vec_in) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) * se.alpha;
+  if (se.col_scale) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const float4 c = *reinterpret_cast<const float4*>(se.col_scale + col0 + j);  // col0 % 16 == 0, fp32 [N] 16B-aligned
+      v[j] *= c.x; v[j + 1] *= c.y; v[j + 2] *= c.z; v[j + 3] *= c.w;
+    }
+  }
+  if (se.bias) {
+    float b[16];
+    if (vec_in) {
+      load16_bf16(se.bias + col0, b);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) b[j] = __bfloat162float(se.bias[col0 + j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] += b[j];
+  }
+  if (rc.dl) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = -__expf(v[j] - rc.dl_l) * rc.dl_g;
+    const long long o = rc.dl_lab - col0;
+    if (o >= 0 && o < 16) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] += (j == (int)o) ? rc.dl_g : 0.f;
+    }
+    if (rc.dl_lab < 0) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = 0.f;
+    }
+  }
+  activate16(v, se.act);
+  if (se.residual) {
+    const __nv_bfloat16* rp = se.residual + (size_t)row * se.ldr + col0;
+    float b[16];
+    if ((se.ldr & 7) == 0 && vec_in) {
+      load16_bf16(rp, b);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) b[j] = __bfloat162float(rp[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] += b[j];
+  }
+}
+
+// ragged last chunk of a row (col0 + 16 > N): rolled, scalar, correct for any alignment; columns >= N come out as 0
+__device__ __noinline__ void tail_values(const uint32_t* r, float* v, int row, int col0, int N, const StoreEpilogue& se, RowCtx rc) {
+#pragma unroll 1
   for (int j = 0; j < 16; ++j) {
     const int col = col0 + j;
-    float x = __uint_as_float(r[j]) * se.alpha;
+    float x = 0.f;
     if (col < N) {
+      x = __uint_as_float(r[j]) * se.alpha;
       if (se.col_scale) x *= se.col_scale[col];
       if (se.bias) x += __bfloat162float(se.bias[col]);
+      if (rc.dl) x = (rc.dl_lab < 0) ? 0.f : (((long long)col == rc.dl_lab ? 1.f : 0.f) - __expf(x - rc.dl_l)) * rc.dl_g;
+      x = apply_act(x, se.act);
+      if (se.residual) x += __bfloat162float(se.residual[(size_t)row * se.ldr + col]);
     }
-    if (dl) {
-      const float pr = __expf(x - dl_l);
-      x = (dl_lab < 0) ? 0.f : (((long long)col == dl_lab ? 1.f : 0.f) - pr) * dl_g;
-    }
-    v[j] = apply_act(x, se.act);
+    v[j] = x;
   }
+}
+
+__device__ __forceinline__ void pack16(const float (&v)[16], uint4 (&pk)[2]) {
+  __nv_bfloat162* p2 = reinterpret_cast<__nv_bfloat162*>(pk);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) p2[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
 }
 
 // Epilogue bodies: one output row per thread, columns [c_lo, c_hi) of the current tile's accumulator.
@@ -133,119 +234,92 @@ __device__ __forceinline__ void epilogue_cols(uint32_t taddr_row, int row, bool 
                                               const ReduceScatterEpilogue& re, uint8_t* stg, const CUtensorMap* map_out,
                                               int row0_warp, int lane) {
   if constexpr (EPI == 0) {
-    const bool vec_ok = ((se.ldo & 7) == 0) && (se.residual == nullptr || (se.ldr & 7) == 0);
-    // d-logits mode (LM-head backward): out = ((col == label) - exp(logit - lse[row])) * grad[row]
-    const bool dl = se.dl_lse != nullptr;
-    float dl_l = 0.f, dl_g = 0.f;
-    long long dl_lab = -1;
-    if (dl && row_ok) { dl_l = se.dl_lse[row]; dl_g = se.dl_grad[row]; dl_lab = se.dl_labels[row]; }
-    if (se.tma_store) {
-      // registers -> (swizzled) shared memory -> one bulk tensor store per 32 x CW chunk: full-line, coalesced global
-      // writes instead of 32 scattered 32-byte row fragments per warp instruction; TMA clips rows >= M / cols >= N.
-      constexpr int ROWB = CW * 2;                                  // bytes per staged row: 128 / 64 / 32
-      constexpr uint32_t SW_MASK = ROWB == 128 ? 7u : (ROWB == 64 ? 3u : 1u);
-      const uint32_t stg_u32 = smem_u32(stg);
-#pragma unroll 1
-      for (int c = c_lo; c < c_hi; c += CW) {
-        if (lane == 0) tma_store_wait_read();   // the previous chunk's store has drained the staging buffer
-        __syncwarp();
-        if (n0 + c >= N) continue;
-#pragma unroll
-        for (int cc = 0; cc < CW; cc += 16) {
-          uint32_t r[16];
-          tmem_ld16(taddr_row + c + cc, r);
-          tmem_ld_wait();
-          const int col0 = n0 + c + cc;
-          float v[16];
-          store_values(r, v, col0, N, se, dl, dl_l, dl_g, dl_lab);
-          if (se.residual && row_ok) {
-            const __nv_bfloat16* rp = se.residual + (size_t)row * se.ldr + col0;
-            if (col0 + 16 <= N && vec_ok) {
-              uint4 ra = *reinterpret_cast<const uint4*>(rp), rb = *reinterpret_cast<const uint4*>(rp + 8);
-              const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&ra);
-              const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(&rb);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) { v[j] += __bfloat162float(h[j]); v[8 + j] += __bfloat162float(g[j]); }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (col0 + j < N) v[j] += __bfloat162float(rp[j]);
-            }
-          }
-          uint4 pk[2];
-          __nv_bfloat162* p2 = reinterpret_cast<__nv_bfloat162*>(pk);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) p2[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            uint32_t off = (uint32_t)lane * ROWB + (uint32_t)(cc * 2 + h * 16);
-            off ^= ((off >> 7) & SW_MASK) << 4;                     // the TMA swizzle: 16-byte unit ^= (128-byte row index)
-            st_shared_v4(stg_u32 + off, pk[h]);
-          }
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_2d(map_out, stg, n0 + c, row0_warp);
-          tma_store_commit();
-        }
-      }
-      return;
-    }
+    RowCtx rc{se.dl_lse != nullptr, 0.f, 0.f, -1};
+    if (rc.dl && row_ok) { rc.dl_l = se.dl_lse[row]; rc.dl_g = se.dl_grad[row]; rc.dl_lab = se.dl_labels[row]; }
+    // 16-byte vector access to bias / residual / output needs 16-byte aligned bases (col0 is a multiple of 16 elements)
+    const bool vec_in = ((reinterpret_cast<uintptr_t>(se.bias) | reinterpret_cast<uintptr_t>(se.residual)) & 15) == 0;
+    const bool vec_out = ((se.ldo & 7) == 0) && ((reinterpret_cast<uintptr_t>(se.out) & 15) == 0);
+    // Two ways out of registers, one shared body:
+    //  * TMA store: registers -> (swizzled) shared memory -> one bulk tensor store per 32 x CW chunk (TMA clips at M / N)
+    //  * direct   : each thread writes its row's 16 columns (32 B) straight to global memory
+    constexpr int ROWB = CW * 2;                                  // bytes per staged row: 128 / 64 / 32
+    constexpr uint32_t SW_MASK = ROWB == 128 ? 7u : (ROWB == 64 ? 3u : 1u);
+    const uint32_t stg_u32 = smem_u32(stg);
+    const bool tma = se.tma_store != 0;
 #pragma unroll 1
     for (int c = c_lo; c < c_hi; c += 16) {
+      const int col0 = n0 + c;
+      if (col0 >= N) break;
+      const int cc = (c - c_lo) % CW;  // offset inside the staged chunk
+      if (tma && cc == 0) {
+        if (lane == 0) tma_store_wait_read();   // the previous chunk's bulk store has drained the staging buffer
+        __syncwarp();
+      }
       uint32_t r[16];
       tmem_ld16(taddr_row + c, r);
       tmem_ld_wait();
-      const int col0 = n0 + c;
-      if (!row_ok || col0 >= N) continue;
       float v[16];
-      store_values(r, v, col0, N, se, dl, dl_l, dl_g, dl_lab);
-      const bool full = (col0 + 16 <= N);
-      if (se.debug_nostore) {  // experiment: keep the math, drop the global stores
-        float acc = 0.f;
+      const bool full = col0 + 16 <= N;
+      if (full) store_values_full(r, v, row_ok ? row : 0, col0, se, rc, vec_in);
+      else {  // rare: keep the address-taken copies out of the hot path's registers
+        uint32_t tr[16];
+        float tv[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc += v[j];
-        if (acc == 1.2345e-30f) reinterpret_cast<float*>(se.out)[0] = acc;
+        for (int j = 0; j < 16; ++j) tr[j] = r[j];
+        tail_values(tr, tv, row_ok ? row : 0, col0, N, se, rc);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = tv[j];
+      }
+      if (tma) {
+        uint4 pk[2];
+        pack16(v, pk);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t off = (uint32_t)lane * ROWB + (uint32_t)(cc * 2 + h * 16);
+          off ^= ((off >> 7) & SW_MASK) << 4;                     // the TMA swizzle: 16-byte unit ^= (128-byte row index)
+          st_shared_v4(stg_u32 + off, pk[h]);
+        }
+        const bool last_of_chunk = (cc + 16 == CW) || (c + 16 >= c_hi) || (col0 + 16 >= N);
+        if (last_of_chunk) {
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {  // the box is clipped at M rows / N columns by the tensor map
+            tma_store_2d(map_out, stg, col0 - cc, row0_warp);
+            tma_store_commit();
+          }
+        }
         continue;
       }
-      if (se.residual) {
-        const __nv_bfloat16* rp = se.residual + (size_t)row * se.ldr + col0;
-        if (full && vec_ok) {
-          uint4 ra = *reinterpret_cast<const uint4*>(rp), rb = *reinterpret_cast<const uint4*>(rp + 8);
-          const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&ra);
-          const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(&rb);
+      if (!row_ok || se.debug_nostore) continue;
+      if (!full) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) { v[j] += __bfloat162float(h[j]); v[8 + j] += __bfloat162float(g[j]); }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (col0 + j < N) v[j] += __bfloat162float(rp[j]);
+        for (int j = 0; j < 16; ++j) {
+          if (j < N - col0) {
+            if (se.out_f32) reinterpret_cast<float*>(se.out)[(size_t)row * se.ldo + col0 + j] = v[j];
+            else reinterpret_cast<__nv_bfloat16*>(se.out)[(size_t)row * se.ldo + col0 + j] = __float2bfloat16(v[j]);
+          }
         }
+        continue;
       }
       if (se.out_f32) {
         float* op = reinterpret_cast<float*>(se.out) + (size_t)row * se.ldo + col0;
-        if (full && (se.ldo & 3) == 0) {
+        if ((se.ldo & 3) == 0 && vec_out) {
 #pragma unroll
           for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (col0 + j < N) op[j] = v[j];
+          for (int j = 0; j < 16; ++j) op[j] = v[j];
         }
       } else {
         __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(se.out) + (size_t)row * se.ldo + col0;
-        if (full && vec_ok) {
+        if (vec_out) {
           uint4 pk[2];
-          __nv_bfloat162* p2 = reinterpret_cast<__nv_bfloat162*>(pk);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) p2[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+          pack16(v, pk);
           *reinterpret_cast<uint4*>(op) = pk[0];
           *reinterpret_cast<uint4*>(op + 8) = pk[1];
         } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (col0 + j < N) op[j] = __float2bfloat16(v[j]);
+          for (int j = 0; j < 16; ++j) op[j] = __float2bfloat16(v[j]);
         }
       }
     }
@@ -259,17 +333,25 @@ __device__ __forceinline__ void epilogue_cols(uint32_t taddr_row, int row, bool 
       tmem_ld_wait();
       const int col0 = n0 + c;
       if (!row_ok || col0 >= N) continue;
-      float v[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        v[j] = __uint_as_float(r[j]);
-        if (se.bias && col0 + j < N) v[j] += __bfloat162float(se.bias[col0 + j]);  // only the rank that owns the bias passes it
-      }
       if (col0 + 16 <= N && (re.ldacc & 3) == 0) {
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+        if (se.bias) {  // only the rank that owns the bias passes it
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] += __bfloat162float(se.bias[col0 + j]);
+        }
 #pragma unroll
         for (int j = 0; j < 16; j += 4) red_add_v4_f32(dst_row + col0 + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
       } else {
-        for (int j = 0; j < 16 && col0 + j < N; ++j) atomicAdd(dst_row + col0 + j, v[j]);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (col0 + j < N) {
+            float x = __uint_as_float(r[j]);
+            if (se.bias) x += __bfloat162float(se.bias[col0 + j]);
+            atomicAdd(dst_row + col0 + j, x);
+          }
+        }
       }
     }
   } else {
@@ -283,6 +365,7 @@ __device__ __forceinline__ void epilogue_cols(uint32_t taddr_row, int row, bool 
     const unsigned long long seed = le.seed + (le.seed_ptr ? (unsigned long long)(*le.seed_ptr) : 0ull) +
                                     0x632BE59BD9B4E019ull * (unsigned long long)(step + 1);
     const bool greedy = le.inv_temperature <= 0.f;
+    const bool vec_bias = (reinterpret_cast<uintptr_t>(le.bias) & 15) == 0;
 #pragma unroll 1
     for (int c = c_lo; c < c_hi; c += 16) {
       uint32_t r[16];
@@ -291,19 +374,33 @@ __device__ __forceinline__ void epilogue_cols(uint32_t taddr_row, int row, bool 
       const int col0 = n0 + c;
       if (!row_ok || col0 >= N) continue;
       float z[16];
-      float cmax = -INFINITY;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int col = col0 + j;
-        float x = -INFINITY;
-        if (col < N && col != suppress) {
-          x = __uint_as_float(r[j]);
-          if (le.bias) x += __bfloat162float(le.bias[col]);
-          if (col == label) le.label_logit[row] = x;
+      for (int j = 0; j < 16; ++j) z[j] = __uint_as_float(r[j]);
+      const int valid = min(16, N - col0);  // < 16 only in the last chunk of a row
+      if (le.bias) {
+        if (valid == 16 && vec_bias) {
+          float b[16];
+          load16_bf16(le.bias + col0, b);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) z[j] += b[j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j < valid) z[j] += __bfloat162float(le.bias[col0 + j]);
         }
-        z[j] = x;
-        cmax = fmaxf(cmax, x);
       }
+      // rare per-chunk fix-ups, resolved with one range test each instead of per-element compares
+      const int so = suppress - col0, lo = (int)(label - col0);
+      if (valid < 16 || (so >= 0 && so < 16) || (label >= col0 && lo < 16)) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (j == lo && label >= col0 && j < valid && j != so) le.label_logit[row] = z[j];
+          if (j >= valid || j == so) z[j] = -INFINITY;
+        }
+      }
+      float cmax = z[0];
+#pragma unroll
+      for (int j = 1; j < 16; ++j) cmax = fmaxf(cmax, z[j]);
       if (cmax > mx) { sum *= __expf(mx - cmax); mx = cmax; }   // exp(-inf - finite) = 0 handles the first chunk
       if (mx > -INFINITY) {
 #pragma unroll
@@ -312,9 +409,9 @@ __device__ __forceinline__ void epilogue_cols(uint32_t taddr_row, int row, bool 
       if (sampling) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          if (z[j] == -INFINITY) continue;
           float key = z[j];
-          if (!greedy) key = z[j] * le.inv_temperature - __logf(-__logf(uniform01(seed, (unsigned)row, (unsigned)(col0 + j))));
+          if (!greedy && key > -INFINITY)
+            key = z[j] * le.inv_temperature - __logf(-__logf(uniform01(seed, (unsigned)row, (unsigned)(col0 + j))));
           if (key > best_key) { best_key = key; best_logit = z[j]; best_idx = col0 + j; }
         }
       }
