@@ -1,1 +1,3 @@
-for t in test_gemm_matches_fp32 test_gemm_persistent_many_tiles test_lmhead_dlogits test_gemm_epilogue test_gemm_strided_input test_linear_autograd test_fused_logprob_autograd; do timeout 100 python -m pytest tests/test_kernels_gpu.py -m gpu -q -x -k "$t" --timeout=45 --timeout-method=thread -p no:cacheprovider 2>&1 | tail -3; done; echo "=== tma store"; timeout 200 python scripts/bench_gemm.py 2>&1 | tail -9; echo "=== direct store"; B200_GEMM_DIRECT_STORE=1 timeout 200 python scripts/bench_gemm.py lmhead_pad train_fc square 2>&1 | tail -3; timeout 300 ncu --set full --clock-control none --import-source on -k regex:gemm_tn_kernel -c 14 -o gpurun_out/prof_gemm_v3 python scripts/ncu_target.py all > gpurun_out/ncu_gemm.log 2>&1; tail -2 gpurun_out/ncu_gemm.log
+bash scripts/gpu_test_groups.sh 2>&1 | grep -E "===|passed|failed|rc=[1-9]|Error" | head -60
+timeout 300 python -m pytest tests/test_engine_gpu.py -m gpu -q -x --timeout=200 --timeout-method=thread -p no:cacheprovider 2>&1 | tail -3
+echo "=== bench"; BENCH_BREAKDOWN=1 timeout 300 python bench.py --steps 10 --warmup 4 2>&1 | tail -2 | cut -c1-1500
