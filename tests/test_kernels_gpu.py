@@ -44,6 +44,24 @@ def test_gemm_persistent_many_tiles(C, M, N, K, bn):
     assert err <= 2e-2 * ref.abs().max().item(), err
 
 
+@pytest.mark.parametrize("M,N,K", [(1792, 768, 3072), (300, 200, 136), (768, 50257 // 8 * 8, 1280), (2304, 768, 1792), (1280, 768, 50257)])
+@pytest.mark.parametrize("a_mn,b_mn", [(False, True), (True, True), (True, False)])
+def test_gemm_mn_major_operands(C, M, N, K, a_mn, b_mn):
+    """Backward-pass layouts: operands stored transposed ([K, M] / [K, N]) are consumed without a transposed copy."""
+    torch.manual_seed(M + N + K)
+    a = (torch.randn(M, K, device="cuda") * 0.5).to(torch.bfloat16)
+    b = (torch.randn(N, K, device="cuda") * 0.5).to(torch.bfloat16)
+    ref = a.float() @ b.float().t()
+    if (a_mn and M % 8) or (b_mn and N % 8) or (K % 8 and not (a_mn and b_mn)):
+        pytest.skip("row pitches must be multiples of 8 elements")
+    a_in = a.t().contiguous() if a_mn else a
+    b_in = b.t().contiguous() if b_mn else b
+    out = C.gemm_ex(a_in, b_in, a_mn, b_mn)
+    assert out.shape == (M, N)
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 2e-2 * ref.abs().max().item() + 1e-2, err
+
+
 def test_lmhead_dlogits(C):
     torch.manual_seed(5)
     M, V, K = 300, 50257, 256

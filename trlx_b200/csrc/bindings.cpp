@@ -31,6 +31,7 @@ int b200_decode_step(const long long*, const float*, const float*, const float*,
 int b200_paged_kv_write(const void*, const void*, void*, void*, const int*, const int*, const int*, int, int, int, int, int,
                         int, long long, long long, cudaStream_t);
 int b200_logprob_from_logits(const void*, const long long*, float*, float*, long long, int, long long, int, cudaStream_t);
+int b200_gemm_bf16_ex(const void*, const void*, void*, int, int, int, long long, long long, long long, int, int, int, cudaStream_t);
 int b200_lmhead_dlogits_bf16(const void*, const void*, void*, int, int, int, long long, long long, long long, const void*,
                              const long long*, const float*, const float*, cudaStream_t);
 int b200_logprob_backward_inplace(void*, const long long*, const float*, const float*, long long, int, long long, int,
@@ -107,6 +108,24 @@ Tensor gemm(const Tensor& x, const Tensor& w, const OptTensor& bias, const OptTe
                        out.stride(0), optptr(bias), optptr(residual), ldr, (const float*)optptr(col_scale), (float)alpha,
                        act_code(act), out.scalar_type() == at::kFloat, (int)force_bn, stream()),
         "gemm");
+  return out;
+}
+
+// out[M, N] = sum_k A(m, k) B(n, k) with either operand optionally MN-major (stored transposed: A as [K, M], B as [K, N]).
+// These are the layouts of the backward GEMMs (dX = dY·W, dW = dYᵀ·X) — no transposed copies are made.
+Tensor gemm_ex(const Tensor& a, const Tensor& b, bool a_mn, bool b_mn, bool out_f32) {
+  CHECK_BF16(a); CHECK_BF16(b);
+  TORCH_CHECK(a.dim() == 2 && b.dim() == 2 && a.stride(1) == 1 && b.stride(1) == 1, "gemm_ex: operands must be row-major 2-D");
+  const int64_t M = a_mn ? a.size(1) : a.size(0), Ka = a_mn ? a.size(0) : a.size(1);
+  const int64_t N = b_mn ? b.size(1) : b.size(0), Kb = b_mn ? b.size(0) : b.size(1);
+  TORCH_CHECK(Ka == Kb, "gemm_ex: contraction sizes differ");
+  TORCH_CHECK(a.stride(0) % 8 == 0 && b.stride(0) % 8 == 0, "gemm_ex: row pitches must be multiples of 8 elements");
+  TORCH_CHECK(reinterpret_cast<uintptr_t>(a.data_ptr()) % 16 == 0 && reinterpret_cast<uintptr_t>(b.data_ptr()) % 16 == 0);
+  c10::cuda::CUDAGuard guard(a.device());
+  Tensor out = torch::empty({M, N}, a.options().dtype(out_f32 ? at::kFloat : at::kBFloat16));
+  check(b200_gemm_bf16_ex(a.data_ptr(), b.data_ptr(), out.data_ptr(), (int)M, (int)N, (int)Ka, a.stride(0), b.stride(0),
+                          out.stride(0), a_mn ? 1 : 0, b_mn ? 1 : 0, out_f32 ? 1 : 0, stream()),
+        "gemm_ex");
   return out;
 }
 
@@ -509,6 +528,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("sample") = false, py::arg("temperature") = 1.0, py::arg("seed") = 0, py::arg("step") = py::none(),
         py::arg("suppress_col") = -1, py::arg("suppress_until") = 0, py::arg("workspace") = py::none(),
         py::arg("seed_tensor") = py::none());
+  m.def("gemm_ex", &gemm_ex, py::arg("a"), py::arg("b"), py::arg("a_mn") = false, py::arg("b_mn") = false,
+        py::arg("out_f32") = false);
   m.def("lmhead_tiles", [](int64_t n) { return (int64_t)b200_lmhead_tiles((int)n); }, py::arg("vocab"));
   m.def("lmhead_dlogits", &lmhead_dlogits, py::arg("h"), py::arg("w"), py::arg("bias"), py::arg("labels"), py::arg("lse"),
         py::arg("grad"));

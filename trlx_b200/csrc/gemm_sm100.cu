@@ -428,7 +428,10 @@ __device__ __forceinline__ void epilogue_cols(uint32_t taddr_row, int row, bool 
 // Persistent, warp-specialised kernel.  Each CTA walks output tiles  t = blockIdx.x, blockIdx.x + gridDim.x, ...
 // (M-fastest order: CTAs that run concurrently share the same B panel in L2).  The accumulator is double-buffered in
 // TMEM (2 x BN fp32 columns), so the epilogue of tile i overlaps the TMA/MMA mainloop of tile i+1.
-template <int BN, int EPI>  // EPI: 0 = store, 1 = lm-head, 2 = reduce-scatter into peer accumulators
+// AMN / BMN: the operand is MN-major in global memory (A given as [K, M], B as [K, N], row-major) — the layouts the backward
+// GEMMs need (dX = dY · W reads W [N, K] as an MN-major B; dW = dYᵀ · X reads both operands MN-major), so no transposes are
+// ever materialised.  Such a tile is fetched as 64-column TMA boxes ([64 k rows] x [64 MN elements]) laid out chunk by chunk.
+template <int BN, int EPI, int AMN = 0, int BMN = 0>  // EPI: 0 = store, 1 = lm-head, 2 = reduce-scatter into peers
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ MapArray maps_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_out, int M, int N, int K, int stages, int rows_per_map,
@@ -437,6 +440,8 @@ gemm_tn_kernel(const __grid_constant__ MapArray maps_a, const __grid_constant__ 
   constexpr uint32_t A_BYTES = BM * BK * 2;
   constexpr uint32_t B_BYTES = BN * BK * 2;
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t MN_CHUNK = BK * 64 * 2;          // one [64 k] x [64 MN] box of an MN-major operand (8 KB)
+  static_assert(!(BMN && BN < 64), "MN-major B needs BN >= 64");
   constexpr uint32_t ACC_COLS = BN < 32 ? 32 : BN;   // TMEM columns of one accumulator buffer
   constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;
   constexpr int HALF = BN / 2;                        // columns per epilogue warp (two warps share a TMEM lane quadrant)
@@ -500,14 +505,24 @@ gemm_tn_kernel(const __grid_constant__ MapArray maps_a, const __grid_constant__ 
           uint8_t* a_dst = smem + (size_t)s * STAGE_BYTES;
           uint8_t* b_dst = a_dst + A_BYTES;
           mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
-          tma_load_2d(a_dst, map_a_ptr, &full_bar[s], kb * BK, a_row);
-          tma_load_2d(b_dst, &map_b, &full_bar[s], kb * BK, n0);
+          if constexpr (AMN) {
+#pragma unroll
+            for (int ch = 0; ch < BM / 64; ++ch) tma_load_2d(a_dst + ch * MN_CHUNK, map_a_ptr, &full_bar[s], m0 + ch * 64, kb * BK);
+          } else {
+            tma_load_2d(a_dst, map_a_ptr, &full_bar[s], kb * BK, a_row);
+          }
+          if constexpr (BMN) {
+#pragma unroll
+            for (int ch = 0; ch < BN / 64; ++ch) tma_load_2d(b_dst + ch * MN_CHUNK, &map_b, &full_bar[s], n0 + ch * 64, kb * BK);
+          } else {
+            tma_load_2d(b_dst, &map_b, &full_bar[s], kb * BK, n0);
+          }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc(1, 1, BM, BN);
+      constexpr uint32_t idesc = umma_idesc(1, 1, BM, BN, AMN, BMN);
       uint32_t it = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
         const uint32_t as = tcount & 1, aphase = (tcount >> 1) & 1;
@@ -520,12 +535,14 @@ gemm_tn_kernel(const __grid_constant__ MapArray maps_a, const __grid_constant__ 
           mbar_wait(&full_bar[s], phase);
           tc_fence_after_sync();
           const uint32_t a_addr = smem_u32(smem + (size_t)s * STAGE_BYTES);
-          const uint64_t da = umma_desc_k_sw128(a_addr);
-          const uint64_t db = umma_desc_k_sw128(a_addr + A_BYTES);
+          const uint64_t da = AMN ? umma_desc_mn_sw128(a_addr, MN_CHUNK) : umma_desc_k_sw128(a_addr);
+          const uint64_t db = BMN ? umma_desc_mn_sw128(a_addr + A_BYTES, MN_CHUNK) : umma_desc_k_sw128(a_addr + A_BYTES);
+          // one UMMA consumes 16 k: K-major = 32 bytes inside the 128-byte swizzle row (+2 in the addr>>4 field);
+          // MN-major = 16 rows of 128 bytes = 2048 bytes (+128)
+          constexpr uint32_t A_STEP = AMN ? (16 * 128) >> 4 : 2, B_STEP = BMN ? (16 * 128) >> 4 : 2;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-            umma_bf16(tmem_acc, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_bf16(tmem_acc, da + A_STEP * k, db + B_STEP * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[s]);
         }
@@ -682,7 +699,7 @@ static int pick_bn(int M, int N) {
   return 32;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int AMN = 0, int BMN = 0>
 static cudaError_t launch(const MapArray& ma, const CUtensorMap& mb, const CUtensorMap& mo, int M, int N, int K,
                           int rows_per_map, const StoreEpilogue& se, const LMHeadEpilogue& le,
                           const ReduceScatterEpilogue& re, cudaStream_t stream) {
@@ -693,7 +710,7 @@ static cudaError_t launch(const MapArray& ma, const CUtensorMap& mb, const CUten
   if (stages > 8) stages = 8;
   if (stages > nkb) stages = nkb < 2 ? 2 : nkb;
   const size_t smem = (size_t)stages * stage_bytes + fixed_bytes;
-  auto kern = gemm_tn_kernel<BN, EPI>;
+  auto kern = gemm_tn_kernel<BN, EPI, AMN, BMN>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -751,6 +768,44 @@ extern "C" int b200_gemm_bf16(const void* A, const void* B, void* out, int M, in
     case 64: e = launch<64, 0>(ma, mb, mo, M, N, K, rpm, se, le, re, stream); break;
     default: e = launch<32, 0>(ma, mb, mo, M, N, K, rpm, se, le, re, stream); break;
   }
+  return (int)e;
+}
+
+// General-layout GEMM for the backward pass: out[M, N] = op(A) · op(B)^T-free, i.e. out[m, n] = sum_k A(m, k) · B(n, k) where
+//   a_mn = 0: A is [M, K] row-major (K contiguous);   a_mn = 1: A is given as [K, M] row-major (M contiguous)
+//   b_mn = 0: B is [N, K] row-major (K contiguous);   b_mn = 1: B is given as [K, N] row-major (N contiguous)
+// lda / ldb are the row pitches of the arrays as stored.  bf16 (or fp32) output, optional accumulate-free bias.
+extern "C" int b200_gemm_bf16_ex(const void* A, const void* B, void* out, int M, int N, int K, long long lda, long long ldb,
+                                 long long ldo, int a_mn, int b_mn, int out_f32, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if (!a_mn && !b_mn)
+    return b200_gemm_bf16(A, B, out, M, N, K, lda, ldb, ldo, nullptr, nullptr, 0, nullptr, 1.0f, ACT_NONE, out_f32, 0, stream);
+  int bn = pick_bn(M, N);
+  if (bn < 64) bn = 64;  // MN-major tiles are fetched in 64-element boxes
+  MapArray ma{};
+  CUtensorMap mb;
+  const bool ok_a = a_mn ? make_map(&ma.m[0], A, K, M, lda, 64, 64) : make_map(&ma.m[0], A, M, K, lda, BM);
+  const bool ok_b = b_mn ? make_map(&mb, B, K, N, ldb, 64, 64) : make_map(&mb, B, N, K, ldb, bn);
+  if (!ok_a || !ok_b) return -1;
+  StoreEpilogue se{out, nullptr, nullptr, nullptr, ldo, 0, 1.0f, ACT_NONE, out_f32};
+  CUtensorMap mo{};
+  if (!setup_tma_store(se, &mo, M, N, bn)) return -1;
+  LMHeadEpilogue le{};
+  ReduceScatterEpilogue re{};
+  const int rpm = 1 << 30;
+  cudaError_t e = cudaErrorInvalidValue;
+#define B200_EX_CASE(BN_)                                                                                     \
+  case BN_:                                                                                                   \
+    if (a_mn && b_mn) e = launch<BN_, 0, 1, 1>(ma, mb, mo, M, N, K, rpm, se, le, re, stream);                 \
+    else if (a_mn) e = launch<BN_, 0, 1, 0>(ma, mb, mo, M, N, K, rpm, se, le, re, stream);                    \
+    else e = launch<BN_, 0, 0, 1>(ma, mb, mo, M, N, K, rpm, se, le, re, stream);                              \
+    break;
+  switch (bn) {
+    B200_EX_CASE(256)
+    B200_EX_CASE(128)
+    B200_EX_CASE(64)
+  }
+#undef B200_EX_CASE
   return (int)e;
 }
 

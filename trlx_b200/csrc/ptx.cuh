@@ -134,10 +134,24 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
-// Instruction descriptor (upper word of the 64-bit idesc): fp32 accumulate, K-major A and B.
+// MN-major operand tile (the MN dimension is the contiguous one in global memory: a "transposed" operand) with 128-byte
+// swizzle.  Shared memory holds [MN/64 chunks][k rows][64 MN elements]: a row is 128 B (64 bf16 of MN), 8 consecutive k
+// rows form one 1024-B swizzle atom (SBO), and the next 64 MN elements start one whole chunk later (LBO = rows * 128 B).
+// Canonical form (CUTLASS cute/atom/mma_traits_sm100.hpp, "UmmaDescriptor Major-MN", B128): ((8,n),(8,k)):((1,LBO),(8,SBO)).
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t chunk_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((chunk_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// Instruction descriptor (upper word of the 64-bit idesc): fp32 accumulate; a_mn / b_mn = 1 selects an MN-major operand.
 // fmt: 1 = bf16 / 0 = f16 for kind::f16 ; 0 = e4m3 / 1 = e5m2 for kind::f8f6f4.
-__host__ __device__ constexpr uint32_t umma_idesc(uint32_t fmt_a, uint32_t fmt_b, uint32_t M, uint32_t N) {
-  return (1u << 4) | (fmt_a << 7) | (fmt_b << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+__host__ __device__ constexpr uint32_t umma_idesc(uint32_t fmt_a, uint32_t fmt_b, uint32_t M, uint32_t N, uint32_t a_mn = 0,
+                                                  uint32_t b_mn = 0) {
+  return (1u << 4) | (fmt_a << 7) | (fmt_b << 10) | (a_mn << 15) | (b_mn << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
 // ---------------------------------------------------------------- cross-GPU (NVLink peer memory) helpers

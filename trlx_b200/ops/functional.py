@@ -1,6 +1,7 @@
 """Autograd-aware wrappers around the sm_100a kernels (CUDA bf16) with PyTorch fallbacks elsewhere."""
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -38,8 +39,30 @@ def _as_2d(x: torch.Tensor) -> torch.Tensor:
     return x2
 
 
+def _ex_ok(t: torch.Tensor) -> bool:
+    return (t.dim() == 2 and t.dtype == torch.bfloat16 and t.stride(1) == 1 and t.stride(0) % 8 == 0
+            and t.data_ptr() % 16 == 0)
+
+
+_OWN_BACKWARD = os.environ.get("TRLX_B200_BACKWARD_GEMM", "tcgen05") != "cublas"
+
+
+def grad_input(g2: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """dX[M, K] = dY[M, N] · W[N, K]: W is consumed as an MN-major B operand (no transposed copy)."""
+    if _OWN_BACKWARD and _ex_ok(g2) and _ex_ok(w):
+        return _ops().C.gemm_ex(g2, w, False, True)
+    return g2 @ w
+
+
+def grad_weight(g2: torch.Tensor, x2: torch.Tensor) -> torch.Tensor:
+    """dW[N, K] = dYᵀ[N, M] · X[M, K]: both operands are consumed MN-major, straight from their forward layouts."""
+    if _OWN_BACKWARD and _ex_ok(g2) and _ex_ok(x2):
+        return _ops().C.gemm_ex(g2, x2, True, True)
+    return g2.t() @ x2
+
+
 class _Linear(torch.autograd.Function):
-    """y = x @ w.T + b (+ residual) — forward on the tcgen05 GEMM, backward on library GEMMs."""
+    """y = x @ w.T + b (+ residual) — forward and both backward GEMMs on the tcgen05 kernel."""
 
     @staticmethod
     def forward(ctx, x, w, b, residual):
@@ -56,12 +79,12 @@ class _Linear(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy):
         x2, w = ctx.saved_tensors
-        g2 = gy.reshape(-1, gy.shape[-1])
+        g2 = _as_2d(gy)
         gx = gw = gb = gr = None
         if ctx.needs_input_grad[0]:
-            gx = (g2 @ w).view(ctx.x_shape)
+            gx = grad_input(g2, w).view(ctx.x_shape)
         if ctx.needs_input_grad[1]:
-            gw = g2.t() @ x2
+            gw = grad_weight(g2, x2)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = g2.sum(0)
         if ctx.has_res and ctx.needs_input_grad[3]:
@@ -111,9 +134,9 @@ class _FusedLogprob(torch.autograd.Function):
         logits = C.lmhead_dlogits(h2, w, b if ctx.has_bias else None, lab, lse, g_lp.reshape(-1).float().contiguous())
         gh = gw = gb = None
         if ctx.needs_input_grad[0]:
-            gh = (logits @ w).view(ctx.h_shape)
+            gh = grad_input(logits, w).view(ctx.h_shape)
         if ctx.needs_input_grad[1]:
-            gw = logits.t() @ h2
+            gw = grad_weight(logits, h2)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = logits.sum(0)
         return gh, gw, gb, None
