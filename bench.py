@@ -282,8 +282,9 @@ def main():
 
         from trlx_b200.pipeline import MiniBatchIterator
 
-        os.environ["TRLX_B200_TRAIN_GRAPH"] = "0"  # kernels inside a replayed graph are attributed per kernel anyway,
-        trainer._graphed_steps = {}                 # but the eager step also shows which autograd node launched them
+        if not os.environ.get("BENCH_PROFILE_GRAPH"):
+            os.environ["TRLX_B200_TRAIN_GRAPH"] = "0"  # the eager step also shows which autograd node launched a kernel
+            trainer._graphed_steps = {}
         os.makedirs("gpurun_out", exist_ok=True)
         for phase in ("train", "rollout"):
             trainer.store.clear_history()
@@ -301,8 +302,11 @@ def main():
                     trainer.make_experience(cfg.method.num_rollouts, 0)
                 torch.cuda.synchronize()
             table = prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=70)
-            with open(f"gpurun_out/profile_{phase}.txt", "w") as fh:
+            suffix = "_graph" if os.environ.get("BENCH_PROFILE_GRAPH") else ""
+            with open(f"gpurun_out/profile_{phase}{suffix}.txt", "w") as fh:
                 fh.write(table)
+            if os.environ.get("BENCH_PROFILE_TRACE"):
+                prof.export_chrome_trace(f"gpurun_out/trace_{phase}{suffix}.json")
     if rank == 0:
         print(json.dumps(out))
     if dist.is_initialized():

@@ -62,6 +62,21 @@ def test_gemm_mn_major_operands(C, M, N, K, a_mn, b_mn):
     assert err <= 2e-2 * ref.abs().max().item() + 1e-2, err
 
 
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True)])
+@pytest.mark.parametrize("split_k", [-1, 3, 16])
+def test_gemm_split_k(C, a_mn, b_mn, split_k):
+    """Skinny output, long contraction: K-ranges are accumulated into an fp32 buffer by red.add from the epilogue."""
+    torch.manual_seed(3)
+    M, N, K = 256, 192, 8192 + 64
+    a = (torch.randn(M, K, device="cuda") * 0.1).to(torch.bfloat16)
+    b = (torch.randn(N, K, device="cuda") * 0.1).to(torch.bfloat16)
+    ref = a.float() @ b.float().t()
+    out = C.gemm_ex(a.t().contiguous() if a_mn else a, b.t().contiguous() if b_mn else b, a_mn, b_mn, False, split_k)
+    out32 = C.gemm_ex(a.t().contiguous() if a_mn else a, b.t().contiguous() if b_mn else b, a_mn, b_mn, True, split_k)
+    assert (out.float() - ref).abs().max().item() <= 2e-2 * ref.abs().max().item()
+    assert (out32 - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
+
+
 def test_lmhead_dlogits(C):
     torch.manual_seed(5)
     M, V, K = 300, 50257, 256

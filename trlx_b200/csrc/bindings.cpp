@@ -2,6 +2,7 @@
 //   * PagedKVAllocator — free-list page allocator behind the paged KV cache used by the rollout engine
 // Kernels live in the .cu files of this directory and export a plain C ABI so that they compile in seconds
 // without torch headers.
+#include <algorithm>
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
 #include <torch/extension.h>
@@ -31,7 +32,9 @@ int b200_decode_step(const long long*, const float*, const float*, const float*,
 int b200_paged_kv_write(const void*, const void*, void*, void*, const int*, const int*, const int*, int, int, int, int, int,
                         int, long long, long long, cudaStream_t);
 int b200_logprob_from_logits(const void*, const long long*, float*, float*, long long, int, long long, int, cudaStream_t);
-int b200_gemm_bf16_ex(const void*, const void*, void*, int, int, int, long long, long long, long long, int, int, int, cudaStream_t);
+int b200_gemm_bf16_ex(const void*, const void*, void*, int, int, int, long long, long long, long long, int, int, int, int, float*,
+                      cudaStream_t);
+int b200_gemm_splitk_plan(int, int, int);
 int b200_lmhead_dlogits_bf16(const void*, const void*, void*, int, int, int, long long, long long, long long, const void*,
                              const long long*, const float*, const float*, cudaStream_t);
 int b200_logprob_backward_inplace(void*, const long long*, const float*, const float*, long long, int, long long, int,
@@ -113,7 +116,7 @@ Tensor gemm(const Tensor& x, const Tensor& w, const OptTensor& bias, const OptTe
 
 // out[M, N] = sum_k A(m, k) B(n, k) with either operand optionally MN-major (stored transposed: A as [K, M], B as [K, N]).
 // These are the layouts of the backward GEMMs (dX = dY·W, dW = dYᵀ·X) — no transposed copies are made.
-Tensor gemm_ex(const Tensor& a, const Tensor& b, bool a_mn, bool b_mn, bool out_f32) {
+Tensor gemm_ex(const Tensor& a, const Tensor& b, bool a_mn, bool b_mn, bool out_f32, int64_t split_k) {
   CHECK_BF16(a); CHECK_BF16(b);
   TORCH_CHECK(a.dim() == 2 && b.dim() == 2 && a.stride(1) == 1 && b.stride(1) == 1, "gemm_ex: operands must be row-major 2-D");
   const int64_t M = a_mn ? a.size(1) : a.size(0), Ka = a_mn ? a.size(0) : a.size(1);
@@ -122,9 +125,13 @@ Tensor gemm_ex(const Tensor& a, const Tensor& b, bool a_mn, bool b_mn, bool out_
   TORCH_CHECK(a.stride(0) % 8 == 0 && b.stride(0) % 8 == 0, "gemm_ex: row pitches must be multiples of 8 elements");
   TORCH_CHECK(reinterpret_cast<uintptr_t>(a.data_ptr()) % 16 == 0 && reinterpret_cast<uintptr_t>(b.data_ptr()) % 16 == 0);
   c10::cuda::CUDAGuard guard(a.device());
-  Tensor out = torch::empty({M, N}, a.options().dtype(out_f32 ? at::kFloat : at::kBFloat16));
+  const int splits = split_k < 0 ? b200_gemm_splitk_plan((int)M, (int)N, (int)Ka) : (int)std::max<int64_t>(split_k, 1);
+  Tensor ws;
+  if (splits > 1) ws = torch::zeros({M, N}, a.options().dtype(at::kFloat));  // partial products are red.add'ed into it
+  Tensor out = (splits > 1 && out_f32) ? ws : torch::empty({M, N}, a.options().dtype(out_f32 ? at::kFloat : at::kBFloat16));
   check(b200_gemm_bf16_ex(a.data_ptr(), b.data_ptr(), out.data_ptr(), (int)M, (int)N, (int)Ka, a.stride(0), b.stride(0),
-                          out.stride(0), a_mn ? 1 : 0, b_mn ? 1 : 0, out_f32 ? 1 : 0, stream()),
+                          out.stride(0), a_mn ? 1 : 0, b_mn ? 1 : 0, out_f32 ? 1 : 0, splits,
+                          splits > 1 ? ws.data_ptr<float>() : nullptr, stream()),
         "gemm_ex");
   return out;
 }
@@ -529,7 +536,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("suppress_col") = -1, py::arg("suppress_until") = 0, py::arg("workspace") = py::none(),
         py::arg("seed_tensor") = py::none());
   m.def("gemm_ex", &gemm_ex, py::arg("a"), py::arg("b"), py::arg("a_mn") = false, py::arg("b_mn") = false,
-        py::arg("out_f32") = false);
+        py::arg("out_f32") = false, py::arg("split_k") = -1);
   m.def("lmhead_tiles", [](int64_t n) { return (int64_t)b200_lmhead_tiles((int)n); }, py::arg("vocab"));
   m.def("lmhead_dlogits", &lmhead_dlogits, py::arg("h"), py::arg("w"), py::arg("bias"), py::arg("labels"), py::arg("lse"),
         py::arg("grad"));

@@ -435,7 +435,7 @@ template <int BN, int EPI, int AMN = 0, int BMN = 0>  // EPI: 0 = store, 1 = lm-
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ MapArray maps_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_out, int M, int N, int K, int stages, int rows_per_map,
-               StoreEpilogue se, LMHeadEpilogue le, ReduceScatterEpilogue re) {
+               StoreEpilogue se, LMHeadEpilogue le, ReduceScatterEpilogue re, int k_splits) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr uint32_t A_BYTES = BM * BK * 2;
   constexpr uint32_t B_BYTES = BN * BK * 2;
@@ -461,6 +461,10 @@ gemm_tn_kernel(const __grid_constant__ MapArray maps_a, const __grid_constant__ 
   const int m_tiles = (M + BM - 1) / BM;
   const int n_tiles = (N + BN - 1) / BN;
   const int total_tiles = m_tiles * n_tiles;
+  // split-K (k_splits > 1, EPI 2 only): work item w = (split, tile) covers k-blocks [split*per, min(nkb, (split+1)*per)) and
+  // its partial product is added into an fp32 accumulator, so a skinny output with a very long contraction still fills the GPU
+  const int total_work = total_tiles * k_splits;
+  const int kb_per = (nkb + k_splits - 1) / k_splits;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps_a.m[0]);
@@ -492,13 +496,15 @@ gemm_tn_kernel(const __grid_constant__ MapArray maps_a, const __grid_constant__ 
   if (warp == 0) {
     if (lane == 0) {
       uint32_t it = 0;  // k-block counter across all of this CTA's tiles (ring position)
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const int tile = w % total_tiles, split = w / total_tiles;
+        const int kb_lo = split * kb_per, kb_hi = min(nkb, kb_lo + kb_per);
         const int m0 = (tile % m_tiles) * BM, n0 = (tile / m_tiles) * BN;
         // which peer's copy of A holds this M-tile (all-gather -> GEMM); plain GEMMs have a single map
         const int a_map = m0 / rows_per_map;
         const int a_row = m0 - a_map * rows_per_map;
         const CUtensorMap* map_a_ptr = &maps_a.m[a_map];
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
+        for (int kb = kb_lo; kb < kb_hi; ++kb, ++it) {
           const int s = it % stages;
           const uint32_t phase = (it / stages) & 1;
           mbar_wait(&empty_bar[s], phase ^ 1);
@@ -524,12 +530,14 @@ gemm_tn_kernel(const __grid_constant__ MapArray maps_a, const __grid_constant__ 
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc(1, 1, BM, BN, AMN, BMN);
       uint32_t it = 0, tcount = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tcount) {
+        const int split = w / total_tiles;
+        const int kb_lo = split * kb_per, kb_hi = min(nkb, kb_lo + kb_per);
         const uint32_t as = tcount & 1, aphase = (tcount >> 1) & 1;
         mbar_wait(&tmem_empty_bar[as], aphase ^ 1);  // epilogue drained this accumulator buffer
         tc_fence_after_sync();
         const uint32_t tmem_acc = tmem_base + as * ACC_COLS;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
+        for (int kb = kb_lo; kb < kb_hi; ++kb, ++it) {
           const int s = it % stages;
           const uint32_t phase = (it / stages) & 1;
           mbar_wait(&full_bar[s], phase);
@@ -542,7 +550,7 @@ gemm_tn_kernel(const __grid_constant__ MapArray maps_a, const __grid_constant__ 
           constexpr uint32_t A_STEP = AMN ? (16 * 128) >> 4 : 2, B_STEP = BMN ? (16 * 128) >> 4 : 2;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            umma_bf16(tmem_acc, da + A_STEP * k, db + B_STEP * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_bf16(tmem_acc, da + A_STEP * k, db + B_STEP * k, idesc, (kb > kb_lo || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[s]);
         }
@@ -557,7 +565,8 @@ gemm_tn_kernel(const __grid_constant__ MapArray maps_a, const __grid_constant__ 
     const int c_lo = half * HALF, c_hi = c_lo + HALF;
     uint8_t* stg = stage_out + (size_t)(warp - 2) * STG_BYTES;
     uint32_t tcount = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tcount) {
+      const int tile = w % total_tiles;
       const uint32_t as = tcount & 1, aphase = (tcount >> 1) & 1;
       const int m_idx = tile % m_tiles, n_idx = tile / m_tiles;
       const int row = m_idx * BM + q * 32 + lane;
@@ -702,7 +711,7 @@ static int pick_bn(int M, int N) {
 template <int BN, int EPI, int AMN = 0, int BMN = 0>
 static cudaError_t launch(const MapArray& ma, const CUtensorMap& mb, const CUtensorMap& mo, int M, int N, int K,
                           int rows_per_map, const StoreEpilogue& se, const LMHeadEpilogue& le,
-                          const ReduceScatterEpilogue& re, cudaStream_t stream) {
+                          const ReduceScatterEpilogue& re, cudaStream_t stream, int k_splits = 1) {
   constexpr int stage_bytes = BM * BK * 2 + BN * BK * 2;
   constexpr int fixed_bytes = NUM_EPI_WARPS * STG_BYTES + 1024 /*alignment slack*/ + 512 /*barriers*/;
   const int nkb = (K + BK - 1) / BK;
@@ -717,9 +726,9 @@ static cudaError_t launch(const MapArray& ma, const CUtensorMap& mb, const CUten
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  const long long tiles = (long long)((N + BN - 1) / BN) * ((M + BM - 1) / BM);
+  const long long tiles = (long long)((N + BN - 1) / BN) * ((M + BM - 1) / BM) * k_splits;
   dim3 grid((unsigned)(tiles < num_sms() ? tiles : num_sms()));  // persistent: one CTA per SM walks the tile list
-  return launch_kernel(kern, grid, dim3(NUM_THREADS), smem, stream, ma, mb, mo, M, N, K, stages, rows_per_map, se, le, re);
+  return launch_kernel(kern, grid, dim3(NUM_THREADS), smem, stream, ma, mb, mo, M, N, K, stages, rows_per_map, se, le, re, k_splits);
 }
 
 // Route a bf16 [M, N] output (row pitch ldo) through the TMA-store epilogue when the pitch allows a tensor map.
@@ -771,17 +780,47 @@ extern "C" int b200_gemm_bf16(const void* A, const void* B, void* out, int M, in
   return (int)e;
 }
 
-// General-layout GEMM for the backward pass: out[M, N] = op(A) · op(B)^T-free, i.e. out[m, n] = sum_k A(m, k) · B(n, k) where
+// Split-K plan: how many K-ranges a (M, N, K) problem should be cut into (1 = none).  Skinny outputs with a very long
+// contraction (dX of the LM head: [1280 x 768] with K = 50257) otherwise leave most SMs idle behind ~800 serial k-blocks.
+extern "C" int b200_gemm_splitk_plan(int M, int N, int K) {
+  int bn = pick_bn(M, N);
+  if (bn < 64) bn = 64;
+  const long long tiles = (long long)((M + BM - 1) / BM) * ((N + bn - 1) / bn);
+  const int nkb = (K + BK - 1) / BK;
+  if (tiles * 2 > num_sms() || nkb < 32) return 1;
+  long long s = num_sms() / tiles;              // about one work item per SM
+  if (s > nkb / 8) s = nkb / 8;                 // at least 8 k-blocks per item
+  if (s > 64) s = 64;
+  if (s < 2) return 1;
+  const int per = (nkb + (int)s - 1) / (int)s;  // no empty trailing split
+  return (nkb + per - 1) / per;
+}
+
+__global__ void splitk_finalize_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ out, long long rows, int N,
+                                       long long ldo) {
+  const long long total = rows * N;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / N;
+    out[r * ldo + (i - r * N)] = __float2bfloat16(acc[i]);
+  }
+}
+
+// General-layout GEMM for the backward pass: out[m, n] = sum_k A(m, k) · B(n, k) where
 //   a_mn = 0: A is [M, K] row-major (K contiguous);   a_mn = 1: A is given as [K, M] row-major (M contiguous)
 //   b_mn = 0: B is [N, K] row-major (K contiguous);   b_mn = 1: B is given as [K, N] row-major (N contiguous)
-// lda / ldb are the row pitches of the arrays as stored.  bf16 (or fp32) output, optional accumulate-free bias.
+// lda / ldb are the row pitches of the arrays as stored.  bf16 (or fp32) output.
+// k_splits > 1 (from b200_gemm_splitk_plan) needs `ws`: a ZEROED fp32 [M, N] buffer the partial products are added into
+// (red.global.add.v4.f32 from the epilogue); it is then converted into `out` (or is the result itself when out_f32).
 extern "C" int b200_gemm_bf16_ex(const void* A, const void* B, void* out, int M, int N, int K, long long lda, long long ldb,
-                                 long long ldo, int a_mn, int b_mn, int out_f32, cudaStream_t stream) {
+                                 long long ldo, int a_mn, int b_mn, int out_f32, int k_splits, float* ws,
+                                 cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
-  if (!a_mn && !b_mn)
+  if (!a_mn && !b_mn && k_splits <= 1)
     return b200_gemm_bf16(A, B, out, M, N, K, lda, ldb, ldo, nullptr, nullptr, 0, nullptr, 1.0f, ACT_NONE, out_f32, 0, stream);
   int bn = pick_bn(M, N);
   if (bn < 64) bn = 64;  // MN-major tiles are fetched in 64-element boxes
+  const bool split = k_splits > 1 && ws != nullptr;
+  if (split && bn > 128) bn = 128;
   MapArray ma{};
   CUtensorMap mb;
   const bool ok_a = a_mn ? make_map(&ma.m[0], A, K, M, lda, 64, 64) : make_map(&ma.m[0], A, M, K, lda, BM);
@@ -789,23 +828,43 @@ extern "C" int b200_gemm_bf16_ex(const void* A, const void* B, void* out, int M,
   if (!ok_a || !ok_b) return -1;
   StoreEpilogue se{out, nullptr, nullptr, nullptr, ldo, 0, 1.0f, ACT_NONE, out_f32};
   CUtensorMap mo{};
-  if (!setup_tma_store(se, &mo, M, N, bn)) return -1;
   LMHeadEpilogue le{};
   ReduceScatterEpilogue re{};
+  if (split) {
+    re.acc[0] = ws;
+    re.ldacc = N;
+    re.rows_per_rank = 1 << 30;
+    se = StoreEpilogue{};
+  } else {
+    k_splits = 1;
+    if (!setup_tma_store(se, &mo, M, N, bn)) return -1;
+  }
   const int rpm = 1 << 30;
   cudaError_t e = cudaErrorInvalidValue;
-#define B200_EX_CASE(BN_)                                                                                     \
-  case BN_:                                                                                                   \
-    if (a_mn && b_mn) e = launch<BN_, 0, 1, 1>(ma, mb, mo, M, N, K, rpm, se, le, re, stream);                 \
-    else if (a_mn) e = launch<BN_, 0, 1, 0>(ma, mb, mo, M, N, K, rpm, se, le, re, stream);                    \
-    else e = launch<BN_, 0, 0, 1>(ma, mb, mo, M, N, K, rpm, se, le, re, stream);                              \
-    break;
-  switch (bn) {
-    B200_EX_CASE(256)
-    B200_EX_CASE(128)
-    B200_EX_CASE(64)
+#define B200_EX_LAUNCH(BN_, EPI_)                                                                                    \
+  (a_mn && b_mn ? launch<BN_, EPI_, 1, 1>(ma, mb, mo, M, N, K, rpm, se, le, re, stream, k_splits)                   \
+   : a_mn       ? launch<BN_, EPI_, 1, 0>(ma, mb, mo, M, N, K, rpm, se, le, re, stream, k_splits)                   \
+   : b_mn       ? launch<BN_, EPI_, 0, 1>(ma, mb, mo, M, N, K, rpm, se, le, re, stream, k_splits)                   \
+                : launch<BN_, EPI_, 0, 0>(ma, mb, mo, M, N, K, rpm, se, le, re, stream, k_splits))
+  if (split) {
+    switch (bn) {
+      case 128: e = B200_EX_LAUNCH(128, 2); break;
+      default: e = B200_EX_LAUNCH(64, 2); break;
+    }
+    if (e == cudaSuccess && !out_f32) {
+      long long blocks = ((long long)M * N + 255) / 256;
+      if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+      splitk_finalize_kernel<<<(int)blocks, 256, 0, stream>>>(ws, (__nv_bfloat16*)out, M, N, ldo);
+      e = cudaGetLastError();
+    }
+  } else {
+    switch (bn) {
+      case 256: e = B200_EX_LAUNCH(256, 0); break;
+      case 128: e = B200_EX_LAUNCH(128, 0); break;
+      default: e = B200_EX_LAUNCH(64, 0); break;
+    }
   }
-#undef B200_EX_CASE
+#undef B200_EX_LAUNCH
   return (int)e;
 }
 
