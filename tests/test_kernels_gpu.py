@@ -77,6 +77,48 @@ def test_gemm_split_k(C, a_mn, b_mn, split_k):
     assert (out32 - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
 
 
+@pytest.mark.parametrize("rms", [False, True])
+def test_gemm_with_folded_norm_and_row_moments(C, rms):
+    """LN(x)·Wᵀ computed as rstd·(x·(γW)ᵀ) − rstd·μ·c1 + (W·β + b) from producer-side row moments; the output's own row
+    moments are accumulated for the next folded norm."""
+    import torch.nn.functional as F
+
+    torch.manual_seed(11)
+    M, K, N, eps = 128, 768, 2304, 1e-5
+    x = (torch.randn(M, K, device="cuda") * 1.5 + 0.3).to(torch.bfloat16)
+    gamma = (1 + 0.1 * torch.randn(K, device="cuda")).to(torch.bfloat16)
+    beta = (0.1 * torch.randn(K, device="cuda")).to(torch.bfloat16)
+    W = (torch.randn(N, K, device="cuda") * K ** -0.5).to(torch.bfloat16)
+    b = (0.1 * torch.randn(N, device="cuda")).to(torch.bfloat16)
+    res = (torch.randn(M, N, device="cuda")).to(torch.bfloat16)
+    xf = x.float()
+    if rms:
+        ref_n = xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps) * gamma.float()
+        bias_f = b.float()
+    else:
+        ref_n = F.layer_norm(xf, (K,), gamma.float(), beta.float(), eps)
+        bias_f = W.float() @ beta.float() + b.float()
+    ref = ref_n @ W.float().t() + b.float() + res.float()
+    Wf = (W.float() * gamma.float()).to(torch.bfloat16)
+    c1 = Wf.float().sum(1).contiguous()
+    stats = torch.stack([xf.sum(1), xf.pow(2).sum(1)], 1).contiguous()
+    out_stats = torch.zeros(M, 2, device="cuda")
+    y = C.gemm_ln(x, Wf, bias_f.to(torch.bfloat16), res, "none", stats, c1, eps, rms, out_stats)
+    err = (y.float() - ref).abs().max().item()
+    assert err <= 3e-2 * ref.abs().max().item(), err
+    torch.testing.assert_close(out_stats[:, 0], y.float().sum(1), atol=0.5, rtol=1e-3)
+    torch.testing.assert_close(out_stats[:, 1], y.float().pow(2).sum(1), atol=0.5, rtol=1e-3)
+    # embed produces the first set of moments
+    wte = (torch.randn(50, K, device="cuda")).to(torch.bfloat16)
+    wpe = (torch.randn(16, K, device="cuda")).to(torch.bfloat16)
+    tok = torch.randint(0, 50, (M,), device="cuda")
+    pos = torch.randint(0, 16, (M,), device="cuda", dtype=torch.int32)
+    st0 = torch.zeros(M, 2, device="cuda")
+    e = C.embed(tok, pos, wte, wpe, 0, None, st0)
+    torch.testing.assert_close(st0[:, 0], e.float().sum(1), atol=0.1, rtol=1e-3)
+    torch.testing.assert_close(st0[:, 1], e.float().pow(2).sum(1), atol=0.1, rtol=1e-3)
+
+
 def test_lmhead_dlogits(C):
     torch.manual_seed(5)
     M, V, K = 300, 50257, 256

@@ -23,7 +23,7 @@ int b200_lmhead_bf16(const void*, const void*, int, int, int, long long, long lo
                      float*, float*, int, float, unsigned long long, const long long*, const int*, int, int, long long*, float*,
                      cudaStream_t);
 int b200_norm_bf16(const void*, const void*, const void*, void*, int, int, long long, long long, float, int, cudaStream_t);
-int b200_embed_bf16(const long long*, const int*, const void*, const void*, int, void*, int, int, cudaStream_t);
+int b200_embed_bf16(const long long*, const int*, const void*, const void*, int, void*, int, int, float*, cudaStream_t);
 int b200_decode_attention_bf16(const void*, void*, void*, const int*, const int*, const int*, void*, int, int, int, int, int,
                                int, float, int, float, int, const float*, int, cudaStream_t);
 int b200_rowdot_bf16(const void*, const void*, const void*, float*, int, int, long long, cudaStream_t);
@@ -32,6 +32,8 @@ int b200_decode_step(const long long*, const float*, const float*, const float*,
 int b200_paged_kv_write(const void*, const void*, void*, void*, const int*, const int*, const int*, int, int, int, int, int,
                         int, long long, long long, cudaStream_t);
 int b200_logprob_from_logits(const void*, const long long*, float*, float*, long long, int, long long, int, cudaStream_t);
+int b200_gemm_bf16_ln(const void*, const void*, void*, int, int, int, long long, long long, long long, const void*, const void*,
+                      long long, int, const float*, const float*, float, int, float*, cudaStream_t);
 int b200_gemm_bf16_ex(const void*, const void*, void*, int, int, int, long long, long long, long long, int, int, int, int, float*,
                       cudaStream_t);
 int b200_gemm_splitk_plan(int, int, int);
@@ -111,6 +113,33 @@ Tensor gemm(const Tensor& x, const Tensor& w, const OptTensor& bias, const OptTe
                        out.stride(0), optptr(bias), optptr(residual), ldr, (const float*)optptr(col_scale), (float)alpha,
                        act_code(act), out.scalar_type() == at::kFloat, (int)force_bn, stream()),
         "gemm");
+  return out;
+}
+
+// y = act(LN(x) @ w^T + b) + residual with the normalisation FOLDED into the GEMM: `x` is the raw residual stream, `w` already
+// carries gamma (w * gamma[None, :]), `bias` carries w @ beta + b, `ln_c1[n] = sum_k w[n, k]`, and `ln_stats` = [M, 2] row
+// (sum, sum of squares) of x that the producer of x accumulated through its own `stats_out`.
+Tensor gemm_ln(const Tensor& x, const Tensor& w, const OptTensor& bias, const OptTensor& residual, const std::string& act,
+               const OptTensor& ln_stats, const OptTensor& ln_c1, double ln_eps, bool ln_rms, const OptTensor& stats_out) {
+  CHECK_BF16(x); CHECK_BF16(w);
+  TORCH_CHECK(x.dim() == 2 && w.dim() == 2 && x.size(1) == w.size(1) && x.stride(1) == 1 && w.stride(1) == 1);
+  const int64_t M = x.size(0), N = w.size(0), K = x.size(1);
+  TORCH_CHECK(K % 8 == 0 && N % 16 == 0 && x.stride(0) % 8 == 0 && w.stride(0) % 8 == 0, "gemm_ln: K % 8, N % 16");
+  c10::cuda::CUDAGuard guard(x.device());
+  Tensor out = torch::empty({M, N}, x.options());
+  long long ldr = 0;
+  if (residual.has_value()) { CHECK_BF16(*residual); TORCH_CHECK(residual->size(0) == M && residual->size(1) == N && residual->stride(1) == 1); ldr = residual->stride(0); }
+  if (bias.has_value()) { CHECK_BF16(*bias); TORCH_CHECK(bias->numel() == N); }
+  const float* st = nullptr; const float* c1 = nullptr; float* so = nullptr;
+  if (ln_stats.has_value()) {
+    CHECK_F32(*ln_stats); TORCH_CHECK(ln_stats->numel() == 2 * M && ln_stats->is_contiguous() && ln_c1.has_value());
+    CHECK_F32(*ln_c1); TORCH_CHECK(ln_c1->numel() == N && ln_c1->is_contiguous());
+    st = ln_stats->data_ptr<float>(); c1 = ln_c1->data_ptr<float>();
+  }
+  if (stats_out.has_value()) { CHECK_F32(*stats_out); TORCH_CHECK(stats_out->numel() == 2 * M && stats_out->is_contiguous()); so = stats_out->data_ptr<float>(); }
+  check(b200_gemm_bf16_ln(x.data_ptr(), w.data_ptr(), out.data_ptr(), (int)M, (int)N, (int)K, x.stride(0), w.stride(0), out.stride(0),
+                          optptr(bias), optptr(residual), ldr, act_code(act), st, c1, (float)ln_eps, ln_rms ? 1 : 0, so, stream()),
+        "gemm_ln");
   return out;
 }
 
@@ -200,7 +229,7 @@ Tensor norm(const Tensor& x, const Tensor& w, const OptTensor& b, double eps, bo
 }
 
 Tensor embed(const Tensor& tokens, const Tensor& positions, const Tensor& wte, const OptTensor& wpe, int64_t pos_offset,
-             const OptTensor& out_) {
+             const OptTensor& out_, const OptTensor& stats_out) {
   CHECK_BF16(wte);
   TORCH_CHECK(tokens.scalar_type() == at::kLong && positions.scalar_type() == at::kInt);
   c10::cuda::CUDAGuard guard(wte.device());
@@ -208,7 +237,8 @@ Tensor embed(const Tensor& tokens, const Tensor& positions, const Tensor& wte, c
   TORCH_CHECK(H % 8 == 0);
   Tensor x = out_.has_value() ? *out_ : torch::empty({B, H}, wte.options());
   check(b200_embed_bf16((const long long*)tokens.data_ptr<int64_t>(), positions.data_ptr<int>(), wte.data_ptr(), optptr(wpe),
-                        (int)pos_offset, x.data_ptr(), (int)B, (int)H, stream()),
+                        (int)pos_offset, x.data_ptr(), (int)B, (int)H,
+                        stats_out.has_value() ? stats_out->data_ptr<float>() : nullptr, stream()),
         "embed");
   return x;
 }
@@ -535,6 +565,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("sample") = false, py::arg("temperature") = 1.0, py::arg("seed") = 0, py::arg("step") = py::none(),
         py::arg("suppress_col") = -1, py::arg("suppress_until") = 0, py::arg("workspace") = py::none(),
         py::arg("seed_tensor") = py::none());
+  m.def("gemm_ln", &gemm_ln, py::arg("x"), py::arg("w"), py::arg("bias") = py::none(), py::arg("residual") = py::none(),
+        py::arg("act") = "none", py::arg("ln_stats") = py::none(), py::arg("ln_c1") = py::none(), py::arg("ln_eps") = 1e-5,
+        py::arg("ln_rms") = false, py::arg("stats_out") = py::none());
   m.def("gemm_ex", &gemm_ex, py::arg("a"), py::arg("b"), py::arg("a_mn") = false, py::arg("b_mn") = false,
         py::arg("out_f32") = false, py::arg("split_k") = -1);
   m.def("lmhead_tiles", [](int64_t n) { return (int64_t)b200_lmhead_tiles((int)n); }, py::arg("vocab"));
@@ -543,7 +576,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("norm", &norm, py::arg("x"), py::arg("w"), py::arg("b") = py::none(), py::arg("eps") = 1e-5, py::arg("rms") = false,
         py::arg("out") = py::none());
   m.def("embed", &embed, py::arg("tokens"), py::arg("positions"), py::arg("wte"), py::arg("wpe") = py::none(),
-        py::arg("pos_offset") = 0, py::arg("out") = py::none());
+        py::arg("pos_offset") = 0, py::arg("out") = py::none(), py::arg("stats_out") = py::none());
   m.def("decode_attention", &decode_attention, py::arg("qkv"), py::arg("kcache"), py::arg("vcache"), py::arg("block_table"),
         py::arg("seq_lens"), py::arg("positions"), py::arg("nq"), py::arg("nkv"), py::arg("d"), py::arg("scale"),
         py::arg("rot_dim") = 0, py::arg("rot_base") = 10000.0, py::arg("rot_interleaved") = false,

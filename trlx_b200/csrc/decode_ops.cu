@@ -65,22 +65,39 @@ __global__ void __launch_bounds__(128) norm_kernel(const __nv_bfloat16* __restri
 // x[b,:] = wte[token[b]] + wpe[pos[b] + pos_offset]   (wpe optional)
 __global__ void embed_kernel(const long long* __restrict__ tokens, const int* __restrict__ positions,
                              const __nv_bfloat16* __restrict__ wte, const __nv_bfloat16* __restrict__ wpe, int pos_offset,
-                             __nv_bfloat16* __restrict__ x, int H) {
+                             __nv_bfloat16* __restrict__ x, int H, float* __restrict__ stats_out) {
   griddep_wait();
   griddep_launch();
   const int b = blockIdx.x;
   const __nv_bfloat16* te = wte + (size_t)tokens[b] * H;
   const __nv_bfloat16* pe = wpe ? wpe + (size_t)(positions[b] + pos_offset) * H : nullptr;
+  float s1 = 0.f, s2 = 0.f;
   for (int i = threadIdx.x; i < (H >> 3); i += blockDim.x) {
     uint4 a = *reinterpret_cast<const uint4*>(te + i * 8);
+    __nv_bfloat162* a2 = reinterpret_cast<__nv_bfloat162*>(&a);
     if (pe) {
       uint4 p = *reinterpret_cast<const uint4*>(pe + i * 8);
-      __nv_bfloat162* a2 = reinterpret_cast<__nv_bfloat162*>(&a);
       const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&p);
 #pragma unroll
       for (int j = 0; j < 4; ++j) a2[j] = __hadd2(a2[j], p2[j]);
     }
+    if (stats_out) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(a2[j]);
+        s1 += f.x + f.y;
+        s2 += f.x * f.x + f.y * f.y;
+      }
+    }
     *reinterpret_cast<uint4*>(x + (size_t)b * H + i * 8) = a;
+  }
+  if (stats_out) {  // row moments for the first block's folded LayerNorm (see gemm_sm100.cu: StoreEpilogue::ln_stats)
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(stats_out + 2 * (size_t)b, s1);
+      atomicAdd(stats_out + 2 * (size_t)b + 1, s2);
+    }
   }
 }
 
@@ -347,10 +364,10 @@ extern "C" int b200_norm_bf16(const void* x, const void* w, const void* b, void*
 }
 
 extern "C" int b200_embed_bf16(const long long* tokens, const int* positions, const void* wte, const void* wpe,
-                               int pos_offset, void* x, int B, int H, cudaStream_t stream) {
+                               int pos_offset, void* x, int B, int H, float* stats_out, cudaStream_t stream) {
   if (B <= 0) return 0;
   return (int)launch_kernel(embed_kernel, dim3(B), dim3(128), 0, stream, tokens, positions, (const __nv_bfloat16*)wte,
-                            (const __nv_bfloat16*)wpe, pos_offset, (__nv_bfloat16*)x, H);
+                            (const __nv_bfloat16*)wpe, pos_offset, (__nv_bfloat16*)x, H, stats_out);
 }
 
 extern "C" int b200_decode_attention_bf16(const void* qkv, void* kcache, void* vcache, const int* block_table,

@@ -47,6 +47,16 @@ struct StoreEpilogue {
   const float* dl_grad;
   const long long* dl_labels;
   int debug_nostore;
+  // LayerNorm / RMSNorm folded into this GEMM (decode path): the A operand is the RAW residual stream x and the weights are
+  // pre-multiplied by gamma, so  LN(x).W^T = rstd*(x.(gamma*W)^T) - rstd*mu*c1 + (W.beta + b)  with per-row (mu, rstd) from
+  // ln_stats = [M, 2] (sum x, sum x^2) that the PRODUCER of x accumulated, c1[n] = sum_k gamma_k W[n,k]; the constant term
+  // is passed as the ordinary bias.  ln_rms: RMSNorm (mu = 0).
+  const float* ln_stats;
+  const float* ln_c1;
+  float ln_inv_k, ln_eps;
+  int ln_rms;
+  // ... and the producer side: accumulate (sum, sum of squares) of the bf16-rounded output rows for the NEXT folded norm
+  float* stats_out;
   int tma_store;              // bf16 output goes through shared memory + cp.async.bulk.tensor (needs ldo % 8 == 0)
 };
 
@@ -148,11 +158,12 @@ struct RowCtx {      // per-thread (= per output row) constants of the store epi
   bool dl;
   float dl_l, dl_g;
   long long dl_lab;
+  float ln_rstd, ln_murstd;
 };
 
 // v = act(alpha * acc [* col_scale] [+ bias])  (or the d-logits transform)  [+ residual]   for a FULL 16-column chunk
 __device__ __forceinline__ void store_values_full(const uint32_t (&r)[16], float (&v)[16], int row, int col0,
-                                                  const StoreEpilogue& se, const RowCtx& rc, bool vec_in) {
+                                                  const StoreEpilogue& se, const RowCtx& rc, bool vec_in, bool row_ok) {
 #pragma unroll
   for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) * se.alpha;
   if (se.col_scale) {
@@ -160,6 +171,16 @@ __device__ __forceinline__ void store_values_full(const uint32_t (&r)[16], float
     for (int j = 0; j < 16; j += 4) {
       const float4 c = *reinterpret_cast<const float4*>(se.col_scale + col0 + j);  // col0 % 16 == 0, fp32 [N] 16B-aligned
       v[j] *= c.x; v[j + 1] *= c.y; v[j + 2] *= c.z; v[j + 3] *= c.w;
+    }
+  }
+  if (se.ln_stats) {  // folded normalisation: per-row scale, per-row x per-column mean correction
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const float4 c = *reinterpret_cast<const float4*>(se.ln_c1 + col0 + j);
+      v[j] = v[j] * rc.ln_rstd - rc.ln_murstd * c.x;
+      v[j + 1] = v[j + 1] * rc.ln_rstd - rc.ln_murstd * c.y;
+      v[j + 2] = v[j + 2] * rc.ln_rstd - rc.ln_murstd * c.z;
+      v[j + 3] = v[j + 3] * rc.ln_rstd - rc.ln_murstd * c.w;
     }
   }
   if (se.bias) {
@@ -199,6 +220,17 @@ __device__ __forceinline__ void store_values_full(const uint32_t (&r)[16], float
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] += b[j];
   }
+  if (se.stats_out && row_ok) {  // moments of what the consumer will actually read (the bf16-rounded row)
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float f = __bfloat162float(__float2bfloat16(v[j]));
+      s1 += f;
+      s2 += f * f;
+    }
+    atomicAdd(se.stats_out + 2 * (size_t)row, s1);
+    atomicAdd(se.stats_out + 2 * (size_t)row + 1, s2);
+  }
 }
 
 // ragged last chunk of a row (col0 + 16 > N): rolled, scalar, correct for any alignment; columns >= N come out as 0
@@ -234,8 +266,15 @@ __device__ __forceinline__ void epilogue_cols(uint32_t taddr_row, int row, bool 
                                               const ReduceScatterEpilogue& re, uint8_t* stg, const CUtensorMap* map_out,
                                               int row0_warp, int lane) {
   if constexpr (EPI == 0) {
-    RowCtx rc{se.dl_lse != nullptr, 0.f, 0.f, -1};
+    RowCtx rc{se.dl_lse != nullptr, 0.f, 0.f, -1, 1.f, 0.f};
     if (rc.dl && row_ok) { rc.dl_l = se.dl_lse[row]; rc.dl_g = se.dl_grad[row]; rc.dl_lab = se.dl_labels[row]; }
+    if (se.ln_stats && row_ok) {
+      const float s1 = se.ln_stats[2 * (size_t)row], s2 = se.ln_stats[2 * (size_t)row + 1];
+      const float mean = se.ln_rms ? 0.f : s1 * se.ln_inv_k;
+      const float var = fmaxf(s2 * se.ln_inv_k - mean * mean, 0.f);
+      rc.ln_rstd = rsqrtf(var + se.ln_eps);
+      rc.ln_murstd = mean * rc.ln_rstd;
+    }
     // 16-byte vector access to bias / residual / output needs 16-byte aligned bases (col0 is a multiple of 16 elements)
     const bool vec_in = ((reinterpret_cast<uintptr_t>(se.bias) | reinterpret_cast<uintptr_t>(se.residual)) & 15) == 0;
     const bool vec_out = ((se.ldo & 7) == 0) && ((reinterpret_cast<uintptr_t>(se.out) & 15) == 0);
@@ -260,7 +299,7 @@ __device__ __forceinline__ void epilogue_cols(uint32_t taddr_row, int row, bool 
       tmem_ld_wait();
       float v[16];
       const bool full = col0 + 16 <= N;
-      if (full) store_values_full(r, v, row_ok ? row : 0, col0, se, rc, vec_in);
+      if (full) store_values_full(r, v, row_ok ? row : 0, col0, se, rc, vec_in, row_ok);
       else {  // rare: keep the address-taken copies out of the hot path's registers
         uint32_t tr[16];
         float tv[16];
@@ -754,9 +793,39 @@ extern "C" void b200_set_pdl(int on) { set_pdl_enabled(on != 0); }
 extern "C" int b200_get_pdl() { return pdl_enabled() ? 1 : 0; }
 
 // act: 0 none, 1 gelu_tanh, 2 gelu_erf, 3 relu, 4 silu.  Requirements: K % 8 == 0, lda/ldb % 8 == 0, 16B-aligned A/B.
+struct LnFold {
+  const float* stats_in = nullptr;  // [M, 2] (sum, sum sq) of the raw A rows
+  const float* c1 = nullptr;        // [N]
+  float eps = 1e-5f;
+  int rms = 0;
+  float* stats_out = nullptr;       // [M, 2] accumulated for the next folded norm
+};
+static int gemm_bf16_impl(const void* A, const void* B, void* out, int M, int N, int K, long long lda, long long ldb,
+                          long long ldo, const void* bias, const void* residual, long long ldr, const float* col_scale,
+                          float alpha, int act, int out_f32, int force_bn, const LnFold& ln, cudaStream_t stream);
+
 extern "C" int b200_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K, long long lda, long long ldb,
                               long long ldo, const void* bias, const void* residual, long long ldr, const float* col_scale,
                               float alpha, int act, int out_f32, int force_bn, cudaStream_t stream) {
+  return gemm_bf16_impl(A, B, out, M, N, K, lda, ldb, ldo, bias, residual, ldr, col_scale, alpha, act, out_f32, force_bn, LnFold{},
+                        stream);
+}
+
+// GEMM with a folded LayerNorm/RMSNorm on its input and/or row-moment accumulation on its output (see StoreEpilogue).
+// Requires N % 16 == 0 (decode shapes); ln_stats_in / ln_c1 / stats_out may each be null.
+extern "C" int b200_gemm_bf16_ln(const void* A, const void* B, void* out, int M, int N, int K, long long lda, long long ldb,
+                                 long long ldo, const void* bias, const void* residual, long long ldr, int act,
+                                 const float* ln_stats_in, const float* ln_c1, float ln_eps, int ln_rms, float* stats_out,
+                                 cudaStream_t stream) {
+  if (N % 16) return -4;
+  LnFold ln;
+  ln.stats_in = ln_stats_in; ln.c1 = ln_c1; ln.eps = ln_eps; ln.rms = ln_rms; ln.stats_out = stats_out;
+  return gemm_bf16_impl(A, B, out, M, N, K, lda, ldb, ldo, bias, residual, ldr, nullptr, 1.0f, act, 0, 0, ln, stream);
+}
+
+static int gemm_bf16_impl(const void* A, const void* B, void* out, int M, int N, int K, long long lda, long long ldb,
+                          long long ldo, const void* bias, const void* residual, long long ldr, const float* col_scale,
+                          float alpha, int act, int out_f32, int force_bn, const LnFold& ln, cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   const int bn = force_bn ? force_bn : pick_bn(M, N);
   MapArray ma{};
@@ -765,6 +834,12 @@ extern "C" int b200_gemm_bf16(const void* A, const void* B, void* out, int M, in
   StoreEpilogue se{out, (const __nv_bfloat16*)bias, (const __nv_bfloat16*)residual, col_scale, ldo, ldr, alpha, act, out_f32};
   static const bool nostore = getenv("B200_GEMM_NOSTORE") != nullptr;
   se.debug_nostore = nostore ? 1 : 0;
+  se.ln_stats = ln.stats_in;
+  se.ln_c1 = ln.c1;
+  se.ln_inv_k = 1.0f / (float)K;
+  se.ln_eps = ln.eps;
+  se.ln_rms = ln.rms;
+  se.stats_out = ln.stats_out;
   CUtensorMap mo{};
   if (!setup_tma_store(se, &mo, M, N, bn)) return -1;
   LMHeadEpilogue le{};

@@ -62,6 +62,30 @@ def _layer_weights(block, spec, idx: int) -> _LayerW:
                    spec.local_window if idx in spec.local_layers else 0)
 
 
+@dataclass
+class _FoldW:
+    """Per-layer derived weights for norm-folded GEMMs: ``LN(x)·Wᵀ = rstd·(x·(γ⊙W)ᵀ) − rstd·μ·c1 + (W·β + b)``."""
+
+    qkv_w: torch.Tensor
+    qkv_b: torch.Tensor
+    qkv_c1: torch.Tensor
+    up_w: torch.Tensor
+    up_b: torch.Tensor
+    up_c1: torch.Tensor
+    trainable: bool
+
+
+def _fold(w: torch.Tensor, b: Optional[torch.Tensor], gamma: torch.Tensor, beta: Optional[torch.Tensor]):
+    wf = (w.float() * gamma.float()).to(torch.bfloat16)
+    c1 = wf.float().sum(1).contiguous()
+    bias = torch.zeros(w.shape[0], dtype=torch.float32, device=w.device)
+    if beta is not None:
+        bias = bias + w.float() @ beta.float()
+    if b is not None:
+        bias = bias + b.float()
+    return wf.contiguous(), bias.to(torch.bfloat16).contiguous(), c1
+
+
 class RolloutEngine:
     @staticmethod
     def supports(model, gen_kwargs: Dict[str, Any], config=None, stop_sequences=None) -> bool:
@@ -119,9 +143,80 @@ class RolloutEngine:
         self.launches_per_step = 0
         import os
 
+        # LayerNorm folding (decode): the two norm kernels of every block disappear — their effect is applied in the
+        # epilogue of the GEMM that consumes them, from row moments accumulated by the GEMM (or embed) that produced x.
+        folded_bytes = sum((W.qkv_w.numel() + W.up_w.numel()) * 2 for W in self.layers + self.ref_layers)
+        self.fold_norms = (os.environ.get("TRLX_B200_FOLD_NORMS", "1") == "1" and self.lm.transformer.emb_norm is None
+                           and spec.hidden_size % 16 == 0 and all(W.qkv_w.shape[0] % 16 == 0 and W.up_w.shape[0] % 16 == 0
+                                                                  for W in self.layers + self.ref_layers)
+                           and folded_bytes <= int(os.environ.get("TRLX_B200_FOLD_BUDGET_MB", "4096")) << 20)
+        self.folded: List[_FoldW] = []
+        self.ref_folded: List[_FoldW] = []
+        self.dirty = True  # folded copies must be (re)built before the next rollout
         self.parallel_branches = os.environ.get("TRLX_B200_PARALLEL_BRANCHES", "1") == "1" and self.branch < len(self.layers)
         self.side = torch.cuda.Stream(device=self.device) if self.parallel_branches else None
         ops.C.set_pdl(os.environ.get("TRLX_B200_PDL", "1") == "1")
+
+    # ------------------------------------------------------------------------------------------------ folded weights
+    def mark_dirty(self):
+        """The trainer calls this after every optimizer step / checkpoint load (weights are updated through raw pointers
+        by the fused optimizer, so tensor version counters cannot be relied on)."""
+        self.dirty = True
+
+    @torch.no_grad()
+    def refresh_folded(self):
+        """(Re)build γ-scaled copies of the QKV / MLP-up weights in place (the captured CUDA graph keeps their addresses)."""
+        if not self.fold_norms or not self.dirty:
+            return
+        first = not self.folded
+
+        def build(W: _LayerW, old: Optional[_FoldW]) -> _FoldW:
+            n2w, n2b = (W.n2w, W.n2b) if W.n2w is not None else (W.n1w, W.n1b)
+            trainable = any(t is not None and t.requires_grad for t in (W.n1w, W.n1b, W.n2w, W.n2b, W.qkv_w, W.qkv_b, W.up_w, W.up_b))
+            if old is not None and not trainable:
+                return old
+            q = _fold(W.qkv_w, W.qkv_b, W.n1w, W.n1b)
+            u = _fold(W.up_w, W.up_b, n2w, n2b)
+            if old is None:
+                return _FoldW(*q, *u, trainable)
+            for dst, src in zip((old.qkv_w, old.qkv_b, old.qkv_c1, old.up_w, old.up_b, old.up_c1), q + u):
+                dst.copy_(src)
+            return old
+
+        self.folded = [build(W, None if first else self.folded[i]) for i, W in enumerate(self.layers)]
+        self.ref_folded = [build(W, None if first else self.ref_folded[i]) for i, W in enumerate(self.ref_layers)]
+        self.dirty = False
+
+    def _layer_folded(self, x, xs, W: _LayerW, FW: _FoldW, kc, vc, st):
+        """One block with both norms folded.  ``xs`` = row moments ``[B, 2]`` of ``x``; returns ``(x_out, moments of x_out)``."""
+        C, spec = ops.C, self.spec
+        rms, eps = spec.norm == "rmsnorm", spec.norm_eps
+        qkv = C.gemm_ln(x, FW.qkv_w, FW.qkv_b, None, "none", xs, FW.qkv_c1, eps, rms, None)
+        a = C.decode_attention(qkv, kc, vc, st["block_table"], st["seq_lens"], st["positions"], spec.num_heads,
+                               spec.num_kv_heads, spec.head_dim, self.scale, self.rot_dim, spec.rotary_base,
+                               spec.rotary_interleaved, self.alibi, W.window)
+        out_stats = self._next_stats(st)
+        if spec.parallel_residual:
+            t = C.gemm(a, W.out_w, W.out_b, x)
+            mid = self._mlp_mid_folded(x, xs, FW)
+            return C.gemm_ln(mid, W.down_w, W.down_b, t, "none", None, None, eps, rms, out_stats), out_stats
+        x = C.gemm_ln(a, W.out_w, W.out_b, x, "none", None, None, eps, rms, out_stats)
+        mid = self._mlp_mid_folded(x, out_stats, FW)
+        out2 = self._next_stats(st)
+        return C.gemm_ln(mid, W.down_w, W.down_b, x, "none", None, None, eps, rms, out2), out2
+
+    def _mlp_mid_folded(self, x, xs, FW: _FoldW):
+        C, spec = ops.C, self.spec
+        rms, eps = spec.norm == "rmsnorm", spec.norm_eps
+        if spec.gated_mlp:
+            g, u = C.gemm_ln(x, FW.up_w, FW.up_b, None, "none", xs, FW.up_c1, eps, rms, None).chunk(2, dim=-1)
+            return (F.silu(g) * u).contiguous() if spec.activation in ("silu", "swish") else (F.gelu(g, approximate="tanh") * u).contiguous()
+        return C.gemm_ln(x, FW.up_w, FW.up_b, None, spec.activation, xs, FW.up_c1, eps, rms, None)
+
+    def _next_stats(self, st):
+        i = st["stats_cursor"]
+        st["stats_cursor"] = i + 1
+        return st["ln_stats"][i]
 
     # ------------------------------------------------------------------------------------------------ kernels per layer
     def _layer(self, x, W: _LayerW, kc, vc, st):
@@ -151,8 +246,14 @@ class RolloutEngine:
         """One token for every running row; pure device work (captured into a CUDA graph)."""
         C, spec, lm, model = ops.C, self.spec, self.lm, self.model
         tr = lm.transformer
+        fold = self.fold_norms
+        xs = None
+        if fold:
+            st["ln_stats"].zero_()  # one memset node: every row-moment slot of this step
+            st["stats_cursor"] = 0
+            xs = self._next_stats(st)
         x = C.embed(st["next_tokens"], st["positions"], tr.wte.weight, tr.wpe.weight if tr.wpe is not None else None,
-                    spec.pos_offset)
+                    spec.pos_offset, None, xs)
         if tr.emb_norm is not None:
             x = C.norm(x, tr.emb_norm.weight, tr.emb_norm.bias, spec.norm_eps, spec.norm == "rmsnorm")
         trunk_x = x
@@ -161,6 +262,7 @@ class RolloutEngine:
         L = len(self.layers)
         main = torch.cuda.current_stream()
         rf = None
+        trunk_xs = xs
         for i, W in enumerate(self.layers):
             if i == self.branch:
                 trunk_x = x
@@ -169,13 +271,21 @@ class RolloutEngine:
                     # graph has two independent chains (policy top blocks || reference blocks) instead of one long one
                     self.side.wait_stream(main)
                     with torch.cuda.stream(self.side):
-                        y = trunk_x
+                        y, ys = trunk_x, xs
                         for j, Wr in enumerate(self.ref_layers):
-                            y = self._layer(y, Wr, st["kc"][L + j], st["vc"][L + j], st)
+                            if fold:
+                                y, ys = self._layer_folded(y, ys, Wr, self.ref_folded[j], st["kc"][L + j], st["vc"][L + j], st)
+                            else:
+                                y = self._layer(y, Wr, st["kc"][L + j], st["vc"][L + j], st)
                         rf = C.norm(y, fh.final_norm.weight, fh.final_norm.bias, spec.norm_eps, rms)
                         if self.cache_trunk:
                             st["trunk_decode"].index_copy_(1, st["step64"], trunk_x.unsqueeze(1))
-            x = self._layer(x, W, st["kc"][i], st["vc"][i], st)
+            if i == self.branch:
+                trunk_xs = xs
+            if fold:
+                x, xs = self._layer_folded(x, xs, W, self.folded[i], st["kc"][i], st["vc"][i], st)
+            else:
+                x = self._layer(x, W, st["kc"][i], st["vc"][i], st)
         if self.cache_trunk and not self.parallel_branches:
             st["trunk_decode"].index_copy_(1, st["step64"], trunk_x.unsqueeze(1))
         hf = C.norm(x, tr.ln_f.weight, tr.ln_f.bias, spec.norm_eps, rms)
@@ -185,9 +295,12 @@ class RolloutEngine:
         h1 = C.gemm(hf, vh[0].weight, vh[0].bias, None, "relu")
         val = C.rowdot(h1, vh[2].weight.view(-1), vh[2].bias)
         if rf is None:
-            y = trunk_x
+            y, ys = trunk_x, (trunk_xs if fold else None)
             for j, W in enumerate(self.ref_layers):
-                y = self._layer(y, W, st["kc"][L + j], st["vc"][L + j], st)
+                if fold:
+                    y, ys = self._layer_folded(y, ys, W, self.ref_folded[j], st["kc"][L + j], st["vc"][L + j], st)
+                else:
+                    y = self._layer(y, W, st["kc"][L + j], st["vc"][L + j], st)
             rf = C.norm(y, fh.final_norm.weight, fh.final_norm.bias, spec.norm_eps, rms)
         else:
             main.wait_stream(self.side)
@@ -221,6 +334,7 @@ class RolloutEngine:
             ws=torch.empty(5 * B * n_tiles + B, **f32), ws_ref=torch.empty(5 * B * n_tiles + B, **f32),
             trunk_decode=(torch.zeros(B, R, spec.hidden_size, dtype=torch.bfloat16, device=dev) if self.cache_trunk else None),
             seed_dev=torch.zeros(1, dtype=torch.long, device=dev), min_new=0, graph=None,
+            ln_stats=torch.zeros(2 * n_layers + 2, B, 2, **f32), stats_cursor=0,
         )
         return st
 
@@ -306,6 +420,7 @@ class RolloutEngine:
         if R is None:
             R = max(int(g.get("max_length", Q + 20)) - Q, 1)
         R = int(R)
+        self.refresh_folded()
         st = self._ensure_state(B, Q, R)
         q_lens = mask.sum(1)
         self._reset(st, q_lens, prompt[:, -1])

@@ -205,6 +205,11 @@ class AcceleratePPOTrainer(AccelerateRLTrainer):
         self._after_weights_changed()
         return stats
 
+    def _after_weights_changed(self):
+        super()._after_weights_changed()
+        if getattr(self, "_engine", None) is not None:
+            self._engine.mark_dirty()  # its γ-folded weight copies are rebuilt lazily before the next rollout
+
     def prepare_learning(self):
         self.eval_dataloader = self.eval_pipeline.create_loader(self.config.method.chunk_size)
         self.make_experience(self.config.method.num_rollouts)
