@@ -275,6 +275,7 @@ def main():
             loader = timed("create_loader", trainer.create_train_dataloader)
             for minibatch in MiniBatchIterator(loader, trainer.mb_size, trainer.num_mb):
                 timed("train_step(16x)", trainer.train_step, minibatch)
+        acc["train_graphs_captured"] = len(getattr(trainer, "_graphed_steps", {}) or {})
         print("BREAKDOWN_MS " + json.dumps({k: round(v, 2) for k, v in acc.items()}), file=sys.stderr)
     if os.environ.get("BENCH_PROFILE") and rank == 0:
         # per-kernel device time of the two phases (torch.profiler/CUPTI; diagnostic only — never a bench number)

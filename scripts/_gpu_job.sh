@@ -1,4 +1,4 @@
-for t in test_gemm_with_folded_norm_and_row_moments test_gemm_split_k test_gemm_mn_major_operands test_linear_autograd test_fused_logprob_autograd test_embed_rowdot; do timeout 100 python -m pytest tests/test_kernels_gpu.py -m gpu -q -x -k "$t" --timeout=45 --timeout-method=thread -p no:cacheprovider 2>&1 | tail -2; done
+for t in test_gemm_with_folded_norm_and_row_moments test_gemm_split_k test_gemm_mn_major_operands test_linear_autograd test_fused_logprob_autograd test_embed_rowdot; do timeout 100 python -m pytest tests/test_kernels_gpu.py -m gpu -q -x -k "$t" --timeout=45 --timeout-method=thread -p no:cacheprovider 2>&1 | grep -E "^E  |passed|failed" | head -12; done
 timeout 300 python -m pytest tests/test_engine_gpu.py -m gpu -q -x --timeout=200 --timeout-method=thread -p no:cacheprovider 2>&1 | tail -4
 echo "=== bench (fold norms)"; BENCH_BREAKDOWN=1 timeout 300 python bench.py --steps 10 --warmup 4 2>&1 | tail -2 | cut -c1-500
 echo "=== bench (no fold)"; TRLX_B200_FOLD_NORMS=0 BENCH_BREAKDOWN=1 timeout 300 python bench.py --steps 10 --warmup 4 2>&1 | tail -2 | cut -c1-500

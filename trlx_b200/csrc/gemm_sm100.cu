@@ -894,6 +894,12 @@ extern "C" int b200_gemm_bf16_ex(const void* A, const void* B, void* out, int M,
     return b200_gemm_bf16(A, B, out, M, N, K, lda, ldb, ldo, nullptr, nullptr, 0, nullptr, 1.0f, ACT_NONE, out_f32, 0, stream);
   int bn = pick_bn(M, N);
   if (bn < 64) bn = 64;  // MN-major tiles are fetched in 64-element boxes
+  if (k_splits > 1) {  // normalise: every split must own at least one k-block
+    const int nkb = (K + BK - 1) / BK;
+    if (k_splits > nkb) k_splits = nkb;
+    const int per = (nkb + k_splits - 1) / k_splits;
+    k_splits = (nkb + per - 1) / per;
+  }
   const bool split = k_splits > 1 && ws != nullptr;
   if (split && bn > 128) bn = 128;
   MapArray ma{};

@@ -80,7 +80,11 @@ def _columns(batch) -> dict:
 
 def _rebuild(batch, cols: dict):
     if is_dataclass(batch):
-        return type(batch)(**cols)
+        out = type(batch)(**cols)
+        for k, v in vars(batch).items():  # per-batch annotations that are not dataclass fields (e.g. ``width``)
+            if k not in cols:
+                setattr(out, k, v)
+        return out
     try:
         return type(batch)(cols)  # BatchEncoding / dict
     except Exception:
@@ -110,6 +114,9 @@ class MiniBatchIterator:
             )
             raise StopIteration
         cols = _columns(batch)
+        n_total = min((len(v) for v in cols.values() if v is not None), default=0)
+        if self.num_mb == 1 and 0 < n_total <= self.mb_size:
+            return [batch]  # nothing to slice: hand the loader's batch through untouched
         out = []
         for i in range(self.num_mb):
             lo, hi = i * self.mb_size, (i + 1) * self.mb_size
