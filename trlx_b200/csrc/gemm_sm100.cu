@@ -855,21 +855,32 @@ static int gemm_bf16_impl(const void* A, const void* B, void* out, int M, int N,
   return (int)e;
 }
 
-// Split-K plan: how many K-ranges a (M, N, K) problem should be cut into (1 = none).  Skinny outputs with a very long
-// contraction (dX of the LM head: [1280 x 768] with K = 50257) otherwise leave most SMs idle behind ~800 serial k-blocks.
-extern "C" int b200_gemm_splitk_plan(int M, int N, int K) {
+// Split-K plan for skinny outputs with a long contraction (dX of the LM head: [1280 x 768] with K = 50257).  Small tiles
+// would fill the SMs but are L2-bandwidth bound (a 128x64 tile moves 42 flop per byte); instead keep the widest tile and cut
+// K so that there are about two work items per SM.  Returns the number of splits (1 = none) and the tile width.
+static int splitk_plan(int M, int N, int K, int* bn_out) {
   int bn = pick_bn(M, N);
   if (bn < 64) bn = 64;
-  const long long tiles = (long long)((M + BM - 1) / BM) * ((N + bn - 1) / bn);
   const int nkb = (K + BK - 1) / BK;
-  if (tiles * 2 > num_sms() || nkb < 32) return 1;
-  long long s = num_sms() / tiles;              // about one work item per SM
-  if (s > nkb / 8) s = nkb / 8;                 // at least 8 k-blocks per item
-  if (s > 64) s = 64;
-  if (s < 2) return 1;
-  const int per = (nkb + (int)s - 1) / (int)s;  // no empty trailing split
-  return (nkb + per - 1) / per;
+  const int sms = num_sms();
+  const long long m_tiles = (M + BM - 1) / BM;
+  int splits = 1;
+  if (nkb >= 32 && m_tiles * ((N + bn - 1) / bn) < 2LL * sms) {
+    bn = N >= 256 ? 256 : (N >= 128 ? 128 : 64);
+    const long long tiles = m_tiles * ((N + bn - 1) / bn);
+    long long s = (2LL * sms + tiles - 1) / tiles;
+    if (s > nkb / 8) s = nkb / 8;  // at least 8 k-blocks per work item
+    if (s > 64) s = 64;
+    if (s >= 2) {
+      const int per = (nkb + (int)s - 1) / (int)s;  // no empty trailing split
+      splits = (nkb + per - 1) / per;
+    }
+    if (splits < 2) { splits = 1; bn = pick_bn(M, N) < 64 ? 64 : pick_bn(M, N); }
+  }
+  if (bn_out) *bn_out = bn;
+  return splits;
 }
+extern "C" int b200_gemm_splitk_plan(int M, int N, int K) { return splitk_plan(M, N, K, nullptr); }
 
 __global__ void splitk_finalize_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ out, long long rows, int N,
                                        long long ldo) {
@@ -894,6 +905,10 @@ extern "C" int b200_gemm_bf16_ex(const void* A, const void* B, void* out, int M,
     return b200_gemm_bf16(A, B, out, M, N, K, lda, ldb, ldo, nullptr, nullptr, 0, nullptr, 1.0f, ACT_NONE, out_f32, 0, stream);
   int bn = pick_bn(M, N);
   if (bn < 64) bn = 64;  // MN-major tiles are fetched in 64-element boxes
+  if (k_splits > 1 && ws != nullptr) {
+    int planned_bn = bn;
+    if (splitk_plan(M, N, K, &planned_bn) > 1) bn = planned_bn;  // split-K keeps wide tiles
+  }
   if (k_splits > 1) {  // normalise: every split must own at least one k-block
     const int nkb = (K + BK - 1) / BK;
     if (k_splits > nkb) k_splits = nkb;
@@ -901,7 +916,6 @@ extern "C" int b200_gemm_bf16_ex(const void* A, const void* B, void* out, int M,
     k_splits = (nkb + per - 1) / per;
   }
   const bool split = k_splits > 1 && ws != nullptr;
-  if (split && bn > 128) bn = 128;
   MapArray ma{};
   CUtensorMap mb;
   const bool ok_a = a_mn ? make_map(&ma.m[0], A, K, M, lda, 64, 64) : make_map(&ma.m[0], A, M, K, lda, BM);
@@ -929,6 +943,7 @@ extern "C" int b200_gemm_bf16_ex(const void* A, const void* B, void* out, int M,
                 : launch<BN_, EPI_, 0, 0>(ma, mb, mo, M, N, K, rpm, se, le, re, stream, k_splits))
   if (split) {
     switch (bn) {
+      case 256: e = B200_EX_LAUNCH(256, 2); break;
       case 128: e = B200_EX_LAUNCH(128, 2); break;
       default: e = B200_EX_LAUNCH(64, 2); break;
     }
