@@ -470,13 +470,17 @@ __device__ __forceinline__ void epilogue_cols(uint32_t taddr_row, int row, bool 
 // AMN / BMN: the operand is MN-major in global memory (A given as [K, M], B as [K, N], row-major) — the layouts the backward
 // GEMMs need (dX = dY · W reads W [N, K] as an MN-major B; dW = dYᵀ · X reads both operands MN-major), so no transposes are
 // ever materialised.  Such a tile is fetched as 64-column TMA boxes ([64 k rows] x [64 MN elements]) laid out chunk by chunk.
-template <int BN, int EPI, int AMN = 0, int BMN = 0>  // EPI: 0 = store, 1 = lm-head, 2 = reduce-scatter into peers
+// TBM: rows per tile, 128 or 64.  UMMA M = 64 keeps its accumulator in lanes 0-15 of each 32-lane TMEM quadrant
+// (row m -> lane (m % 16) + 32 * (m / 16)), so the epilogue warps use half of their lanes; it exists for the decode path,
+// where M = batch is a single 128-row tile and halving the A panel per CTA halves each CTA's (redundant) operand traffic.
+template <int BN, int EPI, int AMN = 0, int BMN = 0, int TBM = 128>  // EPI: 0 = store, 1 = lm-head, 2 = reduce-scatter
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ MapArray maps_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_out, int M, int N, int K, int stages, int rows_per_map,
                StoreEpilogue se, LMHeadEpilogue le, ReduceScatterEpilogue re, int k_splits) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  constexpr uint32_t A_BYTES = BM * BK * 2;
+  constexpr uint32_t A_BYTES = TBM * BK * 2;
+  static_assert(TBM == 128 || (TBM == 64 && !AMN), "64-row tiles: K-major A only");
   constexpr uint32_t B_BYTES = BN * BK * 2;
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t MN_CHUNK = BK * 64 * 2;          // one [64 k] x [64 MN] box of an MN-major operand (8 KB)
@@ -497,7 +501,7 @@ gemm_tn_kernel(const __grid_constant__ MapArray maps_a, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = (K + BK - 1) / BK;
-  const int m_tiles = (M + BM - 1) / BM;
+  const int m_tiles = (M + TBM - 1) / TBM;
   const int n_tiles = (N + BN - 1) / BN;
   const int total_tiles = m_tiles * n_tiles;
   // split-K (k_splits > 1, EPI 2 only): work item w = (split, tile) covers k-blocks [split*per, min(nkb, (split+1)*per)) and
@@ -538,7 +542,7 @@ gemm_tn_kernel(const __grid_constant__ MapArray maps_a, const __grid_constant__ 
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
         const int tile = w % total_tiles, split = w / total_tiles;
         const int kb_lo = split * kb_per, kb_hi = min(nkb, kb_lo + kb_per);
-        const int m0 = (tile % m_tiles) * BM, n0 = (tile / m_tiles) * BN;
+        const int m0 = (tile % m_tiles) * TBM, n0 = (tile / m_tiles) * BN;
         // which peer's copy of A holds this M-tile (all-gather -> GEMM); plain GEMMs have a single map
         const int a_map = m0 / rows_per_map;
         const int a_row = m0 - a_map * rows_per_map;
@@ -552,7 +556,7 @@ gemm_tn_kernel(const __grid_constant__ MapArray maps_a, const __grid_constant__ 
           mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
           if constexpr (AMN) {
 #pragma unroll
-            for (int ch = 0; ch < BM / 64; ++ch) tma_load_2d(a_dst + ch * MN_CHUNK, map_a_ptr, &full_bar[s], m0 + ch * 64, kb * BK);
+            for (int ch = 0; ch < TBM / 64; ++ch) tma_load_2d(a_dst + ch * MN_CHUNK, map_a_ptr, &full_bar[s], m0 + ch * 64, kb * BK);
           } else {
             tma_load_2d(a_dst, map_a_ptr, &full_bar[s], kb * BK, a_row);
           }
@@ -567,7 +571,7 @@ gemm_tn_kernel(const __grid_constant__ MapArray maps_a, const __grid_constant__ 
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc(1, 1, BM, BN, AMN, BMN);
+      constexpr uint32_t idesc = umma_idesc(1, 1, TBM, BN, AMN, BMN);
       uint32_t it = 0, tcount = 0;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tcount) {
         const int split = w / total_tiles;
@@ -608,13 +612,14 @@ gemm_tn_kernel(const __grid_constant__ MapArray maps_a, const __grid_constant__ 
       const int tile = w % total_tiles;
       const uint32_t as = tcount & 1, aphase = (tcount >> 1) & 1;
       const int m_idx = tile % m_tiles, n_idx = tile / m_tiles;
-      const int row = m_idx * BM + q * 32 + lane;
-      const bool row_ok = row < M;
+      constexpr int ROWS_PER_WARP = TBM / 4;  // 32, or 16 valid lanes per quadrant for 64-row tiles
+      const int row = m_idx * TBM + q * ROWS_PER_WARP + lane;
+      const bool row_ok = row < M && lane < ROWS_PER_WARP;
       mbar_wait(&tmem_full_bar[as], aphase);
       tc_fence_after_sync();
       const uint32_t taddr_row = tmem_base + as * ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
       epilogue_cols<EPI, CW>(taddr_row, row, row_ok, n_idx * BN, c_lo, c_hi, N, n_idx * 2 + half, se, le, re, stg, &map_out,
-                             m_idx * BM + q * 32, lane);
+                             m_idx * TBM + q * ROWS_PER_WARP, lane);
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
@@ -747,25 +752,25 @@ static int pick_bn(int M, int N) {
   return 32;
 }
 
-template <int BN, int EPI, int AMN = 0, int BMN = 0>
+template <int BN, int EPI, int AMN = 0, int BMN = 0, int TBM = 128>
 static cudaError_t launch(const MapArray& ma, const CUtensorMap& mb, const CUtensorMap& mo, int M, int N, int K,
                           int rows_per_map, const StoreEpilogue& se, const LMHeadEpilogue& le,
                           const ReduceScatterEpilogue& re, cudaStream_t stream, int k_splits = 1) {
-  constexpr int stage_bytes = BM * BK * 2 + BN * BK * 2;
+  constexpr int stage_bytes = TBM * BK * 2 + BN * BK * 2;
   constexpr int fixed_bytes = NUM_EPI_WARPS * STG_BYTES + 1024 /*alignment slack*/ + 512 /*barriers*/;
   const int nkb = (K + BK - 1) / BK;
   int stages = (227 * 1024 - fixed_bytes) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages > nkb) stages = nkb < 2 ? 2 : nkb;
   const size_t smem = (size_t)stages * stage_bytes + fixed_bytes;
-  auto kern = gemm_tn_kernel<BN, EPI, AMN, BMN>;
+  auto kern = gemm_tn_kernel<BN, EPI, AMN, BMN, TBM>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  const long long tiles = (long long)((N + BN - 1) / BN) * ((M + BM - 1) / BM) * k_splits;
+  const long long tiles = (long long)((N + BN - 1) / BN) * ((M + TBM - 1) / TBM) * k_splits;
   dim3 grid((unsigned)(tiles < num_sms() ? tiles : num_sms()));  // persistent: one CTA per SM walks the tile list
   return launch_kernel(kern, grid, dim3(NUM_THREADS), smem, stream, ma, mb, mo, M, N, K, stages, rows_per_map, se, le, re, k_splits);
 }
@@ -828,9 +833,14 @@ static int gemm_bf16_impl(const void* A, const void* B, void* out, int M, int N,
                           float alpha, int act, int out_f32, int force_bn, const LnFold& ln, cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   const int bn = force_bn ? force_bn : pick_bn(M, N);
+  // 64-row tiles when even 128x32 tiles leave more than half of the SMs idle (decode: M = batch <= 128)
+  static const bool allow_bm64 = getenv("B200_GEMM_NO_BM64") == nullptr;
+  const long long tiles128 = (long long)((M + 127) / 128) * ((N + bn - 1) / bn);
+  const long long tiles64 = (long long)((M + 63) / 64) * ((N + bn - 1) / bn);
+  const bool bm64 = allow_bm64 && bn <= 64 && M > 64 && tiles128 * 2 <= num_sms() && tiles64 <= num_sms() && force_bn >= 0;
   MapArray ma{};
   CUtensorMap mb;
-  if (!make_map(&ma.m[0], A, M, K, lda, BM) || !make_map(&mb, B, N, K, ldb, bn)) return -1;
+  if (!make_map(&ma.m[0], A, M, K, lda, bm64 ? 64 : BM) || !make_map(&mb, B, N, K, ldb, bn)) return -1;
   StoreEpilogue se{out, (const __nv_bfloat16*)bias, (const __nv_bfloat16*)residual, col_scale, ldo, ldr, alpha, act, out_f32};
   static const bool nostore = getenv("B200_GEMM_NOSTORE") != nullptr;
   se.debug_nostore = nostore ? 1 : 0;
@@ -841,11 +851,17 @@ static int gemm_bf16_impl(const void* A, const void* B, void* out, int M, int N,
   se.ln_rms = ln.rms;
   se.stats_out = ln.stats_out;
   CUtensorMap mo{};
-  if (!setup_tma_store(se, &mo, M, N, bn)) return -1;
+  if (bm64) se.tma_store = 0;  // 64-row tiles keep 16 rows per epilogue warp: direct stores
+  else if (!setup_tma_store(se, &mo, M, N, bn)) return -1;
   LMHeadEpilogue le{};
   ReduceScatterEpilogue re{};
   const int rpm = 1 << 30;
   cudaError_t e;
+  if (bm64) {
+    if (bn == 64) e = launch<64, 0, 0, 0, 64>(ma, mb, mo, M, N, K, rpm, se, le, re, stream);
+    else e = launch<32, 0, 0, 0, 64>(ma, mb, mo, M, N, K, rpm, se, le, re, stream);
+    return (int)e;
+  }
   switch (bn) {
     case 256: e = launch<256, 0>(ma, mb, mo, M, N, K, rpm, se, le, re, stream); break;
     case 128: e = launch<128, 0>(ma, mb, mo, M, N, K, rpm, se, le, re, stream); break;
