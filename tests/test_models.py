@@ -267,3 +267,24 @@ def test_beam_search_seq2seq_runs_and_pads_after_eos():
     for row in out.tolist():
         if 1 in row:
             assert all(t == 0 for t in row[row.index(1) + 1:])
+
+
+def test_activation_checkpointing_matches_plain_backward():
+    from trlx_b200.nn.arch import spec_from_hf_config
+    from trlx_b200.nn.transformer import CausalLM
+
+    torch.manual_seed(0)
+    spec = spec_from_hf_config(dict(model_type="llama", vocab_size=40, hidden_size=32, num_hidden_layers=3, num_attention_heads=4,
+                                    num_key_value_heads=2, intermediate_size=64, max_position_embeddings=32))
+    m = CausalLM(spec)
+    ids = torch.randint(0, 40, (2, 9))
+    mask = torch.ones_like(ids)
+    mask[0, :3] = 0
+    m(input_ids=ids, attention_mask=mask, labels=ids).loss.backward()
+    ref = {n: p.grad.clone() for n, p in m.named_parameters()}
+    m.zero_grad()
+    m.gradient_checkpointing_enable()
+    out = m(input_ids=ids, attention_mask=mask, labels=ids)
+    out.loss.backward()
+    for n, p in m.named_parameters():
+        torch.testing.assert_close(p.grad, ref[n], atol=1e-6, rtol=1e-5)

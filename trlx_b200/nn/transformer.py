@@ -281,6 +281,14 @@ class CausalLM(nn.Module):
             elif isinstance(m, nn.Embedding):
                 nn.init.normal_(m.weight, mean=0.0, std=std)
 
+    gradient_checkpointing = False
+
+    def gradient_checkpointing_enable(self, *_, **__):
+        self.gradient_checkpointing = True
+
+    def gradient_checkpointing_disable(self):
+        self.gradient_checkpointing = False
+
     # -- HF-ish accessors --------------------------------------------------------------------------------
     def get_input_embeddings(self):
         return self.transformer.wte
@@ -340,11 +348,19 @@ class CausalLM(nn.Module):
         stop = len(trunk.h) if stop_layer is None else stop_layer
         hiddens = [] if output_hidden_states else None
         presents = [] if use_cache else None
+        recompute = self.gradient_checkpointing and torch.is_grad_enabled() and not use_cache
         for i in range(start_layer, stop):
             if hiddens is not None:
                 hiddens.append(x)
             past = past_key_values[i - start_layer] if past_key_values else None
-            x, present = trunk.h[i](x, ctx, past, use_cache)
+            if recompute and x.requires_grad:
+                # activation checkpointing (reference: NeMo `activations_checkpoint_granularity`, megatron_20b.yaml:77):
+                # keep only the block input, recompute the block in backward
+                from torch.utils.checkpoint import checkpoint
+
+                x, present = checkpoint(trunk.h[i], x, ctx, None, False, use_reentrant=False)
+            else:
+                x, present = trunk.h[i](x, ctx, past, use_cache)
             if presents is not None:
                 presents.append(present)
         final = stop == len(trunk.h)

@@ -92,10 +92,13 @@ class FusedAdamW(Optimizer):
     decoupled = True
 
     def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2,
-                 grad_clip: Optional[float] = None, process_group=None, **unused):
+                 grad_clip: Optional[float] = None, process_group=None, zero_stage: int = 2, **unused):
         defaults = dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay)
         super().__init__(params, defaults)
         self.grad_clip = grad_clip
+        # zero_stage >= 1: optimizer state + gradient reduction sharded (fused RS + AdamW + AG over NVLink peer memory);
+        # zero_stage == 0: DDP semantics — NCCL all-reduce of the flat gradient, replicated update
+        self.zero_stage = int(zero_stage)
         self.process_group = process_group
         self._step_count_fused = 0
         self._flat: Optional[List[Optional[_FlatGroup]]] = None
@@ -132,7 +135,11 @@ class FusedAdamW(Optimizer):
             if not ps:
                 self._flat.append(None)
                 continue
-            symmetric = world > 1
+            symmetric = world > 1 and self.zero_stage >= 1
+            if world > 1 and not symmetric:
+                self._flat.append(_FlatGroup(ps, 1, 0, None, False))
+                self._flat[-1].needs_allreduce = True
+                continue
             try:
                 self._flat.append(_FlatGroup(ps, world, rank, self.process_group, symmetric))
             except Exception as err:  # symmetric memory unavailable → replicated update after an NCCL all-reduce

@@ -149,6 +149,10 @@ class AccelerateRLTrainer(BaseRLTrainer):
         if self.runtime.cuda and self.runtime.dtype != torch.float32:
             model = model.to(self.runtime.dtype)
         self._sync_initial_weights(model)
+        if getattr(self.config.train.parallel, "activation_checkpointing", False):
+            for m in model.modules():
+                if hasattr(m, "gradient_checkpointing_enable") and m is not model:
+                    m.gradient_checkpointing_enable()
         model.eval()
         return model
 
@@ -173,6 +177,7 @@ class AccelerateRLTrainer(BaseRLTrainer):
         if issubclass(optimizer_class, FusedAdamW):
             kwargs.setdefault("grad_clip", self.config.train.parallel.grad_clip)
             kwargs.setdefault("process_group", self.runtime.dp_group)
+            kwargs.setdefault("zero_stage", self.config.train.parallel.zero_stage)
         params = [p for p in self.model.parameters() if p.requires_grad]
         opt = optimizer_class(params, **kwargs)
         if hasattr(opt, "prepare"):

@@ -48,6 +48,10 @@ def train(  # noqa: C901
         else:
             config = default_sft_config()
 
+    if os.environ.get("TRLX_B200_PARALLEL"):  # launch preset (python -m trlx_b200.launch --config_file …)
+        import json
+
+        config = config.evolve(train=dict(parallel=json.loads(os.environ["TRLX_B200_PARALLEL"])))
     set_seed(config.train.seed, config.train.parallel)
 
     if dataset:
