@@ -374,6 +374,12 @@ class AcceleratePPOTrainer(AccelerateRLTrainer):
                 ids, am = batch["input_ids"], batch["attention_mask"]
                 bucket = int(self.config.train.trainer_kwargs.get("prompt_bucket", 16))
                 width = -(-ids.shape[1] // bucket) * bucket
+                if rt.distributed and rt.dp_size > 1:
+                    # every data-parallel rank uses the same padded prompt width, so their rollout blocks — and therefore
+                    # the CUDA-graph shape keys of the training step, whose capture runs cross-GPU barriers — line up
+                    wt = torch.tensor([width], device=device, dtype=torch.int64)
+                    rt.all_reduce(wt, "max", group=rt.dp_group)
+                    width = int(wt.item())
                 if width != ids.shape[1] and self.tokenizer.padding_side == "left":
                     # bucket the (left-padded) prompt width so decode / train-step CUDA graphs see few distinct shapes
                     ids = F.pad(ids, (width - ids.shape[1], 0), value=pad)
