@@ -119,6 +119,19 @@ def test_gemm_with_folded_norm_and_row_moments(C, rms):
     torch.testing.assert_close(st0[:, 1], e.float().pow(2).sum(1), atol=0.1, rtol=1e-3)
 
 
+@pytest.mark.parametrize("M,N,K", [(512, 512, 256), (2048, 4096, 512), (1000, 1304, 192), (4096, 4096, 4096)])
+def test_gemm_cta_pair(C, M, N, K):
+    """cta_group::2: a cluster of two CTAs computes 256 x 256 tiles with one UMMA (M = 256) issued by the leader."""
+    torch.manual_seed(M + K)
+    x = (torch.randn(M, K, device="cuda") * 0.5).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda") * 0.5).to(torch.bfloat16)
+    b = (torch.randn(N, device="cuda")).to(torch.bfloat16)
+    y = C.gemm(x, w, b, None, "none", force_bn=-2)
+    ref = x.float() @ w.float().t() + b.float()
+    err = (y.float() - ref).abs().max().item()
+    assert err <= 2e-2 * ref.abs().max().item(), err
+
+
 def test_lmhead_dlogits(C):
     torch.manual_seed(5)
     M, V, K = 300, 50257, 256

@@ -60,3 +60,28 @@ def test_metric_readback_and_report(tmp_path):
     assert runs["trial"]["reward/mean"][-1] == (2, 0.4)
     md = reference.compare(runs, {"trial": {"reward/mean": [(0, 0.2)]}}, "pr", "base")
     assert "| reward/mean | 0.4 | 0.2 | +0.2 |" in md
+
+
+def test_launcher_dry_run_exports_parallel_preset(capsys):
+    from trlx_b200 import launch
+
+    rc = launch.main(["--config_file", "configs/accelerate/zero2-bf16.yaml", "--num_processes", "2", "--dry_run",
+                      "examples/ppo_sentiments.py", '{"train.total_steps": 2}'])
+    out = capsys.readouterr().out
+    assert rc == 0 and "--nproc-per-node=2" in out and "--master-addr 127.0.0.1" in out
+    assert '"zero_stage": 2' in out and '"grad_clip": 1.0' in out
+
+
+def test_parallel_preset_env_overrides_config(monkeypatch, tmp_path):
+    import trlx_b200 as trlx
+    from trlx_b200.data.default_configs import default_sft_config
+
+    monkeypatch.setenv("TRLX_B200_PARALLEL", json.dumps({"zero_stage": 0, "grad_clip": 0.5}))
+    cfg = default_sft_config().evolve(
+        train=dict(total_steps=1, batch_size=2, seq_length=16, tracker=None, checkpoint_interval=100, eval_interval=100,
+                   checkpoint_dir=str(tmp_path)),
+        model=dict(model_path=dict(model_type="gpt2", vocab_size=257, n_embd=16, n_layer=1, n_head=2, n_positions=32, eos_token_id=256,
+                                   bos_token_id=256)),
+        tokenizer=dict(tokenizer_path="toy://bytes"), method=dict(gen_kwargs=dict(max_new_tokens=2)))
+    trainer = trlx.train(samples=["ab", "cd", "ef", "gh"], eval_prompts=["a"], config=cfg)
+    assert trainer.config.train.parallel.zero_stage == 0 and trainer.config.train.parallel.grad_clip == 0.5

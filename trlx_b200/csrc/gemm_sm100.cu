@@ -634,6 +634,154 @@ gemm_tn_kernel(const __grid_constant__ MapArray maps_a, const __grid_constant__ 
   }
 }
 
+// ---------------------------------------------------------------------------------------------- CTA-pair GEMM
+// 256 x BN output tiles computed by a CLUSTER OF TWO CTAs with tcgen05.mma.cta_group::2 (UMMA M = 256).  CTA r of the pair
+// stages rows [128 r, 128 r + 128) of the A tile and rows [BN/2 r, BN/2 r + BN/2) of the B tile; the leader's single MMA
+// thread multiplies the full 256 x BN x 64 block from both CTAs' shared memory, each CTA's TMEM receives its own 128 rows.
+// Per SM and k-block that is 16 KB of A + 16 KB of B for 128 x 256 x 64 MACs: 128 flop per byte from L2 instead of the 85
+// of the single-CTA 128 x 256 tile — the large-GEMM regime of this part is bound by exactly that L2 -> SMEM path.
+//
+// Barriers (offsets identical in both CTAs):
+//   full[s]        leader only — expect_tx(2 x stage bytes); both CTAs' TMA loads complete_tx on it (peer-bit-cleared address)
+//   empty[s]       one per CTA  — armed by the leader's tcgen05.commit ... multicast::cluster (mask 0b11)
+//   tmem_full[a]   one per CTA  — same multicast commit after the last k-block of a tile
+//   tmem_empty[a]  leader only — 2 x NUM_EPI_WARPS arrivals (the peer's epilogue warps arrive remotely via mapa)
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const __grid_constant__ CUtensorMap map_out, int M, int N, int K, int stages, StoreEpilogue se) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr int HB = BN / 2;                          // B rows staged by each CTA
+  constexpr uint32_t A_BYTES = BM * BK * 2;
+  constexpr uint32_t B_BYTES = HB * BK * 2;
+  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t ACC_COLS = BN;
+  constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;        // double-buffered accumulator
+  constexpr int HALF = BN / 2;
+  constexpr int CW = HALF < 64 ? HALF : 64;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stage_out = smem + (size_t)stages * STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_out + NUM_EPI_WARPS * STG_BYTES);
+  uint64_t* empty_bar = full_bar + stages;
+  uint64_t* tmem_full_bar = empty_bar + stages;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta = cluster_ctarank();
+  const bool leader = cta == 0;
+  const int nkb = (K + BK - 1) / BK;
+  const int m_tiles = (M + 2 * BM - 1) / (2 * BM);   // 256-row tiles
+  const int n_tiles = (N + BN - 1) / BN;
+  const int total_tiles = m_tiles * n_tiles;
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    if (se.tma_store) tma_prefetch_desc(&map_out);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 2 * NUM_EPI_WARPS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2sm(tmem_slot, TMEM_COLS);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();  // the peer's barriers exist before anything remote targets them
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();
+  griddep_launch();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+        const int m0 = (tile % m_tiles) * 2 * BM + (int)cta * BM;  // this CTA's 128 rows of A
+        const int n0 = (tile / m_tiles) * BN + (int)cta * HB;      // ... and its half of the B tile
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % stages;
+          const uint32_t phase = (it / stages) & 1;
+          mbar_wait(&empty_bar[s], phase ^ 1);
+          uint8_t* a_dst = smem + (size_t)s * STAGE_BYTES;
+          if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
+          tma_load_2d_2sm(a_dst, &map_a, &full_bar[s], kb * BK, m0);
+          tma_load_2d_2sm(a_dst + A_BYTES, &map_b, &full_bar[s], kb * BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc(1, 1, 2 * BM, BN);
+      uint32_t it = 0, tcount = 0;
+      for (int tile = pair; tile < total_tiles; tile += n_pairs, ++tcount) {
+        const uint32_t as = tcount & 1, aphase = (tcount >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[as], aphase ^ 1);  // both CTAs' epilogues drained this accumulator buffer
+        tc_fence_after_sync();
+        const uint32_t tmem_acc = tmem_base + as * ACC_COLS;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % stages;
+          const uint32_t phase = (it / stages) & 1;
+          mbar_wait(&full_bar[s], phase);
+          tc_fence_after_sync();
+          const uint32_t a_addr = smem_u32(smem + (size_t)s * STAGE_BYTES);
+          const uint64_t da = umma_desc_k_sw128(a_addr);
+          const uint64_t db = umma_desc_k_sw128(a_addr + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            umma_bf16_2sm(tmem_acc, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_2sm(&empty_bar[s], 0b11);      // frees slot s in BOTH CTAs
+        }
+        umma_commit_2sm(&tmem_full_bar[as], 0b11);   // both epilogues may read their half
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int c_lo = half * HALF, c_hi = c_lo + HALF;
+    uint8_t* stg = stage_out + (size_t)(warp - 2) * STG_BYTES;
+    LMHeadEpilogue le{};
+    ReduceScatterEpilogue re{};
+    // the leader's tmem_empty barrier, as seen from this CTA
+    const uint32_t empty_remote0 = mapa_shared(smem_u32(&tmem_empty_bar[0]), 0);
+    const uint32_t empty_remote1 = mapa_shared(smem_u32(&tmem_empty_bar[1]), 0);
+    uint32_t tcount = 0;
+    for (int tile = pair; tile < total_tiles; tile += n_pairs, ++tcount) {
+      const uint32_t as = tcount & 1, aphase = (tcount >> 1) & 1;
+      const int m_idx = tile % m_tiles, n_idx = tile / m_tiles;
+      const int row0 = m_idx * 2 * BM + (int)cta * BM + q * 32;
+      const int row = row0 + lane;
+      const bool row_ok = row < M;
+      mbar_wait(&tmem_full_bar[as], aphase);
+      tc_fence_after_sync();
+      const uint32_t taddr_row = tmem_base + as * ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
+      epilogue_cols<0, CW>(taddr_row, row, row_ok, n_idx * BN, c_lo, c_hi, N, 0, se, le, re, stg, &map_out, row0, lane);
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(as ? empty_remote1 : empty_remote0);
+    }
+    if (se.tma_store && lane == 0) tma_store_wait_all();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();  // nobody frees TMEM / shared memory the other CTA may still touch
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+  }
+}
+
 // Merge the per-tile partials of the LM-head epilogue.  One warp per row.
 __global__ void lmhead_reduce_kernel(const float* __restrict__ part_max, const float* __restrict__ part_sum,
                                      const float* __restrict__ label_logit, const long long* __restrict__ labels,
@@ -832,12 +980,44 @@ static int gemm_bf16_impl(const void* A, const void* B, void* out, int M, int N,
                           long long ldo, const void* bias, const void* residual, long long ldr, const float* col_scale,
                           float alpha, int act, int out_f32, int force_bn, const LnFold& ln, cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
-  const int bn = force_bn ? force_bn : pick_bn(M, N);
+  const int bn = force_bn > 0 ? force_bn : pick_bn(M, N);
+  // CTA-pair kernel for the large-GEMM regime: plenty of 256x256 tiles and nothing but a plain bf16 store epilogue
+  static const bool allow_2cta = getenv("B200_GEMM_2CTA") != nullptr;  // opt-in until validated on every shape class
+  {
+    const long long t2 = (long long)((M + 255) / 256) * ((N + 255) / 256);
+    const bool force2 = force_bn == -2;
+    if ((allow_2cta || force2) && (force_bn == 0 || force2) && !out_f32 && !col_scale && !ln.stats_in && !ln.stats_out &&
+        (ldo % 8) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (force2 || (t2 * 2 >= num_sms() && K >= 512))) {
+      CUtensorMap m2a, m2b, m2o{};
+      if (!make_map(&m2a, A, M, K, lda, BM) || !make_map(&m2b, B, N, K, ldb, 128)) return -1;
+      StoreEpilogue s2{out, (const __nv_bfloat16*)bias, (const __nv_bfloat16*)residual, nullptr, ldo, ldr, alpha, act, 0};
+      if (!setup_tma_store(s2, &m2o, M, N, 256)) return -1;
+      constexpr int BN2 = 256;
+      constexpr int stage_bytes = BM * BK * 2 + (BN2 / 2) * BK * 2;
+      constexpr int fixed_bytes = NUM_EPI_WARPS * STG_BYTES + 1024 + 512;
+      int stages = (227 * 1024 - fixed_bytes) / stage_bytes;
+      if (stages > 8) stages = 8;
+      const int nkb2 = (K + BK - 1) / BK;
+      if (stages > nkb2) stages = nkb2 < 2 ? 2 : nkb2;
+      auto kern = gemm_2cta_kernel<BN2>;
+      static bool configured = false;
+      if (!configured) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -5;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 0) != cudaSuccess) cudaGetLastError();
+        configured = true;
+      }
+      long long pairs = t2 < num_sms() / 2 ? t2 : num_sms() / 2;
+      dim3 grid((unsigned)(2 * pairs));
+      const size_t smem = (size_t)stages * stage_bytes + fixed_bytes;
+      return (int)launch_kernel_cluster(kern, grid, dim3(NUM_THREADS), smem, stream, 2u, m2a, m2b, m2o, M, N, K, stages, s2);
+    }
+  }
   // 64-row tiles when even 128x32 tiles leave more than half of the SMs idle (decode: M = batch <= 128)
   static const bool allow_bm64 = getenv("B200_GEMM_NO_BM64") == nullptr;
   const long long tiles128 = (long long)((M + 127) / 128) * ((N + bn - 1) / bn);
   const long long tiles64 = (long long)((M + 63) / 64) * ((N + bn - 1) / bn);
   const bool bm64 = allow_bm64 && bn <= 64 && M > 64 && tiles128 * 2 <= num_sms() && tiles64 <= num_sms() && force_bn >= 0;
+  if (force_bn < 0) return -6;  // an explicitly requested CTA-pair launch was not possible
   MapArray ma{};
   CUtensorMap mb;
   if (!make_map(&ma.m[0], A, M, K, lda, bm64 ? 64 : BM) || !make_map(&mb, B, N, K, ldb, bn)) return -1;
