@@ -309,10 +309,22 @@ def main():
             if os.environ.get("BENCH_PROFILE_TRACE"):
                 prof.export_chrome_trace(f"gpurun_out/trace_{phase}{suffix}.json")
     if rank == 0:
-        print(json.dumps(out))
-    if dist.is_initialized():
-        dist.barrier()
-        dist.destroy_process_group()
+        print(json.dumps(out), flush=True)
+    # Teardown order matters with captured CUDA graphs that reference NVLink symmetric memory: drop the graphs first, drain
+    # the device, then leave the process group.  The interpreter is exited directly afterwards — the measurement is done and
+    # NCCL/symmetric-memory destructors racing at interpreter shutdown have hung multi-rank runs (run20).
+    try:
+        getattr(trainer, "_graphed_steps", {}).clear()
+        if getattr(trainer, "_engine", None) is not None:
+            trainer._engine._state = None
+        torch.cuda.synchronize()
+        if dist.is_initialized():
+            dist.barrier()
+    finally:
+        sys.stdout.flush()
+        sys.stderr.flush()
+        if dist.is_initialized() and world > 1:
+            os._exit(0)
     return 0
 
 

@@ -311,6 +311,17 @@ class AccelerateRLTrainer(BaseRLTrainer):
         self._after_weights_changed()
         self.runtime.barrier()
 
+    def release_device_state(self):
+        """Drop captured CUDA graphs / engine state (they hold NVLink symmetric-memory references; destroying them while the
+        process group is being torn down at interpreter exit has deadlocked multi-rank runs)."""
+        if getattr(self, "_graphed_steps", None):
+            self._graphed_steps.clear()
+        eng = getattr(self, "_engine", None)
+        if eng is not None:
+            eng._state = None
+        if self.runtime.cuda:
+            torch.cuda.synchronize()
+
     def _pre_optimizer_step(self):
         """Hook between the last backward and ``opt.step()`` (tensor-parallel gradient fix-ups live here)."""
 

@@ -91,4 +91,6 @@ def train(  # noqa: C901
         trainer.load(config.train.resume_from_checkpoint)
 
     trainer.learn()
+    if hasattr(trainer, "release_device_state"):
+        trainer.release_device_state()  # captured CUDA graphs must not outlive the process group they reference
     return trainer
