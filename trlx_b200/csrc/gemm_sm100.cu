@@ -1013,7 +1013,7 @@ static int gemm_bf16_impl(const void* A, const void* B, void* out, int M, int N,
     }
   }
   // 64-row tiles when even 128x32 tiles leave more than half of the SMs idle (decode: M = batch <= 128)
-  static const bool allow_bm64 = getenv("B200_GEMM_NO_BM64") == nullptr;
+  static const bool allow_bm64 = getenv("B200_GEMM_BM64") != nullptr;  // opt-in: measured neutral on the decode path (run21)
   const long long tiles128 = (long long)((M + 127) / 128) * ((N + bn - 1) / bn);
   const long long tiles64 = (long long)((M + 63) / 64) * ((N + bn - 1) / bn);
   const bool bm64 = allow_bm64 && bn <= 64 && M > 64 && tiles128 * 2 <= num_sms() && tiles64 <= num_sms() && force_bn >= 0;

@@ -143,10 +143,12 @@ class RolloutEngine:
         self.launches_per_step = 0
         import os
 
-        # LayerNorm folding (decode): the two norm kernels of every block disappear — their effect is applied in the
+        # LayerNorm folding (decode, opt-in: TRLX_B200_FOLD_NORMS=1 — measured neutral once PDL overlaps the norm kernels,
+        # run18, and the plain path keeps rollout numerics closest to the training forward): the two norm kernels of every
+        # block disappear — their effect is applied in the
         # epilogue of the GEMM that consumes them, from row moments accumulated by the GEMM (or embed) that produced x.
         folded_bytes = sum((W.qkv_w.numel() + W.up_w.numel()) * 2 for W in self.layers + self.ref_layers)
-        self.fold_norms = (os.environ.get("TRLX_B200_FOLD_NORMS", "1") == "1" and self.lm.transformer.emb_norm is None
+        self.fold_norms = (os.environ.get("TRLX_B200_FOLD_NORMS", "0") == "1" and self.lm.transformer.emb_norm is None
                            and spec.hidden_size % 16 == 0 and all(W.qkv_w.shape[0] % 16 == 0 and W.up_w.shape[0] % 16 == 0
                                                                   for W in self.layers + self.ref_layers)
                            and folded_bytes <= int(os.environ.get("TRLX_B200_FOLD_BUDGET_MB", "4096")) << 20)
