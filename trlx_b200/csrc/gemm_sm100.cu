@@ -889,15 +889,22 @@ static int num_sms() {
 }
 
 static int pick_bn(int M, int N) {
+  // Operand-traffic model: every SM streams (BM + BN) rows per k-block for each of its tiles, and the L2 -> SMEM path is
+  // the limiter, so time ~ rounds x (BM + BN) with rounds = ceil(tiles / SMs).  Pick the width that minimises it (ties go
+  // to the wider tile: fewer, fatter MMAs and less epilogue per flop).  E.g. 1792 x 768: 128-wide gives 84 tiles in one
+  // round (cost 256) where 64-wide needs two rounds of 168 tiles (cost 384).
   const long long m_tiles = (M + BM - 1) / BM;
   const int sms = num_sms();
-  // 128x256 tiles halve the L2->SMEM traffic per flop; worth it once there are a few waves of them
-  if (m_tiles * ((N + 255) / 256) >= 3LL * sms) return 256;
-  // otherwise the widest tile that still gives every SM a tile
-  for (int bn : {128, 64, 32}) {
-    if (m_tiles * ((N + bn - 1) / bn) >= sms) return bn;
+  int best = 32;
+  long long best_cost = -1;
+  for (int bn : {256, 128, 64, 32}) {
+    if (bn > 32 && bn / 2 >= N) continue;  // do not pad a narrow output into a much wider tile
+    const long long tiles = m_tiles * ((N + bn - 1) / bn);
+    const long long rounds = (tiles + sms - 1) / sms;
+    const long long cost = rounds * (BM + bn);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
   }
-  return 32;
+  return best;
 }
 
 template <int BN, int EPI, int AMN = 0, int BMN = 0, int TBM = 128>
