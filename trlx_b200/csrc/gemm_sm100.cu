@@ -989,12 +989,12 @@ static int gemm_bf16_impl(const void* A, const void* B, void* out, int M, int N,
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   const int bn = force_bn > 0 ? force_bn : pick_bn(M, N);
   // CTA-pair kernel for the large-GEMM regime: plenty of 256x256 tiles and nothing but a plain bf16 store epilogue
-  static const bool allow_2cta = getenv("B200_GEMM_2CTA") != nullptr;  // opt-in until validated on every shape class
+  static const bool allow_2cta = getenv("B200_GEMM_NO_2CTA") == nullptr;
   {
     const long long t2 = (long long)((M + 255) / 256) * ((N + 255) / 256);
     const bool force2 = force_bn == -2;
     if ((allow_2cta || force2) && (force_bn == 0 || force2) && !out_f32 && !col_scale && !ln.stats_in && !ln.stats_out &&
-        (ldo % 8) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (force2 || (t2 * 2 >= num_sms() && K >= 512))) {
+        (ldo % 8) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (force2 || getenv("B200_GEMM_2CTA") != nullptr || (t2 >= num_sms() && K >= 1024))) {  // measured: +6 % at K >= 4096, neutral at K = 768 (run22)
       CUtensorMap m2a, m2b, m2o{};
       if (!make_map(&m2a, A, M, K, lda, BM) || !make_map(&m2b, B, N, K, ldb, 128)) return -1;
       StoreEpilogue s2{out, (const __nv_bfloat16*)bias, (const __nv_bfloat16*)residual, nullptr, ldo, ldr, alpha, act, 0};
