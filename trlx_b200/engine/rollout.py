@@ -410,6 +410,40 @@ class RolloutEngine:
         vals = torch.zeros(B, T, device=dev)
         return lp.float(), ref_lp.float(), vals, trunk
 
+    def _prefill_maybe_graphed(self, st, prompt, mask):
+        """The prefill is ~200 small launches for short prompts (CPU-bound when issued eagerly): capture it once per
+        (batch, prompt width) and replay it from static input buffers."""
+        import os
+
+        if not self.use_cuda_graph or os.environ.get("TRLX_B200_PREFILL_GRAPH", "1") != "1" or st.get("prefill_failed") \
+                or prompt.shape[1] < 2:
+            return self._prefill(st, prompt, mask)
+        if st.get("prefill_graph") is None:
+            try:
+                st["pf_prompt"], st["pf_mask"] = prompt.clone(), mask.clone()
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                before = ops.launch_count()
+                with torch.cuda.stream(side):
+                    self._prefill(st, st["pf_prompt"], st["pf_mask"])
+                st["prefill_launches"] = ops.launch_count() - before
+                torch.cuda.current_stream().wait_stream(side)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    outs = self._prefill(st, st["pf_prompt"], st["pf_mask"])
+                st["prefill_graph"], st["prefill_outs"] = graph, outs
+            except Exception as err:  # keep the eager path if anything in the prefill is not capturable
+                logger.warning(f"prefill CUDA graph disabled ({type(err).__name__}: {err})")
+                st["prefill_failed"] = True
+                torch.cuda.synchronize()
+                return self._prefill(st, prompt, mask)
+        st["pf_prompt"].copy_(prompt, non_blocking=True)
+        st["pf_mask"].copy_(mask, non_blocking=True)
+        st["prefill_graph"].replay()
+        ops.add_launches(st["prefill_launches"])
+        lp, ref_lp, vals, trunk = st["prefill_outs"]
+        return lp, ref_lp, vals, trunk  # static buffers: every consumer below copies (cat / index) before the next replay
+
     # ------------------------------------------------------------------------------------------------ public API
     @torch.no_grad()
     def rollout(self, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor] = None) -> Dict[str, Any]:
@@ -430,7 +464,7 @@ class RolloutEngine:
         st["seed_dev"].fill_((self.calls * 0x9E3779B1) & 0x7FFFFFFFFFFF)
         st["min_new"] = max(int(g.get("min_new_tokens") or 0), int(g.get("min_length") or 0) - Q, 0)
 
-        lp_p, ref_lp_p, val_p, trunk_p = self._prefill(st, prompt, mask)
+        lp_p, ref_lp_p, val_p, trunk_p = self._prefill_maybe_graphed(st, prompt, mask)
 
         if self.use_cuda_graph:
             if st["graph"] is None or st.get("graph_key_min_new") != st["min_new"]:
