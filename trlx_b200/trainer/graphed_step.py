@@ -98,5 +98,6 @@ class GraphedPPOStep:
         self._load(batch, width)
         self.trainer.opt.host_prepare()
         self.graph.replay()
+        self.trainer.opt._opt_called = True  # the step ran inside the graph: keep torch's scheduler-order check quiet
         ops.add_launches(self.launches)
         return dict(self.stats)
