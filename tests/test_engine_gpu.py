@@ -107,3 +107,26 @@ def test_ppo_trainer_runs_on_engine(tmp_path):
                          prompts=["hello world", "the quick", "a", "brown fox jumps"] * 4, eval_prompts=["hi"] * 2, config=cfg)
     assert trainer._engine is not None, "the CUDA rollout engine must be the path that ran"
     assert trainer.iter_count == 4
+
+
+def test_fp8_rollout_stays_close_to_bf16(monkeypatch):
+    """rollout_dtype = fp8: teacher-forced log-probs of the fp8 engine's own samples, re-scored by the bf16 torch model, stay
+    within quantisation noise of what the engine reported."""
+    from trlx_b200.engine.rollout import RolloutEngine
+
+    m = _model("gpt2")
+    gen = dict(max_new_tokens=8, do_sample=False, eos_token_id=999, pad_token_id=999, top_k=0, top_p=1.0, _rollout_dtype="fp8")
+    eng = RolloutEngine(m, 999, 999, gen, seed=0)
+    assert eng.fp8
+    torch.manual_seed(1)
+    prompts = torch.randint(0, 990, (16, 7), device="cuda")
+    ro = eng.rollout(prompts, torch.ones_like(prompts))
+    tokens, mask = ro["samples"], ro["mask"]
+    pos = (mask.cumsum(-1) - 1).clamp_min(0)
+    with torch.no_grad():
+        out = m(tokens, attention_mask=mask, position_ids=pos, return_dict=True)
+    lp = torch.log_softmax(out.logits[:, :-1].float(), -1).gather(-1, tokens[:, 1:, None]).squeeze(-1)
+    start = ro["start"]
+    valid = mask[:, start + 1:].bool()
+    diff = (lp[:, start:] - ro["logprobs"][:, start:])[valid].abs()
+    assert diff.mean().item() < 0.15 and torch.isfinite(ro["values"]).all()

@@ -132,6 +132,32 @@ def test_gemm_cta_pair(C, M, N, K):
     assert err <= 2e-2 * ref.abs().max().item(), err
 
 
+@pytest.mark.parametrize("M,N,K", [(128, 2304, 768), (300, 1000 // 16 * 16, 256), (2048, 4096, 1024)])
+def test_gemm_fp8_with_row_and_channel_scales(C, M, N, K):
+    """e4m3 x e4m3 on the tensor cores (kind::f8f6f4): exact against the dequantised operands, close to the bf16 product."""
+    import torch.nn.functional as F
+
+    torch.manual_seed(K)
+    x = (torch.randn(M, K, device="cuda") * 2 + 0.5).to(torch.bfloat16)
+    g = (1 + 0.1 * torch.randn(K, device="cuda")).to(torch.bfloat16)
+    bt = (0.1 * torch.randn(K, device="cuda")).to(torch.bfloat16)
+    W = (torch.randn(N, K, device="cuda") * K ** -0.5).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda").to(torch.bfloat16)
+    a8, a_s = C.norm_quant(x, g, bt, 1e-5, False)
+    h = F.layer_norm(x.float(), (K,), g.float(), bt.float(), 1e-5)
+    a_deq = a8.view(torch.float8_e4m3fn).float() * a_s[:, None]
+    assert (a_deq - h).abs().max().item() <= 0.07 * h.abs().max().item()  # e4m3: 3 mantissa bits
+    w_s = (W.float().abs().amax(1) / 448.0).contiguous()
+    w8 = (W.float() / w_s[:, None]).to(torch.float8_e4m3fn)
+    w_deq = w8.float() * w_s[:, None]
+    y = C.gemm_fp8(a8, w8.view(torch.uint8), a_s, w_s, bias, None, "none")
+    exact = a_deq @ w_deq.t() + bias.float()
+    assert (y.float() - exact).abs().max().item() <= 1e-2 * exact.abs().max().item() + 1e-2
+    full = h @ W.float().t() + bias.float()
+    rel = (y.float() - full).norm() / full.norm()
+    assert rel.item() < 0.06, rel.item()
+
+
 def test_lmhead_dlogits(C):
     torch.manual_seed(5)
     M, V, K = 300, 50257, 256

@@ -32,6 +32,10 @@ int b200_decode_step(const long long*, const float*, const float*, const float*,
 int b200_paged_kv_write(const void*, const void*, void*, void*, const int*, const int*, const int*, int, int, int, int, int,
                         int, long long, long long, cudaStream_t);
 int b200_logprob_from_logits(const void*, const long long*, float*, float*, long long, int, long long, int, cudaStream_t);
+int b200_gemm_fp8(const void*, const void*, void*, int, int, int, long long, long long, long long, const float*, const float*,
+                  const void*, const void*, long long, int, cudaStream_t);
+int b200_norm_quant_fp8(const void*, const void*, const void*, void*, float*, int, int, long long, long long, float, int,
+                        cudaStream_t);
 int b200_gemm_bf16_ln(const void*, const void*, void*, int, int, int, long long, long long, long long, const void*, const void*,
                       long long, int, const float*, const float*, float, int, float*, cudaStream_t);
 int b200_gemm_bf16_ex(const void*, const void*, void*, int, int, int, long long, long long, long long, int, int, int, int, float*,
@@ -141,6 +145,41 @@ Tensor gemm_ln(const Tensor& x, const Tensor& w, const OptTensor& bias, const Op
                           optptr(bias), optptr(residual), ldr, act_code(act), st, c1, (float)ln_eps, ln_rms ? 1 : 0, so, stream()),
         "gemm_ln");
   return out;
+}
+
+// e4m3 x e4m3 GEMM with per-row (A) and per-column (B) dequantisation scales; bf16 output.
+Tensor gemm_fp8(const Tensor& a8, const Tensor& b8, const Tensor& row_scale, const Tensor& col_scale, const OptTensor& bias,
+                const OptTensor& residual, const std::string& act) {
+  TORCH_CHECK(a8.is_cuda() && b8.is_cuda() && a8.element_size() == 1 && b8.element_size() == 1, "gemm_fp8: 1-byte operands");
+  TORCH_CHECK(a8.dim() == 2 && b8.dim() == 2 && a8.size(1) == b8.size(1) && a8.stride(1) == 1 && b8.stride(1) == 1);
+  const int64_t M = a8.size(0), N = b8.size(0), K = a8.size(1);
+  TORCH_CHECK(K % 16 == 0 && a8.stride(0) % 16 == 0 && b8.stride(0) % 16 == 0, "gemm_fp8: K and pitches must be multiples of 16");
+  CHECK_F32(row_scale); CHECK_F32(col_scale);
+  TORCH_CHECK(row_scale.numel() == M && col_scale.numel() == N && row_scale.is_contiguous() && col_scale.is_contiguous());
+  c10::cuda::CUDAGuard guard(a8.device());
+  Tensor out = torch::empty({M, N}, a8.options().dtype(at::kBFloat16));
+  long long ldr = 0;
+  if (residual.has_value()) { CHECK_BF16(*residual); TORCH_CHECK(residual->size(0) == M && residual->size(1) == N && residual->stride(1) == 1); ldr = residual->stride(0); }
+  if (bias.has_value()) { CHECK_BF16(*bias); TORCH_CHECK(bias->numel() == N); }
+  check(b200_gemm_fp8(a8.data_ptr(), b8.data_ptr(), out.data_ptr(), (int)M, (int)N, (int)K, a8.stride(0), b8.stride(0), out.stride(0),
+                      row_scale.data_ptr<float>(), col_scale.data_ptr<float>(), optptr(bias), optptr(residual), ldr, act_code(act),
+                      stream()),
+        "gemm_fp8");
+  return out;
+}
+
+// (y8 [rows, H] e4m3 bytes, scale [rows]) = quantise(norm(x))
+std::vector<Tensor> norm_quant(const Tensor& x, const Tensor& w, const OptTensor& b, double eps, bool rms) {
+  CHECK_BF16(x); CHECK_BF16(w);
+  TORCH_CHECK(x.dim() == 2 && x.stride(1) == 1 && x.size(1) % 16 == 0 && x.stride(0) % 8 == 0);
+  c10::cuda::CUDAGuard guard(x.device());
+  const int64_t rows = x.size(0), H = x.size(1);
+  Tensor y8 = torch::empty({rows, H}, x.options().dtype(at::kByte));
+  Tensor scale = torch::empty({rows}, x.options().dtype(at::kFloat));
+  check(b200_norm_quant_fp8(x.data_ptr(), w.data_ptr(), optptr(b), y8.data_ptr(), scale.data_ptr<float>(), (int)rows, (int)H,
+                            x.stride(0), y8.stride(0), (float)eps, rms ? 1 : 0, stream()),
+        "norm_quant");
+  return {y8, scale};
 }
 
 // out[M, N] = sum_k A(m, k) B(n, k) with either operand optionally MN-major (stored transposed: A as [K, M], B as [K, N]).
@@ -568,6 +607,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm_ln", &gemm_ln, py::arg("x"), py::arg("w"), py::arg("bias") = py::none(), py::arg("residual") = py::none(),
         py::arg("act") = "none", py::arg("ln_stats") = py::none(), py::arg("ln_c1") = py::none(), py::arg("ln_eps") = 1e-5,
         py::arg("ln_rms") = false, py::arg("stats_out") = py::none());
+  m.def("gemm_fp8", &gemm_fp8, py::arg("a8"), py::arg("b8"), py::arg("row_scale"), py::arg("col_scale"), py::arg("bias") = py::none(),
+        py::arg("residual") = py::none(), py::arg("act") = "none");
+  m.def("norm_quant", &norm_quant, py::arg("x"), py::arg("w"), py::arg("b") = py::none(), py::arg("eps") = 1e-5,
+        py::arg("rms") = false);
   m.def("gemm_ex", &gemm_ex, py::arg("a"), py::arg("b"), py::arg("a_mn") = false, py::arg("b_mn") = false,
         py::arg("out_f32") = false, py::arg("split_k") = -1);
   m.def("lmhead_tiles", [](int64_t n) { return (int64_t)b200_lmhead_tiles((int)n); }, py::arg("vocab"));

@@ -2,6 +2,8 @@
 // rotary + cache append, value-head row-dot, and the per-step sequence bookkeeping that keeps the whole decode loop on
 // the device (so it can live in one CUDA graph).  Replaces the per-token Python loop + dozens of aten launches of HF
 // generate() used by the reference (trlx/trainer/accelerate_base_trainer.py:256-269).
+#include <cuda_fp8.h>
+
 #include "ptx.cuh"
 
 namespace b200 {
@@ -58,6 +60,73 @@ __global__ void __launch_bounds__(128) norm_kernel(const __nv_bfloat16* __restri
     float f = (__bfloat162float(xr[i]) - mean) * rstd * __bfloat162float(w[i]);
     if (b) f += __bfloat162float(b[i]);
     yr[i] = __float2bfloat16(f);
+  }
+}
+
+// LayerNorm / RMSNorm fused with per-row e4m3 quantisation (rollout_dtype = fp8): y8[row, :] = e4m3(norm(x) / scale[row]),
+// scale[row] = max|norm(x)| / 448.  Three passes over a row that stays in L1/L2: moments, amax, quantise.
+template <bool RMS>
+__global__ void __launch_bounds__(128) norm_quant_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+                                                         const __nv_bfloat16* __restrict__ b, uint8_t* __restrict__ y8,
+                                                         float* __restrict__ scale_out, int H, long long ldx, long long ldy,
+                                                         float eps) {
+  griddep_wait();
+  griddep_launch();
+  const int row = blockIdx.x;
+  const __nv_bfloat16* xr = x + (size_t)row * ldx;
+  uint8_t* yr = y8 + (size_t)row * ldy;
+  __shared__ float red[3][4];
+  float s = 0.f, ss = 0.f;
+  const int nvec = H >> 3;  // H % 16 == 0 is required by the fp8 GEMM
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+    uint4 v = *reinterpret_cast<const uint4*>(xr + i * 8);
+    const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { float f = __bfloat162float(h[j]); s += f; ss += f * f; }
+  }
+  s = warp_sum(s); ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s; red[1][threadIdx.x >> 5] = ss; }
+  __syncthreads();
+  s = red[0][0] + red[0][1] + red[0][2] + red[0][3];
+  ss = red[1][0] + red[1][1] + red[1][2] + red[1][3];
+  const float mean = RMS ? 0.f : s / H;
+  const float var = RMS ? ss / H : fmaxf(ss / H - mean * mean, 0.f);
+  const float rstd = rsqrtf(var + eps);
+  auto normed = [&](int i, float (&o)[8]) {
+    uint4 v = *reinterpret_cast<const uint4*>(xr + i * 8);
+    uint4 wv = *reinterpret_cast<const uint4*>(w + i * 8);
+    const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&v);
+    const __nv_bfloat16* wh = reinterpret_cast<const __nv_bfloat16*>(&wv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = (__bfloat162float(h[j]) - mean) * rstd * __bfloat162float(wh[j]);
+    if (b) {
+      uint4 bv = *reinterpret_cast<const uint4*>(b + i * 8);
+      const __nv_bfloat16* bh = reinterpret_cast<const __nv_bfloat16*>(&bv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] += __bfloat162float(bh[j]);
+    }
+  };
+  float amax = 0.f;
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+    float o[8];
+    normed(i, o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) amax = fmaxf(amax, fabsf(o[j]));
+  }
+  amax = warp_max(amax);
+  if ((threadIdx.x & 31) == 0) red[2][threadIdx.x >> 5] = amax;
+  __syncthreads();
+  amax = fmaxf(fmaxf(red[2][0], red[2][1]), fmaxf(red[2][2], red[2][3]));
+  const float scale = fmaxf(amax, 1e-12f) / 448.f, inv = 1.f / scale;
+  if (threadIdx.x == 0) scale_out[row] = scale;
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+    float o[8];
+    normed(i, o);
+    uint2 q;
+    uint8_t* qb = reinterpret_cast<uint8_t*>(&q);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) qb[j] = (uint8_t)__nv_cvt_float_to_fp8(o[j] * inv, __NV_SATFINITE, __NV_E4M3);
+    *reinterpret_cast<uint2*>(yr + i * 8) = q;
   }
 }
 
@@ -361,6 +430,17 @@ extern "C" int b200_norm_bf16(const void* x, const void* w, const void* b, void*
                               (const __nv_bfloat16*)w, (const __nv_bfloat16*)nullptr, (__nv_bfloat16*)y, H, ldx, ldy, eps);
   return (int)launch_kernel(norm_kernel<false>, dim3(rows), dim3(128), 0, stream, (const __nv_bfloat16*)x,
                             (const __nv_bfloat16*)w, (const __nv_bfloat16*)b, (__nv_bfloat16*)y, H, ldx, ldy, eps);
+}
+
+extern "C" int b200_norm_quant_fp8(const void* x, const void* w, const void* b, void* y8, float* scale, int rows, int H,
+                                   long long ldx, long long ldy, float eps, int rms, cudaStream_t stream) {
+  if (rows <= 0) return 0;
+  if (H % 16) return -2;
+  if (rms)
+    return (int)launch_kernel(norm_quant_kernel<true>, dim3(rows), dim3(128), 0, stream, (const __nv_bfloat16*)x,
+                              (const __nv_bfloat16*)w, (const __nv_bfloat16*)nullptr, (uint8_t*)y8, scale, H, ldx, ldy, eps);
+  return (int)launch_kernel(norm_quant_kernel<false>, dim3(rows), dim3(128), 0, stream, (const __nv_bfloat16*)x,
+                            (const __nv_bfloat16*)w, (const __nv_bfloat16*)b, (uint8_t*)y8, scale, H, ldx, ldy, eps);
 }
 
 extern "C" int b200_embed_bf16(const long long* tokens, const int* positions, const void* wte, const void* wpe,

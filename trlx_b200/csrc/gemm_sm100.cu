@@ -57,6 +57,7 @@ struct StoreEpilogue {
   int ln_rms;
   // ... and the producer side: accumulate (sum, sum of squares) of the bf16-rounded output rows for the NEXT folded norm
   float* stats_out;
+  const float* row_scale;    // [M] or null: per-row dequantisation scale of an fp8 A operand (col_scale carries B's)
   int tma_store;              // bf16 output goes through shared memory + cp.async.bulk.tensor (needs ldo % 8 == 0)
 };
 
@@ -159,13 +160,16 @@ struct RowCtx {      // per-thread (= per output row) constants of the store epi
   float dl_l, dl_g;
   long long dl_lab;
   float ln_rstd, ln_murstd;
+  float row_scale;
 };
 
 // v = act(alpha * acc [* col_scale] [+ bias])  (or the d-logits transform)  [+ residual]   for a FULL 16-column chunk
 __device__ __forceinline__ void store_values_full(const uint32_t (&r)[16], float (&v)[16], int row, int col0,
                                                   const StoreEpilogue& se, const RowCtx& rc, bool vec_in, bool row_ok) {
 #pragma unroll
-  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) * se.alpha;
+  const float a_scale = se.alpha * rc.row_scale;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) * a_scale;
   if (se.col_scale) {
 #pragma unroll
     for (int j = 0; j < 16; j += 4) {
@@ -240,7 +244,7 @@ __device__ __noinline__ void tail_values(const uint32_t* r, float* v, int row, i
     const int col = col0 + j;
     float x = 0.f;
     if (col < N) {
-      x = __uint_as_float(r[j]) * se.alpha;
+      x = __uint_as_float(r[j]) * se.alpha * rc.row_scale;
       if (se.col_scale) x *= se.col_scale[col];
       if (se.bias) x += __bfloat162float(se.bias[col]);
       if (rc.dl) x = (rc.dl_lab < 0) ? 0.f : (((long long)col == rc.dl_lab ? 1.f : 0.f) - __expf(x - rc.dl_l)) * rc.dl_g;
@@ -266,7 +270,8 @@ __device__ __forceinline__ void epilogue_cols(uint32_t taddr_row, int row, bool 
                                               const ReduceScatterEpilogue& re, uint8_t* stg, const CUtensorMap* map_out,
                                               int row0_warp, int lane) {
   if constexpr (EPI == 0) {
-    RowCtx rc{se.dl_lse != nullptr, 0.f, 0.f, -1, 1.f, 0.f};
+    RowCtx rc{se.dl_lse != nullptr, 0.f, 0.f, -1, 1.f, 0.f, 1.f};
+    if (se.row_scale && row_ok) rc.row_scale = se.row_scale[row];
     if (rc.dl && row_ok) { rc.dl_l = se.dl_lse[row]; rc.dl_g = se.dl_grad[row]; rc.dl_lab = se.dl_labels[row]; }
     if (se.ln_stats && row_ok) {
       const float s1 = se.ln_stats[2 * (size_t)row], s2 = se.ln_stats[2 * (size_t)row + 1];
@@ -473,12 +478,15 @@ __device__ __forceinline__ void epilogue_cols(uint32_t taddr_row, int row, bool 
 // TBM: rows per tile, 128 or 64.  UMMA M = 64 keeps its accumulator in lanes 0-15 of each 32-lane TMEM quadrant
 // (row m -> lane (m % 16) + 32 * (m / 16)), so the epilogue warps use half of their lanes; it exists for the decode path,
 // where M = batch is a single 128-row tile and halving the A panel per CTA halves each CTA's (redundant) operand traffic.
-template <int BN, int EPI, int AMN = 0, int BMN = 0, int TBM = 128>  // EPI: 0 = store, 1 = lm-head, 2 = reduce-scatter
+// FP8: both operands are e4m3 bytes (kind::f8f6f4, UMMA K = 32): a k-block is still one 128-byte swizzle row = 128 elements.
+template <int BN, int EPI, int AMN = 0, int BMN = 0, int TBM = 128, int FP8 = 0>  // EPI: 0 store, 1 lm-head, 2 reduce-scatter
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ MapArray maps_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_out, int M, int N, int K, int stages, int rows_per_map,
                StoreEpilogue se, LMHeadEpilogue le, ReduceScatterEpilogue re, int k_splits) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr int BKE = FP8 ? 2 * BK : BK;            // elements per k-block (128 bytes per row either way)
+  static_assert(!FP8 || (!AMN && !BMN), "fp8 operands are K-major");
   constexpr uint32_t A_BYTES = TBM * BK * 2;
   static_assert(TBM == 128 || (TBM == 64 && !AMN), "64-row tiles: K-major A only");
   constexpr uint32_t B_BYTES = BN * BK * 2;
@@ -500,7 +508,7 @@ gemm_tn_kernel(const __grid_constant__ MapArray maps_a, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nkb = (K + BK - 1) / BK;
+  const int nkb = (K + BKE - 1) / BKE;
   const int m_tiles = (M + TBM - 1) / TBM;
   const int n_tiles = (N + BN - 1) / BN;
   const int total_tiles = m_tiles * n_tiles;
@@ -558,20 +566,20 @@ gemm_tn_kernel(const __grid_constant__ MapArray maps_a, const __grid_constant__ 
 #pragma unroll
             for (int ch = 0; ch < TBM / 64; ++ch) tma_load_2d(a_dst + ch * MN_CHUNK, map_a_ptr, &full_bar[s], m0 + ch * 64, kb * BK);
           } else {
-            tma_load_2d(a_dst, map_a_ptr, &full_bar[s], kb * BK, a_row);
+            tma_load_2d(a_dst, map_a_ptr, &full_bar[s], kb * BKE, a_row);
           }
           if constexpr (BMN) {
 #pragma unroll
             for (int ch = 0; ch < BN / 64; ++ch) tma_load_2d(b_dst + ch * MN_CHUNK, &map_b, &full_bar[s], n0 + ch * 64, kb * BK);
           } else {
-            tma_load_2d(b_dst, &map_b, &full_bar[s], kb * BK, n0);
+            tma_load_2d(b_dst, &map_b, &full_bar[s], kb * BKE, n0);
           }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc(1, 1, TBM, BN, AMN, BMN);
+      constexpr uint32_t idesc = FP8 ? umma_idesc(0, 0, TBM, BN) : umma_idesc(1, 1, TBM, BN, AMN, BMN);  // fp8: e4m3 x e4m3
       uint32_t it = 0, tcount = 0;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tcount) {
         const int split = w / total_tiles;
@@ -593,7 +601,8 @@ gemm_tn_kernel(const __grid_constant__ MapArray maps_a, const __grid_constant__ 
           constexpr uint32_t A_STEP = AMN ? (16 * 128) >> 4 : 2, B_STEP = BMN ? (16 * 128) >> 4 : 2;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            umma_bf16(tmem_acc, da + A_STEP * k, db + B_STEP * k, idesc, (kb > kb_lo || k > 0) ? 1u : 0u);
+            if constexpr (FP8) umma_fp8(tmem_acc, da + 2 * k, db + 2 * k, idesc, (kb > kb_lo || k > 0) ? 1u : 0u);
+            else umma_bf16(tmem_acc, da + A_STEP * k, db + B_STEP * k, idesc, (kb > kb_lo || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[s]);
         }
@@ -851,11 +860,11 @@ static EncodeTiledFn encode_fn() {
 // Row-major bf16 matrix [rows, cols] with row pitch ld (elements); box = box_rows x box_cols elements, swizzle span =
 // box_cols * 2 bytes (128 / 64 / 32).  Operand loads use 64-column (128-byte) boxes.
 static bool make_map(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_rows,
-                     int box_cols = BK) {
-  using Key = std::tuple<const void*, long long, long long, long long, int, int>;
+                     int box_cols = BK, int elem_bytes = 2) {
+  using Key = std::tuple<const void*, long long, long long, long long, int, int, int>;
   static std::map<Key, CUtensorMap> cache;
   static std::mutex mu;
-  Key key{ptr, rows, cols, ld, box_rows, box_cols};
+  Key key{ptr, rows, cols, ld, box_rows, box_cols, elem_bytes};
   {
     std::lock_guard<std::mutex> g(mu);
     auto it = cache.find(key);
@@ -864,12 +873,13 @@ static bool make_map(CUtensorMap* map, const void* ptr, long long rows, long lon
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * elem_bytes};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  const CUtensorMapSwizzle sw = box_cols >= 64 ? CU_TENSOR_MAP_SWIZZLE_128B
-                                : (box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  const int row_bytes = box_cols * elem_bytes;
+  const CUtensorMapSwizzle sw = row_bytes >= 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUresult r = fn(map, elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return false;
   std::lock_guard<std::mutex> g(mu);
@@ -907,18 +917,18 @@ static int pick_bn(int M, int N) {
   return best;
 }
 
-template <int BN, int EPI, int AMN = 0, int BMN = 0, int TBM = 128>
+template <int BN, int EPI, int AMN = 0, int BMN = 0, int TBM = 128, int FP8 = 0>
 static cudaError_t launch(const MapArray& ma, const CUtensorMap& mb, const CUtensorMap& mo, int M, int N, int K,
                           int rows_per_map, const StoreEpilogue& se, const LMHeadEpilogue& le,
                           const ReduceScatterEpilogue& re, cudaStream_t stream, int k_splits = 1) {
   constexpr int stage_bytes = TBM * BK * 2 + BN * BK * 2;
   constexpr int fixed_bytes = NUM_EPI_WARPS * STG_BYTES + 1024 /*alignment slack*/ + 512 /*barriers*/;
-  const int nkb = (K + BK - 1) / BK;
+  const int nkb = (K + (FP8 ? 2 * BK : BK) - 1) / (FP8 ? 2 * BK : BK);
   int stages = (227 * 1024 - fixed_bytes) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages > nkb) stages = nkb < 2 ? 2 : nkb;
   const size_t smem = (size_t)stages * stage_bytes + fixed_bytes;
-  auto kern = gemm_tn_kernel<BN, EPI, AMN, BMN, TBM>;
+  auto kern = gemm_tn_kernel<BN, EPI, AMN, BMN, TBM, FP8>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -1054,6 +1064,34 @@ static int gemm_bf16_impl(const void* A, const void* B, void* out, int M, int N,
     case 128: e = launch<128, 0>(ma, mb, mo, M, N, K, rpm, se, le, re, stream); break;
     case 64: e = launch<64, 0>(ma, mb, mo, M, N, K, rpm, se, le, re, stream); break;
     default: e = launch<32, 0>(ma, mb, mo, M, N, K, rpm, se, le, re, stream); break;
+  }
+  return (int)e;
+}
+
+// fp8 (e4m3) GEMM for the rollout path: out[M, N] (bf16) = act((A8[M, K] . B8[N, K]^T) * row_scale[m] * col_scale[n] + bias[n])
+// + residual.  A8 / B8 are e4m3 bytes, K-major, K % 16 == 0 and row pitches % 16 == 0 (TMA).
+extern "C" int b200_gemm_fp8(const void* A, const void* B, void* out, int M, int N, int K, long long lda, long long ldb,
+                             long long ldo, const float* row_scale, const float* col_scale, const void* bias,
+                             const void* residual, long long ldr, int act, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  const int bn = pick_bn(M, N);
+  MapArray ma{};
+  CUtensorMap mb;
+  if (!make_map(&ma.m[0], A, M, K, lda, BM, 128, 1) || !make_map(&mb, B, N, K, ldb, bn, 128, 1)) return -1;
+  StoreEpilogue se{out, (const __nv_bfloat16*)bias, (const __nv_bfloat16*)residual, col_scale, ldo, ldr, 1.0f, act, 0};
+  se.row_scale = row_scale;
+  se.ln_inv_k = 1.0f;
+  CUtensorMap mo{};
+  if (!setup_tma_store(se, &mo, M, N, bn)) return -1;
+  LMHeadEpilogue le{};
+  ReduceScatterEpilogue re{};
+  const int rpm = 1 << 30;
+  cudaError_t e;
+  switch (bn) {
+    case 256: e = launch<256, 0, 0, 0, 128, 1>(ma, mb, mo, M, N, K, rpm, se, le, re, stream); break;
+    case 128: e = launch<128, 0, 0, 0, 128, 1>(ma, mb, mo, M, N, K, rpm, se, le, re, stream); break;
+    case 64: e = launch<64, 0, 0, 0, 128, 1>(ma, mb, mo, M, N, K, rpm, se, le, re, stream); break;
+    default: e = launch<32, 0, 0, 0, 128, 1>(ma, mb, mo, M, N, K, rpm, se, le, re, stream); break;
   }
   return (int)e;
 }

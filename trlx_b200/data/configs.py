@@ -126,7 +126,8 @@ class ParallelConfig(_Section):
     :param zero_stage: 0 = replicated optimizer (DDP-like), 1/2 = optimizer state + grads sharded
         across DP ranks (fused reduce-scatter + AdamW + all-gather), 3 = parameters sharded as well
     :param precision: compute dtype, ``"bf16"`` (default), ``"fp16"`` or ``"fp32"``
-    :param rollout_dtype: weight dtype for generation: ``"bf16"`` or ``"fp8"`` (block-scaled e4m3)
+    :param rollout_dtype: ``"bf16"`` or ``"fp8"``: with fp8 the rollout engine runs the norm → QKV and norm → MLP-up GEMMs of
+        every block in e4m3 x e4m3 (activations quantised per row inside the norm kernel, weights per output channel)
     :param cuda_graphs: capture decode steps / train steps in CUDA graphs when shapes are static
     :param bucket_mb: gradient bucket size for the fused reduce-scatter/AdamW kernel
     :param grad_clip: global-norm clip applied inside the fused optimizer (0/None = off;

@@ -63,6 +63,25 @@ def _layer_weights(block, spec, idx: int) -> _LayerW:
 
 
 @dataclass
+class _Fp8W:
+    """e4m3 copies of the two weight matrices that follow a norm (QKV and MLP-up), one dequantisation scale per output
+    channel; the matching activations are quantised per row inside the norm kernel (``rollout_dtype = "fp8"``)."""
+
+    qkv_w: torch.Tensor
+    qkv_s: torch.Tensor
+    up_w: torch.Tensor
+    up_s: torch.Tensor
+    trainable: bool
+
+
+def _quant_e4m3(w: torch.Tensor):
+    wf = w.float()
+    scale = (wf.abs().amax(1).clamp_min(1e-12) / 448.0).contiguous()
+    q = (wf / scale[:, None]).clamp(-448.0, 448.0).to(torch.float8_e4m3fn).view(torch.uint8).contiguous()
+    return q, scale
+
+
+@dataclass
 class _FoldW:
     """Per-layer derived weights for norm-folded GEMMs: ``LN(x)·Wᵀ = rstd·(x·(γ⊙W)ᵀ) − rstd·μ·c1 + (W·β + b)``."""
 
@@ -112,7 +131,7 @@ class RolloutEngine:
             return False
         if g.get("num_beams", 1) not in (1, None) or g.get("repetition_penalty") not in (None, 1.0):
             return False
-        if any(isinstance(v, list) for v in g.values()):
+        if any(isinstance(v, list) for k, v in g.items() if not str(k).startswith("_")):
             return False
         return True
 
@@ -152,6 +171,12 @@ class RolloutEngine:
                            and spec.hidden_size % 16 == 0 and all(W.qkv_w.shape[0] % 16 == 0 and W.up_w.shape[0] % 16 == 0
                                                                   for W in self.layers + self.ref_layers)
                            and folded_bytes <= int(os.environ.get("TRLX_B200_FOLD_BUDGET_MB", "4096")) << 20)
+        # fp8 rollout (config.train.parallel.rollout_dtype == "fp8" or TRLX_B200_ROLLOUT_FP8=1): the norm → GEMM pairs of every
+        # block (QKV, MLP up) run e4m3 x e4m3 on the tensor cores with per-row / per-channel scales; half the weight bytes
+        self.fp8 = (str(gen_kwargs.get("_rollout_dtype", os.environ.get("TRLX_B200_ROLLOUT_FP8", ""))).lower() in ("fp8", "1", "true")
+                    and spec.hidden_size % 16 == 0 and not self.fold_norms)
+        self.fp8_w: List[_Fp8W] = []
+        self.ref_fp8_w: List[_Fp8W] = []
         self.folded: List[_FoldW] = []
         self.ref_folded: List[_FoldW] = []
         self.dirty = True  # folded copies must be (re)built before the next rollout
@@ -166,8 +191,31 @@ class RolloutEngine:
         self.dirty = True
 
     @torch.no_grad()
+    def _refresh_fp8(self):
+        first = not self.fp8_w
+
+        def build(W: _LayerW, old: Optional[_Fp8W]) -> _Fp8W:
+            trainable = any(t.requires_grad for t in (W.qkv_w, W.up_w))
+            if old is not None and not trainable:
+                return old
+            q, qs = _quant_e4m3(W.qkv_w)
+            u, us = _quant_e4m3(W.up_w)
+            if old is None:
+                return _Fp8W(q, qs, u, us, trainable)
+            for dst, src in zip((old.qkv_w, old.qkv_s, old.up_w, old.up_s), (q, qs, u, us)):
+                dst.copy_(src)
+            return old
+
+        self.fp8_w = [build(W, None if first else self.fp8_w[i]) for i, W in enumerate(self.layers)]
+        self.ref_fp8_w = [build(W, None if first else self.ref_fp8_w[i]) for i, W in enumerate(self.ref_layers)]
+
+    @torch.no_grad()
     def refresh_folded(self):
         """(Re)build γ-scaled copies of the QKV / MLP-up weights in place (the captured CUDA graph keeps their addresses)."""
+        if self.fp8 and self.dirty:
+            self._refresh_fp8()
+            self.dirty = False
+            return
         if not self.fold_norms or not self.dirty:
             return
         first = not self.folded
@@ -221,8 +269,36 @@ class RolloutEngine:
         return st["ln_stats"][i]
 
     # ------------------------------------------------------------------------------------------------ kernels per layer
+    def _layer_fp8(self, x, W: _LayerW, Q: _Fp8W, kc, vc, st):
+        """Block with the two norm → GEMM pairs in e4m3 (attention, out-proj and MLP-down stay bf16)."""
+        C, spec = ops.C, self.spec
+        rms, eps = spec.norm == "rmsnorm", spec.norm_eps
+        h8, hs = C.norm_quant(x, W.n1w, W.n1b, eps, rms)
+        qkv = C.gemm_fp8(h8, Q.qkv_w, hs, Q.qkv_s, W.qkv_b, None, "none")
+        a = C.decode_attention(qkv, kc, vc, st["block_table"], st["seq_lens"], st["positions"], spec.num_heads,
+                               spec.num_kv_heads, spec.head_dim, self.scale, self.rot_dim, spec.rotary_base,
+                               spec.rotary_interleaved, self.alibi, W.window)
+
+        def mlp_mid(h8_, hs_):
+            if spec.gated_mlp:
+                g, u = C.gemm_fp8(h8_, Q.up_w, hs_, Q.up_s, W.up_b, None, "none").chunk(2, dim=-1)
+                return (F.silu(g) * u).contiguous() if spec.activation in ("silu", "swish") else (F.gelu(g, approximate="tanh") * u).contiguous()
+            return C.gemm_fp8(h8_, Q.up_w, hs_, Q.up_s, W.up_b, None, spec.activation)
+
+        if spec.parallel_residual:
+            h2 = (h8, hs) if W.n2w is None else tuple(C.norm_quant(x, W.n2w, W.n2b, eps, rms))
+            t = C.gemm(a, W.out_w, W.out_b, x)
+            return C.gemm(mlp_mid(*h2), W.down_w, W.down_b, t)
+        x = C.gemm(a, W.out_w, W.out_b, x)
+        h2 = C.norm_quant(x, W.n2w, W.n2b, eps, rms)
+        return C.gemm(mlp_mid(*h2), W.down_w, W.down_b, x)
+
     def _layer(self, x, W: _LayerW, kc, vc, st):
         C, spec = ops.C, self.spec
+        if self.fp8:
+            idx = next((i for i, L_ in enumerate(self.layers) if L_ is W), None)
+            Q = self.fp8_w[idx] if idx is not None else self.ref_fp8_w[next(i for i, L_ in enumerate(self.ref_layers) if L_ is W)]
+            return self._layer_fp8(x, W, Q, kc, vc, st)
         rms = spec.norm == "rmsnorm"
         h = C.norm(x, W.n1w, W.n1b, spec.norm_eps, rms)
         qkv = C.gemm(h, W.qkv_w, W.qkv_b)

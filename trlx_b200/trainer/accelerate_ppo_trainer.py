@@ -249,7 +249,8 @@ class AcceleratePPOTrainer(AccelerateRLTrainer):
 
             gen = self.generate_experience_kwargs or self.generate_kwargs
             if RolloutEngine.supports(self.model, gen, self.config, self.stop_sequences):
-                self._engine = RolloutEngine(self.model, self.tokenizer.pad_token_id, self.tokenizer.eos_token_id, gen,
+                gen_engine = dict(gen, _rollout_dtype=self.config.train.parallel.rollout_dtype)
+                self._engine = RolloutEngine(self.model, self.tokenizer.pad_token_id, self.tokenizer.eos_token_id, gen_engine,
                                              cache_trunk=self.cache_trunk, seed=self.config.train.seed + self.runtime.rank)
             else:
                 self._engine_failed = True
