@@ -2,6 +2,7 @@
 // mbarrier, TMA (cp.async.bulk.tensor), tcgen05 (alloc / mma / commit / ld / fences) and
 // cross-GPU (system-scope) loads/stores/flags.  Compile with -gencode arch=compute_100a,code=sm_100a.
 #pragma once
+#include <cstdlib>
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -262,9 +263,24 @@ __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x));
 bool pdl_enabled();
 void set_pdl_enabled(bool on);
 
+// Every kernel of this library asks for the same L1 / shared-memory split (max shared).  The GEMMs need ~227 KB of dynamic
+// shared memory; if the small kernels between them (norm, attention, bookkeeping) ran with the default L1-heavy carveout the
+// SMs would be reconfigured on every launch of a decode step — measured as ~8 us of dead time around each 4 us GEMM.
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                                  Args... args) {
+  static const bool uniform_carveout = getenv("B200_NO_UNIFORM_CARVEOUT") == nullptr;
+  if (uniform_carveout) {
+    static void* seen[64];
+    static int n_seen = 0;
+    bool known = false;
+    for (int i = 0; i < n_seen; ++i) known |= (seen[i] == reinterpret_cast<void*>(kernel));
+    if (!known) {
+      cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      cudaGetLastError();
+      if (n_seen < 64) seen[n_seen++] = reinterpret_cast<void*>(kernel);
+    }
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = block;

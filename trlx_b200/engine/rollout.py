@@ -494,31 +494,35 @@ class RolloutEngine:
         if not self.use_cuda_graph or os.environ.get("TRLX_B200_PREFILL_GRAPH", "1") != "1" or st.get("prefill_failed") \
                 or prompt.shape[1] < 2:
             return self._prefill(st, prompt, mask)
-        if st.get("prefill_graph") is None:
+        graphs = st.setdefault("prefill_graphs", {})  # one per prompt width (the state itself serves every width <= P pages)
+        Q = int(prompt.shape[1])
+        if Q not in graphs:
+            if len(graphs) >= 8:
+                return self._prefill(st, prompt, mask)
             try:
-                st["pf_prompt"], st["pf_mask"] = prompt.clone(), mask.clone()
+                pf_prompt, pf_mask = prompt.clone(), mask.clone()
                 side = torch.cuda.Stream()
                 side.wait_stream(torch.cuda.current_stream())
                 before = ops.launch_count()
                 with torch.cuda.stream(side):
-                    self._prefill(st, st["pf_prompt"], st["pf_mask"])
-                st["prefill_launches"] = ops.launch_count() - before
+                    self._prefill(st, pf_prompt, pf_mask)
+                launches = ops.launch_count() - before
                 torch.cuda.current_stream().wait_stream(side)
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph):
-                    outs = self._prefill(st, st["pf_prompt"], st["pf_mask"])
-                st["prefill_graph"], st["prefill_outs"] = graph, outs
+                    outs = self._prefill(st, pf_prompt, pf_mask)
+                graphs[Q] = (graph, pf_prompt, pf_mask, outs, launches)
             except Exception as err:  # keep the eager path if anything in the prefill is not capturable
                 logger.warning(f"prefill CUDA graph disabled ({type(err).__name__}: {err})")
                 st["prefill_failed"] = True
                 torch.cuda.synchronize()
                 return self._prefill(st, prompt, mask)
-        st["pf_prompt"].copy_(prompt, non_blocking=True)
-        st["pf_mask"].copy_(mask, non_blocking=True)
-        st["prefill_graph"].replay()
-        ops.add_launches(st["prefill_launches"])
-        lp, ref_lp, vals, trunk = st["prefill_outs"]
-        return lp, ref_lp, vals, trunk  # static buffers: every consumer below copies (cat / index) before the next replay
+        graph, pf_prompt, pf_mask, outs, launches = graphs[Q]
+        pf_prompt.copy_(prompt, non_blocking=True)
+        pf_mask.copy_(mask, non_blocking=True)
+        graph.replay()
+        ops.add_launches(launches)
+        return outs  # static buffers: every consumer below copies (cat / index) before the next replay
 
     # ------------------------------------------------------------------------------------------------ public API
     @torch.no_grad()
