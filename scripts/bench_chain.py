@@ -1,0 +1,83 @@
+"""Per-kernel latency of dependent small GEMMs inside one CUDA graph (the decode regime): a chain y = gemm(y, W_i) over many
+distinct weight matrices (cold in L2, like consecutive layers), timed per kernel for several tile widths."""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from trlx_b200 import ops  # noqa: E402
+
+C = ops.C
+dev = "cuda"
+torch.manual_seed(0)
+M, H = 128, 768
+n_w = int(os.environ.get("CHAIN_WEIGHTS", 48))
+Ws = [(torch.randn(H, H, device=dev) * H ** -0.5).to(torch.bfloat16) for _ in range(n_w)]          # square: chainable
+Wq = [(torch.randn(2304, H, device=dev) * H ** -0.5).to(torch.bfloat16) for _ in range(n_w)]        # QKV-shaped (not chained)
+big = [(torch.randn(3072, H, device=dev) * H ** -0.5).to(torch.bfloat16) for _ in range(n_w)]
+x0 = (torch.randn(M, H, device=dev)).to(torch.bfloat16)
+g = torch.ones(H, device=dev, dtype=torch.bfloat16)
+
+
+def timed_graph(fn, iters=5):
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        fn()
+    torch.cuda.current_stream().wait_stream(s)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        fn()
+    graph.replay()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        graph.replay()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) * 1e3 / iters
+
+
+def chain_square(bn):
+    def fn():
+        y = x0
+        for W in Ws:
+            y = C.gemm(y, W, None, None, "none", force_bn=bn)
+        return y
+    return fn
+
+
+def chain_qkv(bn, weights):
+    def fn():
+        y = x0
+        outs = []
+        for W in weights:  # dependent through a cheap slice so the kernels serialise like layers do
+            o = C.gemm(y, W, None, None, "none", force_bn=bn)
+            y = o[:, :H]
+            if y.stride(0) % 8:
+                y = y.contiguous()
+        return y
+    return fn
+
+
+def chain_norm():
+    def fn():
+        y = x0
+        for _ in range(n_w):
+            y = C.norm(y, g, None, 1e-5, False)
+        return y
+    return fn
+
+
+for pdl in (1, 0):
+    C.set_pdl(bool(pdl))
+    rec = {"pdl": pdl, "norm_us": round(timed_graph(chain_norm()) / n_w, 2)}
+    for bn in (32, 64, 128):
+        rec[f"sq768_bn{bn}_us"] = round(timed_graph(chain_square(bn)) / n_w, 2)
+    for bn in (32, 64, 128):
+        rec[f"qkv2304_bn{bn}_us"] = round(timed_graph(chain_qkv(bn, Wq)) / n_w, 2)
+    rec["fc3072_bn32_us"] = round(timed_graph(chain_qkv(32, big)) / n_w, 2)
+    print(json.dumps(rec), flush=True)
