@@ -60,26 +60,71 @@ def reference_arm(args):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    """SM clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).  NVML in a background thread
+    (first sample immediately, then every 50 ms, last sample at stop) — `nvidia-smi -lms` needs most of a second to start on an
+    8-GPU box and missed short runs entirely; it remains the fallback when the NVML bindings are unavailable."""
 
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
+    REASON_BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, index: int):
         self.index, self.proc, self.path = index, None, None
+        self.thread, self.stop_flag, self.sm, self.mx, self.reasons = None, None, [], [], set()
+
+    def _nvml_sample(self, pynvml, handle):
+        try:
+            self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)))
+            self.mx.append(float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM)))
+            try:
+                bits = pynvml.nvmlDeviceGetCurrentClocksEventReasons(handle)
+            except Exception:
+                bits = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(handle)
+            for name, bit in self.REASON_BITS.items():
+                if bits & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
 
     def start(self):
+        try:
+            import threading
+
+            import pynvml
+
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[self.index]) if visible and visible.split(",")[self.index].isdigit() else self.index
+            handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.stop_flag = threading.Event()
+            self._nvml_sample(pynvml, handle)
+
+            def loop():
+                while not self.stop_flag.wait(0.05):
+                    self._nvml_sample(pynvml, handle)
+                self._nvml_sample(pynvml, handle)
+
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.index)], stdout=open(self.path, "w"),
+                                          "-lms", "100", "-i", str(self.index)], stdout=open(self.path, "w"),
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
     def stop(self):
+        if self.thread is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+            return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                    "samples": len(self.sm), "reasons": sorted(self.reasons), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -103,7 +148,7 @@ class ClockSampler:
         except Exception:
             pass
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi"}
 
 
 def build_trainer(args, tmp):

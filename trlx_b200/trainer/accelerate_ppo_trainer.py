@@ -373,7 +373,7 @@ class AcceleratePPOTrainer(AccelerateRLTrainer):
             t_gen = time()
             if engine is not None:
                 ids, am = batch["input_ids"], batch["attention_mask"]
-                bucket = int(self.config.train.trainer_kwargs.get("prompt_bucket", 16))
+                bucket = int(self.config.train.trainer_kwargs.get("prompt_bucket", 32))
                 width = -(-ids.shape[1] // bucket) * bucket
                 if rt.distributed and rt.dp_size > 1:
                     # every data-parallel rank uses the same padded prompt width, so their rollout blocks — and therefore
