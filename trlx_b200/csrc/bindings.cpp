@@ -67,6 +67,12 @@ int b200_gemm_allgather_bf16(void* const*, int, const void*, void*, int, int, in
                              int, cudaStream_t);
 int b200_gemm_reduce_scatter_bf16(const void*, const void*, float* const*, int, int, int, int, long long, long long, long long,
                                   const void*, cudaStream_t);
+int b200_gemm_flagged_bf16(const void*, const void*, void*, int, int, int, long long, long long, long long, const void*, int,
+                           const uint32_t*, uint32_t, int, int, cudaStream_t);
+int b200_stage_reduce(const void*, int, const void*, const void*, void*, long long, int, long long, long long, long long,
+                      cudaStream_t);
+int b200_gemm_stage_scatter_bf16(const void*, const void*, void* const*, int, int, int, int, int, long long, long long, long long,
+                                 const void*, cudaStream_t);
 int b200_rs_finalize(const float*, const void*, const void*, void*, long long, int, long long, long long, long long,
                      cudaStream_t);
 }
@@ -513,6 +519,51 @@ Tensor gemm_allgather(const std::vector<int64_t>& peers, int64_t rows_per_rank, 
   return out;
 }
 
+// GEMM whose A rows become readable chunk by chunk (flags[c] == epoch), starting with chunk `first_chunk` (see AReady)
+Tensor gemm_flagged(const Tensor& a, const Tensor& w, const OptTensor& bias, const std::string& act, const Tensor& flags,
+                    int64_t epoch, int64_t rows_per_flag, int64_t first_chunk) {
+  CHECK_BF16(a); CHECK_BF16(w);
+  TORCH_CHECK(a.dim() == 2 && w.dim() == 2 && a.size(1) == w.size(1) && a.stride(1) == 1 && w.stride(1) == 1);
+  TORCH_CHECK(flags.scalar_type() == at::kInt && flags.is_cuda() && flags.is_contiguous());
+  TORCH_CHECK(a.size(0) % rows_per_flag == 0 && flags.numel() >= a.size(0) / rows_per_flag);
+  c10::cuda::CUDAGuard guard(a.device());
+  Tensor out = torch::empty({a.size(0), w.size(0)}, a.options());
+  check(b200_gemm_flagged_bf16(a.data_ptr(), w.data_ptr(), out.data_ptr(), (int)a.size(0), (int)w.size(0), (int)a.size(1),
+                               a.stride(0), w.stride(0), out.stride(0), optptr(bias), act_code(act),
+                               reinterpret_cast<const uint32_t*>(flags.data_ptr<int>()), (uint32_t)epoch, (int)rows_per_flag,
+                               (int)first_chunk, stream()),
+        "gemm_flagged");
+  return out;
+}
+
+// partial product x[M, K_local] . w[N, K_local]^T stored (bf16) into slot `rank` of every owner's staging buffer
+void gemm_stage_scatter(const Tensor& x, const Tensor& w, const std::vector<int64_t>& stage_peers, int64_t rank, int64_t ldstage,
+                        const OptTensor& bias) {
+  CHECK_BF16(x); CHECK_BF16(w);
+  TORCH_CHECK(x.dim() == 2 && w.dim() == 2 && x.size(1) == w.size(1) && x.stride(1) == 1 && w.stride(1) == 1);
+  c10::cuda::CUDAGuard guard(x.device());
+  std::vector<void*> p(stage_peers.size());
+  for (size_t i = 0; i < stage_peers.size(); ++i) p[i] = reinterpret_cast<void*>(stage_peers[i]);
+  check(b200_gemm_stage_scatter_bf16(x.data_ptr(), w.data_ptr(), p.data(), (int)p.size(), (int)rank, (int)x.size(0), (int)w.size(0),
+                                     (int)x.size(1), x.stride(0), w.stride(0), ldstage, optptr(bias), stream()),
+        "gemm_stage_scatter");
+}
+
+// out[rows, N] = sum over the `world` slots of stage [world, rows, N] (+ bias + residual)
+Tensor stage_reduce(const Tensor& stage, const OptTensor& bias, const OptTensor& residual) {
+  CHECK_BF16(stage);
+  TORCH_CHECK(stage.dim() == 3 && stage.is_contiguous());
+  c10::cuda::CUDAGuard guard(stage.device());
+  const int64_t world = stage.size(0), rows = stage.size(1), N = stage.size(2);
+  Tensor out = torch::empty({rows, N}, stage.options());
+  long long ldr = 0;
+  if (residual.has_value()) { CHECK_BF16(*residual); TORCH_CHECK(residual->size(0) == rows && residual->size(1) == N && residual->stride(1) == 1); ldr = residual->stride(0); }
+  check(b200_stage_reduce(stage.data_ptr(), (int)world, optptr(bias), optptr(residual), out.data_ptr(), rows, (int)N, N, ldr,
+                          out.stride(0), stream()),
+        "stage_reduce");
+  return out;
+}
+
 // adds this rank's partial product x[M, K_local] . w[N, K_local]^T into the peers' fp32 accumulators (row-blocks by owner)
 void gemm_reduce_scatter(const Tensor& x, const Tensor& w, const std::vector<int64_t>& acc_peers, int64_t ldacc,
                          const OptTensor& bias) {
@@ -611,6 +662,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("residual") = py::none(), py::arg("act") = "none");
   m.def("norm_quant", &norm_quant, py::arg("x"), py::arg("w"), py::arg("b") = py::none(), py::arg("eps") = 1e-5,
         py::arg("rms") = false);
+  m.def("gemm_flagged", &gemm_flagged, py::arg("a"), py::arg("w"), py::arg("bias"), py::arg("act"), py::arg("flags"),
+        py::arg("epoch"), py::arg("rows_per_flag"), py::arg("first_chunk"));
+  m.def("gemm_stage_scatter", &gemm_stage_scatter, py::arg("x"), py::arg("w"), py::arg("stage_peers"), py::arg("rank"),
+        py::arg("ldstage"), py::arg("bias") = py::none());
+  m.def("stage_reduce", &stage_reduce, py::arg("stage"), py::arg("bias") = py::none(), py::arg("residual") = py::none());
   m.def("gemm_ex", &gemm_ex, py::arg("a"), py::arg("b"), py::arg("a_mn") = false, py::arg("b_mn") = false,
         py::arg("out_f32") = false, py::arg("split_k") = -1);
   m.def("lmhead_tiles", [](int64_t n) { return (int64_t)b200_lmhead_tiles((int)n); }, py::arg("vocab"));

@@ -71,6 +71,22 @@ struct ReduceScatterEpilogue {
   float* acc[MAX_TP];
   long long ldacc;
   int rows_per_rank;
+  // staged variant (tensor-parallel GEMM -> reduce-scatter): instead of fp32 atomics into the owner's accumulator, each rank
+  // writes its bf16 partial tile into slot `src_rank` of the owner's staging buffer [world, rows_per_rank, ldstage] with plain
+  // 16-byte stores (half the NVLink bytes, no remote atomics); the owner sums the slots afterwards.
+  __nv_bfloat16* stage[MAX_TP];
+  long long ldstage;
+  int src_rank;
+};
+
+// Row-chunk readiness of the A operand (all-gather -> GEMM): rows [c*rows_per_flag, (c+1)*rows_per_flag) of A may be read once
+// flags[c] == epoch (set by the stream that copies peer shards into the local gathered buffer).  m_rot rotates the M-tile order
+// so every rank starts on its own (already local) shard while the copies of the others are in flight.
+struct AReady {
+  const uint32_t* flags;
+  uint32_t epoch;
+  int rows_per_flag;
+  int m_rot;
 };
 
 struct LMHeadEpilogue {
@@ -369,7 +385,10 @@ __device__ __forceinline__ void epilogue_cols(uint32_t taddr_row, int row, bool 
     }
   } else if constexpr (EPI == 2) {
     const int owner = row_ok ? row / re.rows_per_rank : 0;
-    float* dst_row = row_ok ? re.acc[owner] + (size_t)(row - owner * re.rows_per_rank) * re.ldacc : nullptr;
+    const bool staged = re.stage[0] != nullptr;
+    float* dst_row = (row_ok && !staged) ? re.acc[owner] + (size_t)(row - owner * re.rows_per_rank) * re.ldacc : nullptr;
+    __nv_bfloat16* stg_row = (row_ok && staged)
+        ? re.stage[owner] + ((size_t)re.src_rank * re.rows_per_rank + (row - owner * re.rows_per_rank)) * re.ldstage : nullptr;
 #pragma unroll 1
     for (int c = c_lo; c < c_hi; c += 16) {
       uint32_t r[16];
@@ -377,6 +396,27 @@ __device__ __forceinline__ void epilogue_cols(uint32_t taddr_row, int row, bool 
       tmem_ld_wait();
       const int col0 = n0 + c;
       if (!row_ok || col0 >= N) continue;
+      if (staged) {
+        if (col0 + 16 <= N && (re.ldstage & 7) == 0) {
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+          if (se.bias) {  // the rank that holds the (row-parallel) bias folds it into its partial
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += __bfloat162float(se.bias[col0 + j]);
+          }
+          uint4 pk[2];
+          pack16(v, pk);
+          *reinterpret_cast<uint4*>(stg_row + col0) = pk[0];
+          *reinterpret_cast<uint4*>(stg_row + col0 + 8) = pk[1];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (col0 + j < N)
+              stg_row[col0 + j] = __float2bfloat16(__uint_as_float(r[j]) + (se.bias ? __bfloat162float(se.bias[col0 + j]) : 0.f));
+        }
+        continue;
+      }
       if (col0 + 16 <= N && (re.ldacc & 3) == 0) {
         float v[16];
 #pragma unroll
@@ -483,7 +523,7 @@ template <int BN, int EPI, int AMN = 0, int BMN = 0, int TBM = 128, int FP8 = 0>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ MapArray maps_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_out, int M, int N, int K, int stages, int rows_per_map,
-               StoreEpilogue se, LMHeadEpilogue le, ReduceScatterEpilogue re, int k_splits) {
+               StoreEpilogue se, LMHeadEpilogue le, ReduceScatterEpilogue re, int k_splits, AReady ar) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int BKE = FP8 ? 2 * BK : BK;            // elements per k-block (128 bytes per row either way)
   static_assert(!FP8 || (!AMN && !BMN), "fp8 operands are K-major");
@@ -550,7 +590,12 @@ gemm_tn_kernel(const __grid_constant__ MapArray maps_a, const __grid_constant__ 
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
         const int tile = w % total_tiles, split = w / total_tiles;
         const int kb_lo = split * kb_per, kb_hi = min(nkb, kb_lo + kb_per);
-        const int m0 = (tile % m_tiles) * TBM, n0 = (tile / m_tiles) * BN;
+        const int m0 = (((tile % m_tiles) + ar.m_rot) % m_tiles) * TBM, n0 = (tile / m_tiles) * BN;
+        if (ar.flags) {  // the shard holding these rows has landed in the local gathered buffer
+          const uint32_t* f = ar.flags + m0 / ar.rows_per_flag;
+          while (ld_acquire_sys(f) != ar.epoch) {}
+          __threadfence();
+        }
         // which peer's copy of A holds this M-tile (all-gather -> GEMM); plain GEMMs have a single map
         const int a_map = m0 / rows_per_map;
         const int a_row = m0 - a_map * rows_per_map;
@@ -620,7 +665,7 @@ gemm_tn_kernel(const __grid_constant__ MapArray maps_a, const __grid_constant__ 
     for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tcount) {
       const int tile = w % total_tiles;
       const uint32_t as = tcount & 1, aphase = (tcount >> 1) & 1;
-      const int m_idx = tile % m_tiles, n_idx = tile / m_tiles;
+      const int m_idx = ((tile % m_tiles) + ar.m_rot) % m_tiles, n_idx = tile / m_tiles;
       constexpr int ROWS_PER_WARP = TBM / 4;  // 32, or 16 valid lanes per quadrant for 64-row tiles
       const int row = m_idx * TBM + q * ROWS_PER_WARP + lane;
       const bool row_ok = row < M && lane < ROWS_PER_WARP;
@@ -920,7 +965,7 @@ static int pick_bn(int M, int N) {
 template <int BN, int EPI, int AMN = 0, int BMN = 0, int TBM = 128, int FP8 = 0>
 static cudaError_t launch(const MapArray& ma, const CUtensorMap& mb, const CUtensorMap& mo, int M, int N, int K,
                           int rows_per_map, const StoreEpilogue& se, const LMHeadEpilogue& le,
-                          const ReduceScatterEpilogue& re, cudaStream_t stream, int k_splits = 1) {
+                          const ReduceScatterEpilogue& re, cudaStream_t stream, int k_splits = 1, AReady ar = AReady{}) {
   constexpr int stage_bytes = TBM * BK * 2 + BN * BK * 2;
   constexpr int fixed_bytes = NUM_EPI_WARPS * STG_BYTES + 1024 /*alignment slack*/ + 512 /*barriers*/;
   const int nkb = (K + (FP8 ? 2 * BK : BK) - 1) / (FP8 ? 2 * BK : BK);
@@ -937,7 +982,7 @@ static cudaError_t launch(const MapArray& ma, const CUtensorMap& mb, const CUten
   }
   const long long tiles = (long long)((N + BN - 1) / BN) * ((M + TBM - 1) / TBM) * k_splits;
   dim3 grid((unsigned)(tiles < num_sms() ? tiles : num_sms()));  // persistent: one CTA per SM walks the tile list
-  return launch_kernel(kern, grid, dim3(NUM_THREADS), smem, stream, ma, mb, mo, M, N, K, stages, rows_per_map, se, le, re, k_splits);
+  return launch_kernel(kern, grid, dim3(NUM_THREADS), smem, stream, ma, mb, mo, M, N, K, stages, rows_per_map, se, le, re, k_splits, ar);
 }
 
 // Route a bf16 [M, N] output (row pitch ldo) through the TMA-store epilogue when the pitch allows a tensor map.
@@ -1231,6 +1276,34 @@ extern "C" int b200_lmhead_dlogits_bf16(const void* A, const void* B, void* out,
   return (int)e;
 }
 
+// GEMM over a LOCAL gathered A [M, K] whose row shards become valid one by one (all-gather overlapped with the GEMM): see
+// AReady.  flags: uint32 [M / rows_per_flag] in device memory; rows_per_flag % 128 == 0.
+extern "C" int b200_gemm_flagged_bf16(const void* A, const void* B, void* out, int M, int N, int K, long long lda, long long ldb,
+                                      long long ldo, const void* bias, int act, const uint32_t* flags, uint32_t epoch,
+                                      int rows_per_flag, int first_chunk, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if (rows_per_flag % BM) return -3;
+  const int bn = pick_bn(M, N);
+  MapArray ma{};
+  CUtensorMap mb;
+  if (!make_map(&ma.m[0], A, M, K, lda, BM) || !make_map(&mb, B, N, K, ldb, bn)) return -1;
+  StoreEpilogue se{out, (const __nv_bfloat16*)bias, nullptr, nullptr, ldo, 0, 1.0f, act, 0};
+  CUtensorMap mo{};
+  if (!setup_tma_store(se, &mo, M, N, bn)) return -1;
+  LMHeadEpilogue le{};
+  ReduceScatterEpilogue re{};
+  AReady ar{flags, epoch, rows_per_flag, first_chunk * (rows_per_flag / BM)};
+  const int rpm = 1 << 30;
+  cudaError_t e;
+  switch (bn) {
+    case 256: e = launch<256, 0>(ma, mb, mo, M, N, K, rpm, se, le, re, stream, 1, ar); break;
+    case 128: e = launch<128, 0>(ma, mb, mo, M, N, K, rpm, se, le, re, stream, 1, ar); break;
+    case 64: e = launch<64, 0>(ma, mb, mo, M, N, K, rpm, se, le, re, stream, 1, ar); break;
+    default: e = launch<32, 0>(ma, mb, mo, M, N, K, rpm, se, le, re, stream, 1, ar); break;
+  }
+  return (int)e;
+}
+
 // all-gather -> GEMM: A is sharded by rows over `world` peers (A_peers[r] = peer r's [M/world, K] shard, any of them may
 // be a remote NVLink-mapped pointer); out[M, N] = act(concat_r(A_r) . B^T + bias).  rows_per_rank % 128 == 0.
 extern "C" int b200_gemm_allgather_bf16(void* const* A_peers, int world, const void* B, void* out, int M, int N, int K,
@@ -1282,6 +1355,82 @@ extern "C" int b200_gemm_reduce_scatter_bf16(const void* A, const void* B, float
   const int rpm = 1 << 30;
   cudaError_t e;
   switch (bn) {
+    case 128: e = launch<128, 2>(ma, mb, mo, M, N, K, rpm, se, le, re, stream); break;
+    case 64: e = launch<64, 2>(ma, mb, mo, M, N, K, rpm, se, le, re, stream); break;
+    default: e = launch<32, 2>(ma, mb, mo, M, N, K, rpm, se, le, re, stream); break;
+  }
+  return (int)e;
+}
+
+// Sum the `world` bf16 partial slots of a staged reduce-scatter (+ bias + residual) -> bf16.  8 elements per thread.
+__global__ void stage_reduce_kernel(const __nv_bfloat16* __restrict__ stage, int world, long long slot_elems,
+                                    const __nv_bfloat16* __restrict__ bias, const __nv_bfloat16* __restrict__ residual,
+                                    __nv_bfloat16* __restrict__ out, long long rows, int N, long long ldstage, long long ldr,
+                                    long long ldo) {
+  const int nv = N >> 3;
+  const long long total = rows * nv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / nv;
+    const int c = (int)(i - r * nv) * 8;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int w = 0; w < world; ++w) {
+      const uint4 v = *reinterpret_cast<const uint4*>(stage + w * slot_elems + r * ldstage + c);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(h[j]); acc[2 * j] += f.x; acc[2 * j + 1] += f.y; }
+    }
+    if (bias) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += __bfloat162float(bias[c + j]);
+    }
+    if (residual) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += __bfloat162float(residual[r * ldr + c + j]);
+    }
+    uint4 o;
+    __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(acc[2 * j], acc[2 * j + 1]);
+    *reinterpret_cast<uint4*>(out + r * ldo + c) = o;
+  }
+}
+
+extern "C" int b200_stage_reduce(const void* stage, int world, const void* bias, const void* residual, void* out, long long rows,
+                                 int N, long long ldstage, long long ldr, long long ldo, cudaStream_t stream) {
+  if (rows <= 0) return 0;
+  if (N % 8 || ldstage % 8 || ldo % 8) return -3;
+  long long blocks = (rows * (N / 8) + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  stage_reduce_kernel<<<(int)blocks, 256, 0, stream>>>((const __nv_bfloat16*)stage, world, rows * ldstage,
+                                                       (const __nv_bfloat16*)bias, (const __nv_bfloat16*)residual,
+                                                       (__nv_bfloat16*)out, rows, N, ldstage, ldr, ldo);
+  return (int)cudaGetLastError();
+}
+
+// GEMM -> staged reduce-scatter: out partial tiles (bf16) are stored into slot `rank` of every owner's staging buffer
+// stage_peers[owner] ([world, M/world, ldstage] bf16, peer-mapped).  Follow with a barrier and b200_stage_reduce on the owner.
+extern "C" int b200_gemm_stage_scatter_bf16(const void* A, const void* B, void* const* stage_peers, int world, int rank, int M,
+                                            int N, int K, long long lda, long long ldb, long long ldstage, const void* bias,
+                                            cudaStream_t stream) {
+  if (world < 1 || world > MAX_TP || M % world) return -3;
+  int bn = pick_bn(M, N);
+  MapArray ma{};
+  CUtensorMap mb, mo{};
+  if (!make_map(&ma.m[0], A, M, K, lda, BM) || !make_map(&mb, B, N, K, ldb, bn)) return -1;
+  StoreEpilogue se{};
+  se.bias = (const __nv_bfloat16*)bias;
+  LMHeadEpilogue le{};
+  ReduceScatterEpilogue re{};
+  for (int r = 0; r < world; ++r) re.stage[r] = (__nv_bfloat16*)stage_peers[r];
+  re.ldstage = ldstage;
+  re.src_rank = rank;
+  re.rows_per_rank = M / world;
+  const int rpm = 1 << 30;
+  cudaError_t e;
+  switch (bn) {
+    case 256: e = launch<256, 2>(ma, mb, mo, M, N, K, rpm, se, le, re, stream); break;
     case 128: e = launch<128, 2>(ma, mb, mo, M, N, K, rpm, se, le, re, stream); break;
     case 64: e = launch<64, 2>(ma, mb, mo, M, N, K, rpm, se, le, re, stream); break;
     default: e = launch<32, 2>(ma, mb, mo, M, N, K, rpm, se, le, re, stream); break;

@@ -1,16 +1,18 @@
 """Fused tensor-parallel GEMM ↔ collective operations over NVLink peer memory.
 
-* :meth:`FusedTP.allgather_gemm` — the sequence-sharded activation of every rank lives in a symmetric buffer; ONE kernel
-  computes ``concat_r(x_r) · Wᵀ`` by streaming the A-operand tiles of row-block ``r`` straight out of peer ``r``'s HBM
-  with TMA into the tcgen05 pipeline (no materialised all-gather).
-* :meth:`FusedTP.gemm_reduce_scatter` — every rank's partial product tile is added from the GEMM epilogue into the fp32
-  accumulator of the rank that owns those rows with ``red.global.add.v4.f32`` over NVLink (no separate reduce-scatter).
+* :meth:`FusedTP.allgather_gemm` — the sequence-sharded activation of every rank lives in a symmetric buffer; ONE GEMM
+  kernel computes ``concat_r(x_r) · Wᵀ`` while the peers' shards are still being copied into the local gathered buffer:
+  its TMA producer starts on the local shard and gates each remote shard on a device-side ready flag.
+* :meth:`FusedTP.gemm_reduce_scatter` — every rank's partial product tile goes from the GEMM epilogue straight into the
+  owner's staging slot over NVLink (bf16, 16-byte stores) as soon as its accumulator completes; the owner sums the slots.
+  (Earlier variants — remote TMA loads per tile, fp32 ``red.global.add`` — are kept behind environment switches.)
 
 Ordering between ranks uses the device-side flag barrier of ``csrc/optim.cu`` on the buffers' signal pads.  Backward
 passes use ``torch.distributed`` collectives (library path).
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -23,6 +25,7 @@ class FusedTP:
     def __init__(self, group, rank: int, size: int, device: torch.device):
         self.group, self.rank, self.size, self.device = group, rank, size, device
         self._bufs: Dict[Tuple, Tuple[torch.Tensor, object]] = {}
+        self._local: Dict[Tuple, Tuple[torch.Tensor, torch.Tensor]] = {}
         self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
         self._pads = None
 
@@ -46,26 +49,68 @@ class FusedTP:
         return rows_per_rank % 128 == 0 and k % 8 == 0 and n % 8 == 0
 
     def allgather_gemm(self, x_local: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act: str = "none"):
-        """``x_local`` ``[m, K]`` (this rank's sequence shard) → ``[m·size, N]`` = act(all_gather(x) · wᵀ + bias)."""
+        """``x_local`` ``[m, K]`` (this rank's sequence shard) → ``[m·size, N]`` = act(all_gather(x) · wᵀ + bias).
+
+        Every remote byte crosses NVLink exactly once: the peers' shards are pulled into a local gathered buffer by copies
+        on a side stream (rank+1 first, …) while ONE GEMM kernel is already running on the main stream — its TMA producer
+        starts on this rank's own shard and waits on a per-shard ready flag (device memory, acquire load) before touching the
+        rows of a shard that is still in flight.  (The first version read remote tiles straight out of the peers' HBM with
+        per-peer tensor maps; remote reads are not cached in the local L2, so every N-tile re-fetched its A rows over the
+        link — 5x slower than NCCL + cuBLAS at TP = 4.  ``TRLX_B200_TP_REMOTE_TMA=1`` keeps that variant for comparison.)"""
         m, K = x_local.shape
         buf, hdl = self._symm(("ag", m, K), (m, K), torch.bfloat16)
         buf.copy_(x_local)
         self.barrier()  # every rank's shard is in place
-        out = ops.C.gemm_allgather(list(hdl.buffer_ptrs), m, K, K, w, bias, act)
+        if os.environ.get("TRLX_B200_TP_REMOTE_TMA") == "1":
+            out = ops.C.gemm_allgather(list(hdl.buffer_ptrs), m, K, K, w, bias, act)
+            self.barrier()
+            return out
+        key = ("ag_full", m, K)
+        if key not in self._local:
+            self._local[key] = (torch.empty(self.size * m, K, dtype=torch.bfloat16, device=self.device),
+                                torch.zeros(self.size, dtype=torch.int32, device=self.device))
+            self._copy_stream = getattr(self, "_copy_stream", None) or torch.cuda.Stream(device=self.device)
+        full, flags = self._local[key]
+        self._epoch_host = getattr(self, "_epoch_host", 0) + 1
+        ep = self._epoch_host
+        main = torch.cuda.current_stream()
+        full[self.rank * m:(self.rank + 1) * m].copy_(x_local)
+        flags[self.rank:self.rank + 1].fill_(ep)
+        side = self._copy_stream
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            for d in range(1, self.size):
+                r = (self.rank + d) % self.size
+                peer = hdl.get_buffer(r, (m, K), torch.bfloat16)
+                full[r * m:(r + 1) * m].copy_(peer, non_blocking=True)
+                flags[r:r + 1].fill_(ep)
+        out = ops.C.gemm_flagged(full, w, bias, act, flags, ep, m, self.rank)
+        main.wait_stream(side)
         self.barrier()  # all peers finished reading before the buffer is reused
         return out
 
     def gemm_reduce_scatter(self, x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
                             residual: Optional[torch.Tensor] = None):
-        """``x`` ``[M, K_local]``, ``w`` ``[N, K_local]`` → this rank's ``[M/size, N]`` rows of Σ_ranks x·wᵀ (+bias) (+residual)."""
+        """``x`` ``[M, K_local]``, ``w`` ``[N, K_local]`` → this rank's ``[M/size, N]`` rows of Σ_ranks x·wᵀ (+bias) (+residual).
+
+        The GEMM epilogue stores each bf16 partial tile straight into slot ``rank`` of the OWNER's staging buffer over NVLink
+        (16-byte stores, tile by tile as the accumulators complete), and the owner sums its ``size`` slots afterwards.  (The
+        first version used fp32 ``red.global.add`` into the owner's accumulator: twice the bytes and remote atomics — 3x slower
+        than cuBLAS + NCCL at TP = 4; ``TRLX_B200_TP_RED_ADD=1`` keeps it for comparison.)"""
         M, N = x.shape[0], w.shape[0]
         rows = M // self.size
-        acc, hdl = self._symm(("rs", rows, N), (rows, N), torch.float32)
-        acc.zero_()
-        self.barrier()  # accumulators are clean everywhere
-        ops.C.gemm_reduce_scatter(x, w, list(hdl.buffer_ptrs), N, bias)
-        self.barrier()  # every partial sum has landed
-        return ops.C.rs_finalize(acc, None, residual)
+        if os.environ.get("TRLX_B200_TP_RED_ADD") == "1" or N % 8:
+            acc, hdl = self._symm(("rs", rows, N), (rows, N), torch.float32)
+            acc.zero_()
+            self.barrier()  # accumulators are clean everywhere
+            ops.C.gemm_reduce_scatter(x, w, list(hdl.buffer_ptrs), N, bias)
+            self.barrier()  # every partial sum has landed
+            return ops.C.rs_finalize(acc, None, residual)
+        stage, hdl = self._symm(("rs_stage", rows, N), (self.size, rows, N), torch.bfloat16)
+        self.barrier()  # the previous consumer of the staging slots is done
+        ops.C.gemm_stage_scatter(x, w, list(hdl.buffer_ptrs), self.rank, N, bias)  # bias: real on one rank, zeros elsewhere
+        self.barrier()  # every rank's partial tiles have landed
+        return ops.C.stage_reduce(stage, None, residual)
 
 
 class _ColumnLinearFused(torch.autograd.Function):
@@ -138,4 +183,5 @@ def column_linear(fused: FusedTP, linear, x):
 
 
 def row_linear(fused: FusedTP, linear, x):
-    return _RowLinearFused.apply(x, linear.weight, linear.bias if fused.rank == 0 else None, fused)
+    # the row-parallel bias is real on one rank and zero on the others (tensor_parallel._shard_cols): every rank may add "its" bias
+    return _RowLinearFused.apply(x, linear.weight, linear.bias, fused)
