@@ -703,7 +703,7 @@ gemm_tn_kernel(const __grid_constant__ MapArray maps_a, const __grid_constant__ 
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                 const __grid_constant__ CUtensorMap map_out, int M, int N, int K, int stages, StoreEpilogue se) {
+                 const __grid_constant__ CUtensorMap map_out, int M, int N, int K, int stages, StoreEpilogue se, AReady ar) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int HB = BN / 2;                          // B rows staged by each CTA
   constexpr uint32_t A_BYTES = BM * BK * 2;
@@ -761,8 +761,13 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (lane == 0) {
       uint32_t it = 0;
       for (int tile = pair; tile < total_tiles; tile += n_pairs) {
-        const int m0 = (tile % m_tiles) * 2 * BM + (int)cta * BM;  // this CTA's 128 rows of A
-        const int n0 = (tile / m_tiles) * BN + (int)cta * HB;      // ... and its half of the B tile
+        const int m0 = (((tile % m_tiles) + ar.m_rot) % m_tiles) * 2 * BM + (int)cta * BM;  // this CTA's 128 rows of A
+        const int n0 = (tile / m_tiles) * BN + (int)cta * HB;                               // ... and its half of the B tile
+        if (ar.flags) {  // all-gather -> GEMM: the shard holding these rows has landed (see AReady)
+          const uint32_t* f = ar.flags + m0 / ar.rows_per_flag;
+          while (ld_acquire_sys(f) != ar.epoch) {}
+          __threadfence();
+        }
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % stages;
           const uint32_t phase = (it / stages) & 1;
@@ -813,7 +818,7 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     uint32_t tcount = 0;
     for (int tile = pair; tile < total_tiles; tile += n_pairs, ++tcount) {
       const uint32_t as = tcount & 1, aphase = (tcount >> 1) & 1;
-      const int m_idx = tile % m_tiles, n_idx = tile / m_tiles;
+      const int m_idx = ((tile % m_tiles) + ar.m_rot) % m_tiles, n_idx = tile / m_tiles;
       const int row0 = m_idx * 2 * BM + (int)cta * BM + q * 32;
       const int row = row0 + lane;
       const bool row_ok = row < M;
@@ -1008,6 +1013,40 @@ extern "C" void b200_set_pdl(int on) { set_pdl_enabled(on != 0); }
 extern "C" int b200_get_pdl() { return pdl_enabled() ? 1 : 0; }
 
 // act: 0 none, 1 gelu_tanh, 2 gelu_erf, 3 relu, 4 silu.  Requirements: K % 8 == 0, lda/ldb % 8 == 0, 16B-aligned A/B.
+// ---- CTA-pair launch (shared by the plain and the all-gather-flagged entry points)
+static bool cta_pair_eligible(int M, int N, int K, const void* out, long long ldo, bool forced) {
+  static const bool allow = getenv("B200_GEMM_NO_2CTA") == nullptr;
+  const long long t2 = (long long)((M + 255) / 256) * ((N + 255) / 256);
+  if (!(allow || forced) || (ldo % 8) || (reinterpret_cast<uintptr_t>(out) & 15)) return false;
+  // measured: +6 % at K >= 4096, neutral at K = 768 (run22)
+  return forced || getenv("B200_GEMM_2CTA") != nullptr || (t2 >= num_sms() && K >= 1024);
+}
+
+static int launch_cta_pair(const void* A, const void* B, int M, int N, int K, long long lda, long long ldb, StoreEpilogue s2,
+                           AReady ar, cudaStream_t stream) {
+  CUtensorMap m2a, m2b, m2o{};
+  if (!make_map(&m2a, A, M, K, lda, BM) || !make_map(&m2b, B, N, K, ldb, 128)) return -1;
+  if (!setup_tma_store(s2, &m2o, M, N, 256)) return -1;
+  constexpr int BN2 = 256;
+  constexpr int stage_bytes = BM * BK * 2 + (BN2 / 2) * BK * 2;
+  constexpr int fixed_bytes = NUM_EPI_WARPS * STG_BYTES + 1024 + 512;
+  int stages = (227 * 1024 - fixed_bytes) / stage_bytes;
+  if (stages > 8) stages = 8;
+  const int nkb2 = (K + BK - 1) / BK;
+  if (stages > nkb2) stages = nkb2 < 2 ? 2 : nkb2;
+  auto kern = gemm_2cta_kernel<BN2>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -5;
+    configured = true;
+  }
+  const long long t2 = (long long)((M + 255) / 256) * ((N + 255) / 256);
+  long long pairs = t2 < num_sms() / 2 ? t2 : num_sms() / 2;
+  dim3 grid((unsigned)(2 * pairs));
+  const size_t smem = (size_t)stages * stage_bytes + fixed_bytes;
+  return (int)launch_kernel_cluster(kern, grid, dim3(NUM_THREADS), smem, stream, 2u, m2a, m2b, m2o, M, N, K, stages, s2, ar);
+}
+
 struct LnFold {
   const float* stats_in = nullptr;  // [M, 2] (sum, sum sq) of the raw A rows
   const float* c1 = nullptr;        // [N]
@@ -1044,34 +1083,12 @@ static int gemm_bf16_impl(const void* A, const void* B, void* out, int M, int N,
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   const int bn = force_bn > 0 ? force_bn : pick_bn(M, N);
   // CTA-pair kernel for the large-GEMM regime: plenty of 256x256 tiles and nothing but a plain bf16 store epilogue
-  static const bool allow_2cta = getenv("B200_GEMM_NO_2CTA") == nullptr;
   {
-    const long long t2 = (long long)((M + 255) / 256) * ((N + 255) / 256);
     const bool force2 = force_bn == -2;
-    if ((allow_2cta || force2) && (force_bn == 0 || force2) && !out_f32 && !col_scale && !ln.stats_in && !ln.stats_out &&
-        (ldo % 8) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (force2 || getenv("B200_GEMM_2CTA") != nullptr || (t2 >= num_sms() && K >= 1024))) {  // measured: +6 % at K >= 4096, neutral at K = 768 (run22)
-      CUtensorMap m2a, m2b, m2o{};
-      if (!make_map(&m2a, A, M, K, lda, BM) || !make_map(&m2b, B, N, K, ldb, 128)) return -1;
+    if ((force_bn == 0 || force2) && !out_f32 && !col_scale && !ln.stats_in && !ln.stats_out &&
+        cta_pair_eligible(M, N, K, out, ldo, force2)) {
       StoreEpilogue s2{out, (const __nv_bfloat16*)bias, (const __nv_bfloat16*)residual, nullptr, ldo, ldr, alpha, act, 0};
-      if (!setup_tma_store(s2, &m2o, M, N, 256)) return -1;
-      constexpr int BN2 = 256;
-      constexpr int stage_bytes = BM * BK * 2 + (BN2 / 2) * BK * 2;
-      constexpr int fixed_bytes = NUM_EPI_WARPS * STG_BYTES + 1024 + 512;
-      int stages = (227 * 1024 - fixed_bytes) / stage_bytes;
-      if (stages > 8) stages = 8;
-      const int nkb2 = (K + BK - 1) / BK;
-      if (stages > nkb2) stages = nkb2 < 2 ? 2 : nkb2;
-      auto kern = gemm_2cta_kernel<BN2>;
-      static bool configured = false;
-      if (!configured) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -5;
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 0) != cudaSuccess) cudaGetLastError();
-        configured = true;
-      }
-      long long pairs = t2 < num_sms() / 2 ? t2 : num_sms() / 2;
-      dim3 grid((unsigned)(2 * pairs));
-      const size_t smem = (size_t)stages * stage_bytes + fixed_bytes;
-      return (int)launch_kernel_cluster(kern, grid, dim3(NUM_THREADS), smem, stream, 2u, m2a, m2b, m2o, M, N, K, stages, s2);
+      return launch_cta_pair(A, B, M, N, K, lda, ldb, s2, AReady{}, stream);
     }
   }
   // 64-row tiles when even 128x32 tiles leave more than half of the SMs idle (decode: M = batch <= 128)
@@ -1283,6 +1300,11 @@ extern "C" int b200_gemm_flagged_bf16(const void* A, const void* B, void* out, i
                                       int rows_per_flag, int first_chunk, cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if (rows_per_flag % BM) return -3;
+  if (rows_per_flag % (2 * BM) == 0 && cta_pair_eligible(M, N, K, out, ldo, false)) {
+    StoreEpilogue s2{out, (const __nv_bfloat16*)bias, nullptr, nullptr, ldo, 0, 1.0f, act, 0};
+    return launch_cta_pair(A, B, M, N, K, lda, ldb, s2, AReady{flags, epoch, rows_per_flag, first_chunk * (rows_per_flag / (2 * BM))},
+                           stream);
+  }
   const int bn = pick_bn(M, N);
   MapArray ma{};
   CUtensorMap mb;
