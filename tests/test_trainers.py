@@ -208,3 +208,12 @@ def test_train_argument_validation():
     with pytest.raises(ValueError):
         trlx.train(samples=["a", "b"], rewards=[1.0], config=default_ilql_config().evolve(
             train=dict(tracker=None), model=dict(model_path=GPT2), tokenizer=dict(tokenizer_path="toy://bytes")))
+
+
+def test_prompt_width_buckets():
+    from trlx_b200.trainer.accelerate_ppo_trainer import _bucket_prompt_width as bucket
+
+    assert [bucket(w) for w in (1, 8, 9, 16, 17, 33, 65, 129, 1000)] == [8, 8, 16, 16, 24, 40, 80, 160, 1024]
+    assert bucket(17, 32) == 32 and bucket(32, 32) == 32
+    for w in range(1, 2048):
+        assert w <= bucket(w) < max(w + 8, w * 1.25 + 1)

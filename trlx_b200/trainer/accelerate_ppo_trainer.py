@@ -47,6 +47,16 @@ def _is_config_like(obj) -> bool:
     return isinstance(obj, dict) or (hasattr(obj, "model_type") and not isinstance(obj, str)) or hasattr(obj, "family")
 
 
+def _bucket_prompt_width(width: int, fixed: Optional[int] = None) -> int:
+    """Padded prompt width used for rollouts.  CUDA graphs (decode step, prefill, training step) are keyed by shape, so
+    widths are quantised: a fixed ``prompt_bucket`` when configured, otherwise geometric buckets — multiples of
+    ``max(8, 2^floor(log2 w) / 4)`` — which keep the padding under 25 % and the number of distinct shapes logarithmic
+    in the longest prompt (8, 16, 24, 32, 40, ... 64, 80, 96, 112, 128, 160, ...)."""
+    width = max(int(width), 1)
+    step = int(fixed) if fixed else max(8, (1 << (width.bit_length() - 1)) // 4)
+    return -(-width // step) * step
+
+
 @register_trainer
 class AcceleratePPOTrainer(AccelerateRLTrainer):
     """PPO on the B200 runtime."""
@@ -373,8 +383,7 @@ class AcceleratePPOTrainer(AccelerateRLTrainer):
             t_gen = time()
             if engine is not None:
                 ids, am = batch["input_ids"], batch["attention_mask"]
-                bucket = int(self.config.train.trainer_kwargs.get("prompt_bucket", 32))
-                width = -(-ids.shape[1] // bucket) * bucket
+                width = _bucket_prompt_width(ids.shape[1], self.config.train.trainer_kwargs.get("prompt_bucket"))
                 if rt.distributed and rt.dp_size > 1:
                     # every data-parallel rank uses the same padded prompt width, so their rollout blocks — and therefore
                     # the CUDA-graph shape keys of the training step, whose capture runs cross-GPU barriers — line up
