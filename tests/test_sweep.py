@@ -85,3 +85,25 @@ def test_parallel_preset_env_overrides_config(monkeypatch, tmp_path):
         tokenizer=dict(tokenizer_path="toy://bytes"), method=dict(gen_kwargs=dict(max_new_tokens=2)))
     trainer = trlx.train(samples=["ab", "cd", "ef", "gh"], eval_prompts=["a"], config=cfg)
     assert trainer.config.train.parallel.zero_stage == 0 and trainer.config.train.parallel.grad_clip == 0.5
+
+
+def test_sweep_default_config_yaml_is_applied_under_sampled_hparams(tmp_path):
+    """``--default_config`` (reference ``trlx/sweep.py``): YAML sections are the defaults, sampled keys win."""
+    from trlx_b200 import sweep
+
+    script = tmp_path / "target.py"
+    script.write_text(
+        "import json, os\n"
+        "def main(hparams):\n"
+        "    from trlx_b200.data.configs import TRLConfig\n"
+        "    from trlx_b200.data.default_configs import default_sft_config\n"
+        "    cfg = TRLConfig.update(default_sft_config().to_dict(), hparams)\n"
+        "    with open(os.path.join(cfg.train.logging_dir, 'seen.json'), 'w') as fh:\n"
+        "        json.dump({'bs': cfg.train.batch_size, 'seq': cfg.train.seq_length, 'lr': cfg.optimizer.kwargs['lr']}, fh)\n")
+    default = tmp_path / "default.yml"
+    default.write_text("train:\n  batch_size: 3\n  seq_length: 77\noptimizer:\n  kwargs:\n    lr: 0.5\n")
+    tdir = tmp_path / "trial"
+    proc = sweep.launch_trial(str(script), {"train.batch_size": 5}, str(tdir), [], None, str(default))
+    assert proc.wait(timeout=120) == 0, (tdir / "stdout.log").read_text()
+    seen = json.loads((tdir / "seen.json").read_text())
+    assert seen == {"bs": 5, "seq": 77, "lr": 0.5}

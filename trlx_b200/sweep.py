@@ -118,17 +118,23 @@ mod.main(json.loads(sys.argv[2]))
 def launch_trial(script: str, hparams: Dict[str, Any], trial_dir: str, gpus: List[int], budget_steps: Optional[int],
                  default_config: Optional[str]) -> subprocess.Popen:
     os.makedirs(trial_dir, exist_ok=True)
-    hp = dict(hparams)
+    hp: Dict[str, Any] = {}
+    if default_config:  # YAML TRLConfig sections first, so that the sampled dotted keys override them
+        import yaml
+
+        with open(default_config) as fh:
+            hp.update({k: v for k, v in (yaml.safe_load(fh) or {}).items() if isinstance(v, dict)})
+    hp.update(hparams)
     hp.setdefault("train.tracker", "jsonl")
     hp.setdefault("train.logging_dir", trial_dir)
     hp.setdefault("train.checkpoint_dir", os.path.join(trial_dir, "ckpts"))
     if budget_steps is not None:
         hp["train.total_steps"] = int(budget_steps)
     env = dict(os.environ)
+    pkg_root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # trials import the same trlx_b200 as the sweep
+    env["PYTHONPATH"] = os.pathsep.join(p for p in (pkg_root, env.get("PYTHONPATH", "")) if p)
     if gpus:
         env["CUDA_VISIBLE_DEVICES"] = ",".join(str(g) for g in gpus)
-    if default_config:
-        env["TRLX_B200_DEFAULT_CONFIG"] = default_config
     with open(os.path.join(trial_dir, "hparams.json"), "w") as fh:
         json.dump(hparams, fh, indent=2, default=str)
     runner = os.path.join(trial_dir, "_run_trial.py")
