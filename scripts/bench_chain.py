@@ -72,6 +72,19 @@ def chain_norm():
     return fn
 
 
+down = [(torch.randn(H, 3072, device=dev) * 3072 ** -0.5).to(torch.bfloat16) for _ in range(n_w)]
+
+
+def chain_mlp(bn):
+    """fc (768 -> 3072, GELU) then fc2 (3072 -> 768): the two GEMMs of a decoder MLP, properly dependent."""
+    def fn():
+        y = x0
+        for Wu, Wd in zip(big, down):
+            y = C.gemm(C.gemm(y, Wu, None, None, "gelu_new", force_bn=bn), Wd, None, None, "none", force_bn=bn)
+        return y
+    return fn
+
+
 for pdl in (1, 0):
     C.set_pdl(bool(pdl))
     rec = {"pdl": pdl, "norm_us": round(timed_graph(chain_norm()) / n_w, 2)}
@@ -80,4 +93,10 @@ for pdl in (1, 0):
     for bn in (32, 64, 128):
         rec[f"qkv2304_bn{bn}_us"] = round(timed_graph(chain_qkv(bn, Wq)) / n_w, 2)
     rec["fc3072_bn32_us"] = round(timed_graph(chain_qkv(32, big)) / n_w, 2)
+    # cluster split-K (force_bn = -3) and the automatic choice (0) against the plain 128x32 kernel
+    for tag, bn in (("csk", -3), ("auto", 0)):
+        rec[f"sq768_{tag}_us"] = round(timed_graph(chain_square(bn)) / n_w, 2)
+        rec[f"qkv2304_{tag}_us"] = round(timed_graph(chain_qkv(bn, Wq)) / n_w, 2)
+        rec[f"mlp_pair_{tag}_us"] = round(timed_graph(chain_mlp(bn)) / n_w, 2)
+    rec["mlp_pair_bn32_us"] = round(timed_graph(chain_mlp(32)) / n_w, 2)
     print(json.dumps(rec), flush=True)

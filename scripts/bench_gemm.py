@@ -54,3 +54,21 @@ for name, M, N, K in shapes:
         rec["fused_lmhead_us"] = round(fused, 1)
         rec["fused_lmhead_tflops"] = round(fl / fused / 1e6, 1)
     print(json.dumps(rec), flush=True)
+
+# ---- backward shapes of the PPO update (MN-major operands, split-K): dX = dY·W and dW = dYᵀ·X per linear of a GPT-2 block at
+# 1792 tokens, plus the LM head at 1280 scored positions.  Run with `bwd` as the only argument (or no argument).
+if not only or "bwd" in only:
+    T = 1792
+    for name, n_out, k_in, rows in [("qkv", 2304, 768, T), ("proj", 768, 768, T), ("fc", 3072, 768, T), ("fc2", 768, 3072, T),
+                                    ("lmhead", 50304, 768, 1280)]:
+        dy, w, x = t(rows, n_out), t(n_out, k_in), t(rows, k_in)
+        dx_ours = timeit(lambda: C.gemm_ex(dy, w, False, True))
+        dx_lib = timeit(lambda: dy @ w)
+        dw_ours = timeit(lambda: C.gemm_ex(dy, x, True, True))
+        dw_lib = timeit(lambda: dy.t() @ x)
+        fl = 2.0 * rows * n_out * k_in
+        print(json.dumps(dict(shape="bwd_" + name, rows=rows, n_out=n_out, k_in=k_in,
+                              dx_splits=C.gemm_splitk_plan(rows, k_in, n_out) if hasattr(C, "gemm_splitk_plan") else None,
+                              dx_ours_us=round(dx_ours, 1), dx_cublas_us=round(dx_lib, 1), dw_ours_us=round(dw_ours, 1),
+                              dw_cublas_us=round(dw_lib, 1), dx_ours_tflops=round(fl / dx_ours / 1e6, 1),
+                              dw_ours_tflops=round(fl / dw_ours / 1e6, 1))), flush=True)

@@ -669,6 +669,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("stage_reduce", &stage_reduce, py::arg("stage"), py::arg("bias") = py::none(), py::arg("residual") = py::none());
   m.def("gemm_ex", &gemm_ex, py::arg("a"), py::arg("b"), py::arg("a_mn") = false, py::arg("b_mn") = false,
         py::arg("out_f32") = false, py::arg("split_k") = -1);
+  m.def("gemm_splitk_plan", [](int64_t m, int64_t n, int64_t k) { return (int64_t)b200_gemm_splitk_plan((int)m, (int)n, (int)k); },
+        py::arg("m"), py::arg("n"), py::arg("k"));
   m.def("lmhead_tiles", [](int64_t n) { return (int64_t)b200_lmhead_tiles((int)n); }, py::arg("vocab"));
   m.def("lmhead_dlogits", &lmhead_dlogits, py::arg("h"), py::arg("w"), py::arg("bias"), py::arg("labels"), py::arg("lse"),
         py::arg("grad"));

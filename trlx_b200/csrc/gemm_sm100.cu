@@ -280,11 +280,15 @@ __device__ __forceinline__ void pack16(const float (&v)[16], uint4 (&pk)[2]) {
 // Epilogue bodies: one output row per thread, columns [c_lo, c_hi) of the current tile's accumulator.
 //   stg      : this warp's 4 KB shared-memory staging buffer (TMA-store path)
 //   map_out  : tensor map of the bf16 output (TMA-store path; box = CW columns x 32 rows, swizzle = CW*2 bytes)
-template <int EPI, int CW>
+//   CSK      : cluster split-K leader — `csk_parts` fp32 partial tiles written by the other CTAs of the cluster into this
+//              CTA's shared memory ([chunk of 16 columns][4 x 16-byte unit][lane], `csk_stride` bytes per partial, base
+//              `csk_base` already offset to this warp) are added to the accumulator before the epilogue math
+template <int EPI, int CW, int CSK = 0>
 __device__ __forceinline__ void epilogue_cols(uint32_t taddr_row, int row, bool row_ok, int n0, int c_lo, int c_hi, int N,
                                               int part_idx, const StoreEpilogue& se, const LMHeadEpilogue& le,
                                               const ReduceScatterEpilogue& re, uint8_t* stg, const CUtensorMap* map_out,
-                                              int row0_warp, int lane) {
+                                              int row0_warp, int lane, uint32_t csk_base = 0, int csk_parts = 0,
+                                              uint32_t csk_stride = 0) {
   if constexpr (EPI == 0) {
     RowCtx rc{se.dl_lse != nullptr, 0.f, 0.f, -1, 1.f, 0.f, 1.f};
     if (se.row_scale && row_ok) rc.row_scale = se.row_scale[row];
@@ -318,6 +322,20 @@ __device__ __forceinline__ void epilogue_cols(uint32_t taddr_row, int row, bool 
       uint32_t r[16];
       tmem_ld16(taddr_row + c, r);
       tmem_ld_wait();
+      if constexpr (CSK) {
+        const uint32_t chunk = csk_base + (uint32_t)((c - c_lo) >> 4) * 2048u + (uint32_t)lane * 16u;
+#pragma unroll 1
+        for (int p = 0; p < csk_parts; ++p) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 t = ld_shared_v4f(chunk + (uint32_t)p * csk_stride + (uint32_t)j * 512u);
+            r[4 * j + 0] = __float_as_uint(__uint_as_float(r[4 * j + 0]) + t.x);
+            r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) + t.y);
+            r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + t.z);
+            r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + t.w);
+          }
+        }
+      }
       float v[16];
       const bool full = col0 + 16 <= N;
       if (full) store_values_full(r, v, row_ok ? row : 0, col0, se, rc, vec_in, row_ok);
@@ -688,6 +706,143 @@ gemm_tn_kernel(const __grid_constant__ MapArray maps_a, const __grid_constant__ 
   }
 }
 
+// ---------------------------------------------------------------------------------------------- cluster split-K GEMM
+// Decode-shaped GEMMs (M <= 128: ONE row tile, a few dozen column tiles, K = 768 ... 8192) are latency bound: every CTA of
+// the plain kernel pulls the whole [128, K] activation panel through the ~50 B/clk L2 -> SMEM path while most SMs idle.
+// Here a CLUSTER of S CTAs owns one 128 x BN output tile and CTA r multiplies k-blocks [r*per, (r+1)*per): each SM moves
+// 1/S of the panel.  The fp32 partial tiles of ranks 1..S-1 go straight from TMEM (tcgen05.ld) into rank 0's shared memory
+// through distributed shared memory (st.shared::cluster), one split cluster barrier publishes them, and rank 0 adds them to
+// its own accumulator inside the ordinary store epilogue (bias / activation / residual / folded norm / TMA store).
+// One tile per cluster, no persistence: the grid is (tiles * S) CTAs and the host only picks S so that all clusters are
+// co-resident (cudaOccupancyMaxActiveClusters).
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_csk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                const __grid_constant__ CUtensorMap map_out, int M, int N, int K, int stages, StoreEpilogue se) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr uint32_t A_BYTES = BM * BK * 2;
+  constexpr uint32_t B_BYTES = BN * BK * 2;
+  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t ACC_COLS = BN < 32 ? 32 : BN;
+  constexpr int HALF = BN / 2;
+  constexpr int CW = HALF < 64 ? HALF : 64;
+  constexpr uint32_t PART_BYTES = BN * 512;            // one fp32 128 x BN partial tile
+  constexpr uint32_t WARP_PART = (HALF / 16) * 2048;   // the slice of it one epilogue warp owns
+
+  const uint32_t S = cluster_nctarank(), rank = cluster_ctarank();
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stage_out = smem + (size_t)stages * STAGE_BYTES;
+  uint8_t* parts = stage_out + NUM_EPI_WARPS * STG_BYTES;       // (S - 1) partial tiles (used in rank 0 only)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(parts + (size_t)(S - 1) * PART_BYTES);
+  uint64_t* empty_bar = full_bar + stages;
+  uint64_t* tmem_full_bar = empty_bar + stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = (K + BK - 1) / BK;
+  const int kb_per = (nkb + (int)S - 1) / (int)S;
+  const int kb_lo = (int)rank * kb_per, kb_hi = min(nkb, kb_lo + kb_per);   // host guarantees kb_lo < kb_hi
+  const int n_idx = blockIdx.x / S, n0 = n_idx * BN;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    if (se.tma_store && rank == 0) tma_prefetch_desc(&map_out);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, ACC_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();
+  griddep_launch();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = kb_lo, it = 0; kb < kb_hi; ++kb, ++it) {
+        const int s = it % stages;
+        mbar_wait(&empty_bar[s], ((it / stages) & 1) ^ 1);
+        uint8_t* a_dst = smem + (size_t)s * STAGE_BYTES;
+        mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+        tma_load_2d(a_dst, &map_a, &full_bar[s], kb * BK, 0);
+        tma_load_2d(a_dst + A_BYTES, &map_b, &full_bar[s], kb * BK, n0);
+      }
+    }
+    __syncwarp();
+    cluster_arrive_release();
+    cluster_wait_acquire();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(1, 1, BM, BN);
+      for (int kb = kb_lo, it = 0; kb < kb_hi; ++kb, ++it) {
+        const int s = it % stages;
+        mbar_wait(&full_bar[s], (it / stages) & 1);
+        tc_fence_after_sync();
+        const uint32_t a_addr = smem_u32(smem + (size_t)s * STAGE_BYTES);
+        const uint64_t da = umma_desc_k_sw128(a_addr), db = umma_desc_k_sw128(a_addr + A_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(tmem_full_bar);
+    }
+    __syncwarp();
+    cluster_arrive_release();
+    cluster_wait_acquire();
+  } else {
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int c_lo = half * HALF, c_hi = c_lo + HALF;
+    const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t my_part = smem_u32(parts) + (uint32_t)(warp - 2) * WARP_PART;
+    if (rank != 0) {
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after_sync();
+      const uint32_t dst = mapa_shared(my_part + (rank - 1) * PART_BYTES + (uint32_t)lane * 16u, 0);
+#pragma unroll 1
+      for (int c = c_lo; c < c_hi; c += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr_row + c, r);
+        tmem_ld_wait();
+        const uint32_t chunk = dst + (uint32_t)((c - c_lo) >> 4) * 2048u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) st_cluster_v4(chunk + (uint32_t)j * 512u, r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      cluster_arrive_release();
+      cluster_wait_acquire();
+    } else {
+      cluster_arrive_release();
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after_sync();
+      cluster_wait_acquire();  // every other rank's partial tile has landed in `parts`
+      const int row = q * 32 + lane;
+      LMHeadEpilogue le{};
+      ReduceScatterEpilogue re{};
+      epilogue_cols<0, CW, 1>(taddr_row, row, row < M, n0, c_lo, c_hi, N, 0, se, le, re, stage_out + (size_t)(warp - 2) * STG_BYTES,
+                              &map_out, q * 32, lane, my_part, (int)S - 1, PART_BYTES);
+      tc_fence_before_sync();
+      if (se.tma_store && lane == 0) tma_store_wait_all();
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, ACC_COLS);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- CTA-pair GEMM
 // 256 x BN output tiles computed by a CLUSTER OF TWO CTAs with tcgen05.mma.cta_group::2 (UMMA M = 256).  CTA r of the pair
 // stages rows [128 r, 128 r + 128) of the A tile and rows [BN/2 r, BN/2 r + BN/2) of the B tile; the leader's single MMA
@@ -1047,6 +1202,87 @@ static int launch_cta_pair(const void* A, const void* B, int M, int N, int K, lo
   return (int)launch_kernel_cluster(kern, grid, dim3(NUM_THREADS), smem, stream, 2u, m2a, m2b, m2o, M, N, K, stages, s2, ar);
 }
 
+// ---- cluster split-K launch (decode shapes, see gemm_csk_kernel)
+struct CskPlan {
+  int bn = 0, S = 0, stages = 0;
+  size_t smem = 0;
+};
+
+template <int BN>
+static int csk_max_clusters(int S, size_t smem) {
+  static std::map<std::pair<int, size_t>, int> cache;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> g(mu);
+  auto it = cache.find({S, smem});
+  if (it != cache.end()) return it->second;
+  auto kern = gemm_csk_kernel<BN>;
+  int n = 0;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(S * 64));
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)S;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) n = 0;
+  }
+  cudaGetLastError();  // a failed query must not poison the stream's error state
+  cache[{S, smem}] = n;
+  return n;
+}
+
+// Cost model: kilobytes one CTA pulls through the L2 -> SMEM path (the A panel dominates: 16 KB per k-block) plus a fixed
+// charge for the cluster barrier and the partial-tile exchange.  `forced` ignores the "must save 30 %" threshold.
+static bool csk_plan(int M, int N, int K, bool forced, CskPlan* plan) {
+  static const bool off = getenv("B200_GEMM_NO_CSK") != nullptr;
+  if ((off && !forced) || M > BM) return false;
+  const int nkb = (K + BK - 1) / BK;
+  if (nkb < 4) return false;
+  const int sms = num_sms();
+  const int base_bn = pick_bn(M, N);
+  double best = forced ? 1e30 : 0.7 * nkb * (16.0 + base_bn / 8.0);
+  bool found = false;
+  for (int bn : {32, 64}) {
+    const int tiles = (N + bn - 1) / bn;
+    for (int S = 8; S >= 2; --S) {
+      if (tiles * S > sms) continue;
+      const int per = (nkb + S - 1) / S;
+      if ((nkb + per - 1) / per != S) continue;  // no empty split: the cluster size IS the split count
+      const double cost = per * (16.0 + bn / 8.0) + 14.0 + (S - 1);
+      if (cost >= best) continue;
+      const size_t stage_bytes = (size_t)BM * BK * 2 + (size_t)bn * BK * 2;
+      const size_t fixed = (size_t)NUM_EPI_WARPS * STG_BYTES + (size_t)(S - 1) * bn * 512 + 1024 + 512;
+      int stages = (int)((227 * 1024 - fixed) / stage_bytes);
+      if (stages > 8) stages = 8;
+      if (stages > per) stages = per;
+      if (stages < (per < 2 ? per : 2)) continue;
+      const size_t smem = (size_t)stages * stage_bytes + fixed;
+      const int resident = bn == 32 ? csk_max_clusters<32>(S, smem) : csk_max_clusters<64>(S, smem);
+      if (resident < tiles) continue;  // every cluster must be co-resident: a second wave would double the latency
+      best = cost;
+      *plan = CskPlan{bn, S, stages, smem};
+      found = true;
+    }
+  }
+  return found;
+}
+
+template <int BN>
+static int launch_csk(const void* A, const void* B, int M, int N, int K, long long lda, long long ldb, StoreEpilogue se,
+                      const CskPlan& p, cudaStream_t stream) {
+  CUtensorMap ma, mb, mo{};
+  if (!make_map(&ma, A, M, K, lda, BM) || !make_map(&mb, B, N, K, ldb, BN)) return -1;
+  if (!setup_tma_store(se, &mo, M, N, BN)) return -1;
+  const int tiles = (N + BN - 1) / BN;
+  return (int)launch_kernel_cluster(gemm_csk_kernel<BN>, dim3((unsigned)(tiles * p.S)), dim3(NUM_THREADS), p.smem, stream,
+                                    (unsigned)p.S, ma, mb, mo, M, N, K, p.stages, se);
+}
+
 struct LnFold {
   const float* stats_in = nullptr;  // [M, 2] (sum, sum sq) of the raw A rows
   const float* c1 = nullptr;        // [N]
@@ -1089,6 +1325,21 @@ static int gemm_bf16_impl(const void* A, const void* B, void* out, int M, int N,
         cta_pair_eligible(M, N, K, out, ldo, force2)) {
       StoreEpilogue s2{out, (const __nv_bfloat16*)bias, (const __nv_bfloat16*)residual, nullptr, ldo, ldr, alpha, act, 0};
       return launch_cta_pair(A, B, M, N, K, lda, ldb, s2, AReady{}, stream);
+    }
+  }
+  // cluster split-K for single-row-tile (decode) shapes: force_bn == -3 requests it explicitly
+  if (force_bn == 0 || force_bn == -3) {
+    CskPlan cp;
+    if (csk_plan(M, N, K, force_bn == -3, &cp)) {
+      StoreEpilogue sc{out, (const __nv_bfloat16*)bias, (const __nv_bfloat16*)residual, col_scale, ldo, ldr, alpha, act, out_f32};
+      sc.ln_stats = ln.stats_in;
+      sc.ln_c1 = ln.c1;
+      sc.ln_inv_k = 1.0f / (float)K;
+      sc.ln_eps = ln.eps;
+      sc.ln_rms = ln.rms;
+      sc.stats_out = ln.stats_out;
+      return cp.bn == 32 ? launch_csk<32>(A, B, M, N, K, lda, ldb, sc, cp, stream)
+                         : launch_csk<64>(A, B, M, N, K, lda, ldb, sc, cp, stream);
     }
   }
   // 64-row tiles when even 128x32 tiles leave more than half of the SMs idle (decode: M = batch <= 128)
@@ -1168,7 +1419,9 @@ static int splitk_plan(int M, int N, int K, int* bn_out) {
   const int sms = num_sms();
   const long long m_tiles = (M + BM - 1) / BM;
   int splits = 1;
-  if (nkb >= 32 && m_tiles * ((N + bn - 1) / bn) < 2LL * sms) {
+  // K >= 8192 only: at K = 2304 / 3072 (the dX GEMMs of a GPT-2 block) the memset + red.add + finalize sequence cost more
+  // than the split saved (38 / 42 us against 26 us unsplit and 21 us for cuBLAS, run33)
+  if (nkb >= 128 && m_tiles * ((N + bn - 1) / bn) < 2LL * sms) {
     bn = N >= 256 ? 256 : (N >= 128 ? 128 : 64);
     const long long tiles = m_tiles * ((N + bn - 1) / bn);
     long long s = (2LL * sms + tiles - 1) / tiles;
