@@ -85,6 +85,60 @@ def chain_mlp(bn):
     return fn
 
 
+def chain_one(weights, act="none"):
+    """Dependent chain over one weight shape [N, 768] -> feeds the first 768 columns on (auto plan / env override)."""
+    def fn():
+        y = x0
+        for W in weights:
+            o = C.gemm(y, W, None, None, act)
+            y = o[:, :H] if o.shape[1] > H else o
+        return y
+    return fn
+
+
+def chain_fc2():
+    """fc pinned to the plain 128x32 kernel (force_bn > 0), fc2 ([128, 3072] x [768, 3072]^T) on the plan under test."""
+    def fn():
+        y = x0
+        for Wu, Wd in zip(big, down):
+            y = C.gemm(C.gemm(y, Wu, None, None, "gelu_new", force_bn=32), Wd, None, None, "none")
+        return y
+    return fn
+
+
+if os.environ.get("CHAIN_SWEEP"):
+    # cluster split-K tile-width / cluster-size sweep (B200_CSK_FORCE is read at every launch)
+    C.set_pdl(True)
+    sweep = {"sq768": (Ws, [(32, 6), (32, 4), (32, 3), (32, 2), (64, 6), (64, 4)]),
+             "qkv2304": (Wq, [(32, 2), (64, 4), (64, 3), (64, 2)]),
+             "fc3072": (big, [(64, 3), (64, 2)])}
+    for name, (weights, cfgs) in sweep.items():
+        rec = {"shape": name}
+        os.environ["B200_GEMM_NO_CSK"] = "1"
+        rec["plain"] = round(timed_graph(chain_one(weights)) / n_w, 2)
+        del os.environ["B200_GEMM_NO_CSK"]
+        for bn, S in cfgs:
+            os.environ["B200_CSK_FORCE"] = f"{bn},{S}"
+            try:
+                rec[f"bn{bn}_S{S}"] = round(timed_graph(chain_one(weights)) / n_w, 2)
+            except RuntimeError as e:
+                rec[f"bn{bn}_S{S}"] = "n/a"
+        os.environ.pop("B200_CSK_FORCE", None)
+        print(json.dumps(rec), flush=True)
+    rec = {"shape": "fc_plain+fc2"}
+    os.environ["B200_GEMM_NO_CSK"] = "1"
+    rec["plain"] = round(timed_graph(chain_fc2()) / n_w, 2)
+    del os.environ["B200_GEMM_NO_CSK"]
+    for bn, S in [(64, 8), (64, 6), (64, 4), (32, 6), (32, 4), (32, 3)]:
+        os.environ["B200_CSK_FORCE"] = f"{bn},{S}"
+        try:
+            rec[f"bn{bn}_S{S}"] = round(timed_graph(chain_fc2()) / n_w, 2)
+        except RuntimeError:
+            rec[f"bn{bn}_S{S}"] = "n/a"
+    os.environ.pop("B200_CSK_FORCE", None)
+    print(json.dumps(rec), flush=True)
+    sys.exit(0)
+
 for pdl in (1, 0):
     C.set_pdl(bool(pdl))
     rec = {"pdl": pdl, "norm_us": round(timed_graph(chain_norm()) / n_w, 2)}

@@ -259,6 +259,58 @@ def test_lmhead_greedy_and_sampling(C):
     assert (t != 0).all()
 
 
+@pytest.mark.parametrize("B,H,Tq,Tk,d", [(4, 12, 56, 56, 64), (2, 3, 128, 128, 64), (3, 2, 17, 17, 128), (2, 4, 8, 24, 64),
+                                         (1, 2, 1, 9, 32)])
+@pytest.mark.parametrize("mode", ["causal", "bias", "bias_broadcast"])
+def test_attention_short_forward_backward(C, B, H, Tq, Tk, d, mode):
+    """One-CTA-per-(batch, head) attention vs an fp32 reference: strided q/k/v views of a fused QKV buffer, causal flag or an
+    additive (finite-min) mask with left padding, rectangular score tiles; forward, dQ, dK, dV."""
+    from trlx_b200 import ops
+
+    torch.manual_seed(Tq * 131 + d)
+    Tmax = max(Tq, Tk)
+    qkv = (torch.randn(B, Tmax, 3 * H * d, device="cuda") * 0.7).to(torch.bfloat16).requires_grad_(True)
+    q, k, v = qkv.split(H * d, dim=-1)
+    q = q[:, :Tq].view(B, Tq, H, d).transpose(1, 2)
+    k = k[:, :Tk].view(B, Tk, H, d).transpose(1, 2)
+    v = v[:, :Tk].view(B, Tk, H, d).transpose(1, 2)
+    scale = d ** -0.5
+    i = torch.arange(Tq, device="cuda").view(Tq, 1) + (Tk - Tq)
+    j = torch.arange(Tk, device="cuda").view(1, Tk)
+    allowed = (j <= i).view(1, 1, Tq, Tk)
+    if mode == "causal":
+        bias = None
+    else:
+        pad = torch.zeros(B, Tk, dtype=torch.bool, device="cuda")
+        for b in range(B):
+            pad[b, : (b * 3) % max(Tk - 1, 1)] = True  # left padding of varying length
+        ok = allowed & ~pad.view(B, 1, 1, Tk)
+        neg = torch.finfo(torch.float32).min
+        bias = torch.zeros(ok.shape, device="cuda").masked_fill(~ok, neg)
+        if mode == "bias_broadcast" and Tq == 1:
+            bias = bias[:, :, :1]
+    assert C.attn_short_ok(Tq, Tk, d, True)
+    from trlx_b200.ops import functional
+
+    out = functional._ShortAttention.apply(q, k, v, bias, bias is None, scale)  # the autograd node itself (training default: SDPA)
+    with torch.no_grad():  # the public entry point takes the same kernel on no-grad paths (prefill / scoring)
+        assert torch.equal(ops.attention(q, k, v, bias, causal=bias is None, scale=scale), out)
+    g = (torch.randn(B, Tq, H * d, device="cuda") * 0.5).to(torch.bfloat16)
+    (out.transpose(1, 2).reshape(B, Tq, H * d) * g).sum().backward()
+    got_grad = qkv.grad.float().clone()
+    qkv.grad = None
+
+    qf, kf, vf = q.float(), k.float(), v.float()
+    sc = qf @ kf.transpose(-1, -2) * scale + (bias if bias is not None else torch.zeros_like(allowed, dtype=torch.float32)
+                                               .masked_fill(~allowed, float("-inf")))
+    ref = torch.softmax(sc, dim=-1) @ vf
+    (ref.transpose(1, 2).reshape(B, Tq, H * d) * g.float()).sum().backward()
+    ref_grad = qkv.grad.float()
+    assert (out.float() - ref).abs().max().item() <= 2e-2 * max(ref.abs().max().item(), 1.0)
+    tol = 3e-2 * max(ref_grad.abs().max().item(), 1.0)
+    assert (got_grad - ref_grad).abs().max().item() <= tol, ((got_grad - ref_grad).abs().max().item(), tol)
+
+
 @pytest.mark.parametrize("rms", [False, True])
 def test_norm(C, rms):
     torch.manual_seed(5)

@@ -61,7 +61,15 @@ int b200_signal_barrier(void* const*, int, int, unsigned int*, cudaStream_t);
 int b200_rs_adamw_ag(void* const*, void* const*, int, long long, long long, float*, float*, float*, float*, int, float, float,
                      float, float, int, const float*, double*, cudaStream_t);
 int b200_lerp_bf16(void*, const void*, long long, float, cudaStream_t);
+int b200_attn_short_ok(int, int, int, int);
+int b200_attn_short_fwd(const void*, const void*, const void*, const float*, void*, float*, int, int, int, int, int,
+                        const long long*, const long long*, const long long*, const long long*, float, int, cudaStream_t);
+int b200_attn_short_bwd(const void*, const void*, const void*, const float*, const void*, const void*, const long long*,
+                        const float*, void*, void*, void*, int, int, int, int, int, const long long*, const long long*,
+                        const long long*, const long long*, float, int, cudaStream_t);
 void b200_set_pdl(int);
+void b200_set_static_weights(int);
+int b200_get_static_weights();
 int b200_get_pdl();
 int b200_gemm_allgather_bf16(void* const*, int, const void*, void*, int, int, int, long long, long long, long long, const void*,
                              int, cudaStream_t);
@@ -208,6 +216,75 @@ Tensor gemm_ex(const Tensor& a, const Tensor& b, bool a_mn, bool b_mn, bool out_
                           splits > 1 ? ws.data_ptr<float>() : nullptr, stream()),
         "gemm_ex");
   return out;
+}
+
+// ---- short-sequence attention (attention.cu): q/k/v are [B, H, T, d] views with a contiguous head dimension
+namespace {
+struct AttnArgs {
+  long long qs[3], ks[3], vs[3], bs[3];
+  const float* bias = nullptr;
+};
+AttnArgs attn_args(const Tensor& q, const Tensor& k, const Tensor& v, const OptTensor& bias) {
+  CHECK_BF16(q); CHECK_BF16(k); CHECK_BF16(v);
+  TORCH_CHECK(q.dim() == 4 && k.dim() == 4 && v.dim() == 4, "attn_short: q/k/v must be [B, H, T, d]");
+  TORCH_CHECK(q.stride(3) == 1 && k.stride(3) == 1 && v.stride(3) == 1, "attn_short: head dimension must be contiguous");
+  TORCH_CHECK(k.sizes() == v.sizes() && q.size(0) == k.size(0) && q.size(1) == k.size(1) && q.size(3) == k.size(3));
+  for (const Tensor* t : {&q, &k, &v}) {
+    TORCH_CHECK(reinterpret_cast<uintptr_t>(t->data_ptr()) % 16 == 0 && t->stride(0) % 8 == 0 && t->stride(1) % 8 == 0 &&
+                t->stride(2) % 8 == 0, "attn_short: 16-byte aligned rows required");
+  }
+  AttnArgs a;
+  for (int i = 0; i < 3; ++i) { a.qs[i] = q.stride(i); a.ks[i] = k.stride(i); a.vs[i] = v.stride(i); a.bs[i] = 0; }
+  if (bias.has_value()) {
+    const Tensor& bt = *bias;
+    CHECK_F32(bt);
+    TORCH_CHECK(bt.dim() == 4 && bt.size(3) == k.size(2) && (bt.size(3) == 1 || bt.stride(3) == 1), "attn_short: bad bias");
+    TORCH_CHECK((bt.size(0) == 1 || bt.size(0) == q.size(0)) && (bt.size(1) == 1 || bt.size(1) == q.size(1)) &&
+                (bt.size(2) == 1 || bt.size(2) == q.size(2)), "attn_short: bias must broadcast to [B, H, Tq, Tk]");
+    a.bs[0] = bt.size(0) == 1 ? 0 : bt.stride(0);
+    a.bs[1] = bt.size(1) == 1 ? 0 : bt.stride(1);
+    a.bs[2] = bt.size(2) == 1 ? 0 : bt.stride(2);
+    a.bias = bt.data_ptr<float>();
+  }
+  return a;
+}
+}  // namespace
+
+// returns (o [B, Tq, H, d] bf16 contiguous, stats [B, H, Tq, 2] fp32 = row max and 1 / row sum)
+std::vector<Tensor> attn_short_fwd(const Tensor& q, const Tensor& k, const Tensor& v, const OptTensor& bias, bool causal,
+                                   double scale) {
+  AttnArgs a = attn_args(q, k, v, bias);
+  const int B = (int)q.size(0), H = (int)q.size(1), Tq = (int)q.size(2), Tk = (int)k.size(2), d = (int)q.size(3);
+  c10::cuda::CUDAGuard guard(q.device());
+  Tensor o = torch::empty({B, Tq, H, d}, q.options());
+  Tensor stats = torch::empty({B, H, Tq, 2}, q.options().dtype(at::kFloat));
+  check(b200_attn_short_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), a.bias, o.data_ptr(), stats.data_ptr<float>(), B, H, Tq,
+                            Tk, d, a.qs, a.ks, a.vs, a.bs, (float)scale, causal ? 1 : 0, stream()),
+        "attn_short_fwd");
+  return {o, stats};
+}
+
+// d_o: [B, H, Tq, d] view (any strides, contiguous head dim); returns dq, dk, dv as [B, T, H, d] contiguous
+std::vector<Tensor> attn_short_bwd(const Tensor& q, const Tensor& k, const Tensor& v, const OptTensor& bias, const Tensor& o,
+                                   const Tensor& d_o, const Tensor& stats, bool causal, double scale) {
+  AttnArgs a = attn_args(q, k, v, bias);
+  const int B = (int)q.size(0), H = (int)q.size(1), Tq = (int)q.size(2), Tk = (int)k.size(2), d = (int)q.size(3);
+  CHECK_BF16(o); CHECK_BF16(d_o); CHECK_F32(stats);
+  TORCH_CHECK(o.is_contiguous() && o.size(0) == B && o.size(1) == Tq && o.size(2) == H && o.size(3) == d);
+  TORCH_CHECK(d_o.dim() == 4 && d_o.size(0) == B && d_o.size(1) == H && d_o.size(2) == Tq && d_o.size(3) == d &&
+              d_o.stride(3) == 1 && d_o.stride(0) % 8 == 0 && d_o.stride(1) % 8 == 0 && d_o.stride(2) % 8 == 0 &&
+              reinterpret_cast<uintptr_t>(d_o.data_ptr()) % 16 == 0, "attn_short_bwd: bad d_o");
+  TORCH_CHECK(stats.is_contiguous() && stats.numel() == (int64_t)B * H * Tq * 2);
+  c10::cuda::CUDAGuard guard(q.device());
+  Tensor dq = torch::empty({B, Tq, H, d}, q.options());
+  Tensor dk = torch::empty({B, Tk, H, d}, q.options());
+  Tensor dv = torch::empty({B, Tk, H, d}, q.options());
+  const long long dos[3] = {d_o.stride(0), d_o.stride(1), d_o.stride(2)};
+  check(b200_attn_short_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), a.bias, o.data_ptr(), d_o.data_ptr(), dos,
+                            stats.data_ptr<float>(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), B, H, Tq, Tk, d, a.qs, a.ks,
+                            a.vs, a.bs, (float)scale, causal ? 1 : 0, stream()),
+        "attn_short_bwd");
+  return {dq, dk, dv};
 }
 
 // LM-head backward: d-logits[M, N] (bf16, row pitch padded to a multiple of 64 so every consumer is vectorised) from
@@ -708,6 +785,16 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("rs_finalize", &rs_finalize, py::arg("acc"), py::arg("bias") = py::none(), py::arg("residual") = py::none(),
         py::arg("out") = py::none());
   m.def("ppo_loss_num_outputs", [] { return b200_ppo_loss_num_outputs(); });
+  m.def("set_static_weights", [](bool on) { b200_set_static_weights(on ? 1 : 0); },
+        "GEMMs launched while set may prefetch their weight tiles ahead of the PDL wait (weights must be read-only)");
+  m.def("get_static_weights", []() { return b200_get_static_weights() != 0; });
+  m.def("attn_short_ok", [](int64_t tq, int64_t tk, int64_t d, bool backward) {
+    return b200_attn_short_ok((int)tq, (int)tk, (int)d, backward ? 1 : 0) != 0; },
+        py::arg("tq"), py::arg("tk"), py::arg("d"), py::arg("backward") = false);
+  m.def("attn_short_fwd", &attn_short_fwd, py::arg("q"), py::arg("k"), py::arg("v"), py::arg("bias") = py::none(),
+        py::arg("causal") = false, py::arg("scale") = 1.0);
+  m.def("attn_short_bwd", &attn_short_bwd, py::arg("q"), py::arg("k"), py::arg("v"), py::arg("bias"), py::arg("o"),
+        py::arg("d_o"), py::arg("stats"), py::arg("causal") = false, py::arg("scale") = 1.0);
   m.def("set_pdl", [](bool on) { b200_set_pdl(on ? 1 : 0); }, "enable/disable programmatic dependent launch for the kernels");
   m.def("get_pdl", [] { return b200_get_pdl() != 0; });
   py::class_<PagedKVAllocator>(m, "PagedKVAllocator")

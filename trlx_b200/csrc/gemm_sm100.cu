@@ -87,6 +87,9 @@ struct AReady {
   uint32_t epoch;
   int rows_per_flag;
   int m_rot;
+  // B (the weights) is not written by the kernel that precedes this one in the stream: its first tiles are fetched BEFORE
+  // griddepcontrol.wait, i.e. while the producer of A is still running (decode graphs; see b200_set_static_weights)
+  int b_static;
 };
 
 struct LMHeadEpilogue {
@@ -597,8 +600,20 @@ gemm_tn_kernel(const __grid_constant__ MapArray maps_a, const __grid_constant__ 
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped with the tail of the previous
-  // kernel; from here on we touch memory it produced.  Let our own successor start its prologue right away.
+  uint32_t b_pre = 0;  // leading k-blocks of this CTA's first tile whose B boxes are already in flight (producer thread only)
+  if constexpr (!BMN) {
+    if (ar.b_static && warp == 0 && lane == 0 && (int)blockIdx.x < total_work) {
+      const int tile = blockIdx.x % total_tiles, split = blockIdx.x / total_tiles;
+      const int kb_lo = split * kb_per, kb_hi = min(nkb, kb_lo + kb_per);
+      const int n0 = (tile / m_tiles) * BN;
+      for (int kb = kb_lo; kb < kb_hi && (int)b_pre < stages; ++kb, ++b_pre) {
+        mbar_arrive_expect_tx(&full_bar[b_pre], STAGE_BYTES);
+        tma_load_2d(smem + (size_t)b_pre * STAGE_BYTES + A_BYTES, &map_b, &full_bar[b_pre], kb * BKE, n0);
+      }
+    }
+  }
+  // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch, static-weight tiles) overlapped with the
+  // tail of the previous kernel; from here on we touch memory it produced.  Let our own successor start its prologue.
   griddep_wait();
   griddep_launch();
 
@@ -621,10 +636,13 @@ gemm_tn_kernel(const __grid_constant__ MapArray maps_a, const __grid_constant__ 
         for (int kb = kb_lo; kb < kb_hi; ++kb, ++it) {
           const int s = it % stages;
           const uint32_t phase = (it / stages) & 1;
-          mbar_wait(&empty_bar[s], phase ^ 1);
           uint8_t* a_dst = smem + (size_t)s * STAGE_BYTES;
           uint8_t* b_dst = a_dst + A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+          const bool b_inflight = it < b_pre;  // armed + B issued before the PDL wait (first pass over fresh stages)
+          if (!b_inflight) {
+            mbar_wait(&empty_bar[s], phase ^ 1);
+            mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+          }
           if constexpr (AMN) {
 #pragma unroll
             for (int ch = 0; ch < TBM / 64; ++ch) tma_load_2d(a_dst + ch * MN_CHUNK, map_a_ptr, &full_bar[s], m0 + ch * 64, kb * BK);
@@ -635,7 +653,7 @@ gemm_tn_kernel(const __grid_constant__ MapArray maps_a, const __grid_constant__ 
 #pragma unroll
             for (int ch = 0; ch < BN / 64; ++ch) tma_load_2d(b_dst + ch * MN_CHUNK, &map_b, &full_bar[s], n0 + ch * 64, kb * BK);
           } else {
-            tma_load_2d(b_dst, &map_b, &full_bar[s], kb * BKE, n0);
+            if (!b_inflight) tma_load_2d(b_dst, &map_b, &full_bar[s], kb * BKE, n0);
           }
         }
       }
@@ -718,7 +736,8 @@ gemm_tn_kernel(const __grid_constant__ MapArray maps_a, const __grid_constant__ 
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_csk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                const __grid_constant__ CUtensorMap map_out, int M, int N, int K, int stages, StoreEpilogue se) {
+                const __grid_constant__ CUtensorMap map_out, int M, int N, int K, int stages, StoreEpilogue se,
+                int b_static) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr uint32_t A_BYTES = BM * BK * 2;
   constexpr uint32_t B_BYTES = BN * BK * 2;
@@ -763,6 +782,13 @@ gemm_csk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  int b_pre = 0;  // weight tiles already in flight when the PDL wait returns (see AReady::b_static)
+  if (b_static && warp == 0 && lane == 0) {
+    for (int kb = kb_lo; kb < kb_hi && b_pre < stages; ++kb, ++b_pre) {
+      mbar_arrive_expect_tx(&full_bar[b_pre], STAGE_BYTES);
+      tma_load_2d(smem + (size_t)b_pre * STAGE_BYTES + A_BYTES, &map_b, &full_bar[b_pre], kb * BK, n0);
+    }
+  }
   griddep_wait();
   griddep_launch();
 
@@ -770,11 +796,13 @@ gemm_csk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     if (lane == 0) {
       for (int kb = kb_lo, it = 0; kb < kb_hi; ++kb, ++it) {
         const int s = it % stages;
-        mbar_wait(&empty_bar[s], ((it / stages) & 1) ^ 1);
         uint8_t* a_dst = smem + (size_t)s * STAGE_BYTES;
-        mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+        if (it >= b_pre) {
+          mbar_wait(&empty_bar[s], ((it / stages) & 1) ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+          tma_load_2d(a_dst + A_BYTES, &map_b, &full_bar[s], kb * BK, n0);
+        }
         tma_load_2d(a_dst, &map_a, &full_bar[s], kb * BK, 0);
-        tma_load_2d(a_dst + A_BYTES, &map_b, &full_bar[s], kb * BK, n0);
       }
     }
     __syncwarp();
@@ -1122,6 +1150,11 @@ static int pick_bn(int M, int N) {
   return best;
 }
 
+// While set, every K-major GEMM launched from this process may fetch its B operand ahead of the programmatic-dependent-launch
+// wait.  Only valid when the kernel that precedes each GEMM in its stream never writes B: the rollout engine sets it around
+// the capture of its decode / prefill graphs (weights are read-only there) and clears it afterwards.
+static bool g_static_b = false;
+
 template <int BN, int EPI, int AMN = 0, int BMN = 0, int TBM = 128, int FP8 = 0>
 static cudaError_t launch(const MapArray& ma, const CUtensorMap& mb, const CUtensorMap& mo, int M, int N, int K,
                           int rows_per_map, const StoreEpilogue& se, const LMHeadEpilogue& le,
@@ -1141,6 +1174,7 @@ static cudaError_t launch(const MapArray& ma, const CUtensorMap& mb, const CUten
     configured = true;
   }
   const long long tiles = (long long)((N + BN - 1) / BN) * ((M + TBM - 1) / TBM) * k_splits;
+  ar.b_static = (g_static_b && !AMN && !BMN && ar.flags == nullptr) ? 1 : 0;
   dim3 grid((unsigned)(tiles < num_sms() ? tiles : num_sms()));  // persistent: one CTA per SM walks the tile list
   return launch_kernel(kern, grid, dim3(NUM_THREADS), smem, stream, ma, mb, mo, M, N, K, stages, rows_per_map, se, le, re, k_splits, ar);
 }
@@ -1165,6 +1199,8 @@ void set_pdl_enabled(bool on) { g_pdl = on; }
 using namespace b200;
 
 extern "C" void b200_set_pdl(int on) { set_pdl_enabled(on != 0); }
+extern "C" void b200_set_static_weights(int on) { g_static_b = on != 0; }
+extern "C" int b200_get_static_weights() { return g_static_b ? 1 : 0; }
 extern "C" int b200_get_pdl() { return pdl_enabled() ? 1 : 0; }
 
 // act: 0 none, 1 gelu_tanh, 2 gelu_erf, 3 relu, 4 silu.  Requirements: K % 8 == 0, lda/ldb % 8 == 0, 16B-aligned A/B.
@@ -1239,7 +1275,7 @@ static int csk_max_clusters(int S, size_t smem) {
 // Cost model: kilobytes one CTA pulls through the L2 -> SMEM path (the A panel dominates: 16 KB per k-block) plus a fixed
 // charge for the cluster barrier and the partial-tile exchange.  `forced` ignores the "must save 30 %" threshold.
 static bool csk_plan(int M, int N, int K, bool forced, CskPlan* plan) {
-  static const bool off = getenv("B200_GEMM_NO_CSK") != nullptr;
+  const bool off = getenv("B200_GEMM_NO_CSK") != nullptr;  // read per launch: the A/B scripts toggle it inside one process
   if ((off && !forced) || M > BM) return false;
   const int nkb = (K + BK - 1) / BK;
   if (nkb < 4) return false;
@@ -1247,13 +1283,22 @@ static bool csk_plan(int M, int N, int K, bool forced, CskPlan* plan) {
   const int base_bn = pick_bn(M, N);
   double best = forced ? 1e30 : 0.7 * nkb * (16.0 + base_bn / 8.0);
   bool found = false;
+  int want_bn = 0, want_s = 0;  // B200_CSK_FORCE="bn,S": tuning override (scripts/bench_chain.py sweeps it)
+  if (const char* f = getenv("B200_CSK_FORCE")) {
+    if (sscanf(f, "%d,%d", &want_bn, &want_s) == 2) best = 1e30;
+    else want_bn = want_s = 0;
+  }
   for (int bn : {32, 64}) {
     const int tiles = (N + bn - 1) / bn;
+    if (want_bn && bn != want_bn) continue;
     for (int S = 8; S >= 2; --S) {
+      if (want_s && S != want_s) continue;
       if (tiles * S > sms) continue;
       const int per = (nkb + S - 1) / S;
       if ((nkb + per - 1) / per != S) continue;  // no empty split: the cluster size IS the split count
-      const double cost = per * (16.0 + bn / 8.0) + 14.0 + (S - 1);
+      // measured in-chain (run35): the 64-wide tile halves the number of leaders, whose serial epilogue then costs more than
+      // the narrower tile's extra A traffic (QKV: 6.5 us at 32x2 vs 7.3 at 64x3; fc2: 9.3 vs 10.7) — hence the surcharge
+      const double cost = per * (16.0 + bn / 8.0) + 14.0 + (S - 1) + (bn == 64 ? 30.0 : 0.0);
       if (cost >= best) continue;
       const size_t stage_bytes = (size_t)BM * BK * 2 + (size_t)bn * BK * 2;
       const size_t fixed = (size_t)NUM_EPI_WARPS * STG_BYTES + (size_t)(S - 1) * bn * 512 + 1024 + 512;
@@ -1280,7 +1325,7 @@ static int launch_csk(const void* A, const void* B, int M, int N, int K, long lo
   if (!setup_tma_store(se, &mo, M, N, BN)) return -1;
   const int tiles = (N + BN - 1) / BN;
   return (int)launch_kernel_cluster(gemm_csk_kernel<BN>, dim3((unsigned)(tiles * p.S)), dim3(NUM_THREADS), p.smem, stream,
-                                    (unsigned)p.S, ma, mb, mo, M, N, K, p.stages, se);
+                                    (unsigned)p.S, ma, mb, mo, M, N, K, p.stages, se, g_static_b ? 1 : 0);
 }
 
 struct LnFold {

@@ -19,6 +19,7 @@ The result has exactly the tensors ``AcceleratePPOTrainer.make_experience`` need
 """
 from __future__ import annotations
 
+import contextlib
 import math
 from dataclasses import dataclass
 from typing import Any, Dict, List, Optional
@@ -486,6 +487,22 @@ class RolloutEngine:
         vals = torch.zeros(B, T, device=dev)
         return lp.float(), ref_lp.float(), vals, trunk
 
+    @contextlib.contextmanager
+    def _static_weights(self):
+        """Inside the rollout graphs no kernel writes a weight matrix, so the GEMMs captured here may fetch their first
+        weight tiles ahead of the programmatic-dependent-launch wait — while the producer of their activations is still
+        running (``b200_set_static_weights``).  ``TRLX_B200_WEIGHT_PREFETCH=0`` disables it."""
+        import os
+
+        on = os.environ.get("TRLX_B200_WEIGHT_PREFETCH", "1") == "1" and hasattr(ops.C, "set_static_weights")
+        if on:
+            ops.C.set_static_weights(True)
+        try:
+            yield
+        finally:
+            if on:
+                ops.C.set_static_weights(False)
+
     def _prefill_maybe_graphed(self, st, prompt, mask):
         """The prefill is ~200 small launches for short prompts (CPU-bound when issued eagerly): capture it once per
         (batch, prompt width) and replay it from static input buffers."""
@@ -509,7 +526,7 @@ class RolloutEngine:
                 launches = ops.launch_count() - before
                 torch.cuda.current_stream().wait_stream(side)
                 graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
+                with torch.cuda.graph(graph), self._static_weights():
                     outs = self._prefill(st, pf_prompt, pf_mask)
                 graphs[Q] = (graph, pf_prompt, pf_mask, outs, launches)
             except Exception as err:  # keep the eager path if anything in the prefill is not capturable
@@ -562,7 +579,7 @@ class RolloutEngine:
                     st[k].copy_(v)
                 st["tokens_out"].fill_(self.pad)
                 graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
+                with torch.cuda.graph(graph), self._static_weights():
                     self._decode_step(st)
                 for k, v in snap.items():
                     st[k].copy_(v)

@@ -152,10 +152,10 @@ class Attention(nn.Module):
             k = k.repeat_interleave(rep, dim=1)
             v = v.repeat_interleave(rep, dim=1)
         bias = ctx.local_bias if self.is_local else ctx.bias
-        if bias is None:
-            o = F.scaled_dot_product_attention(q, k, v, is_causal=(T > 1), scale=self.scale)
-        else:
-            o = F.scaled_dot_product_attention(q, k, v, attn_mask=bias.to(q.dtype), scale=self.scale)
+        # short sequences: one-CTA-per-(batch, head) kernels (csrc/attention.cu); otherwise the library SDPA
+        from trlx_b200 import ops
+
+        o = ops.attention(q, k, v, bias, causal=(bias is None and T > 1), scale=self.scale)
         o = o.transpose(1, 2).reshape(B, T, s.q_size)
         return project(self.out, o), present
 

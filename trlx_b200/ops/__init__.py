@@ -117,6 +117,7 @@ def enabled_for(*tensors) -> bool:
 
 
 from trlx_b200.ops.functional import (  # noqa: E402,F401
+    attention,
     fused_logprob,
     gae_and_whiten,
     linear,

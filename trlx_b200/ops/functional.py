@@ -110,6 +110,61 @@ def linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor] = None, a
     return y if residual is None else y + residual
 
 
+class _ShortAttention(torch.autograd.Function):
+    """softmax(scale * q kᵀ + bias) v on the one-CTA-per-(batch, head) kernels of ``csrc/attention.cu`` (T <= 128)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, bias, causal, scale):
+        o, stats = _ops().C.attn_short_fwd(q, k, v, bias, causal, scale)
+        ctx.save_for_backward(q, k, v, bias, o, stats)
+        ctx.causal, ctx.scale = causal, scale
+        return o.transpose(1, 2)  # [B, H, Tq, d] view of the [B, Tq, H, d] buffer
+
+    @staticmethod
+    def backward(ctx, g):
+        q, k, v, bias, o, stats = ctx.saved_tensors
+        if g.stride(-1) != 1 or any(st % 8 for st in g.stride()[:3]) or g.data_ptr() % 16:
+            g = g.contiguous()
+        dq, dk, dv = _ops().C.attn_short_bwd(q, k, v, bias, o, g, stats, ctx.causal, ctx.scale)
+        return dq.transpose(1, 2), dk.transpose(1, 2), dv.transpose(1, 2), None, None, None
+
+
+# "auto": the in-repo kernels serve the no-grad paths (prefill, scoring), the library SDPA serves training — the CUDA-core
+# backward is shared-memory-bandwidth bound and measured 2x slower than cuDNN's tensor-core kernel at 32 x 12 x 56 x 56
+# (run36: 29.6 vs 26.7 ms per 16 optimizer steps); "own" / "sdpa" force one side for A/B runs.
+_ATTENTION_MODE = os.environ.get("TRLX_B200_ATTENTION", "auto")
+
+
+def _attn_view_ok(t: torch.Tensor) -> bool:
+    return t.stride(-1) == 1 and all(st % 8 == 0 for st in t.stride()[:3]) and t.data_ptr() % 16 == 0
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, bias: Optional[torch.Tensor] = None, causal: bool = False,
+              scale: Optional[float] = None) -> torch.Tensor:
+    """``softmax(scale · q kᵀ + bias) v`` for ``[B, H, T, d]`` operands; ``bias`` is an additive fp32 mask broadcastable to
+    ``[B, H, Tq, Tk]`` (or ``None`` with ``causal``).  Sequences of at most 128 tokens run on the in-repo kernels (forward
+    and backward, any operand strides with a contiguous head dimension); everything else — CPU tensors, longer sequences —
+    goes through ``F.scaled_dot_product_attention``."""
+    scale = float(scale) if scale is not None else q.shape[-1] ** -0.5
+    need_grad = torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad)
+    own = _ATTENTION_MODE == "own" or (_ATTENTION_MODE == "auto" and not need_grad)
+    if (own and q.is_cuda and q.dtype == torch.bfloat16 and k.dtype == torch.bfloat16 and v.dtype == torch.bfloat16
+            and q.dim() == 4 and _ops().available() and hasattr(_ops().C, "attn_short_fwd")
+            and _ops().C.attn_short_ok(q.shape[2], k.shape[2], q.shape[3], need_grad)
+            and (bias is None or (bias.dim() == 4 and bias.shape[-1] == k.shape[2]))):
+        q, k, v = (t if _attn_view_ok(t) else t.contiguous() for t in (q, k, v))
+        if bias is not None:
+            bias = bias.float()
+            if bias.stride(-1) != 1 and bias.shape[-1] != 1:
+                bias = bias.contiguous()
+        return _ShortAttention.apply(q, k, v, bias, bool(causal) and bias is None, scale)
+    import torch.nn.functional as F
+
+    if bias is None:
+        return F.scaled_dot_product_attention(q, k, v, is_causal=bool(causal) and q.shape[2] > 1, scale=scale)
+    return F.scaled_dot_product_attention(q, k, v, attn_mask=bias.to(q.dtype), scale=scale)
+
+
 class _FusedLogprob(torch.autograd.Function):
     """log p(label | h) through the LM head without materialising logits in the forward.
     Backward: one tcgen05 GEMM recomputes the logits tile by tile and emits d-logits straight from its epilogue
