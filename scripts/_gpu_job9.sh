@@ -1,0 +1,4 @@
+echo "=== engine tests"; timeout 500 python -m pytest tests/test_engine_gpu.py -m gpu -q -x --timeout=300 --timeout-method=thread -p no:cacheprovider 2>&1 | grep -E "^E  |passed|failed|Error" | head -12
+for v in "X=1" "TRLX_B200_DEFER_REF=0"; do
+echo "=== bench $v"; env $v BENCH_BREAKDOWN=1 timeout 250 python bench.py --steps 6 --warmup 4 2>&1 | tail -2 | cut -c1-330
+done

@@ -28,9 +28,14 @@ def _model(family="gpt2"):
 
 @pytest.mark.parametrize("family", ["gpt2", "llama"])
 @pytest.mark.parametrize("graph", [False, True])
-def test_greedy_rollout_matches_torch_path(family, graph):
+@pytest.mark.parametrize("defer_ref", ["1", "0"])
+def test_greedy_rollout_matches_torch_path(family, graph, defer_ref, monkeypatch):
+    """``defer_ref``: reference log-probs from one batched pass over the cached trunk activations after the loop (default)
+    vs the frozen branch inside every decode step."""
     from trlx_b200.engine.rollout import RolloutEngine
     from trlx_b200.models.generation import generate
+
+    monkeypatch.setenv("TRLX_B200_DEFER_REF", defer_ref)
 
     m = _model(family)
     pad = eos = 999
@@ -71,6 +76,7 @@ def test_greedy_rollout_matches_torch_path(family, graph):
     # prompt-position log-probs (used for the KL statistic) and the cached trunk activation
     pm = amask[:, :start].bool() & amask[:, 1:Q].bool()
     torch.testing.assert_close(ro["logprobs"][:, :start][pm], lp[:, :start][pm].float(), atol=6e-2, rtol=5e-2)
+    torch.testing.assert_close(ro["ref_logprobs"][:, :start][pm], rlp[:, :start][pm].float(), atol=6e-2, rtol=5e-2)
     t_eng, t_ref = ro["trunk"], trunk[:, : ro["trunk"].shape[1]]
     tm = amask[:, : t_eng.shape[1]].bool() & torch.cat([torch.ones(B, Q, dtype=torch.bool, device="cuda"), resp_valid[:, 1:Rg]], 1)[:, : t_eng.shape[1]]
     torch.testing.assert_close(t_eng[tm].float(), t_ref[tm].float(), atol=8e-2, rtol=5e-2)

@@ -181,7 +181,13 @@ class RolloutEngine:
         self.folded: List[_FoldW] = []
         self.ref_folded: List[_FoldW] = []
         self.dirty = True  # folded copies must be (re)built before the next rollout
-        self.parallel_branches = os.environ.get("TRLX_B200_PARALLEL_BRANCHES", "1") == "1" and self.branch < len(self.layers)
+        # Deferred reference scoring: the frozen branch only produces log-probs that are consumed AFTER generation, so it does
+        # not have to sit on the per-token critical path.  The decode graph then keeps just the trunk activation of every
+        # position, and one batched pass (2 frozen blocks + LM head over [B, Q+R] tokens at GEMM-efficient M) scores all
+        # positions at the end — instead of 2 latency-bound blocks + a 77 MB LM-head sweep per decoded token.
+        self.defer_ref = os.environ.get("TRLX_B200_DEFER_REF", "1") == "1"
+        self.parallel_branches = (os.environ.get("TRLX_B200_PARALLEL_BRANCHES", "1") == "1" and self.branch < len(self.layers)
+                                  and not self.defer_ref)
         self.side = torch.cuda.Stream(device=self.device) if self.parallel_branches else None
         ops.C.set_pdl(os.environ.get("TRLX_B200_PDL", "1") == "1")
 
@@ -365,7 +371,7 @@ class RolloutEngine:
                 x, xs = self._layer_folded(x, xs, W, self.folded[i], st["kc"][i], st["vc"][i], st)
             else:
                 x = self._layer(x, W, st["kc"][i], st["vc"][i], st)
-        if self.cache_trunk and not self.parallel_branches:
+        if (self.cache_trunk or self.defer_ref) and not self.parallel_branches:
             st["trunk_decode"].index_copy_(1, st["step64"], trunk_x.unsqueeze(1))
         hf = C.norm(x, tr.ln_f.weight, tr.ln_f.bias, spec.norm_eps, rms)
         _, _, tok, tlp = C.lmhead(hf, lm.lm_head.weight, lm.lm_head.bias, None, True, self.temperature, self.seed,
@@ -373,7 +379,9 @@ class RolloutEngine:
         vh = model.v_head
         h1 = C.gemm(hf, vh[0].weight, vh[0].bias, None, "relu")
         val = C.rowdot(h1, vh[2].weight.view(-1), vh[2].bias)
-        if rf is None:
+        if self.defer_ref:
+            ref_lp = tlp  # placeholder column; the real reference log-probs come from `_ref_score` after the loop
+        elif rf is None:
             y, ys = trunk_x, (trunk_xs if fold else None)
             for j, W in enumerate(self.ref_layers):
                 if fold:
@@ -384,7 +392,8 @@ class RolloutEngine:
         else:
             main.wait_stream(self.side)
             rf.record_stream(main)
-        _, ref_lp, _, _ = C.lmhead(rf, fh.lm_head.weight, fh.lm_head.bias, tok, False, 1.0, 0, None, -1, 0, st["ws_ref"])
+        if not self.defer_ref:
+            _, ref_lp, _, _ = C.lmhead(rf, fh.lm_head.weight, fh.lm_head.bias, tok, False, 1.0, 0, None, -1, 0, st["ws_ref"])
         C.decode_step(tok, tlp, ref_lp, val, st["step"], st["R"], self.eos, self.pad, st["tokens_out"], st["lp_out"],
                       st["ref_lp_out"], st["val_out"], st["finished"], st["resp_lens"], st["seq_lens"], st["positions"],
                       st["next_tokens"], st["n_running"])
@@ -394,7 +403,7 @@ class RolloutEngine:
     def _build_state(self, B: int, Q: int, R: int):
         spec, dev = self.spec, self.device
         P = (Q + R + PAGE - 1) // PAGE
-        n_layers = len(self.layers) + len(self.ref_layers)
+        n_layers = len(self.layers) + (0 if self.defer_ref else len(self.ref_layers))  # deferred scoring needs no ref KV cache
         i32 = dict(dtype=torch.int32, device=dev)
         f32 = dict(dtype=torch.float32, device=dev)
         V = spec.vocab_size
@@ -411,7 +420,8 @@ class RolloutEngine:
             tokens_out=torch.full((B, R), self.pad, dtype=torch.long, device=dev), lp_out=torch.zeros(B, R, **f32),
             ref_lp_out=torch.zeros(B, R, **f32), val_out=torch.zeros(B, R, **f32),
             ws=torch.empty(5 * B * n_tiles + B, **f32), ws_ref=torch.empty(5 * B * n_tiles + B, **f32),
-            trunk_decode=(torch.zeros(B, R, spec.hidden_size, dtype=torch.bfloat16, device=dev) if self.cache_trunk else None),
+            trunk_decode=(torch.zeros(B, R, spec.hidden_size, dtype=torch.bfloat16, device=dev)
+                          if (self.cache_trunk or self.defer_ref) else None),
             seed_dev=torch.zeros(1, dtype=torch.long, device=dev), min_new=0, graph=None,
             ln_stats=torch.zeros(2 * n_layers + 2, B, 2, **f32), stats_cursor=0,
         )
@@ -474,6 +484,9 @@ class RolloutEngine:
         final = out.last_hidden_state
         labels = prompt[:, 1:Q]
         lp, _ = ops.fused_logprob(final, lm.lm_head.weight, lm.lm_head.bias, labels)
+        vals = torch.zeros(B, T, device=dev)
+        if self.defer_ref:
+            return lp.float(), None, vals, trunk
         # reference branch on the shared trunk activation
         fh = model.frozen_head
         ctx = build_attn_context(spec, am, pos, T, 0, trunk.dtype, dev)
@@ -484,8 +497,27 @@ class RolloutEngine:
             scatter(L + j, present)
         y = fh.final_norm(y)
         ref_lp, _ = ops.fused_logprob(y, fh.lm_head.weight, fh.lm_head.bias, labels)
-        vals = torch.zeros(B, T, device=dev)
         return lp.float(), ref_lp.float(), vals, trunk
+
+    @torch.no_grad()
+    def _ref_score(self, prompt: torch.Tensor, mask: torch.Tensor, trunk: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+        """Reference log-probs of ``labels`` ``[B, T]`` from the trunk activations ``[B, T, H]`` of the T = Q-1+r input
+        positions: the frozen blocks and LM head run ONCE over all positions (reference: ``forward_hydra``,
+        ``trlx/models/modeling_ppo.py:356-401``, which re-runs the whole model instead)."""
+        spec, fh = self.spec, self.model.frozen_head
+        B, T = labels.shape
+        Q = prompt.shape[1]
+        # inputs are prompt[0..Q-1] followed by the sampled tokens: the prompt keeps its (left-)padding mask, every generated
+        # position is visible — exactly what the incremental decode attends to
+        am = torch.cat([mask, mask.new_ones(B, max(T - Q, 0))], 1)[:, :T]
+        pos = (am.long().cumsum(-1) - 1).clamp_min(0)
+        ctx = build_attn_context(spec, am, pos, T, 0, trunk.dtype, self.device)
+        y = trunk
+        for blk in fh.decoder_blocks:
+            y, _ = blk(y, ctx, None, False)
+        y = fh.final_norm(y)
+        ref_lp, _ = ops.fused_logprob(y, fh.lm_head.weight, fh.lm_head.bias, labels)
+        return ref_lp.float()
 
     @contextlib.contextmanager
     def _static_weights(self):
@@ -603,12 +635,17 @@ class RolloutEngine:
         r_max = max(int(resp_lens.max().item()), 1)
         sample_outputs = st["tokens_out"][:, :r_max].clone()
         logprobs = torch.cat([lp_p, st["lp_out"][:, :r_max]], 1)
-        ref_logprobs = torch.cat([ref_lp_p, st["ref_lp_out"][:, :r_max]], 1)
         values = torch.cat([val_p, st["val_out"][:, :r_max]], 1)
         all_tokens = torch.cat([prompt, sample_outputs], 1)
         full_mask = all_tokens.not_equal(self.pad).long()
         trunk = None
-        if self.cache_trunk:
+        if self.cache_trunk or self.defer_ref:
             trunk = torch.cat([trunk_p, st["trunk_decode"][:, :r_max]], 1)
+        if self.defer_ref:
+            ref_logprobs = self._ref_score(prompt, mask, trunk, all_tokens[:, 1:Q + r_max])
+            if not self.cache_trunk:
+                trunk = None
+        else:
+            ref_logprobs = torch.cat([ref_lp_p, st["ref_lp_out"][:, :r_max]], 1)
         return dict(samples=all_tokens, prompt_tensors=prompt, sample_outputs=sample_outputs, logprobs=logprobs,
                     ref_logprobs=ref_logprobs, values=values, mask=full_mask, start=Q - 1, trunk=trunk)
