@@ -29,6 +29,12 @@ if which in ("all", "gemm"):
     a, w, b = t(1792, 768), t(3072, 768), t(3072)  # training MLP up-projection + GELU
     for _ in range(3):
         C.gemm(a, w, b, None, "gelu_tanh")
+if which in ("all", "csk"):
+    # decode shapes on the cluster split-K kernel: out-proj (768 -> 768) and MLP down (3072 -> 768) at batch 128
+    for n, k in ((768, 768), (768, 3072)):
+        a, w, b, r = t(128, k), t(n, k), t(n), t(128, n)
+        for _ in range(3):
+            C.gemm(a, w, b, r, "none")
 if which in ("all", "dlogits"):
     a, w = t(1280, 768), t(50304, 768)            # LM-head backward recompute shape (short K, huge N)
     for _ in range(2):
