@@ -312,6 +312,44 @@ def test_attention_short_forward_backward(C, B, H, Tq, Tk, d, mode):
 
 
 @pytest.mark.parametrize("rms", [False, True])
+@pytest.mark.parametrize("M,H", [(1792, 768), (37, 4096), (5, 64), (300, 1000)])
+def test_training_norm_forward_backward(C, rms, M, H):
+    """LayerNorm / RMSNorm with saved row statistics and the one-pass backward (dx, d-gamma, d-beta) vs fp32 autograd."""
+    from trlx_b200 import ops
+
+    torch.manual_seed(H + M)
+    x = (_bf(M, H, scale=2.0) + 0.5).requires_grad_(True)
+    w = (_bf(H) * 0.3 + 1.0).requires_grad_(True)
+    b = None if rms else _bf(H).requires_grad_(True)
+    g = _bf(M, H)
+    assert ops.norm_ok(x, w, b)
+    y = ops.layer_norm(x.view(1, M, H), w, b, 1e-5, rms).view(M, H)
+    y.backward(g)
+    got = [y.detach().float(), x.grad.float().clone(), w.grad.float().clone()] + ([] if rms else [b.grad.float().clone()])
+    x.grad = w.grad = None
+    xf, wf = x.float(), w.float()
+    if rms:
+        ref = xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-5) * wf
+    else:
+        b.grad = None
+        ref = F.layer_norm(xf, (H,), wf, b.float(), 1e-5)
+    ref.backward(g.float())
+    want = [ref.detach(), x.grad.float(), w.grad.float()] + ([] if rms else [b.grad.float()])
+    for name, a, e in zip(("y", "dx", "dgamma", "dbeta"), got, want):
+        tol = 2e-2 * max(e.abs().max().item(), 1.0)
+        assert (a - e).abs().max().item() <= tol, (name, (a - e).abs().max().item(), tol)
+
+
+@pytest.mark.parametrize("M,N", [(1792, 3072), (1792, 768), (7, 66), (1280, 50304), (0, 64)])
+def test_bias_gradient_column_sum(C, M, N):
+    x = _bf(M, N + 2)[:, :N]  # strided view: row pitch != N
+    out = C.colsum(x)
+    ref = x.float().sum(0)
+    assert out.shape == (N,)
+    assert (out.float() - ref).abs().max().item() <= 1e-2 * max(ref.abs().max().item(), 1.0) + 1e-6
+
+
+@pytest.mark.parametrize("rms", [False, True])
 def test_norm(C, rms):
     torch.manual_seed(5)
     x, w, b = _bf(333, 768), _bf(768), _bf(768)

@@ -67,6 +67,12 @@ int b200_attn_short_fwd(const void*, const void*, const void*, const float*, voi
 int b200_attn_short_bwd(const void*, const void*, const void*, const float*, const void*, const void*, const long long*,
                         const float*, void*, void*, void*, int, int, int, int, int, const long long*, const long long*,
                         const long long*, const long long*, float, int, cudaStream_t);
+int b200_ln_train_ok(int);
+int b200_ln_bwd_ctas(int);
+int b200_ln_fwd(const void*, const void*, const void*, void*, float*, int, int, long long, float, int, cudaStream_t);
+int b200_ln_bwd(const void*, const void*, const float*, const void*, void*, float*, void*, void*, int, int, long long, long long,
+                int, cudaStream_t);
+int b200_colsum_bf16(const void*, void*, int, int, long long, cudaStream_t);
 void b200_set_pdl(int);
 void b200_set_static_weights(int);
 int b200_get_static_weights();
@@ -285,6 +291,51 @@ std::vector<Tensor> attn_short_bwd(const Tensor& q, const Tensor& k, const Tenso
                             a.vs, a.bs, (float)scale, causal ? 1 : 0, stream()),
         "attn_short_bwd");
   return {dq, dk, dv};
+}
+
+// ---- training-side norms and the bias-gradient column sum (norm_train.cu)
+std::vector<Tensor> ln_fwd(const Tensor& x, const Tensor& w, const OptTensor& b, double eps, bool rms) {
+  CHECK_BF16(x); CHECK_BF16(w);
+  TORCH_CHECK(x.dim() == 2 && x.stride(1) == 1 && x.stride(0) % 8 == 0 && w.is_contiguous() && w.numel() == x.size(1));
+  TORCH_CHECK(b200_ln_train_ok((int)x.size(1)), "ln_fwd: unsupported hidden size");
+  TORCH_CHECK(reinterpret_cast<uintptr_t>(x.data_ptr()) % 16 == 0 && reinterpret_cast<uintptr_t>(w.data_ptr()) % 16 == 0);
+  if (b.has_value()) { CHECK_BF16(*b); TORCH_CHECK(b->is_contiguous() && reinterpret_cast<uintptr_t>(b->data_ptr()) % 16 == 0); }
+  c10::cuda::CUDAGuard guard(x.device());
+  Tensor y = torch::empty({x.size(0), x.size(1)}, x.options());
+  Tensor stats = torch::empty({x.size(0), 2}, x.options().dtype(at::kFloat));
+  check(b200_ln_fwd(x.data_ptr(), w.data_ptr(), rms ? nullptr : optptr(b), y.data_ptr(), stats.data_ptr<float>(), (int)x.size(0),
+                    (int)x.size(1), x.stride(0), (float)eps, rms ? 1 : 0, stream()),
+        "ln_fwd");
+  return {y, stats};
+}
+
+// returns (dx [M, H], d-gamma [H], d-beta [H] or empty)
+std::vector<Tensor> ln_bwd(const Tensor& x, const Tensor& w, const Tensor& stats, const Tensor& dy, bool rms, bool has_bias) {
+  CHECK_BF16(x); CHECK_BF16(w); CHECK_BF16(dy); CHECK_F32(stats);
+  TORCH_CHECK(x.dim() == 2 && dy.dim() == 2 && x.sizes() == dy.sizes() && x.stride(1) == 1 && dy.stride(1) == 1 &&
+              x.stride(0) % 8 == 0 && dy.stride(0) % 8 == 0 && stats.is_contiguous() && stats.numel() == 2 * x.size(0));
+  TORCH_CHECK(reinterpret_cast<uintptr_t>(x.data_ptr()) % 16 == 0 && reinterpret_cast<uintptr_t>(dy.data_ptr()) % 16 == 0);
+  const int rows = (int)x.size(0), H = (int)x.size(1);
+  c10::cuda::CUDAGuard guard(x.device());
+  Tensor dx = torch::empty({rows, H}, x.options());
+  Tensor partial = torch::empty({(int64_t)b200_ln_bwd_ctas(rows), 2, H}, x.options().dtype(at::kFloat));
+  Tensor dgamma = torch::empty({H}, x.options());
+  Tensor dbeta = (has_bias && !rms) ? torch::empty({H}, x.options()) : Tensor();
+  check(b200_ln_bwd(x.data_ptr(), w.data_ptr(), stats.data_ptr<float>(), dy.data_ptr(), dx.data_ptr(), partial.data_ptr<float>(),
+                    dgamma.data_ptr(), dbeta.defined() ? dbeta.data_ptr() : nullptr, rows, H, x.stride(0), dy.stride(0),
+                    rms ? 1 : 0, stream()),
+        "ln_bwd");
+  return {dx, dgamma, dbeta};
+}
+
+Tensor colsum(const Tensor& x) {
+  CHECK_BF16(x);
+  TORCH_CHECK(x.dim() == 2 && x.stride(1) == 1 && x.size(1) % 2 == 0 && x.stride(0) % 2 == 0 &&
+              reinterpret_cast<uintptr_t>(x.data_ptr()) % 4 == 0, "colsum: bf16 [M, N] with even N and pitch");
+  c10::cuda::CUDAGuard guard(x.device());
+  Tensor out = torch::empty({x.size(1)}, x.options());
+  check(b200_colsum_bf16(x.data_ptr(), out.data_ptr(), (int)x.size(0), (int)x.size(1), x.stride(0), stream()), "colsum");
+  return out;
 }
 
 // LM-head backward: d-logits[M, N] (bf16, row pitch padded to a multiple of 64 so every consumer is vectorised) from
@@ -795,6 +846,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("causal") = false, py::arg("scale") = 1.0);
   m.def("attn_short_bwd", &attn_short_bwd, py::arg("q"), py::arg("k"), py::arg("v"), py::arg("bias"), py::arg("o"),
         py::arg("d_o"), py::arg("stats"), py::arg("causal") = false, py::arg("scale") = 1.0);
+  m.def("ln_train_ok", [](int64_t h) { return b200_ln_train_ok((int)h) != 0; });
+  m.def("ln_fwd", &ln_fwd, py::arg("x"), py::arg("w"), py::arg("b") = py::none(), py::arg("eps") = 1e-5, py::arg("rms") = false);
+  m.def("ln_bwd", &ln_bwd, py::arg("x"), py::arg("w"), py::arg("stats"), py::arg("dy"), py::arg("rms") = false,
+        py::arg("has_bias") = true);
+  m.def("colsum", &colsum, py::arg("x"));
   m.def("set_pdl", [](bool on) { b200_set_pdl(on ? 1 : 0); }, "enable/disable programmatic dependent launch for the kernels");
   m.def("get_pdl", [] { return b200_get_pdl() != 0; });
   py::class_<PagedKVAllocator>(m, "PagedKVAllocator")

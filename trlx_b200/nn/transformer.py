@@ -70,6 +70,11 @@ class Norm(nn.Module):
         self.bias = nn.Parameter(torch.zeros(spec.hidden_size, dtype=dtype)) if spec.norm == "layernorm" else None
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if x.is_cuda and x.dtype == torch.bfloat16:
+            from trlx_b200 import ops
+
+            if ops.norm_ok(x, self.weight, self.bias):  # forward keeps (mean, rstd); one-pass backward (csrc/norm_train.cu)
+                return ops.layer_norm(x, self.weight, self.bias, self.eps, self.kind != "layernorm")
         if self.kind == "layernorm":
             return F.layer_norm(x, (x.shape[-1],), self.weight, self.bias, self.eps)
         xf = x.float()

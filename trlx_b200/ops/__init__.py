@@ -120,7 +120,9 @@ from trlx_b200.ops.functional import (  # noqa: E402,F401
     attention,
     fused_logprob,
     gae_and_whiten,
+    layer_norm,
     linear,
     logprobs_from_logits,
+    norm_ok,
     ppo_loss,
 )

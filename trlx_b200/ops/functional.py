@@ -61,6 +61,56 @@ def grad_weight(g2: torch.Tensor, x2: torch.Tensor) -> torch.Tensor:
     return g2.t() @ x2
 
 
+def col_sum(g2: torch.Tensor) -> torch.Tensor:
+    """Bias gradient ``g2.sum(0)`` of a bf16 ``[M, N]`` matrix on the 64-column-per-CTA kernel (``csrc/norm_train.cu``)."""
+    C = _ops().C
+    if (hasattr(C, "colsum") and g2.is_cuda and g2.dtype == torch.bfloat16 and g2.dim() == 2 and g2.stride(1) == 1
+            and g2.shape[1] % 2 == 0 and g2.stride(0) % 2 == 0 and g2.data_ptr() % 4 == 0):
+        return C.colsum(g2)
+    return g2.sum(0)
+
+
+class _Norm(torch.autograd.Function):
+    """LayerNorm / RMSNorm over the last dimension with the row statistics kept for a one-pass backward."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, eps, rms):
+        C = _ops().C
+        x2 = _as_2d(x)
+        y, stats = C.ln_fwd(x2, w, None if rms else b, eps, rms)
+        ctx.save_for_backward(x2, w, stats)
+        ctx.rms, ctx.has_bias, ctx.x_shape = rms, (b is not None and not rms), x.shape
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x2, w, stats = ctx.saved_tensors
+        dx, dg, db = _ops().C.ln_bwd(x2, w, stats, _as_2d(gy), ctx.rms, ctx.has_bias)
+        return dx.view(ctx.x_shape), dg, (db if ctx.has_bias else None), None, None
+
+
+_OWN_NORM = os.environ.get("TRLX_B200_NORM", "own") != "torch"
+
+
+def norm_ok(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor]) -> bool:
+    """The training-side norm kernels apply: CUDA bf16, contiguous 16-byte aligned parameters, H % 8 == 0, H <= 4096."""
+    if not (_OWN_NORM and x.is_cuda and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and _ops().available()):
+        return False
+    C = _ops().C
+    if not hasattr(C, "ln_fwd") or not C.ln_train_ok(x.shape[-1]):
+        return False
+    ok = w.is_contiguous() and w.data_ptr() % 16 == 0
+    if b is not None:
+        ok = ok and b.dtype == torch.bfloat16 and b.is_contiguous() and b.data_ptr() % 16 == 0
+    return ok
+
+
+def layer_norm(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], eps: float, rms: bool = False) -> torch.Tensor:
+    """``LayerNorm(x)`` (or ``RMSNorm`` with ``rms``) on the in-repo forward / backward kernels; callers check
+    :func:`norm_ok` first."""
+    return _Norm.apply(x, w, b, float(eps), bool(rms))
+
+
 class _Linear(torch.autograd.Function):
     """y = x @ w.T + b (+ residual) — forward and both backward GEMMs on the tcgen05 kernel."""
 
@@ -86,7 +136,7 @@ class _Linear(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             gw = grad_weight(g2, x2)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = g2.sum(0)
+            gb = col_sum(g2)
         if ctx.has_res and ctx.needs_input_grad[3]:
             gr = gy
         return gx, gw, gb, gr
@@ -193,7 +243,7 @@ class _FusedLogprob(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             gw = grad_weight(logits, h2)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = logits.sum(0)
+            gb = col_sum(logits)
         return gh, gw, gb, None
 
 
