@@ -24,6 +24,15 @@ class MegatronMixin:
             from trlx_b200.parallel.megatron_cfg import apply_megatron_cfg
 
             config = apply_megatron_cfg(config, tk["megatron_cfg"], tk.get("pretrained_model"))
+            try:  # step / wall-clock limits of the recipe's ``trainer`` section (PTL Trainer + StatelessTimer in the reference)
+                from trlx_b200.trainer.nemo_ilql_trainer import megatron_trainer
+
+                plan = megatron_trainer(tk["megatron_cfg"], seed_everything=False)  # ``train()`` seeded already
+                self._max_time = plan.max_time
+                if plan.max_steps:
+                    config = config.evolve(train=dict(total_steps=min(int(plan.max_steps), int(config.train.total_steps))))
+            except (KeyError, ValueError, TypeError, OSError) as err:
+                logger.warning(f"megatron_cfg: trainer section not applied ({err})")
         pp = int(getattr(config.train.parallel, "pipeline_parallel", 1) or 1)
         if pp > 1:
             if config.model.model_arch_type == "seq2seq":

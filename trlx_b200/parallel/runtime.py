@@ -74,6 +74,7 @@ class Runtime:
         set_statistics_group(None)
         if not self.distributed or (tp == 1 and pp == 1):
             self.dp_group = None  # WORLD
+            self._publish_state()
             return
         for p in range(pp):
             for d in range(self.dp_size):
@@ -94,6 +95,15 @@ class Runtime:
                 if self.rank in ranks:
                     self.pp_group = g
         set_statistics_group(self.dp_group)  # model-parallel peers hold identical data: statistics span DP only
+        self._publish_state()
+
+    def _publish_state(self):
+        """Make the layout visible to group-less building blocks (``parallel/state.py``)."""
+        from trlx_b200.parallel.state import set_model_parallel
+
+        set_model_parallel(tp_group=self.tp_group, tp_rank=self.tp_rank, tp_size=self.tp_size, pp_group=self.pp_group,
+                           pp_rank=self.pp_rank, pp_size=self.pp_size, dp_group=self.dp_group, dp_rank=self.dp_rank,
+                           dp_size=self.dp_size)
 
     @property
     def is_replica_leader(self) -> bool:

@@ -67,11 +67,31 @@ def _materialise(stats: Dict[str, Any]) -> Dict[str, Any]:
     return stats
 
 
+def _parse_max_time(value) -> Optional[float]:
+    """Seconds from a number or a ``"DD:HH:MM:SS"`` string (``None`` → no limit)."""
+    if value is None or value == "":
+        return None
+    if isinstance(value, (int, float)):
+        return float(value)
+    parts = [int(p) for p in str(value).split(":")]
+    while len(parts) < 4:
+        parts.insert(0, 0)
+    d, h, m, sec = parts[-4:]
+    return float(((d * 24 + h) * 60 + m) * 60 + sec)
+
+
 @register_trainer
 class AccelerateRLTrainer(BaseRLTrainer):
     """Abstract trainer on the B200 runtime."""
 
+    #: ``train.trainer_kwargs`` keys that configure this framework's trainers (read from the config where they are used);
+    #: everything else in ``trainer_kwargs`` is a constructor argument, exactly as in the reference (``trlx/trlx.py:92-98``)
+    FRAMEWORK_KWARGS = ("prompt_bucket", "rank0_reward", "cache_trunk", "zero_stage", "max_time", "megatron_cfg",
+                        "pretrained_model")
+
     def __init__(self, config: TRLConfig, **kwargs):
+        for key in self.FRAMEWORK_KWARGS:
+            kwargs.pop(key, None)
         super().__init__(config, **kwargs)
         self.max_length = config.train.seq_length
         if config.train.minibatch_size:
@@ -499,6 +519,8 @@ class AccelerateRLTrainer(BaseRLTrainer):
         tbar = logging.tqdm(initial=self.iter_count, total=self.total_steps, disable=not self.runtime.is_main_process,
                             position=0, leave=True)
         best_reward = -float("inf")
+        time_limit = _parse_max_time((self.config.train.trainer_kwargs or {}).get("max_time", getattr(self, "_max_time", None)))
+        t_start = time()
         for _ in range(self.config.train.epochs):
             for _ in range(self.n_inner_epochs):
                 train_dataloader = self.create_train_dataloader()
@@ -530,6 +552,16 @@ class AccelerateRLTrainer(BaseRLTrainer):
                     if self.iter_count >= self.total_steps:
                         tbar.close()
                         return results
+                    if time_limit is not None:
+                        # wall-clock budget (the reference's NeMo path stops through PTL's StatelessTimer,
+                        # ``trlx/trainer/nemo_ilql_trainer.py:72-77``): all ranks agree, checkpoint, stop cleanly
+                        up = torch.tensor(int(time() - t_start >= time_limit), device=self.runtime.device)
+                        self.runtime.all_reduce(up, "max")
+                        if bool(up.item()):
+                            logger.info(f"max_time reached after {self.iter_count} steps: saving a checkpoint and stopping")
+                            self._save_checkpoint(os.path.join(self.config.train.checkpoint_dir, self._checkpoint_name()))
+                            tbar.close()
+                            return results
                 self.post_backward_callback()
             self.post_epoch_callback()
         tbar.close()
