@@ -107,3 +107,41 @@ def test_sweep_default_config_yaml_is_applied_under_sampled_hparams(tmp_path):
     assert proc.wait(timeout=120) == 0, (tdir / "stdout.log").read_text()
     seen = json.loads((tdir / "seen.json").read_text())
     assert seen == {"bs": 5, "seq": 77, "lr": 0.5}
+
+
+@pytest.mark.parametrize("alg", ["random", "bayesopt", "bohb"])
+def test_search_algorithms_propose_inside_the_space_and_use_observations(alg):
+    import math
+
+    from trlx_b200 import sweep
+
+    space = {"lr": {"strategy": "loguniform", "values": [1e-6, 1e-2]}, "x": {"strategy": "quniform", "values": [0, 1, 0.05]},
+             "n": {"strategy": "randint", "values": [1, 9]}, "c": {"strategy": "choice", "values": ["a", "b"]}}
+    searcher = sweep.get_search_alg({"search_alg": alg, "num_samples": 24, "mode": "min"}, space, seed=0)
+    seen, best = 0, float("inf")
+    while True:
+        hp = searcher.suggest()
+        if hp is None:
+            break
+        seen += 1
+        assert 1e-6 <= hp["lr"] <= 1e-2 and 0 <= hp["x"] <= 1 and 1 <= hp["n"] < 9 and hp["c"] in ("a", "b")
+        assert abs(hp["x"] / 0.05 - round(hp["x"] / 0.05)) < 1e-6
+        loss = (math.log10(hp["lr"]) + 4) ** 2 + 10 * (hp["x"] - 0.3) ** 2
+        best = min(best, loss)
+        searcher.observe(hp, loss)
+    assert seen == 24 and len(searcher.history) == 24
+    assert best < 1.5  # a 2-D bowl with minimum 0: every searcher gets close within 24 trials
+    with pytest.raises(NotImplementedError):
+        sweep.get_search_alg({"search_alg": "annealing"}, space)
+
+
+def test_scheduler_rungs_and_tune_config():
+    from trlx_b200 import sweep
+
+    assert sweep.get_scheduler({"scheduler": "fifo"}) == dict(name="fifo", rungs=[None], eta=1)
+    hb = sweep.get_scheduler({"scheduler": "hyperbandforbohb", "max_t": 90, "reduction_factor": 3})
+    assert hb["rungs"] == [10, 30, 90] and hb["eta"] == 3
+    with pytest.raises(NotImplementedError):
+        sweep.get_scheduler({"scheduler": "pbt"})
+    cfg = sweep.get_tune_config({"search_alg": "bohb", "scheduler": "hyperband", "max_t": 9}, {}, 0)
+    assert cfg["metric"] == "reward/mean" and cfg["search_alg"].name == "bohb" and cfg["scheduler"]["rungs"][-1] == 9

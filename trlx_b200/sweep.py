@@ -4,8 +4,9 @@ Reference counterpart: ``trlx/sweep.py`` (Ray Tune + W&B reports): parameter-spa
 algorithms / schedulers ``:103-176``, the report ``:178-265``, the CLI ``:268-348``.  Same YAML schema and CLI, but no Ray
 and no W&B dependency: trials are plain subprocesses (``python -m torch.distributed.run`` when a trial uses several GPUs)
 scheduled over the node's GPUs, each logging through the ``jsonl`` tracker; the sweep reads the target metric back from
-those logs, supports ``random`` and grid search with ``fifo`` or successive-halving (``asha`` / ``hyperband`` names)
-scheduling, and writes ``sweep_results.json`` + a Markdown report (best trials, parameter table) instead of a W&B report.
+those logs, supports ``random`` / grid search, a Gaussian-process ``bayesopt`` searcher and a TPE (``bohb``) searcher
+(scikit-learn / pure Python, suggestions are drawn as slots free up) with ``fifo`` or successive-halving (``hyperband``,
+``hyperbandforbohb``) scheduling, and writes ``sweep_results.json`` + a Markdown report (best trials, parameter table) instead of a W&B report.
 
 An example script only has to expose ``main(hparams: dict)`` (every script under ``examples/`` does).
 """
@@ -105,6 +106,194 @@ def iter_trials(space: Dict[str, Dict[str, Any]], tune_config: Dict[str, Any], s
             yield hp
 
 
+# ---- search algorithms -------------------------------------------------------------------------------------------------------
+_NUMERIC = ("uniform", "quniform", "loguniform", "qloguniform", "randint", "qrandint", "lograndint", "qlograndint")
+
+
+def _to_unit(spec: Dict[str, Any], value) -> Optional[float]:
+    """Position of ``value`` inside the range of a numeric entry, on the scale it is sampled on (``None``: not numeric)."""
+    st, v = spec["strategy"], spec["values"]
+    if st not in _NUMERIC:
+        return None
+    lo, hi = float(v[0]), float(v[1])
+    if "log" in st:
+        lo, hi, value = math.log(lo), math.log(hi), math.log(max(float(value), 1e-300))
+    return min(max((float(value) - lo) / max(hi - lo, 1e-12), 0.0), 1.0)
+
+
+def _from_unit(spec: Dict[str, Any], u: float):
+    st, v = spec["strategy"], spec["values"]
+    lo, hi = float(v[0]), float(v[1])
+    if "log" in st:
+        x = math.exp(math.log(lo) + u * (math.log(hi) - math.log(lo)))
+    else:
+        x = lo + u * (hi - lo)
+    x = min(max(x, lo), hi)  # exp(log(hi)) may overshoot by an ulp
+    if st in ("quniform", "qloguniform", "qrandint", "qlograndint"):
+        x = _quantize(x, v[2])
+    if "int" in st:
+        x = int(min(max(round(x), int(lo)), int(hi) - (1 if st == "randint" else 0)))
+    return x
+
+
+class RandomSearcher:
+    """Grid entries enumerated exhaustively, everything else re-sampled ``num_samples`` times per grid point."""
+
+    name = "random"
+
+    def __init__(self, space, tune_config, seed: int = 0):
+        self.space, self.mode = space, tune_config.get("mode", "max")
+        self._it = iter_trials(space, tune_config, seed)
+        self.history: List[Tuple[Dict[str, Any], float]] = []
+
+    def suggest(self) -> Optional[Dict[str, Any]]:
+        return next(self._it, None)
+
+    def observe(self, hparams: Dict[str, Any], score: Optional[float]) -> None:
+        if score is not None and math.isfinite(score):
+            self.history.append((hparams, score if self.mode == "max" else -score))
+
+
+class _ModelBasedSearcher(RandomSearcher):
+    """Common part of the sequential searchers: ``n_initial`` random trials, then ``_propose`` from the observations.
+    Numeric entries are modelled on the unit interval of their sampling scale; ``choice`` / grid entries are drawn at
+    random and only enter the model through the numeric coordinates they co-occur with."""
+
+    def __init__(self, space, tune_config, seed: int = 0):
+        super().__init__(space, tune_config, seed)
+        self.rng = random.Random(seed + 1)
+        self.numeric = [k for k, sp in space.items() if sp["strategy"] in _NUMERIC]
+        grid = 1
+        for sp in space.values():
+            if sp["strategy"] in ("grid_search", "grid"):
+                grid *= max(len(sp["values"]), 1)
+        self.total = int(tune_config.get("num_samples", 1)) * grid
+        self.n_initial = int(tune_config.get("n_initial_points", max(4, 2 * len(self.numeric))))
+        self.issued = 0
+
+    def _random(self) -> Dict[str, Any]:
+        return {k: sample_value(sp, self.rng) for k, sp in self.space.items()}
+
+    def _unit(self, hp) -> List[float]:
+        return [_to_unit(self.space[k], hp[k]) for k in self.numeric]
+
+    def suggest(self) -> Optional[Dict[str, Any]]:
+        if self.issued >= self.total:
+            return None
+        self.issued += 1
+        if not self.numeric or len(self.history) < self.n_initial:
+            return self._random()
+        hp = self._random()
+        for k, u in zip(self.numeric, self._propose()):
+            hp[k] = _from_unit(self.space[k], u)
+        return hp
+
+    def _propose(self) -> List[float]:  # pragma: no cover - abstract
+        raise NotImplementedError
+
+
+class BayesOptSearcher(_ModelBasedSearcher):
+    """Gaussian-process surrogate (Matérn 5/2, scikit-learn) + expected improvement maximised over random candidates —
+    the role of Ray Tune's ``BayesOptSearch`` in the reference (``trlx/sweep.py:103-133``)."""
+
+    name = "bayesopt"
+
+    def _propose(self) -> List[float]:
+        try:
+            import numpy as np
+            from scipy.stats import norm
+            from sklearn.gaussian_process import GaussianProcessRegressor
+            from sklearn.gaussian_process.kernels import ConstantKernel, Matern, WhiteKernel
+        except ImportError:  # pragma: no cover
+            return [self.rng.random() for _ in self.numeric]
+        X = np.array([self._unit(hp) for hp, _ in self.history])
+        y = np.array([sc for _, sc in self.history], dtype=float)
+        y = (y - y.mean()) / (y.std() + 1e-9)
+        gp = GaussianProcessRegressor(ConstantKernel(1.0) * Matern(length_scale=0.3, nu=2.5) + WhiteKernel(1e-3),
+                                      normalize_y=False, random_state=self.rng.randrange(2 ** 31))
+        import warnings
+
+        with warnings.catch_warnings():  # hyper-parameter fit on a handful of points: convergence chatter is expected
+            warnings.simplefilter("ignore")
+            gp.fit(X, y)
+        cand = np.array([[self.rng.random() for _ in self.numeric] for _ in range(512)])
+        mu, sd = gp.predict(cand, return_std=True)
+        best = y.max()
+        z = (mu - best - 0.01) / np.maximum(sd, 1e-9)
+        ei = (mu - best - 0.01) * norm.cdf(z) + sd * norm.pdf(z)
+        return [float(v) for v in cand[int(np.argmax(ei))]]
+
+
+class TPESearcher(_ModelBasedSearcher):
+    """Tree-structured Parzen estimator (the model inside BOHB, ``search_alg: bohb``): kernel density of the best quarter of
+    the observations against the rest, candidates drawn from the former and ranked by the density ratio."""
+
+    name = "bohb"
+
+    def _propose(self) -> List[float]:
+        ranked = sorted(self.history, key=lambda t: t[1], reverse=True)
+        n_good = max(len(ranked) // 4, 2)
+        good = [self._unit(hp) for hp, _ in ranked[:n_good]]
+        bad = [self._unit(hp) for hp, _ in ranked[n_good:]] or good
+
+        def density(points, x, bw):
+            return sum(math.exp(-0.5 * ((x - p) / bw) ** 2) for p in points) / (len(points) * bw) + 1e-12
+
+        out = []
+        for d in range(len(self.numeric)):
+            g, b = [p[d] for p in good], [p[d] for p in bad]
+            bw = max(1.06 * (max(g) - min(g) + 0.1) * len(g) ** -0.2, 0.05)
+            cands = [min(max(self.rng.gauss(self.rng.choice(g), bw), 0.0), 1.0) for _ in range(24)]
+            out.append(max(cands, key=lambda x: density(g, x, bw) / density(b, x, bw)))
+        return out
+
+
+def get_search_alg(tune_config: Dict[str, Any], space: Optional[Dict[str, Dict[str, Any]]] = None, seed: int = 0):
+    """``search_alg`` of the sweep YAML → searcher with ``suggest()`` / ``observe(hparams, score)`` (reference
+    ``trlx/sweep.py:103-133``: ``bayesopt``, ``bohb``, ``random``; unknown names raise like the reference)."""
+    name = str(tune_config.get("search_alg", "random") or "random").lower()
+    space = space or {}
+    if name in ("random", "grid"):
+        return RandomSearcher(space, tune_config, seed)
+    if name == "bayesopt":
+        return BayesOptSearcher(space, tune_config, seed)
+    if name in ("bohb", "tpe"):
+        return TPESearcher(space, tune_config, seed)
+    raise NotImplementedError(f"search_alg `{name}` is not supported (random, bayesopt, bohb)")
+
+
+def get_scheduler(tune_config: Dict[str, Any]) -> Dict[str, Any]:
+    """``scheduler`` of the sweep YAML → ``dict(name, rungs, eta)`` (reference ``:136-158``: ``hyperband``,
+    ``hyperbandforbohb``, ``fifo``).  The hyperband family runs successive halving: rungs of growing step budget
+    (``grace_period · eta^i`` up to ``max_t``), the best ``1/eta`` of a rung is promoted."""
+    name = str(tune_config.get("scheduler", "fifo") or "fifo").lower()
+    if name in ("hyperband", "hyperbandforbohb", "asha", "bohb", "median"):
+        max_t = int(tune_config.get("max_t", tune_config.get("max_steps", 0)) or 0)
+        eta = int(tune_config.get("reduction_factor", 3))
+        grace = int(tune_config.get("grace_period", max(max_t // (eta ** 2), 1))) if max_t else None
+        rungs: List[Optional[int]] = []
+        t = grace
+        while max_t and t < max_t:
+            rungs.append(t)
+            t *= eta
+        rungs.append(max_t if max_t else None)
+        return dict(name=name, rungs=rungs, eta=eta)
+    if name != "fifo":
+        raise NotImplementedError(f"scheduler `{name}` is not supported (fifo, hyperband, hyperbandforbohb)")
+    return dict(name="fifo", rungs=[None], eta=1)
+
+
+def get_tune_config(tune_config: Dict[str, Any], space: Optional[Dict[str, Dict[str, Any]]] = None, seed: int = 0) -> Dict[str, Any]:
+    """Normalised ``tune_config`` with the searcher and scheduler objects filled in (reference ``:161-176``)."""
+    cfg = dict(tune_config)
+    cfg.setdefault("metric", "reward/mean")
+    cfg.setdefault("mode", "max")
+    cfg.setdefault("num_samples", 1)
+    cfg["search_alg"] = get_search_alg(tune_config, space, seed)
+    cfg["scheduler"] = get_scheduler(tune_config)
+    return cfg
+
+
 # ---- running trials ------------------------------------------------------------------------------------------------------------
 _TRIAL_SNIPPET = """
 import importlib.util, json, sys
@@ -172,9 +361,11 @@ def run_sweep(script: str, sweep_config: Dict[str, Any], out_dir: str, num_gpus:
               default_config: Optional[str] = None, seed: int = 0, poll: float = 1.0) -> List[Dict[str, Any]]:
     tune_config = dict(sweep_config.get("tune_config", {}))
     metric, mode = tune_config.get("metric", "reward/mean"), tune_config.get("mode", "max")
-    scheduler = str(tune_config.get("scheduler", "fifo")).lower()
     space = get_param_space(sweep_config)
-    trials = [dict(id=i, hparams=hp) for i, hp in enumerate(iter_trials(space, tune_config, seed))]
+    searcher = get_search_alg(tune_config, space, seed)
+    sched = get_scheduler(tune_config)
+    rungs, eta = sched["rungs"], sched["eta"]
+    trials: List[Dict[str, Any]] = []
     os.makedirs(out_dir, exist_ok=True)
     if gpu_ids is None:
         try:
@@ -190,36 +381,33 @@ def run_sweep(script: str, sweep_config: Dict[str, Any], out_dir: str, num_gpus:
         slots = [[] for _ in range(max(max_conc, 1))]
     slots = slots[:max(max_conc, 1)]
 
-    # successive halving ("asha"/"hyperband"/"bohb" schedulers): rungs of growing step budget, keep the top 1/eta
-    if scheduler in ("hyperband", "asha", "bohb", "median"):
-        max_t = int(tune_config.get("max_t", tune_config.get("max_steps", 0)) or 0)
-        eta = int(tune_config.get("reduction_factor", 3))
-        grace = int(tune_config.get("grace_period", max(max_t // (eta ** 2), 1))) if max_t else None
-        rungs = []
-        t = grace
-        while max_t and t < max_t:
-            rungs.append(t)
-            t *= eta
-        rungs.append(max_t if max_t else None)
-    else:
-        if scheduler != "fifo":
-            print(f"[sweep] unknown scheduler `{scheduler}`; running every trial to completion (fifo)")
-        rungs, eta = [None], 1
-
-    alive = trials
+    alive: List[Dict[str, Any]] = []
     for rung_i, budget in enumerate(rungs):
+        # rung 0 draws its trials from the searcher as slots free up (model-based searchers see the results so far);
+        # later rungs re-run the promoted trials with a larger step budget
         pending = list(alive)
+        exhausted = rung_i > 0
         running: List[Tuple[Dict[str, Any], subprocess.Popen, List[int]]] = []
         free = list(slots)
-        while pending or running:
-            while pending and free:
-                tr = pending.pop(0)
+        while pending or running or not exhausted:
+            while free and (pending or not exhausted):
+                if pending:
+                    tr = pending.pop(0)
+                else:
+                    hp = searcher.suggest()
+                    if hp is None:
+                        exhausted = True
+                        break
+                    tr = dict(id=len(trials), hparams=hp)
+                    trials.append(tr)
                 slot = free.pop(0)
                 tdir = os.path.join(out_dir, f"trial_{tr['id']:04d}", f"rung_{rung_i}")
                 tr["dir"] = tdir
                 proc = launch_trial(script, tr["hparams"], tdir, slot, budget, default_config)
                 running.append((tr, proc, slot))
                 print(f"[sweep] trial {tr['id']} (rung {rung_i}, budget {budget}) started on gpus {slot}: {tr['hparams']}")
+            if not running:
+                continue
             time.sleep(poll)
             for item in list(running):
                 tr, proc, slot = item
@@ -230,7 +418,11 @@ def run_sweep(script: str, sweep_config: Dict[str, Any], out_dir: str, num_gpus:
                 free.append(slot)
                 best, last, n = read_metric(tr["dir"], metric, mode)
                 tr.update(returncode=rc, best=best, last=last, points=n, budget=budget)
+                if rung_i == 0:
+                    searcher.observe(tr["hparams"], best)
                 print(f"[sweep] trial {tr['id']} finished rc={rc} {metric}: best={best} last={last}")
+        if rung_i == 0:
+            alive = list(trials)
         if rung_i < len(rungs) - 1:
             scored = [t for t in alive if t.get("best") is not None]
             scored.sort(key=lambda t: t["best"], reverse=(mode == "max"))
@@ -267,6 +459,11 @@ def write_report(results, space, metric: str, mode: str, script: str, path: str)
             lines.append(f"* `{k}`: " + ", ".join(f"{v if not isinstance(v, float) else format(v, '.3g')}→{b:.4g}" for v, b in pts))
     with open(path, "w") as fh:
         fh.write("\n".join(lines) + "\n")
+
+
+def create_report(results, space, metric: str, mode: str, script: str, path: str) -> None:
+    """Name used by the reference (``trlx/sweep.py:177-264``, a W&B report there); writes the Markdown report."""
+    write_report(results, space, metric, mode, script, path)
 
 
 def main(argv: Optional[List[str]] = None) -> int:
