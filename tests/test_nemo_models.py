@@ -285,3 +285,79 @@ def _ppogpt_tp_job(rank, world):
 def test_ppogpt_tensor_parallel_matches_dense():
     for res in run_distributed(_ppogpt_tp_job, 2):
         assert res["logits"] < 1e-4 and res["value"] < 1e-4 and res["head_rows"] == 16, res
+
+
+def test_megatron_batch_sampler_slices_global_batches_per_rank():
+    from trlx_b200.models.megatron_api import MegatronBatchSampler
+
+    r0 = list(MegatronBatchSampler(22, 0, 2, 8, 0, 2))
+    r1 = list(MegatronBatchSampler(22, 0, 2, 8, 1, 2))
+    assert r0 == [[0, 1, 2, 3], [8, 9, 10, 11]] and r1 == [[4, 5, 6, 7], [12, 13, 14, 15]]
+    assert list(MegatronBatchSampler(22, 8, 2, 8, 1, 2)) == [[12, 13, 14, 15]]  # resume after 8 consumed samples
+    assert len(MegatronBatchSampler(22, 0, 2, 8, 0, 2)) == 2
+    with pytest.raises(ValueError):
+        MegatronBatchSampler(22, 0, 3, 8, 0, 2)
+
+
+def test_model_api_training_step_checkpoint_and_inference_mode(tmp_path):
+    from trlx_b200.data.default_configs import default_ppo_config, default_sft_config
+    from trlx_b200.data.ppo_types import PPORLBatch
+    from trlx_b200.models.modeling_nemo_ppo import PPOGPT
+    from trlx_b200.models.modeling_nemo_sft import SFTGPT
+    from trlx_b200.parallel.state import set_model_parallel
+
+    set_model_parallel()
+    torch.manual_seed(0)
+    cfg = default_ppo_config().evolve(model=dict(model_path=_TINY, num_layers_unfrozen=1), train=dict(batch_size=4, minibatch_size=2))
+    model = PPOGPT(cfg)
+    B, Q, R = 4, 5, 3
+    batch = PPORLBatch(query_tensors=torch.randint(1, 50, (B, Q)), response_tensors=torch.randint(1, 50, (B, R)),
+                       logprobs=torch.randn(B, R) * 0.1 - 2, values=torch.randn(B, R) * 0.1, rewards=torch.randn(B, R) * 0.1)
+    opt, _ = model.configure_optimizers()
+    before = [p.detach().clone() for p in model.parameters() if p.requires_grad]
+    stats = model.training_step(batch, opt)
+    assert "loss" in stats and any(not torch.equal(a, b) for a, b in zip(before, (p for p in model.parameters() if p.requires_grad)))
+    lp, rlp, val = model.infer_logprobs_and_values(torch.randint(1, 50, (2, 7)))
+    assert lp.shape == rlp.shape == val.shape == (2, 6)
+    path = model.save_pretrained(str(tmp_path))
+    assert path.endswith(os.path.join("mp_rank_00", "model_weights.ckpt")) and os.path.exists(path)
+    clone = PPOGPT(cfg)
+    clone.load_from_pretrained(str(tmp_path), strict=True)
+    ids = torch.randint(1, 50, (2, 7))
+    torch.testing.assert_close(clone(ids).logits, model(ids).logits)
+    loader = model.build_data_loader(list(range(20)), lambda xs: xs)
+    assert [len(b) for b in loader] == [4] * 5
+
+    sft = SFTGPT(default_sft_config().evolve(model=dict(model_path=_TINY)), dtype=torch.float32)
+    sft.activation_checkpointing_(True)
+    with sft.inference_mode():
+        assert not torch.is_grad_enabled() and not sft.training
+        assert not any(getattr(m, "gradient_checkpointing", False) for m in sft.modules())
+    assert sft.training and any(getattr(m, "gradient_checkpointing", False) for m in sft.modules())
+    opt, _ = sft.configure_optimizers()
+    l0 = sft.training_step(dict(input_ids=torch.arange(16).view(2, 8) % 50), opt)["loss"]
+    l1 = sft.training_step(dict(input_ids=torch.arange(16).view(2, 8) % 50), opt)["loss"]
+    assert l1 < l0
+    assert sft.maybe_initalize_per_dp_rng(3).initial_seed() == 3
+
+
+def test_ilqlgpt_training_step_and_generate():
+    from trlx_b200.data.default_configs import default_ilql_config
+    from trlx_b200.models.modeling_nemo_ilql import ILQLGPT
+    from trlx_b200.parallel.state import set_model_parallel
+    from trlx_b200.trainer.accelerate_ilql_trainer import make_experience
+    from trlx_b200.utils.tokenizer import build_toy_tokenizer
+
+    set_model_parallel()
+    torch.manual_seed(0)
+    cfg = default_ilql_config().evolve(model=dict(model_path=_TINY))
+    model = ILQLGPT(cfg.method, cfg, dtype=torch.float32)
+    tok = build_toy_tokenizer("toy://chars?alphabet=abcdefghij")
+    store = make_experience([["ab", "cd"], ["ef", "gh"], ["ab", "ij"], ["cd", "ef"]], [1.0, 0.5, 0.2, 0.9], tok, max_length=16,
+                            verbose=False)
+    batch = next(iter(store.create_loader(4)))
+    opt, _ = model.configure_optimizers()
+    stats = model.training_step(batch, opt)
+    assert stats["loss"] > 0 and "losses/loss_q" in stats
+    out = model.generate(torch.randint(1, 10, (2, 3)), max_new_tokens=3)
+    assert out.shape == (2, 6)

@@ -15,6 +15,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from trlx_b200.models.megatron_api import MegatronModelMixin, unwrap_float16_module  # noqa: F401
 from trlx_b200.models.modeling_nemo_ppo import make_parallel_head, reshard_for_pipeline_parallelism  # noqa: F401
 from trlx_b200.parallel import state as parallel_state
 
@@ -66,14 +67,14 @@ class LMHeads(nn.Module):
         return out.logits, self.other_heads(out.hidden_states[-1])
 
 
-class ILQLGPT(nn.Module):
+class ILQLGPT(MegatronModelMixin, nn.Module):
     """Causal LM (tensor-parallel blocks) with :class:`ParallelILQLHeads`, plus the reference's advantage-shifted
     next-token distribution for generation (``:723-735``): ``log π_β + β · (min target-Q − V)``."""
 
     def __init__(self, ilql_config, config=None, language_model: Optional[nn.Module] = None, hidden_size: Optional[int] = None,
-                 vocab_size: Optional[int] = None, dtype: torch.dtype = torch.bfloat16):
+                 vocab_size: Optional[int] = None, dtype: torch.dtype = torch.bfloat16, metric_fn=None):
         super().__init__()
-        self.ilql_config = ilql_config
+        self.ilql_config, self.config, self.metric_fn = ilql_config, config, metric_fn
         if language_model is None:
             from trlx_b200.models.modeling_base import build_base_model
             from trlx_b200.parallel.tensor_parallel import apply_tensor_parallel
@@ -107,3 +108,37 @@ class ILQLGPT(nn.Module):
 
     def sync_target_q_heads(self) -> None:
         self.heads.sync_target_q_heads()
+
+    def _loss(self, batch):
+        """ILQL loss of one :class:`~trlx_b200.data.ilql_types.ILQLBatch` (reference loss closure ``:612-683``): heads are
+        evaluated on the state / action positions only."""
+        from trlx_b200.models.modeling_ilql import batched_index_select
+
+        dev = next(self.parameters()).device
+        batch = type(batch)(**{k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in vars(batch).items()})
+        out = self.model.language_model(batch.input_ids, attention_mask=batch.attention_mask, output_hidden_states=True)
+        hs = out.hidden_states[-1]
+        qs, target_qs, _ = self.heads(batched_index_select(hs, batch.actions_ixs, 1))
+        vs = self.heads.v_head(batched_index_select(hs, batch.states_ixs, 1))
+        return self.ilql_config.loss((out.logits, (qs, target_qs, vs)), batch)
+
+    @torch.no_grad()
+    def generate(self, input_ids, attention_mask=None, max_new_tokens: int = 16, beta: Optional[float] = None,
+                 temperature: float = 1.0, do_sample: bool = False, eos_token_id: Optional[int] = None,
+                 pad_token_id: int = 0, **_):
+        """Sampling from the advantage-shifted distribution, one token at a time (reference ``:737-785``)."""
+        ids = input_ids
+        am = attention_mask if attention_mask is not None else torch.ones_like(ids)
+        done = torch.zeros(ids.shape[0], dtype=torch.bool, device=ids.device)
+        for _step in range(int(max_new_tokens)):
+            pos = (am.long().cumsum(-1) - 1).clamp_min(0)
+            scores = self.shifted_logits(ids, am, pos, beta) / max(float(temperature), 1e-6)
+            nxt = torch.multinomial(torch.softmax(scores, -1), 1).squeeze(-1) if do_sample else scores.argmax(-1)
+            nxt = torch.where(done, torch.full_like(nxt, pad_token_id), nxt)
+            ids = torch.cat([ids, nxt.unsqueeze(-1)], 1)
+            am = torch.cat([am, (~done).long().unsqueeze(-1)], 1)
+            if eos_token_id is not None:
+                done = done | (nxt == eos_token_id)
+                if bool(done.all()):
+                    break
+        return ids

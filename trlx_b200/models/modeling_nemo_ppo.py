@@ -29,6 +29,8 @@ import torch.distributed as dist
 import torch.nn as nn
 import torch.nn.functional as F
 
+from trlx_b200.models.megatron_api import (MegatronBatchSampler, MegatronModelMixin,  # noqa: F401  (re-exported)
+                                           patch_attention_for_llama, unwrap_float16_module)
 from trlx_b200.parallel import state as parallel_state
 from trlx_b200.parallel.tensor_parallel import _CopyToTP, _ReduceFromTP
 from trlx_b200.utils import logging
@@ -303,7 +305,7 @@ def reshard_for_pipeline_parallelism(num_layers: int, state_dict: Dict[str, Any]
     return out
 
 
-class PPOGPT(nn.Module):
+class PPOGPT(MegatronModelMixin, nn.Module):
     """The model the model-parallel PPO trainer optimises (reference ``PPOGPT(MegatronGPTModel)``, ``:355-1222``): a
     causal LM whose blocks are sharded over the tensor-parallel group, a model-parallel :class:`ValueHead`, and the
     reference policy either as the hydra branch of the wrapped model or as :class:`RefLMHeads` host copies.
@@ -312,8 +314,10 @@ class PPOGPT(nn.Module):
     :mod:`trlx_b200.parallel.state`; the NeMo-style trainer (:class:`~trlx_b200.trainer.nemo_ppo_trainer.NeMoPPOTrainer`)
     performs the same construction through ``MegatronMixin.setup_model``."""
 
-    def __init__(self, config, build_reference_model: Optional[bool] = None, parallel_value_head: bool = True):
+    def __init__(self, config, build_reference_model: Optional[bool] = None, parallel_value_head: bool = True,
+                 pad_token_id: int = 0, metric_fn: Optional[Callable] = None):
         super().__init__()
+        self.config, self.ppo_config, self.pad_token_id, self.metric_fn = config, config.method, pad_token_id, metric_fn
         from trlx_b200.models.modeling_ppo import AutoModelForCausalLMWithHydraValueHead, AutoModelForCausalLMWithValueHead
         from trlx_b200.parallel.tensor_parallel import apply_tensor_parallel
 
@@ -361,3 +365,63 @@ class PPOGPT(nn.Module):
 
     def generate(self, *args, **kwargs):
         return self.model.generate(*args, **kwargs)
+
+    # Per-rank shards are stored with the canonical (sharded) parameter names: the wrapped model's own ``state_dict`` emits
+    # HF key names for whole, unsharded checkpoints, which is not what an ``mp_rank_XX`` file holds.
+    def state_dict(self, *args, **kwargs):
+        sd = {f"model.{k}": v for k, v in nn.Module.state_dict(self.model).items()}
+        if self.value_head is not None:
+            sd.update({f"value_head.{k}": v for k, v in self.value_head.state_dict().items()})
+        return sd
+
+    def load_state_dict(self, state_dict, strict: bool = True, **kwargs):
+        res = nn.Module.load_state_dict(self.model, {k[len("model."):]: v for k, v in state_dict.items() if k.startswith("model.")},
+                                        strict=strict)
+        if self.value_head is not None:
+            vh = {k[len("value_head."):]: v for k, v in state_dict.items() if k.startswith("value_head.")}
+            if vh or strict:
+                self.value_head.load_state_dict(vh, strict=strict)
+        if self.ref_heads is not None and self.ref_heads.build_reference_model:
+            self.ref_heads.snapshot_reference()
+        return res
+
+    def offload_reference_model(self) -> None:
+        """Make sure the *policy* weights are the ones on the device (no-op with a hydra reference branch)."""
+        if self.ref_heads is not None:
+            self.ref_heads.offload_reference_model()
+
+    @torch.no_grad()
+    def infer_logprobs_and_values(self, input_ids, attention_mask=None, position_ids=None):
+        """``(logprobs, ref_logprobs, values)`` of every next token, ``[B, T-1]`` each (reference ``:1095-1156``)."""
+        from trlx_b200.utils.modeling import logprobs_of_labels
+
+        if attention_mask is None:
+            attention_mask = input_ids.ne(self.pad_token_id).long()
+        if position_ids is None:
+            position_ids = (attention_mask.cumsum(-1) - 1).clamp_min(0)
+        with self.inference_mode():
+            out = self(input_ids, attention_mask, position_ids)
+            ref_logits = self.reference_logits(input_ids, attention_mask, position_ids)
+        labels = input_ids[:, 1:]
+        return (logprobs_of_labels(out.logits[:, :-1], labels).float(), logprobs_of_labels(ref_logits[:, :-1], labels).float(),
+                out.value[:, :-1].float())
+
+    def _loss(self, batch):
+        """PPO loss of one :class:`~trlx_b200.data.ppo_types.PPORLBatch` (the fwd/loss closure of the reference, ``:945-1026``)."""
+        from trlx_b200.utils.modeling import logprobs_of_labels
+
+        method = self.ppo_config
+        dev = next(self.parameters()).device
+        query, response = batch.query_tensors.to(dev), batch.response_tensors.to(dev)
+        old_logprobs, old_values, old_rewards = batch.logprobs.to(dev), batch.values.to(dev), batch.rewards.to(dev)
+        n_resp = old_rewards.shape[1]
+        advantages, returns = method.get_advantages_and_returns(old_values, old_rewards, n_resp)
+        tokens = torch.cat((query, response), dim=1)
+        attention_mask = tokens.ne(self.pad_token_id).long()
+        position_ids = (attention_mask.cumsum(-1) - 1).clamp_min(0)
+        out = self(tokens, attention_mask, position_ids)
+        start, end = query.shape[1] - 1, query.shape[1] - 1 + n_resp
+        logprobs = logprobs_of_labels(out.logits[:, :-1], tokens[:, 1:])[:, start:end]
+        values = out.value[:, :-1][:, start:end]
+        return method.loss(logprobs=logprobs.float(), values=values.float(), old_logprobs=old_logprobs, old_values=old_values,
+                           advantages=advantages, returns=returns, mask=attention_mask[:, start + 1:end + 1].float())

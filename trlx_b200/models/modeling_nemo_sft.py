@@ -13,6 +13,7 @@ import torch
 import torch.distributed as dist
 import torch.nn as nn
 
+from trlx_b200.models.megatron_api import MegatronModelMixin
 from trlx_b200.parallel import state as parallel_state
 
 
@@ -56,14 +57,15 @@ def vocab_parallel_cross_entropy(vocab_parallel_logits: torch.Tensor, target: to
     return _VocabParallelCrossEntropy.apply(vocab_parallel_logits, target, st.tp_group, st.tp_rank if world > 1 else 0, world)
 
 
-class SFTGPT(nn.Module):
+class SFTGPT(MegatronModelMixin, nn.Module):
     """Causal LM (tensor-parallel blocks) trained with next-token cross entropy over the positions selected by
     ``loss_mask`` (reference ``SFTGPT``).  With ``vocab_parallel=True`` the LM head weight is sharded by vocabulary rows and
     the loss is :func:`vocab_parallel_cross_entropy`; otherwise the (replicated) head feeds the fused log-prob kernel."""
 
     def __init__(self, config=None, language_model: Optional[nn.Module] = None, vocab_parallel: bool = False,
-                 dtype: torch.dtype = torch.bfloat16):
+                 dtype: torch.dtype = torch.bfloat16, metric_fn=None):
         super().__init__()
+        self.config, self.metric_fn = config, metric_fn
         st = parallel_state.get_model_parallel()
         if language_model is None:
             from trlx_b200.models.modeling_base import build_base_model
@@ -101,3 +103,20 @@ class SFTGPT(nn.Module):
             per_token = torch.nn.functional.cross_entropy(out.logits[:, :-1].float().transpose(1, 2), labels, reduction="none")
         loss = (per_token * mask).sum() / mask.sum().clamp_min(1.0)
         return loss, out.logits
+
+    def _loss(self, batch):
+        """``batch``: mapping with ``input_ids`` and optionally ``attention_mask`` / ``loss_mask`` (reference loss closure
+        ``:433-457``)."""
+        loss, _ = self(batch["input_ids"], batch.get("attention_mask"), batch.get("position_ids"), batch.get("loss_mask"))
+        return loss, {"loss": float(loss.detach())}
+
+    def build_attention_mask_and_position_ids(self, input_ids, pad_token_id: int = 0):
+        """``(attention_mask, position_ids)`` of a right- or left-padded batch (reference ``:394-406`` builds Megatron's
+        lower-triangular mask explicitly; causality is handled inside the attention kernels here)."""
+        am = input_ids.ne(pad_token_id).long()
+        return am, (am.cumsum(-1) - 1).clamp_min(0)
+
+    def generate(self, *args, **kwargs):
+        from trlx_b200.models.generation import generate
+
+        return generate(self.language_model, *args, **kwargs)

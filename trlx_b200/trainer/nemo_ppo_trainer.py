@@ -19,3 +19,11 @@ from trlx_b200.trainer.accelerate_ppo_trainer import AcceleratePPOTrainer
 @register_trainer
 class NeMoPPOTrainer(MegatronMixin, AcceleratePPOTrainer):
     """PPO with tensor/sequence/pipeline parallelism (``config.train.parallel``)."""
+
+
+def rank_0_tqdm(*args, **kwargs):
+    """``tqdm`` that only draws on the first process of the job (reference ``nemo_ppo_trainer.py:44-49``)."""
+    from trlx_b200.utils import logging, rank
+
+    kwargs.setdefault("disable", rank() != 0)
+    return logging.tqdm(*args, **kwargs)
