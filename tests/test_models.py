@@ -288,3 +288,13 @@ def test_activation_checkpointing_matches_plain_backward():
     out.loss.backward()
     for n, p in m.named_parameters():
         torch.testing.assert_close(p.grad, ref[n], atol=1e-6, rtol=1e-5)
+
+
+def test_push_to_hub_fails_cleanly_when_the_hub_is_disabled(monkeypatch):
+    from trlx_b200.models.modeling_ppo import AutoModelForCausalLMWithValueHead
+
+    monkeypatch.setenv("HF_HUB_OFFLINE", "1")
+    model = AutoModelForCausalLMWithValueHead.from_config(dict(model_type="gpt2", vocab_size=20, n_embd=8, n_layer=1, n_head=2,
+                                                                n_positions=16))
+    with pytest.raises(RuntimeError, match="disabled"):
+        model.push_to_hub("someone/some-model")

@@ -212,6 +212,26 @@ class PreTrainedModelWrapper(nn.Module):
         checkpoint_io.save_state_dict(save_directory, state_dict, max_shard_bytes=kwargs.get("max_shard_bytes"),
                                       safe_serialization=bool(kwargs.get("safe_serialization", False)))
 
+    def push_to_hub(self, repo_id: str, commit_message: str = "Upload model", private: Optional[bool] = None,
+                    token: Optional[str] = None, revision: Optional[str] = None, create_pr: bool = False, **save_kwargs):
+        """Serialise with :meth:`save_pretrained` into a temporary directory and upload it (the reference inherits this from
+        ``transformers.utils.PushToHubMixin``, ``trlx/models/modeling_base.py:37``).  Needs ``huggingface_hub`` and network
+        access; both are checked up front so an offline box fails with a clear message instead of half-way through."""
+        import tempfile
+
+        try:
+            from huggingface_hub import HfApi
+        except ImportError as err:  # pragma: no cover
+            raise RuntimeError("push_to_hub needs the `huggingface_hub` package") from err
+        if os.environ.get("HF_HUB_OFFLINE", "0") == "1" or os.environ.get("TRANSFORMERS_OFFLINE", "0") == "1":
+            raise RuntimeError("push_to_hub: the Hugging Face Hub is disabled (HF_HUB_OFFLINE / TRANSFORMERS_OFFLINE)")
+        api = HfApi(token=token)
+        with tempfile.TemporaryDirectory() as tmp:
+            self.save_pretrained(tmp, **save_kwargs)
+            api.create_repo(repo_id, private=private, exist_ok=True)
+            return api.upload_folder(repo_id=repo_id, folder_path=tmp, commit_message=commit_message, revision=revision,
+                                     create_pr=create_pr)
+
     def post_init(self, *args, **kwargs):
         """Hook run after construction in ``from_pretrained`` (loads head weights)."""
 
