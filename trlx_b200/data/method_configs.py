@@ -38,5 +38,14 @@ def get_method(name: str):
     """Return the config class registered under ``name``."""
     try:
         return _METHODS.get(name)
+    except KeyError:
+        pass
+    # PPOConfig / ILQLConfig / SFTConfig / RFTConfig register themselves when their modules are imported; a bare
+    # ``TRLConfig.load_yaml`` may run before anything imported them
+    import importlib
+
+    importlib.import_module("trlx_b200.utils.loading")
+    try:
+        return _METHODS.get(name)
     except KeyError as e:
         raise Exception(f"Error: Trying to access a method that has not been registered ({e})") from None

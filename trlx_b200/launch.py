@@ -37,6 +37,27 @@ def build_command(args, preset: dict) -> List[str]:
     return cmd + [args.script] + list(args.script_args)
 
 
+def parallel_from_deepspeed(ds: dict) -> dict:
+    """The part of a DeepSpeed JSON config (``examples/summarize_rlhf/configs/ds_config_*.json`` in the reference) that has a
+    counterpart here: ZeRO stage → ``zero_stage`` of the fused sharded optimizer, ``bf16`` / ``fp16`` → ``precision``,
+    ``gradient_clipping`` → ``grad_clip``, an all-gather / reduce bucket size → ``bucket_mb``.  CPU offload sections are
+    ignored (optimizer state is sharded across 180 GB GPUs instead)."""
+    out = {}
+    zero = ds.get("zero_optimization") or {}
+    if "stage" in zero:
+        out["zero_stage"] = int(zero["stage"])
+    if (ds.get("bf16") or {}).get("enabled"):
+        out["precision"] = "bf16"
+    elif (ds.get("fp16") or {}).get("enabled"):
+        out["precision"] = "fp16"
+    if ds.get("gradient_clipping"):
+        out["grad_clip"] = float(ds["gradient_clipping"])
+    bucket = zero.get("reduce_bucket_size") or zero.get("allgather_bucket_size")
+    if bucket:
+        out["bucket_mb"] = max(float(bucket) * 2 / (1 << 20), 1.0)  # elements (fp16) → MiB
+    return out
+
+
 def main(argv: Optional[List[str]] = None) -> int:
     ap = argparse.ArgumentParser(description="start a trlx_b200 training script on every GPU of the node")
     ap.add_argument("--config_file", type=str, default=None, help="launch preset (configs/accelerate/*.yaml)")
@@ -45,6 +66,8 @@ def main(argv: Optional[List[str]] = None) -> int:
     ap.add_argument("--machine_rank", type=int, default=int(os.environ.get("SLURM_NODEID", 0)))
     ap.add_argument("--main_process_ip", type=str, default=os.environ.get("MASTER_ADDR", "127.0.0.1"))
     ap.add_argument("--main_process_port", type=int, default=int(os.environ.get("MASTER_PORT", 29500)))
+    ap.add_argument("--deepspeed_config", type=str, default=None,
+                    help="DeepSpeed JSON whose ZeRO stage / precision / clipping are mapped onto the parallel preset")
     ap.add_argument("--dry_run", action="store_true", help="print the command and exit")
     ap.add_argument("script")
     ap.add_argument("script_args", nargs=argparse.REMAINDER)
@@ -54,6 +77,10 @@ def main(argv: Optional[List[str]] = None) -> int:
         with open(args.config_file) as fh:
             preset = yaml.safe_load(fh) or {}
     env = dict(os.environ)
+    ds_path = args.deepspeed_config or (preset.get("deepspeed_config") or {}).get("deepspeed_config_file")
+    if ds_path:
+        with open(ds_path) as fh:
+            preset = dict(preset, parallel={**parallel_from_deepspeed(json.load(fh)), **(preset.get("parallel") or {})})
     if preset.get("parallel"):
         env["TRLX_B200_PARALLEL"] = json.dumps(preset["parallel"])
     cmd = build_command(args, preset)
