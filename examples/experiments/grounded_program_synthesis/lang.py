@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import random
 import re
-from typing import Any, Callable, Dict, List, Tuple, Union
+from typing import Callable, Dict, List, Tuple, Union
 
 Value = Union[int, List[int]]
 

@@ -12,7 +12,6 @@ from __future__ import annotations
 import json
 import math
 import os
-import sys
 import urllib.request
 from typing import Callable, List, Optional, Sequence
 

@@ -2,7 +2,7 @@
 pairwise comparisons for the reward model, and a helper that renders the JSONL dumps.  Hub datasets are used when they are on
 disk; otherwise the synthetic summaries of ``examples/_offline.py`` stand in so every stage runs offline."""
 import json
-from typing import List, Optional, Tuple
+from typing import List
 
 import torch
 from torch.utils.data import Dataset

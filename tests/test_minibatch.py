@@ -1,6 +1,5 @@
 from dataclasses import dataclass
 
-import pytest
 import torch
 from torch.utils.data import DataLoader, Dataset
 

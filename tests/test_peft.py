@@ -7,7 +7,7 @@ import torch
 
 from trlx_b200.models.modeling_ilql import AutoModelForCausalLMWithILQLHeads
 from trlx_b200.models.modeling_ppo import AutoModelForCausalLMWithHydraValueHead, AutoModelForSeq2SeqLMWithHydraValueHead
-from trlx_b200.models.peft import PeftConfig, PeftModel, get_peft_config
+from trlx_b200.models.peft import get_peft_config
 from trlx_b200.trainer.accelerate_sft_trainer import CausalLMWrapper
 
 GPT2 = dict(model_type="gpt2", vocab_size=64, n_embd=32, n_layer=2, n_head=2, n_positions=64)

@@ -4,7 +4,7 @@ from hypothesis import given, settings
 from hypothesis import strategies as st
 
 from trlx_b200.data.ppo_types import PPORLElement
-from trlx_b200.pipeline.offline_pipeline import (DialogMessage, DialogStore, PromptPipeline, pad_rows, tokenize_dialogue)
+from trlx_b200.pipeline.offline_pipeline import DialogStore, PromptPipeline, pad_rows, tokenize_dialogue
 from trlx_b200.pipeline.ppo_pipeline import DeviceBatchLoader, PPORolloutStorage, RolloutBlock, ppo_collate_fn
 from trlx_b200.utils.tokenizer import build_toy_tokenizer, load_tokenizer
 

@@ -4,8 +4,7 @@ checkpoint exists.  The Megatron-style defaults return plain :class:`TRLConfig` 
 layout instead of OmegaConf trees."""
 from __future__ import annotations
 
-from trlx_b200.data.configs import (ModelConfig, OptimizerConfig, ParallelConfig, SchedulerConfig, TokenizerConfig,
-                                    TrainConfig, TRLConfig)
+from trlx_b200.data.configs import ModelConfig, OptimizerConfig, SchedulerConfig, TokenizerConfig, TrainConfig, TRLConfig
 from trlx_b200.models.modeling_ilql import ILQLConfig
 from trlx_b200.models.modeling_ppo import PPOConfig
 from trlx_b200.trainer.accelerate_sft_trainer import SFTConfig

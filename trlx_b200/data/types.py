@@ -8,10 +8,9 @@ helpers that the reference's NeMo backend imports but never defined (SURVEY §0.
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, fields, is_dataclass
-from typing import Any, Callable, Iterable, List, Optional, Tuple, Type
+from dataclasses import dataclass, fields
+from typing import Any, Callable, Iterable, List, Optional, Type
 
-import torch
 from torch import Tensor
 
 

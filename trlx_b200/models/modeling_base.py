@@ -18,7 +18,7 @@ import torch.nn as nn
 from trlx_b200.models import checkpoint_io
 from trlx_b200.models.peft import ADAPTER_CONFIG, PeftConfig, PeftModel, get_peft_config, get_peft_model
 from trlx_b200.nn import hf_compat
-from trlx_b200.nn.arch import ArchSpec, resolve_config, spec_from_hf_config
+from trlx_b200.nn.arch import resolve_config, spec_from_hf_config
 from trlx_b200.utils import logging
 
 logger = logging.get_logger(__name__)

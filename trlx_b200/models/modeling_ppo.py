@@ -18,7 +18,7 @@ import copy
 import gc
 import re
 from dataclasses import dataclass
-from typing import Any, Dict, List, Optional, Tuple, Union
+from typing import Any, Dict, Optional, Tuple
 
 import numpy as np
 import torch
@@ -30,7 +30,7 @@ from trlx_b200.models.modeling_base import PreTrainedModelWrapper, base_lm, expo
 from trlx_b200.models.peft import PeftModel
 from trlx_b200.nn import hf_compat
 from trlx_b200.nn.transformer import CausalLM, build_attn_context
-from trlx_b200.utils.modeling import flatten_dict, get_tensor_stats, make_head, whiten
+from trlx_b200.utils.modeling import make_head, whiten
 
 
 # ---- KL controllers ---------------------------------------------------------------------------------------------------

@@ -25,7 +25,6 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from trlx_b200.nn import hf_compat
-from trlx_b200.nn.arch import ArchSpec
 
 ADAPTER_CONFIG = "adapter_config.json"
 ADAPTER_WEIGHTS = "adapter_model.bin"

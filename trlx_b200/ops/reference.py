@@ -2,7 +2,7 @@
 tests compare against.  Formulas follow the reference implementation cited in each docstring."""
 from __future__ import annotations
 
-from typing import Dict, Optional, Tuple
+from typing import Dict, Tuple
 
 import torch
 import torch.nn.functional as F

@@ -9,7 +9,7 @@ The reference's NeMo trainers take ``trainer_kwargs = {"megatron_cfg": <yaml nam
 from __future__ import annotations
 
 import os
-from typing import Any, Dict, Optional, Tuple
+from typing import Any, Dict, Optional
 
 import yaml
 

@@ -17,7 +17,7 @@ in-repo stand-in for ``bitsandbytes`` (reference: ``trlx/utils/__init__.py:104-1
 from __future__ import annotations
 
 import math
-from typing import Any, Dict, Iterable, List, Optional
+from typing import Any, Dict, List, Optional
 
 import torch
 import torch.distributed as dist

@@ -25,7 +25,6 @@ maths runs on ``torch.distributed`` collectives through the autograd functions b
 from __future__ import annotations
 
 import math
-from typing import Optional, Tuple
 
 import torch
 import torch.distributed as dist
@@ -33,7 +32,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from trlx_b200.models.modeling_base import base_lm
-from trlx_b200.nn.transformer import AttnContext, Attention, Block, MLP, activation_fn, apply_rotary
+from trlx_b200.nn.transformer import AttnContext, Attention, Block, MLP, apply_rotary
 from trlx_b200.utils import logging
 
 logger = logging.get_logger(__name__)

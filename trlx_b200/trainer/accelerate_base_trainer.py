@@ -30,8 +30,7 @@ from trlx_b200.pipeline import MiniBatchIterator
 from trlx_b200.trainer import BaseRLTrainer, register_trainer
 from trlx_b200.utils import (filter_non_scalars, get_distributed_config, get_git_tag, get_optimizer_class,
                              get_scheduler_class, logging, significant)
-from trlx_b200.utils.modeling import (flatten_dict, freeze_bottom_causal_layers, freeze_bottom_seq2seq_layers,
-                                      gather_dict)
+from trlx_b200.utils.modeling import flatten_dict, freeze_bottom_causal_layers, freeze_bottom_seq2seq_layers
 from trlx_b200.utils.tokenizer import load_tokenizer
 
 logger = logging.get_logger(__name__)

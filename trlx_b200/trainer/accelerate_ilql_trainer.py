@@ -8,7 +8,7 @@ so the five ``[B, A, V]`` tensors of the reference are never materialised.
 from __future__ import annotations
 
 import os
-from typing import List, Optional, Sequence, Union, cast
+from typing import List, Sequence, Union, cast
 
 import numpy as np
 import torch

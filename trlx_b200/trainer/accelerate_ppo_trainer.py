@@ -22,7 +22,7 @@ import json
 import os
 import uuid
 from time import time
-from typing import Any, Callable, Dict, List, Optional, Tuple
+from typing import Any, Dict, List, Optional, Tuple
 
 import numpy as np
 import torch
@@ -30,7 +30,7 @@ import torch.nn.functional as F
 
 from trlx_b200 import ops
 from trlx_b200.data.configs import TRLConfig
-from trlx_b200.data.ppo_types import PPORLBatch, PPORLElement
+from trlx_b200.data.ppo_types import PPORLBatch
 from trlx_b200.models.modeling_ppo import (AdaptiveKLController, AutoModelForCausalLMWithHydraValueHead,
                                            AutoModelForSeq2SeqLMWithHydraValueHead, FixedKLController)
 from trlx_b200.pipeline.offline_pipeline import PromptPipeline, pad_rows

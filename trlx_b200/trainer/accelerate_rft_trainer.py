@@ -11,9 +11,7 @@ from collections import defaultdict
 from dataclasses import dataclass
 
 import numpy as np
-import torch
 
-from trlx_b200.data.configs import TRLConfig
 from trlx_b200.data.method_configs import MethodConfig, register_method
 from trlx_b200.pipeline.offline_pipeline import PromptPipeline
 from trlx_b200.trainer import register_trainer

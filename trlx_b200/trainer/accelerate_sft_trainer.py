@@ -8,7 +8,6 @@ the reference are not materialised.
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Any, Dict, Optional
 
 import torch
 
