@@ -298,3 +298,30 @@ def test_push_to_hub_fails_cleanly_when_the_hub_is_disabled(monkeypatch):
                                                                 n_positions=16))
     with pytest.raises(RuntimeError, match="disabled"):
         model.push_to_hub("someone/some-model")
+
+
+def test_ops_attention_cpu_path_matches_manual_softmax():
+    from trlx_b200 import ops
+
+    torch.manual_seed(0)
+    q, k, v = (torch.randn(2, 3, 5, 8) for _ in range(3))
+    causal = ops.attention(q, k, v, None, causal=True)
+    s = q @ k.transpose(-1, -2) * 8 ** -0.5
+    mask = torch.ones(5, 5, dtype=torch.bool).tril()
+    ref = torch.softmax(s.masked_fill(~mask, float("-inf")), -1) @ v
+    torch.testing.assert_close(causal, ref, atol=1e-5, rtol=1e-5)
+    bias = torch.zeros(2, 1, 5, 5).masked_fill(~mask, torch.finfo(torch.float32).min)
+    torch.testing.assert_close(ops.attention(q, k, v, bias, scale=8 ** -0.5), ref, atol=1e-5, rtol=1e-5)
+
+
+def test_norm_module_cpu_matches_functional():
+    from trlx_b200.nn.arch import spec_from_hf_config
+    from trlx_b200.nn.transformer import Norm
+
+    spec = spec_from_hf_config(dict(model_type="gpt2", vocab_size=20, n_embd=16, n_layer=1, n_head=2, n_positions=8))
+    norm = Norm(spec)
+    with torch.no_grad():
+        norm.weight.uniform_(0.5, 1.5)
+        norm.bias.uniform_(-0.5, 0.5)
+    x = torch.randn(3, 4, 16)
+    torch.testing.assert_close(norm(x), torch.nn.functional.layer_norm(x, (16,), norm.weight, norm.bias, norm.eps))

@@ -113,6 +113,7 @@ class AccelerateRLTrainer(BaseRLTrainer):
         if self.tokenizer.pad_token is None:
             self.tokenizer.pad_token = "<|padding|>"
 
+        self._fit_random_init_vocab()
         self.model = self.setup_model()
         self.opt = self.setup_optimizer()
         self.scheduler = self.setup_scheduler()
@@ -153,6 +154,21 @@ class AccelerateRLTrainer(BaseRLTrainer):
                     self.generate_sweep_kwarg = (k, v)
 
     # ---- setup --------------------------------------------------------------------------------------------------------
+    def _fit_random_init_vocab(self) -> None:
+        """A model described by a *config mapping* is initialised from scratch, so nothing ties its vocabulary size to a
+        checkpoint: grow it to the tokenizer's when the tokenizer has more ids (offline runs pair synthetic tokenizers with
+        small architecture presets; an id past the embedding table would otherwise be an index error deep inside the model)."""
+        path = self.config.model.model_path
+        if not isinstance(path, dict) or "vocab_size" not in path:
+            return
+        try:
+            n_tok = len(self.tokenizer)
+        except TypeError:
+            n_tok = int(getattr(self.tokenizer, "vocab_size", 0) or 0)
+        if n_tok > int(path["vocab_size"]):
+            logger.warning(f"random-init model: vocab_size {path['vocab_size']} -> {n_tok} to cover the tokenizer")
+            self.config.model.model_path = dict(path, vocab_size=n_tok)
+
     def setup_model(self):
         logger.info(f"Initializing model: {self.config.model.model_path}")
         model = self.get_arch(self.config)
