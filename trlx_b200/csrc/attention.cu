@@ -225,6 +225,192 @@ attn_short_bwd_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* 
   }
 }
 
+// ---------------------------------------------------------------------------------------------- tcgen05 forward
+// The same forward on the tensor cores: S = Q.K^T and O = P.V are two tcgen05.mma groups (UMMA M = 128) with the accumulators
+// in TMEM — S in columns [0, 128), O in [128, 128 + d).  TMEM lane = query row, so after tcgen05.ld every thread holds one
+// whole row of scores: bias, masking, max, exp and the row sum are thread-local (no shuffles), and the un-normalised
+// probabilities go back to shared memory as the bf16 K-major A operand of the second MMA (128-byte swizzled rows, the layout
+// TMA would have produced).  V is consumed as an MN-major B operand straight from its [token, d] layout.  One CTA of 128 threads
+// per (batch, head); Tq, Tk <= 128, d in {64, 128}.
+constexpr int ATC_THREADS = 128;
+
+// [rows_total x 64] bf16 tile, 128-byte rows, 16-byte units XOR-swizzled with (row & 7); rows >= rows_valid are zero
+__device__ __forceinline__ void atc_load_tile(uint32_t tile_u32, const __nv_bfloat16* src, long long row_stride, int rows_valid,
+                                              int rows_total) {
+  for (int idx = threadIdx.x; idx < rows_total * 8; idx += ATC_THREADS) {
+    const int r = idx >> 3, u = idx & 7;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (r < rows_valid) v = *reinterpret_cast<const uint4*>(src + (long long)r * row_stride + u * 8);
+    uint32_t off = (uint32_t)r * 128u + (uint32_t)u * 16u;
+    off ^= ((off >> 7) & 7u) << 4;
+    st_shared_v4(tile_u32 + off, v);
+  }
+}
+
+__global__ void __launch_bounds__(ATC_THREADS, 1)
+attn_tc_fwd_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v,
+                   const float* __restrict__ bias, __nv_bfloat16* __restrict__ o, float* __restrict__ stats, AttnDims D) {
+  extern __shared__ __align__(1024) uint8_t atc_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(atc_raw) + 1023) & ~uintptr_t(1023));
+  const int b = blockIdx.x / D.H, h = blockIdx.x % D.H;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int dch = D.d / 64;                       // 64-column chunks of the head dimension (k-blocks of the first MMA)
+  const int n_s = (D.Tk + 15) & ~15;              // UMMA N of S = Q.K^T (and K extent of P.V), multiple of 16
+  const int kb_tok = (n_s + 63) / 64;             // 64-token k-blocks of the second MMA
+  // shared memory: Q [dch][128 x 128 B] | K [dch][128 x 128 B] | V [kb_tok][dch][64 x 128 B] | P [kb_tok][128 x 128 B] | bar, slot
+  const uint32_t q_u32 = smem_u32(smem);
+  const uint32_t k_u32 = q_u32 + (uint32_t)dch * 16384u;
+  const uint32_t v_u32 = k_u32 + (uint32_t)dch * 16384u;
+  const uint32_t p_u32 = v_u32 + (uint32_t)kb_tok * dch * 8192u;
+  uint8_t* tail = smem + (size_t)dch * 32768 + (size_t)kb_tok * dch * 8192 + (size_t)kb_tok * 16384;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(tail);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 16);
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  griddep_wait();
+  griddep_launch();
+  const __nv_bfloat16* qb = q + b * D.q_sb + h * D.q_sh;
+  const __nv_bfloat16* kb_ = k + b * D.k_sb + h * D.k_sh;
+  const __nv_bfloat16* vb = v + b * D.v_sb + h * D.v_sh;
+  for (int c = 0; c < dch; ++c) {
+    atc_load_tile(q_u32 + c * 16384u, qb + c * 64, D.q_st, D.Tq, 128);
+    atc_load_tile(k_u32 + c * 16384u, kb_ + c * 64, D.k_st, D.Tk, 128);
+  }
+  for (int t = 0; t < kb_tok; ++t)
+    for (int c = 0; c < dch; ++c)
+      atc_load_tile(v_u32 + (uint32_t)(t * dch + c) * 8192u, vb + (long long)t * 64 * D.v_st + c * 64, D.v_st,
+                    max(min(D.Tk - t * 64, 64), 0), 64);
+  fence_proxy_async();           // generic-proxy writes -> visible to the tensor core (async proxy)
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (threadIdx.x == 0) {  // S = Q . K^T
+    const uint32_t idesc = umma_idesc(1, 1, 128, (uint32_t)n_s);
+    for (int c = 0; c < dch; ++c) {
+      const uint64_t da = umma_desc_k_sw128(q_u32 + c * 16384u), db = umma_desc_k_sw128(k_u32 + c * 16384u);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) umma_bf16(tmem_base, da + 2 * kk, db + 2 * kk, idesc, (c > 0 || kk > 0) ? 1u : 0u);
+    }
+    umma_commit(&bar[0]);
+  }
+  mbar_wait(&bar[0], 0);
+  tc_fence_after_sync();
+
+  const int i = warp * 32 + lane;  // query row == TMEM lane
+  const bool row_ok = i < D.Tq;
+  const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+  const float* brow = (bias && row_ok) ? bias + b * D.b_sb + h * D.b_sh + (long long)i * D.b_sq : nullptr;
+  const int shift = D.Tk - D.Tq;
+  float m = -INFINITY;
+  for (int c0 = 0; c0 < n_s; c0 += 16) {
+    uint32_t r[16];
+    tmem_ld16(taddr + c0, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int col = c0 + j;
+      if (row_ok && col < D.Tk && !(D.causal && col > i + shift))
+        m = fmaxf(m, __uint_as_float(r[j]) * D.scale + (brow ? brow[col] : 0.f));
+    }
+  }
+  if (m == -INFINITY) m = 0.f;
+  float sum = 0.f;
+  for (int c0 = 0; c0 < kb_tok * 64; c0 += 16) {
+    float e[16];
+    if (c0 < n_s) {
+      uint32_t r[16];
+      tmem_ld16(taddr + c0, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int col = c0 + j;
+        const bool ok = row_ok && col < D.Tk && !(D.causal && col > i + shift);
+        e[j] = ok ? __expf(__uint_as_float(r[j]) * D.scale + (brow ? brow[col] : 0.f) - m) : 0.f;
+        // the second MMA consumes bf16 probabilities: accumulate the row sum from the rounded values it will actually use
+        e[j] = __bfloat162float(__float2bfloat16(e[j]));
+        sum += e[j];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) e[j] = 0.f;
+    }
+    uint4 pk[2];
+    __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(pk);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) h2[j] = __floats2bfloat162_rn(e[2 * j], e[2 * j + 1]);
+    const uint32_t tile = p_u32 + (uint32_t)(c0 >> 6) * 16384u;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      uint32_t off = (uint32_t)i * 128u + (uint32_t)((c0 & 63) * 2 + hh * 16);
+      off ^= ((off >> 7) & 7u) << 4;
+      st_shared_v4(tile + off, pk[hh]);
+    }
+  }
+  const float inv = sum > 0.f ? 1.f / sum : 0.f;
+  fence_proxy_async();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+
+  if (threadIdx.x == 0) {  // O = P . V   (A: P K-major, B: V MN-major)
+    const uint32_t idesc = umma_idesc(1, 1, 128, (uint32_t)D.d, 0, 1);
+    bool first = true;
+    for (int t = 0; t < kb_tok; ++t) {
+      const uint64_t da = umma_desc_k_sw128(p_u32 + (uint32_t)t * 16384u);
+      const uint64_t db = umma_desc_mn_sw128(v_u32 + (uint32_t)t * dch * 8192u, 8192u);
+      const int steps = min((n_s - t * 64) / 16, 4);
+      for (int kk = 0; kk < steps; ++kk) {
+        umma_bf16(tmem_base + 128, da + 2 * kk, db + 128 * kk, idesc, first ? 0u : 1u);
+        first = false;
+      }
+    }
+    umma_commit(&bar[1]);
+  }
+  mbar_wait(&bar[1], 0);
+  tc_fence_after_sync();
+  // every lane runs the (warp-aligned) TMEM loads; only the stores are predicated on the row being real
+  __nv_bfloat16* orow = o + (((long long)b * D.Tq + (row_ok ? i : 0)) * D.H + h) * D.d;
+  for (int c0 = 0; c0 < D.d; c0 += 16) {
+    uint32_t r[16];
+    tmem_ld16(taddr + 128 + c0, r);
+    tmem_ld_wait();
+    uint4 pk[2];
+    __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(pk);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) h2[j] = __floats2bfloat162_rn(__uint_as_float(r[2 * j]) * inv, __uint_as_float(r[2 * j + 1]) * inv);
+    if (row_ok) {
+      *reinterpret_cast<uint4*>(orow + c0) = pk[0];
+      *reinterpret_cast<uint4*>(orow + c0 + 8) = pk[1];
+    }
+  }
+  if (row_ok && stats) {
+    float* st = stats + (((long long)b * D.H + h) * D.Tq + i) * 2;
+    st[0] = m;
+    st[1] = inv;
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+static size_t attn_tc_smem(int Tk, int d) {
+  const int dch = d / 64, kb_tok = (((Tk + 15) & ~15) + 63) / 64;
+  return (size_t)dch * 32768 + (size_t)kb_tok * dch * 8192 + (size_t)kb_tok * 16384 + 64 + 1024;
+}
+
 static size_t attn_fwd_smem(int Tq, int Tk, int d) {
   return (size_t)(2 * Tk + Tq) * (d / 2 + 1) * 4 + (size_t)ATT_WARPS * Tk * 4;
 }
@@ -279,4 +465,25 @@ extern "C" int b200_attn_short_bwd(const void* q, const void* k, const void* v, 
                             (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, bias,
                             (const __nv_bfloat16*)o, (const __nv_bfloat16*)d_o, dos[0], dos[1], dos[2], stats,
                             (__nv_bfloat16*)dq, (__nv_bfloat16*)dk, (__nv_bfloat16*)dv, D);
+}
+
+// tcgen05 forward (Tq, Tk <= 128, d in {64, 128}); same contract as b200_attn_short_fwd
+extern "C" int b200_attn_tc_ok(int Tq, int Tk, int d) {
+  return (Tq >= 1 && Tk >= 1 && Tq <= 128 && Tk <= 128 && (d == 64 || d == 128)) ? 1 : 0;
+}
+
+extern "C" int b200_attn_tc_fwd(const void* q, const void* k, const void* v, const float* bias, void* o, float* stats, int B,
+                                int H, int Tq, int Tk, int d, const long long* qs, const long long* ks, const long long* vs,
+                                const long long* bs, float scale, int causal, cudaStream_t stream) {
+  if (!b200_attn_tc_ok(Tq, Tk, d)) return -1;
+  AttnDims D{B, H, Tq, Tk, d, qs[0], qs[1], qs[2], ks[0], ks[1], ks[2], vs[0], vs[1], vs[2],
+             bias ? bs[0] : 0, bias ? bs[1] : 0, bias ? bs[2] : 0, scale, causal};
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return -5;
+    configured = true;
+  }
+  return (int)launch_kernel(attn_tc_fwd_kernel, dim3((unsigned)(B * H)), dim3(ATC_THREADS), attn_tc_smem(Tk, d), stream,
+                            (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, bias, (__nv_bfloat16*)o,
+                            stats, D);
 }

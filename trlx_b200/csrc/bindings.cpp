@@ -62,6 +62,9 @@ int b200_rs_adamw_ag(void* const*, void* const*, int, long long, long long, floa
                      float, float, int, const float*, double*, cudaStream_t);
 int b200_lerp_bf16(void*, const void*, long long, float, cudaStream_t);
 int b200_attn_short_ok(int, int, int, int);
+int b200_attn_tc_ok(int, int, int);
+int b200_attn_tc_fwd(const void*, const void*, const void*, const float*, void*, float*, int, int, int, int, int,
+                     const long long*, const long long*, const long long*, const long long*, float, int, cudaStream_t);
 int b200_attn_short_fwd(const void*, const void*, const void*, const float*, void*, float*, int, int, int, int, int,
                         const long long*, const long long*, const long long*, const long long*, float, int, cudaStream_t);
 int b200_attn_short_bwd(const void*, const void*, const void*, const float*, const void*, const void*, const long long*,
@@ -267,6 +270,21 @@ std::vector<Tensor> attn_short_fwd(const Tensor& q, const Tensor& k, const Tenso
   check(b200_attn_short_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), a.bias, o.data_ptr(), stats.data_ptr<float>(), B, H, Tq,
                             Tk, d, a.qs, a.ks, a.vs, a.bs, (float)scale, causal ? 1 : 0, stream()),
         "attn_short_fwd");
+  return {o, stats};
+}
+
+// same contract on the tcgen05 kernel (Tq, Tk <= 128, d in {64, 128})
+std::vector<Tensor> attn_tc_fwd(const Tensor& q, const Tensor& k, const Tensor& v, const OptTensor& bias, bool causal,
+                                double scale) {
+  AttnArgs a = attn_args(q, k, v, bias);
+  const int B = (int)q.size(0), H = (int)q.size(1), Tq = (int)q.size(2), Tk = (int)k.size(2), d = (int)q.size(3);
+  TORCH_CHECK(b200_attn_tc_ok(Tq, Tk, d), "attn_tc_fwd: unsupported shape");
+  c10::cuda::CUDAGuard guard(q.device());
+  Tensor o = torch::empty({B, Tq, H, d}, q.options());
+  Tensor stats = torch::empty({B, H, Tq, 2}, q.options().dtype(at::kFloat));
+  check(b200_attn_tc_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), a.bias, o.data_ptr(), stats.data_ptr<float>(), B, H, Tq, Tk, d,
+                         a.qs, a.ks, a.vs, a.bs, (float)scale, causal ? 1 : 0, stream()),
+        "attn_tc_fwd");
   return {o, stats};
 }
 
@@ -842,6 +860,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("attn_short_ok", [](int64_t tq, int64_t tk, int64_t d, bool backward) {
     return b200_attn_short_ok((int)tq, (int)tk, (int)d, backward ? 1 : 0) != 0; },
         py::arg("tq"), py::arg("tk"), py::arg("d"), py::arg("backward") = false);
+  m.def("attn_tc_ok", [](int64_t tq, int64_t tk, int64_t d) { return b200_attn_tc_ok((int)tq, (int)tk, (int)d) != 0; });
+  m.def("attn_tc_fwd", &attn_tc_fwd, py::arg("q"), py::arg("k"), py::arg("v"), py::arg("bias") = py::none(),
+        py::arg("causal") = false, py::arg("scale") = 1.0);
   m.def("attn_short_fwd", &attn_short_fwd, py::arg("q"), py::arg("k"), py::arg("v"), py::arg("bias") = py::none(),
         py::arg("causal") = false, py::arg("scale") = 1.0);
   m.def("attn_short_bwd", &attn_short_bwd, py::arg("q"), py::arg("k"), py::arg("v"), py::arg("bias"), py::arg("o"),

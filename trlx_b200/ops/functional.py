@@ -165,7 +165,11 @@ class _ShortAttention(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, q, k, v, bias, causal, scale):
-        o, stats = _ops().C.attn_short_fwd(q, k, v, bias, causal, scale)
+        C = _ops().C
+        if _ATTENTION_TC and hasattr(C, "attn_tc_fwd") and C.attn_tc_ok(q.shape[2], k.shape[2], q.shape[3]):
+            o, stats = C.attn_tc_fwd(q, k, v, bias, causal, scale)   # tcgen05: S and O accumulate in TMEM
+        else:
+            o, stats = C.attn_short_fwd(q, k, v, bias, causal, scale)
         ctx.save_for_backward(q, k, v, bias, o, stats)
         ctx.causal, ctx.scale = causal, scale
         return o.transpose(1, 2)  # [B, H, Tq, d] view of the [B, Tq, H, d] buffer
@@ -179,10 +183,13 @@ class _ShortAttention(torch.autograd.Function):
         return dq.transpose(1, 2), dk.transpose(1, 2), dv.transpose(1, 2), None, None, None
 
 
-# "auto": the in-repo kernels serve the no-grad paths (prefill, scoring), the library SDPA serves training — the CUDA-core
-# backward is shared-memory-bandwidth bound and measured 2x slower than cuDNN's tensor-core kernel at 32 x 12 x 56 x 56
-# (run36: 29.6 vs 26.7 ms per 16 optimizer steps); "own" / "sdpa" force one side for A/B runs.
+# "auto": the in-repo kernels serve no-grad calls with tiny score tiles (the rollout prefill), the library SDPA everything else —
+# the CUDA-core backward is shared-memory-bandwidth bound and measured 2x slower than cuDNN's tensor-core kernel at
+# 32 x 12 x 56 x 56 (run36: 29.6 vs 26.7 ms per 16 optimizer steps), and the forward loses from ~56 x 56 on (run45);
+# "own" / "sdpa" force one side for A/B runs.
 _ATTENTION_MODE = os.environ.get("TRLX_B200_ATTENTION", "auto")
+# forward on the tcgen05 kernel (``attn_tc_fwd_kernel``) instead of the CUDA-core one; opt-in until it has been A/B-measured
+_ATTENTION_TC = os.environ.get("TRLX_B200_ATTENTION_TC", "0") == "1"
 
 
 def _attn_view_ok(t: torch.Tensor) -> bool:
@@ -197,7 +204,9 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, bias: Optional[
     goes through ``F.scaled_dot_product_attention``."""
     scale = float(scale) if scale is not None else q.shape[-1] ** -0.5
     need_grad = torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad)
-    own = _ATTENTION_MODE == "own" or (_ATTENTION_MODE == "auto" and not need_grad)
+    # measured (profiles/attention_fwd_bench.jsonl): the one-CTA-per-head kernels win only on tiny score tiles (prefill, 24 x 24:
+    # 37 us vs 47 us for cuDNN); from ~56 x 56 on the library's tensor-core kernel is 2-3x faster
+    own = _ATTENTION_MODE == "own" or (_ATTENTION_MODE == "auto" and not need_grad and q.shape[2] * k.shape[2] <= 32 * 32)
     if (own and q.is_cuda and q.dtype == torch.bfloat16 and k.dtype == torch.bfloat16 and v.dtype == torch.bfloat16
             and q.dim() == 4 and _ops().available() and hasattr(_ops().C, "attn_short_fwd")
             and _ops().C.attn_short_ok(q.shape[2], k.shape[2], q.shape[3], need_grad)
