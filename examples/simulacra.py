@@ -37,4 +37,7 @@ def main(hparams={}):
 
 
 if __name__ == "__main__":
-    main()
+    import json
+    import sys
+
+    main({} if len(sys.argv) == 1 else json.loads(sys.argv[1]))
