@@ -10,45 +10,46 @@ from trlx_b200.models.modeling_ppo import PPOConfig
 from trlx_b200.trainer.accelerate_sft_trainer import SFTConfig
 
 
-def default_ppo_config() -> TRLConfig:
+# Every default shares the AdamW / cosine recipe and differs in a handful of numbers; the tables below are those numbers
+# (values: ``trlx/data/default_configs.py:17-121``).
+_ADAMW = dict(betas=(0.9, 0.95), eps=1.0e-8, weight_decay=1.0e-6)
+_SAMPLING = dict(max_new_tokens=40, top_k=0, top_p=1.0, do_sample=True)
+
+
+def _base(trainer: str, lr: float, model: str, unfrozen: int, method, **train) -> TRLConfig:
+    train.setdefault("epochs", 100)
+    train.setdefault("eval_interval", 100)
     return TRLConfig(
-        train=TrainConfig(seq_length=1024, epochs=100, total_steps=10000, batch_size=32, checkpoint_interval=10000,
-                          eval_interval=100, pipeline="PromptPipeline", trainer="AcceleratePPOTrainer"),
-        model=ModelConfig(model_path="lvwerra/gpt2-imdb", num_layers_unfrozen=2),
+        method=method,
+        model=ModelConfig(model_path=model, num_layers_unfrozen=unfrozen),
         tokenizer=TokenizerConfig(tokenizer_path="gpt2", truncation_side="right"),
-        optimizer=OptimizerConfig(name="adamw", kwargs=dict(lr=3e-5, betas=(0.9, 0.95), eps=1.0e-8, weight_decay=1.0e-6)),
-        scheduler=SchedulerConfig(name="cosine_annealing", kwargs=dict(T_max=1e12, eta_min=3e-5)),
-        method=PPOConfig(name="PPOConfig", num_rollouts=128, chunk_size=128, ppo_epochs=4, init_kl_coef=0.001, target=None,
-                         horizon=10000, gamma=1, lam=0.95, cliprange=0.2, cliprange_value=0.2, vf_coef=1,
-                         scale_reward="ignored", ref_mean=None, ref_std=None, cliprange_reward=10,
-                         gen_kwargs=dict(max_new_tokens=40, top_k=0, top_p=1.0, do_sample=True)),
+        optimizer=OptimizerConfig(name="adamw", kwargs=dict(lr=lr, **_ADAMW)),
+        scheduler=SchedulerConfig(name="cosine_annealing", kwargs=dict(T_max=1e12, eta_min=lr)),  # constant lr in practice
+        train=TrainConfig(pipeline="PromptPipeline", trainer=trainer, **train),
     )
+
+
+def default_ppo_config() -> TRLConfig:
+    """GPT-2 (IMDB-tuned) with two unfrozen blocks, 128 rollouts of 40 tokens, 4 PPO epochs (the benchmark configuration)."""
+    ppo = PPOConfig(name="PPOConfig", ppo_epochs=4, num_rollouts=128, chunk_size=128, gamma=1, lam=0.95, init_kl_coef=0.001,
+                    target=None, horizon=10000, cliprange=0.2, cliprange_value=0.2, cliprange_reward=10, vf_coef=1,
+                    scale_reward="ignored", ref_mean=None, ref_std=None, gen_kwargs=dict(_SAMPLING))
+    return _base("AcceleratePPOTrainer", 3e-5, "lvwerra/gpt2-imdb", 2, ppo, seq_length=1024, batch_size=32, total_steps=10000,
+                 checkpoint_interval=10000)
 
 
 def default_ilql_config() -> TRLConfig:
-    return TRLConfig(
-        train=TrainConfig(seq_length=64, batch_size=128, epochs=100, total_steps=1000, checkpoint_interval=1000,
-                          eval_interval=100, pipeline="PromptPipeline", trainer="AccelerateILQLTrainer"),
-        model=ModelConfig(model_path="gpt2", num_layers_unfrozen=-1),
-        tokenizer=TokenizerConfig(tokenizer_path="gpt2", truncation_side="right"),
-        optimizer=OptimizerConfig(name="adamw", kwargs=dict(lr=5.0e-5, betas=(0.9, 0.95), eps=1.0e-8, weight_decay=1.0e-6)),
-        scheduler=SchedulerConfig(name="cosine_annealing", kwargs=dict(T_max=1e12, eta_min=5.0e-5)),
-        method=ILQLConfig(name="ilqlconfig", tau=0.7, gamma=0.99, cql_scale=0.1, awac_scale=1, alpha=0.001, beta=0,
-                          steps_for_target_q_sync=5, two_qs=True,
-                          gen_kwargs=dict(max_new_tokens=56, top_k=20, beta=1, temperature=1.0)),
-    )
+    """Offline ILQL on GPT-2: two Q heads, expectile 0.7, top-20 advantage-shifted sampling."""
+    ilql = ILQLConfig(name="ilqlconfig", two_qs=True, tau=0.7, gamma=0.99, alpha=0.001, beta=0, cql_scale=0.1, awac_scale=1,
+                      steps_for_target_q_sync=5, gen_kwargs=dict(max_new_tokens=56, top_k=20, beta=1, temperature=1.0))
+    return _base("AccelerateILQLTrainer", 5.0e-5, "gpt2", -1, ilql, seq_length=64, batch_size=128, total_steps=1000,
+                 checkpoint_interval=1000)
 
 
 def default_sft_config() -> TRLConfig:
-    return TRLConfig(
-        train=TrainConfig(seq_length=1024, epochs=100, total_steps=1000, batch_size=8, checkpoint_interval=10000,
-                          eval_interval=100, pipeline="PromptPipeline", trainer="AccelerateSFTTrainer"),
-        model=ModelConfig(model_path="gpt2", num_layers_unfrozen=-1),
-        tokenizer=TokenizerConfig(tokenizer_path="gpt2", truncation_side="right"),
-        optimizer=OptimizerConfig(name="adamw", kwargs=dict(lr=1.0e-4, betas=(0.9, 0.95), eps=1.0e-8, weight_decay=1.0e-6)),
-        scheduler=SchedulerConfig(name="cosine_annealing", kwargs=dict(T_max=1e12, eta_min=1.0e-4)),
-        method=SFTConfig(name="sftconfig", gen_kwargs=dict(max_new_tokens=40, top_k=0, top_p=1.0, do_sample=True)),
-    )
+    """Supervised fine-tuning of GPT-2, every layer trained."""
+    return _base("AccelerateSFTTrainer", 1.0e-4, "gpt2", -1, SFTConfig(name="sftconfig", gen_kwargs=dict(_SAMPLING)),
+                 seq_length=1024, batch_size=8, total_steps=1000, checkpoint_interval=10000)
 
 
 def _megatron(model: str, tp: int, pp: int = 1, sp: bool = True) -> TRLConfig:

@@ -24,6 +24,10 @@ class MegatronMixin:
             from trlx_b200.parallel.megatron_cfg import apply_megatron_cfg
 
             config = apply_megatron_cfg(config, tk["megatron_cfg"], tk.get("pretrained_model"))
+            if isinstance(config.model.model_path, dict):  # one CPU process cannot hold a 20B recipe: plumbing-run size
+                from trlx_b200.parallel.megatron_cfg import debug_sized
+
+                config = config.evolve(model=dict(model_path=debug_sized(config.model.model_path)))
             try:  # step / wall-clock limits of the recipe's ``trainer`` section (PTL Trainer + StatelessTimer in the reference)
                 from trlx_b200.trainer.nemo_ilql_trainer import megatron_trainer
 

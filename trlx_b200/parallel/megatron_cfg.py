@@ -77,6 +77,29 @@ def parse_megatron_cfg(cfg) -> Dict[str, Any]:
                 optim=model.get("optim"), precision=parallel["precision"])
 
 
+def debug_sized(arch: Dict[str, Any]) -> Dict[str, Any]:
+    """A multi-billion-parameter recipe on a single CPU process can only be a plumbing run: keep the family, the head layout
+    and the vocabulary, shrink depth and width (``TRLX_B200_FULL_SIZE=1`` keeps the recipe's size)."""
+    import torch
+
+    if torch.cuda.is_available() or int(os.environ.get("WORLD_SIZE", "1")) > 1 or os.environ.get("TRLX_B200_FULL_SIZE") == "1":
+        return arch
+    hidden = int(arch.get("n_embd", arch.get("hidden_size", 0)) or 0)
+    layers = int(arch.get("n_layer", arch.get("num_hidden_layers", 0)) or 0)
+    if 12 * hidden * hidden * layers < 1_000_000_000:
+        return arch
+    small = dict(arch)
+    for key, val in (("n_embd", 64), ("hidden_size", 64), ("n_layer", 2), ("num_hidden_layers", 2), ("n_head", 4),
+                     ("num_attention_heads", 4), ("num_key_value_heads", 4), ("n_inner", 256), ("intermediate_size", 256)):
+        if key in small:
+            small[key] = val
+    import warnings
+
+    warnings.warn(f"megatron_cfg: {layers} x {hidden} model on one CPU process — using a 2 x 64 model of the same family for this "
+                  "run (set TRLX_B200_FULL_SIZE=1 to keep the recipe's size)")
+    return small
+
+
 def apply_megatron_cfg(config, megatron_cfg, pretrained_model: Optional[str] = None):
     """Fold a recipe into a :class:`TRLConfig` (returns a new config): parallel layout, architecture (unless a checkpoint
     directory / explicit model is given) and, when the recipe carries one, the optimizer + schedule."""

@@ -60,6 +60,15 @@ class Runtime:
     # ---- topology ---------------------------------------------------------------------------------------------------
     def _build_groups(self):
         tp, pp = int(self.parallel.tensor_parallel), int(self.parallel.pipeline_parallel)
+        if self.world_size == 1 and tp * pp > 1:
+            # a single process cannot be mis-sharded: run the recipe unsharded (debugging / smoke runs of the NeMo-style examples)
+            import warnings
+
+            warnings.warn(f"tensor_parallel={tp} x pipeline_parallel={pp} requested but only one process is running: "
+                          "continuing without model parallelism")
+            tp = pp = 1
+            self.parallel.tensor_parallel = self.parallel.pipeline_parallel = 1
+            self.parallel.sequence_parallel = False
         if self.world_size % (tp * pp) != 0:
             raise ValueError(f"world_size {self.world_size} is not divisible by tp*pp = {tp * pp}")
         self.tp_size, self.pp_size = tp, pp

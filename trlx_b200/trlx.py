@@ -65,6 +65,9 @@ def train(  # noqa: C901
 
     batch_size = config.train.batch_size * int(os.environ.get("WORLD_SIZE", 1))
     max_prompt_length = config.train.seq_length - config.method.gen_kwargs["max_new_tokens"]
+    if prompts is not None and max_prompt_length <= 0:
+        raise ValueError(f"train.seq_length ({config.train.seq_length}) leaves no room for prompts next to "
+                         f"gen_kwargs.max_new_tokens ({config.method.gen_kwargs['max_new_tokens']})")
     seq2seq = config.model.model_arch_type == "seq2seq"
     pipeline_cls = get_pipeline(config.train.pipeline)
 
