@@ -8,19 +8,17 @@ import trlx_b200 as trlx
 from examples._offline import GPT2_TINY, offline_model, synthetic_dialogues
 from examples.hh.ppo_hh import apply_preset
 from examples.hh.reward import create_reward_fn
-from trlx_b200.data.configs import ModelConfig, OptimizerConfig, SchedulerConfig, TokenizerConfig, TrainConfig, TRLConfig
-from trlx_b200.models.modeling_ilql import ILQLConfig
+from trlx_b200.data.configs import TRLConfig
+from trlx_b200.data.default_configs import default_ilql_config
 
-default_config = TRLConfig(
-    train=TrainConfig(seq_length=1024, batch_size=4, epochs=100, total_steps=20000, checkpoint_interval=10000, eval_interval=1000,
-                      pipeline="PromptPipeline", trainer="AccelerateILQLTrainer", checkpoint_dir="checkpoints/ilql_hh"),
-    model=ModelConfig(model_path="EleutherAI/gpt-j-6B", num_layers_unfrozen=-1),
-    tokenizer=TokenizerConfig(tokenizer_path="EleutherAI/gpt-j-6B", truncation_side="left"),
-    optimizer=OptimizerConfig(name="adamw", kwargs=dict(lr=1e-6, betas=(0.9, 0.95), eps=1.0e-8, weight_decay=1.0e-6)),
-    scheduler=SchedulerConfig(name="cosine_annealing", kwargs=dict(T_max=1000000000, eta_min=1e-6)),
-    method=ILQLConfig(name="ilqlconfig", tau=0.6, gamma=0.99, cql_scale=0.1, awac_scale=1, alpha=0.0001, beta=0,
-                      steps_for_target_q_sync=1, two_qs=True,
-                      gen_kwargs=dict(max_new_tokens=128, top_k=20, beta=[1, 4], temperature=1.0)),
+default_config = default_ilql_config().evolve(
+    train=dict(seq_length=1024, batch_size=4, total_steps=20000, checkpoint_interval=10000, eval_interval=1000,
+               checkpoint_dir="checkpoints/ilql_hh"),
+    model=dict(model_path="EleutherAI/gpt-j-6B"),
+    tokenizer=dict(tokenizer_path="EleutherAI/gpt-j-6B", truncation_side="left"),
+    optimizer=dict(kwargs=dict(lr=1e-6)),
+    scheduler=dict(kwargs=dict(T_max=1000000000, eta_min=1e-6)),
+    method=dict(tau=0.6, alpha=0.0001, steps_for_target_q_sync=1, gen_kwargs=dict(max_new_tokens=128, beta=[1, 4])),
 )
 _ILQL_MODELS = {"125M": "EleutherAI/pythia-125m-deduped", "1B": "EleutherAI/pythia-1.4b-deduped", "6B": "EleutherAI/pythia-6.9b-deduped",
                 "20B": "EleutherAI/gpt-neox-20b"}

@@ -7,17 +7,16 @@ import trlx_b200 as trlx
 from examples._offline import GPT2_TINY, offline_model, synthetic_dialogues
 from examples.hh.ppo_hh import apply_preset
 from examples.hh.reward import create_reward_fn
-from trlx_b200.data.configs import ModelConfig, OptimizerConfig, SchedulerConfig, TokenizerConfig, TrainConfig, TRLConfig
-from trlx_b200.trainer.accelerate_sft_trainer import SFTConfig
+from trlx_b200.data.configs import TRLConfig
+from trlx_b200.data.default_configs import default_sft_config
 
-default_config = TRLConfig(
-    train=TrainConfig(seq_length=1024, epochs=100, total_steps=10000, batch_size=4, checkpoint_interval=10000, eval_interval=1000,
-                      pipeline="PromptPipeline", trainer="AccelerateSFTTrainer", checkpoint_dir="checkpoints/sft_hh"),
-    model=ModelConfig(model_path="EleutherAI/gpt-j-6B", num_layers_unfrozen=-1),
-    tokenizer=TokenizerConfig(tokenizer_path="EleutherAI/gpt-j-6B", truncation_side="left"),
-    optimizer=OptimizerConfig(name="adamw", kwargs=dict(lr=1e-6, betas=(0.9, 0.95), eps=1.0e-8, weight_decay=1.0e-6)),
-    scheduler=SchedulerConfig(name="cosine_annealing", kwargs=dict(T_max=100000000, eta_min=1e-6)),
-    method=SFTConfig(name="sftconfig", gen_kwargs=dict(max_new_tokens=128, top_k=20, top_p=1.0, do_sample=True)),
+default_config = default_sft_config().evolve(
+    train=dict(total_steps=10000, batch_size=4, eval_interval=1000, checkpoint_dir="checkpoints/sft_hh"),
+    model=dict(model_path="EleutherAI/gpt-j-6B"),
+    tokenizer=dict(tokenizer_path="EleutherAI/gpt-j-6B", truncation_side="left"),
+    optimizer=dict(kwargs=dict(lr=1e-6)),
+    scheduler=dict(kwargs=dict(T_max=100000000, eta_min=1e-6)),
+    method=dict(gen_kwargs=dict(max_new_tokens=128, top_k=20)),
 )
 apply_preset(default_config, os.environ.get("CONFIG_NAME"), "sft_hh")
 

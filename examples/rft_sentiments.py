@@ -8,19 +8,18 @@ import torch
 
 import trlx_b200 as trlx
 from examples._offline import GPT2_SMALL, load_imdb, offline_model, sentiment_scorer
-from trlx_b200.data.configs import ModelConfig, OptimizerConfig, SchedulerConfig, TokenizerConfig, TrainConfig, TRLConfig
+from trlx_b200.data.configs import TRLConfig
+from trlx_b200.data.default_configs import default_sft_config
 from trlx_b200.trainer.accelerate_rft_trainer import RFTConfig
 
-default_config = TRLConfig(
-    train=TrainConfig(seq_length=1024, epochs=100, total_steps=1000, batch_size=32, checkpoint_interval=10000, eval_interval=100,
-                      pipeline="PromptPipeline", trainer="AccelerateRFTTrainer"),
-    model=ModelConfig(model_path=offline_model("lvwerra/gpt2-imdb", GPT2_SMALL), num_layers_unfrozen=-1),
-    tokenizer=TokenizerConfig(tokenizer_path="gpt2", truncation_side="right"),
-    optimizer=OptimizerConfig(name="adamw", kwargs=dict(lr=3e-5, betas=(0.9, 0.95), eps=1.0e-8, weight_decay=1.0e-6)),
-    scheduler=SchedulerConfig(name="cosine_annealing", kwargs=dict(T_max=1e12, eta_min=3e-5)),
-    method=RFTConfig(name="RFTConfig", n_generations_per_prompt=4, start_percentile=0.9, end_percentile=0.95, n_improve_steps=1,
-                     gen_kwargs=dict(max_new_tokens=40, top_k=0, top_p=1.0, temperature=1.0, do_sample=True)),
+default_config = default_sft_config().evolve(   # same optimiser recipe as SFT at the PPO learning rate, RFT method on top
+    train=dict(trainer="AccelerateRFTTrainer", batch_size=32),
+    model=dict(model_path=offline_model("lvwerra/gpt2-imdb", GPT2_SMALL)),
+    optimizer=dict(kwargs=dict(lr=3e-5)),
+    scheduler=dict(kwargs=dict(eta_min=3e-5)),
 )
+default_config.method = RFTConfig(name="RFTConfig", n_generations_per_prompt=4, n_improve_steps=1, start_percentile=0.9,
+                                  end_percentile=0.95, gen_kwargs=dict(default_config.method.gen_kwargs, temperature=1.0))
 
 
 def main(hparams={}):
