@@ -108,10 +108,8 @@ class MiniBatchIterator:
     def __next__(self) -> List[Any]:
         batch = next(self.data_loader_iter)
         if batch is None:
-            logger.warning(
-                "WARNING: Not enough samples to saturate the minibatch size. Increase the number "
-                "of prompts or samples or decrease the minibatch size."
-            )
+            logger.warning("MiniBatchIterator: the loader produced no batch — there are fewer samples than one minibatch needs; "
+                           "add prompts / samples or lower `train.minibatch_size`")
             raise StopIteration
         cols = _columns(batch)
         n_total = min((len(v) for v in cols.values() if v is not None), default=0)
@@ -124,18 +122,12 @@ class MiniBatchIterator:
             n_rows = min((len(v) for v in piece.values() if v is not None), default=0)
             if n_rows == 0:
                 if self.num_mb > 1:
-                    logger.warning(
-                        "WARNING: MiniBatchIterator generated a minibatch with 0 elements. "
-                        "This may be due to the wrong mb_size and/or num_mb or the last batch "
-                        "in the dataset being smaller."
-                    )
+                    logger.warning(f"MiniBatchIterator: micro-batch {i} of {self.num_mb} is empty (batch of {n_total} rows, "
+                                   f"mb_size {self.mb_size}): short last batch, or mb_size x num_mb exceeds the batch size")
                 break
             if self.num_mb > 1 and n_rows < self.mb_size:
-                logger.warning(
-                    "WARNING: MiniBatchIterator generated a minibatch with fewer elements than mb_size. "
-                    "This may be due to the wrong mb_size and/or num_mb or the last batch in the dataset "
-                    "being smaller."
-                )
+                logger.warning(f"MiniBatchIterator: micro-batch {i} holds {n_rows} of {self.mb_size} rows (short last batch, or "
+                               "mb_size x num_mb exceeds the batch size)")
             out.append(_rebuild(batch, piece))
         if not out:
             raise StopIteration

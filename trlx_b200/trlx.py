@@ -38,62 +38,68 @@ def train(  # noqa: C901
     :param stop_sequences: generations are trimmed (and right-stripped) at the first occurrence of any of these
     :returns: the trainer
     """
-    if config is None:
-        warnings.warn("Passing the `config` argument implicitly is depreciated, use or adapt some from "
-                      "`trlx_b200/data/default_configs.py` instead")
-        if reward_fn:
-            config = default_ppo_config()
-        elif rewards:
-            config = default_ilql_config()
-        else:
-            config = default_sft_config()
-
-    if os.environ.get("TRLX_B200_PARALLEL"):  # launch preset (python -m trlx_b200.launch --config_file …)
-        import json
-
-        config = config.evolve(train=dict(parallel=json.loads(os.environ["TRLX_B200_PARALLEL"])))
+    config = _resolve_config(config, model_path, online=bool(reward_fn), with_rewards=bool(rewards) or bool(dataset))
     set_seed(config.train.seed, config.train.parallel)
-
     if dataset:
         warnings.warn("the `dataset` argument is being depreciated, split it into `samples` and `rewards` instead")
         samples, rewards = dataset
-    if model_path:
-        config.model.model_path = model_path
 
-    trainer = get_trainer(config.train.trainer)(config=config, reward_fn=reward_fn, metric_fn=metric_fn,
-                                                stop_sequences=stop_sequences, **config.train.trainer_kwargs)
+    trainer_cls = get_trainer(config.train.trainer)
+    trainer = trainer_cls(config=config, reward_fn=reward_fn, metric_fn=metric_fn, stop_sequences=stop_sequences,
+                          **config.train.trainer_kwargs)
 
-    batch_size = config.train.batch_size * int(os.environ.get("WORLD_SIZE", 1))
-    max_prompt_length = config.train.seq_length - config.method.gen_kwargs["max_new_tokens"]
-    if prompts is not None and max_prompt_length <= 0:
+    global_batch = config.train.batch_size * int(os.environ.get("WORLD_SIZE", 1))
+    new_tokens = config.method.gen_kwargs["max_new_tokens"]
+    prompt_budget = config.train.seq_length - new_tokens
+    if prompts is not None and prompt_budget <= 0:
         raise ValueError(f"train.seq_length ({config.train.seq_length}) leaves no room for prompts next to "
-                         f"gen_kwargs.max_new_tokens ({config.method.gen_kwargs['max_new_tokens']})")
-    seq2seq = config.model.model_arch_type == "seq2seq"
-    pipeline_cls = get_pipeline(config.train.pipeline)
+                         f"gen_kwargs.max_new_tokens ({new_tokens})")
+    bos = trainer.tokenizer.bos_token
 
-    if reward_fn:  # online
-        prompts = prompts or [trainer.tokenizer.bos_token] * batch_size
-        if eval_prompts is None:
-            eval_prompts = prompts[:batch_size]
-        trainer.add_prompt_pipeline(pipeline_cls(prompts, max_prompt_length, trainer.tokenizer, add_special_tokens=seq2seq))
-    elif samples:  # offline
-        if rewards is not None and len(samples) != len(rewards):
-            raise ValueError(f"Number of samples {len(samples)} should match the number of rewards {len(rewards)}")
-        if eval_prompts is None:
-            eval_prompts = [trainer.tokenizer.bos_token] * batch_size
-        if rewards is not None:
+    def prompt_pipeline(items):
+        return get_pipeline(config.train.pipeline)(items, prompt_budget, trainer.tokenizer,
+                                                   add_special_tokens=config.model.model_arch_type == "seq2seq")
+
+    if reward_fn:
+        # online methods (PPO, RFT): roll out from the prompts; with none given, generation starts from BOS
+        prompts = prompts or [bos] * global_batch
+        eval_prompts = prompts[:global_batch] if eval_prompts is None else eval_prompts
+        trainer.add_prompt_pipeline(prompt_pipeline(prompts))
+    elif samples:
+        # offline methods: ILQL when rewards come with the samples, SFT otherwise
+        if rewards is None:
+            trainer.make_experience(samples, config.train.seq_length)
+        elif len(rewards) == len(samples):
             trainer.make_experience(samples, rewards, config.train.seq_length)
         else:
-            trainer.make_experience(samples, config.train.seq_length)
+            raise ValueError(f"Number of samples {len(samples)} should match the number of rewards {len(rewards)}")
+        eval_prompts = [bos] * global_batch if eval_prompts is None else eval_prompts
     else:
         raise ValueError("Either `samples` or `reward_fn` should be given for training")
+    trainer.add_eval_pipeline(prompt_pipeline(eval_prompts))
 
-    trainer.add_eval_pipeline(pipeline_cls(eval_prompts, max_prompt_length, trainer.tokenizer, add_special_tokens=seq2seq))
-
-    if config.train.resume_from_checkpoint and os.path.exists(config.train.resume_from_checkpoint):
-        trainer.load(config.train.resume_from_checkpoint)
+    checkpoint = config.train.resume_from_checkpoint
+    if checkpoint and os.path.exists(checkpoint):
+        trainer.load(checkpoint)
 
     trainer.learn()
     if hasattr(trainer, "release_device_state"):
         trainer.release_device_state()  # captured CUDA graphs must not outlive the process group they reference
     return trainer
+
+
+def _resolve_config(config: Optional[TRLConfig], model_path, online: bool, with_rewards: bool) -> TRLConfig:
+    """The config the run uses: the caller's, or (deprecated) a default picked from which arguments were given; then the launch
+    preset of ``python -m trlx_b200.launch`` (``TRLX_B200_PARALLEL``) and the ``model_path`` override."""
+    if config is None:
+        warnings.warn("Passing the `config` argument implicitly is depreciated, use or adapt some from "
+                      "`trlx_b200/data/default_configs.py` instead")
+        config = default_ppo_config() if online else (default_ilql_config() if with_rewards else default_sft_config())
+    preset = os.environ.get("TRLX_B200_PARALLEL")
+    if preset:
+        import json
+
+        config = config.evolve(train=dict(parallel=json.loads(preset)))
+    if model_path:
+        config.model.model_path = model_path
+    return config
