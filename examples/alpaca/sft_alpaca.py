@@ -10,16 +10,19 @@ from examples._offline import GPT2_TINY, load_imdb, offline_model, sentiment_sco
 from trlx_b200.data.default_configs import TRLConfig, default_sft_config
 
 
+# The (public) Stanford Alpaca prompt format: a fixed preamble, then "### Instruction" / optional "### Input" / "### Response".
+_PREAMBLE = {True: "Below is an instruction that describes a task, paired with an input that provides further context. "
+                   "Write a response that appropriately completes the request.",
+             False: "Below is an instruction that describes a task. Write a response that appropriately completes the request."}
+
+
 def preprocess(instruction: str, input: str, output: str):
-    """Build Alpaca prompt and output from instruction and input/output examples"""
+    """``[prompt, output]`` pair for the SFT trainer (the loss covers the output only)."""
+    sections = [_PREAMBLE[bool(input)], f"### Instruction:\n{instruction}"]
     if input:
-        prefix = ("Below is an instruction that describes a task, paired with an input that provides further context. "
-                  "Write a response that appropriately completes the request.")
-        prompt = f"{prefix}\n\n### Instruction:\n{instruction}\n\n### Input:\n{input}\n\n### Response:\n"
-    else:
-        prefix = "Below is an instruction that describes a task. Write a response that appropriately completes the request."
-        prompt = f"{prefix}\n\n### Instruction:\n{instruction}\n\n### Response:\n"
-    return [prompt, output]
+        sections.append(f"### Input:\n{input}")
+    sections.append("### Response:\n")
+    return ["\n\n".join(sections), output]
 
 
 def load_alpaca(path_or_name: str):
