@@ -3,7 +3,7 @@ import json
 import sys
 
 import trlx_b200 as trlx
-from examples.randomwalks import generate_random_walks
+from examples.randomwalks import online_task
 from examples.randomwalks.randomwalks import MODEL, TOKENIZER
 from trlx_b200.data.configs import TRLConfig
 from trlx_b200.data.default_configs import default_sft_config
@@ -20,9 +20,7 @@ default_config.method = RFTConfig(name="RFTConfig", n_generations_per_prompt=100
 
 def main(hparams={}):
     config = TRLConfig.update(default_config, hparams)
-    metric_fn, prompts, *_ = generate_random_walks(seed=config.train.seed)
-    return trlx.train(reward_fn=lambda samples, **kw: metric_fn(samples)["optimality"], prompts=prompts, eval_prompts=prompts,
-                      metric_fn=lambda samples, **kw: metric_fn(samples), config=config)
+    return trlx.train(config=config, **online_task(config.train.seed))
 
 
 if __name__ == "__main__":
