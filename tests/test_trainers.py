@@ -217,3 +217,28 @@ def test_prompt_width_buckets():
     assert bucket(17, 32) == 32 and bucket(32, 32) == 32
     for w in range(1, 2048):
         assert w <= bucket(w) < max(w + 8, w * 1.25 + 1)
+
+
+def test_ppo_full_finetune_with_host_resident_reference(tmp_path):
+    """``trainer_kwargs.offload_reference``: no second model; the reference weights are swapped in from host copies."""
+    import trlx_b200 as trlx
+    from trlx_b200.data.default_configs import default_ppo_config
+    from trlx_b200.trainer.accelerate_ppo_trainer import _SwappedReference
+
+    cfg = default_ppo_config().evolve(
+        train=dict(total_steps=2, batch_size=4, seq_length=24, tracker=None, checkpoint_interval=100, eval_interval=100,
+                   checkpoint_dir=str(tmp_path), trainer_kwargs=dict(offload_reference=True)),
+        model=dict(model_path=dict(model_type="gpt2", vocab_size=257, n_embd=16, n_layer=2, n_head=2, n_positions=32,
+                                   eos_token_id=256, bos_token_id=256), num_layers_unfrozen=-1),
+        tokenizer=dict(tokenizer_path="toy://bytes"),
+        method=dict(num_rollouts=8, chunk_size=4, ppo_epochs=1, gen_kwargs=dict(max_new_tokens=6)))
+    trainer = trlx.train(reward_fn=lambda samples, **kw: [float(len(s)) for s in samples], prompts=["ab", "cd", "ef", "gh"] * 2,
+                         eval_prompts=["ab"], config=cfg)
+    assert isinstance(trainer.ref_model, _SwappedReference) and trainer.iter_count >= 2
+    # the policy has moved, the reference has not: its forward differs from the policy's and restores the policy afterwards
+    ids = torch.randint(0, 256, (2, 8))
+    policy_before = trainer.model(ids, return_dict=True).logits.detach().clone()
+    ref_logits = trainer.ref_model(ids, return_dict=True).logits
+    policy_after = trainer.model(ids, return_dict=True).logits.detach()
+    torch.testing.assert_close(policy_before, policy_after)
+    assert (ref_logits - policy_before).abs().max() > 0

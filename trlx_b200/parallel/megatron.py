@@ -48,7 +48,7 @@ class MegatronMixin:
         super().__init__(config, **kwargs)
         self._pp_stage = getattr(self, "_pp_stage", None)
         ref = getattr(self, "ref_model", None)
-        if self._pp_stage is not None and ref is not None:
+        if self._pp_stage is not None and isinstance(ref, torch.nn.Module):
             from trlx_b200.parallel.pipeline_parallel import apply_pipeline_parallel
 
             rt = self.runtime

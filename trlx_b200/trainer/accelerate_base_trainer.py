@@ -86,7 +86,7 @@ class AccelerateRLTrainer(BaseRLTrainer):
     #: ``train.trainer_kwargs`` keys that configure this framework's trainers (read from the config where they are used);
     #: everything else in ``trainer_kwargs`` is a constructor argument, exactly as in the reference (``trlx/trlx.py:92-98``)
     FRAMEWORK_KWARGS = ("prompt_bucket", "rank0_reward", "cache_trunk", "zero_stage", "max_time", "megatron_cfg",
-                        "pretrained_model")
+                        "pretrained_model", "offload_reference", "no_train_graph")
 
     def __init__(self, config: TRLConfig, **kwargs):
         for key in self.FRAMEWORK_KWARGS:

@@ -57,6 +57,42 @@ def _bucket_prompt_width(width: int, fixed: Optional[int] = None) -> int:
     return -(-width // step) * step
 
 
+class _SwappedReference:
+    """Callable stand-in for a separate reference model (``trainer_kwargs.offload_reference``): forwards run through the
+    *policy's* modules while the reference weights — kept as pinned host copies by
+    :class:`~trlx_b200.models.modeling_nemo_ppo.RefLMHeads` — are swapped in, and the policy weights are restored afterwards.
+    Costs two host↔device copies of the trainable parameters per call, saves one full model of device memory."""
+
+    def __init__(self, model):
+        from trlx_b200.models.modeling_nemo_ppo import RefLMHeads
+
+        self.model = model
+        self.swap = RefLMHeads(model.base_model, None, build_reference_model=True)
+
+    @torch.no_grad()
+    def __call__(self, *args, **kwargs):
+        was_training = self.model.training
+        self.model.eval()
+        try:
+            with self.swap.reference():
+                return self.model(*args, **kwargs)
+        finally:
+            self.model.train(was_training)
+
+    # the trainer treats ``ref_model`` like a module in a few places (device moves, eval, checkpoint filters)
+    def eval(self):
+        return self
+
+    def requires_grad_(self, *_):
+        return self
+
+    def to(self, *_, **__):
+        return self
+
+    def parameters(self):
+        return iter(())
+
+
 @register_trainer
 class AcceleratePPOTrainer(AccelerateRLTrainer):
     """PPO on the B200 runtime."""
@@ -75,7 +111,12 @@ class AcceleratePPOTrainer(AccelerateRLTrainer):
 
         # a separate full reference model is only needed when neither a frozen branch nor an adapter provides one
         self.ref_model = None
-        if getattr(self.model, "frozen_head", None) is None and not self.model.peft_type:
+        if getattr(self.model, "frozen_head", None) is None and not self.model.peft_type and \
+                config.train.trainer_kwargs.get("offload_reference", False):
+            # full fine-tuning without a second model in HBM: the reference policy lives in pinned host memory and is swapped
+            # into the policy's own modules for the reference forward (reference: RefLMHeads, modeling_nemo_ppo.py:167-312)
+            self.ref_model = _SwappedReference(self.model)
+        elif getattr(self.model, "frozen_head", None) is None and not self.model.peft_type:
             self.ref_model = self.get_arch(self.config).to(self.runtime.device)
             if self.runtime.cuda and self.runtime.dtype != torch.float32:
                 self.ref_model = self.ref_model.to(self.runtime.dtype)
