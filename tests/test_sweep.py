@@ -145,3 +145,31 @@ def test_scheduler_rungs_and_tune_config():
         sweep.get_scheduler({"scheduler": "pbt"})
     cfg = sweep.get_tune_config({"search_alg": "bohb", "scheduler": "hyperband", "max_t": 9}, {}, 0)
     assert cfg["metric"] == "reward/mean" and cfg["search_alg"].name == "bohb" and cfg["scheduler"]["rungs"][-1] == 9
+
+
+def test_run_sweep_end_to_end_with_model_based_search_and_successive_halving(tmp_path):
+    """A trivial target script logs ``score`` through the jsonl tracker format; the sweep draws trials lazily from the TPE
+    searcher, promotes the best third to the second rung and writes results + report."""
+    script = tmp_path / "target.py"
+    script.write_text(
+        "import json, os\n"
+        "def main(hparams):\n"
+        "    steps = int(hparams.get('train.total_steps', 4))\n"
+        "    x = float(hparams['x'])\n"
+        "    os.makedirs(hparams['train.logging_dir'], exist_ok=True)\n"
+        "    with open(os.path.join(hparams['train.logging_dir'], 'run.jsonl'), 'w') as fh:\n"
+        "        for s in range(steps):\n"
+        "            fh.write(json.dumps({'step': s, 'score': -(x - 0.3) ** 2 + 0.01 * s}) + '\\n')\n")
+    cfg = {"tune_config": {"metric": "score", "mode": "max", "search_alg": "bohb", "scheduler": "hyperband", "max_t": 9,
+                           "reduction_factor": 3, "grace_period": 3, "num_samples": 6, "max_concurrent_trials": 2,
+                           "n_initial_points": 3},
+           "x": {"strategy": "uniform", "values": [0.0, 1.0]}}
+    out = tmp_path / "sweep"
+    results = sweep.run_sweep(str(script), cfg, str(out), num_gpus=0, gpu_ids=[], poll=0.05)
+    assert len(results) == 6 and all(r["returncode"] == 0 for r in results)
+    promoted = [r for r in results if r["budget"] == 9]
+    assert 1 <= len(promoted) <= 2 and all("rung_1" in r["dir"] for r in promoted)
+    best = results[0]
+    assert best["best"] == max(r["best"] for r in results) and best in promoted
+    saved = json.loads((out / "sweep_results.json").read_text())
+    assert saved["metric"] == "score" and len(saved["trials"]) == 6 and (out / "report.md").exists()
