@@ -593,7 +593,10 @@ class RolloutEngine:
         st["seed_dev"].fill_((self.calls * 0x9E3779B1) & 0x7FFFFFFFFFFF)
         st["min_new"] = max(int(g.get("min_new_tokens") or 0), int(g.get("min_length") or 0) - Q, 0)
 
+        torch.cuda.nvtx.range_push("engine/prefill")
         lp_p, ref_lp_p, val_p, trunk_p = self._prefill_maybe_graphed(st, prompt, mask)
+        torch.cuda.nvtx.range_pop()
+        torch.cuda.nvtx.range_push("engine/decode")
 
         if self.use_cuda_graph:
             if st["graph"] is None or st.get("graph_key_min_new") != st["min_new"]:
@@ -631,6 +634,7 @@ class RolloutEngine:
                 if (s_i & 7) == 7 and s_i + 1 < R and int(st["n_running"].item()) == 0:
                     break
 
+        torch.cuda.nvtx.range_pop()
         resp_lens = st["resp_lens"].clone()
         r_max = max(int(resp_lens.max().item()), 1)
         sample_outputs = st["tokens_out"][:, :r_max].clone()
@@ -642,7 +646,9 @@ class RolloutEngine:
         if self.cache_trunk or self.defer_ref:
             trunk = torch.cat([trunk_p, st["trunk_decode"][:, :r_max]], 1)
         if self.defer_ref:
+            torch.cuda.nvtx.range_push("engine/reference_scoring")
             ref_logprobs = self._ref_score(prompt, mask, trunk, all_tokens[:, 1:Q + r_max])
+            torch.cuda.nvtx.range_pop()
             if not self.cache_trunk:
                 trunk = None
         else:

@@ -258,6 +258,18 @@ class Runtime:
 
     # ---- timing / profiling -----------------------------------------------------------------------------------------
     @contextlib.contextmanager
+    def nvtx(self, name: str):
+        """NVTX range only (no events, no synchronisation): phase markers for timelines (``ncu --nvtx``, CUPTI traces)."""
+        if self.cuda:
+            torch.cuda.nvtx.range_push(name)
+            try:
+                yield
+            finally:
+                torch.cuda.nvtx.range_pop()
+        else:
+            yield
+
+    @contextlib.contextmanager
     def phase(self, name: str, sink: Optional[Dict[str, float]] = None):
         """NVTX range + device-timed duration (seconds) stored into ``sink[name]``."""
         if self.cuda:

@@ -540,7 +540,8 @@ class AccelerateRLTrainer(BaseRLTrainer):
             for _ in range(self.n_inner_epochs):
                 train_dataloader = self.create_train_dataloader()
                 for minibatch in MiniBatchIterator(train_dataloader, self.mb_size, self.num_mb):
-                    stats = self.train_step(minibatch)
+                    with self.runtime.nvtx("train_step"):
+                        stats = self.train_step(minibatch)
                     if self.iter_count % self.config.train.checkpoint_interval == 0 or self.iter_count >= self.total_steps:
                         self._save_checkpoint(os.path.join(self.config.train.checkpoint_dir, self._checkpoint_name()))
                     for gi, lr in enumerate(self.scheduler.get_last_lr()):

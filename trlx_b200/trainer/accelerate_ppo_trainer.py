@@ -435,18 +435,22 @@ class AcceleratePPOTrainer(AccelerateRLTrainer):
                     # bucket the (left-padded) prompt width so decode / train-step CUDA graphs see few distinct shapes
                     ids = F.pad(ids, (width - ids.shape[1], 0), value=pad)
                     am = F.pad(am, (width - am.shape[1], 0), value=0)
-                ro = engine.rollout(ids, am)
+                with rt.nvtx("rollout/engine"):
+                    ro = engine.rollout(ids, am)
             else:
-                ro = self._rollout_torch(batch, device)
+                with rt.nvtx("rollout/torch"):
+                    ro = self._rollout_torch(batch, device)
             stats["time/rollout_generate"] = time() - t_gen
 
             prompt_tensors, sample_outputs = ro["prompt_tensors"], ro["sample_outputs"]
             if "strings" in ro and not (self.rank0_reward and rt.distributed):
                 t0 = time()
-                scores = self._score_with_reward_fn(*ro["strings"], metadata, device)
+                with rt.nvtx("rollout/reward_fn"):
+                    scores = self._score_with_reward_fn(*ro["strings"], metadata, device)
                 stats["time/rollout_score"] = time() - t0
             else:
-                scores = self._collect_scores(prompt_tensors, ro["samples"], metadata, device, stats)
+                with rt.nvtx("rollout/reward_fn"):
+                    scores = self._collect_scores(prompt_tensors, ro["samples"], metadata, device, stats)
             scores_mask = scores != float("-inf")
             scores = torch.where(scores_mask, scores, torch.zeros_like(scores))
 
