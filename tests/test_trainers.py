@@ -242,3 +242,24 @@ def test_ppo_full_finetune_with_host_resident_reference(tmp_path):
     policy_after = trainer.model(ids, return_dict=True).logits.detach()
     torch.testing.assert_close(policy_before, policy_after)
     assert (ref_logits - policy_before).abs().max() > 0
+
+
+def test_divergence_watchdog_stops_training_and_keeps_checkpoints_clean(tmp_path):
+    import math
+
+    import trlx_b200 as trlx
+    from trlx_b200.data.default_configs import default_sft_config
+
+    cfg = default_sft_config().evolve(
+        train=dict(total_steps=50, epochs=50, batch_size=2, seq_length=16, tracker=None, checkpoint_interval=1, eval_interval=1000,
+                   checkpoint_dir=str(tmp_path), trainer_kwargs=dict(max_nonfinite_steps=3)),
+        model=dict(model_path=dict(model_type="gpt2", vocab_size=257, n_embd=16, n_layer=1, n_head=2, n_positions=32,
+                                   eos_token_id=256, bos_token_id=256)),
+        tokenizer=dict(tokenizer_path="toy://bytes"), optimizer=dict(kwargs=dict(lr=float("nan"))),
+        scheduler=dict(kwargs=dict(eta_min=float("nan"))), method=dict(gen_kwargs=dict(max_new_tokens=2)))
+    with pytest.raises(FloatingPointError, match="diverged"):
+        trlx.train(samples=["ab", "cd", "ef", "gh"], eval_prompts=["a"], config=cfg)
+    # the first step's loss is still finite (the NaN learning rate only poisons the weights afterwards): exactly that step may
+    # have been checkpointed, none of the poisoned ones
+    saved = [d for d in os.listdir(tmp_path) if d.startswith("checkpoint_")]
+    assert len(saved) <= 1

@@ -86,7 +86,7 @@ class AccelerateRLTrainer(BaseRLTrainer):
     #: ``train.trainer_kwargs`` keys that configure this framework's trainers (read from the config where they are used);
     #: everything else in ``trainer_kwargs`` is a constructor argument, exactly as in the reference (``trlx/trlx.py:92-98``)
     FRAMEWORK_KWARGS = ("prompt_bucket", "rank0_reward", "cache_trunk", "zero_stage", "max_time", "megatron_cfg",
-                        "pretrained_model", "offload_reference", "no_train_graph")
+                        "pretrained_model", "offload_reference", "no_train_graph", "max_nonfinite_steps")
 
     def __init__(self, config: TRLConfig, **kwargs):
         for key in self.FRAMEWORK_KWARGS:
@@ -522,6 +522,28 @@ class AccelerateRLTrainer(BaseRLTrainer):
         stats["time/backward"] = bwd / self.num_mb
         return stats
 
+    _LOSS_KEYS = ("loss", "losses/loss", "losses/total_loss")
+
+    def _check_finite(self, stats: Dict[str, Any]) -> bool:
+        """Divergence watchdog (the reference has none): a non-finite loss is logged, its step never overwrites a
+        checkpoint, and after ``trainer_kwargs.max_nonfinite_steps`` (default 8) consecutive ones training stops with an error
+        instead of burning the remaining budget on NaN weights.  Reads the already-materialised statistics: no extra sync."""
+        import math
+
+        bad = [k for k in self._LOSS_KEYS if isinstance(stats.get(k), (int, float)) and not math.isfinite(stats[k])]
+        if not bad:
+            self._nonfinite_streak = 0
+            return True
+        self._nonfinite_streak = getattr(self, "_nonfinite_streak", 0) + 1
+        limit = int((self.config.train.trainer_kwargs or {}).get("max_nonfinite_steps", 8))
+        logger.warning(f"step {self.iter_count}: non-finite {bad[0]} ({self._nonfinite_streak} in a row; abort at {limit})")
+        if self._nonfinite_streak >= limit:
+            raise FloatingPointError(
+                f"training diverged: {bad[0]} has been non-finite for {self._nonfinite_streak} consecutive steps "
+                f"(last healthy checkpoint is under {self.config.train.checkpoint_dir}); lower the learning rate or enable "
+                "`train.parallel.grad_clip`")
+        return False
+
     def learn(self):  # noqa: C901
         """Train from ``self.store``; checkpoint / evaluate on their intervals; returns the last eval results."""
         logger.info("Starting training")
@@ -542,11 +564,13 @@ class AccelerateRLTrainer(BaseRLTrainer):
                 for minibatch in MiniBatchIterator(train_dataloader, self.mb_size, self.num_mb):
                     with self.runtime.nvtx("train_step"):
                         stats = self.train_step(minibatch)
-                    if self.iter_count % self.config.train.checkpoint_interval == 0 or self.iter_count >= self.total_steps:
-                        self._save_checkpoint(os.path.join(self.config.train.checkpoint_dir, self._checkpoint_name()))
                     for gi, lr in enumerate(self.scheduler.get_last_lr()):
                         stats[f"learning_rate_group_{gi}"] = lr
                     stats = _materialise(stats)
+                    healthy = self._check_finite(stats)
+                    if healthy and (self.iter_count % self.config.train.checkpoint_interval == 0
+                                    or self.iter_count >= self.total_steps):
+                        self._save_checkpoint(os.path.join(self.config.train.checkpoint_dir, self._checkpoint_name()))
                     if self.iter_count % self.config.train.eval_interval == 0 or self.iter_count >= self.total_steps:
                         results = self.evaluate()
                         stats.update(results)
