@@ -177,3 +177,39 @@ def test_logging_rank_filter():
     logging.disable_progress_bar()
     assert not logging.is_progress_bar_enabled() and list(logging.tqdm([1, 2])) == [1, 2]
     logging.enable_progress_bar()
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
+def test_flat_optimizer_partition_with_virtual_ranks(world):
+    """N-virtual-rank simulation of the sharded optimizer layout (no process group): the shards tile the flat buffer exactly, stay
+    16-byte aligned, and `reduce-scatter → per-shard AdamW → all-gather` reproduces the unsharded update."""
+    import copy
+
+    from trlx_b200.ops.reference import adamw_step
+    from trlx_b200.parallel.optim import _ALIGN, _FlatGroup
+
+    torch.manual_seed(world)
+    shapes = [(7, 5), (33,), (16, 16), (1,), (129, 3)]
+    base = [torch.nn.Parameter(torch.randn(*s).to(torch.bfloat16)) for s in shapes]
+    groups = [_FlatGroup(copy.deepcopy(base), world, r, None, symmetric=False) for r in range(world)]
+    g0 = groups[0]
+    assert g0.numel % (_ALIGN * world) == 0 and all(o % _ALIGN == 0 for o in g0.offsets)
+    covered = torch.zeros(g0.numel, dtype=torch.int32)
+    for g in groups:
+        assert g.lo % _ALIGN == 0 and g.shard % _ALIGN == 0 and g.numel == g0.numel and g.offsets == g0.offsets
+        covered[g.lo:g.lo + g.shard] += 1
+    assert bool((covered == 1).all())  # no gaps, no overlap
+    for p, o in zip(g0.params, g0.offsets):  # parameters are views of the flat buffer, padding is zero
+        assert p.data_ptr() == g0.flat_param.data_ptr() + 2 * o
+    # every rank holds a different local gradient; the step uses their mean (data parallelism)
+    grads = [torch.randn(g0.numel) for _ in range(world)]
+    mean_grad = torch.stack(grads).mean(0)
+    hp = dict(lr=1e-2, beta1=0.9, beta2=0.95, eps=1e-8, weight_decay=0.01)
+    full_w = g0.flat_param.float().clone()
+    expect = adamw_step(full_w.clone(), mean_grad.clone(), torch.zeros_like(full_w), torch.zeros_like(full_w), 1, **hp)
+    gathered = torch.empty_like(full_w)
+    for g in groups:
+        sl = slice(g.lo, g.lo + g.shard)
+        reduced = torch.stack([gr[sl] for gr in grads]).mean(0)                      # reduce-scatter
+        gathered[sl] = adamw_step(g.master.clone(), reduced, g.exp_avg, g.exp_avg_sq, 1, **hp)   # all-gather of the new shard
+    torch.testing.assert_close(gathered, expect)
