@@ -69,3 +69,32 @@ def test_seed_is_shared_inside_a_model_parallel_replica(monkeypatch):
             assert (draws[a] == draws[b]) == (dp_of[a] == dp_of[b])
     monkeypatch.setenv("RANK", "0")
     monkeypatch.setenv("WORLD_SIZE", "1")
+
+
+def test_debug_sized_only_shrinks_huge_recipes_on_a_single_cpu_process(monkeypatch):
+    from trlx_b200.parallel.megatron_cfg import debug_sized
+
+    big = dict(model_type="gpt2", n_embd=6144, n_layer=44, n_head=48, n_inner=24576, vocab_size=50304)
+    small = dict(model_type="gpt2", n_embd=64, n_layer=2, n_head=4, vocab_size=100)
+    monkeypatch.delenv("TRLX_B200_FULL_SIZE", raising=False)
+    monkeypatch.setenv("WORLD_SIZE", "1")
+    import torch
+
+    if not torch.cuda.is_available():
+        with pytest.warns(UserWarning, match="2 x 64"):
+            shrunk = debug_sized(big)
+        assert (shrunk["n_embd"], shrunk["n_layer"], shrunk["vocab_size"], shrunk["model_type"]) == (64, 2, 50304, "gpt2")
+    assert debug_sized(small) == small
+    monkeypatch.setenv("TRLX_B200_FULL_SIZE", "1")
+    assert debug_sized(big) == big
+
+
+def test_single_process_runtime_runs_model_parallel_recipes_unsharded(monkeypatch):
+    from trlx_b200.data.configs import ParallelConfig
+    from trlx_b200.parallel.runtime import Runtime
+
+    monkeypatch.setenv("WORLD_SIZE", "1")
+    monkeypatch.setenv("RANK", "0")
+    with pytest.warns(UserWarning, match="without model parallelism"):
+        rt = Runtime(ParallelConfig(tensor_parallel=4, pipeline_parallel=2, sequence_parallel=True))
+    assert (rt.tp_size, rt.pp_size, rt.dp_size) == (1, 1, 1) and rt.parallel.sequence_parallel is False

@@ -137,3 +137,23 @@ def test_device_block_loader_matches_collate():
         assert torch.equal(b.response_tensors[:, :w], ref.response_tensors) and b.response_tensors.shape[1] <= w + 1
         assert torch.equal(b.rewards, ref.rewards) and torch.equal(b.values, ref.values)
         assert b.trunk_hidden.shape[:2] == (len(ref.query_tensors), b.query_tensors.shape[1] + b.response_tensors.shape[1])
+
+
+def test_reward_model_repository_packaging(tmp_path):
+    """``examples/hh/to_triton.py``: the serving entry (weights + serving.json) the reward server is started from."""
+    import json
+    import os
+    import sys
+
+    sys.path.insert(0, os.getcwd())
+    from examples.hh.to_triton import build_repository
+
+    ckpt = tmp_path / "rm"
+    ckpt.mkdir()
+    (ckpt / "pytorch_model.bin").write_bytes(b"weights")
+    (ckpt / "config.json").write_text("{}")
+    (ckpt / "notes.tmp").write_text("ignored")
+    version_dir = build_repository(str(ckpt), str(tmp_path / "store"), "gptj-rm-static", max_batch_size=8, port=8123)
+    assert sorted(os.listdir(version_dir)) == ["config.json", "pytorch_model.bin"]
+    spec = json.loads((tmp_path / "store" / "gptj-rm-static" / "serving.json").read_text())
+    assert spec["max_batch_size"] == 8 and spec["port"] == 8123 and spec["files"] == ["config.json", "pytorch_model.bin"]

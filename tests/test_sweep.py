@@ -173,3 +173,20 @@ def test_run_sweep_end_to_end_with_model_based_search_and_successive_halving(tmp
     assert best["best"] == max(r["best"] for r in results) and best in promoted
     saved = json.loads((out / "sweep_results.json").read_text())
     assert saved["metric"] == "score" and len(saved["trials"]) == 6 and (out / "report.md").exists()
+
+
+def test_launcher_maps_deepspeed_json_onto_the_parallel_preset(tmp_path, capsys):
+    from trlx_b200 import launch
+
+    assert launch.parallel_from_deepspeed({"zero_optimization": {"stage": 3, "reduce_bucket_size": 5e8}, "fp16": {"enabled": True},
+                                           "gradient_clipping": 0.5}) == dict(zero_stage=3, precision="fp16", grad_clip=0.5,
+                                                                              bucket_mb=5e8 * 2 / (1 << 20))
+    ds = tmp_path / "ds.json"
+    ds.write_text(json.dumps({"zero_optimization": {"stage": 2}, "bf16": {"enabled": True}}))
+    rc = launch.main(["--deepspeed_config", str(ds), "--num_processes", "2", "--dry_run", "examples/ppo_sentiments.py"])
+    out = capsys.readouterr().out
+    assert rc == 0 and '"zero_stage": 2' in out and '"precision": "bf16"' in out
+    # the summarisation preset points at its DeepSpeed-style JSON
+    rc = launch.main(["--config_file", "examples/summarize_rlhf/configs/default_accelerate_config.yaml", "--dry_run", "x.py"])
+    out = capsys.readouterr().out
+    assert rc == 0 and "--nproc-per-node=7" in out and '"grad_clip": 1.0' in out
