@@ -282,3 +282,55 @@ def test_pipeline_parallel_trainers_run(kind, tmp_path):
     res = run_distributed(_pp_trainer_job, 2, (kind, str(tmp_path)))
     assert [r["iters"] for r in res] == [3, 3]
     assert res[0]["owned"] == [0, 1] and res[1]["owned"] == [2, 3]
+
+
+def _sp_odd_length_job(rank, world, family):
+    """Sequence parallelism with a length the group cannot shard (7 tokens on 2 ranks) and with a KV-cache decode: the forward
+    falls back to replicated activations, gradients (incl. the block norms after the SP gradient all-reduce) stay exact."""
+    from trlx_b200.models.generation import generate
+    from trlx_b200.models.modeling_ppo import AutoModelForCausalLMWithHydraValueHead
+    from trlx_b200.parallel.tensor_parallel import allreduce_sequence_parallel_grads, apply_tensor_parallel
+
+    cfgs = {"gpt2": dict(model_type="gpt2", vocab_size=48, n_embd=32, n_layer=3, n_head=4, n_positions=32),
+            "llama": dict(model_type="llama", vocab_size=48, hidden_size=32, num_hidden_layers=3, num_attention_heads=4,
+                          num_key_value_heads=2, intermediate_size=64, max_position_embeddings=32)}
+    torch.manual_seed(0)
+    model = AutoModelForCausalLMWithHydraValueHead.from_config(cfgs[family], num_layers_unfrozen=-1).eval()
+    torch.manual_seed(1)
+    out = {}
+    refs = {}
+    for T in (7, 8):  # indivisible, then divisible (sharded) — the same module must handle both back to back
+        ids = torch.randint(0, 48, (2, T))
+        mask = torch.ones(2, T, dtype=torch.long)
+        mask[0, :2] = 0
+        ref = model(ids, mask, return_dict=True)
+        ref.logits.float().pow(2).mean().add(ref.value.pow(2).mean()).backward()
+        norm = model.base_model.transformer.h[1].norm1.weight
+        refs[T] = (ids, mask, ref.logits.detach(), norm.grad.clone(), model.base_model.transformer.h[-1].mlp.down.weight.grad.clone(),
+                   model.base_model.transformer.wte.weight.grad.clone())
+        model.zero_grad()
+    gen_ref = generate(model.base_model, refs[7][0], attention_mask=refs[7][1], max_new_tokens=4, do_sample=False, pad_token_id=0,
+                       eos_token_id=47)
+    apply_tensor_parallel(model, None, rank, world, sequence_parallel=True)
+    for T, (ids, mask, logits, norm_grad, down_grad, wte_grad) in refs.items():
+        res = model(ids, mask, return_dict=True)
+        res.logits.float().pow(2).mean().add(res.value.pow(2).mean()).backward()
+        allreduce_sequence_parallel_grads(model, None)
+        f = down_grad.shape[1] // world
+        out[T] = dict(logits=(res.logits - logits).abs().max().item(),
+                      norm=(model.base_model.transformer.h[1].norm1.weight.grad - norm_grad).abs().max().item(),
+                      down=(model.base_model.transformer.h[-1].mlp.down.weight.grad - down_grad[:, rank * f:(rank + 1) * f]).abs().max().item(),
+                      wte=(model.base_model.transformer.wte.weight.grad - wte_grad).abs().max().item())
+        model.zero_grad()
+    gen = generate(model.base_model, refs[7][0], attention_mask=refs[7][1], max_new_tokens=4, do_sample=False, pad_token_id=0,
+                   eos_token_id=47)
+    out["gen_equal"] = bool(torch.equal(gen, gen_ref))
+    return out
+
+
+@pytest.mark.parametrize("family", ["gpt2", "llama"])
+def test_sequence_parallel_handles_indivisible_lengths_and_cached_decoding(family):
+    for r in run_distributed(_sp_odd_length_job, 2, args=(family,)):
+        for T in (7, 8):
+            assert r[T]["logits"] < 1e-4 and r[T]["norm"] < 1e-5 and r[T]["down"] < 1e-5 and r[T]["wte"] < 1e-5, r
+        assert r["gen_equal"], r

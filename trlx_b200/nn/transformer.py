@@ -69,17 +69,30 @@ class Norm(nn.Module):
         self.weight = nn.Parameter(torch.ones(spec.hidden_size, dtype=dtype))
         self.bias = nn.Parameter(torch.zeros(spec.hidden_size, dtype=dtype)) if spec.norm == "layernorm" else None
 
+    #: optional ``() -> float | None`` installed by sequence parallelism: factor applied to the *gradients* of weight / bias
+    #: (forward values unchanged) for forwards that run with replicated activations, so that the later sum over the
+    #: tensor-parallel group yields the true gradient (parallel/tensor_parallel.py)
+    _grad_scale = None
+
+    def _params(self):
+        factor = self._grad_scale() if self._grad_scale is not None else None
+        if factor is None or factor == 1.0:
+            return self.weight, self.bias
+        scale = lambda p: None if p is None else p.detach() + (p - p.detach()) * factor  # noqa: E731
+        return scale(self.weight), scale(self.bias)
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        weight, bias = self._params()
         if x.is_cuda and x.dtype == torch.bfloat16:
             from trlx_b200 import ops
 
-            if ops.norm_ok(x, self.weight, self.bias):  # forward keeps (mean, rstd); one-pass backward (csrc/norm_train.cu)
-                return ops.layer_norm(x, self.weight, self.bias, self.eps, self.kind != "layernorm")
+            if ops.norm_ok(x, weight, bias):  # forward keeps (mean, rstd); one-pass backward (csrc/norm_train.cu)
+                return ops.layer_norm(x, weight, bias, self.eps, self.kind != "layernorm")
         if self.kind == "layernorm":
-            return F.layer_norm(x, (x.shape[-1],), self.weight, self.bias, self.eps)
+            return F.layer_norm(x, (x.shape[-1],), weight, bias, self.eps)
         xf = x.float()
         xf = xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + self.eps)
-        return (xf.to(x.dtype)) * self.weight
+        return (xf.to(x.dtype)) * weight
 
 
 def alibi_slopes(n_heads: int) -> torch.Tensor:

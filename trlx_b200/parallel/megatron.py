@@ -37,6 +37,11 @@ class MegatronMixin:
                     config = config.evolve(train=dict(total_steps=min(int(plan.max_steps), int(config.train.total_steps))))
             except (KeyError, ValueError, TypeError, OSError) as err:
                 logger.warning(f"megatron_cfg: trainer section not applied ({err})")
+        par = config.train.parallel
+        if int(getattr(par, "tensor_parallel", 1) or 1) > 1 and bool(getattr(par, "sequence_parallel", False)):
+            # with sequence parallelism the activation at the branch point is a per-rank sequence shard whose layout depends on
+            # the length of the forward that produced it: it cannot be stored per rollout and re-sliced per minibatch
+            config = config.evolve(train=dict(trainer_kwargs=dict(cache_trunk=False)))
         pp = int(getattr(config.train.parallel, "pipeline_parallel", 1) or 1)
         if pp > 1:
             if config.model.model_arch_type == "seq2seq":

@@ -127,6 +127,25 @@ class _ScatterSeq(torch.autograd.Function):
         return torch.cat(parts, dim=1), None
 
 
+class _SplitSeqReplicated(torch.autograd.Function):
+    """keep this rank's sequence slice forward, all-gather the gradient slices backward.  For producers whose computation is
+    *replicated* across the group (the embedding lookup): every rank then holds the complete gradient of the full-length
+    activation, so the replicated parameters behind it get full — not partial — gradients (mirror of ``_GatherSeqReplicated``)."""
+
+    @staticmethod
+    def forward(ctx, x, group, rank):
+        ctx.group = group
+        world = dist.get_world_size(group)
+        return x.chunk(world, dim=1)[rank].contiguous()
+
+    @staticmethod
+    def backward(ctx, g):
+        world = dist.get_world_size(ctx.group)
+        parts = [torch.empty_like(g) for _ in range(world)]
+        dist.all_gather(parts, g.contiguous(), group=ctx.group)
+        return torch.cat(parts, dim=1), None, None
+
+
 def split_sequence(x: torch.Tensor, rank: int, world: int) -> torch.Tensor:
     """Keep this rank's slice of the sequence dimension (entering a sequence-parallel region)."""
     return x.chunk(world, dim=1)[rank].contiguous()
@@ -136,16 +155,22 @@ class TPContext:
     def __init__(self, group, rank: int, size: int, sequence_parallel: bool):
         self.group, self.rank, self.size, self.sequence_parallel = group, rank, size, sequence_parallel
         self.fused = None  # set by enable_fused_kernels()
+        self.sp_active = True  # cleared for forwards whose sequence cannot be sharded (see _install_sequence_parallel)
+
+    @property
+    def sp(self) -> bool:
+        """Sequence parallelism applies to the forward that is running."""
+        return self.sequence_parallel and self.sp_active
 
     def enter_column(self, x):
         """Activation entering a column-parallel GEMM."""
-        if self.sequence_parallel:
+        if self.sp:
             return _GatherSeq.apply(x, self.group)
         return _CopyToTP.apply(x, self.group)
 
     def exit_row(self, y):
         """Partial sums leaving a row-parallel GEMM."""
-        if self.sequence_parallel:
+        if self.sp:
             return _ScatterSeq.apply(y, self.group)
         return _ReduceFromTP.apply(y, self.group)
 
@@ -159,7 +184,7 @@ class TPContext:
 
     def column_linear(self, linear: nn.Linear, x: torch.Tensor) -> torch.Tensor:
         """``all_gather_seq(x) · Wᵀ + b`` (SP) / ``x · Wᵀ + b`` with an all-reduced input gradient (no SP)."""
-        if self.sequence_parallel and self._fusable(x, linear, x.shape[0] * x.shape[1]):
+        if self.sp and self._fusable(x, linear, x.shape[0] * x.shape[1]):
             from trlx_b200.parallel.fused_tp import column_linear
 
             return column_linear(self.fused, linear, x)
@@ -167,7 +192,7 @@ class TPContext:
 
     def row_linear(self, linear: nn.Linear, x: torch.Tensor) -> torch.Tensor:
         """``reduce_scatter_seq(x · Wᵀ) + b`` (SP) / ``all_reduce(x · Wᵀ) + b`` (no SP); ``b`` lives on rank 0."""
-        if self.sequence_parallel and x.shape[1] % self.size == 0 and \
+        if self.sp and x.shape[1] % self.size == 0 and \
                 self._fusable(x, linear, x.shape[0] * x.shape[1] // self.size):
             from trlx_b200.parallel.fused_tp import row_linear
 
@@ -329,7 +354,7 @@ def apply_tensor_parallel(model, group, rank: int, size: int, sequence_parallel:
 
 def _gather_before(norm: nn.Module, tp: "TPContext") -> None:
     orig = norm.forward
-    norm.forward = lambda x: orig(_GatherSeqReplicated.apply(x, tp.group, tp.rank))
+    norm.forward = lambda x: orig(_GatherSeqReplicated.apply(x, tp.group, tp.rank) if tp.sp else x)
 
 
 def _install_sequence_parallel(lm, tp: TPContext) -> None:
@@ -340,10 +365,49 @@ def _install_sequence_parallel(lm, tp: TPContext) -> None:
     orig_embed = trunk.embed
 
     def embed(input_ids, position_ids):
-        return split_sequence(orig_embed(input_ids, position_ids), tp.rank, tp.size)
+        x = orig_embed(input_ids, position_ids)
+        if not tp.sp:
+            return x
+        return _SplitSeqReplicated.apply(x, tp.group, tp.rank) if x.requires_grad else split_sequence(x, tp.rank, tp.size)
 
     trunk.embed = embed
     _gather_before(trunk.ln_f, tp)
+
+    # A sequence can only be sharded when its length is a multiple of the group size, and an incremental decode step (KV cache,
+    # one new token) cannot be sharded at all.  Such forwards run with replicated activations (plain tensor parallelism) — the
+    # reference switches sequence parallelism off around inference for the same reason (``modeling_nemo_ppo.py:820-870``).
+    # With autograd the replicated block norms would then hold full instead of partial gradients while the optimizer step still
+    # sums them over the group (``allreduce_sequence_parallel_grads``): their gradients are scaled by 1 / tp for such forwards.
+    from trlx_b200.nn.transformer import Norm
+
+    for name, module in lm.named_modules():
+        if isinstance(module, Norm) and ".h." in f".{name}.":
+            module._grad_scale = lambda: (1.0 / tp.size) if (not tp.sp_active and torch.is_grad_enabled()) else None
+    orig_forward = lm.forward
+
+    def forward(*args, **kw):
+        ids = kw.get("input_ids", args[0] if args else None)
+        hidden_in = kw.get("hidden_in")
+        cached = bool(kw.get("past_key_values")) or bool(kw.get("use_cache"))
+        if kw.get("inputs_embeds") is not None or (ids is None and hidden_in is None):
+            return orig_forward(*args, **kw)
+        if hidden_in is not None:
+            mask, pos = kw.get("attention_mask"), kw.get("position_ids")
+            full = mask.shape[1] if mask is not None else (pos.shape[1] if pos is not None else hidden_in.shape[1])
+            if hidden_in.shape[1] != full:  # already a sequence shard (produced by a sharded forward)
+                tp.sp_active = True
+                return orig_forward(*args, **kw)
+            length = full
+        else:
+            length = ids.shape[1]
+        # The decision is sticky until the next LM forward: the frozen reference branch (``ModelBranch.run_blocks``) and the heads
+        # that consume this forward's activations run right after it, outside this wrapper, and must see the same layout.
+        tp.sp_active = (not cached) and length % tp.size == 0
+        if tp.sp_active and hidden_in is not None:  # a replicated (cached) activation enters a sharded region: keep our slice
+            kw = dict(kw, hidden_in=split_sequence(hidden_in, tp.rank, tp.size))
+        return orig_forward(*args, **kw)  # sp_active False: replicated activations, block norms scale their gradients by 1 / tp
+
+    lm.forward = forward
 
 
 # ---- checkpoint resharding (HF → TP shards and back) ------------------------------------------------------------------------
