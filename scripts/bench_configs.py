@@ -99,15 +99,18 @@ def build(name: str, small: bool, tmp: str):
     if name == "neox20b_tp4":
         arch = tiny(NEOX_20B) if small else NEOX_20B
         world = int(os.environ.get("WORLD_SIZE", "1"))
-        tp = 4 if world % 4 == 0 else (2 if world % 2 == 0 else 1)
+        pp = int(os.environ.get("BENCH_PP", "1"))  # optional pipeline stages on top (world = tp x pp x dp)
+        per_stage = max(world // pp, 1)
+        tp = 4 if per_stage % 4 == 0 else (2 if per_stage % 2 == 0 else 1)
         cfg = default_ppo_config().evolve(
             train=dict(seq_length=64 if small else 1024, batch_size=4 if small else 8, trainer="NeMoPPOTrainer",
-                       parallel=dict(tensor_parallel=tp, sequence_parallel=tp > 1), **common),
+                       parallel=dict(tensor_parallel=tp, pipeline_parallel=pp, sequence_parallel=tp > 1), **common),
             model=dict(model_path=arch, num_layers_unfrozen=2), tokenizer=dict(tokenizer_path=tok or "toy://bpe?vocab=50432"),
             method=dict(num_rollouts=8 if small else 32, chunk_size=4 if small else 16,
                         gen_kwargs=dict(max_new_tokens=16 if small else 64)))
         trainer, step = online(cfg, words(256, 8))
-        return trainer, step, f"PPO, GPT-NeoX-20B-shaped{' (tiny)' if small else ''}, TP={tp} x DP={max(world // tp, 1)}"
+        return trainer, step, (f"PPO, GPT-NeoX-20B-shaped{' (tiny)' if small else ''}, TP={tp} x PP={pp} x "
+                               f"DP={max(world // (tp * pp), 1)}")
     if name == "ilql_gptj":
         arch = tiny(GPTJ_6B) if small else GPTJ_6B
         cfg = default_ilql_config().evolve(

@@ -334,3 +334,32 @@ def test_sequence_parallel_handles_indivisible_lengths_and_cached_decoding(famil
         for T in (7, 8):
             assert r[T]["logits"] < 1e-4 and r[T]["norm"] < 1e-5 and r[T]["down"] < 1e-5 and r[T]["wte"] < 1e-5, r
         assert r["gen_equal"], r
+
+
+# ---- whole trainers on model-parallel layouts (gloo, tiny models) through scripts/bench_configs.py ----------------------------------
+def _run_config_bench(world: int, env: dict) -> dict:
+    import json
+    import subprocess
+    import sys
+
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), "scripts/bench_configs.py", "--config", "neox20b_tp4", "--tiny", "--steps", "1",
+           "--warmup", "1"]
+    full_env = dict(os.environ, OMP_NUM_THREADS="1", BENCH_HANG_DUMP="400", **env)
+    proc = subprocess.run(cmd, env=full_env, capture_output=True, text=True, timeout=900)
+    lines = [ln for ln in proc.stdout.splitlines() if ln.startswith("{")]
+    assert proc.returncode == 0 and lines, proc.stderr[-3000:]
+    return json.loads(lines[-1])
+
+
+def test_ppo_trainer_with_tensor_and_sequence_parallelism_end_to_end():
+    """Rollouts (KV-cache decoding), scoring with the hydra branch and PPO updates on TP = 2 with sequence parallelism, for
+    whatever sequence lengths the prompts produce."""
+    rec = _run_config_bench(2, {})
+    assert "TP=2 x PP=1" in rec["what"] and rec["value"] > 0
+
+
+def test_ppo_trainer_with_tensor_and_pipeline_parallelism_end_to_end():
+    """TP = 2 x PP = 2: sharded separate reference model, 1F1B updates, generation relayed through the stages."""
+    rec = _run_config_bench(4, {"BENCH_PP": "2"})
+    assert "TP=2 x PP=2" in rec["what"] and rec["value"] > 0

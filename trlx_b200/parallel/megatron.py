@@ -38,11 +38,16 @@ class MegatronMixin:
             except (KeyError, ValueError, TypeError, OSError) as err:
                 logger.warning(f"megatron_cfg: trainer section not applied ({err})")
         par = config.train.parallel
-        if int(getattr(par, "tensor_parallel", 1) or 1) > 1 and bool(getattr(par, "sequence_parallel", False)):
+        if int(getattr(par, "tensor_parallel", 1) or 1) > 1 and bool(getattr(par, "sequence_parallel", False)) and \
+                int(getattr(par, "pipeline_parallel", 1) or 1) == 1:
             # with sequence parallelism the activation at the branch point is a per-rank sequence shard whose layout depends on
             # the length of the forward that produced it: it cannot be stored per rollout and re-sliced per minibatch
             config = config.evolve(train=dict(trainer_kwargs=dict(cache_trunk=False)))
         pp = int(getattr(config.train.parallel, "pipeline_parallel", 1) or 1)
+        if pp > 1 and bool(getattr(config.train.parallel, "sequence_parallel", False)):
+            # the stage-to-stage relay exchanges full-length activations; sequence shards would need a gather at every boundary
+            logger.warning("sequence parallelism is not combined with pipeline parallelism: running TP x PP without it")
+            config = config.evolve(train=dict(parallel=dict(sequence_parallel=False)))
         if pp > 1:
             if config.model.model_arch_type == "seq2seq":
                 raise NotImplementedError("pipeline parallelism covers decoder-only models")
@@ -52,17 +57,23 @@ class MegatronMixin:
                 config = config.evolve(model=dict(num_layers_unfrozen=-1))
         super().__init__(config, **kwargs)
         self._pp_stage = getattr(self, "_pp_stage", None)
-        ref = getattr(self, "ref_model", None)
-        if self._pp_stage is not None and isinstance(ref, torch.nn.Module):
+
+    def _shard_like_policy(self, model) -> None:
+        """Give a second model (the separate PPO reference) the policy's tensor / pipeline layout; called before its weights are
+        copied from the (already sharded) policy."""
+        if getattr(model, "_model_parallel_applied", False):
+            return
+        rt = self.runtime
+        if rt.tp_size > 1:
+            from trlx_b200.parallel.tensor_parallel import apply_tensor_parallel
+
+            apply_tensor_parallel(model, rt.tp_group, rt.tp_rank, rt.tp_size,
+                                  sequence_parallel=bool(self.config.train.parallel.sequence_parallel))
+        if rt.pp_size > 1:
             from trlx_b200.parallel.pipeline_parallel import apply_pipeline_parallel
 
-            rt = self.runtime
-            if rt.tp_size > 1:
-                from trlx_b200.parallel.tensor_parallel import apply_tensor_parallel
-
-                apply_tensor_parallel(ref, rt.tp_group, rt.tp_rank, rt.tp_size,
-                                      sequence_parallel=bool(self.config.train.parallel.sequence_parallel))
-            apply_pipeline_parallel(ref, rt.pp_group, rt.pp_rank, rt.pp_size)
+            apply_pipeline_parallel(model, rt.pp_group, rt.pp_rank, rt.pp_size)
+        model._model_parallel_applied = True
 
     def setup_model(self):
         model = super().setup_model()

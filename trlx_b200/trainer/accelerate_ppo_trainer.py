@@ -120,6 +120,8 @@ class AcceleratePPOTrainer(AccelerateRLTrainer):
             self.ref_model = self.get_arch(self.config).to(self.runtime.device)
             if self.runtime.cuda and self.runtime.dtype != torch.float32:
                 self.ref_model = self.ref_model.to(self.runtime.dtype)
+            if hasattr(self, "_shard_like_policy"):  # model-parallel trainers: same TP / PP layout before copying the weights
+                self._shard_like_policy(self.ref_model)
             self.ref_model.load_state_dict({k: v for k, v in self.model.raw_state_dict().items() if v.numel()}, strict=False)
             self.ref_model.eval().requires_grad_(False)
 
