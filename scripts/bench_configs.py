@@ -102,6 +102,7 @@ def build(name: str, small: bool, tmp: str):
         pp = int(os.environ.get("BENCH_PP", "1"))  # optional pipeline stages on top (world = tp x pp x dp)
         per_stage = max(world // pp, 1)
         tp = 4 if per_stage % 4 == 0 else (2 if per_stage % 2 == 0 else 1)
+        tp = int(os.environ.get("BENCH_TP", tp))  # e.g. BENCH_TP=2 on 4 ranks: TP = 2 x DP = 2
         cfg = default_ppo_config().evolve(
             train=dict(seq_length=64 if small else 1024, batch_size=4 if small else 8, trainer="NeMoPPOTrainer",
                        parallel=dict(tensor_parallel=tp, pipeline_parallel=pp, sequence_parallel=tp > 1), **common),
@@ -111,6 +112,44 @@ def build(name: str, small: bool, tmp: str):
         trainer, step = online(cfg, words(256, 8))
         return trainer, step, (f"PPO, GPT-NeoX-20B-shaped{' (tiny)' if small else ''}, TP={tp} x PP={pp} x "
                                f"DP={max(world // (tp * pp), 1)}")
+    if name in ("neox20b_ilql_tp4", "neox20b_sft_tp4"):
+        from trlx_b200.data.default_configs import default_sft_config
+
+        arch = tiny(NEOX_20B) if small else NEOX_20B
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        pp = int(os.environ.get("BENCH_PP", "1"))
+        per_stage = max(world // pp, 1)
+        tp = 4 if per_stage % 4 == 0 else (2 if per_stage % 2 == 0 else 1)
+        ilql = name == "neox20b_ilql_tp4"
+        base = default_ilql_config() if ilql else default_sft_config()
+        cfg = base.evolve(
+            train=dict(seq_length=64, batch_size=8 if small else 32, trainer="NeMoILQLTrainer" if ilql else "NeMoSFTTrainer",
+                       parallel=dict(tensor_parallel=tp, pipeline_parallel=pp, sequence_parallel=tp > 1), **common),
+            model=dict(model_path=arch), tokenizer=dict(tokenizer_path=tok or "toy://bpe?vocab=50432"))
+        set_seed(cfg.train.seed, cfg.train.parallel)
+        trainer = get_trainer(cfg.train.trainer)(config=cfg, **cfg.train.trainer_kwargs)
+        texts = words(512, 12)
+        if ilql:
+            trainer.make_experience([[t[: len(t) // 2], t[len(t) // 2:]] for t in texts], [float(len(t) % 7) for t in texts],
+                                    cfg.train.seq_length)
+        else:
+            trainer.make_experience(texts, cfg.train.seq_length)
+        trainer.add_eval_pipeline(PromptPipeline(texts[:4], 32, trainer.tokenizer))
+        trainer.prepare_learning()
+        state = {"it": None}
+
+        def step():
+            if state["it"] is None:
+                state["it"] = iter(MiniBatchIterator(trainer.create_train_dataloader(), trainer.mb_size, trainer.num_mb))
+            try:
+                mb = next(state["it"])
+            except StopIteration:
+                state["it"] = iter(MiniBatchIterator(trainer.create_train_dataloader(), trainer.mb_size, trainer.num_mb))
+                mb = next(state["it"])
+            trainer.train_step(mb)
+            return cfg.train.batch_size
+        kind = "ILQL" if ilql else "SFT"
+        return trainer, step, f"{kind}, GPT-NeoX-20B-shaped{' (tiny)' if small else ''}, TP={tp} x PP={pp} x DP={max(world // (tp * pp), 1)}"
     if name == "ilql_gptj":
         arch = tiny(GPTJ_6B) if small else GPTJ_6B
         cfg = default_ilql_config().evolve(
@@ -141,7 +180,7 @@ def build(name: str, small: bool, tmp: str):
 
 def main(argv=None):
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
-    ap.add_argument("--config", required=True, choices=["randomwalks", "ilql_gptj", "llama_lora_fp8", "neox20b_tp4"])
+    ap.add_argument("--config", required=True, choices=["randomwalks", "ilql_gptj", "llama_lora_fp8", "neox20b_tp4", "neox20b_ilql_tp4", "neox20b_sft_tp4"])
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--tiny", action="store_true", help="2-layer model of the same family (CPU / plumbing runs)")
