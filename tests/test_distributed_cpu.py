@@ -363,3 +363,19 @@ def test_ppo_trainer_with_tensor_and_pipeline_parallelism_end_to_end():
     """TP = 2 x PP = 2: sharded separate reference model, 1F1B updates, generation relayed through the stages."""
     rec = _run_config_bench(4, {"BENCH_PP": "2"})
     assert "TP=2 x PP=2" in rec["what"] and rec["value"] > 0
+
+
+@pytest.mark.parametrize("world,pp", [(2, 1), (4, 2)])
+def test_model_parallel_trainer_save_and_resume(world, pp, tmp_path):
+    """Every (tensor, pipeline) rank writes and reads back its own shard (``model_state_mp_XX[_YYY].pt``, ``mp_rank_XX[_YYY]/``)."""
+    import subprocess
+    import sys
+
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), "scripts/check_mp_resume.py"]
+    proc = subprocess.run(cmd, env=dict(os.environ, OMP_NUM_THREADS="1", PP=str(pp), CKPT_DIR=str(tmp_path)), capture_output=True,
+                          text=True, timeout=900)
+    assert proc.returncode == 0, proc.stderr[-3000:]
+    assert proc.stdout.count("resume_err 0.000e+00") == world, proc.stdout
+    saved = sorted(os.listdir(tmp_path / "ck"))
+    assert sum(n.startswith("model_state_mp_") for n in saved) == world  # dp = 1: one file per model-parallel rank

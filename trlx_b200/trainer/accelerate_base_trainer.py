@@ -304,9 +304,10 @@ class AccelerateRLTrainer(BaseRLTrainer):
         directory = directory or self.config.train.checkpoint_dir
         os.makedirs(directory, exist_ok=True)
         rank = self.runtime.rank
-        if self.runtime.is_main_process:
+        if self.runtime.dp_rank == 0:  # one writer per model-parallel rank: its tensor / pipeline shard of the weights
             torch.save({k: v.detach().cpu() for k, v in self.model.raw_state_dict().items()},
-                       os.path.join(directory, "model_state.pt"))
+                       os.path.join(directory, self._model_state_name()))
+        if self.runtime.is_main_process:
             with open(os.path.join(directory, "state.json"), "w") as fh:
                 json.dump({"iter_count": self.iter_count, "nth_evaluation": self.nth_evaluation,
                            "world_size": self.runtime.world_size}, fh)
@@ -319,16 +320,26 @@ class AccelerateRLTrainer(BaseRLTrainer):
             self.model.save_pretrained(directory)
         self.runtime.barrier()
 
+    def _model_state_name(self) -> str:
+        """``model_state.pt`` for unsharded models; one file per (tensor, pipeline) rank otherwise."""
+        rt = self.runtime
+        if rt.tp_size == 1 and rt.pp_size == 1:
+            return "model_state.pt"
+        return f"model_state_mp_{rt.tp_rank:02d}" + (f"_{rt.pp_rank:03d}" if rt.pp_size > 1 else "") + ".pt"
+
     def load(self, directory: Optional[str] = None, **kwargs):
         """Restore what :meth:`save` wrote (or, for a plain ``hf_model`` export, just the weights)."""
         directory = directory or self.config.train.checkpoint_dir
-        path = os.path.join(directory, "model_state.pt")
+        path = os.path.join(directory, self._model_state_name())
         if os.path.exists(path):
             sd = torch.load(path, map_location="cpu", weights_only=True)
             own = self.model.raw_state_dict()
             with torch.no_grad():
                 for k, v in sd.items():
                     if k in own:
+                        if own[k].shape != v.shape:
+                            raise ValueError(f"checkpoint tensor {k} has shape {tuple(v.shape)}, the model expects "
+                                             f"{tuple(own[k].shape)}: was it written with a different parallel layout?")
                         own[k].copy_(v.to(own[k].dtype))
         st_path = os.path.join(directory, f"trainer_state_rank{self.runtime.rank}.pt")
         if os.path.exists(st_path):
