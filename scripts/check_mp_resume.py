@@ -11,7 +11,7 @@ from trlx_b200.utils import set_seed
 from trlx_b200.utils.loading import get_trainer
 import torch.distributed as dist
 arch = dict(model_type="gpt_neox", vocab_size=512, hidden_size=64, num_hidden_layers=2, num_attention_heads=4, intermediate_size=128, max_position_embeddings=128, rotary_pct=0.25)
-pp = int(os.environ.get("PP", "1")); world = int(os.environ["WORLD_SIZE"]); tp = world // pp
+pp = int(os.environ.get("PP", "1")); world = int(os.environ["WORLD_SIZE"]); tp = int(os.environ.get("TP", world // pp))
 d = os.environ["CKPT_DIR"]
 cfg = default_sft_config().evolve(train=dict(seq_length=32, batch_size=4, trainer="NeMoSFTTrainer", tracker=None, checkpoint_dir=d, checkpoint_interval=10**9, eval_interval=10**9, total_steps=10**9, parallel=dict(tensor_parallel=tp, pipeline_parallel=pp, sequence_parallel=pp == 1)), model=dict(model_path=arch), tokenizer=dict(tokenizer_path="toy://bpe?vocab=512"))
 def make():
@@ -35,5 +35,13 @@ t2.load(os.path.join(d, "ck"))
 with torch.no_grad():
     b = t2.model(ids, attention_mask=torch.ones_like(ids)).logits
 err = (a - b).abs().max().item()
+# the optimizer state came back too: one more identical step on both trainers must land on the same weights
+t.train_step(mb)
+t2.train_step(mb)
+with torch.no_grad():
+    a2 = t.model(ids, attention_mask=torch.ones_like(ids)).logits
+    b2 = t2.model(ids, attention_mask=torch.ones_like(ids)).logits
+step_err = (a2 - b2).abs().max().item()
+assert step_err < 1e-5 and (a2 - a).abs().max().item() > 0, (step_err, "weights did not move" if (a2 - a).abs().max().item() == 0 else "")
 print(f"rank {dist.get_rank()} resume_err {err:.3e} iter {t2.iter_count} files {sorted(os.listdir(os.path.join(d,'ck')))[:6]} hf {sorted(os.listdir(os.path.join(d,'hf')))[:6]}", flush=True)
 assert err < 1e-5

@@ -367,7 +367,9 @@ def test_ppo_trainer_with_tensor_and_pipeline_parallelism_end_to_end():
 
 @pytest.mark.parametrize("world,pp", [(2, 1), (4, 2)])
 def test_model_parallel_trainer_save_and_resume(world, pp, tmp_path):
-    """Every (tensor, pipeline) rank writes and reads back its own shard (``model_state_mp_XX[_YYY].pt``, ``mp_rank_XX[_YYY]/``)."""
+    """Every (tensor, pipeline) rank writes and reads back its own shard (``model_state_mp_XX[_YYY].pt``, ``mp_rank_XX[_YYY]/``);
+    the script also takes one more optimizer step on the original and the resumed trainer and requires identical weights
+    (optimizer shards, master weights and scheduler came back)."""
     import subprocess
     import sys
 
