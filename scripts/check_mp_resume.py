@@ -45,3 +45,11 @@ step_err = (a2 - b2).abs().max().item()
 assert step_err < 1e-5 and (a2 - a).abs().max().item() > 0, (step_err, "weights did not move" if (a2 - a).abs().max().item() == 0 else "")
 print(f"rank {dist.get_rank()} resume_err {err:.3e} iter {t2.iter_count} files {sorted(os.listdir(os.path.join(d,'ck')))[:6]} hf {sorted(os.listdir(os.path.join(d,'hf')))[:6]}", flush=True)
 assert err < 1e-5
+# weights-only export / import in the per-rank layout (``mp_rank_XX[_YYY]/model_weights.ckpt``) of the model-parallel trainers
+if hasattr(t2, "load_from_pretrained") and (tp > 1 or pp > 1):
+    t3 = make()
+    t3.load_from_pretrained(os.path.join(d, "hf"))
+    with torch.no_grad():
+        c = t3.model(ids, attention_mask=torch.ones_like(ids)).logits
+    assert (c - a).abs().max().item() < 1e-5, (c - a).abs().max().item()
+    print(f"rank {dist.get_rank()} pretrained_roundtrip ok", flush=True)
