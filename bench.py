@@ -16,7 +16,7 @@ sampled tokens and the loss statistics back device→host.
     python bench.py --gpus 1 --steps 5 --warmup 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 \
         bench.py --gpus 8 --steps 5 --warmup 3
-    python bench.py --impl reference      # the unmodified reference (prints why it is unavailable offline)
+    python bench.py --impl reference      # the unmodified reference from baseline/_ref via baseline/run_reference.py
     python bench.py --impl eager          # this framework with every custom kernel disabled (PyTorch eager + NCCL)
 """
 from __future__ import annotations
@@ -47,16 +47,16 @@ BASELINE_PUBLISHED = None  # the reference publishes no throughput number (BASEL
 
 
 def reference_arm(args):
-    """Run the UNMODIFIED reference from baseline/_ref.  Offline this image cannot satisfy its pinned stack:
-    the reference targets transformers 4.32 + accelerate + deepspeed + ray + torchtyping; with the only available
-    transformers (5.5) its forward-kwarg introspection (trlx/models/modeling_base.py:320-326) sees ['self'] because
-    HF now wraps ``forward`` in decorators, so every model call drops its inputs, and its copied per-family branch
-    forwards (trlx/models/modeling_ppo.py:547-1222) use the 4.32 block signatures.  Details: DESIGN.md."""
-    why = ("reference installs only with --no-deps (accelerate/deepspeed/ray/torchtyping not in the offline wheelhouse) and "
-           "its model wrappers are incompatible with the image's transformers 5.5 (needs 4.32): "
-           "inspect.getfullargspec(base_model.forward) -> ['self'] drops all inputs")
-    print(json.dumps({"impl": "reference", "unavailable": why}))
-    return 0
+    """Run the UNMODIFIED reference (``baseline/_ref``) through its own public API — ``trlx.train()`` → stock
+    ``AcceleratePPOTrainer.make_experience`` / ``learn`` — on the same recipe (see ``baseline/run_reference.py``).  Runs in
+    this process' place (``exec``) so none of this framework's modules, kernels or engine are loaded on that path."""
+    runner = os.path.join(ROOT, "baseline", "run_reference.py")
+    if not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "trlx")):
+        print(json.dumps({"impl": "reference", "unavailable": "baseline/_ref is not installed (pip install --no-deps "
+                          "--target baseline/_ref <copy of /root/reference>)"}))
+        return 0
+    os.execv(sys.executable, [sys.executable, runner, "--gpus", str(args.gpus), "--steps", str(args.steps),
+                              "--warmup", str(args.warmup)])
 
 
 class ClockSampler:

@@ -148,7 +148,9 @@ class MegatronMixin:
         rt = self.runtime
         if rt.tp_size == 1 and rt.pp_size == 1:
             return super().save_pretrained(directory, **kwargs)
-        directory = directory or os.path.join(self.config.train.checkpoint_dir, "hf_model")
+        from trlx_b200.utils import resolve_output_dir
+
+        directory = resolve_output_dir(directory or os.path.join(self.config.train.checkpoint_dir, "hf_model"))
         rt.barrier()
         if rt.dp_rank == 0:
             sub = os.path.join(directory, self._mp_subdir())

@@ -29,7 +29,7 @@ from trlx_b200.parallel.runtime import Runtime
 from trlx_b200.pipeline import MiniBatchIterator
 from trlx_b200.trainer import BaseRLTrainer, register_trainer
 from trlx_b200.utils import (filter_non_scalars, get_distributed_config, get_git_tag, get_optimizer_class,
-                             get_scheduler_class, logging, significant)
+                             get_scheduler_class, logging, significant, resolve_output_dir)
 from trlx_b200.utils.modeling import flatten_dict, freeze_bottom_causal_layers, freeze_bottom_seq2seq_layers
 from trlx_b200.utils.tokenizer import load_tokenizer
 
@@ -102,6 +102,11 @@ class AccelerateRLTrainer(BaseRLTrainer):
         self.mb_count = 0
         self.gradient_accumulation_steps = 1
 
+        # relative output locations are resolved once (TRLX_B200_OUT / never into the source checkout)
+        config.train.checkpoint_dir = resolve_output_dir(config.train.checkpoint_dir)
+        config.train.logging_dir = resolve_output_dir(config.train.logging_dir or "logs")
+        if getattr(config.train, "rollout_logging_dir", None):
+            config.train.rollout_logging_dir = resolve_output_dir(config.train.rollout_logging_dir)
         self.runtime = Runtime(config.train.parallel)
         self.accelerator = self.runtime  # attribute name kept for user code written against the reference
         self.runtime.barrier()
@@ -284,6 +289,7 @@ class AccelerateRLTrainer(BaseRLTrainer):
         """HF-layout export (``config.json`` + weights + tokenizer) of the wrapped model."""
         if directory is None:
             directory = os.path.join(self.config.train.checkpoint_dir, "hf_model")
+        directory = resolve_output_dir(directory)
         self.runtime.barrier()
         if self.runtime.is_main_process:
             self.model.save_pretrained(directory, **kwargs)
@@ -301,7 +307,7 @@ class AccelerateRLTrainer(BaseRLTrainer):
 
     def save(self, directory: Optional[str] = None, **kwargs):
         """Full training state: raw model tensors, optimizer shard of every rank, scheduler, RNG, counters."""
-        directory = directory or self.config.train.checkpoint_dir
+        directory = resolve_output_dir(directory or self.config.train.checkpoint_dir)
         os.makedirs(directory, exist_ok=True)
         rank = self.runtime.rank
         if self.runtime.dp_rank == 0:  # one writer per model-parallel rank: its tensor / pipeline shard of the weights
@@ -329,7 +335,7 @@ class AccelerateRLTrainer(BaseRLTrainer):
 
     def load(self, directory: Optional[str] = None, **kwargs):
         """Restore what :meth:`save` wrote (or, for a plain ``hf_model`` export, just the weights)."""
-        directory = directory or self.config.train.checkpoint_dir
+        directory = resolve_output_dir(directory or self.config.train.checkpoint_dir, for_read=True)
         path = os.path.join(directory, self._model_state_name())
         if os.path.exists(path):
             sd = torch.load(path, map_location="cpu", weights_only=True)

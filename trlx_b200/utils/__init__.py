@@ -26,6 +26,48 @@ import numpy as np
 import torch
 
 
+_SOURCE_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def output_root() -> Optional[str]:
+    """Where relative output paths (checkpoints, logs, exports) go.
+
+    ``$TRLX_B200_OUT`` wins.  Otherwise the current directory, like the reference (``checkpoint_dir="ckpts"`` is
+    cwd-relative there) — unless the current directory is inside this source checkout: artefacts written there travel
+    with every repository snapshot (a 498 MB example checkpoint once pushed one over its size limit), so they are
+    redirected to ``<tmp>/trlx_b200_out``.  Returns ``None`` for "use cwd"."""
+    env = os.environ.get("TRLX_B200_OUT")
+    if env:
+        return env
+    cwd = os.path.realpath(os.getcwd())
+    root = os.path.realpath(_SOURCE_ROOT)
+    in_checkout = os.path.exists(os.path.join(root, "__graft_entry__.py")) and (cwd == root or cwd.startswith(root + os.sep))
+    if in_checkout:
+        import tempfile
+
+        return os.path.join(tempfile.gettempdir(), "trlx_b200_out")
+    return None
+
+
+def resolve_output_dir(path: Optional[str], for_read: bool = False) -> Optional[str]:
+    """Map a user-supplied output directory through :func:`output_root`.  Absolute paths pass through; with
+    ``for_read`` an existing cwd-relative path is preferred (loading a checkpoint someone put there on purpose)."""
+    if path is None or os.path.isabs(path):
+        return path
+    if for_read and os.path.exists(path):
+        return path
+    root = output_root()
+    if root is None:
+        return path
+    out = os.path.join(root, path)
+    if not for_read and not getattr(resolve_output_dir, "_told", False):
+        resolve_output_dir._told = True
+        import logging as _logging
+
+        _logging.getLogger(__name__).warning(f"relative output paths are written under {root} (set TRLX_B200_OUT to choose)")
+    return out
+
+
 def is_peft_available() -> bool:
     """External ``peft`` is never required: adapters are implemented in ``trlx_b200.models.peft``."""
     return importlib.util.find_spec("peft") is not None
