@@ -325,3 +325,32 @@ def test_norm_module_cpu_matches_functional():
         norm.bias.uniform_(-0.5, 0.5)
     x = torch.randn(3, 4, 16)
     torch.testing.assert_close(norm(x), torch.nn.functional.layer_norm(x, (16,), norm.weight, norm.bias, norm.eps))
+
+
+def test_from_pretrained_accepts_base_model_checkpoints_and_never_stays_silently_random(tmp_path):
+    """A GPT-2 directory saved from the *base* class (``wte.weight``, ``h.0.*`` — no ``transformer.`` prefix, no
+    ``lm_head``) must load; a checkpoint that matches nothing must raise instead of leaving random weights."""
+    import json
+
+    import transformers
+
+    cfg = transformers.GPT2Config(vocab_size=64, n_embd=32, n_layer=2, n_head=2, n_positions=32)
+    torch.manual_seed(3)
+    hf = transformers.GPT2LMHeadModel(cfg).eval()
+    d = tmp_path / "base_only"
+    d.mkdir()
+    json.dump({**cfg.to_dict(), "architectures": ["GPT2Model"]}, open(d / "config.json", "w"))
+    torch.save(hf.transformer.state_dict(), d / "pytorch_model.bin")  # keys: wte.weight, h.0.ln_1.weight, …
+    model = AutoModelForCausalLMWithValueHead.from_pretrained(str(d)).eval()
+    ids, mask, pos = _inputs(B=2, T=6)
+    with torch.no_grad():
+        want = hf(ids, attention_mask=mask, position_ids=pos).logits
+        got = model(ids, attention_mask=mask, position_ids=pos, return_dict=True).logits
+    assert torch.allclose(got[mask.bool()], want[mask.bool()], atol=1e-4)
+
+    bad = tmp_path / "garbage"
+    bad.mkdir()
+    json.dump(cfg.to_dict(), open(bad / "config.json", "w"))
+    torch.save({"something.else": torch.zeros(3)}, bad / "pytorch_model.bin")
+    with pytest.raises(ValueError, match="randomly initialised"):
+        AutoModelForCausalLMWithValueHead.from_pretrained(str(bad))

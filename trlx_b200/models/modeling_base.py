@@ -59,27 +59,63 @@ def export_base_state_dict(model: nn.Module, prefix: str = "") -> Dict[str, torc
     return {prefix + k: v for k, v in hf.items()}
 
 
+def _base_prefix(lm) -> str:
+    """``transformer.`` / ``model.`` / ``gpt_neox.`` / ``model.decoder.``: what HF puts in front of base-model keys."""
+    try:
+        fam = hf_compat.family(lm.config)
+        return fam.wte.rsplit(".", 1)[0] + "." if "." in fam.wte else ""
+    except Exception:
+        return ""
+
+
 def import_base_state_dict(model: nn.Module, hf_sd: Dict[str, torch.Tensor], strict: bool = True) -> None:
+    """Load an HF-layout (or canonical) state dict into the base LM.
+
+    Accepts checkpoints saved from the *base* model class (``wte.weight``, ``h.0.*`` — no ``transformer.`` prefix, no
+    ``lm_head``; how the hub's ``gpt2`` weights are stored).  Never leaves the model silently random: raises when nothing
+    matched, warns loudly about every non-head tensor that stayed at its initial value (``strict`` raises instead)."""
     lm = base_lm(model)
-    canon = lm.from_hf_state_dict(hf_sd) if hasattr(lm, "from_hf_state_dict") else hf_compat.from_hf(lm.config, hf_sd)
-    if not canon and hf_sd:
-        canon = dict(hf_sd)  # already canonical
+
+    def convert(sd):
+        return lm.from_hf_state_dict(sd) if hasattr(lm, "from_hf_state_dict") else hf_compat.from_hf(lm.config, sd)
+
     target = lm.state_dict()
+    canon = convert(hf_sd)
+    if not any(k in target for k in canon) and hf_sd:
+        prefix = _base_prefix(lm)
+        if prefix and not any(k.startswith(prefix) for k in hf_sd):
+            canon = convert({prefix + k: v for k, v in hf_sd.items()})  # base-model checkpoint: re-attach the prefix
+        if not any(k in target for k in canon):
+            canon = dict(hf_sd)  # already canonical
     remap = {}
     for k, v in canon.items():
         if k in target:
             remap[k] = v
         else:  # LoRA-wrapped projection: weights live under ``.base``
-            alt = k.rsplit(".", 1)[0] + ".base." + k.rsplit(".", 1)[1]
+            alt = k.rsplit(".", 1)[0] + ".base." + k.rsplit(".", 1)[1] if "." in k else k
             if alt in target:
                 remap[alt] = v
             elif strict:
                 raise KeyError(f"unexpected key {k} in checkpoint")
+    if hf_sd and not remap:
+        raise ValueError("no tensor of the checkpoint matches the model (first checkpoint keys: "
+                         f"{list(hf_sd)[:4]}, first model keys: {list(target)[:4]}); refusing to continue with "
+                         "randomly initialised weights")
     missing = [k for k in target if k not in remap and ".lora_" not in k]
     tied = getattr(lm.config, "tie_word_embeddings", False)
     missing = [k for k in missing if not (tied and k == "lm_head.weight")]
-    if strict and missing:
-        raise KeyError(f"checkpoint is missing keys: {missing[:8]}{'…' if len(missing) > 8 else ''}")
+    if "lm_head.weight" in missing and "transformer.wte.weight" in remap and \
+            target["lm_head.weight"].shape == remap["transformer.wte.weight"].shape:
+        remap["lm_head.weight"] = remap["transformer.wte.weight"]  # base-model checkpoint: the head is the embedding
+        missing.remove("lm_head.weight")
+    buffers = {k for k, _ in lm.named_buffers()}
+    missing = [k for k in missing if k not in buffers]
+    if missing:
+        msg = (f"{len(missing)} of {len(target)} model tensors are NOT in the checkpoint and keep their initial values: "
+               f"{missing[:8]}{'…' if len(missing) > 8 else ''}")
+        if strict:
+            raise KeyError(msg)
+        logger.warning(msg)
     lm.load_state_dict(remap, strict=False)
 
 

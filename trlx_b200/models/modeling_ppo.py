@@ -413,7 +413,42 @@ class AutoModelForCausalLMWithHydraValueHead(AutoModelForCausalLMWithValueHead):
                       stop_layer=self.branch_layer).last_hidden_state
 
     def can_share_trunk(self) -> bool:
-        return self.frozen_head is not None and not self.peft_type and self.num_layers_unfrozen > 0
+        # a value branch deeper than the policy branch needs an activation below the shared one: no sharing then
+        # (``score`` and ``forward`` must compute the same value function)
+        import os
+
+        return (self.frozen_head is not None and not self.peft_type and self.num_layers_unfrozen > 0
+                and self.num_value_layers_unfrozen <= self.num_layers_unfrozen
+                and os.environ.get("TRLX_B200_SHARE_TRUNK", "1") != "0")
+
+    def freeze_trunk_parameters(self) -> int:
+        """Mark every parameter below the branch layer as frozen (returns how many tensors changed).
+
+        The shared-trunk paths run the trunk under ``no_grad`` — which is what ``num_layers_unfrozen`` promises — but
+        the reference's ``freeze_bottom_causal_layers`` leaves *learned position embeddings* (GPT-2 ``wpe``, OPT
+        ``embed_positions``) trainable, so there they still receive a gradient through the frozen blocks
+        (``trlx/utils/modeling.py:22-38``).  Here they are frozen explicitly, so the optimizer does not hold state for,
+        decay, or reduce tensors that never get a gradient.  ``train.trainer_kwargs.cache_trunk=False`` +
+        ``TRLX_B200_SHARE_TRUNK=0`` restores the reference behaviour (full forward/backward)."""
+        if not self.can_share_trunk():
+            return 0
+        lm = base_lm(self.base_model)
+        keep = set()
+        blocks = list(lm.transformer.h)
+        for b in blocks[self.branch_layer:]:
+            keep.update(id(p) for p in b.parameters())
+        for name in ("ln_f",):
+            m = getattr(lm.transformer, name, None)
+            if m is not None:
+                keep.update(id(p) for p in m.parameters())
+        if getattr(lm, "lm_head", None) is not None:
+            keep.update(id(p) for p in lm.lm_head.parameters())
+        n = 0
+        for p in lm.parameters():
+            if id(p) not in keep and p.requires_grad:
+                p.requires_grad_(False)
+                n += 1
+        return n
 
     def policy_from_trunk(self, trunk_hidden, attention_mask, position_ids, need_value_hidden: bool = True):
         """Run the trainable top blocks on a cached trunk activation → ``(final hidden, hidden_states tail)``."""

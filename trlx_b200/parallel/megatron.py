@@ -168,3 +168,7 @@ class MegatronMixin:
             for k, v in sd.items():
                 if k in own:
                     own[k].copy_(v.to(own[k].dtype))
+        if hasattr(self.opt, "resync_master"):
+            self.opt.resync_master(reset_moments=True)  # fresh weights: the fp32 master copy and moments restart from them
+        self._after_weights_changed()
+        rt.barrier()

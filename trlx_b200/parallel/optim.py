@@ -165,8 +165,14 @@ class FusedAdamW(Optimizer):
                 fg.rebind_grads()
 
     @torch.no_grad()
-    def step(self, closure=None):
+    def step(self, closure=None, graph=None):
+        """``graph``: a captured CUDA graph whose tail is :meth:`device_step` (whole-train-step graphs) — the host half runs
+        here and the graph replay stands in for the device half, so ``scheduler.step()`` keeps following ``optimizer.step()``."""
         self._lazy_init()
+        if graph is not None:
+            self.host_prepare()
+            graph.replay()
+            return None
         loss = closure() if closure is not None else None
         world, rank = self._world()
         if self._fallback is not None:
@@ -272,6 +278,23 @@ class FusedAdamW(Optimizer):
                 dst.copy_(src)
             fg.flat_grad.zero_()
 
+    @torch.no_grad()
+    def resync_master(self, reset_moments: bool = False) -> None:
+        """Re-derive the fp32 master shard from the bf16 parameters.  MUST be called after any write to the parameters
+        that did not go through :meth:`step` (checkpoint import, ``load_from_pretrained``, manual surgery): the update
+        kernel reads ``master`` and rewrites the flat parameters from it, so a stale master would silently undo the
+        write at the next step."""
+        self._lazy_init()
+        for fg in self._flat or []:
+            if fg is None:
+                continue
+            fg.master.copy_(fg.flat_param[fg.lo:fg.lo + fg.shard].float())
+            if reset_moments:
+                fg.exp_avg.zero_()
+                fg.exp_avg_sq.zero_()
+        if reset_moments:
+            self._step_count_fused = 0
+
     # -- checkpointing ------------------------------------------------------------------------------------------------------
     def state_dict(self) -> Dict[str, Any]:
         self._lazy_init()
@@ -286,13 +309,16 @@ class FusedAdamW(Optimizer):
 
     def load_state_dict(self, sd: Dict[str, Any]) -> None:
         self._lazy_init()
+        mine = "torch" if self._fallback is not None else "flat"
+        if sd.get("kind") != mine:
+            raise ValueError(f"optimizer state was saved by the '{sd.get('kind')}' backend but this run uses '{mine}' "
+                             "(CPU/fp32 ↔ CUDA/bf16 switch?); load the weights only, or resume on the same backend")
         self._step_count_fused = sd.get("step", 0)
-        if sd["kind"] == "torch":
-            if self._fallback is not None:
-                self._fallback.load_state_dict(sd["state"])
+        if mine == "torch":
+            self._fallback.load_state_dict(sd["state"])
             return
-        if self._flat is None:
-            return
+        if len(sd["shards"]) != len(self._flat):
+            raise ValueError("optimizer state has a different number of parameter groups")
         for fg, sh in zip(self._flat, sd["shards"]):
             if fg is None or sh is None:
                 continue

@@ -348,6 +348,10 @@ class AccelerateRLTrainer(BaseRLTrainer):
                                              f"{tuple(own[k].shape)}: was it written with a different parallel layout?")
                         own[k].copy_(v.to(own[k].dtype))
         st_path = os.path.join(directory, f"trainer_state_rank{self.runtime.rank}.pt")
+        if hasattr(self.opt, "resync_master"):
+            # the weights were just written behind the optimizer's back: its fp32 master copy must follow (restored
+            # below when the checkpoint carries optimizer state, which then overwrites it with the exact fp32 values)
+            self.opt.resync_master()
         if os.path.exists(st_path):
             st = torch.load(st_path, map_location="cpu", weights_only=False)
             self.opt.load_state_dict(st["optimizer"])

@@ -157,14 +157,33 @@ class AcceleratePPOTrainer(AccelerateRLTrainer):
                        num_value_layers_unfrozen=config.method.num_value_layers_unfrozen,
                        peft_config=config.model.peft_config, **config.model.model_extra_configs)
 
+    def setup_model(self):
+        model = super().setup_model()
+        if hasattr(model, "freeze_trunk_parameters"):
+            n = model.freeze_trunk_parameters()
+            if n:
+                logger.info(f"shared frozen trunk: {n} parameter tensors below the branch layer (e.g. learned position "
+                            "embeddings) are frozen explicitly; TRLX_B200_SHARE_TRUNK=0 restores full-trunk gradients")
+        return model
+
     # ---- loss -------------------------------------------------------------------------------------------------------------
     def loss(self, batch: PPORLBatch) -> Tuple[torch.Tensor, Dict[str, Any]]:
         dev = self.runtime.device
         pad = self.tokenizer.pad_token_id
         query, response = batch.query_tensors.to(dev), batch.response_tensors.to(dev)
         old_logprobs, old_values, old_rewards = batch.logprobs.to(dev), batch.values.to(dev), batch.rewards.to(dev)
-        response_length = old_rewards.shape[1]
         width_tensor = getattr(batch, "width_tensor", None)  # device-side effective width (CUDA-graph replay)
+        width = getattr(batch, "width", None)
+        trunk_in = getattr(batch, "trunk_hidden", None)
+        if width_tensor is None and width is not None and width < old_rewards.shape[1]:
+            # a static-shape (full block width) batch on the eager path: trim to the widest response of THIS batch, the width
+            # the reference collate would have produced — GAE / whitening run over padded columns too, so the width is maths
+            rtok = min(width + 1, response.shape[1])
+            response = response[:, :rtok]
+            old_logprobs, old_values, old_rewards = old_logprobs[:, :width], old_values[:, :width], old_rewards[:, :width]
+            if trunk_in is not None:
+                trunk_in = trunk_in[:, : query.shape[1] + rtok]
+        response_length = old_rewards.shape[1]
         advantages, returns = self.config.method.get_advantages_and_returns(old_values, old_rewards, response_length,
                                                                             width_tensor=width_tensor)
 
@@ -185,7 +204,7 @@ class AcceleratePPOTrainer(AccelerateRLTrainer):
             start = query.shape[1] - 1
             end = start + response_length
             labels = tokens[:, 1:]
-            trunk = getattr(batch, "trunk_hidden", None)
+            trunk = trunk_in
             if hasattr(self.model, "score") and self.model.can_share_trunk():
                 # heads only on the response rows; trunk activation reused when the store carries it
                 inp, am, pos = tokens[:, :-1], attention_mask[:, :-1], position_ids[:, :-1]

@@ -96,8 +96,7 @@ class GraphedPPOStep:
         if self.graph is None:
             self.capture(batch, width)
         self._load(batch, width)
-        self.trainer.opt.host_prepare()
-        self.graph.replay()
-        self.trainer.opt._opt_called = True  # the step ran inside the graph: keep torch's scheduler-order check quiet
+        # the optimizer step IS the replay: host half (lr, bias corrections → pinned staging), then the captured device half
+        self.trainer.opt.step(graph=self.graph)
         ops.add_launches(self.launches)
         return dict(self.stats)
