@@ -517,18 +517,27 @@ def test_ppo_loss_and_grads():
         torch.testing.assert_close(stats[k].float(), torch.as_tensor(v, device="cuda").float(), atol=2e-3, rtol=2e-3, msg=k)
 
 
-def test_kl_rewards(C):
+def test_rollout_rewards(C):
+    """make_experience's fused post-processing (csrc/rl_ops.cu: rollout_rewards_kernel) vs the PyTorch formulation."""
     torch.manual_seed(11)
     from trlx_b200.ops import reference
 
-    B, R = 16, 12
-    lp, rlp = torch.randn(B, R, device="cuda"), torch.randn(B, R, device="cuda")
-    lens = torch.randint(1, R + 1, (B,), device="cuda", dtype=torch.int32)
+    B, Q, R = 16, 5, 12
+    T = Q + R
+    start = Q - 1
+    lp, rlp, val = (torch.randn(B, T - 1, device="cuda") * 0.3 for _ in range(3))
+    mask = torch.ones(B, T, dtype=torch.long, device="cuda")
+    for b in range(B):
+        mask[b, : b % 3] = 0                       # left-padded prompt
+        mask[b, Q + (b * 5) % (R + 1):] = 0        # response ends early (or never)
     scores = torch.randn(B, device="cuda")
-    rw, st = C.kl_rewards(lp, rlp, lens, scores, 0.05)
-    ref_rw, ref_kl = reference.kl_rewards(lp, rlp, lens, scores, 0.05)
-    torch.testing.assert_close(rw, ref_rw, atol=1e-5, rtol=1e-4)
-    torch.testing.assert_close(st[0].float(), ref_kl.sum(), atol=1e-2, rtol=1e-3)
+    rw, lp_s, v_s, slen, kl = C.rollout_rewards(lp, rlp, val, mask, scores, start, 0.05)
+    ref = reference.rollout_rewards(lp, rlp, val, mask, scores, start, 0.05)
+    torch.testing.assert_close(rw, ref[0], atol=1e-5, rtol=1e-4)
+    torch.testing.assert_close(lp_s, ref[1])
+    torch.testing.assert_close(v_s, ref[2])
+    assert torch.equal(slen.long(), ref[3])
+    torch.testing.assert_close(kl[0].float(), ref[4].float(), atol=1e-2, rtol=1e-3)
 
 
 def test_adamw_flat(C):

@@ -86,6 +86,61 @@ def test_fused_dp_adamw_matches_reference(clip):
         torch.testing.assert_close(got, ref, atol=2e-2, rtol=2e-2)
 
 
+def _dp_overlap_job(rank, world, overlap):
+    """A small MLP trained for a few steps with per-rank data: bucketed (tiny buckets → several of them) fused optimizer,
+    bucket kernels launched from autograd hooks on a side stream while backward is still running."""
+    from trlx_b200.parallel.optim import FusedAdamW
+
+    torch.manual_seed(0)
+    dims = [64, 256, 256, 128, 8]
+    layers = []
+    for a, b in zip(dims[:-1], dims[1:]):
+        layers += [torch.nn.Linear(a, b), torch.nn.Tanh()]
+    net = torch.nn.Sequential(*layers[:-1]).cuda().to(torch.bfloat16)
+    ref = [p.detach().float().clone() for p in net.parameters()]
+    opt = FusedAdamW(net.parameters(), lr=3e-3, betas=(0.9, 0.95), weight_decay=0.0, overlap=overlap, bucket_mb=0.05).prepare()
+    fg = opt._flat[0]
+    grads_log = []
+    for step in range(4):
+        torch.manual_seed(10 * step + rank)
+        x = torch.randn(32, 64, device="cuda").to(torch.bfloat16)
+        loss = net(x).float().pow(2).mean()
+        if opt.can_overlap:
+            opt.host_prepare()
+            opt.arm_overlap()
+        loss.backward()
+        grads_log.append([p.grad.detach().float().cpu().clone() for p in net.parameters()])
+        opt.step()
+        opt.zero_grad()
+    return dict(params=[p.detach().float().cpu() for p in net.parameters()], init=[r.cpu() for r in ref], grads=grads_log,
+                buckets=len(fg.buckets), overlapped=opt.can_overlap, symmetric=fg.symm_grad is not None)
+
+
+@pytest.mark.parametrize("overlap", [True, False])
+def test_bucketed_overlapped_dp_adamw(overlap):
+    """Gradients as produced by a real backward; the bucketed kernels (launched from hooks when ``overlap``) must leave
+    identical replicas that follow the reference AdamW on the rank-averaged gradients — and both schedules must agree."""
+    _need(2)
+    from trlx_b200.ops import reference
+
+    res = run(_dp_overlap_job, 2, args=(overlap,))
+    assert all(r["symmetric"] for r in res) and res[0]["buckets"] >= 3 and res[0]["overlapped"] == overlap
+    for a, b in zip(res[0]["params"], res[1]["params"]):
+        assert torch.equal(a, b)
+    # replay the optimizer on the logged per-rank gradients (the gradients themselves depend on the evolving weights, so
+    # they are taken from the run; what is checked is reduce + update + gather)
+    w = [i.clone() for i in res[0]["init"]]
+    m, v = [torch.zeros_like(x) for x in w], [torch.zeros_like(x) for x in w]
+    for step in range(4):
+        g = [(res[0]["grads"][step][i].to(torch.bfloat16).float() + res[1]["grads"][step][i].to(torch.bfloat16).float()) / 2
+             for i in range(len(w))]
+        for i in range(len(w)):
+            reference.adamw_step(w[i], g[i], m[i], v[i], step + 1, 3e-3, 0.9, 0.95, 1e-8, 0.0)
+            w[i] = w[i].to(torch.bfloat16).float() if False else w[i]
+    for got, ref in zip(res[0]["params"], w):
+        torch.testing.assert_close(got, ref, atol=2e-2, rtol=2e-2)
+
+
 # ---- fused TP GEMM <-> collective kernels -------------------------------------------------------------------------------------
 def _tp_kernels_job(rank, world):
     from trlx_b200.parallel.fused_tp import FusedTP

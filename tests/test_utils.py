@@ -179,10 +179,12 @@ def test_logging_rank_filter():
     logging.enable_progress_bar()
 
 
+@pytest.mark.parametrize("bucket_elems", [1 << 62, 200])
 @pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
-def test_flat_optimizer_partition_with_virtual_ranks(world):
-    """N-virtual-rank simulation of the sharded optimizer layout (no process group): the shards tile the flat buffer exactly, stay
-    16-byte aligned, and `reduce-scatter → per-shard AdamW → all-gather` reproduces the unsharded update."""
+def test_flat_optimizer_partition_with_virtual_ranks(world, bucket_elems):
+    """N-virtual-rank simulation of the sharded, bucketed optimizer layout (no process group): every rank owns 1/world of every
+    gradient bucket, the owned slices tile the flat buffer exactly, stay 16-byte aligned, and `reduce-scatter → per-shard AdamW →
+    all-gather` bucket by bucket reproduces the unsharded update."""
     import copy
 
     from trlx_b200.ops.reference import adamw_step
@@ -191,13 +193,18 @@ def test_flat_optimizer_partition_with_virtual_ranks(world):
     torch.manual_seed(world)
     shapes = [(7, 5), (33,), (16, 16), (1,), (129, 3)]
     base = [torch.nn.Parameter(torch.randn(*s).to(torch.bfloat16)) for s in shapes]
-    groups = [_FlatGroup(copy.deepcopy(base), world, r, None, symmetric=False) for r in range(world)]
+    groups = [_FlatGroup(copy.deepcopy(base), world, r, None, symmetric=False, bucket_elems=bucket_elems) for r in range(world)]
     g0 = groups[0]
     assert g0.numel % (_ALIGN * world) == 0 and all(o % _ALIGN == 0 for o in g0.offsets)
+    assert len(g0.buckets) == (1 if bucket_elems > 10 ** 6 else 2)
+    assert sorted(i for b in g0.buckets for i in b["params"]) == list(range(len(shapes)))
     covered = torch.zeros(g0.numel, dtype=torch.int32)
     for g in groups:
-        assert g.lo % _ALIGN == 0 and g.shard % _ALIGN == 0 and g.numel == g0.numel and g.offsets == g0.offsets
-        covered[g.lo:g.lo + g.shard] += 1
+        assert g.numel == g0.numel and g.offsets == g0.offsets and g.layout() == g0.layout()
+        assert g.shard == sum(b["shard"] for b in g.buckets) and g.master.numel() == g.shard
+        for b in g.buckets:
+            assert b["mine"] % _ALIGN == 0 and b["shard"] % _ALIGN == 0 and b["lo"] <= b["mine"] and b["mine"] + b["shard"] <= b["hi"]
+            covered[b["mine"]:b["mine"] + b["shard"]] += 1
     assert bool((covered == 1).all())  # no gaps, no overlap
     for p, o in zip(g0.params, g0.offsets):  # parameters are views of the flat buffer, padding is zero
         assert p.data_ptr() == g0.flat_param.data_ptr() + 2 * o
@@ -209,7 +216,9 @@ def test_flat_optimizer_partition_with_virtual_ranks(world):
     expect = adamw_step(full_w.clone(), mean_grad.clone(), torch.zeros_like(full_w), torch.zeros_like(full_w), 1, **hp)
     gathered = torch.empty_like(full_w)
     for g in groups:
-        sl = slice(g.lo, g.lo + g.shard)
-        reduced = torch.stack([gr[sl] for gr in grads]).mean(0)                      # reduce-scatter
-        gathered[sl] = adamw_step(g.master.clone(), reduced, g.exp_avg, g.exp_avg_sq, 1, **hp)   # all-gather of the new shard
+        for b in g.buckets:
+            sl = slice(b["mine"], b["mine"] + b["shard"])
+            ms = slice(b["moff"], b["moff"] + b["shard"])
+            reduced = torch.stack([gr[sl] for gr in grads]).mean(0)                      # reduce-scatter
+            gathered[sl] = adamw_step(g.master[ms].clone(), reduced, g.exp_avg[ms], g.exp_avg_sq[ms], 1, **hp)  # all-gather
     torch.testing.assert_close(gathered, expect)

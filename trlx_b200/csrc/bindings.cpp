@@ -52,7 +52,8 @@ int b200_ppo_loss_num_outputs();
 int b200_ppo_loss_workspace_floats(int);
 int b200_ppo_loss(const float*, const float*, const float*, const float*, const float*, const float*, const float*, int, float,
                   float, float, float*, float*, float*, int, float*, int, const int*, cudaStream_t);
-int b200_kl_rewards(const float*, const float*, const int*, const float*, int, int, float, float*, double*, cudaStream_t);
+int b200_rollout_rewards(const float*, const float*, const float*, const long long*, const float*, int, int, int, float, float*,
+                         float*, float*, int*, double*, cudaStream_t);
 int b200_adamw_flat(void*, float*, const void*, int, float*, float*, long long, float, float, float, float, int, const float*,
                     cudaStream_t);
 int b200_sqnorm(const void*, int, long long, double*, cudaStream_t);
@@ -61,6 +62,11 @@ int b200_signal_barrier(void* const*, int, int, unsigned int*, cudaStream_t);
 int b200_rs_adamw_ag(void* const*, void* const*, int, long long, long long, float*, float*, float*, float*, int, float, float,
                      float, float, int, const float*, double*, cudaStream_t);
 int b200_lerp_bf16(void*, const void*, long long, float, cudaStream_t);
+int b200_rs_adamw_ag_bucket(void* const*, void* const*, int, int, long long, long long, float*, float*, float*, float*, int,
+                            float, float, float, float, int, const float*, double*, void* const*, long long, unsigned int*,
+                            unsigned int*, int, cudaStream_t);
+int b200_clip_exchange(void* const*, void* const*, long long, int, int, const double*, unsigned int*, float, float*, float*,
+                       cudaStream_t);
 int b200_attn_short_ok(int, int, int, int);
 int b200_attn_tc_ok(int, int, int);
 int b200_attn_tc_fwd(const void*, const void*, const void*, const float*, void*, float*, int, int, int, int, int,
@@ -92,6 +98,12 @@ int b200_gemm_stage_scatter_bf16(const void*, const void*, void* const*, int, in
                                  const void*, cudaStream_t);
 int b200_rs_finalize(const float*, const void*, const void*, void*, long long, int, long long, long long, long long,
                      cudaStream_t);
+int b200_decode_mega_make_map(void*, const void*, long long, long long, long long);
+int b200_decode_mega_layer_bytes();
+int b200_decode_mega_stages(int, int);
+int b200_decode_mega_max_clusters(int, int);
+int b200_decode_mega(int, int, int, int, int, int, int, float, float, int, int, const int*, const int*, void*, void*, void*,
+                     const void*, const void*, void*, long long, const long long*, int, const float*, long long*, cudaStream_t);
 }
 
 namespace {
@@ -581,18 +593,26 @@ std::vector<Tensor> ppo_loss(const Tensor& logprobs, const Tensor& values, const
 }
 
 // returns (rewards[B,R], kl_stats double[2] = (sum of per-row KL, rows))
-std::vector<Tensor> kl_rewards(const Tensor& lp, const Tensor& ref_lp, const Tensor& resp_lens, const Tensor& scores,
-                               double kl_coef) {
-  CHECK_F32(lp); CHECK_F32(ref_lp); CHECK_F32(scores);
-  TORCH_CHECK(lp.is_contiguous() && ref_lp.is_contiguous() && resp_lens.scalar_type() == at::kInt);
+
+// make_experience's per-chunk post-processing in one launch → (rewards, logprobs, values on the response window, slice_len, Σk3)
+std::vector<Tensor> rollout_rewards(const Tensor& lp, const Tensor& ref_lp, const Tensor& values, const Tensor& mask,
+                                    const Tensor& scores, int64_t start, double kl_coef) {
+  CHECK_F32(lp); CHECK_F32(ref_lp); CHECK_F32(values); CHECK_F32(scores);
+  TORCH_CHECK(lp.is_contiguous() && ref_lp.is_contiguous() && values.is_contiguous() && mask.is_contiguous() &&
+              scores.is_contiguous() && mask.scalar_type() == at::kLong);
+  const int64_t B = lp.size(0), Tm1 = lp.size(1), R = Tm1 - start;
+  TORCH_CHECK(mask.size(0) == B && mask.size(1) == Tm1 + 1 && scores.numel() == B && R > 0);
   c10::cuda::CUDAGuard guard(lp.device());
-  Tensor rewards = torch::empty_like(lp);
-  Tensor st = torch::zeros({2}, lp.options().dtype(at::kDouble));
-  check(b200_kl_rewards(lp.data_ptr<float>(), ref_lp.data_ptr<float>(), resp_lens.data_ptr<int>(), scores.data_ptr<float>(),
-                        (int)lp.size(0), (int)lp.size(1), (float)kl_coef, rewards.data_ptr<float>(), st.data_ptr<double>(),
-                        stream()),
-        "kl_rewards");
-  return {rewards, st};
+  Tensor rewards = torch::empty({B, R}, lp.options()), lp_out = torch::empty({B, R}, lp.options()),
+         v_out = torch::empty({B, R}, lp.options());
+  Tensor slice_len = torch::empty({B}, lp.options().dtype(at::kInt));
+  Tensor kl = torch::zeros({1}, lp.options().dtype(at::kDouble));
+  check(b200_rollout_rewards(lp.data_ptr<float>(), ref_lp.data_ptr<float>(), values.data_ptr<float>(),
+                             reinterpret_cast<const long long*>(mask.data_ptr<int64_t>()), scores.data_ptr<float>(), (int)B,
+                             (int)Tm1, (int)start, (float)kl_coef, rewards.data_ptr<float>(), lp_out.data_ptr<float>(),
+                             v_out.data_ptr<float>(), slice_len.data_ptr<int>(), kl.data_ptr<double>(), stream()),
+        "rollout_rewards");
+  return {rewards, lp_out, v_out, slice_len, kl};
 }
 
 void adamw_flat(Tensor& param, Tensor& master, const Tensor& grad, Tensor& exp_avg, Tensor& exp_avg_sq, double beta1,
@@ -640,6 +660,43 @@ void rs_adamw_ag(const std::vector<int64_t>& grads, const std::vector<int64_t>& 
                          (float)eps, (float)weight_decay, decoupled ? 1 : 0, hyper.data_ptr<float>(),
                          (double*)optptr(sq_out), stream()),
         "rs_adamw_ag");
+}
+
+// One gradient bucket of the overlapped distributed optimizer; master / exp_avg / exp_avg_sq / gshard are the views of this
+// bucket's shard, `epoch` / `done` 1-element int32 views of the per-bucket device counters.
+void rs_adamw_ag_bucket(const std::vector<int64_t>& grads, const std::vector<int64_t>& params, int64_t rank, int64_t lo,
+                        int64_t n, Tensor& master, Tensor& exp_avg, Tensor& exp_avg_sq, const OptTensor& gshard, int64_t mode,
+                        double beta1, double beta2, double eps, double weight_decay, bool decoupled, const Tensor& hyper,
+                        const OptTensor& sq_out, const std::vector<int64_t>& flags, int64_t flag_offset, Tensor& epoch,
+                        Tensor& done, int64_t max_blocks) {
+  TORCH_CHECK(grads.size() == params.size() && grads.size() == flags.size());
+  TORCH_CHECK(epoch.scalar_type() == at::kInt && done.scalar_type() == at::kInt);
+  std::vector<void*> g(grads.size()), p(params.size()), f(flags.size());
+  for (size_t i = 0; i < grads.size(); ++i) {
+    g[i] = reinterpret_cast<void*>(grads[i]);
+    p[i] = reinterpret_cast<void*>(params[i]);
+    f[i] = reinterpret_cast<void*>(flags[i]);
+  }
+  c10::cuda::CUDAGuard guard(master.device());
+  check(b200_rs_adamw_ag_bucket(g.data(), p.data(), (int)grads.size(), (int)rank, lo, n, master.data_ptr<float>(),
+                                exp_avg.data_ptr<float>(), exp_avg_sq.data_ptr<float>(), (float*)optptr(gshard), (int)mode,
+                                (float)beta1, (float)beta2, (float)eps, (float)weight_decay, decoupled ? 1 : 0,
+                                hyper.data_ptr<float>(), (double*)optptr(sq_out), f.data(), flag_offset,
+                                reinterpret_cast<unsigned int*>(epoch.data_ptr<int>()),
+                                reinterpret_cast<unsigned int*>(done.data_ptr<int>()), (int)max_blocks, stream()),
+        "rs_adamw_ag_bucket");
+}
+
+void clip_exchange(const std::vector<int64_t>& sqbufs, const std::vector<int64_t>& flags, int64_t flag_offset, int64_t rank,
+                   const Tensor& sq_local, Tensor& epoch, double max_norm, Tensor& hyper, const OptTensor& norm_out) {
+  TORCH_CHECK(sqbufs.size() == flags.size() && sq_local.scalar_type() == at::kDouble && epoch.scalar_type() == at::kInt);
+  std::vector<void*> s(sqbufs.size()), f(flags.size());
+  for (size_t i = 0; i < sqbufs.size(); ++i) { s[i] = reinterpret_cast<void*>(sqbufs[i]); f[i] = reinterpret_cast<void*>(flags[i]); }
+  c10::cuda::CUDAGuard guard(hyper.device());
+  check(b200_clip_exchange(s.data(), f.data(), flag_offset, (int)rank, (int)sqbufs.size(), sq_local.data_ptr<double>(),
+                           reinterpret_cast<unsigned int*>(epoch.data_ptr<int>()), (float)max_norm, hyper.data_ptr<float>(),
+                           (float*)optptr(norm_out), stream()),
+        "clip_exchange");
 }
 
 void lerp_(Tensor& tgt, const Tensor& src, double alpha) {
@@ -789,9 +846,90 @@ class PagedKVAllocator {
   std::unordered_map<int64_t, std::vector<int32_t>> seqs_;
 };
 
+
+// ---- decode megakernel (csrc/decode_mega.cu): per-layer pointer table + weight tensor maps, built once per engine ----
+// `layers`: list (one per block) of lists [ln1_w, ln1_b, ln2_w, ln2_b, qkv_w, qkv_b, out_w, out_b, fc_w, fc_b, fc2_w, fc2_b,
+// kcache, vcache]; biases / ln biases may be None.  Returns (pointer table, tensor maps) as uint8 CUDA tensors.
+std::vector<Tensor> decode_mega_build(const std::vector<std::vector<OptTensor>>& layers) {
+  const size_t L = layers.size();
+  TORCH_CHECK(L > 0, "no layers");
+  const int lb = b200_decode_mega_layer_bytes();
+  TORCH_CHECK(lb == 10 * (int)sizeof(void*), "DmLayer layout mismatch");
+  std::vector<const void*> table(L * 10, nullptr);
+  std::vector<uint8_t> maps(L * 4 * 128, 0);
+  at::Device dev(at::kCPU);
+  for (size_t l = 0; l < L; ++l) {
+    const auto& t = layers[l];
+    TORCH_CHECK(t.size() == 14, "each layer needs 14 entries");
+    auto ptr = [&](int i) -> const void* {
+      if (!t[i].has_value()) return nullptr;
+      CHECK_BF16(*t[i]);
+      TORCH_CHECK(t[i]->is_contiguous(), "megakernel tensors must be contiguous");
+      return t[i]->data_ptr();
+    };
+    const void* e[10] = {ptr(0), ptr(1), ptr(2), ptr(3), ptr(5), ptr(7), ptr(9), ptr(11), ptr(12), ptr(13)};
+    for (int i = 0; i < 10; ++i) table[l * 10 + i] = e[i];
+    const int widx[4] = {4, 6, 8, 10};
+    for (int g = 0; g < 4; ++g) {
+      TORCH_CHECK(t[widx[g]].has_value(), "weight missing");
+      const Tensor& w = *t[widx[g]];
+      CHECK_BF16(w);
+      TORCH_CHECK(w.dim() == 2 && w.stride(1) == 1, "weights must be row-major [out, in]");
+      dev = w.device();
+      check(b200_decode_mega_make_map(maps.data() + (l * 4 + g) * 128, w.data_ptr(), w.size(0), w.size(1), w.stride(0)),
+            "decode_mega_make_map");
+    }
+  }
+  c10::cuda::CUDAGuard guard(dev);
+  auto opts = torch::TensorOptions().dtype(torch::kUInt8);
+  Tensor table_t = torch::from_blob(table.data(), {(int64_t)(table.size() * sizeof(void*))}, opts).clone().to(dev);
+  // tensor maps must be 64-byte aligned: over-allocate and hand back an aligned view
+  Tensor raw = torch::empty({(int64_t)maps.size() + 128}, opts.device(dev));
+  const uintptr_t base = reinterpret_cast<uintptr_t>(raw.data_ptr());
+  const int64_t off = (int64_t)(((base + 127) & ~uintptr_t(127)) - base);
+  Tensor maps_t = raw.narrow(0, off, (int64_t)maps.size());
+  maps_t.copy_(torch::from_blob(maps.data(), {(int64_t)maps.size()}, opts));
+  return {table_t, maps_t};
+}
+
+void decode_mega(Tensor& x, Tensor& a, Tensor& mid, const Tensor& block_table, const Tensor& seq_lens, const Tensor& table,
+                 const Tensor& maps, int64_t nh, int64_t L, const std::string& act, bool rms, double eps, double scale,
+                 int64_t page_size, const OptTensor& trunk_out, const OptTensor& step, int64_t branch, const OptTensor& alibi,
+                 const OptTensor& timing) {
+  CHECK_BF16(x); CHECK_BF16(a); CHECK_BF16(mid);
+  TORCH_CHECK(x.is_contiguous() && a.is_contiguous() && mid.is_contiguous() && block_table.is_contiguous());
+  TORCH_CHECK(block_table.scalar_type() == at::kInt && seq_lens.scalar_type() == at::kInt);
+  c10::cuda::CUDAGuard guard(x.device());
+  const int B = (int)x.size(0), H = (int)x.size(1), F = (int)mid.size(1);
+  void* tr = nullptr;
+  long long tr_stride = 0;
+  const long long* step_ptr = nullptr;
+  if (trunk_out.has_value()) {
+    CHECK_BF16(*trunk_out);
+    TORCH_CHECK(trunk_out->dim() == 3 && trunk_out->size(2) == H && trunk_out->stride(2) == 1 && trunk_out->stride(1) == H);
+    tr = trunk_out->data_ptr();
+    tr_stride = trunk_out->stride(0);
+    TORCH_CHECK(step.has_value() && step->scalar_type() == at::kLong);
+    step_ptr = reinterpret_cast<const long long*>(step->data_ptr<int64_t>());
+  }
+  check(b200_decode_mega(B, H, F, (int)nh, (int)L, act_code(act), rms ? 1 : 0, (float)eps, (float)scale, (int)page_size,
+                         (int)block_table.size(1), block_table.data_ptr<int>(), seq_lens.data_ptr<int>(), x.data_ptr(),
+                         a.data_ptr(), mid.data_ptr(), table.data_ptr(), maps.data_ptr(), tr, tr_stride, step_ptr, (int)branch,
+                         (const float*)optptr(alibi),
+                         timing.has_value() ? reinterpret_cast<long long*>(timing->data_ptr<int64_t>()) : nullptr, stream()),
+        "decode_mega");
+}
+
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.def("decode_mega_build", &decode_mega_build);
+  m.def("decode_mega", &decode_mega, py::arg("x"), py::arg("a"), py::arg("mid"), py::arg("block_table"), py::arg("seq_lens"),
+        py::arg("table"), py::arg("maps"), py::arg("nh"), py::arg("L"), py::arg("act"), py::arg("rms"), py::arg("eps"),
+        py::arg("scale"), py::arg("page_size"), py::arg("trunk_out") = py::none(), py::arg("step") = py::none(),
+        py::arg("branch") = -1, py::arg("alibi") = py::none(), py::arg("timing") = py::none());
+  m.def("decode_mega_stages", [](int64_t H, int64_t F) { return b200_decode_mega_stages((int)H, (int)F); });
+  m.def("decode_mega_max_clusters", [](int64_t H, int64_t F) { return b200_decode_mega_max_clusters((int)H, (int)F); });
   namespace py = pybind11;
   m.doc() = "trlx_b200 sm_100a kernels";
   m.def("gemm", &gemm, py::arg("x"), py::arg("w"), py::arg("bias") = py::none(), py::arg("residual") = py::none(),
@@ -840,12 +978,14 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("ppo_loss", &ppo_loss, py::arg("logprobs"), py::arg("values"), py::arg("old_logprobs"), py::arg("old_values"),
         py::arg("adv"), py::arg("ret"), py::arg("mask"), py::arg("clip"), py::arg("clip_v"), py::arg("vf_coef"),
         py::arg("width_tensor") = py::none());
-  m.def("kl_rewards", &kl_rewards);
   m.def("adamw_flat", &adamw_flat);
   m.def("sqnorm_", &sqnorm_);
   m.def("clip_coef_", &clip_coef_, py::arg("sqsum"), py::arg("max_norm"), py::arg("hyper"), py::arg("norm_out") = py::none());
   m.def("signal_barrier", &signal_barrier);
   m.def("rs_adamw_ag", &rs_adamw_ag);
+  m.def("rs_adamw_ag_bucket", &rs_adamw_ag_bucket);
+  m.def("rollout_rewards", &rollout_rewards);
+  m.def("clip_exchange", &clip_exchange);
   m.def("lerp_", &lerp_);
   m.def("gemm_allgather", &gemm_allgather, py::arg("peers"), py::arg("rows_per_rank"), py::arg("K"), py::arg("lda"),
         py::arg("w"), py::arg("bias") = py::none(), py::arg("act") = "none", py::arg("out") = py::none());

@@ -99,6 +99,40 @@ __global__ void signal_barrier_kernel(PeerPtrs pads, int rank, int world, uint32
   __threadfence_system();
 }
 
+// Cross-rank readiness of ONE gradient bucket, folded into the reduce kernel itself (no separate barrier launch): block 0
+// tells every peer "my gradients of this bucket are final" (flag slot [rank] in the peer's flag buffer := epoch), every block
+// waits until all peers have said so.  The epoch lives on the device and is advanced by the last block to finish, so the
+// kernel can sit inside a replayed CUDA graph and be launched per bucket from autograd hooks while backward is still running.
+struct BucketSync {
+  void* flags[MAX_PEERS];   // peers' flag buffers, already offset to this bucket's row of `world` uint32 slots
+  uint32_t* epoch;          // local: last completed epoch of this bucket
+  uint32_t* done;           // local: blocks finished (wraps to 0)
+  int rank, enabled;
+};
+
+__device__ __forceinline__ uint32_t bucket_sync_begin(const BucketSync& sync, int world) {
+  if (!sync.enabled) return 0;
+  const uint32_t target = *sync.epoch + 1;
+  if (blockIdx.x == 0 && (int)threadIdx.x < world) {
+    __threadfence_system();
+    st_release_sys(reinterpret_cast<uint32_t*>(sync.flags[threadIdx.x]) + sync.rank, target);
+  }
+  if ((int)threadIdx.x < world) {
+    const uint32_t* mine = reinterpret_cast<const uint32_t*>(sync.flags[sync.rank]) + threadIdx.x;
+    while ((int32_t)(ld_acquire_sys(mine) - target) < 0) { __nanosleep(100); }
+  }
+  __syncthreads();
+  return target;
+}
+__device__ __forceinline__ void bucket_sync_end(const BucketSync& sync, uint32_t target) {
+  if (!sync.enabled) return;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicInc(sync.done, gridDim.x - 1) == gridDim.x - 1) *sync.epoch = target;
+  }
+}
+
 // Fused reduce-scatter + AdamW + all-gather over the owned shard [lo, lo + n).  8 bf16 (16 B) per thread-iteration.
 // lo and n must be multiples of 8.  If sq_out != null the squared norm of the averaged gradient is accumulated instead
 // of updating (phase 1 of clipped updates: the reduced gradient is parked in fp32 `gshard`).
@@ -106,7 +140,8 @@ template <bool UPDATE>
 __global__ void __launch_bounds__(256)
 rs_adamw_ag_kernel(PeerPtrs grads, PeerPtrs params, int world, long long lo, long long n, float* __restrict__ master,
                    float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq, float* __restrict__ gshard, int use_gshard,
-                   AdamArgs a, const float* __restrict__ hyper, double* __restrict__ sq_out) {
+                   AdamArgs a, const float* __restrict__ hyper, double* __restrict__ sq_out, BucketSync sync) {
+  const uint32_t sync_target = bucket_sync_begin(sync, world);
   const float lr = hyper[0], bc1 = hyper[1], bc2 = hyper[2], gs = hyper[3];
   const float inv_world = 1.f / (float)world;
   float sq = 0.f;
@@ -149,6 +184,37 @@ rs_adamw_ag_kernel(PeerPtrs grads, PeerPtrs params, int world, long long lo, lon
   if (!UPDATE && sq_out) {
     sq = warp_sum(sq);
     if ((threadIdx.x & 31) == 0) atomicAdd(sq_out, (double)sq);
+  }
+  bucket_sync_end(sync, sync_target);
+}
+
+// Global gradient norm for clipping without a library collective: every rank writes its partial sum of squares into slot
+// [parity][rank] of every peer's buffer (P2P store), a flag round publishes them, and each rank adds the `world` slots
+// (same order everywhere -> bit-identical coefficient on every rank).  One block of >= world threads.
+__global__ void clip_exchange_kernel(PeerPtrs sqbufs, PeerPtrs flags, int rank, int world, const double* __restrict__ sq_local,
+                                     uint32_t* __restrict__ epoch_ptr, float max_norm, float* __restrict__ hyper,
+                                     float* __restrict__ norm_out) {
+  const int t = threadIdx.x;
+  const uint32_t epoch = *epoch_ptr + 1;
+  const int parity = epoch & 1;
+  __syncthreads();
+  if (t < world) {
+    double* slot = reinterpret_cast<double*>(sqbufs.p[t]) + parity * world + rank;
+    *reinterpret_cast<volatile double*>(slot) = *sq_local;
+    __threadfence_system();
+    st_release_sys(reinterpret_cast<uint32_t*>(flags.p[t]) + rank, epoch);
+    const uint32_t* mine = reinterpret_cast<const uint32_t*>(flags.p[rank]) + t;
+    while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) { __nanosleep(64); }
+  }
+  __syncthreads();
+  if (t == 0) {
+    *epoch_ptr = epoch;
+    const volatile double* mine = reinterpret_cast<const volatile double*>(sqbufs.p[rank]) + parity * world;
+    double tot = 0.0;
+    for (int r = 0; r < world; ++r) tot += mine[r];
+    const float norm = (float)sqrt(tot);
+    if (norm_out) *norm_out = norm;
+    hyper[3] = fminf(1.f, max_norm / (norm + 1e-6f));
   }
 }
 
@@ -208,10 +274,51 @@ extern "C" int b200_rs_adamw_ag(void* const* grads, void* const* params, int wor
   for (int i = 0; i < world; ++i) { g.p[i] = grads[i]; p.p[i] = params[i]; }
   AdamArgs a{beta1, beta2, eps, weight_decay, decoupled};
   const int grid = grid_for(n, 8);
+  BucketSync sync{};
   if (mode == 1)
-    rs_adamw_ag_kernel<false><<<grid, 256, 0, stream>>>(g, p, world, lo, n, master, exp_avg, exp_avg_sq, gshard, 1, a, hyper, sq_out);
+    rs_adamw_ag_kernel<false><<<grid, 256, 0, stream>>>(g, p, world, lo, n, master, exp_avg, exp_avg_sq, gshard, 1, a, hyper, sq_out, sync);
   else
-    rs_adamw_ag_kernel<true><<<grid, 256, 0, stream>>>(g, p, world, lo, n, master, exp_avg, exp_avg_sq, gshard, mode == 2, a, hyper, nullptr);
+    rs_adamw_ag_kernel<true><<<grid, 256, 0, stream>>>(g, p, world, lo, n, master, exp_avg, exp_avg_sq, gshard, mode == 2, a, hyper, nullptr, sync);
+  return (int)cudaGetLastError();
+}
+
+// One gradient bucket: same modes as above, with the cross-rank "gradients final" handshake folded into the kernel.
+// flags[r] = rank r's flag buffer (uint32), flag_offset = first slot of this bucket's row; epoch / done: local counters.
+extern "C" int b200_rs_adamw_ag_bucket(void* const* grads, void* const* params, int world, int rank, long long lo, long long n,
+                                       float* master, float* exp_avg, float* exp_avg_sq, float* gshard, int mode, float beta1,
+                                       float beta2, float eps, float weight_decay, int decoupled, const float* hyper,
+                                       double* sq_out, void* const* flags, long long flag_offset, unsigned int* epoch,
+                                       unsigned int* done, int max_blocks, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  if (world > MAX_PEERS || (lo & 7) || (n & 7)) return -3;
+  PeerPtrs g{}, p{};
+  BucketSync sync{};
+  for (int i = 0; i < world; ++i) {
+    g.p[i] = grads[i];
+    p.p[i] = params[i];
+    sync.flags[i] = reinterpret_cast<uint32_t*>(flags[i]) + flag_offset;
+  }
+  sync.epoch = epoch; sync.done = done; sync.rank = rank; sync.enabled = mode != 2;  // phase 2 reads the parked gradient
+  AdamArgs a{beta1, beta2, eps, weight_decay, decoupled};
+  int grid = grid_for(n, 8);
+  if (max_blocks > 0 && grid > max_blocks) grid = max_blocks;
+  if (mode == 1)
+    rs_adamw_ag_kernel<false><<<grid, 256, 0, stream>>>(g, p, world, lo, n, master, exp_avg, exp_avg_sq, gshard, 1, a, hyper, sq_out, sync);
+  else
+    rs_adamw_ag_kernel<true><<<grid, 256, 0, stream>>>(g, p, world, lo, n, master, exp_avg, exp_avg_sq, gshard, mode == 2, a, hyper, nullptr, sync);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int b200_clip_exchange(void* const* sqbufs, void* const* flags, long long flag_offset, int rank, int world,
+                                  const double* sq_local, unsigned int* epoch, float max_norm, float* hyper, float* norm_out,
+                                  cudaStream_t stream) {
+  if (world > MAX_PEERS) return -3;
+  PeerPtrs s{}, f{};
+  for (int i = 0; i < world; ++i) {
+    s.p[i] = sqbufs[i];
+    f.p[i] = reinterpret_cast<uint32_t*>(flags[i]) + flag_offset;
+  }
+  clip_exchange_kernel<<<1, 32, 0, stream>>>(s, f, rank, world, sq_local, epoch, max_norm, hyper, norm_out);
   return (int)cudaGetLastError();
 }
 

@@ -3,7 +3,8 @@
 //   * gae + whiten        : reverse scan per row + global moments                  (trlx/models/modeling_ppo.py:161-173)
 //   * ppo_loss            : clipped policy / value losses, ~20 statistics and both gradients in one pass
 //                           (trlx/models/modeling_ppo.py:189-238 — every `.item()` there is a device sync)
-//   * kl_rewards          : per-token KL penalty, score placement, k3 KL statistics (accelerate_ppo_trainer.py:455-504)
+//   * rollout_rewards     : per-token KL penalty, score placement, window slicing, k3 KL statistics
+//                           (accelerate_ppo_trainer.py:455-504)
 #include "ptx.cuh"
 
 namespace b200 {
@@ -242,35 +243,62 @@ __global__ void ppo_grad_scale_kernel(float* __restrict__ dlogprobs, float* __re
   if (i < total) { dlogprobs[i] *= inv_n; dvalues[i] *= vf_coef * inv_n; }
 }
 
-// ----------------------------------------------------------------------------- KL-penalty rewards
-// rewards[b,t] = -kl_coef * (lp - ref_lp) on valid response tokens (+ score on the last valid token);
-// kl_stats (double[2]) += (sum over rows of sum_t k3(t), B)  where k3 = exp(d) - 1 - d, d = lp - ref_lp (masked).
-__global__ void kl_rewards_kernel(const float* __restrict__ lp, const float* __restrict__ ref_lp,
-                                  const int* __restrict__ resp_lens, const float* __restrict__ scores, int B, int R,
-                                  float kl_coef, float* __restrict__ rewards, double* __restrict__ kl_stats) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  double kl = 0.0;
-  if (b < B) {
-    const int n = resp_lens[b];
-    for (int t = 0; t < R; ++t) {
-      float r = 0.f;
-      if (t < n) {
-        const float d = lp[(size_t)b * R + t] - ref_lp[(size_t)b * R + t];
-        kl += (double)(__expf(d) - 1.f - d);
-        r = -kl_coef * d;
-        if (t == n - 1) r += scores[b];
-      }
-      rewards[(size_t)b * R + t] = r;
+// ----------------------------------------------------------------------------- rollout post-processing
+// Everything `make_experience` derives from a scored rollout, in one launch (reference: accelerate_ppo_trainer.py:455-504,
+// a Python loop over samples; previously ~12 aten launches here).  One block per row.
+//   lp / ref_lp / values : [B, T-1] over all positions;  mask : [B, T] (1 = real token);  start = Q - 1;  R = T - 1 - start
+//   slice_len[b] = min(sum(mask[b, start:]) + 1, R)          scored response positions (the reference includes the EOS step)
+//   rewards[b, c] = -kl_coef * (lp - ref_lp)[b, start + c] * mask   for c < slice_len, + score[b] at c = slice_len - 1
+//   lp_out / v_out = lp / values on the same window, zero past slice_len
+//   kl_sum        += sum over ALL positions of k3 = exp(d) - 1 - d,  d = (lp - ref_lp) * mask     (mean_kl statistics)
+__global__ void __launch_bounds__(128)
+rollout_rewards_kernel(const float* __restrict__ lp, const float* __restrict__ ref_lp, const float* __restrict__ values,
+                       const long long* __restrict__ mask, const float* __restrict__ scores, int Tm1, int start, float kl_coef,
+                       float* __restrict__ rewards, float* __restrict__ lp_out, float* __restrict__ v_out,
+                       int* __restrict__ slice_len, double* __restrict__ kl_sum) {
+  __shared__ float sh[4];
+  __shared__ int sh_len;
+  const int b = blockIdx.x, T = Tm1 + 1, R = Tm1 - start;
+  const long long* mrow = mask + (size_t)b * T;
+  float cnt = 0.f;
+  for (int t = start + threadIdx.x; t < T; t += blockDim.x) cnt += mrow[t] ? 1.f : 0.f;
+  cnt = block_sum(cnt, sh);
+  if (threadIdx.x == 0) {
+    sh_len = min((int)(cnt + 0.5f) + 1, R);
+    slice_len[b] = sh_len;
+  }
+  __syncthreads();
+  const int n = sh_len;
+  float kl = 0.f;
+  for (int t = threadIdx.x; t < Tm1; t += blockDim.x) {
+    const float d = mrow[t] ? lp[(size_t)b * Tm1 + t] - ref_lp[(size_t)b * Tm1 + t] : 0.f;
+    kl += __expf(d) - 1.f - d;
+    const int c = t - start;
+    if (c >= 0) {
+      const bool valid = c < n;
+      float r = valid ? -kl_coef * d : 0.f;
+      if (c == n - 1) r += scores[b];
+      rewards[(size_t)b * R + c] = r;
+      lp_out[(size_t)b * R + c] = valid ? lp[(size_t)b * Tm1 + t] : 0.f;
+      v_out[(size_t)b * R + c] = valid ? values[(size_t)b * Tm1 + t] : 0.f;
     }
   }
-  for (int o = 16; o > 0; o >>= 1) kl += __shfl_xor_sync(0xffffffffu, kl, o);
-  if ((threadIdx.x & 31) == 0) atomicAdd(&kl_stats[0], kl);
-  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&kl_stats[1], (double)B);
+  kl = block_sum(kl, sh);
+  if (threadIdx.x == 0) atomicAdd(kl_sum, (double)kl);
 }
 
 }  // namespace b200
 
 using namespace b200;
+
+extern "C" int b200_rollout_rewards(const float* lp, const float* ref_lp, const float* values, const long long* mask,
+                                    const float* scores, int B, int Tm1, int start, float kl_coef, float* rewards,
+                                    float* lp_out, float* v_out, int* slice_len, double* kl_sum, cudaStream_t stream) {
+  if (B <= 0 || Tm1 - start <= 0) return 0;
+  rollout_rewards_kernel<<<B, 128, 0, stream>>>(lp, ref_lp, values, mask, scores, Tm1, start, kl_coef, rewards, lp_out, v_out,
+                                                slice_len, kl_sum);
+  return (int)cudaGetLastError();
+}
 
 // dtype: 0 = fp32, 1 = bf16, 2 = fp16
 extern "C" int b200_logprob_from_logits(const void* logits, const long long* labels, float* out, float* lse, long long rows,
@@ -325,9 +353,3 @@ extern "C" int b200_ppo_loss(const float* logprobs, const float* values, const f
   return (int)cudaGetLastError();
 }
 
-extern "C" int b200_kl_rewards(const float* lp, const float* ref_lp, const int* resp_lens, const float* scores, int B, int R,
-                               float kl_coef, float* rewards, double* kl_stats, cudaStream_t stream) {
-  if (B <= 0) return 0;
-  kl_rewards_kernel<<<(B + 63) / 64, 64, 0, stream>>>(lp, ref_lp, resp_lens, scores, B, R, kl_coef, rewards, kl_stats);
-  return (int)cudaGetLastError();
-}

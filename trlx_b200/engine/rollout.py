@@ -190,6 +190,58 @@ class RolloutEngine:
                                   and not self.defer_ref)
         self.side = torch.cuda.Stream(device=self.device) if self.parallel_branches else None
         ops.C.set_pdl(os.environ.get("TRLX_B200_PDL", "1") == "1")
+        # Persistent decode megakernel (csrc/decode_mega.cu): the whole policy layer stack of a decode step in ONE launch —
+        # 16-CTA clusters own 16 batch rows each and walk all blocks with cluster barriers between phases.
+        self.mega = self._mega_eligible() and os.environ.get("TRLX_B200_DECODE_MEGA", "1") == "1"
+        self._mega_tables = None
+
+    # ------------------------------------------------------------------------------------------------ megakernel
+    def _mega_eligible(self) -> bool:
+        spec = self.spec
+        if not hasattr(ops.C, "decode_mega") or self.fp8 or self.fold_norms or not self.defer_ref:
+            return False
+        if spec.head_dim != 64 or spec.num_kv_heads != spec.num_heads or spec.hidden_size != spec.num_heads * 64:
+            return False
+        if spec.hidden_size % 64 or spec.ffn_size % 64 or spec.parallel_residual or spec.gated_mlp:
+            return False
+        if spec.pos not in ("learned", "none", "alibi") or spec.local_layers or self.lm.transformer.emb_norm is not None:
+            return False
+        if any(W.n2w is None for W in self.layers):
+            return False
+        try:
+            return int(ops.C.decode_mega_stages(spec.hidden_size, spec.ffn_size)) >= 4
+        except Exception:
+            return False
+
+    def _mega_build(self, st):
+        """Pointer table + weight tensor maps of the policy stack for this state's KV caches (addresses are stable: the
+        parameters are views of the optimizer's flat buffer, the caches live as long as the state)."""
+        rows = []
+        for i, W in enumerate(self.layers):
+            rows.append([W.n1w, W.n1b, W.n2w, W.n2b, W.qkv_w, W.qkv_b, W.out_w, W.out_b, W.up_w, W.up_b, W.down_w, W.down_b,
+                         st["kc"][i], st["vc"][i]])
+        table, maps = ops.C.decode_mega_build(rows)
+        B, spec = st["B"], self.spec
+        import os
+
+        timing = (torch.zeros(16 * len(self.layers) * 16, dtype=torch.int64, device=self.device)
+                  if os.environ.get("TRLX_B200_MEGA_TIMING") == "1" else None)  # clock64 stamps of cluster 0 (profiling aid)
+        st["mega"] = dict(table=table, maps=maps, timing=timing,
+                          a=torch.empty(B, spec.hidden_size, dtype=torch.bfloat16, device=self.device),
+                          mid=torch.empty(B, spec.ffn_size, dtype=torch.bfloat16, device=self.device))
+
+    def _mega_stack(self, x, st):
+        """All policy blocks on ``x`` (in place) + the trunk capture; returns ``x``."""
+        spec = self.spec
+        if "mega" not in st:
+            self._mega_build(st)
+        m = st["mega"]
+        want_trunk = (self.cache_trunk or self.defer_ref) and st["trunk_decode"] is not None
+        ops.C.decode_mega(x, m["a"], m["mid"], st["block_table"], st["seq_lens"], m["table"], m["maps"], spec.num_heads,
+                          len(self.layers), spec.activation, spec.norm == "rmsnorm", spec.norm_eps, self.scale, PAGE,
+                          st["trunk_decode"] if want_trunk else None, st["step64"] if want_trunk else None,
+                          self.branch if want_trunk else -1, self.alibi, m["timing"])
+        return x
 
     # ------------------------------------------------------------------------------------------------ folded weights
     def mark_dirty(self):
@@ -348,7 +400,10 @@ class RolloutEngine:
         main = torch.cuda.current_stream()
         rf = None
         trunk_xs = xs
-        for i, W in enumerate(self.layers):
+        mega = self.mega and not fold
+        if mega:
+            x = self._mega_stack(x, st)
+        for i, W in enumerate(() if mega else self.layers):
             if i == self.branch:
                 trunk_x = x
                 if self.parallel_branches:
@@ -371,7 +426,7 @@ class RolloutEngine:
                 x, xs = self._layer_folded(x, xs, W, self.folded[i], st["kc"][i], st["vc"][i], st)
             else:
                 x = self._layer(x, W, st["kc"][i], st["vc"][i], st)
-        if (self.cache_trunk or self.defer_ref) and not self.parallel_branches:
+        if (self.cache_trunk or self.defer_ref) and not self.parallel_branches and not mega:
             st["trunk_decode"].index_copy_(1, st["step64"], trunk_x.unsqueeze(1))
         hf = C.norm(x, tr.ln_f.weight, tr.ln_f.bias, spec.norm_eps, rms)
         _, _, tok, tlp = C.lmhead(hf, lm.lm_head.weight, lm.lm_head.bias, None, True, self.temperature, self.seed,

@@ -88,19 +88,22 @@ def ppo_loss(logprobs, values, old_logprobs, old_values, advantages, returns, ma
     return loss, stats
 
 
-def kl_rewards(logprobs, ref_logprobs, resp_lens, scores, kl_coef: float):
-    """Per-token ``-β·(lp − ref_lp)`` with the scalar score added on the last response token, and the summed
-    k3 KL estimate per row (``trlx/trainer/accelerate_ppo_trainer.py:455-504``)."""
-    B, R = logprobs.shape
-    t = torch.arange(R, device=logprobs.device).unsqueeze(0)
-    valid = t < resp_lens.unsqueeze(1)
-    d = (logprobs - ref_logprobs) * valid
-    kl = (torch.exp(d) - 1 - d) * valid
-    rewards = -kl_coef * d
-    last = (resp_lens - 1).clamp_min(0).long()
-    has = resp_lens > 0
-    rewards[torch.arange(B, device=logprobs.device)[has], last[has]] += scores[has]
-    return rewards, kl.sum(1)
+def rollout_rewards(logprobs, ref_logprobs, values, mask, scores, start: int, kl_coef: float):
+    """What ``make_experience`` derives from a scored rollout (``trlx/trainer/accelerate_ppo_trainer.py:455-504``):
+    ``(rewards, logprobs, values)`` on the response window ``[start, T-1)`` zeroed past ``slice_len``, ``slice_len`` and the
+    summed k3 KL estimate over all positions.  ``scores``: one scalar per row, added on the last scored token."""
+    R = logprobs.shape[1] - start
+    log_ratio = (logprobs - ref_logprobs) * mask[:, :-1]
+    kl = log_ratio.exp() - 1 - log_ratio
+    slice_len = (mask[:, start:].sum(1) + 1).clamp(max=R)
+    cols = torch.arange(R, device=logprobs.device).unsqueeze(0)
+    valid = cols < slice_len.unsqueeze(1)
+    zero = torch.zeros_like(logprobs[:, start:])
+    lp_s = torch.where(valid, logprobs[:, start:], zero)
+    v_s = torch.where(valid, values[:, start:], zero)
+    rewards = torch.where(valid, -kl_coef * log_ratio[:, start:], zero)
+    rewards.scatter_add_(1, (slice_len - 1).clamp_min(0).unsqueeze(1), scores.reshape(-1, 1).to(rewards.dtype))
+    return rewards, lp_s, v_s, slice_len, kl.sum()
 
 
 def adamw_step(w, g, m, v, step: int, lr, beta1, beta2, eps, weight_decay, decoupled=True):

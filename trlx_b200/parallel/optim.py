@@ -35,31 +35,62 @@ def _round_up(n: int, m: int) -> int:
 
 
 class _FlatGroup:
-    """Flat storage for one param group."""
+    """Flat storage for one param group, cut into gradient BUCKETS.
 
-    def __init__(self, params: List[torch.nn.Parameter], world: int, rank: int, group, symmetric: bool):
+    A bucket is a contiguous run of parameters (in ``model.parameters()`` order, ≈ ``bucket_elems`` elements) padded to a
+    multiple of ``8 * world``; every rank owns the ``1 / world`` slice ``[lo + rank * shard, lo + (rank + 1) * shard)`` of
+    every bucket and keeps fp32 master weights + Adam moments only for those slices (concatenated, bucket after bucket).
+    Backward completes buckets last-to-first, so the reduce-scatter + update + all-gather of a finished bucket runs on a side
+    stream while the rest of the backward is still computing (the per-layer buckets + overlap hooks of the reference's
+    distributed optimizer, ``trlx/models/modeling_nemo_ppo.py:586-609,689-701``, and DDP's bucketed reducer)."""
+
+    def __init__(self, params: List[torch.nn.Parameter], world: int, rank: int, group, symmetric: bool,
+                 bucket_elems: int = 8 << 20):
         self.params = params
         self.device = params[0].device
-        sizes = [p.numel() for p in params]
-        self.offsets, off = [], 0
-        for n in sizes:
-            self.offsets.append(off)
-            off += _round_up(n, _ALIGN)
-        self.numel = _round_up(off, _ALIGN * max(world, 1))
         self.world, self.rank, self.group = world, rank, group
-        self.shard = self.numel // max(world, 1)
-        self.lo = self.shard * rank
-        self.symm_param = self.symm_grad = None
+        unit = _ALIGN * max(world, 1)
+        self.offsets: List[int] = []
+        self.buckets: List[Dict[str, Any]] = []
+        off = start = 0
+        members: List[int] = []
+        for i, p in enumerate(params):
+            self.offsets.append(off)
+            off += _round_up(p.numel(), _ALIGN)
+            members.append(i)
+            if off - start >= bucket_elems or i == len(params) - 1:
+                off = start + _round_up(off - start, unit)
+                self.buckets.append(dict(lo=start, hi=off, params=members))
+                start, members = off, []
+        self.numel = off
+        moff = 0
+        for b in self.buckets:
+            b["shard"] = (b["hi"] - b["lo"]) // max(world, 1)
+            b["mine"] = b["lo"] + b["shard"] * rank
+            b["moff"] = moff
+            moff += b["shard"]
+        self.shard = moff  # elements of optimizer state this rank holds
+        self.bucket_of = {}
+        for k, b in enumerate(self.buckets):
+            for i in b["params"]:
+                self.bucket_of[i] = k
+        self.symm_param = self.symm_grad = self.symm_flags = self.symm_sq = None
+        nb = len(self.buckets)
         if symmetric:
             import torch.distributed._symmetric_memory as symm
 
             self.flat_param = symm.empty(self.numel, dtype=torch.bfloat16, device=self.device)
             self.flat_grad = symm.empty(self.numel, dtype=torch.bfloat16, device=self.device)
-            self.flat_param.zero_()
-            self.flat_grad.zero_()
+            # rows 0..nb-1: "bucket gradients final" flags, row nb: end-of-step barrier, row nb+1: clip-norm exchange
+            self.flags = symm.empty((nb + 2) * world, dtype=torch.int32, device=self.device)
+            self.sqbuf = symm.empty(2 * world, dtype=torch.float64, device=self.device)
+            for t in (self.flat_param, self.flat_grad, self.flags, self.sqbuf):
+                t.zero_()
             name = group.group_name if group is not None else dist.group.WORLD.group_name
             self.symm_param = symm.rendezvous(self.flat_param, name)
             self.symm_grad = symm.rendezvous(self.flat_grad, name)
+            self.symm_flags = symm.rendezvous(self.flags, name)
+            self.symm_sq = symm.rendezvous(self.sqbuf, name)
         else:
             self.flat_param = torch.zeros(self.numel, dtype=torch.bfloat16, device=self.device)
             self.flat_grad = torch.zeros(self.numel, dtype=torch.bfloat16, device=self.device)
@@ -68,16 +99,26 @@ class _FlatGroup:
             self.flat_param[o:o + n].copy_(p.data.reshape(-1))
             p.data = self.flat_param[o:o + n].view(p.shape)
             p.grad = self.flat_grad[o:o + n].view(p.shape)
-        sl = slice(self.lo, self.lo + self.shard)
-        self.master = self.flat_param[sl].float()
+        self.master = torch.empty(self.shard, dtype=torch.float32, device=self.device)
+        self.resync_master()
         self.exp_avg = torch.zeros(self.shard, dtype=torch.float32, device=self.device)
         self.exp_avg_sq = torch.zeros(self.shard, dtype=torch.float32, device=self.device)
         self.gshard: Optional[torch.Tensor] = None
         self.hyper = torch.ones(4, dtype=torch.float32, device=self.device)
         self.hyper_host = torch.ones(4, dtype=torch.float32).pin_memory() if self.device.type == "cuda" else torch.ones(4)
         self.sq = torch.zeros(1, dtype=torch.float64, device=self.device)
-        self.epoch = torch.zeros(1, dtype=torch.int32, device=self.device)  # device-side barrier epoch
+        self.epochs = torch.zeros(nb + 2, dtype=torch.int32, device=self.device)  # device-side epochs (buckets, barrier, clip)
+        self.done = torch.zeros(nb + 1, dtype=torch.int32, device=self.device)    # per-bucket finished-block counters
         self.norm = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self.pending = [0] * nb       # overlap: parameters of the bucket still waiting for their gradient
+        self.launched = [False] * nb
+
+    def resync_master(self):
+        for b in self.buckets:
+            self.master[b["moff"]:b["moff"] + b["shard"]].copy_(self.flat_param[b["mine"]:b["mine"] + b["shard"]].float())
+
+    def layout(self):
+        return [(b["lo"], b["hi"]) for b in self.buckets]
 
     def rebind_grads(self):
         """(Re)attach ``.grad`` views — needed after anything set them to ``None``."""
@@ -87,12 +128,22 @@ class _FlatGroup:
 
 
 class FusedAdamW(Optimizer):
-    """AdamW (``decoupled=True``) with flat bf16 storage + fp32 master shard and a fused (optionally cross-GPU) update."""
+    """AdamW (``decoupled=True``) with flat bf16 storage + fp32 master shard and a fused (optionally cross-GPU) update.
+
+    Data-parallel runs (``zero_stage >= 1``): gradients are reduced, the owned shard updated and the new parameters
+    written to every peer by ONE kernel per gradient bucket over NVLink peer memory; the cross-rank "gradients of this
+    bucket are final" handshake is folded into that kernel.  With ``overlap`` (default) the bucket kernels are launched from
+    post-accumulate-grad hooks on a side stream, so all but the first layers' traffic hides behind the backward pass.
+    Parameters that receive no gradient in a step are updated with a zero gradient (moment / weight decay still apply) —
+    unlike ``torch.optim.AdamW``, which skips them; freeze what must not move."""
 
     decoupled = True
 
     def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2,
-                 grad_clip: Optional[float] = None, process_group=None, zero_stage: int = 2, **unused):
+                 grad_clip: Optional[float] = None, process_group=None, zero_stage: int = 2, overlap: Optional[bool] = None,
+                 bucket_mb: Optional[float] = None, **unused):
+        import os
+
         defaults = dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay)
         super().__init__(params, defaults)
         self.grad_clip = grad_clip
@@ -100,9 +151,16 @@ class FusedAdamW(Optimizer):
         # zero_stage == 0: DDP semantics — NCCL all-reduce of the flat gradient, replicated update
         self.zero_stage = int(zero_stage)
         self.process_group = process_group
+        self.overlap = (os.environ.get("TRLX_B200_OVERLAP_GRAD", "1") == "1") if overlap is None else bool(overlap)
+        mb = float(os.environ.get("TRLX_B200_BUCKET_MB", bucket_mb if bucket_mb is not None else 16))
+        self.bucket_elems = max(int(mb * (1 << 20) / 2), 1024)
+        self.overlap_blocks = int(os.environ.get("TRLX_B200_OVERLAP_BLOCKS", "32"))  # CTAs per overlapped bucket kernel
         self._step_count_fused = 0
         self._flat: Optional[List[Optional[_FlatGroup]]] = None
         self._fallback: Optional[Optimizer] = None
+        self._armed = False
+        self._side: Optional[torch.cuda.Stream] = None
+        self._hooks: List[Any] = []
         self.last_grad_norm: Optional[torch.Tensor] = None
 
     # -- setup ------------------------------------------------------------------------------------------------------------
@@ -137,22 +195,85 @@ class FusedAdamW(Optimizer):
                 continue
             symmetric = world > 1 and self.zero_stage >= 1
             if world > 1 and not symmetric:
-                self._flat.append(_FlatGroup(ps, 1, 0, None, False))
+                self._flat.append(_FlatGroup(ps, 1, 0, None, False, 1 << 62))
                 self._flat[-1].needs_allreduce = True
                 continue
             try:
-                self._flat.append(_FlatGroup(ps, world, rank, self.process_group, symmetric))
+                self._flat.append(_FlatGroup(ps, world, rank, self.process_group, symmetric,
+                                             self.bucket_elems if symmetric else 1 << 62))
             except Exception as err:  # symmetric memory unavailable → replicated update after an NCCL all-reduce
                 if not symmetric:
                     raise
                 logger.warning(f"symmetric memory unavailable ({err}); falling back to all-reduce + replicated update")
-                self._flat.append(_FlatGroup(ps, 1, 0, None, False))
+                self._flat.append(_FlatGroup(ps, 1, 0, None, False, 1 << 62))
                 self._flat[-1].needs_allreduce = True
+        if self.overlap and not self.grad_clip and any(fg is not None and fg.world > 1 for fg in self._flat):
+            self._side = torch.cuda.Stream(device=next(fg for fg in self._flat if fg is not None).device)
+            for gi, fg in enumerate(self._flat):
+                if fg is None or fg.world == 1:
+                    continue
+                for pi, p in enumerate(fg.params):
+                    self._hooks.append(p.register_post_accumulate_grad_hook(
+                        lambda _p, gi=gi, pi=pi: self._on_grad(gi, pi)))
 
     def prepare(self):
         """Flatten storage now (call once after the model is on its device, before the first backward)."""
         self._lazy_init()
         return self
+
+    # -- overlap ------------------------------------------------------------------------------------------------------------
+    @property
+    def can_overlap(self) -> bool:
+        self._lazy_init()
+        return self._side is not None
+
+    def arm_overlap(self):
+        """Call right before the backward whose gradients complete an optimizer step (the last micro-batch), after
+        :meth:`host_prepare`: from then on every bucket whose gradients are final is reduced / updated / gathered on a side
+        stream while the rest of the backward runs.  :meth:`device_step` joins."""
+        if not self.can_overlap:
+            return
+        for fg in self._flat:
+            if fg is None or fg.world == 1:
+                continue
+            fg.hyper.copy_(fg.hyper_host, non_blocking=True)
+            for k, b in enumerate(fg.buckets):
+                fg.pending[k] = len(b["params"])
+                fg.launched[k] = False
+        self._armed = True
+
+    def _on_grad(self, gi: int, pi: int):
+        if not self._armed:
+            return
+        fg = self._flat[gi]
+        k = fg.bucket_of[pi]
+        fg.pending[k] -= 1
+        if fg.pending[k] == 0 and not fg.launched[k]:
+            self._side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._side):
+                self._bucket_kernel(self.param_groups[gi], fg, k, 0, self.overlap_blocks)
+            fg.launched[k] = True
+
+    def _bucket_kernel(self, g, fg: _FlatGroup, k: int, mode: int, max_blocks: int = 0):
+        from trlx_b200 import ops
+
+        b = fg.buckets[k]
+        b1, b2 = g["betas"]
+        sl = slice(b["moff"], b["moff"] + b["shard"])
+        gsh = fg.gshard[sl] if (mode != 0 and fg.gshard is not None) else None
+        ops.C.rs_adamw_ag_bucket(list(fg.symm_grad.buffer_ptrs), list(fg.symm_param.buffer_ptrs), fg.rank, b["mine"],
+                                 b["shard"], fg.master[sl], fg.exp_avg[sl], fg.exp_avg_sq[sl], gsh, mode, b1, b2, g["eps"],
+                                 g["weight_decay"], self.decoupled, fg.hyper, fg.sq if mode == 1 else None,
+                                 list(fg.symm_flags.buffer_ptrs), k * fg.world, fg.epochs[k:k + 1], fg.done[k:k + 1],
+                                 max_blocks)
+
+    def _end_barrier(self, fg: _FlatGroup):
+        """Every rank's new parameters are visible everywhere (and nobody still reads this rank's gradients)."""
+        from trlx_b200 import ops
+
+        nb = len(fg.buckets)
+        pads = [int(p) + nb * fg.world * 4 for p in fg.symm_flags.buffer_ptrs]
+        ops.C.signal_barrier(pads, fg.rank, fg.epochs[nb:nb + 1])
 
     # -- step -------------------------------------------------------------------------------------------------------------
     def zero_grad(self, set_to_none: bool = False):
@@ -193,7 +314,8 @@ class FusedAdamW(Optimizer):
             self._fallback.step()
             return loss
 
-        self.host_prepare()
+        if not self._armed:
+            self.host_prepare()
         self.device_step()
         return loss
 
@@ -218,13 +340,14 @@ class FusedAdamW(Optimizer):
 
         C = ops.C
         world, rank = self._world()
+        armed, self._armed = self._armed, False
         for g, fg in zip(self.param_groups, self._flat):
             if fg is None:
                 continue
             b1, b2 = g["betas"]
-            fg.hyper.copy_(fg.hyper_host, non_blocking=True)
             args = (b1, b2, g["eps"], g["weight_decay"], self.decoupled)
             if fg.world == 1:
+                fg.hyper.copy_(fg.hyper_host, non_blocking=True)
                 if getattr(fg, "needs_allreduce", False) and world > 1:
                     dist.all_reduce(fg.flat_grad, group=self.process_group)
                     fg.flat_grad.div_(world)
@@ -235,25 +358,34 @@ class FusedAdamW(Optimizer):
                     self.last_grad_norm = fg.norm
                 C.adamw_flat(fg.flat_param, fg.master, fg.flat_grad, fg.exp_avg, fg.exp_avg_sq, *args, fg.hyper)
                 continue
-            # ---- data-parallel: fused reduce-scatter + AdamW + all-gather over NVLink peer memory
-            pads = list(fg.symm_grad.signal_pad_ptrs)
-            grads, params = list(fg.symm_grad.buffer_ptrs), list(fg.symm_param.buffer_ptrs)
-            C.signal_barrier(pads, fg.rank, fg.epoch)  # every rank finished accumulating gradients
-            if self.grad_clip:
+            # ---- data-parallel: fused reduce-scatter + AdamW + all-gather over NVLink peer memory, bucket by bucket
+            nb = len(fg.buckets)
+            if armed and self._side is not None:
+                main = torch.cuda.current_stream()
+                late = [k for k in range(nb) if not fg.launched[k]]  # buckets holding parameters that got no gradient
+                if late:
+                    self._side.wait_stream(main)
+                    with torch.cuda.stream(self._side):
+                        for k in reversed(late):
+                            self._bucket_kernel(g, fg, k, 0)
+                main.wait_stream(self._side)
+            elif self.grad_clip:
+                fg.hyper.copy_(fg.hyper_host, non_blocking=True)
                 if fg.gshard is None:
                     fg.gshard = torch.empty(fg.shard, dtype=torch.float32, device=fg.device)
                 fg.sq.zero_()
-                C.rs_adamw_ag(grads, params, fg.lo, fg.shard, fg.master, fg.exp_avg, fg.exp_avg_sq, fg.gshard, 1, *args,
-                              fg.hyper, fg.sq)
-                dist.all_reduce(fg.sq, group=self.process_group)
-                C.clip_coef_(fg.sq, float(self.grad_clip), fg.hyper, fg.norm)
+                for k in reversed(range(nb)):
+                    self._bucket_kernel(g, fg, k, 1)           # reduce into the parked fp32 shard + Σg² partial
+                C.clip_exchange(list(fg.symm_sq.buffer_ptrs), list(fg.symm_flags.buffer_ptrs), (nb + 1) * fg.world, fg.rank,
+                                fg.sq, fg.epochs[nb + 1:nb + 2], float(self.grad_clip), fg.hyper, fg.norm)
                 self.last_grad_norm = fg.norm
-                C.rs_adamw_ag(grads, params, fg.lo, fg.shard, fg.master, fg.exp_avg, fg.exp_avg_sq, fg.gshard, 2, *args,
-                              fg.hyper, None)
+                for k in reversed(range(nb)):
+                    self._bucket_kernel(g, fg, k, 2)           # clipped update + all-gather
             else:
-                C.rs_adamw_ag(grads, params, fg.lo, fg.shard, fg.master, fg.exp_avg, fg.exp_avg_sq, None, 0, *args,
-                              fg.hyper, None)
-            C.signal_barrier(pads, fg.rank, fg.epoch)  # every rank's new parameters are visible everywhere
+                fg.hyper.copy_(fg.hyper_host, non_blocking=True)
+                for k in reversed(range(nb)):
+                    self._bucket_kernel(g, fg, k, 0)
+            self._end_barrier(fg)
 
     @property
     def graph_capturable(self) -> bool:
@@ -288,7 +420,7 @@ class FusedAdamW(Optimizer):
         for fg in self._flat or []:
             if fg is None:
                 continue
-            fg.master.copy_(fg.flat_param[fg.lo:fg.lo + fg.shard].float())
+            fg.resync_master()
             if reset_moments:
                 fg.exp_avg.zero_()
                 fg.exp_avg_sq.zero_()
@@ -303,7 +435,8 @@ class FusedAdamW(Optimizer):
         shards = []
         for fg in self._flat:
             shards.append(None if fg is None else dict(master=fg.master.cpu(), exp_avg=fg.exp_avg.cpu(),
-                                                       exp_avg_sq=fg.exp_avg_sq.cpu(), lo=fg.lo, shard=fg.shard))
+                                                       exp_avg_sq=fg.exp_avg_sq.cpu(), layout=fg.layout(), rank=fg.rank,
+                                                       world=fg.world))
         return {"kind": "flat", "step": self._step_count_fused, "shards": shards,
                 "lrs": [g["lr"] for g in self.param_groups]}
 
@@ -322,8 +455,9 @@ class FusedAdamW(Optimizer):
         for fg, sh in zip(self._flat, sd["shards"]):
             if fg is None or sh is None:
                 continue
-            if sh["lo"] != fg.lo or sh["shard"] != fg.shard:
-                raise ValueError("optimizer shard layout changed (different world size?)")
+            if (sh.get("layout") != fg.layout() or sh.get("rank") != fg.rank or sh.get("world") != fg.world
+                    or sh["master"].numel() != fg.shard):
+                raise ValueError("optimizer shard layout changed (different world size or bucket size?)")
             fg.master.copy_(sh["master"])
             fg.exp_avg.copy_(sh["exp_avg"])
             fg.exp_avg_sq.copy_(sh["exp_avg_sq"])

@@ -520,11 +520,13 @@ class AccelerateRLTrainer(BaseRLTrainer):
         times: Dict[str, float] = {}
         stats_accum = []
         fwd = bwd = 0.0
-        for microbatch in minibatch:
+        for mb_index, microbatch in enumerate(minibatch):
             with self._accumulate():
                 with self.runtime.phase("forward", times):
                     loss, stats = self.loss(microbatch)
                 fwd += times["forward"]
+                if mb_index == len(minibatch) - 1:
+                    self._arm_grad_overlap()
                 with self.runtime.phase("backward", times):
                     self.model.train()
                     loss.backward()
@@ -542,6 +544,15 @@ class AccelerateRLTrainer(BaseRLTrainer):
         stats["time/forward"] = fwd / self.num_mb
         stats["time/backward"] = bwd / self.num_mb
         return stats
+
+    def _arm_grad_overlap(self):
+        """Before the backward that completes an optimizer step: let the fused data-parallel optimizer reduce / update /
+        gather every gradient bucket as soon as it is final, on a side stream, while the rest of the backward runs.  Not
+        with model parallelism: its gradient fix-ups (``_pre_optimizer_step``) run after the backward."""
+        rt = self.runtime
+        if getattr(self.opt, "can_overlap", False) and rt.tp_size == 1 and rt.pp_size == 1:
+            self.opt.host_prepare()
+            self.opt.arm_overlap()
 
     _LOSS_KEYS = ("loss", "losses/loss", "losses/total_loss")
 

@@ -490,27 +490,36 @@ class AcceleratePPOTrainer(AccelerateRLTrainer):
             elif method.scale_reward == "ref":
                 scores = scores / self.ref_std
 
-            # ---- vectorised version of the reference's per-sample slicing (``:455-504``)
+            # ---- the reference's per-sample slicing (``:455-504``): KL-penalty rewards, score placement, k3 statistics
             logprobs, ref_logprobs, values, mask, start = ro["logprobs"], ro["ref_logprobs"], ro["values"], ro["mask"], ro["start"]
-            log_ratio = (logprobs - ref_logprobs) * mask[:, :-1]
-            kl = log_ratio.exp() - 1 - log_ratio
-            mean_kl_per_token = kl.mean()
-            mean_kl = kl.sum(1).mean()
-
             R = logprobs.shape[1] - start
-            slice_len = (mask[:, start:].sum(1) + 1).clamp(max=R)
-            cols = torch.arange(R, device=device).unsqueeze(0)
-            valid = cols < slice_len.unsqueeze(1)
-            lp_s = torch.where(valid, logprobs[:, start:], torch.zeros_like(logprobs[:, start:]))
-            v_s = torch.where(valid, values[:, start:], torch.zeros_like(values[:, start:]))
-            rewards = torch.where(valid, -self.kl_ctl.value * log_ratio[:, start:], torch.zeros_like(lp_s))
-            if scores.shape[1] == 1:
-                rewards.scatter_add_(1, (slice_len - 1).clamp_min(0).unsqueeze(1), scores[:, :1].to(rewards.dtype))
+            fused = (rt.cuda and scores.shape[1] == 1 and ops.enabled_for(logprobs) and hasattr(ops.C, "rollout_rewards")
+                     and logprobs.dtype == torch.float32)
+            if fused:  # one launch (csrc/rl_ops.cu: rollout_rewards_kernel)
+                rewards, lp_s, v_s, slice_len, kl_sum = ops.C.rollout_rewards(
+                    logprobs.contiguous(), ref_logprobs.float().contiguous(), values.float().contiguous(), mask.contiguous(),
+                    scores[:, 0].float().contiguous(), start, float(self.kl_ctl.value))
+                slice_len = slice_len.long()
+                mean_kl = (kl_sum[0] / logprobs.shape[0]).float()
+                mean_kl_per_token = (kl_sum[0] / logprobs.numel()).float()
             else:
-                k = min(scores.shape[1], R)
-                dense = torch.zeros_like(rewards)
-                dense[:, :k] = (scores * scores_mask)[:, :k]
-                rewards = rewards + torch.where(valid, dense, torch.zeros_like(dense))
+                log_ratio = (logprobs - ref_logprobs) * mask[:, :-1]
+                kl = log_ratio.exp() - 1 - log_ratio
+                mean_kl_per_token = kl.mean()
+                mean_kl = kl.sum(1).mean()
+                slice_len = (mask[:, start:].sum(1) + 1).clamp(max=R)
+                cols = torch.arange(R, device=device).unsqueeze(0)
+                valid = cols < slice_len.unsqueeze(1)
+                lp_s = torch.where(valid, logprobs[:, start:], torch.zeros_like(logprobs[:, start:]))
+                v_s = torch.where(valid, values[:, start:], torch.zeros_like(values[:, start:]))
+                rewards = torch.where(valid, -self.kl_ctl.value * log_ratio[:, start:], torch.zeros_like(lp_s))
+                if scores.shape[1] == 1:
+                    rewards.scatter_add_(1, (slice_len - 1).clamp_min(0).unsqueeze(1), scores[:, :1].to(rewards.dtype))
+                else:
+                    k = min(scores.shape[1], R)
+                    dense = torch.zeros_like(rewards)
+                    dense[:, :k] = (scores * scores_mask)[:, :k]
+                    rewards = rewards + torch.where(valid, dense, torch.zeros_like(dense))
 
             q_lens = prompt_tensors.ne(pad).sum(1)
             block = RolloutBlock(queries=prompt_tensors, responses=sample_outputs, logprobs=lp_s, values=v_s, rewards=rewards,

@@ -59,6 +59,9 @@ class GraphedPPOStep:
     def _body(self):
         tr = self.trainer
         loss, stats = tr.loss(self.batch)
+        rt = tr.runtime
+        if getattr(tr.opt, "can_overlap", False) and rt.tp_size == 1 and rt.pp_size == 1:
+            tr.opt.arm_overlap()  # bucket kernels fork onto a side stream inside the graph; device_step() joins them
         tr.model.train()
         loss.backward()
         tr.model.eval()
