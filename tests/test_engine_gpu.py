@@ -215,3 +215,33 @@ def test_engine_logprobs_against_fp32_oracle():
     dv = (val[:, start:] - ro["values"][:, start:])[valid].abs()
     assert dlp.max().item() < 2e-2 + 2e-2 * lp.abs().max().item(), dlp.max()
     assert dlp.mean().item() < 1e-2 and dv.mean().item() < 1e-2, (dlp.mean(), dv.mean())
+
+
+def test_engine_top_k_top_p_sampling():
+    """top-k / top-p run inside the engine (no fall-back to the PyTorch sampler): every sampled token lies in the filtered
+    set of the teacher-forced distribution and the reported log-probs are the RAW policy log-probs."""
+    from trlx_b200.engine.rollout import RolloutEngine
+
+    m = _mid_model()
+    pad = eos = 999
+    B, Q, R = 24, 6, 10
+    gen = dict(max_new_tokens=R, do_sample=True, eos_token_id=eos, pad_token_id=pad, top_k=5, top_p=0.9, temperature=0.8)
+    assert RolloutEngine.why_not(m, gen) is None
+    eng = RolloutEngine(m, pad, eos, gen, cache_trunk=True, seed=4)
+    assert eng.filtered
+    ids = torch.randint(1, 900, (B, Q), device="cuda")
+    ro = eng.rollout(ids, torch.ones_like(ids))
+    tokens, amask = ro["samples"], ro["mask"]
+    pos = (amask.cumsum(-1) - 1).clamp_min(0)
+    with torch.no_grad():
+        logits = m(tokens, attention_mask=amask, position_ids=pos, return_dict=True).logits.float()
+    start = ro["start"]
+    lp_all = torch.log_softmax(logits[:, :-1], -1)
+    nxt = tokens[:, 1:]
+    valid = amask[:, 1:].bool()
+    valid[:, :start] = False
+    rank = (lp_all > lp_all.gather(-1, nxt[..., None])).sum(-1)  # how many tokens are strictly more likely
+    assert (rank[valid] < 5 + 2).all(), "a token outside the top-k set (allowing bf16 near-ties) was sampled"
+    got = ro["logprobs"][:, start:][valid[:, start:]]
+    want = lp_all.gather(-1, nxt[..., None]).squeeze(-1)[:, start:][valid[:, start:]]
+    torch.testing.assert_close(got, want, atol=6e-2, rtol=5e-2)

@@ -596,3 +596,52 @@ def test_fused_logprob_autograd():
     torch.testing.assert_close(lp, ref, atol=3e-3, rtol=1e-3)
     torch.testing.assert_close(gh.float(), h.grad.float(), atol=2e-2 * h.grad.float().abs().max().item(), rtol=5e-2)
     torch.testing.assert_close(gw.float(), w.grad.float(), atol=2e-2 * w.grad.float().abs().max().item(), rtol=5e-2)
+
+
+@pytest.mark.parametrize("top_k,top_p,temperature", [(0, 0.9, 1.0), (20, 1.0, 0.7), (50, 0.8, 1.3), (1, 1.0, 1.0)])
+def test_sample_filtered_matches_hf_filtering(C, top_k, top_p, temperature):
+    """temperature -> top-k -> top-p -> multinomial (csrc/decode_ops.cu: sample_filtered_kernel) vs the same chain written
+    with sort / cumsum in PyTorch (HF ``TemperatureLogitsWarper`` / ``TopKLogitsWarper`` / ``TopPLogitsWarper``)."""
+    torch.manual_seed(21)
+    V, B = 1003, 16384
+    row = torch.randn(V, device="cuda") * 2.0
+    logits = torch.zeros(B, 1008, device="cuda")
+    logits[:, :V] = row
+    tok, lp = C.sample_filtered(logits, V, top_k, top_p, temperature, 1234)
+    # reference keep-set and distribution
+    scaled = row / temperature
+    keep = torch.ones(V, dtype=torch.bool, device="cuda")
+    if top_k > 0:
+        keep &= scaled >= torch.topk(scaled, top_k).values[-1]
+    masked = scaled.masked_fill(~keep, -float("inf"))
+    if top_p < 1.0:
+        sorted_logits, idx = torch.sort(masked, descending=False)
+        cum = sorted_logits.softmax(-1).cumsum(-1)
+        remove = cum <= (1 - top_p)
+        remove[-1] = False
+        keep &= ~torch.zeros(V, dtype=torch.bool, device="cuda").scatter(0, idx, remove)
+        masked = scaled.masked_fill(~keep, -float("inf"))
+    probs = masked.softmax(-1)
+    assert keep[tok].all(), "a filtered-out token was drawn"
+    torch.testing.assert_close(lp, torch.log_softmax(row, -1)[tok], atol=1e-4, rtol=1e-4)  # RAW log-prob (what PPO scores)
+    freq = torch.bincount(tok, minlength=V).float() / B
+    sigma = (probs * (1 - probs) / B).sqrt()
+    assert ((freq - probs).abs() <= 5 * sigma + 1e-4).all(), (freq - probs).abs().max()
+
+
+def test_sample_filtered_suppresses_eos_and_varies_with_step(C):
+    torch.manual_seed(22)
+    V, B = 517, 256
+    logits = torch.randn(B, 520, device="cuda")
+    logits[:, 7] = 50.0  # "EOS" dominates
+    step = torch.zeros(1, dtype=torch.int32, device="cuda")
+    tok0, _ = C.sample_filtered(logits, V, 0, 0.95, 1.0, 5, step, 7, 3)
+    assert (tok0 != 7).all()  # suppressed while step < 3
+    step.fill_(3)
+    tok3, _ = C.sample_filtered(logits, V, 0, 0.95, 1.0, 5, step, 7, 3)
+    assert (tok3 == 7).all()
+    logits[:, 7] = 0.0
+    a, _ = C.sample_filtered(logits, V, 40, 1.0, 1.0, 5, step)
+    step.fill_(4)
+    b, _ = C.sample_filtered(logits, V, 40, 1.0, 1.0, 5, step)
+    assert (a != b).float().mean() > 0.5  # fresh noise per step

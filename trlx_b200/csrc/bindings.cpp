@@ -27,6 +27,8 @@ int b200_embed_bf16(const long long*, const int*, const void*, const void*, int,
 int b200_decode_attention_bf16(const void*, void*, void*, const int*, const int*, const int*, void*, int, int, int, int, int,
                                int, float, int, float, int, const float*, int, cudaStream_t);
 int b200_rowdot_bf16(const void*, const void*, const void*, float*, int, int, long long, cudaStream_t);
+int b200_sample_filtered(const float*, long long, int, int, int, float, float, unsigned long long, const long long*, const int*,
+                         int, int, long long*, float*, cudaStream_t);
 int b200_decode_step(const long long*, const float*, const float*, const float*, int*, int, int, long long, long long,
                      long long*, float*, float*, float*, int*, int*, int*, int*, long long*, int*, cudaStream_t);
 int b200_paged_kv_write(const void*, const void*, void*, void*, const int*, const int*, const int*, int, int, int, int, int,
@@ -418,6 +420,26 @@ std::vector<Tensor> lmhead(const Tensor& h, const Tensor& w, const OptTensor& bi
                          stream()),
         "lmhead");
   return {lse, lp, tok, tlp};
+}
+
+// temperature / top-k / top-p sampling from fp32 logits [B, >= V] (row pitch = stride(0)) -> (token, raw log-prob of it)
+std::vector<Tensor> sample_filtered(const Tensor& logits, int64_t V, int64_t top_k, double top_p, double temperature,
+                                    int64_t seed, const OptTensor& step, int64_t suppress_col, int64_t suppress_until,
+                                    const OptTensor& seed_tensor) {
+  CHECK_F32(logits);
+  TORCH_CHECK(logits.dim() == 2 && logits.stride(1) == 1 && logits.size(1) >= V);
+  c10::cuda::CUDAGuard guard(logits.device());
+  const int64_t B = logits.size(0);
+  Tensor tok = torch::empty({B}, logits.options().dtype(at::kLong)), lp = torch::empty({B}, logits.options());
+  const long long* seedp = nullptr;
+  if (seed_tensor.has_value()) { TORCH_CHECK(seed_tensor->scalar_type() == at::kLong && seed_tensor->is_cuda()); seedp = (const long long*)seed_tensor->data_ptr<int64_t>(); }
+  const int* sp = nullptr;
+  if (step.has_value()) { TORCH_CHECK(step->scalar_type() == at::kInt); sp = step->data_ptr<int>(); }
+  check(b200_sample_filtered(logits.data_ptr<float>(), logits.stride(0), (int)B, (int)V, (int)top_k, (float)top_p,
+                             (float)temperature, (unsigned long long)seed, seedp, sp, (int)suppress_col, (int)suppress_until,
+                             (long long*)tok.data_ptr<int64_t>(), lp.data_ptr<float>(), stream()),
+        "sample_filtered");
+  return {tok, lp};
 }
 
 Tensor norm(const Tensor& x, const Tensor& w, const OptTensor& b, double eps, bool rms, const OptTensor& out_) {
@@ -985,6 +1007,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("rs_adamw_ag", &rs_adamw_ag);
   m.def("rs_adamw_ag_bucket", &rs_adamw_ag_bucket);
   m.def("rollout_rewards", &rollout_rewards);
+  m.def("sample_filtered", &sample_filtered, py::arg("logits"), py::arg("V"), py::arg("top_k"), py::arg("top_p"),
+        py::arg("temperature"), py::arg("seed"), py::arg("step") = py::none(), py::arg("suppress_col") = -1,
+        py::arg("suppress_until") = 0, py::arg("seed_tensor") = py::none());
   m.def("clip_exchange", &clip_exchange);
   m.def("lerp_", &lerp_);
   m.def("gemm_allgather", &gemm_allgather, py::arg("peers"), py::arg("rows_per_rank"), py::arg("K"), py::arg("lda"),

@@ -468,6 +468,168 @@ extern "C" int b200_decode_attention_bf16(const void* qkv, void* kcache, void* v
 #undef LAUNCH
 }
 
+// ------------------------------------------------------------------------------------------------ top-k / top-p sampling
+// HF `generate(do_sample=True, temperature, top_k, top_p)` semantics on one row of fp32 logits per block:
+//   temperature -> top-k (keep everything >= the k-th largest, ties included) -> top-p (smallest prefix of the sorted
+//   distribution whose mass reaches top_p; the crossing token is kept) -> multinomial draw (Gumbel-max over the kept set).
+// The thresholds are found EXACTLY by 4-pass radix selection on the order-preserving integer image of the logits
+// (256-bin histograms of counts for top-k, of probability mass for top-p) instead of sorting 50k entries.
+// Also returns the RAW log-probability of the drawn token (temperature 1, no filtering): what PPO scores.
+__device__ __forceinline__ uint32_t float_key(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float samp_uniform(unsigned long long seed, unsigned int row, unsigned int col) {
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (((unsigned long long)row << 32) | col);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return ((float)(z >> 40) + 0.5f) * (1.0f / 16777216.0f);
+}
+
+__global__ void __launch_bounds__(1024)
+sample_filtered_kernel(const float* __restrict__ logits, long long ld, int V, int top_k, float top_p, float inv_temp,
+                       unsigned long long seed, const long long* __restrict__ seed_ptr, const int* __restrict__ step_ptr,
+                       int suppress_col, int suppress_until, long long* __restrict__ tok_out, float* __restrict__ lp_out) {
+  griddep_wait();
+  griddep_launch();
+  __shared__ float red_a[32], red_b[32];
+  __shared__ int red_i[32];
+  __shared__ float hist_m[256];
+  __shared__ int hist_c[256];
+  __shared__ uint32_t sh_prefix;
+  __shared__ float sh_above;
+  __shared__ int sh_kleft;
+  const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const float* x = logits + (size_t)row * ld;
+  const int step = step_ptr ? *step_ptr : 0;
+  const int sup = (suppress_col >= 0 && step < suppress_until) ? suppress_col : -1;
+  const unsigned long long sd = seed + (seed_ptr ? (unsigned long long)(*seed_ptr) : 0ull) + 0x632BE59BD9B4E019ull * (unsigned long long)(step + 1);
+  auto at = [&](int i) { return i == sup ? -INFINITY : x[i]; };
+  auto bsum = [&](float v) {
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red_a[warp] = v;
+    __syncthreads();
+    float r = 0.f;
+    for (int i = 0; i < nw; ++i) r += red_a[i];
+    return r;
+  };
+  // ---- pass 1: max, then raw and tempered partition functions
+  float mx = -INFINITY;
+  for (int i = tid; i < V; i += blockDim.x) mx = fmaxf(mx, at(i));
+  mx = warp_max(mx);
+  if (lane == 0) red_b[warp] = mx;
+  __syncthreads();
+  mx = -INFINITY;
+  for (int i = 0; i < nw; ++i) mx = fmaxf(mx, red_b[i]);
+  float z1 = 0.f;
+  for (int i = tid; i < V; i += blockDim.x) z1 += __expf(at(i) - mx);
+  z1 = bsum(z1);
+  const float lse_raw = mx + __logf(z1);
+
+  // ---- top-k: key of the k-th largest logit
+  uint32_t kth = 0u;  // keep keys >= kth
+  if (top_k > 0 && top_k < V) {
+    if (tid == 0) { sh_prefix = 0u; sh_kleft = top_k; }
+    for (int level = 0; level < 4; ++level) {
+      const int shift = 24 - 8 * level;
+      if (tid < 256) hist_c[tid] = 0;
+      __syncthreads();
+      const uint32_t prefix = sh_prefix;
+      const uint32_t pmask = level == 0 ? 0u : (0xFFFFFFFFu << (shift + 8));
+      for (int i = tid; i < V; i += blockDim.x) {
+        const uint32_t key = float_key(at(i));
+        if ((key & pmask) == prefix) atomicAdd(&hist_c[(key >> shift) & 255u], 1);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int left = sh_kleft, b = 255;
+        for (; b > 0; --b) {
+          if (hist_c[b] >= left) break;
+          left -= hist_c[b];
+        }
+        sh_kleft = left;
+        sh_prefix = prefix | ((uint32_t)b << shift);
+      }
+      __syncthreads();
+    }
+    kth = sh_prefix;
+  }
+  // ---- tempered mass of the kept set
+  float zt = 0.f;
+  for (int i = tid; i < V; i += blockDim.x) {
+    const float v = at(i);
+    if (float_key(v) >= kth) zt += __expf((v - mx) * inv_temp);
+  }
+  zt = bsum(zt);
+  // ---- top-p: key of the token at which the sorted cumulative mass first reaches top_p
+  uint32_t pth = kth;
+  if (top_p < 1.f && top_p > 0.f) {
+    const float target = top_p * zt;
+    if (tid == 0) { sh_prefix = 0u; sh_above = 0.f; }
+    for (int level = 0; level < 4; ++level) {
+      const int shift = 24 - 8 * level;
+      if (tid < 256) hist_m[tid] = 0.f;
+      __syncthreads();
+      const uint32_t prefix = sh_prefix;
+      const uint32_t pmask = level == 0 ? 0u : (0xFFFFFFFFu << (shift + 8));
+      for (int i = tid; i < V; i += blockDim.x) {
+        const float v = at(i);
+        const uint32_t key = float_key(v);
+        if (key >= kth && (key & pmask) == prefix) atomicAdd(&hist_m[(key >> shift) & 255u], __expf((v - mx) * inv_temp));
+      }
+      __syncthreads();
+      if (tid == 0) {
+        float above = sh_above;
+        int b = 255;
+        for (; b > 0; --b) {
+          if (above + hist_m[b] >= target) break;
+          above += hist_m[b];
+        }
+        sh_above = above;
+        sh_prefix = prefix | ((uint32_t)b << shift);
+      }
+      __syncthreads();
+    }
+    pth = sh_prefix > kth ? sh_prefix : kth;
+  }
+  // ---- draw: Gumbel-max over the kept set (inv_temp <= 0: greedy)
+  float best = -INFINITY, best_logit = 0.f;
+  int best_i = 0x7fffffff;
+  for (int i = tid; i < V; i += blockDim.x) {
+    const float v = at(i);
+    if (float_key(v) < pth || v == -INFINITY) continue;
+    float key = v;
+    if (inv_temp > 0.f) key = v * inv_temp - __logf(-__logf(samp_uniform(sd, (unsigned)row, (unsigned)i)));
+    if (key > best || (key == best && i < best_i)) { best = key; best_i = i; best_logit = v; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o), ol = __shfl_xor_sync(0xffffffffu, best_logit, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+    if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; best_logit = ol; }
+  }
+  __syncthreads();
+  if (lane == 0) { red_a[warp] = best; red_b[warp] = best_logit; red_i[warp] = best_i; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < nw; ++w)
+      if (red_a[w] > best || (red_a[w] == best && red_i[w] < best_i)) { best = red_a[w]; best_i = red_i[w]; best_logit = red_b[w]; }
+    tok_out[row] = best_i;
+    lp_out[row] = best_logit - lse_raw;
+  }
+}
+
+extern "C" int b200_sample_filtered(const float* logits, long long ld, int B, int V, int top_k, float top_p, float temperature,
+                                    unsigned long long seed, const long long* seed_ptr, const int* step_ptr, int suppress_col,
+                                    int suppress_until, long long* tok_out, float* lp_out, cudaStream_t stream) {
+  if (B <= 0) return 0;
+  const float inv_temp = temperature > 0.f ? 1.f / temperature : 0.f;
+  return (int)launch_kernel(sample_filtered_kernel, dim3(B), dim3(1024), 0, stream, logits, ld, V, top_k, top_p, inv_temp, seed,
+                            seed_ptr, step_ptr, suppress_col, suppress_until, tok_out, lp_out);
+}
+
 extern "C" int b200_rowdot_bf16(const void* x, const void* w, const void* bias, float* out, int M, int K, long long ldx,
                                 cudaStream_t stream) {
   if (M <= 0) return 0;

@@ -108,33 +108,46 @@ def _fold(w: torch.Tensor, b: Optional[torch.Tensor], gamma: torch.Tensor, beta:
 
 class RolloutEngine:
     @staticmethod
-    def supports(model, gen_kwargs: Dict[str, Any], config=None, stop_sequences=None) -> bool:
-        """Decoder-only hydra model with a frozen reference branch, bf16 on CUDA, plain (temperature) sampling."""
-        try:
-            if not ops.available():
-                return False
-        except ops.ExtensionMissing:
-            raise
-        if stop_sequences:
-            return False  # trimming + re-tokenisation changes token ids → reference-faithful PyTorch path
-        if getattr(model, "peft_type", None) or getattr(model, "frozen_head", None) is None:
-            return False
+    def why_not(model, gen_kwargs: Dict[str, Any], config=None, stop_sequences=None) -> Optional[str]:
+        """``None`` when the engine can serve this model / sampling configuration, else the reason it cannot."""
+        if not ops.available():
+            return "the sm_100a extension is not available"
+        if getattr(model, "peft_type", None):
+            return "PEFT adapters are scored through the PyTorch path"
+        if getattr(model, "frozen_head", None) is None:
+            return "no frozen reference branch (num_layers_unfrozen <= 0 or a separate reference model)"
         if getattr(model, "num_value_layers_unfrozen", 0) != 0:
-            return False
+            return "the value head has its own transformer branch"
+        if getattr(model, "tp_context", None) is not None or getattr(base_lm(model.base_model), "tp_context", None) is not None:
+            return "tensor-parallel weights are sharded: the engine's kernels assume full (replicated) weight matrices"
+        from trlx_b200.parallel import state as pstate
+
+        if pstate.get_tensor_model_parallel_world_size() > 1 or pstate.get_pipeline_model_parallel_world_size() > 1:
+            return "model-parallel run (tensor / pipeline parallel groups are active)"
         lm = base_lm(model.base_model)
         spec = lm.config
         if not hasattr(lm, "transformer") or lm.dtype != torch.bfloat16 or not lm.device.type == "cuda":
-            return False
+            return "needs a decoder-only bf16 model on CUDA"
         if spec.head_dim % 8 or spec.hidden_size % 8 or spec.head_dim > 256 or spec.ffn_size % 8:
-            return False
+            return "head_dim / hidden / ffn sizes must be multiples of 8 (head_dim <= 256)"
         g = gen_kwargs or {}
-        if g.get("top_k") not in (0, None) or g.get("top_p") not in (1.0, 1, None):
-            return False
-        if g.get("num_beams", 1) not in (1, None) or g.get("repetition_penalty") not in (None, 1.0):
-            return False
+        if g.get("num_beams", 1) not in (1, None):
+            return "beam search"
+        if g.get("repetition_penalty") not in (None, 1.0):
+            return "repetition_penalty"
+        for k in ("typical_p", "penalty_alpha", "no_repeat_ngram_size", "bad_words_ids", "num_return_sequences"):
+            if g.get(k) not in (None, 0, 1, 1.0):
+                return f"generation option {k}"
         if any(isinstance(v, list) for k, v in g.items() if not str(k).startswith("_")):
-            return False
-        return True
+            return "a generation option is being swept (list value)"
+        return None
+
+    @staticmethod
+    def supports(model, gen_kwargs: Dict[str, Any], config=None, stop_sequences=None) -> bool:
+        """Decoder-only hydra model with a frozen reference branch, bf16 on CUDA; temperature / top-k / top-p sampling or
+        greedy.  With ``stop_sequences`` the engine still generates, but the trainer re-tokenises the trimmed text and
+        re-scores it exactly like the reference does (token ids may change at the cut)."""
+        return RolloutEngine.why_not(model, gen_kwargs, config, stop_sequences) is None
 
     def __init__(self, model, pad_token_id: int, eos_token_id: int, gen_kwargs: Dict[str, Any], cache_trunk: bool = True,
                  seed: int = 0, use_cuda_graph: bool = True):
@@ -160,6 +173,12 @@ class RolloutEngine:
         do_sample = bool(self.gen.get("do_sample", False))
         t = self.gen.get("temperature", 1.0)
         self.temperature = float(t if t is not None else 1.0) if do_sample else 0.0
+        # top-k / top-p: the LM head then writes fp32 logits once and a radix-select sampling kernel applies HF's
+        # temperature -> top-k -> top-p -> multinomial chain (csrc/decode_ops.cu: sample_filtered_kernel)
+        self.top_k = int(self.gen.get("top_k") or 0) if do_sample else 0
+        tp_ = self.gen.get("top_p")
+        self.top_p = float(tp_ if tp_ is not None else 1.0) if do_sample else 1.0
+        self.filtered = do_sample and ((0 < self.top_k < spec.vocab_size) or self.top_p < 1.0)
         self.launches_per_step = 0
         import os
 
@@ -429,8 +448,14 @@ class RolloutEngine:
         if (self.cache_trunk or self.defer_ref) and not self.parallel_branches and not mega:
             st["trunk_decode"].index_copy_(1, st["step64"], trunk_x.unsqueeze(1))
         hf = C.norm(x, tr.ln_f.weight, tr.ln_f.bias, spec.norm_eps, rms)
-        _, _, tok, tlp = C.lmhead(hf, lm.lm_head.weight, lm.lm_head.bias, None, True, self.temperature, self.seed,
-                                  st["step"], self.eos if st["min_new"] > 0 else -1, st["min_new"], st["ws"], st["seed_dev"])
+        if self.filtered:
+            V = spec.vocab_size
+            C.gemm(hf, lm.lm_head.weight, lm.lm_head.bias, None, "none", True, st["logits"][:, :V])
+            tok, tlp = C.sample_filtered(st["logits"], V, self.top_k, self.top_p, self.temperature, self.seed, st["step"],
+                                         self.eos if st["min_new"] > 0 else -1, st["min_new"], st["seed_dev"])
+        else:
+            _, _, tok, tlp = C.lmhead(hf, lm.lm_head.weight, lm.lm_head.bias, None, True, self.temperature, self.seed,
+                                      st["step"], self.eos if st["min_new"] > 0 else -1, st["min_new"], st["ws"], st["seed_dev"])
         vh = model.v_head
         h1 = C.gemm(hf, vh[0].weight, vh[0].bias, None, "relu")
         val = C.rowdot(h1, vh[2].weight.view(-1), vh[2].bias)
@@ -479,6 +504,7 @@ class RolloutEngine:
                           if (self.cache_trunk or self.defer_ref) else None),
             seed_dev=torch.zeros(1, dtype=torch.long, device=dev), min_new=0, graph=None,
             ln_stats=torch.zeros(2 * n_layers + 2, B, 2, **f32), stats_cursor=0,
+            logits=torch.empty(B, (V + 7) // 8 * 8, **f32) if self.filtered else None,
         )
         return st
 

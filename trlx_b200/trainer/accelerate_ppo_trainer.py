@@ -320,7 +320,10 @@ class AcceleratePPOTrainer(AccelerateRLTrainer):
             from trlx_b200.engine.rollout import RolloutEngine
 
             gen = self.generate_experience_kwargs or self.generate_kwargs
-            if RolloutEngine.supports(self.model, gen, self.config, self.stop_sequences):
+            why = RolloutEngine.why_not(self.model, gen, self.config, self.stop_sequences)
+            if why is not None:
+                logger.warning(f"rollouts use the PyTorch sampler + scoring pass, not the CUDA rollout engine: {why}")
+            if why is None:
                 gen_engine = dict(gen, _rollout_dtype=self.config.train.parallel.rollout_dtype)
                 self._engine = RolloutEngine(self.model, self.tokenizer.pad_token_id, self.tokenizer.eos_token_id, gen_engine,
                                              cache_trunk=self.cache_trunk, seed=self.config.train.seed + self.runtime.rank)
@@ -371,10 +374,12 @@ class AcceleratePPOTrainer(AccelerateRLTrainer):
         stats["time/rollout_score"] = time() - t0
         return payload[0][rt.rank * n:(rt.rank + 1) * n].to(device)
 
-    def _rollout_torch(self, batch, device):
-        """PyTorch path: sample, (re-tokenise outputs as the reference does), then ONE shared-trunk scoring pass."""
+    def _rollout_torch(self, batch, device, samples=None):
+        """PyTorch path: sample (unless ``samples`` were already generated by the engine), re-tokenise the decoded / trimmed
+        outputs as the reference does, then ONE shared-trunk scoring pass."""
         pad, eos = self.tokenizer.pad_token_id, self.tokenizer.eos_token_id
-        samples = self.generate(batch["input_ids"], batch["attention_mask"])
+        if samples is None:
+            samples = self.generate(batch["input_ids"], batch["attention_mask"])
         prompt_tensors = batch["input_ids"].to(device)
         seq2seq = self.config.model.model_arch_type == "seq2seq"
         str_samples, str_prompts, str_outputs = self.decode(prompt_tensors, samples, append_eos_token=True)
@@ -458,6 +463,11 @@ class AcceleratePPOTrainer(AccelerateRLTrainer):
                     am = F.pad(am, (width - am.shape[1], 0), value=0)
                 with rt.nvtx("rollout/engine"):
                     ro = engine.rollout(ids, am)
+                if self.stop_sequences:
+                    # generation ran on the engine; trimming at a stop sequence changes the text, so re-tokenise and re-score
+                    # exactly like the reference (``accelerate_ppo_trainer.py:304-345``) instead of reusing decode-time scores
+                    with rt.nvtx("rollout/rescore"):
+                        ro = self._rollout_torch(dict(batch, input_ids=ids, attention_mask=am), device, samples=ro["samples"])
             else:
                 with rt.nvtx("rollout/torch"):
                     ro = self._rollout_torch(batch, device)
