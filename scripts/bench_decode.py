@@ -71,7 +71,10 @@ def main():
                "ms_per_token": round(tot / n, 4), "rollout_ms": round(rollout_ms, 3), "kernels_per_step": eng.launches_per_step}
         if eng.mega:
             spec = eng.spec
-            out["max_active_clusters"] = int(ops.C.decode_mega_max_clusters(spec.hidden_size, spec.ffn_size))
+            groups = (args.batch + 15) // 16
+            cs = int(ops.C.decode_mega_cluster_size(spec.hidden_size, spec.ffn_size, groups))
+            out["cluster_size"] = cs
+            out["max_active_clusters"] = {str(c): int(ops.C.decode_mega_max_clusters(spec.hidden_size, spec.ffn_size, c)) for c in (16, 14, 12, 10, 8)}
             out["ring_stages"] = int(ops.C.decode_mega_stages(spec.hidden_size, spec.ffn_size))
             # streamed weight bytes per token (policy stack) / time → achieved fraction of the measured HBM copy bandwidth
             wbytes = sum(W.qkv_w.numel() + W.out_w.numel() + W.up_w.numel() + W.down_w.numel() for W in eng.layers) * 2

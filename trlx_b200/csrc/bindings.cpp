@@ -103,9 +103,11 @@ int b200_rs_finalize(const float*, const void*, const void*, void*, long long, i
 int b200_decode_mega_make_map(void*, const void*, long long, long long, long long);
 int b200_decode_mega_layer_bytes();
 int b200_decode_mega_stages(int, int);
-int b200_decode_mega_max_clusters(int, int);
+int b200_decode_mega_max_clusters(int, int, int);
+int b200_decode_mega_cluster_size(int, int, int);
 int b200_decode_mega(int, int, int, int, int, int, int, float, float, int, int, const int*, const int*, void*, void*, void*,
-                     const void*, const void*, void*, long long, const long long*, int, const float*, long long*, cudaStream_t);
+                     const void*, const void*, void*, long long, const long long*, int, const float*, long long*, int,
+                     cudaStream_t);
 }
 
 namespace {
@@ -917,7 +919,7 @@ std::vector<Tensor> decode_mega_build(const std::vector<std::vector<OptTensor>>&
 void decode_mega(Tensor& x, Tensor& a, Tensor& mid, const Tensor& block_table, const Tensor& seq_lens, const Tensor& table,
                  const Tensor& maps, int64_t nh, int64_t L, const std::string& act, bool rms, double eps, double scale,
                  int64_t page_size, const OptTensor& trunk_out, const OptTensor& step, int64_t branch, const OptTensor& alibi,
-                 const OptTensor& timing) {
+                 const OptTensor& timing, int64_t cluster_size) {
   CHECK_BF16(x); CHECK_BF16(a); CHECK_BF16(mid);
   TORCH_CHECK(x.is_contiguous() && a.is_contiguous() && mid.is_contiguous() && block_table.is_contiguous());
   TORCH_CHECK(block_table.scalar_type() == at::kInt && seq_lens.scalar_type() == at::kInt);
@@ -938,7 +940,8 @@ void decode_mega(Tensor& x, Tensor& a, Tensor& mid, const Tensor& block_table, c
                          (int)block_table.size(1), block_table.data_ptr<int>(), seq_lens.data_ptr<int>(), x.data_ptr(),
                          a.data_ptr(), mid.data_ptr(), table.data_ptr(), maps.data_ptr(), tr, tr_stride, step_ptr, (int)branch,
                          (const float*)optptr(alibi),
-                         timing.has_value() ? reinterpret_cast<long long*>(timing->data_ptr<int64_t>()) : nullptr, stream()),
+                         timing.has_value() ? reinterpret_cast<long long*>(timing->data_ptr<int64_t>()) : nullptr,
+                         (int)cluster_size, stream()),
         "decode_mega");
 }
 
@@ -949,9 +952,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("decode_mega", &decode_mega, py::arg("x"), py::arg("a"), py::arg("mid"), py::arg("block_table"), py::arg("seq_lens"),
         py::arg("table"), py::arg("maps"), py::arg("nh"), py::arg("L"), py::arg("act"), py::arg("rms"), py::arg("eps"),
         py::arg("scale"), py::arg("page_size"), py::arg("trunk_out") = py::none(), py::arg("step") = py::none(),
-        py::arg("branch") = -1, py::arg("alibi") = py::none(), py::arg("timing") = py::none());
+        py::arg("branch") = -1, py::arg("alibi") = py::none(), py::arg("timing") = py::none(), py::arg("cluster_size") = 0);
   m.def("decode_mega_stages", [](int64_t H, int64_t F) { return b200_decode_mega_stages((int)H, (int)F); });
-  m.def("decode_mega_max_clusters", [](int64_t H, int64_t F) { return b200_decode_mega_max_clusters((int)H, (int)F); });
+  m.def("decode_mega_max_clusters", [](int64_t H, int64_t F, int64_t cs) { return b200_decode_mega_max_clusters((int)H, (int)F, (int)cs); },
+        py::arg("H"), py::arg("F"), py::arg("cluster_size") = 16);
+  m.def("decode_mega_cluster_size", [](int64_t H, int64_t F, int64_t groups) { return b200_decode_mega_cluster_size((int)H, (int)F, (int)groups); });
   namespace py = pybind11;
   m.doc() = "trlx_b200 sm_100a kernels";
   m.def("gemm", &gemm, py::arg("x"), py::arg("w"), py::arg("bias") = py::none(), py::arg("residual") = py::none(),

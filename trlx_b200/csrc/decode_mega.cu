@@ -30,7 +30,7 @@
 
 namespace b200 {
 
-constexpr int DM_CS = 16;        // CTAs per cluster
+constexpr int DM_MAX_CS = 16;    // CTAs per cluster: chosen at launch (largest size with enough co-resident clusters)
 constexpr int DM_ROWS = 16;      // batch rows per cluster = UMMA N
 constexpr int DM_TM = 64;        // features per tile = UMMA M
 constexpr int DM_BK = 64;        // k-block (one 128-byte swizzle row of bf16)
@@ -38,8 +38,15 @@ constexpr int DM_WORKERS = 8;    // worker warps (LN / copy / epilogue / attenti
 constexpr int DM_THREADS = 64 + 32 * DM_WORKERS;
 constexpr int DM_WTILE = DM_TM * DM_BK * 2;     // 8 KB weight tile
 constexpr int DM_ATILE = DM_ROWS * DM_BK * 2;   // 2 KB activation k-block
-constexpr int DM_SLOTS = 4;      // TMEM accumulator slots (16 columns each)
+constexpr int DM_SLOTS = 4;      // TMEM accumulator slots
+constexpr int DM_NACC = 4;       // independent sub-accumulators per tile (k-step j of every k-block accumulates into sub-accumulator j):
+                                 // consecutive tcgen05.mma on ONE accumulator serialise at the MMA latency (~150 clk measured for these
+                                 // 64x16x16 atoms), four independent chains hide it; the epilogue adds the four
+constexpr int DM_SLOT_COLS = DM_NACC * DM_ROWS;
+constexpr int DM_TMEM_COLS = DM_SLOTS * DM_SLOT_COLS;   // 256
 constexpr int DM_MAX_STAGES = 24;
+
+static_assert(DM_NACC == 4 && DM_BK / 16 == DM_NACC, "one sub-accumulator per k-step of a k-block");
 
 struct DmLayer {
   const __nv_bfloat16 *ln1_w, *ln1_b, *ln2_w, *ln2_b, *qkv_b, *out_b, *fc_b, *fc2_b;
@@ -65,6 +72,7 @@ struct DmParams {
   int stages;
   const float* alibi;     // optional per-head slopes
   long long* timing;      // optional [16 ranks][L][16] clock64 stamps of cluster 0 (bring-up / profiling aid)
+  int cluster_size;
 };
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
@@ -87,12 +95,12 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
 __device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * DM_WORKERS) : "memory"); }
 __device__ __forceinline__ uint4 ldcg16(const void* p) {
   uint4 v;
-  asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
   return v;
 }
 __device__ __forceinline__ uint2 ldcg8(const void* p) {
   uint2 v;
-  asm volatile("ld.global.cg.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  asm volatile("ld.global.cg.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
   return v;
 }
 __device__ __forceinline__ float dm_act(float v, int act) {
@@ -109,6 +117,8 @@ __device__ __forceinline__ uint32_t act_chunk_off(int r, int c) {
   return (uint32_t)(c >> 3) * DM_ATILE + (uint32_t)r * 128u + (uint32_t)(((c & 7) ^ (r & 7)) << 4);
 }
 
+// MAXC: 16-byte chunks of a residual row each lane keeps in registers while normalising it (hidden <= 256 * MAXC)
+template <int MAXC>
 __global__ void __launch_bounds__(DM_THREADS, 1) decode_mega_kernel(const DmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int H = p.H, F = p.F, nh = p.nh, stages = p.stages;
@@ -128,6 +138,7 @@ __global__ void __launch_bounds__(DM_THREADS, 1) decode_mega_kernel(const DmPara
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
+  const int DM_CS = (int)cluster_nctarank();
   const int group = blockIdx.x / DM_CS;              // which 16 rows of the batch
   const int row0 = group * DM_ROWS;
   const int rows_here = min(DM_ROWS, p.B - row0);
@@ -142,7 +153,7 @@ __global__ void __launch_bounds__(DM_THREADS, 1) decode_mega_kernel(const DmPara
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 64);
+    tmem_alloc(tmem_slot, DM_TMEM_COLS);
     tmem_relinquish();
   }
   tc_fence_before_sync();
@@ -186,7 +197,7 @@ __global__ void __launch_bounds__(DM_THREADS, 1) decode_mega_kernel(const DmPara
         const uint32_t slot = tc % DM_SLOTS;
         mbar_wait(&tempty_bar[slot], ((tc / DM_SLOTS) & 1) ^ 1);
         tc_fence_after_sync();
-        const uint32_t tacc = tmem_base + slot * DM_ROWS;
+        const uint32_t tacc = tmem_base + slot * DM_SLOT_COLS;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % stages;
           mbar_wait(&full_bar[s], (it / stages) & 1);
@@ -194,7 +205,7 @@ __global__ void __launch_bounds__(DM_THREADS, 1) decode_mega_kernel(const DmPara
           const uint64_t da = umma_desc_k_sw128(smem_u32(ring + (size_t)s * DM_WTILE));
           const uint64_t db = umma_desc_k_sw128(act_addr + (uint32_t)kb * DM_ATILE);
 #pragma unroll
-          for (int k = 0; k < DM_BK / 16; ++k) umma_bf16(tacc, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < DM_BK / 16; ++k) umma_bf16(tacc + k * DM_ROWS, da + 2 * k, db + 2 * k, idesc, kb > 0 ? 1u : 0u);
           umma_commit(&empty_bar[s]);
         }
         umma_commit(&tfull_bar[slot]);
@@ -256,35 +267,50 @@ __global__ void __launch_bounds__(DM_THREADS, 1) decode_mega_kernel(const DmPara
     // swizzled bf16 operand <- LayerNorm / RMSNorm of x rows (two rows per warp)
     auto fill_norm = [&](const __nv_bfloat16* w, const __nv_bfloat16* b) {
       const int nchunk = H >> 3;
+      uint4 raw[2][MAXC];
+      float s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};
+#pragma unroll
       for (int rr = 0; rr < 2; ++rr) {
         const int r = wi * 2 + rr;
-        const bool ok = r < rows_here;
         const __nv_bfloat16* xr = p.x + (size_t)(row0 + r) * H;
-        float s1 = 0.f, s2 = 0.f;
-        if (ok)
-          for (int c = lane; c < nchunk; c += 32) {
-            const uint4 raw = ldcg16(xr + c * 8);
-            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 f = __bfloat1622float2(h2[j]);
-              s1 += f.x + f.y;
-              s2 += f.x * f.x + f.y * f.y;
-            }
+        for (int u = 0; u < MAXC; ++u) {
+          const int c = lane + 32 * u;
+          raw[rr][u] = make_uint4(0, 0, 0, 0);
+          if (c < nchunk && r < rows_here) raw[rr][u] = ldcg16(xr + c * 8);
+        }
+      }
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+#pragma unroll
+        for (int u = 0; u < MAXC; ++u) {
+          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw[rr][u]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = __bfloat1622float2(h2[j]);
+            s1[rr] += f.x + f.y;
+            s2[rr] += f.x * f.x + f.y * f.y;
           }
-        s1 = warp_sum(s1);
-        s2 = warp_sum(s2);
-        const float mean = p.rms ? 0.f : s1 / (float)H;
-        const float var = fmaxf(s2 / (float)H - mean * mean, 0.f);
+        }
+        s1[rr] = warp_sum(s1[rr]);
+        s2[rr] = warp_sum(s2[rr]);
+      }
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int r = wi * 2 + rr;
+        const float mean = p.rms ? 0.f : s1[rr] / (float)H;
+        const float var = fmaxf(s2[rr] / (float)H - mean * mean, 0.f);
         const float rstd = rsqrtf(var + p.eps);
-        for (int c = lane; c < nchunk; c += 32) {
+#pragma unroll
+        for (int u = 0; u < MAXC; ++u) {
+          const int c = lane + 32 * u;
+          if (c >= nchunk) continue;
           uint4 outv = make_uint4(0, 0, 0, 0);
-          if (ok) {
-            const uint4 raw = ldcg16(xr + c * 8);
+          if (r < rows_here) {
             const uint4 wraw = *reinterpret_cast<const uint4*>(w + c * 8);
             uint4 braw = make_uint4(0, 0, 0, 0);
             if (b) braw = *reinterpret_cast<const uint4*>(b + c * 8);
-            const __nv_bfloat162* x2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+            const __nv_bfloat162* x2 = reinterpret_cast<const __nv_bfloat162*>(&raw[rr][u]);
             const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(&wraw);
             const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&braw);
             __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&outv);
@@ -301,12 +327,23 @@ __global__ void __launch_bounds__(DM_THREADS, 1) decode_mega_kernel(const DmPara
     };
     // swizzled bf16 operand <- rows of a [B, K] global buffer
     auto fill_copy = [&](const __nv_bfloat16* src, int K) {
-      const int nchunk = K >> 3;
-      for (int i = wt; i < DM_ROWS * nchunk; i += 32 * DM_WORKERS) {
-        const int r = i / nchunk, c = i - r * nchunk;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (r < rows_here) v = ldcg16(src + (size_t)(row0 + r) * K + c * 8);
-        *reinterpret_cast<uint4*>(act_s + act_chunk_off(r, c)) = v;
+      const int nchunk = K >> 3, total = DM_ROWS * nchunk;
+      // 8 independent 16-byte loads in flight per thread, then 8 shared-memory stores
+      for (int i0 = wt; i0 < total; i0 += 8 * 32 * DM_WORKERS) {
+        uint4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = i0 + u * 32 * DM_WORKERS;
+          const int r = i / nchunk, c = i - r * nchunk;
+          v[u] = make_uint4(0, 0, 0, 0);
+          if (i < total && r < rows_here) v[u] = ldcg16(src + (size_t)(row0 + r) * K + c * 8);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = i0 + u * 32 * DM_WORKERS;
+          const int r = i / nchunk, c = i - r * nchunk;
+          if (i < total) *reinterpret_cast<uint4*>(act_s + act_chunk_off(r, c)) = v[u];
+        }
       }
       act_ready();
     };
@@ -315,11 +352,14 @@ __global__ void __launch_bounds__(DM_THREADS, 1) decode_mega_kernel(const DmPara
       const uint32_t slot = tc % DM_SLOTS;
       mbar_wait(&tfull_bar[slot], (tc / DM_SLOTS) & 1);
       tc_fence_after_sync();
-      uint32_t r[8];
-      tmem_ld8(tmem_base + slot * DM_ROWS + ch * 8 + (static_cast<uint32_t>(q * 32) << 16), r);
+      uint32_t r[DM_NACC][8];
+#pragma unroll
+      for (int a = 0; a < DM_NACC; ++a)
+        tmem_ld8(tmem_base + slot * DM_SLOT_COLS + a * DM_ROWS + ch * 8 + (static_cast<uint32_t>(q * 32) << 16), r[a]);
       tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
+      for (int j = 0; j < 8; ++j)
+        v[j] = (__uint_as_float(r[0][j]) + __uint_as_float(r[1][j])) + (__uint_as_float(r[2][j]) + __uint_as_float(r[3][j]));
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[slot]);
@@ -330,7 +370,7 @@ __global__ void __launch_bounds__(DM_THREADS, 1) decode_mega_kernel(const DmPara
     griddep_launch();
 
     for (int l = 0; l < p.L; ++l) {
-      const DmLayer& Lw = p.layers[l];
+      const DmLayer Lw = p.layers[l];   // by value: the pointers stay in registers across the asm memory barriers below
       stamp_l = l; stamp_i = 0;
       stamp();  // 0: layer start
       // ---- optional capture of the trunk activation entering block `branch`
@@ -421,11 +461,14 @@ __global__ void __launch_bounds__(DM_THREADS, 1) decode_mega_kernel(const DmPara
                     }
                   }
                   sc = dot * p.scale + slope * (float)t;
-                } else if (t == last) {
-                  float dot = 0.f;
-#pragma unroll 8
-                  for (int c = 0; c < DM_TM; ++c) dot += qs[c] * ks[c];
-                  sc = dot * p.scale + slope * (float)t;
+                }
+                if (t0 + 16 > last) {  // the chunk holding the new key: its q . k_new is computed by all 16 lanes (4 dims each)
+                  float part = 0.f;
+#pragma unroll
+                  for (int d = 0; d < 4; ++d) part += qs[l16 * 4 + d] * ks[l16 * 4 + d];
+#pragma unroll
+                  for (int o2 = 8; o2 > 0; o2 >>= 1) part += __shfl_xor_sync(hmask, part, o2);
+                  if (t == last) sc = part * p.scale + slope * (float)t;
                 }
                 float mx = sc;
 #pragma unroll
@@ -554,7 +597,7 @@ __global__ void __launch_bounds__(DM_THREADS, 1) decode_mega_kernel(const DmPara
   cluster_sync_all();
   if (warp == 1) {
     tc_fence_after_sync();
-    tmem_dealloc(tmem_base, 64);
+    tmem_dealloc(tmem_base, DM_TMEM_COLS);
   }
 }
 
@@ -610,52 +653,68 @@ extern "C" int b200_decode_mega_stages(int H, int F) {
   return 0;
 }
 
-// How many 16-CTA clusters of this kernel can be co-resident (informational: clusters are independent).
-extern "C" int b200_decode_mega_max_clusters(int H, int F) {
+// How many `cs`-CTA clusters of this kernel can be co-resident (clusters are independent, this only decides waves).
+static int dm_max_clusters(int H, int F, int cs) {
   const int stages = b200_decode_mega_stages(H, F);
   if (!stages) return 0;
   const size_t smem = dm_smem_bytes(H, F, stages);
-  cudaFuncSetAttribute(decode_mega_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-  cudaFuncSetAttribute(decode_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  auto kern = H <= 1024 ? decode_mega_kernel<4> : decode_mega_kernel<8>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(DM_CS * 8);
+  cfg.gridDim = dim3(cs * 8);
   cfg.blockDim = dim3(DM_THREADS);
   cfg.dynamicSmemBytes = smem;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = DM_CS;
+  attr[0].val.clusterDim.x = cs;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, decode_mega_kernel, &cfg) != cudaSuccess) {
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {
     cudaGetLastError();
     return -1;
   }
   return n;
+}
+extern "C" int b200_decode_mega_max_clusters(int H, int F, int cs) { return dm_max_clusters(H, F, cs > 0 ? cs : DM_MAX_CS); }
+
+// Cluster size for `groups` row groups: the largest size <= 16 whose clusters all fit at once (one wave) — a GPC that lost
+// SMs to yield caps 16-CTA clusters at 7 on some parts, 12-CTA clusters fit 8+ — falling back to the size with most CTAs.
+extern "C" int b200_decode_mega_cluster_size(int H, int F, int groups) {
+  static int cache[64][2];
+  static int ncache = 0;
+  for (int i = 0; i < ncache; ++i) if (cache[i][0] == groups) return cache[i][1];
+  int best = 8, best_ctas = 0;
+  for (int cs = DM_MAX_CS; cs >= 4; cs -= 2) {
+    const int n = dm_max_clusters(H, F, cs);
+    if (n >= groups) { best = cs; best_ctas = 1 << 30; break; }
+    if (n > 0 && n * cs > best_ctas) { best = cs; best_ctas = n * cs; }
+  }
+  if (ncache < 64) { cache[ncache][0] = groups; cache[ncache][1] = best; ++ncache; }
+  return best;
 }
 
 extern "C" int b200_decode_mega(int B, int H, int F, int nh, int L, int act, int rms, float eps, float scale, int page_size,
                                 int max_pages, const int* block_table, const int* seq_lens, void* x, void* a, void* mid,
                                 const void* layers, const void* maps, void* trunk_out, long long trunk_stride,
                                 const long long* step_ptr, int branch, const float* alibi, long long* timing,
-                                cudaStream_t stream) {
+                                int cluster_size, cudaStream_t stream) {
   if (B <= 0 || L <= 0) return 0;
-  if (H % 64 || F % 64 || nh * DM_TM != H) return -2;
+  if (H % 64 || F % 64 || nh * DM_TM != H || H > 2048) return -2;
   const int stages = b200_decode_mega_stages(H, F);
   if (!stages) return -2;
   const size_t smem = dm_smem_bytes(H, F, stages);
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(decode_mega_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) return -4;
-    cudaFuncSetAttribute(decode_mega_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    configured = true;
-  }
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    if (cudaFuncSetAttribute(decode_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -4;
-    smem_set = smem;
+  auto kern = H <= 1024 ? decode_mega_kernel<4> : decode_mega_kernel<8>;
+  static size_t smem_set[2] = {0, 0};
+  const int ki = H <= 1024 ? 0 : 1;
+  if (smem > smem_set[ki]) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) return -4;
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -4;
+    smem_set[ki] = smem;
   }
   DmParams p{};
   p.B = B; p.H = H; p.F = F; p.nh = nh; p.L = L; p.act = act; p.rms = rms; p.eps = eps; p.scale = scale;
@@ -665,19 +724,21 @@ extern "C" int b200_decode_mega(int B, int H, int F, int nh, int L, int act, int
   p.trunk_out = (__nv_bfloat16*)trunk_out; p.trunk_stride = trunk_stride; p.step_ptr = step_ptr; p.branch = branch;
   p.stages = stages; p.alibi = alibi; p.timing = timing;
   const int groups = (B + DM_ROWS - 1) / DM_ROWS;
+  const int cs = cluster_size > 0 ? cluster_size : b200_decode_mega_cluster_size(H, F, groups);
+  p.cluster_size = cs;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(groups * DM_CS);
+  cfg.gridDim = dim3(groups * cs);
   cfg.blockDim = dim3(DM_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = DM_CS;
+  attr[0].val.clusterDim.x = cs;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  return (int)cudaLaunchKernelEx(&cfg, decode_mega_kernel, p);
+  return (int)cudaLaunchKernelEx(&cfg, kern, p);
 }

@@ -141,7 +141,7 @@ class FusedAdamW(Optimizer):
 
     def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2,
                  grad_clip: Optional[float] = None, process_group=None, zero_stage: int = 2, overlap: Optional[bool] = None,
-                 bucket_mb: Optional[float] = None, **unused):
+                 bucket_mb: Optional[float] = None, local_only: bool = False, **unused):
         import os
 
         defaults = dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay)
@@ -151,6 +151,9 @@ class FusedAdamW(Optimizer):
         # zero_stage == 0: DDP semantics — NCCL all-reduce of the flat gradient, replicated update
         self.zero_stage = int(zero_stage)
         self.process_group = process_group
+        # local_only: the parameters handed in are already this rank's partition and their gradients arrive reduced
+        # (ZeRO-3, parallel/zero3.py) — no cross-rank traffic here, only the global-norm exchange when clipping
+        self.local_only = bool(local_only)
         self.overlap = (os.environ.get("TRLX_B200_OVERLAP_GRAD", "1") == "1") if overlap is None else bool(overlap)
         mb = float(os.environ.get("TRLX_B200_BUCKET_MB", bucket_mb if bucket_mb is not None else 16))
         self.bucket_elems = max(int(mb * (1 << 20) / 2), 1024)
@@ -165,6 +168,8 @@ class FusedAdamW(Optimizer):
 
     # -- setup ------------------------------------------------------------------------------------------------------------
     def _world(self):
+        if self.local_only:
+            return 1, 0
         if dist.is_available() and dist.is_initialized():
             return dist.get_world_size(self.process_group), dist.get_rank(self.process_group)
         return 1, 0
@@ -310,7 +315,16 @@ class FusedAdamW(Optimizer):
                     p.grad.copy_(flat[off:off + p.numel()].view_as(p.grad))
                     off += p.numel()
             if self.grad_clip:
-                self.last_grad_norm = torch.nn.utils.clip_grad_norm_(params, self.grad_clip)
+                if self.local_only and dist.is_available() and dist.is_initialized():
+                    sq = torch.stack([p.grad.float().pow(2).sum() for p in params]).sum() if params else torch.zeros(())
+                    dist.all_reduce(sq, group=self.process_group)
+                    norm = sq.sqrt()
+                    coef = (self.grad_clip / (norm + 1e-6)).clamp(max=1.0)
+                    for p in params:
+                        p.grad.mul_(coef.to(p.grad.dtype))
+                    self.last_grad_norm = norm
+                else:
+                    self.last_grad_norm = torch.nn.utils.clip_grad_norm_(params, self.grad_clip)
             self._fallback.step()
             return loss
 
@@ -354,6 +368,8 @@ class FusedAdamW(Optimizer):
                 if self.grad_clip:
                     fg.sq.zero_()
                     C.sqnorm_(fg.flat_grad, fg.sq)
+                    if self.local_only and dist.is_available() and dist.is_initialized():
+                        dist.all_reduce(fg.sq, group=self.process_group)  # the partitions' norms add up to the global one
                     C.clip_coef_(fg.sq, float(self.grad_clip), fg.hyper, fg.norm)
                     self.last_grad_norm = fg.norm
                 C.adamw_flat(fg.flat_param, fg.master, fg.flat_grad, fg.exp_avg, fg.exp_avg_sq, *args, fg.hyper)

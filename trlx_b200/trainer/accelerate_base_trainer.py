@@ -219,6 +219,17 @@ class AccelerateRLTrainer(BaseRLTrainer):
             kwargs.setdefault("process_group", self.runtime.dp_group)
             kwargs.setdefault("zero_stage", self.config.train.parallel.zero_stage)
         params = [p for p in self.model.parameters() if p.requires_grad]
+        self.zero3 = None
+        rt = self.runtime
+        if (int(self.config.train.parallel.zero_stage) >= 3 and rt.tp_size == 1 and rt.pp_size == 1
+                and (rt.dp_size > 1 or os.environ.get("TRLX_B200_ZERO3_FORCE") == "1")):
+            # ZeRO-3: parameters, gradients and optimizer state partitioned over the data-parallel ranks (parallel/zero3.py)
+            from trlx_b200.parallel.zero3 import Zero3ParamSharder, default_units
+
+            self.zero3 = Zero3ParamSharder(self.model, default_units(self.model), rt.dp_group)
+            params = self.zero3.shard_parameters()
+            if issubclass(optimizer_class, FusedAdamW):
+                kwargs["local_only"] = True
         opt = optimizer_class(params, **kwargs)
         if hasattr(opt, "prepare"):
             opt.prepare()
@@ -291,13 +302,21 @@ class AccelerateRLTrainer(BaseRLTrainer):
             directory = os.path.join(self.config.train.checkpoint_dir, "hf_model")
         directory = resolve_output_dir(directory)
         self.runtime.barrier()
+        with self._full_params():
+            if self.runtime.is_main_process:
+                self.model.save_pretrained(directory, **kwargs)
         if self.runtime.is_main_process:
-            self.model.save_pretrained(directory, **kwargs)
             try:
                 self.tokenizer.save_pretrained(directory)
             except Exception as err:  # pragma: no cover
                 logger.warning(f"could not save tokenizer: {err}")
         self.runtime.barrier()
+
+    def _full_params(self, writeback: bool = False):
+        """All parameters materialised on every rank (no-op unless ZeRO-3 partitions them); collective: every data-parallel
+        rank must enter."""
+        z = getattr(self, "zero3", None)
+        return z.summon_full_params(writeback=writeback) if z is not None else contextlib.nullcontext()
 
     def _extra_state(self) -> Dict[str, Any]:
         return {}
@@ -310,9 +329,10 @@ class AccelerateRLTrainer(BaseRLTrainer):
         directory = resolve_output_dir(directory or self.config.train.checkpoint_dir)
         os.makedirs(directory, exist_ok=True)
         rank = self.runtime.rank
-        if self.runtime.dp_rank == 0:  # one writer per model-parallel rank: its tensor / pipeline shard of the weights
-            torch.save({k: v.detach().cpu() for k, v in self.model.raw_state_dict().items()},
-                       os.path.join(directory, self._model_state_name()))
+        with self._full_params():
+            if self.runtime.dp_rank == 0:  # one writer per model-parallel rank: its tensor / pipeline shard of the weights
+                torch.save({k: v.detach().cpu() for k, v in self.model.raw_state_dict().items()},
+                           os.path.join(directory, self._model_state_name()))
         if self.runtime.is_main_process:
             with open(os.path.join(directory, "state.json"), "w") as fh:
                 json.dump({"iter_count": self.iter_count, "nth_evaluation": self.nth_evaluation,
@@ -339,8 +359,8 @@ class AccelerateRLTrainer(BaseRLTrainer):
         path = os.path.join(directory, self._model_state_name())
         if os.path.exists(path):
             sd = torch.load(path, map_location="cpu", weights_only=True)
-            own = self.model.raw_state_dict()
-            with torch.no_grad():
+            with self._full_params(writeback=True), torch.no_grad():
+                own = self.model.raw_state_dict()
                 for k, v in sd.items():
                     if k in own:
                         if own[k].shape != v.shape:
@@ -536,8 +556,12 @@ class AccelerateRLTrainer(BaseRLTrainer):
         n = len(stats_accum)
         stats = {k: sum(s[k] for s in stats_accum) / self.num_mb for k in stats_accum[0]}
         self._pre_optimizer_step()
+        if self.zero3 is not None:
+            self.zero3.reduce_pending()
         self.opt.step()
         self.opt.zero_grad()
+        if self.zero3 is not None:
+            self.zero3.finish_step()
         self.scheduler.step()
         self.iter_count += 1
         self._after_weights_changed()

@@ -246,6 +246,7 @@ class AcceleratePPOTrainer(AccelerateRLTrainer):
         return bool(self.runtime.cuda and self.config.train.parallel.cuda_graphs and self.num_mb == 1
                     and getattr(self.opt, "graph_capturable", False) and self.config.model.model_arch_type != "seq2seq"
                     and hasattr(self.model, "can_share_trunk") and self.model.can_share_trunk()
+                    and getattr(self, "zero3", None) is None  # gathered parameters move between pooled buffers
                     and not self.config.train.trainer_kwargs.get("no_train_graph", False)
                     and os.environ.get("TRLX_B200_TRAIN_GRAPH", "1") == "1")
 
@@ -321,6 +322,8 @@ class AcceleratePPOTrainer(AccelerateRLTrainer):
 
             gen = self.generate_experience_kwargs or self.generate_kwargs
             why = RolloutEngine.why_not(self.model, gen, self.config, self.stop_sequences)
+            if getattr(self, "zero3", None) is not None:
+                why = "ZeRO-3 partitions the parameters (the engine needs resident, address-stable weights)"
             if why is not None:
                 logger.warning(f"rollouts use the PyTorch sampler + scoring pass, not the CUDA rollout engine: {why}")
             if why is None:
