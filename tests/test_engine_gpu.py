@@ -245,3 +245,54 @@ def test_engine_top_k_top_p_sampling():
     got = ro["logprobs"][:, start:][valid[:, start:]]
     want = lp_all.gather(-1, nxt[..., None]).squeeze(-1)[:, start:][valid[:, start:]]
     torch.testing.assert_close(got, want, atol=6e-2, rtol=5e-2)
+
+
+@pytest.mark.parametrize("fp8", [False, True])
+def test_engine_serves_lora_models_with_merged_weights(fp8):
+    """PEFT / LoRA policies run on the engine: rollouts read W + (alpha/r) B A (re-merged after weight changes), reference
+    log-probs come from one adapter-free pass; checked against teacher-forced scoring with adapters on / off."""
+    from trlx_b200.engine.rollout import RolloutEngine
+    from trlx_b200.models.modeling_ppo import AutoModelForCausalLMWithHydraValueHead
+
+    torch.manual_seed(0)
+    cfg = dict(model_type="gpt2", vocab_size=1000, n_embd=256, n_layer=3, n_head=4, n_positions=128, eos_token_id=999, bos_token_id=999)
+    m = AutoModelForCausalLMWithHydraValueHead.from_config(
+        cfg, peft_config=dict(peft_type="LORA", task_type="CAUSAL_LM", r=8, lora_alpha=32, lora_dropout=0.0))
+    m = m.cuda().to(torch.bfloat16).eval()
+
+    def perturb(scale):
+        with torch.no_grad():
+            for n, p in m.named_parameters():
+                if "lora_B" in n:
+                    p.copy_(torch.randn_like(p) * scale)
+
+    perturb(0.05)
+    pad = eos = 999
+    B, Q, R = 16, 6, 8
+    gen = dict(max_new_tokens=R, do_sample=False, eos_token_id=eos, pad_token_id=pad, top_k=0, top_p=1.0)
+    if fp8:
+        gen["_rollout_dtype"] = "fp8"
+    assert RolloutEngine.why_not(m, gen) is None
+    eng = RolloutEngine(m, pad, eos, gen, seed=1)
+    assert eng.lora and eng.fp8 == fp8
+    ids = torch.randint(1, 900, (B, Q), device="cuda")
+    tol = 0.2 if fp8 else 6e-2
+    for round_ in range(2):
+        ro = eng.rollout(ids, torch.ones_like(ids))
+        tokens, amask = ro["samples"], ro["mask"]
+        pos = (amask.cumsum(-1) - 1).clamp_min(0)
+        with torch.no_grad():
+            on = m(tokens, attention_mask=amask, position_ids=pos, return_dict=True)
+            off = m(tokens, attention_mask=amask, position_ids=pos, return_dict=True, ignore_peft_adapter=True)
+        nxt = tokens[:, 1:, None]
+        lp_on = torch.log_softmax(on.logits[:, :-1].float(), -1).gather(-1, nxt).squeeze(-1)
+        lp_off = torch.log_softmax(off.logits[:, :-1].float(), -1).gather(-1, nxt).squeeze(-1)
+        start = ro["start"]
+        valid = amask[:, 1:].bool()
+        valid[:, :start] = False
+        assert (lp_on - lp_off)[valid].abs().mean() > 0.02, "the adapters must change the policy for this test to mean anything"
+        assert (ro["logprobs"] - lp_on)[valid].abs().mean() < tol / 3 and (ro["logprobs"] - lp_on)[valid].abs().max() < tol * 2
+        torch.testing.assert_close(ro["ref_logprobs"][valid], lp_off[valid], atol=6e-2, rtol=5e-2)
+        assert ro["trunk"] is None
+        perturb(0.08)          # "optimizer step": new adapters ...
+        eng.mark_dirty()       # ... must be re-merged before the next rollout

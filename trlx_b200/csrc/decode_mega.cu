@@ -85,10 +85,10 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(addr), "r"(parity)
+        : "r"(addr), "r"(parity), "r"(2000u)
         : "memory");
   } while (!done);
 }
@@ -252,11 +252,15 @@ __global__ void __launch_bounds__(DM_THREADS, 1) decode_mega_kernel(const DmPara
         p.timing[((size_t)rank * p.L + stamp_l) * 16 + stamp_i] = clock64();
       ++stamp_i;
     };
-    auto cluster_phase = [&]() {   // all 16 CTAs finished their global-memory writes of this phase
+    auto cluster_phase = [&]() {   // all CTAs of the cluster finished their global-memory writes of this phase
       __threadfence();
       worker_sync();
       if (wt < DM_CS) mbar_arrive_cluster(mapa_shared(cl_local, (uint32_t)wt));
-      mbar_wait_cluster(cl_bar, cphase & 1);
+      // ONE thread polls: every cluster-scope acquire makes ptxas emit CCTL.IVALL (an L1 invalidate), and 256 threads spinning
+      // on it starved the SM's whole load / store path (ncu: millions of CCTL.IVALL, every phase ~4x slower); the others
+      // sleep on the hardware barrier
+      if (wt == 0) mbar_wait_cluster(cl_bar, cphase & 1);
+      worker_sync();
       ++cphase;
     };
     auto act_ready = [&]() {

@@ -55,12 +55,24 @@ class _LayerW:
     window: int
 
 
+def _w(linear):
+    """Weight a rollout kernel should read: LoRA-wrapped projections contribute ``W + (alpha / r) B A`` (a merged copy that
+    the engine refreshes after optimizer steps), plain ones their own tensor."""
+    return linear.merged_weight() if hasattr(linear, "merged_weight") and len(getattr(linear, "lora_A", ())) else linear.weight
+
+
 def _layer_weights(block, spec, idx: int) -> _LayerW:
     n2 = block.norm2
     return _LayerW(block.norm1.weight, block.norm1.bias, n2.weight if n2 is not None else None,
-                   n2.bias if n2 is not None else None, block.attn.qkv.weight, block.attn.qkv.bias, block.attn.out.weight,
-                   block.attn.out.bias, block.mlp.up.weight, block.mlp.up.bias, block.mlp.down.weight, block.mlp.down.bias,
+                   n2.bias if n2 is not None else None, _w(block.attn.qkv), block.attn.qkv.bias, _w(block.attn.out),
+                   block.attn.out.bias, _w(block.mlp.up), block.mlp.up.bias, _w(block.mlp.down), block.mlp.down.bias,
                    spec.local_window if idx in spec.local_layers else 0)
+
+
+def _lora_sources(block):
+    """``[(field of _LayerW, LoRA-wrapped linear)]`` for the projections of ``block`` that carry adapters."""
+    pairs = (("qkv_w", block.attn.qkv), ("out_w", block.attn.out), ("up_w", block.mlp.up), ("down_w", block.mlp.down))
+    return [(f, lin) for f, lin in pairs if hasattr(lin, "merged_weight") and len(getattr(lin, "lora_A", ()))]
 
 
 @dataclass
@@ -112,9 +124,10 @@ class RolloutEngine:
         """``None`` when the engine can serve this model / sampling configuration, else the reason it cannot."""
         if not ops.available():
             return "the sm_100a extension is not available"
-        if getattr(model, "peft_type", None):
-            return "PEFT adapters are scored through the PyTorch path"
-        if getattr(model, "frozen_head", None) is None:
+        peft = getattr(model, "peft_type", None)
+        if peft and str(peft).upper().split(".")[-1] != "LORA":
+            return f"{peft} adapters are scored through the PyTorch path (only LoRA is merged into the rollout weights)"
+        if not peft and getattr(model, "frozen_head", None) is None:
             return "no frozen reference branch (num_layers_unfrozen <= 0 or a separate reference model)"
         if getattr(model, "num_value_layers_unfrozen", 0) != 0:
             return "the value head has its own transformer branch"
@@ -156,16 +169,21 @@ class RolloutEngine:
         self.spec = self.lm.config
         self.pad, self.eos = int(pad_token_id), int(eos_token_id if eos_token_id is not None else -1)
         self.gen = dict(gen_kwargs)
-        self.cache_trunk = cache_trunk
+        self.cache_trunk = cache_trunk and not getattr(model, "peft_type", None)  # adapters leave no frozen trunk to share
         self.seed = int(seed)
         self.calls = 0
         self.use_cuda_graph = use_cuda_graph
         self.device = self.lm.device
-        self.branch = model.branch_layer
+        self.branch = model.branch_layer if not getattr(model, "peft_type", None) else 0
         spec = self.spec
+        # LoRA (the reference toggles adapters per forward, ``trlx/models/modeling_ppo.py:318-324``): rollouts read merged
+        # weights W + (alpha / r) B A, refreshed in place after optimizer steps — zero adapter overhead per decoded token and the
+        # fp8 / megakernel paths apply unchanged; reference log-probs come from ONE batched adapter-free pass after the loop
+        self.lora = bool(getattr(model, "peft_type", None))
         self.layers = [_layer_weights(b, spec, i) for i, b in enumerate(self.lm.transformer.h)]
-        fh = model.frozen_head
-        self.ref_layers = [_layer_weights(b, spec, self.branch + j) for j, b in enumerate(fh.decoder_blocks)]
+        self._lora_src = [_lora_sources(b) for b in self.lm.transformer.h] if self.lora else []
+        fh = model.frozen_head if not self.lora else None
+        self.ref_layers = [_layer_weights(b, spec, self.branch + j) for j, b in enumerate(fh.decoder_blocks)] if fh is not None else []
         self.scale = spec.attn_scale if spec.attn_scale is not None else 1.0 / math.sqrt(spec.head_dim)
         self.alibi = alibi_slopes(spec.num_heads).to(self.device) if spec.pos == "alibi" else None
         self.rot_dim = spec.rotary_dim if spec.pos == "rotary" else 0
@@ -204,7 +222,8 @@ class RolloutEngine:
         # not have to sit on the per-token critical path.  The decode graph then keeps just the trunk activation of every
         # position, and one batched pass (2 frozen blocks + LM head over [B, Q+R] tokens at GEMM-efficient M) scores all
         # positions at the end — instead of 2 latency-bound blocks + a 77 MB LM-head sweep per decoded token.
-        self.defer_ref = os.environ.get("TRLX_B200_DEFER_REF", "1") == "1"
+        self.defer_ref = os.environ.get("TRLX_B200_DEFER_REF", "1") == "1" or self.lora
+        self.keep_trunk = (self.cache_trunk or self.defer_ref) and not self.lora  # per-position activation at the branch point
         self.parallel_branches = (os.environ.get("TRLX_B200_PARALLEL_BRANCHES", "1") == "1" and self.branch < len(self.layers)
                                   and not self.defer_ref)
         self.side = torch.cuda.Stream(device=self.device) if self.parallel_branches else None
@@ -255,7 +274,7 @@ class RolloutEngine:
         if "mega" not in st:
             self._mega_build(st)
         m = st["mega"]
-        want_trunk = (self.cache_trunk or self.defer_ref) and st["trunk_decode"] is not None
+        want_trunk = self.keep_trunk and st["trunk_decode"] is not None
         ops.C.decode_mega(x, m["a"], m["mid"], st["block_table"], st["seq_lens"], m["table"], m["maps"], spec.num_heads,
                           len(self.layers), spec.activation, spec.norm == "rmsnorm", spec.norm_eps, self.scale, PAGE,
                           st["trunk_decode"] if want_trunk else None, st["step64"] if want_trunk else None,
@@ -273,7 +292,7 @@ class RolloutEngine:
         first = not self.fp8_w
 
         def build(W: _LayerW, old: Optional[_Fp8W]) -> _Fp8W:
-            trainable = any(t.requires_grad for t in (W.qkv_w, W.up_w))
+            trainable = any(t.requires_grad for t in (W.qkv_w, W.up_w)) or self.lora  # merged LoRA copies change every step
             if old is not None and not trainable:
                 return old
             q, qs = _quant_e4m3(W.qkv_w)
@@ -288,8 +307,19 @@ class RolloutEngine:
         self.ref_fp8_w = [build(W, None if first else self.ref_fp8_w[i]) for i, W in enumerate(self.ref_layers)]
 
     @torch.no_grad()
+    def _refresh_lora(self):
+        """Re-merge ``W + (alpha / r) B A`` into the engine's weight copies IN PLACE (graphs / tensor maps keep the addresses)."""
+        for W, srcs in zip(self.layers, self._lora_src):
+            for field, lin in srcs:
+                getattr(W, field).copy_(lin.merged_weight())
+
+    @torch.no_grad()
     def refresh_folded(self):
         """(Re)build γ-scaled copies of the QKV / MLP-up weights in place (the captured CUDA graph keeps their addresses)."""
+        if self.lora and self.dirty:
+            self._refresh_lora()
+            if not self.fp8 and not self.fold_norms:
+                self.dirty = False
         if self.fp8 and self.dirty:
             self._refresh_fp8()
             self.dirty = False
@@ -445,7 +475,7 @@ class RolloutEngine:
                 x, xs = self._layer_folded(x, xs, W, self.folded[i], st["kc"][i], st["vc"][i], st)
             else:
                 x = self._layer(x, W, st["kc"][i], st["vc"][i], st)
-        if (self.cache_trunk or self.defer_ref) and not self.parallel_branches and not mega:
+        if self.keep_trunk and not self.parallel_branches and not mega:
             st["trunk_decode"].index_copy_(1, st["step64"], trunk_x.unsqueeze(1))
         hf = C.norm(x, tr.ln_f.weight, tr.ln_f.bias, spec.norm_eps, rms)
         if self.filtered:
@@ -501,7 +531,7 @@ class RolloutEngine:
             ref_lp_out=torch.zeros(B, R, **f32), val_out=torch.zeros(B, R, **f32),
             ws=torch.empty(5 * B * n_tiles + B, **f32), ws_ref=torch.empty(5 * B * n_tiles + B, **f32),
             trunk_decode=(torch.zeros(B, R, spec.hidden_size, dtype=torch.bfloat16, device=dev)
-                          if (self.cache_trunk or self.defer_ref) else None),
+                          if self.keep_trunk else None),
             seed_dev=torch.zeros(1, dtype=torch.long, device=dev), min_new=0, graph=None,
             ln_stats=torch.zeros(2 * n_layers + 2, B, 2, **f32), stats_cursor=0,
             logits=torch.empty(B, (V + 7) // 8 * 8, **f32) if self.filtered else None,
@@ -598,6 +628,22 @@ class RolloutEngine:
             y, _ = blk(y, ctx, None, False)
         y = fh.final_norm(y)
         ref_lp, _ = ops.fused_logprob(y, fh.lm_head.weight, fh.lm_head.bias, labels)
+        return ref_lp.float()
+
+    @torch.no_grad()
+    def _ref_score_adapter_free(self, all_tokens: torch.Tensor, full_mask: torch.Tensor, Q: int) -> torch.Tensor:
+        """LoRA models: reference log-probs of every next token from ONE batched forward with the adapters switched off (the
+        reference toggles them the same way, ``trlx/models/modeling_ppo.py:318-324``, but re-runs the model per chunk after
+        ``generate``); there is no frozen branch or shared trunk with adapters on every layer."""
+        lm, peft_model = self.lm, self.model.base_model
+        ids, am = all_tokens[:, :-1], full_mask[:, :-1]
+        # generated positions are all visible to later ones even when a row sampled the pad token id (pad == eos)
+        am = torch.cat([am[:, :Q], torch.ones_like(am[:, Q:])], 1)
+        pos = (am.long().cumsum(-1) - 1).clamp_min(0)
+        ctx = peft_model.disable_adapter() if hasattr(peft_model, "disable_adapter") else contextlib.nullcontext()
+        with ctx:
+            out = lm(input_ids=ids, attention_mask=am, position_ids=pos, compute_logits=False)
+        ref_lp, _ = ops.fused_logprob(out.last_hidden_state, lm.lm_head.weight, lm.lm_head.bias, all_tokens[:, 1:])
         return ref_lp.float()
 
     @contextlib.contextmanager
@@ -724,9 +770,13 @@ class RolloutEngine:
         all_tokens = torch.cat([prompt, sample_outputs], 1)
         full_mask = all_tokens.not_equal(self.pad).long()
         trunk = None
-        if self.cache_trunk or self.defer_ref:
+        if self.keep_trunk:
             trunk = torch.cat([trunk_p, st["trunk_decode"][:, :r_max]], 1)
-        if self.defer_ref:
+        if self.lora:
+            torch.cuda.nvtx.range_push("engine/reference_scoring")
+            ref_logprobs = self._ref_score_adapter_free(all_tokens, full_mask, Q)
+            torch.cuda.nvtx.range_pop()
+        elif self.defer_ref:
             torch.cuda.nvtx.range_push("engine/reference_scoring")
             ref_logprobs = self._ref_score(prompt, mask, trunk, all_tokens[:, 1:Q + r_max])
             torch.cuda.nvtx.range_pop()

@@ -53,6 +53,7 @@ class _Unit:
         self.shard_numel = self.numel // world
         self.lo = self.shard_numel * rank
         self.shapes = [p.shape for p in params]
+        self.numels = [p.numel() for p in params]
         self.dtype = params[0].dtype
         self.trainable = any(p.requires_grad for p in params)
         self.full: Optional[torch.Tensor] = None       # gathered parameters (pooled)
@@ -158,8 +159,8 @@ class Zero3ParamSharder:
         else:
             dist.all_gather_into_tensor(full, u.shard.data.contiguous(), group=self.group)
         u.full = full
-        for p, o, shape in zip(u.params, u.offsets, u.shapes):
-            p.data = full[o:o + p.numel()].view(shape)
+        for p, o, n, shape in zip(u.params, u.offsets, u.numels, u.shapes):
+            p.data = full[o:o + n].view(shape)
 
     def _release(self, u: _Unit, force: bool = False):
         u.users = 0 if force else max(u.users - 1, 0)
@@ -180,9 +181,9 @@ class Zero3ParamSharder:
     def _reduce_grads(self, u: _Unit):
         full_grad = self._take(u.numel, torch.float32)
         full_grad.zero_()
-        for p, o in zip(u.params, u.offsets):
+        for p, o, n in zip(u.params, u.offsets, u.numels):
             if p.grad is not None:
-                full_grad[o:o + p.numel()].copy_(p.grad.reshape(-1))
+                full_grad[o:o + n].copy_(p.grad.reshape(-1))
                 p.grad = None
         if self.world > 1:
             out = torch.empty(u.shard_numel, dtype=torch.float32, device=self.device)

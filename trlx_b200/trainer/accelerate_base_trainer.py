@@ -218,6 +218,7 @@ class AccelerateRLTrainer(BaseRLTrainer):
             kwargs.setdefault("grad_clip", self.config.train.parallel.grad_clip)
             kwargs.setdefault("process_group", self.runtime.dp_group)
             kwargs.setdefault("zero_stage", self.config.train.parallel.zero_stage)
+            kwargs.setdefault("bucket_mb", self.config.train.parallel.bucket_mb)
         params = [p for p in self.model.parameters() if p.requires_grad]
         self.zero3 = None
         rt = self.runtime
