@@ -432,3 +432,78 @@ def test_zero3_parameter_partitioning_matches_replicated_training(tmp_path):
         torch.testing.assert_close(got[1]["full"][k], v, atol=1e-5, rtol=1e-4, msg=k)
     assert torch.equal(got[0]["gen"], ref[0]["gen"])
     assert os.path.exists(tmp_path / "hf3" / "config.json")
+
+
+# ---- tensor x pipeline parallelism with sequence parallelism ---------------------------------------------------------------------
+def _tp_pp_sp_job(rank, world):
+    """4 ranks = TP 2 x PP 2, sequence parallel on: stage boundaries carry each TP rank's sequence shard."""
+    import copy
+
+    from trlx_b200.nn.arch import spec_from_hf_config
+    from trlx_b200.nn.transformer import CausalLM
+    from trlx_b200.parallel import pipeline_parallel as pp
+    from trlx_b200.parallel.tensor_parallel import allreduce_sequence_parallel_grads, apply_tensor_parallel
+
+    tp_size, pp_size = 2, 2
+    pp_rank, tp_rank = rank // tp_size, rank % tp_size
+    tp_groups = [dist.new_group([s * tp_size + t for t in range(tp_size)]) for s in range(pp_size)]
+    pp_groups = [dist.new_group([s * tp_size + t for s in range(pp_size)]) for t in range(tp_size)]
+    tp_group, pp_group = tp_groups[pp_rank], pp_groups[tp_rank]
+
+    torch.manual_seed(0)
+    spec = spec_from_hf_config(dict(model_type="gpt2", vocab_size=61, n_embd=32, n_layer=4, n_head=4, n_positions=64,
+                                    tie_word_embeddings=False))
+    full = CausalLM(spec).float()
+    staged = copy.deepcopy(full)
+    tpc = apply_tensor_parallel(staged, tp_group, tp_rank, tp_size, sequence_parallel=True)
+    stage = pp.apply_pipeline_parallel(staged, pp_group, pp_rank, pp_size)
+    g = torch.Generator().manual_seed(1)
+    mbs = []
+    for i in range(4):
+        T = 8 if i % 2 == 0 else 6  # even lengths: shardable over TP = 2
+        ids = torch.randint(0, 61, (2, T), generator=g)
+        mbs.append(dict(input_ids=ids, attention_mask=torch.ones_like(ids), labels=ids))
+    ref_losses = []
+    for mb in mbs:
+        out = full(**mb)
+        out.loss.backward()
+        ref_losses.append(out.loss.detach())
+    ref_ln = full.transformer.h[stage.lo].norm1.weight.grad.clone()
+    ref_down = full.transformer.h[stage.lo].mlp.down.weight.grad.clone()
+
+    boundary_shapes = []
+    orig_exchange = pp._exchange
+
+    def spy(st, send_next=None, send_prev=None, recv_prev_shape=None, recv_next_shape=None, **kw):
+        for sh in (recv_prev_shape, recv_next_shape):
+            if sh is not None:
+                boundary_shapes.append(tuple(sh))
+        return orig_exchange(st, send_next=send_next, send_prev=send_prev, recv_prev_shape=recv_prev_shape,
+                             recv_next_shape=recv_next_shape, **kw)
+
+    pp._exchange = spy
+
+    def loss_fn(mb):
+        out = staged(**mb)
+        return out.loss, {"loss": out.loss.detach()}
+
+    stats = pp.run_1f1b(stage, mbs, loss_fn, torch.device("cpu"))
+    pp._exchange = orig_exchange
+    allreduce_sequence_parallel_grads(staged, tp_group)
+    shared = pp.broadcast_stats(stage, {"loss": sum(s["loss"] for s in stats) / len(mbs)} if stage.last else None, torch.device("cpu"))
+    blk = staged.transformer.h[stage.lo]
+    f = ref_down.shape[1] // tp_size
+    return dict(mean_loss=shared["loss"], ref_mean=sum(ref_losses) / len(ref_losses),
+                ln_err=(blk.norm1.weight.grad - ref_ln).abs().max().item(),
+                down_err=(blk.mlp.down.weight.grad - ref_down[:, tp_rank * f:(tp_rank + 1) * f]).abs().max().item(),
+                shapes=boundary_shapes, sp=tpc.sequence_parallel)
+
+
+def test_tensor_pipeline_sequence_parallel_matches_single_rank():
+    res = run_distributed(_tp_pp_sp_job, 4)
+    for r in res:
+        assert r["sp"]
+        torch.testing.assert_close(r["mean_loss"], r["ref_mean"], atol=1e-5, rtol=1e-5)
+        assert r["ln_err"] < 2e-5 and r["down_err"] < 2e-5, r
+        # every boundary tensor is a sequence SHARD: T / tp positions, not T
+        assert r["shapes"] and all(sh[1] in (4, 3) for sh in r["shapes"]), r["shapes"]

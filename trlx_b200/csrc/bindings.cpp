@@ -100,6 +100,7 @@ int b200_gemm_stage_scatter_bf16(const void*, const void*, void* const*, int, in
                                  const void*, cudaStream_t);
 int b200_rs_finalize(const float*, const void*, const void*, void*, long long, int, long long, long long, long long,
                      cudaStream_t);
+int b200_umma_probe(int, int, int, int, long long*, cudaStream_t);
 int b200_decode_mega_make_map(void*, const void*, long long, long long, long long);
 int b200_decode_mega_layer_bytes();
 int b200_decode_mega_stages(int, int);
@@ -948,6 +949,12 @@ void decode_mega(Tensor& x, Tensor& a, Tensor& mid, const Tensor& block_table, c
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.def("umma_probe", [](int64_t M, int64_t N, int64_t n_mma, int64_t nacc) {
+    Tensor out = torch::zeros({2}, torch::TensorOptions().dtype(torch::kLong).device(torch::kCUDA));
+    check(b200_umma_probe((int)M, (int)N, (int)n_mma, (int)nacc, reinterpret_cast<long long*>(out.data_ptr<int64_t>()), stream()),
+          "umma_probe");
+    return out;
+  });
   m.def("decode_mega_build", &decode_mega_build);
   m.def("decode_mega", &decode_mega, py::arg("x"), py::arg("a"), py::arg("mid"), py::arg("block_table"), py::arg("seq_lens"),
         py::arg("table"), py::arg("maps"), py::arg("nh"), py::arg("L"), py::arg("act"), py::arg("rms"), py::arg("eps"),

@@ -90,11 +90,13 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     (BUILD / "ptxas.log").write_text("\n".join(logs))
 
     lib_dirs = cpp_extension.library_paths(device_type="cuda")
-    link = ["g++", "-shared", "-o", TARGET, *objs]
+    tmp_target = TARGET.with_suffix(".so.tmp")  # linked aside and renamed: a concurrent snapshot never sees a half-written library
+    link = ["g++", "-shared", "-o", tmp_target, *objs]
     for d in lib_dirs:
         link += [f"-L{d}", f"-Wl,-rpath,{d}"]
     link += ["-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch", "-ltorch_python", "-lcudart"]
     _run(link, verbose)
+    os.replace(tmp_target, TARGET)
     stamp.write_text(digest)
     return TARGET
 

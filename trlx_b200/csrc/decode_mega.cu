@@ -166,13 +166,13 @@ __global__ void __launch_bounds__(DM_THREADS, 1) decode_mega_kernel(const DmPara
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer: weight tiles in schedule order
     if (lane == 0) {
-      uint32_t it = 0;
+      int s = 0;
+      uint32_t ph = 0;   // ring position / pass parity kept incrementally (a runtime `%` / `/` per k-block is ~150 cycles of ALU)
       auto load = [&](const CUtensorMap* m, int row, int kb) {
-        const int s = it % stages;
-        mbar_wait(&empty_bar[s], ((it / stages) & 1) ^ 1);
+        mbar_wait(&empty_bar[s], ph ^ 1);
         mbar_arrive_expect_tx(&full_bar[s], DM_WTILE);
         tma_load_2d(ring + (size_t)s * DM_WTILE, m, &full_bar[s], kb * DM_BK, row);
-        ++it;
+        if (++s == stages) { s = 0; ph ^= 1; }
       };
       for (int l = 0; l < p.L; ++l) {
         const CUtensorMap* m = p.maps + (size_t)l * 4;
@@ -191,22 +191,23 @@ __global__ void __launch_bounds__(DM_THREADS, 1) decode_mega_kernel(const DmPara
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc(1, 1, DM_TM, DM_ROWS);
-      uint32_t it = 0, tc = 0, fills = 0;
-      const uint32_t act_addr = smem_u32(act_s);
+      uint32_t tc = 0, fills = 0, ph = 0;
+      int s = 0;
+      const uint32_t act_addr = smem_u32(act_s), ring_addr = smem_u32(ring);
       auto tile = [&](int nkb) {
         const uint32_t slot = tc % DM_SLOTS;
         mbar_wait(&tempty_bar[slot], ((tc / DM_SLOTS) & 1) ^ 1);
         tc_fence_after_sync();
         const uint32_t tacc = tmem_base + slot * DM_SLOT_COLS;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % stages;
-          mbar_wait(&full_bar[s], (it / stages) & 1);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full_bar[s], ph);
           tc_fence_after_sync();
-          const uint64_t da = umma_desc_k_sw128(smem_u32(ring + (size_t)s * DM_WTILE));
+          const uint64_t da = umma_desc_k_sw128(ring_addr + (uint32_t)s * DM_WTILE);
           const uint64_t db = umma_desc_k_sw128(act_addr + (uint32_t)kb * DM_ATILE);
 #pragma unroll
           for (int k = 0; k < DM_BK / 16; ++k) umma_bf16(tacc + k * DM_ROWS, da + 2 * k, db + 2 * k, idesc, kb > 0 ? 1u : 0u);
           umma_commit(&empty_bar[s]);
+          if (++s == stages) { s = 0; ph ^= 1; }
         }
         umma_commit(&tfull_bar[slot]);
         ++tc;

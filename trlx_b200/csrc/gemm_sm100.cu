@@ -111,6 +111,13 @@ struct LMHeadEpilogue {
   int n_tiles;
 };
 
+// Ring-buffer position kept incrementally: `it % stages` / `(it / stages) & 1` with a run-time `stages` cost two integer
+// divisions (~150 cycles of dependent ALU work) per k-block in the single producer / MMA-issuer threads — more than the
+// tensor-core time of a narrow tile's k-block.
+__device__ __forceinline__ void ring_next(int& s, uint32_t& phase, int stages) {
+  if (++s == stages) { s = 0; phase ^= 1u; }
+}
+
 __device__ __forceinline__ float apply_act(float x, int act) {
   switch (act) {
     case ACT_GELU_TANH: return gelu_tanh(x);
@@ -620,22 +627,25 @@ gemm_tn_kernel(const __grid_constant__ MapArray maps_a, const __grid_constant__ 
   if (warp == 0) {
     if (lane == 0) {
       uint32_t it = 0;  // k-block counter across all of this CTA's tiles (ring position)
+      int rs = 0;
+      uint32_t rph = 0;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
         const int tile = w % total_tiles, split = w / total_tiles;
         const int kb_lo = split * kb_per, kb_hi = min(nkb, kb_lo + kb_per);
         const int m0 = (((tile % m_tiles) + ar.m_rot) % m_tiles) * TBM, n0 = (tile / m_tiles) * BN;
         if (ar.flags) {  // the shard holding these rows has landed in the local gathered buffer
           const uint32_t* f = ar.flags + m0 / ar.rows_per_flag;
-          while (ld_acquire_sys(f) != ar.epoch) {}
+          while (ld_relaxed_sys(f) != ar.epoch) { __nanosleep(32); }   // relaxed polls + one fence (no CCTL.IVALL per poll)
+          fence_acq_rel_sys();
           __threadfence();
         }
         // which peer's copy of A holds this M-tile (all-gather -> GEMM); plain GEMMs have a single map
         const int a_map = m0 / rows_per_map;
         const int a_row = m0 - a_map * rows_per_map;
         const CUtensorMap* map_a_ptr = &maps_a.m[a_map];
-        for (int kb = kb_lo; kb < kb_hi; ++kb, ++it) {
-          const int s = it % stages;
-          const uint32_t phase = (it / stages) & 1;
+        for (int kb = kb_lo; kb < kb_hi; ++kb, ++it, ring_next(rs, rph, stages)) {
+          const int s = rs;
+          const uint32_t phase = rph;
           uint8_t* a_dst = smem + (size_t)s * STAGE_BYTES;
           uint8_t* b_dst = a_dst + A_BYTES;
           const bool b_inflight = it < b_pre;  // armed + B issued before the PDL wait (first pass over fresh stages)
@@ -661,7 +671,8 @@ gemm_tn_kernel(const __grid_constant__ MapArray maps_a, const __grid_constant__ 
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = FP8 ? umma_idesc(0, 0, TBM, BN) : umma_idesc(1, 1, TBM, BN, AMN, BMN);  // fp8: e4m3 x e4m3
-      uint32_t it = 0, tcount = 0;
+      uint32_t it = 0, tcount = 0, rph = 0;
+      int rs = 0;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tcount) {
         const int split = w / total_tiles;
         const int kb_lo = split * kb_per, kb_hi = min(nkb, kb_lo + kb_per);
@@ -669,9 +680,9 @@ gemm_tn_kernel(const __grid_constant__ MapArray maps_a, const __grid_constant__ 
         mbar_wait(&tmem_empty_bar[as], aphase ^ 1);  // epilogue drained this accumulator buffer
         tc_fence_after_sync();
         const uint32_t tmem_acc = tmem_base + as * ACC_COLS;
-        for (int kb = kb_lo; kb < kb_hi; ++kb, ++it) {
-          const int s = it % stages;
-          const uint32_t phase = (it / stages) & 1;
+        for (int kb = kb_lo; kb < kb_hi; ++kb, ++it, ring_next(rs, rph, stages)) {
+          const int s = rs;
+          const uint32_t phase = rph;
           mbar_wait(&full_bar[s], phase);
           tc_fence_after_sync();
           const uint32_t a_addr = smem_u32(smem + (size_t)s * STAGE_BYTES);
@@ -794,11 +805,13 @@ gemm_csk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = kb_lo, it = 0; kb < kb_hi; ++kb, ++it) {
-        const int s = it % stages;
+      int rs = 0;
+      uint32_t rph = 0;
+      for (int kb = kb_lo, it = 0; kb < kb_hi; ++kb, ++it, ring_next(rs, rph, stages)) {
+        const int s = rs;
         uint8_t* a_dst = smem + (size_t)s * STAGE_BYTES;
         if (it >= b_pre) {
-          mbar_wait(&empty_bar[s], ((it / stages) & 1) ^ 1);
+          mbar_wait(&empty_bar[s], rph ^ 1);
           mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
           tma_load_2d(a_dst + A_BYTES, &map_b, &full_bar[s], kb * BK, n0);
         }
@@ -811,9 +824,11 @@ gemm_csk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc(1, 1, BM, BN);
-      for (int kb = kb_lo, it = 0; kb < kb_hi; ++kb, ++it) {
-        const int s = it % stages;
-        mbar_wait(&full_bar[s], (it / stages) & 1);
+      int rs = 0;
+      uint32_t rph = 0;
+      for (int kb = kb_lo, it = 0; kb < kb_hi; ++kb, ++it, ring_next(rs, rph, stages)) {
+        const int s = rs;
+        mbar_wait(&full_bar[s], rph);
         tc_fence_after_sync();
         const uint32_t a_addr = smem_u32(smem + (size_t)s * STAGE_BYTES);
         const uint64_t da = umma_desc_k_sw128(a_addr), db = umma_desc_k_sw128(a_addr + A_BYTES);
@@ -942,18 +957,20 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
   if (warp == 0) {
     if (lane == 0) {
-      uint32_t it = 0;
+      uint32_t it = 0, rph = 0;
+      int rs = 0;
       for (int tile = pair; tile < total_tiles; tile += n_pairs) {
         const int m0 = (((tile % m_tiles) + ar.m_rot) % m_tiles) * 2 * BM + (int)cta * BM;  // this CTA's 128 rows of A
         const int n0 = (tile / m_tiles) * BN + (int)cta * HB;                               // ... and its half of the B tile
         if (ar.flags) {  // all-gather -> GEMM: the shard holding these rows has landed (see AReady)
           const uint32_t* f = ar.flags + m0 / ar.rows_per_flag;
-          while (ld_acquire_sys(f) != ar.epoch) {}
+          while (ld_relaxed_sys(f) != ar.epoch) { __nanosleep(32); }   // relaxed polls + one fence (no CCTL.IVALL per poll)
+          fence_acq_rel_sys();
           __threadfence();
         }
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % stages;
-          const uint32_t phase = (it / stages) & 1;
+        for (int kb = 0; kb < nkb; ++kb, ++it, ring_next(rs, rph, stages)) {
+          const int s = rs;
+          const uint32_t phase = rph;
           mbar_wait(&empty_bar[s], phase ^ 1);
           uint8_t* a_dst = smem + (size_t)s * STAGE_BYTES;
           if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
@@ -965,15 +982,16 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   } else if (warp == 1) {
     if (lane == 0 && leader) {
       constexpr uint32_t idesc = umma_idesc(1, 1, 2 * BM, BN);
-      uint32_t it = 0, tcount = 0;
+      uint32_t it = 0, tcount = 0, rph = 0;
+      int rs = 0;
       for (int tile = pair; tile < total_tiles; tile += n_pairs, ++tcount) {
         const uint32_t as = tcount & 1, aphase = (tcount >> 1) & 1;
         mbar_wait(&tmem_empty_bar[as], aphase ^ 1);  // both CTAs' epilogues drained this accumulator buffer
         tc_fence_after_sync();
         const uint32_t tmem_acc = tmem_base + as * ACC_COLS;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % stages;
-          const uint32_t phase = (it / stages) & 1;
+        for (int kb = 0; kb < nkb; ++kb, ++it, ring_next(rs, rph, stages)) {
+          const int s = rs;
+          const uint32_t phase = rph;
           mbar_wait(&full_bar[s], phase);
           tc_fence_after_sync();
           const uint32_t a_addr = smem_u32(smem + (size_t)s * STAGE_BYTES);

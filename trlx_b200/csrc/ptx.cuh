@@ -236,6 +236,14 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// Polling form: relaxed loads in the spin loop, ONE acquire fence after it (an acquire on every iteration makes ptxas emit an
+// L1 invalidate, CCTL.IVALL, per poll — measured to starve the load/store path of everything else running on the SM)
+__device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 __device__ __forceinline__ uint32_t atom_add_release_sys(uint32_t* p, uint32_t v) {
   uint32_t old;
   asm volatile("atom.add.release.sys.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");

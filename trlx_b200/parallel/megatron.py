@@ -38,16 +38,11 @@ class MegatronMixin:
             except (KeyError, ValueError, TypeError, OSError) as err:
                 logger.warning(f"megatron_cfg: trainer section not applied ({err})")
         par = config.train.parallel
-        if int(getattr(par, "tensor_parallel", 1) or 1) > 1 and bool(getattr(par, "sequence_parallel", False)) and \
-                int(getattr(par, "pipeline_parallel", 1) or 1) == 1:
+        if int(getattr(par, "tensor_parallel", 1) or 1) > 1 and bool(getattr(par, "sequence_parallel", False)):
             # with sequence parallelism the activation at the branch point is a per-rank sequence shard whose layout depends on
             # the length of the forward that produced it: it cannot be stored per rollout and re-sliced per minibatch
             config = config.evolve(train=dict(trainer_kwargs=dict(cache_trunk=False)))
         pp = int(getattr(config.train.parallel, "pipeline_parallel", 1) or 1)
-        if pp > 1 and bool(getattr(config.train.parallel, "sequence_parallel", False)):
-            # the stage-to-stage relay exchanges full-length activations; sequence shards would need a gather at every boundary
-            logger.warning("sequence parallelism is not combined with pipeline parallelism: running TP x PP without it")
-            config = config.evolve(train=dict(parallel=dict(sequence_parallel=False)))
         if pp > 1:
             if config.model.model_arch_type == "seq2seq":
                 raise NotImplementedError("pipeline parallelism covers decoder-only models")

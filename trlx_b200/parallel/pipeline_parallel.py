@@ -121,7 +121,13 @@ class PipelineStage:
         ref = inputs_embeds if inputs_embeds is not None else input_ids
         B, T = ref.shape[0], ref.shape[1]
         device, dtype = ref.device, self.param_dtype()
-        hshape = (B, T, spec.hidden_size)
+        oshape = (B, T, spec.hidden_size)
+        # with sequence parallelism the residual stream between blocks — and therefore every stage boundary — is this tensor-
+        # parallel rank's 1 / tp slice of the sequence: each TP rank relays its own shard to the same TP rank of the next stage
+        # (the reference runs TP x PP with SP on, configs/nemo_configs/megatron_65b.yaml:47-50,80)
+        tpc = getattr(lm, "_tp_context", None)
+        sp_on = tpc is not None and tpc.sp
+        hshape = (B, T // tpc.size, spec.hidden_size) if sp_on else oshape
         if self.mode == "probe":
             self.probe_shape = hshape
             raise StageBoundary()
@@ -181,7 +187,7 @@ class PipelineStage:
                 phantom = _SendToNext.apply(x, self)
             else:
                 dist.send(x.contiguous(), dst=self.next_global, group=self.group)
-            x = torch.empty(hshape, dtype=dtype, device=device)
+            x = torch.empty(oshape, dtype=dtype, device=device)
             logits = torch.empty((B, T, spec.vocab_size), dtype=dtype, device=device) if compute_logits else None
             self._broadcast_outputs(x, logits, compute_logits)
             if phantom is not None:  # ties the (complete, but constant) outputs to this stage's graph

@@ -339,6 +339,7 @@ def apply_tensor_parallel(model, group, rank: int, size: int, sequence_parallel:
             blocks += list(branch.decoder_blocks)
     for b in blocks:
         shard_block(b, tp)
+    lm._tp_context = tp  # pipeline stages size their boundary activations by the sequence-parallel layout
     if sequence_parallel:
         _install_sequence_parallel(lm, tp)
         for extra in ("frozen_head", "v_head"):
