@@ -108,3 +108,32 @@ def test_seq2seq_ppo_on_gpu(tmp_path):
     trainer = trlx.train(reward_fn=lambda samples, **kw: [float(len(s)) for s in samples], prompts=PROMPTS, eval_prompts=["hi"] * 2,
                          config=cfg)
     assert trainer.iter_count == 4
+
+
+def test_bf16_gradient_accumulation_error_is_bounded():
+    """`.grad` tensors are views of the optimizer's flat bf16 buffer, so micro-batch accumulation rounds to bf16 after every
+    backward.  Over 8 micro-batches the accumulated gradient must stay within bf16 rounding noise of an fp32 accumulation of
+    the same per-micro-batch gradients (relative L2 error and cosine per tensor)."""
+    from trlx_b200.parallel.optim import FusedAdamW
+
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(256, 512), torch.nn.GELU(), torch.nn.Linear(512, 256), torch.nn.GELU(),
+                              torch.nn.Linear(256, 16)).cuda().to(torch.bfloat16)
+    opt = FusedAdamW(net.parameters(), lr=1e-3).prepare()
+    assert opt._flat is not None and all(p.grad.dtype == torch.bfloat16 for p in net.parameters())
+    fp32_acc = [torch.zeros_like(p, dtype=torch.float32) for p in net.parameters()]
+    n_mb = 8
+    for i in range(n_mb):
+        x = torch.randn(64, 256, device="cuda").to(torch.bfloat16)
+        y = torch.randn(64, 16, device="cuda")
+        loss = (net(x).float() - y).pow(2).mean() / n_mb
+        # per-micro-batch gradient in fp32 (autograd.grad does not touch .grad), accumulated in fp32 ...
+        gs = torch.autograd.grad(loss, list(net.parameters()), retain_graph=True)
+        for acc, g in zip(fp32_acc, gs):
+            acc += g.float()
+        loss.backward()  # ... while .grad accumulates in the flat bf16 buffer
+    for p, ref in zip(net.parameters(), fp32_acc):
+        got = p.grad.float()
+        rel = (got - ref).norm() / ref.norm().clamp_min(1e-12)
+        cos = torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0)
+        assert rel < 1.5e-2 and cos > 0.9999, (tuple(p.shape), rel.item(), cos.item())

@@ -27,6 +27,9 @@ int b200_embed_bf16(const long long*, const int*, const void*, const void*, int,
 int b200_decode_attention_bf16(const void*, void*, void*, const int*, const int*, const int*, void*, int, int, int, int, int,
                                int, float, int, float, int, const float*, int, cudaStream_t);
 int b200_rowdot_bf16(const void*, const void*, const void*, float*, int, int, long long, cudaStream_t);
+int b200_ilql_sample(const float*, const float*, const float*, const float*, long long, int, int, float, int, float,
+                     unsigned long long, const long long*, const int*, const unsigned char*, int, int, const long long*, long long*,
+                     cudaStream_t);
 int b200_sample_filtered(const float*, long long, int, int, int, float, float, unsigned long long, const long long*, const int*,
                          int, int, long long*, float*, cudaStream_t);
 int b200_decode_step(const long long*, const float*, const float*, const float*, int*, int, int, long long, long long,
@@ -443,6 +446,40 @@ std::vector<Tensor> sample_filtered(const Tensor& logits, int64_t V, int64_t top
                              (long long*)tok.data_ptr<int64_t>(), lp.data_ptr<float>(), stream()),
         "sample_filtered");
   return {tok, lp};
+}
+
+// ILQL advantage-shifted sampling step: logits / q1 / q2 fp32 [B, >= V] sharing one row pitch, vs fp32 [B] -> tokens [B]
+Tensor ilql_sample(const Tensor& logits, const Tensor& q1, const OptTensor& q2, const Tensor& vs, int64_t V, double beta,
+                   int64_t top_k, double temperature, int64_t seed, const OptTensor& step, const OptTensor& seed_tensor,
+                   const OptTensor& logit_mask, const OptTensor& last_tokens) {
+  CHECK_F32(logits); CHECK_F32(q1); CHECK_F32(vs);
+  TORCH_CHECK(logits.dim() == 2 && logits.stride(1) == 1 && logits.size(1) >= V && q1.stride(0) == logits.stride(0) &&
+              q1.stride(1) == 1 && vs.is_contiguous() && vs.numel() == logits.size(0));
+  const float* q2p = nullptr;
+  if (q2.has_value()) { CHECK_F32(*q2); TORCH_CHECK(q2->stride(0) == logits.stride(0) && q2->stride(1) == 1); q2p = q2->data_ptr<float>(); }
+  c10::cuda::CUDAGuard guard(logits.device());
+  const int64_t B = logits.size(0);
+  Tensor tok = torch::empty({B}, logits.options().dtype(at::kLong));
+  const long long* seedp = nullptr;
+  if (seed_tensor.has_value()) { TORCH_CHECK(seed_tensor->scalar_type() == at::kLong && seed_tensor->is_cuda()); seedp = (const long long*)seed_tensor->data_ptr<int64_t>(); }
+  const int* sp = nullptr;
+  if (step.has_value()) { TORCH_CHECK(step->scalar_type() == at::kInt); sp = step->data_ptr<int>(); }
+  const unsigned char* mp = nullptr;
+  int mr = 0, mc = 0;
+  const long long* lastp = nullptr;
+  if (logit_mask.has_value()) {
+    TORCH_CHECK(logit_mask->is_cuda() && logit_mask->dim() == 2 && logit_mask->is_contiguous() &&
+                (logit_mask->scalar_type() == at::kBool || logit_mask->scalar_type() == at::kByte));
+    TORCH_CHECK(last_tokens.has_value() && last_tokens->scalar_type() == at::kLong && last_tokens->numel() == B);
+    mp = reinterpret_cast<const unsigned char*>(logit_mask->data_ptr());
+    mr = (int)logit_mask->size(0); mc = (int)logit_mask->size(1);
+    lastp = (const long long*)last_tokens->data_ptr<int64_t>();
+  }
+  check(b200_ilql_sample(logits.data_ptr<float>(), q1.data_ptr<float>(), q2p, vs.data_ptr<float>(), logits.stride(0), (int)B, (int)V,
+                         (float)beta, (int)top_k, (float)temperature, (unsigned long long)seed, seedp, sp, mp, mr, mc, lastp,
+                         (long long*)tok.data_ptr<int64_t>(), stream()),
+        "ilql_sample");
+  return tok;
 }
 
 Tensor norm(const Tensor& x, const Tensor& w, const OptTensor& b, double eps, bool rms, const OptTensor& out_) {
@@ -1019,6 +1056,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("rs_adamw_ag", &rs_adamw_ag);
   m.def("rs_adamw_ag_bucket", &rs_adamw_ag_bucket);
   m.def("rollout_rewards", &rollout_rewards);
+  m.def("ilql_sample", &ilql_sample, py::arg("logits"), py::arg("q1"), py::arg("q2") = py::none(), py::arg("vs"), py::arg("V"),
+        py::arg("beta"), py::arg("top_k"), py::arg("temperature"), py::arg("seed"), py::arg("step") = py::none(),
+        py::arg("seed_tensor") = py::none(), py::arg("logit_mask") = py::none(), py::arg("last_tokens") = py::none());
   m.def("sample_filtered", &sample_filtered, py::arg("logits"), py::arg("V"), py::arg("top_k"), py::arg("top_p"),
         py::arg("temperature"), py::arg("seed"), py::arg("step") = py::none(), py::arg("suppress_col") = -1,
         py::arg("suppress_until") = 0, py::arg("seed_tensor") = py::none());

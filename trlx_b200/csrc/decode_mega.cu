@@ -165,13 +165,18 @@ __global__ void __launch_bounds__(DM_THREADS, 1) decode_mega_kernel(const DmPara
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer: weight tiles in schedule order
-    if (lane == 0) {
+    // (the loop is warp-uniform, the elected lane issues: a single-thread loop costs ~100 cycles per UTMALDG / UTCHMMA in
+    // register-to-uniform-register marshalling, see gemm_sm100.cu)
+    {
       int s = 0;
       uint32_t ph = 0;   // ring position / pass parity kept incrementally (a runtime `%` / `/` per k-block is ~150 cycles of ALU)
       auto load = [&](const CUtensorMap* m, int row, int kb) {
         mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_arrive_expect_tx(&full_bar[s], DM_WTILE);
-        tma_load_2d(ring + (size_t)s * DM_WTILE, m, &full_bar[s], kb * DM_BK, row);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&full_bar[s], DM_WTILE);
+          tma_load_2d(ring + (size_t)s * DM_WTILE, m, &full_bar[s], kb * DM_BK, row);
+        }
+        __syncwarp();
         if (++s == stages) { s = 0; ph ^= 1; }
       };
       for (int l = 0; l < p.L; ++l) {
@@ -188,8 +193,8 @@ __global__ void __launch_bounds__(DM_THREADS, 1) decode_mega_kernel(const DmPara
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (warp-uniform loop, elected lane issues)
+    {
       constexpr uint32_t idesc = umma_idesc(1, 1, DM_TM, DM_ROWS);
       uint32_t tc = 0, fills = 0, ph = 0;
       int s = 0;
@@ -204,12 +209,15 @@ __global__ void __launch_bounds__(DM_THREADS, 1) decode_mega_kernel(const DmPara
           tc_fence_after_sync();
           const uint64_t da = umma_desc_k_sw128(ring_addr + (uint32_t)s * DM_WTILE);
           const uint64_t db = umma_desc_k_sw128(act_addr + (uint32_t)kb * DM_ATILE);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < DM_BK / 16; ++k) umma_bf16(tacc + k * DM_ROWS, da + 2 * k, db + 2 * k, idesc, kb > 0 ? 1u : 0u);
-          umma_commit(&empty_bar[s]);
+            for (int k = 0; k < DM_BK / 16; ++k) umma_bf16(tacc + k * DM_ROWS, da + 2 * k, db + 2 * k, idesc, kb > 0 ? 1u : 0u);
+            umma_commit(&empty_bar[s]);
+            if (kb == nkb - 1) umma_commit(&tfull_bar[slot]);
+          }
+          __syncwarp();
           if (++s == stages) { s = 0; ph ^= 1; }
         }
-        umma_commit(&tfull_bar[slot]);
         ++tc;
       };
       auto wait_act = [&]() {

@@ -630,6 +630,122 @@ extern "C" int b200_sample_filtered(const float* logits, long long ld, int B, in
                             seed_ptr, step_ptr, suppress_col, suppress_until, tok_out, lp_out);
 }
 
+// ------------------------------------------------------------------------------------------------ ILQL advantage-shifted sampling
+// One decode step of the reference's ILQL sampler (trlx/models/modeling_ilql.py:360-412) on one row per block:
+//   pi_beta = log_softmax(mask(logits));  score = pi_beta + beta * (min(q1, q2) - v);  keep the top-k scores;
+//   token ~ softmax(score / T)   (T == 0: argmax).   logits / q1 / q2: fp32 [B, >= V] with row pitch ld; q2 may be null.
+// logit_mask: optional uint8 table [mask_rows, mask_cols]; entry [last_token, col] != 0 forbids `col` after `last_token`.
+__global__ void __launch_bounds__(1024)
+ilql_sample_kernel(const float* __restrict__ logits, const float* __restrict__ q1, const float* __restrict__ q2,
+                   const float* __restrict__ vs, long long ld, int V, float beta, int top_k, float inv_temp,
+                   unsigned long long seed, const long long* __restrict__ seed_ptr, const int* __restrict__ step_ptr,
+                   const unsigned char* __restrict__ logit_mask, int mask_rows, int mask_cols,
+                   const long long* __restrict__ last_tokens, long long* __restrict__ tok_out) {
+  griddep_wait();
+  griddep_launch();
+  __shared__ float red_a[32], red_b[32];
+  __shared__ int red_i[32];
+  __shared__ int hist_c[256];
+  __shared__ uint32_t sh_prefix;
+  __shared__ int sh_kleft;
+  const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const float* x = logits + (size_t)row * ld;
+  const float* a1 = q1 + (size_t)row * ld;
+  const float* a2 = q2 ? q2 + (size_t)row * ld : nullptr;
+  const float v = vs[row];
+  const int step = step_ptr ? *step_ptr : 0;
+  const unsigned long long sd = seed + (seed_ptr ? (unsigned long long)(*seed_ptr) : 0ull) + 0x632BE59BD9B4E019ull * (unsigned long long)(step + 1);
+  const unsigned char* mrow = nullptr;
+  if (logit_mask) {
+    const long long last = last_tokens[row];
+    if (last >= 0 && last < mask_rows) mrow = logit_mask + (size_t)last * mask_cols;
+  }
+  auto lg = [&](int i) { return (mrow && i < mask_cols && mrow[i]) ? -INFINITY : x[i]; };
+  // ---- log-softmax normaliser of the (masked) behaviour policy
+  float mx = -INFINITY;
+  for (int i = tid; i < V; i += blockDim.x) mx = fmaxf(mx, lg(i));
+  mx = warp_max(mx);
+  if (lane == 0) red_b[warp] = mx;
+  __syncthreads();
+  mx = -INFINITY;
+  for (int i = 0; i < nw; ++i) mx = fmaxf(mx, red_b[i]);
+  float z = 0.f;
+  for (int i = tid; i < V; i += blockDim.x) z += __expf(lg(i) - mx);
+  z = warp_sum(z);
+  __syncthreads();
+  if (lane == 0) red_a[warp] = z;
+  __syncthreads();
+  z = 0.f;
+  for (int i = 0; i < nw; ++i) z += red_a[i];
+  const float lse = mx + __logf(z);
+  auto score = [&](int i) {
+    const float q = a2 ? fminf(a1[i], a2[i]) : a1[i];
+    return (lg(i) - lse) + beta * (q - v);
+  };
+  // ---- top-k on the shifted scores (exact: 4-pass radix selection of the k-th largest key)
+  uint32_t kth = 0u;
+  if (top_k > 0 && top_k < V) {
+    if (tid == 0) { sh_prefix = 0u; sh_kleft = top_k; }
+    for (int level = 0; level < 4; ++level) {
+      const int shift = 24 - 8 * level;
+      if (tid < 256) hist_c[tid] = 0;
+      __syncthreads();
+      const uint32_t prefix = sh_prefix;
+      const uint32_t pmask = level == 0 ? 0u : (0xFFFFFFFFu << (shift + 8));
+      for (int i = tid; i < V; i += blockDim.x) {
+        const uint32_t key = float_key(score(i));
+        if ((key & pmask) == prefix) atomicAdd(&hist_c[(key >> shift) & 255u], 1);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int left = sh_kleft, b = 255;
+        for (; b > 0; --b) {
+          if (hist_c[b] >= left) break;
+          left -= hist_c[b];
+        }
+        sh_kleft = left;
+        sh_prefix = prefix | ((uint32_t)b << shift);
+      }
+      __syncthreads();
+    }
+    kth = sh_prefix;
+  }
+  // ---- draw
+  float best = -INFINITY;
+  int best_i = 0x7fffffff;
+  for (int i = tid; i < V; i += blockDim.x) {
+    const float sc = score(i);
+    if (float_key(sc) < kth || sc == -INFINITY) continue;
+    float key = sc;
+    if (inv_temp > 0.f) key = sc * inv_temp - __logf(-__logf(samp_uniform(sd, (unsigned)row, (unsigned)i)));
+    if (key > best || (key == best && i < best_i)) { best = key; best_i = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+    if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
+  }
+  __syncthreads();
+  if (lane == 0) { red_a[warp] = best; red_i[warp] = best_i; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < nw; ++w)
+      if (red_a[w] > best || (red_a[w] == best && red_i[w] < best_i)) { best = red_a[w]; best_i = red_i[w]; }
+    tok_out[row] = best_i == 0x7fffffff ? 0 : best_i;
+  }
+}
+
+extern "C" int b200_ilql_sample(const float* logits, const float* q1, const float* q2, const float* vs, long long ld, int B, int V,
+                                float beta, int top_k, float temperature, unsigned long long seed, const long long* seed_ptr,
+                                const int* step_ptr, const unsigned char* logit_mask, int mask_rows, int mask_cols,
+                                const long long* last_tokens, long long* tok_out, cudaStream_t stream) {
+  if (B <= 0) return 0;
+  const float inv_temp = temperature > 0.f ? 1.f / temperature : 0.f;
+  return (int)launch_kernel(ilql_sample_kernel, dim3(B), dim3(1024), 0, stream, logits, q1, q2, vs, ld, V, beta, top_k, inv_temp,
+                            seed, seed_ptr, step_ptr, logit_mask, mask_rows, mask_cols, last_tokens, tok_out);
+}
+
 extern "C" int b200_rowdot_bf16(const void* x, const void* w, const void* bias, float* out, int M, int K, long long ldx,
                                 cudaStream_t stream) {
   if (M <= 0) return 0;

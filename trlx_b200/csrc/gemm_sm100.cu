@@ -609,13 +609,16 @@ gemm_tn_kernel(const __grid_constant__ MapArray maps_a, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
   uint32_t b_pre = 0;  // leading k-blocks of this CTA's first tile whose B boxes are already in flight (producer thread only)
   if constexpr (!BMN) {
-    if (ar.b_static && warp == 0 && lane == 0 && (int)blockIdx.x < total_work) {
+    if (ar.b_static && warp == 0 && (int)blockIdx.x < total_work) {   // whole warp: see the note on warp-uniform issue loops below
       const int tile = blockIdx.x % total_tiles, split = blockIdx.x / total_tiles;
       const int kb_lo = split * kb_per, kb_hi = min(nkb, kb_lo + kb_per);
       const int n0 = (tile / m_tiles) * BN;
       for (int kb = kb_lo; kb < kb_hi && (int)b_pre < stages; ++kb, ++b_pre) {
-        mbar_arrive_expect_tx(&full_bar[b_pre], STAGE_BYTES);
-        tma_load_2d(smem + (size_t)b_pre * STAGE_BYTES + A_BYTES, &map_b, &full_bar[b_pre], kb * BKE, n0);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&full_bar[b_pre], STAGE_BYTES);
+          tma_load_2d(smem + (size_t)b_pre * STAGE_BYTES + A_BYTES, &map_b, &full_bar[b_pre], kb * BKE, n0);
+        }
+        __syncwarp();
       }
     }
   }
@@ -624,8 +627,14 @@ gemm_tn_kernel(const __grid_constant__ MapArray maps_a, const __grid_constant__ 
   griddep_wait();
   griddep_launch();
 
+  // The producer and MMA-issuer loops are executed by ALL 32 lanes of their warp; only the tcgen05 / TMA instructions sit
+  // under `elect_one()`.  When the whole loop ran in one thread (`if (lane == 0)`), every descriptor lived in that thread's
+  // vector registers and ptxas wrapped each UTCHMMA / UTMALDG (which take uniform registers) in an R2UR + ELECT + BRA.U.ANY
+  // "waterfall": ~103 cycles per MMA issue regardless of its shape (scripts/umma_probe.py) — more than the tensor-core time of
+  // any atom narrower than N = 256.  With warp-uniform control flow the operands stay in uniform registers and consecutive
+  // UTCHMMAs issue back to back.
   if (warp == 0) {
-    if (lane == 0) {
+    {
       uint32_t it = 0;  // k-block counter across all of this CTA's tiles (ring position)
       int rs = 0;
       uint32_t rph = 0;
@@ -634,10 +643,13 @@ gemm_tn_kernel(const __grid_constant__ MapArray maps_a, const __grid_constant__ 
         const int kb_lo = split * kb_per, kb_hi = min(nkb, kb_lo + kb_per);
         const int m0 = (((tile % m_tiles) + ar.m_rot) % m_tiles) * TBM, n0 = (tile / m_tiles) * BN;
         if (ar.flags) {  // the shard holding these rows has landed in the local gathered buffer
-          const uint32_t* f = ar.flags + m0 / ar.rows_per_flag;
-          while (ld_relaxed_sys(f) != ar.epoch) { __nanosleep(32); }   // relaxed polls + one fence (no CCTL.IVALL per poll)
-          fence_acq_rel_sys();
-          __threadfence();
+          if (lane == 0) {
+            const uint32_t* f = ar.flags + m0 / ar.rows_per_flag;
+            while (ld_relaxed_sys(f) != ar.epoch) { __nanosleep(32); }   // relaxed polls + one fence (no CCTL.IVALL per poll)
+            fence_acq_rel_sys();
+            __threadfence();
+          }
+          __syncwarp();
         }
         // which peer's copy of A holds this M-tile (all-gather -> GEMM); plain GEMMs have a single map
         const int a_map = m0 / rows_per_map;
@@ -649,27 +661,28 @@ gemm_tn_kernel(const __grid_constant__ MapArray maps_a, const __grid_constant__ 
           uint8_t* a_dst = smem + (size_t)s * STAGE_BYTES;
           uint8_t* b_dst = a_dst + A_BYTES;
           const bool b_inflight = it < b_pre;  // armed + B issued before the PDL wait (first pass over fresh stages)
-          if (!b_inflight) {
-            mbar_wait(&empty_bar[s], phase ^ 1);
-            mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
-          }
-          if constexpr (AMN) {
+          if (!b_inflight) mbar_wait(&empty_bar[s], phase ^ 1);
+          if (elect_one()) {
+            if (!b_inflight) mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+            if constexpr (AMN) {
 #pragma unroll
-            for (int ch = 0; ch < TBM / 64; ++ch) tma_load_2d(a_dst + ch * MN_CHUNK, map_a_ptr, &full_bar[s], m0 + ch * 64, kb * BK);
-          } else {
-            tma_load_2d(a_dst, map_a_ptr, &full_bar[s], kb * BKE, a_row);
-          }
-          if constexpr (BMN) {
+              for (int ch = 0; ch < TBM / 64; ++ch) tma_load_2d(a_dst + ch * MN_CHUNK, map_a_ptr, &full_bar[s], m0 + ch * 64, kb * BK);
+            } else {
+              tma_load_2d(a_dst, map_a_ptr, &full_bar[s], kb * BKE, a_row);
+            }
+            if constexpr (BMN) {
 #pragma unroll
-            for (int ch = 0; ch < BN / 64; ++ch) tma_load_2d(b_dst + ch * MN_CHUNK, &map_b, &full_bar[s], n0 + ch * 64, kb * BK);
-          } else {
-            if (!b_inflight) tma_load_2d(b_dst, &map_b, &full_bar[s], kb * BKE, n0);
+              for (int ch = 0; ch < BN / 64; ++ch) tma_load_2d(b_dst + ch * MN_CHUNK, &map_b, &full_bar[s], n0 + ch * 64, kb * BK);
+            } else {
+              if (!b_inflight) tma_load_2d(b_dst, &map_b, &full_bar[s], kb * BKE, n0);
+            }
           }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = FP8 ? umma_idesc(0, 0, TBM, BN) : umma_idesc(1, 1, TBM, BN, AMN, BMN);  // fp8: e4m3 x e4m3
       uint32_t it = 0, tcount = 0, rph = 0;
       int rs = 0;
@@ -691,14 +704,17 @@ gemm_tn_kernel(const __grid_constant__ MapArray maps_a, const __grid_constant__ 
           // one UMMA consumes 16 k: K-major = 32 bytes inside the 128-byte swizzle row (+2 in the addr>>4 field);
           // MN-major = 16 rows of 128 bytes = 2048 bytes (+128)
           constexpr uint32_t A_STEP = AMN ? (16 * 128) >> 4 : 2, B_STEP = BMN ? (16 * 128) >> 4 : 2;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            if constexpr (FP8) umma_fp8(tmem_acc, da + 2 * k, db + 2 * k, idesc, (kb > kb_lo || k > 0) ? 1u : 0u);
-            else umma_bf16(tmem_acc, da + A_STEP * k, db + B_STEP * k, idesc, (kb > kb_lo || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              if constexpr (FP8) umma_fp8(tmem_acc, da + 2 * k, db + 2 * k, idesc, (kb > kb_lo || k > 0) ? 1u : 0u);
+              else umma_bf16(tmem_acc, da + A_STEP * k, db + B_STEP * k, idesc, (kb > kb_lo || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[s]);
+            if (kb == kb_hi - 1) umma_commit(&tmem_full_bar[as]);   // same thread as the MMAs it tracks
           }
-          umma_commit(&empty_bar[s]);
+          __syncwarp();
         }
-        umma_commit(&tmem_full_bar[as]);
       }
     }
   } else {
@@ -794,35 +810,41 @@ gemm_csk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   int b_pre = 0;  // weight tiles already in flight when the PDL wait returns (see AReady::b_static)
-  if (b_static && warp == 0 && lane == 0) {
+  if (b_static && warp == 0) {   // warp-uniform loop, elected lane issues (see gemm_tn_kernel)
     for (int kb = kb_lo; kb < kb_hi && b_pre < stages; ++kb, ++b_pre) {
-      mbar_arrive_expect_tx(&full_bar[b_pre], STAGE_BYTES);
-      tma_load_2d(smem + (size_t)b_pre * STAGE_BYTES + A_BYTES, &map_b, &full_bar[b_pre], kb * BK, n0);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&full_bar[b_pre], STAGE_BYTES);
+        tma_load_2d(smem + (size_t)b_pre * STAGE_BYTES + A_BYTES, &map_b, &full_bar[b_pre], kb * BK, n0);
+      }
+      __syncwarp();
     }
   }
   griddep_wait();
   griddep_launch();
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       int rs = 0;
       uint32_t rph = 0;
       for (int kb = kb_lo, it = 0; kb < kb_hi; ++kb, ++it, ring_next(rs, rph, stages)) {
         const int s = rs;
         uint8_t* a_dst = smem + (size_t)s * STAGE_BYTES;
-        if (it >= b_pre) {
-          mbar_wait(&empty_bar[s], rph ^ 1);
-          mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
-          tma_load_2d(a_dst + A_BYTES, &map_b, &full_bar[s], kb * BK, n0);
+        if (it >= b_pre) mbar_wait(&empty_bar[s], rph ^ 1);
+        if (elect_one()) {
+          if (it >= b_pre) {
+            mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+            tma_load_2d(a_dst + A_BYTES, &map_b, &full_bar[s], kb * BK, n0);
+          }
+          tma_load_2d(a_dst, &map_a, &full_bar[s], kb * BK, 0);
         }
-        tma_load_2d(a_dst, &map_a, &full_bar[s], kb * BK, 0);
+        __syncwarp();
       }
     }
     __syncwarp();
     cluster_arrive_release();
     cluster_wait_acquire();
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = umma_idesc(1, 1, BM, BN);
       int rs = 0;
       uint32_t rph = 0;
@@ -832,11 +854,14 @@ gemm_csk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         tc_fence_after_sync();
         const uint32_t a_addr = smem_u32(smem + (size_t)s * STAGE_BYTES);
         const uint64_t da = umma_desc_k_sw128(a_addr), db = umma_desc_k_sw128(a_addr + A_BYTES);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
-        umma_commit(&empty_bar[s]);
+          for (int k = 0; k < BK / UMMA_K; ++k) umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[s]);
+          if (kb == kb_hi - 1) umma_commit(tmem_full_bar);
+        }
+        __syncwarp();
       }
-      umma_commit(tmem_full_bar);
     }
     __syncwarp();
     cluster_arrive_release();
@@ -956,31 +981,37 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   griddep_launch();
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       uint32_t it = 0, rph = 0;
       int rs = 0;
       for (int tile = pair; tile < total_tiles; tile += n_pairs) {
         const int m0 = (((tile % m_tiles) + ar.m_rot) % m_tiles) * 2 * BM + (int)cta * BM;  // this CTA's 128 rows of A
         const int n0 = (tile / m_tiles) * BN + (int)cta * HB;                               // ... and its half of the B tile
         if (ar.flags) {  // all-gather -> GEMM: the shard holding these rows has landed (see AReady)
-          const uint32_t* f = ar.flags + m0 / ar.rows_per_flag;
-          while (ld_relaxed_sys(f) != ar.epoch) { __nanosleep(32); }   // relaxed polls + one fence (no CCTL.IVALL per poll)
-          fence_acq_rel_sys();
-          __threadfence();
+          if (lane == 0) {
+            const uint32_t* f = ar.flags + m0 / ar.rows_per_flag;
+            while (ld_relaxed_sys(f) != ar.epoch) { __nanosleep(32); }   // relaxed polls + one fence (no CCTL.IVALL per poll)
+            fence_acq_rel_sys();
+            __threadfence();
+          }
+          __syncwarp();
         }
         for (int kb = 0; kb < nkb; ++kb, ++it, ring_next(rs, rph, stages)) {
           const int s = rs;
           const uint32_t phase = rph;
           mbar_wait(&empty_bar[s], phase ^ 1);
           uint8_t* a_dst = smem + (size_t)s * STAGE_BYTES;
-          if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
-          tma_load_2d_2sm(a_dst, &map_a, &full_bar[s], kb * BK, m0);
-          tma_load_2d_2sm(a_dst + A_BYTES, &map_b, &full_bar[s], kb * BK, n0);
+          if (elect_one()) {   // warp-uniform loop, elected lane issues (see gemm_tn_kernel)
+            if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
+            tma_load_2d_2sm(a_dst, &map_a, &full_bar[s], kb * BK, m0);
+            tma_load_2d_2sm(a_dst + A_BYTES, &map_b, &full_bar[s], kb * BK, n0);
+          }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && leader) {
+    if (leader) {
       constexpr uint32_t idesc = umma_idesc(1, 1, 2 * BM, BN);
       uint32_t it = 0, tcount = 0, rph = 0;
       int rs = 0;
@@ -997,13 +1028,16 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           const uint32_t a_addr = smem_u32(smem + (size_t)s * STAGE_BYTES);
           const uint64_t da = umma_desc_k_sw128(a_addr);
           const uint64_t db = umma_desc_k_sw128(a_addr + A_BYTES);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            umma_bf16_2sm(tmem_acc, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              umma_bf16_2sm(tmem_acc, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit_2sm(&empty_bar[s], 0b11);      // frees slot s in BOTH CTAs
+            if (kb == nkb - 1) umma_commit_2sm(&tmem_full_bar[as], 0b11);   // both epilogues may read their half
           }
-          umma_commit_2sm(&empty_bar[s], 0b11);      // frees slot s in BOTH CTAs
+          __syncwarp();
         }
-        umma_commit_2sm(&tmem_full_bar[as], 0b11);   // both epilogues may read their half
       }
     }
   } else {

@@ -19,7 +19,33 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(int M, int N, int n_
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = tmem_slot;
-  if (threadIdx.x == 0) {
+  if (nacc >= 100) {
+    // warp-uniform issue loop: all 32 lanes of warp 0 run the control flow and the descriptor arithmetic (so the compiler keeps
+    // them in uniform registers), only the elected lane executes the tcgen05 instructions
+    if (threadIdx.x < 32) {
+      const int mode = nacc - 100;
+      const uint32_t idesc = umma_idesc(1, 1, (uint32_t)M, (uint32_t)N);
+      const uint64_t da = umma_desc_k_sw128(smem_u32(smem)), db = umma_desc_k_sw128(smem_u32(smem + 128 * 128));
+      const int acc_stride = mode == 1 ? 0 : N;
+      const long long t0 = clock64();
+      for (int i = 0; i < n_mma / 4; ++i) {
+        if (mode == 24) mbar_wait(&bar2, 0);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + k * acc_stride, da + 2 * k, db + 2 * k, idesc, (i > 0 || (mode == 1 && k > 0)) ? 1u : 0u);
+          if (mode >= 14) umma_commit(&bar3);
+        }
+        __syncwarp();
+      }
+      const long long t1 = clock64();
+      if (elect_one()) umma_commit(&bar);
+      __syncwarp();
+      mbar_wait(&bar, 0);
+      const long long t2 = clock64();
+      if (threadIdx.x == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+    }
+  } else if (threadIdx.x == 0) {
     const uint32_t idesc = umma_idesc(1, 1, (uint32_t)M, (uint32_t)N);
     const uint64_t da = umma_desc_k_sw128(smem_u32(smem)), db = umma_desc_k_sw128(smem_u32(smem + 128 * 128));
     const long long t0 = clock64();
@@ -48,7 +74,7 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(int M, int N, int n_
 }  // namespace b200
 
 extern "C" int b200_umma_probe(int M, int N, int n_mma, int nacc, long long* out, cudaStream_t stream) {
-  if (!(M == 64 || M == 128) || N % 8 || N < 8 || N > 256 || nacc < 1 || (nacc == 1 ? 1 : 4) * N > 512) return -2;
+  if (!(M == 64 || M == 128) || N % 8 || N < 8 || N > 256 || nacc < 1 || ((nacc % 100) == 1 ? 1 : 4) * N > 512) return -2;
   const size_t smem = (128 + 256) * 128 + 1024;
   cudaFuncSetAttribute(b200::umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   b200::umma_probe_kernel<<<1, 128, smem, stream>>>(M, N, n_mma, nacc, out);
