@@ -645,3 +645,37 @@ def test_sample_filtered_suppresses_eos_and_varies_with_step(C):
     step.fill_(4)
     b, _ = C.sample_filtered(logits, V, 40, 1.0, 1.0, 5, step)
     assert (a != b).float().mean() > 0.5  # fresh noise per step
+
+
+@pytest.mark.parametrize("two_qs,with_mask", [(True, False), (False, True)])
+def test_ilql_sample_kernel(C, two_qs, with_mask):
+    """log pi_beta + beta * (min Q - V) -> top-k -> softmax(T) sampling (csrc/decode_ops.cu: ilql_sample_kernel) vs the PyTorch
+    formulation used by the model's own generate loop; temperature 0 must give the exact argmax."""
+    from trlx_b200.models.modeling_ilql import topk_mask
+
+    torch.manual_seed(31)
+    V, B = 777, 8192
+    row_logits = torch.randn(V, device="cuda") * 1.5
+    q1r, q2r = torch.randn(V, device="cuda"), torch.randn(V, device="cuda")
+    logits = torch.zeros(B, 784, device="cuda"); logits[:, :V] = row_logits
+    q1 = torch.zeros(B, 784, device="cuda"); q1[:, :V] = q1r
+    q2 = torch.zeros(B, 784, device="cuda"); q2[:, :V] = q2r
+    vs = torch.full((B,), 0.3, device="cuda")
+    beta, top_k, T = 2.0, 12, 0.8
+    mask = last = None
+    masked_logits = row_logits.clone()
+    if with_mask:
+        mask = torch.zeros(5, 600, dtype=torch.bool, device="cuda")  # covers only part of the vocabulary
+        mask[3, ::2] = True
+        last = torch.full((B,), 3, dtype=torch.long, device="cuda")
+        masked_logits[:600][mask[3]] = -float("inf")
+    tok = C.ilql_sample(logits, q1, q2 if two_qs else None, vs, V, beta, top_k, T, 99, None, None, mask, last)
+    q = torch.minimum(q1r, q2r) if two_qs else q1r
+    shifted = topk_mask((torch.log_softmax(masked_logits, -1) + beta * (q - 0.3))[None], top_k)[0]
+    probs = torch.softmax(shifted / T, -1)
+    assert (probs[tok] > 0).all()
+    freq = torch.bincount(tok, minlength=V).float() / B
+    sigma = (probs * (1 - probs) / B).sqrt()
+    assert ((freq - probs).abs() <= 5 * sigma + 1e-4).all()
+    greedy = C.ilql_sample(logits, q1, q2 if two_qs else None, vs, V, beta, top_k, 0.0, 99, None, None, mask, last)
+    assert (greedy == shifted.argmax()).all()

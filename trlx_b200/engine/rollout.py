@@ -174,7 +174,8 @@ class RolloutEngine:
         self.calls = 0
         self.use_cuda_graph = use_cuda_graph
         self.device = self.lm.device
-        self.branch = model.branch_layer if not getattr(model, "peft_type", None) else 0
+        self.ilql = bool(getattr(self, "ilql", False))  # set by engine/ilql.py before calling up
+        self.branch = model.branch_layer if (hasattr(model, "branch_layer") and not getattr(model, "peft_type", None)) else 0
         spec = self.spec
         # LoRA (the reference toggles adapters per forward, ``trlx/models/modeling_ppo.py:318-324``): rollouts read merged
         # weights W + (alpha / r) B A, refreshed in place after optimizer steps — zero adapter overhead per decoded token and the
@@ -182,7 +183,7 @@ class RolloutEngine:
         self.lora = bool(getattr(model, "peft_type", None))
         self.layers = [_layer_weights(b, spec, i) for i, b in enumerate(self.lm.transformer.h)]
         self._lora_src = [_lora_sources(b) for b in self.lm.transformer.h] if self.lora else []
-        fh = model.frozen_head if not self.lora else None
+        fh = getattr(model, "frozen_head", None) if not self.lora else None
         self.ref_layers = [_layer_weights(b, spec, self.branch + j) for j, b in enumerate(fh.decoder_blocks)] if fh is not None else []
         self.scale = spec.attn_scale if spec.attn_scale is not None else 1.0 / math.sqrt(spec.head_dim)
         self.alibi = alibi_slopes(spec.num_heads).to(self.device) if spec.pos == "alibi" else None
@@ -222,15 +223,20 @@ class RolloutEngine:
         # not have to sit on the per-token critical path.  The decode graph then keeps just the trunk activation of every
         # position, and one batched pass (2 frozen blocks + LM head over [B, Q+R] tokens at GEMM-efficient M) scores all
         # positions at the end — instead of 2 latency-bound blocks + a 77 MB LM-head sweep per decoded token.
-        self.defer_ref = os.environ.get("TRLX_B200_DEFER_REF", "1") == "1" or self.lora
-        self.keep_trunk = (self.cache_trunk or self.defer_ref) and not self.lora  # per-position activation at the branch point
+        self.defer_ref = os.environ.get("TRLX_B200_DEFER_REF", "1") == "1" or self.lora or self.ilql
+        # per-position activation at the branch point (no branch with adapters on every layer / in ILQL generation)
+        self.keep_trunk = (self.cache_trunk or self.defer_ref) and not self.lora and not self.ilql
         self.parallel_branches = (os.environ.get("TRLX_B200_PARALLEL_BRANCHES", "1") == "1" and self.branch < len(self.layers)
                                   and not self.defer_ref)
         self.side = torch.cuda.Stream(device=self.device) if self.parallel_branches else None
         ops.C.set_pdl(os.environ.get("TRLX_B200_PDL", "1") == "1")
         # Persistent decode megakernel (csrc/decode_mega.cu): the whole policy layer stack of a decode step in ONE launch —
-        # 16-CTA clusters own 16 batch rows each and walk all blocks with cluster barriers between phases.
-        self.mega = self._mega_eligible() and os.environ.get("TRLX_B200_DECODE_MEGA", "1") == "1"
+        # clusters of up to 16 CTAs own 16 batch rows each and walk all blocks with cluster barriers between phases.  Opt-in
+        # (TRLX_B200_DECODE_MEGA=1): numerically validated, but measured at 1.23 ms / token against 0.64 ms for the
+        # kernel-per-op graph on GPT-2 124M, batch 128 — with 16 rows per cluster the 64 x 16 x 16 tcgen05 atoms are bound by
+        # the ~68-cycle issue interval of one UTCHMMA (scripts/umma_probe.py), ~1000 of them per layer and CTA
+        # (profiles/decode_megakernel.md has the phase-by-phase timeline and what would close the gap).
+        self.mega = self._mega_eligible() and os.environ.get("TRLX_B200_DECODE_MEGA", "0") == "1"
         self._mega_tables = None
 
     # ------------------------------------------------------------------------------------------------ megakernel

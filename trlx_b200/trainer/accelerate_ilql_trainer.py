@@ -111,6 +111,43 @@ class AccelerateILQLTrainer(AccelerateRLTrainer):
         )
         self.generate_experience_kwargs = None
 
+    def _generate(self, input_ids, attention_mask, kwargs):
+        """ILQL sampling on the CUDA engine (``engine/ilql.py``) when the model allows it, else the PyTorch loop of the model."""
+        eng = self._ilql_engine()
+        if eng is None:
+            return super()._generate(input_ids, attention_mask, kwargs)
+        return eng.generate(input_ids, attention_mask, **kwargs)
+
+    def _ilql_engine(self):
+        if getattr(self, "_ilql_engine_obj", None) is not None or getattr(self, "_ilql_engine_failed", False):
+            return getattr(self, "_ilql_engine_obj", None)
+        self._ilql_engine_obj = None
+        try:
+            from trlx_b200 import ops
+            from trlx_b200.engine.ilql import ILQLDecodeEngine
+
+            why = ("no CUDA device" if not self.runtime.cuda else
+                   "seq2seq models generate through the PyTorch loop" if self.config.model.model_arch_type == "seq2seq" else
+                   "ZeRO-3 partitions the parameters" if getattr(self, "zero3", None) is not None else
+                   ILQLDecodeEngine.why_not(self.model))
+            if why is None:
+                self._ilql_engine_obj = ILQLDecodeEngine(self.model, self.tokenizer.pad_token_id, self.tokenizer.eos_token_id,
+                                                         seed=self.config.train.seed + self.runtime.rank)
+            else:
+                if self.runtime.cuda:
+                    logger.warning(f"ILQL generation uses the PyTorch sampling loop, not the CUDA engine: {why}")
+                self._ilql_engine_failed = True
+        except ImportError as err:
+            logger.warning(f"ILQL decode engine unavailable: {err}")
+            self._ilql_engine_failed = True
+        return self._ilql_engine_obj
+
+    def _after_weights_changed(self):
+        super()._after_weights_changed()
+        eng = getattr(self, "_ilql_engine_obj", None)
+        if eng is not None:
+            eng.mark_dirty()
+
     def get_arch(self, config):
         cls = (AutoModelForSeq2SeqLMWithILQLHeads if config.model.model_arch_type == "seq2seq"
                else AutoModelForCausalLMWithILQLHeads)
