@@ -175,6 +175,43 @@ def test_fused_tp_gemm_collectives():
         assert r["ag_err"] < 5e-2 and r["ag2_err"] < 5e-2 and r["rs_err"] < 6e-2, r
 
 
+def _tp_bwd_job(rank, world):
+    """Column → row parallel linear pair (sequence-parallel layout): gradients from the fused backward (GEMM→RS / AG→GEMM
+    kernels + peer-copy gathers) against the NCCL + torch.matmul backward on the same tensors."""
+    import os
+
+    from trlx_b200.parallel.fused_tp import FusedTP, column_linear, row_linear
+
+    fused = FusedTP(None, rank, world, torch.device("cuda", rank))
+    torch.manual_seed(3)
+    B, T, K, F = 2, 256, 512, 1024
+    t, f = T // world, F // world
+    up = torch.nn.Linear(K, f).cuda().to(torch.bfloat16)
+    down = torch.nn.Linear(f, K).cuda().to(torch.bfloat16)
+    torch.manual_seed(10 + rank)
+    x0 = (torch.randn(B, t, K, device="cuda") * 0.5).to(torch.bfloat16)
+    gout = (torch.randn(B, t, K, device="cuda") * 0.1).to(torch.bfloat16)
+    res = {}
+    for mode in ("1", "0"):
+        os.environ["TRLX_B200_TP_FUSED_BWD"] = mode
+        for p in list(up.parameters()) + list(down.parameters()):
+            p.grad = None
+        x = x0.clone().requires_grad_(True)
+        h = torch.nn.functional.gelu(column_linear(fused, up, x).float(), approximate="tanh").to(torch.bfloat16)
+        y = row_linear(fused, down, h)
+        y.backward(gout)
+        res[mode] = [x.grad.float().cpu(), up.weight.grad.float().cpu(), up.bias.grad.float().cpu(), down.weight.grad.float().cpu()]
+    os.environ.pop("TRLX_B200_TP_FUSED_BWD", None)
+    errs = [((a - b).norm() / b.norm().clamp_min(1e-6)).item() for a, b in zip(res["1"], res["0"])]
+    return dict(errs=errs)
+
+
+def test_fused_tp_backward_matches_nccl_backward():
+    _need(2)
+    for r in run(_tp_bwd_job, 2):
+        assert max(r["errs"]) < 2e-2, r
+
+
 # ---- TP/SP model on GPUs with the fused kernels ------------------------------------------------------------------------------------
 def _tp_model_job(rank, world, sp):
     from trlx_b200.models.modeling_ppo import AutoModelForCausalLMWithHydraValueHead

@@ -142,7 +142,8 @@ template <bool UPDATE>
 __global__ void __launch_bounds__(256)
 rs_adamw_ag_kernel(PeerPtrs grads, PeerPtrs params, int world, long long lo, long long n, float* __restrict__ master,
                    float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq, float* __restrict__ gshard, int use_gshard,
-                   AdamArgs a, const float* __restrict__ hyper, double* __restrict__ sq_out, BucketSync sync) {
+                   AdamArgs a, const float* __restrict__ hyper, double* __restrict__ sq_out, BucketSync sync,
+                   const __nv_bfloat16* __restrict__ mc_grad, __nv_bfloat16* __restrict__ mc_param) {
   const uint32_t sync_target = bucket_sync_begin(sync, world);
   const float lr = hyper[0], bc1 = hyper[1], bc2 = hyper[2], gs = hyper[3];
   const float inv_world = 1.f / (float)world;
@@ -157,11 +158,18 @@ rs_adamw_ag_kernel(PeerPtrs grads, PeerPtrs params, int world, long long lo, lon
     } else {
 #pragma unroll
       for (int j = 0; j < 8; ++j) g[j] = 0.f;
-      for (int r = 0; r < world; ++r) {
-        const int4 raw = ld_nc_v4(reinterpret_cast<const int4*>(reinterpret_cast<const __nv_bfloat16*>(grads.p[r]) + lo + i));
+      if (mc_grad) {   // NVLS: ONE load, the NVSwitch adds the `world` copies (fp32 accumulate) on the way
+        const uint4 raw = multimem_ld_reduce_add_bf16x8(mc_grad + lo + i);
         const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&raw);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) g[j] += __bfloat162float(h[j]);
+        for (int j = 0; j < 8; ++j) g[j] = __bfloat162float(h[j]);
+      } else {
+        for (int r = 0; r < world; ++r) {
+          const int4 raw = ld_nc_v4(reinterpret_cast<const int4*>(reinterpret_cast<const __nv_bfloat16*>(grads.p[r]) + lo + i));
+          const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&raw);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g[j] += __bfloat162float(h[j]);
+        }
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) g[j] *= inv_world;
@@ -180,8 +188,12 @@ rs_adamw_ag_kernel(PeerPtrs grads, PeerPtrs params, int world, long long lo, lon
       master[i + j] = w; exp_avg[i + j] = m; exp_avg_sq[i + j] = v;
       ph[j] = __float2bfloat16(w);
     }
-    for (int r = 0; r < world; ++r)
-      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(params.p[r]) + lo + i) = packed;
+    if (mc_param) {   // NVLS: one multicast store updates every rank's copy of the parameters
+      multimem_st_bf16x8(mc_param + lo + i, packed);
+    } else {
+      for (int r = 0; r < world; ++r)
+        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(params.p[r]) + lo + i) = packed;
+    }
   }
   if (!UPDATE && sq_out) {
     sq = warp_sum(sq);
@@ -279,9 +291,9 @@ extern "C" int b200_rs_adamw_ag(void* const* grads, void* const* params, int wor
   const int grid = grid_for(n, 8);
   BucketSync sync{};
   if (mode == 1)
-    rs_adamw_ag_kernel<false><<<grid, 256, 0, stream>>>(g, p, world, lo, n, master, exp_avg, exp_avg_sq, gshard, 1, a, hyper, sq_out, sync);
+    rs_adamw_ag_kernel<false><<<grid, 256, 0, stream>>>(g, p, world, lo, n, master, exp_avg, exp_avg_sq, gshard, 1, a, hyper, sq_out, sync, nullptr, nullptr);
   else
-    rs_adamw_ag_kernel<true><<<grid, 256, 0, stream>>>(g, p, world, lo, n, master, exp_avg, exp_avg_sq, gshard, mode == 2, a, hyper, nullptr, sync);
+    rs_adamw_ag_kernel<true><<<grid, 256, 0, stream>>>(g, p, world, lo, n, master, exp_avg, exp_avg_sq, gshard, mode == 2, a, hyper, nullptr, sync, nullptr, nullptr);
   return (int)cudaGetLastError();
 }
 
@@ -291,7 +303,8 @@ extern "C" int b200_rs_adamw_ag_bucket(void* const* grads, void* const* params, 
                                        float* master, float* exp_avg, float* exp_avg_sq, float* gshard, int mode, float beta1,
                                        float beta2, float eps, float weight_decay, int decoupled, const float* hyper,
                                        double* sq_out, void* const* flags, long long flag_offset, unsigned int* epoch,
-                                       unsigned int* done, int max_blocks, cudaStream_t stream) {
+                                       unsigned int* done, int max_blocks, const void* mc_grad, void* mc_param,
+                                       cudaStream_t stream) {
   if (n <= 0) return 0;
   if (world > MAX_PEERS || (lo & 7) || (n & 7)) return -3;
   PeerPtrs g{}, p{};
@@ -305,10 +318,13 @@ extern "C" int b200_rs_adamw_ag_bucket(void* const* grads, void* const* params, 
   AdamArgs a{beta1, beta2, eps, weight_decay, decoupled};
   int grid = grid_for(n, 8);
   if (max_blocks > 0 && grid > max_blocks) grid = max_blocks;
+  const __nv_bfloat16* mg = reinterpret_cast<const __nv_bfloat16*>(mc_grad);
+  __nv_bfloat16* mp = reinterpret_cast<__nv_bfloat16*>(mc_param);
   if (mode == 1)
-    rs_adamw_ag_kernel<false><<<grid, 256, 0, stream>>>(g, p, world, lo, n, master, exp_avg, exp_avg_sq, gshard, 1, a, hyper, sq_out, sync);
+    rs_adamw_ag_kernel<false><<<grid, 256, 0, stream>>>(g, p, world, lo, n, master, exp_avg, exp_avg_sq, gshard, 1, a, hyper, sq_out, sync, mg, mp);
   else
-    rs_adamw_ag_kernel<true><<<grid, 256, 0, stream>>>(g, p, world, lo, n, master, exp_avg, exp_avg_sq, gshard, mode == 2, a, hyper, nullptr, sync);
+    rs_adamw_ag_kernel<true><<<grid, 256, 0, stream>>>(g, p, world, lo, n, master, exp_avg, exp_avg_sq, gshard, mode == 2, a, hyper, nullptr, sync,
+                                                       mode == 2 ? nullptr : mg, mp);
   return (int)cudaGetLastError();
 }
 

@@ -244,6 +244,19 @@ __device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
   return v;
 }
 __device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+// ---------------------------------------------------------------- NVLS (NVSwitch in-fabric reduction / broadcast)
+// `mc` addresses come from a multicast mapping of a symmetric allocation (every GPU's copy behind one address): a load-reduce
+// returns the SUM over all GPUs computed inside the switch (fp32 accumulation, bf16 result), a store lands in every GPU's copy.
+__device__ __forceinline__ uint4 multimem_ld_reduce_add_bf16x8(const void* mc) {
+  uint4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(mc) : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st_bf16x8(void* mc, uint4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.bf16x2 [%0], {%1,%2,%3,%4};" ::"l"(mc), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
 __device__ __forceinline__ uint32_t atom_add_release_sys(uint32_t* p, uint32_t v) {
   uint32_t old;
   asm volatile("atom.add.release.sys.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");

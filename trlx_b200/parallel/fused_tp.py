@@ -7,8 +7,13 @@
   owner's staging slot over NVLink (bf16, 16-byte stores) as soon as its accumulator completes; the owner sums the slots.
   (Earlier variants — remote TMA loads per tile, fp32 ``red.global.add`` — are kept behind environment switches.)
 
-Ordering between ranks uses the device-side flag barrier of ``csrc/optim.cu`` on the buffers' signal pads.  Backward
-passes use ``torch.distributed`` collectives (library path).
+Ordering between ranks uses the device-side flag barrier of ``csrc/optim.cu`` on the buffers' signal pads.
+
+The backward passes are the same two primitives with the roles swapped (Apex does AG / RS in both directions,
+``trlx/models/modeling_nemo_ppo.py:93-120``): column-parallel ``dX = RS(dY · W)`` is a GEMM→reduce-scatter on a transposed
+weight copy, row-parallel ``dX = AG(dY) · W`` an all-gather→GEMM; the weight gradients contract over the *gathered* rows,
+which arrive by peer copies on a side stream while the dgrad kernel runs (column) or are the gathered buffer the dgrad
+all-gather→GEMM just filled (row).  ``TRLX_B200_TP_FUSED_BWD=0`` switches the backward to NCCL + ``torch.matmul``.
 """
 from __future__ import annotations
 
@@ -48,7 +53,8 @@ class FusedTP:
     def usable(rows_per_rank: int, k: int, n: int) -> bool:
         return rows_per_rank % 128 == 0 and k % 8 == 0 and n % 8 == 0
 
-    def allgather_gemm(self, x_local: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act: str = "none"):
+    def allgather_gemm(self, x_local: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act: str = "none",
+                       slot: str = "fwd"):
         """``x_local`` ``[m, K]`` (this rank's sequence shard) → ``[m·size, N]`` = act(all_gather(x) · wᵀ + bias).
 
         Every remote byte crosses NVLink exactly once: the peers' shards are pulled into a local gathered buffer by copies
@@ -58,14 +64,26 @@ class FusedTP:
         per-peer tensor maps; remote reads are not cached in the local L2, so every N-tile re-fetched its A rows over the
         link — 5x slower than NCCL + cuBLAS at TP = 4.  ``TRLX_B200_TP_REMOTE_TMA=1`` keeps that variant for comparison.)"""
         m, K = x_local.shape
-        buf, hdl = self._symm(("ag", m, K), (m, K), torch.bfloat16)
+        buf, hdl = self._symm(("ag", m, K, slot), (m, K), torch.bfloat16)
         buf.copy_(x_local)
         self.barrier()  # every rank's shard is in place
         if os.environ.get("TRLX_B200_TP_REMOTE_TMA") == "1":
             out = ops.C.gemm_allgather(list(hdl.buffer_ptrs), m, K, K, w, bias, act)
             self.barrier()
             return out
-        key = ("ag_full", m, K)
+        full, flags, ep = self._start_gather(buf, hdl, slot)
+        out = ops.C.gemm_flagged(full, w, bias, act, flags, ep, m, self.rank)
+        torch.cuda.current_stream().wait_stream(self._copy_stream)
+        self.barrier()  # all peers finished reading before the buffer is reused
+        self.last_gathered = full  # valid until the next gather with the same (shape, slot): the wgrad of a row-parallel layer reads it
+        return out
+
+    def _start_gather(self, x_local: torch.Tensor, hdl, slot: str = "fwd"):
+        """Own shard into the gathered buffer now, the peers' shards by copy-engine pulls on the side stream; returns
+        ``(gathered buffer, per-shard ready flags, epoch)`` — consumers either gate on the flags (fused GEMM) or wait for the
+        side stream."""
+        m, K = x_local.shape
+        key = ("ag_full", m, K, slot)
         if key not in self._local:
             self._local[key] = (torch.empty(self.size * m, K, dtype=torch.bfloat16, device=self.device),
                                 torch.zeros(self.size, dtype=torch.int32, device=self.device))
@@ -84,10 +102,22 @@ class FusedTP:
                 peer = hdl.get_buffer(r, (m, K), torch.bfloat16)
                 full[r * m:(r + 1) * m].copy_(peer, non_blocking=True)
                 flags[r:r + 1].fill_(ep)
-        out = ops.C.gemm_flagged(full, w, bias, act, flags, ep, m, self.rank)
-        main.wait_stream(side)
-        self.barrier()  # all peers finished reading before the buffer is reused
-        return out
+        return full, flags, ep
+
+    def gather_async(self, x_local: torch.Tensor, slot: str = "bwd"):
+        """Start an all-gather of ``x_local`` ``[m, K]`` over NVLink peer copies; :meth:`gather_wait` returns the ``[m·size, K]``
+        result.  Anything launched in between on the current stream overlaps the transfer."""
+        m, K = x_local.shape
+        buf, hdl = self._symm(("ag", m, K, slot), (m, K), torch.bfloat16)
+        buf.copy_(x_local)
+        self.barrier()
+        full, _, _ = self._start_gather(buf, hdl, slot)
+        return full
+
+    def gather_wait(self, full: torch.Tensor) -> torch.Tensor:
+        torch.cuda.current_stream().wait_stream(self._copy_stream)
+        self.barrier()  # peers are done reading this rank's staging buffer
+        return full
 
     def gemm_reduce_scatter(self, x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
                             residual: Optional[torch.Tensor] = None):
@@ -113,8 +143,13 @@ class FusedTP:
         return ops.C.stage_reduce(stage, None, residual)
 
 
+def _fused_bwd() -> bool:
+    return os.environ.get("TRLX_B200_TP_FUSED_BWD", "1") == "1"
+
+
 class _ColumnLinearFused(torch.autograd.Function):
-    """AG→GEMM forward (fused kernel); backward via NCCL: dX = RS(dY·W), dW = dYᵀ·AG(x)."""
+    """AG→GEMM forward; backward: ``dX = RS(dY · W)`` on the fused GEMM→reduce-scatter kernel (transposed weight copy) while the
+    all-gather of ``x`` for ``dW = dYᵀ · AG(x)`` travels over NVLink on the side stream."""
 
     @staticmethod
     def forward(ctx, x, w, b, fused: FusedTP):
@@ -127,27 +162,40 @@ class _ColumnLinearFused(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gy):
+        from trlx_b200.ops.functional import col_sum, grad_weight
+
         x, w = ctx.saved_tensors
         fused = ctx.fused
         B, t, K = x.shape
         g = gy.reshape(B, fused.size, t, -1).permute(1, 0, 2, 3).reshape(fused.size * B * t, -1).contiguous()
         gx = gw = gb = None
+        use_fused = _fused_bwd() and FusedTP.usable(B * t, g.shape[1], K) and g.dtype == torch.bfloat16
+        xs = None
+        if ctx.needs_input_grad[1] and use_fused:
+            xs = fused.gather_async(x.reshape(B * t, K).contiguous())  # peer copies run behind the dgrad kernel below
         if ctx.needs_input_grad[0]:
-            full = g @ w
-            out = torch.empty(B * t, K, dtype=full.dtype, device=full.device)
-            dist.reduce_scatter_tensor(out, full, group=fused.group)
-            gx = out.view(B, t, K)
+            if use_fused:
+                gx = fused.gemm_reduce_scatter(g, w.t().contiguous()).view(B, t, K)
+            else:
+                full = g @ w
+                out = torch.empty(B * t, K, dtype=full.dtype, device=full.device)
+                dist.reduce_scatter_tensor(out, full, group=fused.group)
+                gx = out.view(B, t, K)
         if ctx.needs_input_grad[1]:
-            xs = torch.empty(fused.size * B * t, K, dtype=x.dtype, device=x.device)
-            dist.all_gather_into_tensor(xs, x.reshape(B * t, K).contiguous(), group=fused.group)
-            gw = g.t() @ xs
+            if xs is not None:
+                gw = grad_weight(g, fused.gather_wait(xs))
+            else:
+                xs = torch.empty(fused.size * B * t, K, dtype=x.dtype, device=x.device)
+                dist.all_gather_into_tensor(xs, x.reshape(B * t, K).contiguous(), group=fused.group)
+                gw = g.t() @ xs
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = g.sum(0)
+            gb = col_sum(g)
         return gx, gw, gb, None
 
 
 class _RowLinearFused(torch.autograd.Function):
-    """GEMM→RS forward (fused kernel); backward via NCCL: dY_full = AG(dy), dX = dY_full·W, dW = dY_fullᵀ·x."""
+    """GEMM→RS forward; backward: ``dX = AG(dY) · W`` on the fused all-gather→GEMM kernel (transposed weight copy), and
+    ``dW = AG(dY)ᵀ · x`` from the gathered buffer that kernel just filled."""
 
     @staticmethod
     def forward(ctx, x, w, b, fused: FusedTP):
@@ -161,20 +209,33 @@ class _RowLinearFused(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gy):
+        from trlx_b200.ops.functional import col_sum, grad_weight
+
         xr, w = ctx.saved_tensors
         fused = ctx.fused
         B, T, K = ctx.shape
         t = T // fused.size
         g_local = gy.reshape(B * t, -1).contiguous()
-        g = torch.empty(fused.size * B * t, g_local.shape[1], dtype=g_local.dtype, device=g_local.device)
-        dist.all_gather_into_tensor(g, g_local, group=fused.group)
+        N = g_local.shape[1]
         gx = gw = gb = None
-        if ctx.needs_input_grad[0]:
-            gx = (g @ w).view(fused.size, B, t, K).permute(1, 0, 2, 3).reshape(B, T, K)
+        use_fused = _fused_bwd() and FusedTP.usable(B * t, N, K) and g_local.dtype == torch.bfloat16
+        g = None
+        if use_fused:
+            if ctx.needs_input_grad[0]:
+                full = fused.allgather_gemm(g_local, w.t().contiguous(), None, "none", slot="bwd")  # [M, K_local]
+                gx = full.view(fused.size, B, t, K).permute(1, 0, 2, 3).reshape(B, T, K)
+                g = fused.last_gathered
+            else:
+                g = fused.gather_wait(fused.gather_async(g_local))
+        else:
+            g = torch.empty(fused.size * B * t, N, dtype=g_local.dtype, device=g_local.device)
+            dist.all_gather_into_tensor(g, g_local, group=fused.group)
+            if ctx.needs_input_grad[0]:
+                gx = (g @ w).view(fused.size, B, t, K).permute(1, 0, 2, 3).reshape(B, T, K)
         if ctx.needs_input_grad[1]:
-            gw = g.t() @ xr
+            gw = grad_weight(g, xr) if use_fused else g.t() @ xr
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = g.sum(0)
+            gb = col_sum(g) if use_fused else g.sum(0)
         return gx, gw, gb, None
 
 

@@ -75,6 +75,7 @@ class _FlatGroup:
             for i in b["params"]:
                 self.bucket_of[i] = k
         self.symm_param = self.symm_grad = self.symm_flags = self.symm_sq = None
+        self.mc_grad = self.mc_param = 0
         nb = len(self.buckets)
         if symmetric:
             import torch.distributed._symmetric_memory as symm
@@ -91,6 +92,15 @@ class _FlatGroup:
             self.symm_grad = symm.rendezvous(self.flat_grad, name)
             self.symm_flags = symm.rendezvous(self.flags, name)
             self.symm_sq = symm.rendezvous(self.sqbuf, name)
+            import os
+
+            # NVLS (NVSwitch multicast mapping of the symmetric buffers): multimem.ld_reduce / multimem.st in the fused kernel —
+            # one in-switch reduction / broadcast instead of `world` peer loads / stores per element (TRLX_B200_NVLS=0 disables)
+            if os.environ.get("TRLX_B200_NVLS", "1") == "1":
+                self.mc_grad = int(getattr(self.symm_grad, "multicast_ptr", 0) or 0)
+                self.mc_param = int(getattr(self.symm_param, "multicast_ptr", 0) or 0)
+                if not (self.mc_grad and self.mc_param):
+                    self.mc_grad = self.mc_param = 0
         else:
             self.flat_param = torch.zeros(self.numel, dtype=torch.bfloat16, device=self.device)
             self.flat_grad = torch.zeros(self.numel, dtype=torch.bfloat16, device=self.device)
@@ -270,7 +280,7 @@ class FusedAdamW(Optimizer):
                                  b["shard"], fg.master[sl], fg.exp_avg[sl], fg.exp_avg_sq[sl], gsh, mode, b1, b2, g["eps"],
                                  g["weight_decay"], self.decoupled, fg.hyper, fg.sq if mode == 1 else None,
                                  list(fg.symm_flags.buffer_ptrs), k * fg.world, fg.epochs[k:k + 1], fg.done[k:k + 1],
-                                 max_blocks)
+                                 max_blocks, fg.mc_grad, fg.mc_param)
 
     def _end_barrier(self, fg: _FlatGroup):
         """Every rank's new parameters are visible everywhere (and nobody still reads this rank's gradients)."""
