@@ -36,9 +36,20 @@ def _worker(rank, world, port, fn, out_dir, args):
         dist.destroy_process_group()
 
 
-def run(fn, world=2, args=()):
+def run(fn, world=2, args=(), deadline_s: float = 240.0):
+    """Spawn ``world`` ranks; a rank that deadlocks (spin-waiting kernels, mismatched collectives) must not hang the whole GPU
+    session: after ``deadline_s`` every child is killed and the test fails."""
+    import time
+
     out = tempfile.mkdtemp()
-    mp.spawn(_worker, args=(world, _free_port(), fn, out, args), nprocs=world, join=True)
+    ctx = mp.spawn(_worker, args=(world, _free_port(), fn, out, args), nprocs=world, join=False)
+    t0 = time.time()
+    while not ctx.join(timeout=5):
+        if time.time() - t0 > deadline_s:
+            for p in ctx.processes:
+                if p.is_alive():
+                    p.kill()
+            raise TimeoutError(f"{fn.__name__}: ranks still running after {deadline_s:.0f} s (deadlock?) — killed")
     return [torch.load(os.path.join(out, f"r{r}.pt"), weights_only=False) for r in range(world)]
 
 

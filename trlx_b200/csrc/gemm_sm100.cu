@@ -645,7 +645,7 @@ gemm_tn_kernel(const __grid_constant__ MapArray maps_a, const __grid_constant__ 
         if (ar.flags) {  // the shard holding these rows has landed in the local gathered buffer
           if (lane == 0) {
             const uint32_t* f = ar.flags + m0 / ar.rows_per_flag;
-            while (ld_relaxed_sys(f) != ar.epoch) { __nanosleep(32); }   // relaxed polls + one fence (no CCTL.IVALL per poll)
+            { const long long t0 = clock64(); while (ld_relaxed_sys(f) != ar.epoch) { __nanosleep(32); spin_guard(t0); } }   // relaxed polls + one fence (no CCTL.IVALL per poll)
             fence_acq_rel_sys();
             __threadfence();
           }
@@ -990,7 +990,7 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (ar.flags) {  // all-gather -> GEMM: the shard holding these rows has landed (see AReady)
           if (lane == 0) {
             const uint32_t* f = ar.flags + m0 / ar.rows_per_flag;
-            while (ld_relaxed_sys(f) != ar.epoch) { __nanosleep(32); }   // relaxed polls + one fence (no CCTL.IVALL per poll)
+            { const long long t0 = clock64(); while (ld_relaxed_sys(f) != ar.epoch) { __nanosleep(32); spin_guard(t0); } }   // relaxed polls + one fence (no CCTL.IVALL per poll)
             fence_acq_rel_sys();
             __threadfence();
           }

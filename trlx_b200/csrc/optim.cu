@@ -93,7 +93,8 @@ __global__ void signal_barrier_kernel(PeerPtrs pads, int rank, int world, uint32
     uint32_t* remote = reinterpret_cast<uint32_t*>(pads.p[t]) + rank;
     st_release_sys(remote, epoch);
     const uint32_t* mine = reinterpret_cast<const uint32_t*>(pads.p[rank]) + t;
-    while ((int32_t)(ld_relaxed_sys(mine) - epoch) < 0) { __nanosleep(64); }
+    const long long t0 = clock64();
+    while ((int32_t)(ld_relaxed_sys(mine) - epoch) < 0) { __nanosleep(64); spin_guard(t0); }
     fence_acq_rel_sys();
   }
   __syncthreads();
@@ -120,7 +121,8 @@ __device__ __forceinline__ uint32_t bucket_sync_begin(const BucketSync& sync, in
   }
   if ((int)threadIdx.x < world) {
     const uint32_t* mine = reinterpret_cast<const uint32_t*>(sync.flags[sync.rank]) + threadIdx.x;
-    while ((int32_t)(ld_relaxed_sys(mine) - target) < 0) { __nanosleep(100); }
+    const long long t0 = clock64();
+    while ((int32_t)(ld_relaxed_sys(mine) - target) < 0) { __nanosleep(100); spin_guard(t0); }
     fence_acq_rel_sys();
   }
   __syncthreads();
@@ -218,7 +220,8 @@ __global__ void clip_exchange_kernel(PeerPtrs sqbufs, PeerPtrs flags, int rank, 
     __threadfence_system();
     st_release_sys(reinterpret_cast<uint32_t*>(flags.p[t]) + rank, epoch);
     const uint32_t* mine = reinterpret_cast<const uint32_t*>(flags.p[rank]) + t;
-    while ((int32_t)(ld_relaxed_sys(mine) - epoch) < 0) { __nanosleep(64); }
+    const long long t0 = clock64();
+    while ((int32_t)(ld_relaxed_sys(mine) - epoch) < 0) { __nanosleep(64); spin_guard(t0); }
     fence_acq_rel_sys();
   }
   __syncthreads();

@@ -244,6 +244,12 @@ __device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
   return v;
 }
 __device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+// Every cross-GPU spin loop is bounded: a peer that never signals (mismatched launch order, a crashed rank) turns into a
+// kernel trap — a CUDA error on the host — after ~30 s instead of a GPU that spins forever.
+constexpr long long SPIN_LIMIT_CYCLES = 60000000000ll;  // ~30 s at 2 GHz
+__device__ __forceinline__ void spin_guard(long long t0) {
+  if (clock64() - t0 > SPIN_LIMIT_CYCLES) __trap();
+}
 // ---------------------------------------------------------------- NVLS (NVSwitch in-fabric reduction / broadcast)
 // `mc` addresses come from a multicast mapping of a symmetric allocation (every GPU's copy behind one address): a load-reduce
 // returns the SUM over all GPUs computed inside the switch (fp32 accumulation, bf16 result), a store lands in every GPU's copy.

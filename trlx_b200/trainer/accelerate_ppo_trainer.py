@@ -243,6 +243,11 @@ class AcceleratePPOTrainer(AccelerateRLTrainer):
 
     def _graphs_enabled(self) -> bool:
         """Whole-step CUDA graphs: CUDA, fused optimizer, one micro-batch per step, decoder-only hydra with shared trunk."""
+        rt = self.runtime
+        if rt.tp_size > 1 or rt.pp_size > 1:
+            # the fused tensor-parallel kernels hand host-side epochs to their flag waits and fork copy streams per call: a replayed
+            # graph would wait for flags that never come (2-GPU NeMoPPOTrainer deadlocked this way); model-parallel steps run eagerly
+            return False
         return bool(self.runtime.cuda and self.config.train.parallel.cuda_graphs and self.num_mb == 1
                     and getattr(self.opt, "graph_capturable", False) and self.config.model.model_arch_type != "seq2seq"
                     and hasattr(self.model, "can_share_trunk") and self.model.can_share_trunk()
