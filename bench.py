@@ -186,6 +186,18 @@ def build_trainer(args, tmp):
     return trainer, cfg
 
 
+def _optimizer_note(trainer) -> str:
+    """Which gradient-reduction path ran (for the record next to a multi-GPU number)."""
+    fg = next((g for g in (getattr(trainer.opt, "_flat", None) or []) if g is not None), None)
+    if fg is None:
+        return "torch fallback"
+    if fg.world == 1:
+        return "fused AdamW (single rank)"
+    return (f"fused RS+AdamW+AG over NVLink, {len(fg.buckets)} buckets, "
+            f"{'overlapped with backward' if getattr(trainer.opt, 'can_overlap', False) else 'after backward'}, "
+            f"{'NVLS multimem' if getattr(fg, 'mc_grad', 0) else 'P2P ld/st'}")
+
+
 def ppo_iteration(trainer):
     """Exactly the per-epoch body of ``AccelerateRLTrainer.learn`` for PPO (without eval / checkpoint IO)."""
     from trlx_b200.pipeline import MiniBatchIterator
@@ -285,7 +297,8 @@ def main():
                    "seq_len": cfg.train.seq_length, "parallelism": f"dp{world}", "num_rollouts_per_gpu": m.num_rollouts,
                    "chunk_size": m.chunk_size, "ppo_epochs": m.ppo_epochs, "max_new_tokens": r, "num_layers_unfrozen": 2,
                    "optimizer_steps_per_step": opt_steps, "l2": "flushed (256 MiB write) before every timed iteration",
-                   "learn_tokens_per_sec": round(samples_per_step * m.ppo_epochs * (q + r) / (ms_per_step / 1e3), 1)},
+                   "learn_tokens_per_sec": round(samples_per_step * m.ppo_epochs * (q + r) / (ms_per_step / 1e3), 1),
+                   "optimizer": _optimizer_note(trainer)},
         "clocks": clocks,
         "e2e": {"value": round(samples_per_step / e2e_s_per_step, 2), "unit": "samples/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h)},
