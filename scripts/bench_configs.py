@@ -225,8 +225,13 @@ def main(argv=None):
     if dist.is_initialized():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dp = max(trainer.runtime.dp_size, 1)
+    eng = getattr(trainer, "_engine", None) or getattr(trainer, "_ilql_engine_obj", None)
+    engine = ("none (PyTorch sampler)" if eng is None else
+              f"{type(eng).__name__}{' fp8' if getattr(eng, 'fp8', False) else ' bf16'}{' lora-merged' if getattr(eng, 'lora', False) else ''}"
+              f"{' megakernel' if getattr(eng, 'mega', False) else ''}")
     if trainer.runtime.is_main_process:
-        print(json.dumps({"config": args.config, "what": what, "metric": "samples_per_sec", "value": round(samples * dp / t.item(), 3),
+        print(json.dumps({"config": args.config, "what": what, "rollout_engine": engine, "zero3": getattr(trainer, "zero3", None) is not None,
+                          "metric": "samples_per_sec", "value": round(samples * dp / t.item(), 3),
                           "unit": "samples/s", "n_gpus": world if cuda else 0, "steps": args.steps, "warmup": args.warmup,
                           "ms_per_step": round(t.item() / args.steps * 1e3, 3), "tiny": bool(args.tiny),
                           "dtype": "bf16" if cuda else "fp32 (cpu)", "data": "synthetic"}), flush=True)

@@ -69,7 +69,7 @@ int b200_rs_adamw_ag(void* const*, void* const*, int, long long, long long, floa
 int b200_lerp_bf16(void*, const void*, long long, float, cudaStream_t);
 int b200_rs_adamw_ag_bucket(void* const*, void* const*, int, int, long long, long long, float*, float*, float*, float*, int,
                             float, float, float, float, int, const float*, double*, void* const*, long long, unsigned int*,
-                            unsigned int*, int, const void*, void*, cudaStream_t);
+                            unsigned int*, int, const void*, void*, float, cudaStream_t);
 int b200_clip_exchange(void* const*, void* const*, long long, int, int, const double*, unsigned int*, float, float*, float*,
                        cudaStream_t);
 int b200_attn_short_ok(int, int, int, int);
@@ -730,7 +730,7 @@ void rs_adamw_ag_bucket(const std::vector<int64_t>& grads, const std::vector<int
                         int64_t n, Tensor& master, Tensor& exp_avg, Tensor& exp_avg_sq, const OptTensor& gshard, int64_t mode,
                         double beta1, double beta2, double eps, double weight_decay, bool decoupled, const Tensor& hyper,
                         const OptTensor& sq_out, const std::vector<int64_t>& flags, int64_t flag_offset, Tensor& epoch,
-                        Tensor& done, int64_t max_blocks, int64_t mc_grad, int64_t mc_param) {
+                        Tensor& done, int64_t max_blocks, int64_t mc_grad, int64_t mc_param, double grad_scale) {
   TORCH_CHECK(grads.size() == params.size() && grads.size() == flags.size());
   TORCH_CHECK(epoch.scalar_type() == at::kInt && done.scalar_type() == at::kInt);
   std::vector<void*> g(grads.size()), p(params.size()), f(flags.size());
@@ -746,7 +746,8 @@ void rs_adamw_ag_bucket(const std::vector<int64_t>& grads, const std::vector<int
                                 hyper.data_ptr<float>(), (double*)optptr(sq_out), f.data(), flag_offset,
                                 reinterpret_cast<unsigned int*>(epoch.data_ptr<int>()),
                                 reinterpret_cast<unsigned int*>(done.data_ptr<int>()), (int)max_blocks,
-                                reinterpret_cast<const void*>(mc_grad), reinterpret_cast<void*>(mc_param), stream()),
+                                reinterpret_cast<const void*>(mc_grad), reinterpret_cast<void*>(mc_param), (float)grad_scale,
+                                stream()),
         "rs_adamw_ag_bucket");
 }
 

@@ -145,10 +145,12 @@ __global__ void __launch_bounds__(256)
 rs_adamw_ag_kernel(PeerPtrs grads, PeerPtrs params, int world, long long lo, long long n, float* __restrict__ master,
                    float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq, float* __restrict__ gshard, int use_gshard,
                    AdamArgs a, const float* __restrict__ hyper, double* __restrict__ sq_out, BucketSync sync,
-                   const __nv_bfloat16* __restrict__ mc_grad, __nv_bfloat16* __restrict__ mc_param) {
+                   const __nv_bfloat16* __restrict__ mc_grad, __nv_bfloat16* __restrict__ mc_param, float grad_scale) {
   const uint32_t sync_target = bucket_sync_begin(sync, world);
   const float lr = hyper[0], bc1 = hyper[1], bc2 = hyper[2], gs = hyper[3];
-  const float inv_world = 1.f / (float)world;
+  // the reduced gradient is (sum over the group) * grad_scale: 1 / world for data parallelism; 1 / dp for parameters that are
+  // replicated inside a tensor-parallel group under sequence parallelism (partial gradients per TP rank are SUMMED)
+  const float inv_world = grad_scale > 0.f ? grad_scale : 1.f / (float)world;
   float sq = 0.f;
   const long long nvec = n >> 3;
   for (long long vi = (long long)blockIdx.x * blockDim.x + threadIdx.x; vi < nvec; vi += (long long)gridDim.x * blockDim.x) {
@@ -294,9 +296,9 @@ extern "C" int b200_rs_adamw_ag(void* const* grads, void* const* params, int wor
   const int grid = grid_for(n, 8);
   BucketSync sync{};
   if (mode == 1)
-    rs_adamw_ag_kernel<false><<<grid, 256, 0, stream>>>(g, p, world, lo, n, master, exp_avg, exp_avg_sq, gshard, 1, a, hyper, sq_out, sync, nullptr, nullptr);
+    rs_adamw_ag_kernel<false><<<grid, 256, 0, stream>>>(g, p, world, lo, n, master, exp_avg, exp_avg_sq, gshard, 1, a, hyper, sq_out, sync, nullptr, nullptr, 0.f);
   else
-    rs_adamw_ag_kernel<true><<<grid, 256, 0, stream>>>(g, p, world, lo, n, master, exp_avg, exp_avg_sq, gshard, mode == 2, a, hyper, nullptr, sync, nullptr, nullptr);
+    rs_adamw_ag_kernel<true><<<grid, 256, 0, stream>>>(g, p, world, lo, n, master, exp_avg, exp_avg_sq, gshard, mode == 2, a, hyper, nullptr, sync, nullptr, nullptr, 0.f);
   return (int)cudaGetLastError();
 }
 
@@ -307,7 +309,7 @@ extern "C" int b200_rs_adamw_ag_bucket(void* const* grads, void* const* params, 
                                        float beta2, float eps, float weight_decay, int decoupled, const float* hyper,
                                        double* sq_out, void* const* flags, long long flag_offset, unsigned int* epoch,
                                        unsigned int* done, int max_blocks, const void* mc_grad, void* mc_param,
-                                       cudaStream_t stream) {
+                                       float grad_scale, cudaStream_t stream) {
   if (n <= 0) return 0;
   if (world > MAX_PEERS || (lo & 7) || (n & 7)) return -3;
   PeerPtrs g{}, p{};
@@ -324,10 +326,10 @@ extern "C" int b200_rs_adamw_ag_bucket(void* const* grads, void* const* params, 
   const __nv_bfloat16* mg = reinterpret_cast<const __nv_bfloat16*>(mc_grad);
   __nv_bfloat16* mp = reinterpret_cast<__nv_bfloat16*>(mc_param);
   if (mode == 1)
-    rs_adamw_ag_kernel<false><<<grid, 256, 0, stream>>>(g, p, world, lo, n, master, exp_avg, exp_avg_sq, gshard, 1, a, hyper, sq_out, sync, mg, mp);
+    rs_adamw_ag_kernel<false><<<grid, 256, 0, stream>>>(g, p, world, lo, n, master, exp_avg, exp_avg_sq, gshard, 1, a, hyper, sq_out, sync, mg, mp, grad_scale);
   else
     rs_adamw_ag_kernel<true><<<grid, 256, 0, stream>>>(g, p, world, lo, n, master, exp_avg, exp_avg_sq, gshard, mode == 2, a, hyper, nullptr, sync,
-                                                       mode == 2 ? nullptr : mg, mp);
+                                                       mode == 2 ? nullptr : mg, mp, grad_scale);
   return (int)cudaGetLastError();
 }
 

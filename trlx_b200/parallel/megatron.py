@@ -85,6 +85,32 @@ class MegatronMixin:
             self._pp_stage = apply_pipeline_parallel(model, rt.pp_group, rt.pp_rank, rt.pp_size)
         return model
 
+    def _optimizer_param_groups(self, params, optimizer_class):
+        """With sequence parallelism the block norms are replicated inside the TP group but see sequence-sharded activations:
+        every TP rank holds a PARTIAL gradient for them.  Instead of a separate flatten → all-reduce → copy pass before the
+        optimizer (the reference pattern, ``modeling_nemo_ppo.py:627-645``), they form their own parameter group whose fused
+        reduce-scatter + AdamW + all-gather runs over the whole stage (TP x DP ranks) and divides by DP only — the TP sum
+        happens inside the optimizer kernel."""
+        from trlx_b200.parallel.optim import FusedAdamW
+
+        rt = self.runtime
+        self._sp_grads_in_optimizer = False
+        if not (issubclass(optimizer_class, FusedAdamW) and rt.tp_size > 1 and self.config.train.parallel.sequence_parallel
+                and getattr(self, "zero3", None) is None and getattr(rt, "stage_group", None) is not None):
+            return params
+        from trlx_b200.parallel.tensor_parallel import sequence_parallel_grad_params
+
+        shared = {id(p) for p in sequence_parallel_grad_params(self.model)}
+        sp = [p for p in params if id(p) in shared]
+        rest = [p for p in params if id(p) not in shared]
+        if not sp:
+            return params
+        self._sp_grads_in_optimizer = True
+        groups = [{"params": sp, "reduce_group": rt.stage_group, "grad_divisor": float(rt.dp_size)}]
+        if rest:
+            groups.insert(0, {"params": rest})
+        return groups
+
     # ---- pipeline-parallel optimizer step -------------------------------------------------------------------------------
     def train_step(self, minibatch):
         stage = getattr(self, "_pp_stage", None)
@@ -127,7 +153,7 @@ class MegatronMixin:
             from trlx_b200.parallel.pipeline_parallel import allreduce_tied_embedding_grads
 
             allreduce_tied_embedding_grads(stage)
-        if rt.tp_size > 1 and self.config.train.parallel.sequence_parallel:
+        if rt.tp_size > 1 and self.config.train.parallel.sequence_parallel and not getattr(self, "_sp_grads_in_optimizer", False):
             from trlx_b200.parallel.tensor_parallel import allreduce_sequence_parallel_grads
 
             allreduce_sequence_parallel_grads(self.model, rt.tp_group)

@@ -211,14 +211,25 @@ class FusedAdamW(Optimizer):
             if not ps:
                 self._flat.append(None)
                 continue
+            # a param group may name its own reduction group and divisor: `reduce_group` (default: the optimizer's data-
+            # parallel group) and `grad_divisor` (default: its size).  Tensor-parallel trainers use it for the parameters that
+            # sequence parallelism leaves replicated inside the TP group: reduce over TP x DP, divide by DP only
+            pg = g.get("reduce_group", self.process_group)
+            if "reduce_group" in g and not self.local_only and dist.is_available() and dist.is_initialized():
+                world, rank = dist.get_world_size(pg), dist.get_rank(pg)
+            else:
+                world, rank = self._world()
             symmetric = world > 1 and self.zero_stage >= 1
             if world > 1 and not symmetric:
                 self._flat.append(_FlatGroup(ps, 1, 0, None, False, 1 << 62))
                 self._flat[-1].needs_allreduce = True
+                self._flat[-1].reduce_group, self._flat[-1].reduce_world = pg, world
+                self._flat[-1].grad_divisor = float(g.get("grad_divisor", world))
                 continue
             try:
-                self._flat.append(_FlatGroup(ps, world, rank, self.process_group, symmetric,
+                self._flat.append(_FlatGroup(ps, world, rank, pg, symmetric,
                                              self.bucket_elems if symmetric else 1 << 62))
+                self._flat[-1].grad_divisor = float(g.get("grad_divisor", world))
             except Exception as err:  # symmetric memory unavailable → replicated update after an NCCL all-reduce
                 if not symmetric:
                     raise
@@ -283,7 +294,7 @@ class FusedAdamW(Optimizer):
                                  b["shard"], fg.master[sl], fg.exp_avg[sl], fg.exp_avg_sq[sl], gsh, mode, b1, b2, g["eps"],
                                  g["weight_decay"], self.decoupled, fg.hyper, fg.sq if mode == 1 else None,
                                  list(fg.symm_flags.buffer_ptrs), k * fg.world, fg.epochs[k:k + 1], fg.done[k:k + 1],
-                                 max_blocks, fg.mc_grad, fg.mc_param)
+                                 max_blocks, fg.mc_grad, fg.mc_param, 1.0 / getattr(fg, "grad_divisor", fg.world))
 
     def _end_barrier(self, fg: _FlatGroup):
         """Every rank's new parameters are visible everywhere (and nobody still reads this rank's gradients)."""
@@ -319,14 +330,21 @@ class FusedAdamW(Optimizer):
                                     self._fallback.param_groups):
                 g_fb["lr"] = g_self["lr"]
             params = [p for g in self._fallback.param_groups for p in g["params"] if p.grad is not None]
-            if world > 1 and params:
-                flat = torch.cat([p.grad.reshape(-1).float() for p in params])
-                dist.all_reduce(flat, group=self.process_group)
-                flat /= world
-                off = 0
-                for p in params:
-                    p.grad.copy_(flat[off:off + p.numel()].view_as(p.grad))
-                    off += p.numel()
+            live = [g for g in self.param_groups if any(p.requires_grad for p in g["params"])]
+            for g_self in live:  # every param group reduces over its own group / divisor (see _lazy_init)
+                pg = g_self.get("reduce_group", self.process_group)
+                if self.local_only or not (dist.is_available() and dist.is_initialized()):
+                    break
+                gw = dist.get_world_size(pg)
+                gp = [p for p in g_self["params"] if p.requires_grad and p.grad is not None]
+                if gw > 1 and gp:
+                    flat = torch.cat([p.grad.reshape(-1).float() for p in gp])
+                    dist.all_reduce(flat, group=pg)
+                    flat /= float(g_self.get("grad_divisor", gw))
+                    off = 0
+                    for p in gp:
+                        p.grad.copy_(flat[off:off + p.numel()].view_as(p.grad))
+                        off += p.numel()
             if self.grad_clip:
                 if self.local_only and dist.is_available() and dist.is_initialized():
                     sq = torch.stack([p.grad.float().pow(2).sum() for p in params]).sum() if params else torch.zeros(())
@@ -375,9 +393,9 @@ class FusedAdamW(Optimizer):
             args = (b1, b2, g["eps"], g["weight_decay"], self.decoupled)
             if fg.world == 1:
                 fg.hyper.copy_(fg.hyper_host, non_blocking=True)
-                if getattr(fg, "needs_allreduce", False) and world > 1:
-                    dist.all_reduce(fg.flat_grad, group=self.process_group)
-                    fg.flat_grad.div_(world)
+                if getattr(fg, "needs_allreduce", False) and getattr(fg, "reduce_world", world) > 1:
+                    dist.all_reduce(fg.flat_grad, group=getattr(fg, "reduce_group", self.process_group))
+                    fg.flat_grad.div_(getattr(fg, "grad_divisor", world))
                 if self.grad_clip:
                     fg.sq.zero_()
                     C.sqnorm_(fg.flat_grad, fg.sq)

@@ -77,7 +77,7 @@ class Runtime:
         self.tp_rank = self.rank % tp
         self.dp_rank = (self.rank // tp) % self.dp_size
         self.pp_rank = self.rank // (tp * self.dp_size)
-        self.tp_group = self.dp_group = self.pp_group = None
+        self.tp_group = self.dp_group = self.pp_group = self.stage_group = None
         from trlx_b200.utils.modeling import set_statistics_group
 
         set_statistics_group(None)
@@ -103,6 +103,15 @@ class Runtime:
                 g = dist.new_group(ranks)
                 if self.rank in ranks:
                     self.pp_group = g
+        # every rank of one pipeline stage (tensor x data parallel): the replica set of parameters that sequence parallelism
+        # leaves replicated inside the TP group (block norms) — their gradients are summed over TP and averaged over DP in ONE
+        # pass of the fused optimizer kernel over this group
+        self.stage_group = None
+        for p in range(pp):
+            ranks = [((p * self.dp_size) + d) * tp + t for d in range(self.dp_size) for t in range(tp)]
+            g = dist.new_group(ranks)
+            if self.rank in ranks:
+                self.stage_group = g
         set_statistics_group(self.dp_group)  # model-parallel peers hold identical data: statistics span DP only
         self._publish_state()
 

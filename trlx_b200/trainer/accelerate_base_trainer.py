@@ -231,7 +231,7 @@ class AccelerateRLTrainer(BaseRLTrainer):
             params = self.zero3.shard_parameters()
             if issubclass(optimizer_class, FusedAdamW):
                 kwargs["local_only"] = True
-        opt = optimizer_class(params, **kwargs)
+        opt = optimizer_class(self._optimizer_param_groups(params, optimizer_class), **kwargs)
         if hasattr(opt, "prepare"):
             opt.prepare()
         if "8bit" in optimizer_class.__name__:
@@ -239,6 +239,10 @@ class AccelerateRLTrainer(BaseRLTrainer):
                 if isinstance(module, torch.nn.Embedding):
                     module.weight._optim_32bit = True
         return opt
+
+    def _optimizer_param_groups(self, params, optimizer_class):
+        """Hook for trainers whose parameters do not all reduce over the same ranks (tensor-parallel trainers)."""
+        return params
 
     def setup_scheduler(self):
         scheduler_class = get_scheduler_class(self.config.scheduler.name)
