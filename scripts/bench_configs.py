@@ -88,7 +88,7 @@ def build(name: str, small: bool, tmp: str):
         arch = tiny(LLAMA2_7B) if small else LLAMA2_7B
         seq, new = (64, 16) if small else (2048, 256)
         cfg = default_ppo_config().evolve(
-            train=dict(seq_length=seq, batch_size=4 if small else 16, **common),
+            train=dict(seq_length=seq, batch_size=4 if small else 16, parallel=dict(rollout_dtype="fp8"), **common),
             model=dict(model_path=arch, num_layers_unfrozen=2,
                        peft_config=dict(peft_type="LORA", task_type="CAUSAL_LM", r=8, lora_alpha=32, lora_dropout=0.0)),
             tokenizer=dict(tokenizer_path=tok or "toy://bpe?vocab=32000"),

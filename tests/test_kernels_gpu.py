@@ -395,10 +395,11 @@ def test_training_norm_forward_backward(C, rms, M, H):
 @pytest.mark.parametrize("M,N", [(1792, 3072), (1792, 768), (7, 66), (1280, 50304), (0, 64)])
 def test_bias_gradient_column_sum(C, M, N):
     x = _bf(M, N + 2)[:, :N]  # strided view: row pitch != N
-    out = C.colsum(x)
     ref = x.float().sum(0)
-    assert out.shape == (N,)
-    assert (out.float() - ref).abs().max().item() <= 1e-2 * max(ref.abs().max().item(), 1.0) + 1e-6
+    for _ in range(3):  # repeated calls share one workspace that the kernel must leave zeroed
+        out = C.colsum(x)
+        assert out.shape == (N,)
+        assert (out.float() - ref).abs().max().item() <= 1e-2 * max(ref.abs().max().item(), 1.0) + 1e-6
 
 
 @pytest.mark.parametrize("rms", [False, True])

@@ -86,7 +86,8 @@ int b200_ln_bwd_ctas(int);
 int b200_ln_fwd(const void*, const void*, const void*, void*, float*, int, int, long long, float, int, cudaStream_t);
 int b200_ln_bwd(const void*, const void*, const float*, const void*, void*, float*, void*, void*, int, int, long long, long long,
                 int, cudaStream_t);
-int b200_colsum_bf16(const void*, void*, int, int, long long, cudaStream_t);
+int b200_colsum_bf16(const void*, void*, int, int, long long, float*, cudaStream_t);
+int b200_colsum_rows(int, int);
 void b200_set_pdl(int);
 void b200_set_static_weights(int);
 int b200_get_static_weights();
@@ -372,7 +373,20 @@ Tensor colsum(const Tensor& x) {
               reinterpret_cast<uintptr_t>(x.data_ptr()) % 4 == 0, "colsum: bf16 [M, N] with even N and pitch");
   c10::cuda::CUDAGuard guard(x.device());
   Tensor out = torch::empty({x.size(1)}, x.options());
-  check(b200_colsum_bf16(x.data_ptr(), out.data_ptr(), (int)x.size(0), (int)x.size(1), x.stride(0), stream()), "colsum");
+  const int64_t N = x.size(1);
+  // one zeroed workspace per (device, width), reused by every call: the kernel restores it to zero before it finishes, and calls
+  // on one stream are ordered (the bias gradients of a step are reduced one after the other)
+  static std::unordered_map<int64_t, Tensor> ws_cache;
+  Tensor ws;
+  if (b200_colsum_rows((int)x.size(0), (int)N) > 1) {
+    const int64_t key = (int64_t)x.device().index() * (1ll << 32) + N;
+    auto it = ws_cache.find(key);
+    if (it == ws_cache.end()) it = ws_cache.emplace(key, torch::zeros({N + (N + 63) / 64 + 1}, x.options().dtype(at::kFloat))).first;
+    ws = it->second;
+  }
+  check(b200_colsum_bf16(x.data_ptr(), out.data_ptr(), (int)x.size(0), (int)N, x.stride(0),
+                         ws.defined() ? ws.data_ptr<float>() : nullptr, stream()),
+        "colsum");
   return out;
 }
 

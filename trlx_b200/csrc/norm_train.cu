@@ -242,19 +242,26 @@ __global__ void ln_bwd_finalize_kernel(const float* __restrict__ partial, __nv_b
   else if (dbeta) dbeta[c - H] = __float2bfloat16(s);
 }
 
-// out[n] = sum_m x[m, n]: CTA = 64 columns, 8 warps stride over the rows, lanes own a bf16 pair
+// out[n] = sum_m x[m, n].  CTA (bx, by) = 64 columns x the by-th slice of the rows; its 8 warps stride over the slice (lanes own a
+// bf16 pair, four independent loads in flight), one shared-memory fold, then fp32 atomics into `acc`; the LAST slice to finish a
+// column block (ticket counter) converts it to bf16 and clears accumulator + ticket for the next call.  (A 64-column CTA over ALL
+// rows — 12 CTAs for a 768-wide bias — was a chain of ~56 dependent L2 round trips: 26 us x 9 bias gradients per optimizer step.)
 __global__ void __launch_bounds__(256)
-colsum_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int M, int N, long long ldx) {
+colsum_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int M, int N, long long ldx,
+              float* __restrict__ acc, unsigned int* __restrict__ tickets) {
   __shared__ float red[8][64];
+  __shared__ bool last;
   griddep_wait();
   griddep_launch();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int col = blockIdx.x * 64 + lane * 2;
+  const int rows_per = (M + gridDim.y - 1) / gridDim.y;
+  const int m_lo = blockIdx.y * rows_per, m_hi = min(M, m_lo + rows_per);
   float a0 = 0.f, a1 = 0.f;
   if (col < N) {  // N is even (checked on the host), so the pair is either fully inside or fully outside
     const __nv_bfloat16* p = x + col;
-    int m = warp;
-    for (; m + 24 < M; m += 32) {  // four independent loads in flight per lane
+    int m = m_lo + warp;
+    for (; m + 24 < m_hi; m += 32) {  // four independent loads in flight per lane
       const float2 v0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p + (size_t)m * ldx));
       const float2 v1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p + (size_t)(m + 8) * ldx));
       const float2 v2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p + (size_t)(m + 16) * ldx));
@@ -262,7 +269,7 @@ colsum_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ o
       a0 += (v0.x + v1.x) + (v2.x + v3.x);
       a1 += (v0.y + v1.y) + (v2.y + v3.y);
     }
-    for (; m < M; m += 8) {
+    for (; m < m_hi; m += 8) {
       const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p + (size_t)m * ldx));
       a0 += v.x;
       a1 += v.y;
@@ -271,12 +278,29 @@ colsum_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ o
   red[warp][lane * 2] = a0;
   red[warp][lane * 2 + 1] = a1;
   __syncthreads();
+  const int c = blockIdx.x * 64 + threadIdx.x;
   if (threadIdx.x < 64) {
     float s = 0.f;
 #pragma unroll
     for (int w8 = 0; w8 < 8; ++w8) s += red[w8][threadIdx.x];
-    const int c = blockIdx.x * 64 + threadIdx.x;
-    if (c < N) out[c] = __float2bfloat16(s);
+    if (gridDim.y == 1) {
+      if (c < N) out[c] = __float2bfloat16(s);
+    } else if (c < N) {
+      atomicAdd(acc + c, s);
+    }
+  }
+  if (gridDim.y == 1) return;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(tickets + blockIdx.x, 1u) == gridDim.y - 1;
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    if (threadIdx.x < 64 && c < N) {
+      out[c] = __float2bfloat16(__ldcg(acc + c));
+      acc[c] = 0.f;
+    }
+    if (threadIdx.x == 0) tickets[blockIdx.x] = 0u;
   }
 }
 
@@ -337,9 +361,21 @@ extern "C" int b200_ln_bwd(const void* x, const void* w, const float* stats, con
                             (__nv_bfloat16*)dgamma, (__nv_bfloat16*)dbeta, ctas, H);
 }
 
-extern "C" int b200_colsum_bf16(const void* x, void* out, int M, int N, long long ldx, cudaStream_t stream) {
+// `workspace`: N fp32 accumulators + ceil(N / 64) tickets, ZERO on entry (the kernel leaves it zero again); may be null for
+// short matrices (single row slice).
+extern "C" int b200_colsum_rows(int M, int N) {
+  const int col_blocks = (N + 63) / 64;
+  int r = (2 * 148 + col_blocks - 1) / col_blocks;   // ~2 CTAs per SM in total
+  const int max_r = (M + 63) / 64;                   // at least 64 rows per CTA
+  if (r > max_r) r = max_r;
+  return r < 1 ? 1 : r;
+}
+
+extern "C" int b200_colsum_bf16(const void* x, void* out, int M, int N, long long ldx, float* workspace, cudaStream_t stream) {
   if (N <= 0) return 0;
   if (N % 2 || ldx % 2) return -2;
-  return (int)launch_kernel(colsum_kernel, dim3((N + 63) / 64), dim3(256), 0, stream, (const __nv_bfloat16*)x,
-                            (__nv_bfloat16*)out, M, N, ldx);
+  const int r = workspace ? b200_colsum_rows(M, N) : 1;
+  return (int)launch_kernel(colsum_kernel, dim3((N + 63) / 64, r), dim3(256), 0, stream, (const __nv_bfloat16*)x,
+                            (__nv_bfloat16*)out, M, N, ldx, workspace,
+                            reinterpret_cast<unsigned int*>(workspace ? workspace + N : nullptr));
 }
