@@ -330,3 +330,34 @@ def test_ilql_decode_engine_matches_model_generate():
     # sampling mode runs and respects the vocabulary / EOS conventions
     s = eng.generate(ids, mask, beta=1.0, max_new_tokens=R, temperature=1.0, top_k=20, pad_token_id=599, eos_token_id=599)
     assert s.shape[0] == B and (s >= 0).all() and (s < 600).all()
+
+
+def test_engine_serves_models_with_a_value_branch():
+    """``num_value_layers_unfrozen > 0``: the value function has its own transformer branch.  The engine samples without it and
+    scores every position in one batched pass over the cached trunk activations — same values as ``model.score``."""
+    from trlx_b200.engine.rollout import RolloutEngine
+    from trlx_b200.models.modeling_ppo import AutoModelForCausalLMWithHydraValueHead
+    from trlx_b200.utils.modeling import freeze_bottom_causal_layers
+
+    torch.manual_seed(0)
+    cfg = dict(model_type="gpt2", vocab_size=1000, n_embd=256, n_layer=4, n_head=4, n_positions=128, eos_token_id=999, bos_token_id=999)
+    m = AutoModelForCausalLMWithHydraValueHead.from_config(cfg, num_layers_unfrozen=2, num_value_layers_unfrozen=1)
+    freeze_bottom_causal_layers(m.base_model, 2)
+    m = m.cuda().to(torch.bfloat16).eval()
+    pad = eos = 999
+    B, Q, R = 12, 6, 8
+    gen = dict(max_new_tokens=R, do_sample=True, eos_token_id=eos, pad_token_id=pad, top_k=0, top_p=1.0)
+    assert RolloutEngine.why_not(m, gen) is None
+    eng = RolloutEngine(m, pad, eos, gen, seed=1)
+    assert eng.value_branch
+    ids = torch.randint(1, 900, (B, Q), device="cuda")
+    ro = eng.rollout(ids, torch.ones_like(ids))
+    tokens, amask = ro["samples"], ro["mask"]
+    pos = (amask.cumsum(-1) - 1).clamp_min(0)
+    labels = torch.cat([tokens[:, 1:], tokens.new_full((B, 1), -1)], 1)
+    with torch.no_grad():
+        lp, val, _, _ = m.score(tokens, amask, pos, labels, with_ref=False)
+    start = ro["start"]
+    valid = amask[:, start + 1:].bool()
+    torch.testing.assert_close(ro["values"][:, start:][valid], val[:, :-1][:, start:][valid].float(), atol=3e-2, rtol=3e-2)
+    torch.testing.assert_close(ro["logprobs"][:, start:][valid], lp[:, :-1][:, start:][valid].float(), atol=6e-2, rtol=5e-2)

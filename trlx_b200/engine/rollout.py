@@ -129,8 +129,8 @@ class RolloutEngine:
             return f"{peft} adapters are scored through the PyTorch path (only LoRA is merged into the rollout weights)"
         if not peft and getattr(model, "frozen_head", None) is None:
             return "no frozen reference branch (num_layers_unfrozen <= 0 or a separate reference model)"
-        if getattr(model, "num_value_layers_unfrozen", 0) != 0:
-            return "the value head has its own transformer branch"
+        if getattr(model, "num_value_layers_unfrozen", 0) != 0 and (peft or not model.can_share_trunk()):
+            return "a value branch deeper than the policy branch (no shared trunk activation to score it from)"
         if getattr(model, "tp_context", None) is not None or getattr(base_lm(model.base_model), "tp_context", None) is not None:
             return "tensor-parallel weights are sharded: the engine's kernels assume full (replicated) weight matrices"
         from trlx_b200.parallel import state as pstate
@@ -181,6 +181,9 @@ class RolloutEngine:
         # weights W + (alpha / r) B A, refreshed in place after optimizer steps — zero adapter overhead per decoded token and the
         # fp8 / megakernel paths apply unchanged; reference log-probs come from ONE batched adapter-free pass after the loop
         self.lora = bool(getattr(model, "peft_type", None))
+        # value *branch* (``num_value_layers_unfrozen > 0``, reference ``modeling_ppo.py:331-343``): sampling never needs the
+        # value, so the decode graph skips it and ONE batched pass over the cached trunk activations scores every position
+        self.value_branch = int(getattr(model, "num_value_layers_unfrozen", 0) or 0) > 0
         self.layers = [_layer_weights(b, spec, i) for i, b in enumerate(self.lm.transformer.h)]
         self._lora_src = [_lora_sources(b) for b in self.lm.transformer.h] if self.lora else []
         fh = getattr(model, "frozen_head", None) if not self.lora else None
@@ -492,9 +495,12 @@ class RolloutEngine:
         else:
             _, _, tok, tlp = C.lmhead(hf, lm.lm_head.weight, lm.lm_head.bias, None, True, self.temperature, self.seed,
                                       st["step"], self.eos if st["min_new"] > 0 else -1, st["min_new"], st["ws"], st["seed_dev"])
-        vh = model.v_head
-        h1 = C.gemm(hf, vh[0].weight, vh[0].bias, None, "relu")
-        val = C.rowdot(h1, vh[2].weight.view(-1), vh[2].bias)
+        if self.value_branch:
+            val = None  # the value function has its own transformer branch: all positions are scored in one pass after the loop
+        else:
+            vh = model.v_head
+            h1 = C.gemm(hf, vh[0].weight, vh[0].bias, None, "relu")
+            val = C.rowdot(h1, vh[2].weight.view(-1), vh[2].bias)
         if self.defer_ref:
             ref_lp = tlp  # placeholder column; the real reference log-probs come from `_ref_score` after the loop
         elif rf is None:
@@ -778,6 +784,12 @@ class RolloutEngine:
         trunk = None
         if self.keep_trunk:
             trunk = torch.cat([trunk_p, st["trunk_decode"][:, :r_max]], 1)
+        if self.value_branch:
+            am = torch.cat([mask, mask.new_ones(B, r_max)], 1)[:, :-1]
+            pos = (am.long().cumsum(-1) - 1).clamp_min(0)
+            _, v_all, _, _ = self.model.score(all_tokens[:, :-1], am, pos, all_tokens[:, 1:], trunk_hidden=trunk, with_ref=False)
+            values = v_all.float()
+            values[:, :Q - 1] = 0.0  # prompt positions carry no value (matches the in-graph path)
         if self.lora:
             torch.cuda.nvtx.range_push("engine/reference_scoring")
             ref_logprobs = self._ref_score_adapter_free(all_tokens, full_mask, Q)
