@@ -304,7 +304,7 @@ def main():
                 "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),
     }
-    if os.environ.get("BENCH_BREAKDOWN") and rank == 0:
+    if os.environ.get("BENCH_BREAKDOWN") and rank == 0 and world == 1:  # rank-0-only re-run: would desynchronise collectives
         # coarse per-phase wall-clock (synchronised) for one more iteration — diagnostic only, not part of the metric
         import collections
 
