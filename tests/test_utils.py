@@ -222,3 +222,24 @@ def test_flat_optimizer_partition_with_virtual_ranks(world, bucket_elems):
             reduced = torch.stack([gr[sl] for gr in grads]).mean(0)                      # reduce-scatter
             gathered[sl] = adamw_step(g.master[ms].clone(), reduced, g.exp_avg[ms], g.exp_avg_sq[ms], 1, **hp)  # all-gather
     torch.testing.assert_close(gathered, expect)
+
+
+def test_relative_outputs_never_land_in_the_source_checkout(tmp_path, monkeypatch):
+    """`resolve_output_dir`: TRLX_B200_OUT wins; inside the source checkout relative paths are redirected to a temp root (a 498 MB
+    example checkpoint written into the repo once voided a whole round of measurements); elsewhere they stay cwd-relative."""
+    import os
+
+    import trlx_b200.utils as U
+
+    monkeypatch.delenv("TRLX_B200_OUT", raising=False)
+    assert U.resolve_output_dir("/abs/path") == "/abs/path" and U.resolve_output_dir(None) is None
+    repo = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(U.__file__))))
+    monkeypatch.chdir(repo)
+    out = U.resolve_output_dir("ckpts")
+    assert os.path.isabs(out) and not os.path.realpath(out).startswith(os.path.realpath(repo))
+    monkeypatch.chdir(tmp_path)
+    assert U.resolve_output_dir("ckpts") == "ckpts"
+    monkeypatch.setenv("TRLX_B200_OUT", str(tmp_path / "o"))
+    assert U.resolve_output_dir("ckpts") == str(tmp_path / "o" / "ckpts")
+    (tmp_path / "here").mkdir()
+    assert U.resolve_output_dir("here", for_read=True) == "here"  # an existing cwd-relative checkpoint is read where it is
