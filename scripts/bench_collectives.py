@@ -17,7 +17,7 @@ rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
 dev = torch.device("cuda", torch.cuda.current_device())
 dist.init_process_group("nccl", device_id=dev)
-NVLINK = 900e9  # bytes/s per direction per GPU
+NVLINK = 770e9  # bytes/s per direction per GPU: measured peer-copy bandwidth on this pool (B200_PROFILING.md; nominal 900e9)
 GEMM_PEAK = 1.46e15  # sustained cuBLAS bf16 on this part (MEASURED_PEAKS.json)
 
 
