@@ -42,8 +42,11 @@ def report(**kw):
         print(json.dumps(kw), flush=True)
 
 
+PARTS = os.environ.get("BENCH_COLL_PARTS", "opt,ag,rs").split(",")
+TAG = {k: os.environ[k] for k in ("TRLX_B200_TP_RS_NVLS", "TRLX_B200_TP_RS_SPLIT") if k in os.environ}
+
 # ---- 1. fused reduce-scatter + AdamW + all-gather vs NCCL RS + torch AdamW + NCCL AG -------------------------------------
-n = 64 * 1024 * 1024  # 64 M bf16 parameters
+n = 64 * 1024 * 1024 if "opt" in PARTS else 1 << 20  # 64 M bf16 parameters
 p = torch.nn.Parameter(torch.randn(n, device=dev).to(torch.bfloat16))
 opt = FusedAdamW([p], lr=1e-4, process_group=None).prepare()
 p.grad.copy_(torch.randn_like(p))
@@ -67,13 +70,14 @@ def nccl_step():
 
 
 t_nccl = timed(nccl_step)
-report(op="rs+adamw+ag", params=n, world=world, fused_ms=round(t_fused * 1e3, 3), nccl_ms=round(t_nccl * 1e3, 3),
-       nvlink_bytes_per_rank=int(moved), fused_nvlink_fraction=round(moved / NVLINK / t_fused, 3),
-       speedup_vs_nccl=round(t_nccl / t_fused, 2))
+if "opt" in PARTS:
+    report(op="rs+adamw+ag", params=n, world=world, fused_ms=round(t_fused * 1e3, 3), nccl_ms=round(t_nccl * 1e3, 3),
+           nvlink_bytes_per_rank=int(moved), fused_nvlink_fraction=round(moved / NVLINK / t_fused, 3),
+           speedup_vs_nccl=round(t_nccl / t_fused, 2))
 
 # ---- 2. all-gather -> GEMM and GEMM -> reduce-scatter (TP = world), GPT-NeoX-20B-like block shapes -----------------------------
 tp = FusedTP(None, rank, world, dev)
-for (name, tokens, K, N) in (("qkv 20B", 8192, 6144, 3 * 6144), ("mlp-up 20B", 8192, 6144, 4 * 6144)):
+for (name, tokens, K, N) in ((("qkv 20B", 8192, 6144, 3 * 6144), ("mlp-up 20B", 8192, 6144, 4 * 6144)) if "ag" in PARTS else ()):
     m = tokens // world  # sequence shard per rank
     n_loc = N // world
     x = (torch.randn(m, K, device=dev) * 0.1).to(torch.bfloat16)
@@ -91,7 +95,7 @@ for (name, tokens, K, N) in (("qkv 20B", 8192, 6144, 3 * 6144), ("mlp-up 20B", 8
     roof = max(flops / GEMM_PEAK, link / NVLINK)
     report(op="allgather->gemm", shape=name, world=world, fused_ms=round(t_f * 1e3, 3), nccl_cublas_ms=round(t_n * 1e3, 3),
            tflops=round(flops / t_f / 1e12, 1), roofline_fraction=round(roof / t_f, 3), speedup=round(t_n / t_f, 2))
-for (name, tokens, Kfull, N) in (("attn-out 20B", 8192, 6144, 6144), ("mlp-down 20B", 8192, 4 * 6144, 6144)):
+for (name, tokens, Kfull, N) in ((("attn-out 20B", 8192, 6144, 6144), ("mlp-down 20B", 8192, 4 * 6144, 6144)) if "rs" in PARTS else ()):
     k_loc = Kfull // world
     x = (torch.randn(tokens, k_loc, device=dev) * 0.1).to(torch.bfloat16)
     w = (torch.randn(N, k_loc, device=dev) * Kfull ** -0.5).to(torch.bfloat16)
@@ -105,10 +109,10 @@ for (name, tokens, Kfull, N) in (("attn-out 20B", 8192, 6144, 6144), ("mlp-down 
 
     t_n = timed(nccl_gemm_rs)
     flops = 2.0 * tokens * k_loc * N
-    link = (world - 1) * (tokens // world) * N * 4  # fp32 partials pushed to the owners
+    link = (world - 1) * (tokens // world) * N * 2  # bf16 partials of the other ranks arriving at the owner
     roof = max(flops / GEMM_PEAK, link / NVLINK)
     report(op="gemm->reduce_scatter", shape=name, world=world, fused_ms=round(t_f * 1e3, 3), nccl_cublas_ms=round(t_n * 1e3, 3),
-           tflops=round(flops / t_f / 1e12, 1), roofline_fraction=round(roof / t_f, 3), speedup=round(t_n / t_f, 2))
+           tflops=round(flops / t_f / 1e12, 1), roofline_fraction=round(roof / t_f, 3), speedup=round(t_n / t_f, 2), **TAG)
 dist.barrier()
 torch.cuda.synchronize()
 os._exit(0)

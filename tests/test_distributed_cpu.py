@@ -168,7 +168,7 @@ def test_tp_state_dict_resharding_roundtrip():
 
 
 # ---- pipeline parallelism -------------------------------------------------------------------------------------------------
-def _pp_job(rank, world, family, tied):
+def _pp_job(rank, world, family, tied, virtual=1, M=5):
     import copy
 
     from trlx_b200.nn.arch import spec_from_hf_config
@@ -185,8 +185,8 @@ def _pp_job(rank, world, family, tied):
     assert spec.tie_word_embeddings == tied
     full = CausalLM(spec).float()
     staged = copy.deepcopy(full)
-    stage = pp.apply_pipeline_parallel(staged, None, rank, world)
-    M = 5
+    stage = pp.apply_pipeline_parallel(staged, None, rank, world, virtual)
+    assert stage.virtual == virtual
     g = torch.Generator().manual_seed(1)
     mbs = []
     for i in range(M):
@@ -219,7 +219,7 @@ def _pp_job(rank, world, family, tied):
         out = staged(**mb)
         return out.loss, {"loss": out.loss.detach()}
 
-    stats = pp.run_1f1b(stage, mbs, loss_fn, torch.device("cpu"))
+    stats = pp.run_schedule(stage, mbs, loss_fn, torch.device("cpu"))
     pp.allreduce_tied_embedding_grads(stage)
     sched_grads = {n: p.grad.clone() for n, p in staged.named_parameters() if p.grad is not None and p.numel()}
     shared = pp.broadcast_stats(stage, {"loss": sum(s["loss"] for s in stats) / M} if stage.last else None, torch.device("cpu"))
@@ -235,9 +235,26 @@ def _pp_job(rank, world, family, tied):
                 owned=(stage.lo, stage.hi))
 
 
-@pytest.mark.parametrize("world,family,tied", [(2, "gpt2", True), (3, "llama", False)])
-def test_pipeline_parallel_matches_single_rank(world, family, tied):
-    res = run_distributed(_pp_job, world, (family, tied))
+def test_interleaved_schedule_plan():
+    """Every (P, V, M): each rank runs every operation exactly once, and a round's transfers are matched by construction."""
+    from trlx_b200.parallel.pipeline_parallel import interleaved_rounds
+
+    for P in (2, 3, 4, 8):
+        for V in (1, 2, 3):
+            for M in (1, 3, 4, 5, 8, 16):
+                rounds = interleaved_rounds(P, V, M)
+                for r in range(P):
+                    mine = [a[r] for a in rounds if a[r] is not None]
+                    assert len(mine) == len(set(mine)) == 2 * M * V
+    # the bubble shrinks with the number of chunks: P = 4, 16 micro-batches, measured in whole-stage units
+    cost = {V: len(interleaved_rounds(4, V, 16)) / V for V in (1, 2, 4)}
+    assert cost[4] < cost[2] < cost[1]
+
+
+@pytest.mark.parametrize("world,family,tied,virtual,M", [(2, "gpt2", True, 1, 5), (3, "llama", False, 1, 5),
+                                                         (2, "gpt2", True, 2, 4), (2, "llama", False, 2, 5)])
+def test_pipeline_parallel_matches_single_rank(world, family, tied, virtual, M):
+    res = run_distributed(_pp_job, world, (family, tied, virtual, M))
     ref = res[0]["ref_grads"]
     seen = set()
     for r in res:
@@ -252,13 +269,13 @@ def test_pipeline_parallel_matches_single_rank(world, family, tied):
     assert seen == set(ref), f"parameters without a gradient on any stage: {set(ref) - seen}"
 
 
-def _pp_trainer_job(rank, world, kind, tmp):
+def _pp_trainer_job(rank, world, kind, tmp, virtual=1):
     import trlx_b200 as trlx
     from trlx_b200.data.default_configs import default_ppo_config, default_sft_config
 
     gpt2 = dict(model_type="gpt2", vocab_size=257, n_embd=32, n_layer=4, n_head=2, n_positions=64, eos_token_id=256, bos_token_id=256)
     common = dict(seq_length=16, batch_size=4, minibatch_size=1, total_steps=3, epochs=4, checkpoint_interval=100, eval_interval=3,
-                  tracker=None, checkpoint_dir=tmp, seed=3, parallel=dict(pipeline_parallel=world))
+                  tracker=None, checkpoint_dir=tmp, seed=3, parallel=dict(pipeline_parallel=world, virtual_pipeline_parallel=virtual))
     prompts = ["hello a", "what is", "b", "count the a", "zz", "dog dog", "a dog", "the"]
     if kind == "ppo":
         cfg = default_ppo_config().evolve(
@@ -282,6 +299,13 @@ def test_pipeline_parallel_trainers_run(kind, tmp_path):
     res = run_distributed(_pp_trainer_job, 2, (kind, str(tmp_path)))
     assert [r["iters"] for r in res] == [3, 3]
     assert res[0]["owned"] == [0, 1] and res[1]["owned"] == [2, 3]
+
+
+def test_interleaved_pipeline_ppo_trainer_runs(tmp_path):
+    """``virtual_pipeline_parallel=2``: every rank owns two non-adjacent chunks, the optimizer step runs the interleaved schedule."""
+    res = run_distributed(_pp_trainer_job, 2, ("ppo", str(tmp_path), 2))
+    assert [r["iters"] for r in res] == [3, 3]
+    assert res[0]["owned"] == [0, 2] and res[1]["owned"] == [1, 3]
 
 
 def _sp_odd_length_job(rank, world, family):

@@ -100,6 +100,8 @@ int b200_gemm_flagged_bf16(const void*, const void*, void*, int, int, int, long 
                            const uint32_t*, uint32_t, int, int, cudaStream_t);
 int b200_stage_reduce(const void*, int, const void*, const void*, void*, long long, int, long long, long long, long long,
                       cudaStream_t);
+int b200_mc_reduce_rows(const void*, const void*, const void*, void*, long long, int, int, long long, long long, long long, int,
+                        cudaStream_t);
 int b200_gemm_stage_scatter_bf16(const void*, const void*, void* const*, int, int, int, int, int, long long, long long, long long,
                                  const void*, cudaStream_t);
 int b200_rs_finalize(const float*, const void*, const void*, void*, long long, int, long long, long long, long long,
@@ -845,6 +847,21 @@ Tensor stage_reduce(const Tensor& stage, const OptTensor& bias, const OptTensor&
   return out;
 }
 
+// out[rows, col0 : col0 + ncols] = NVLS sum over all ranks of their partial [.., ldp] rows behind the multicast address `mc_ptr`
+// (already offset to this rank's first row) (+ bias + residual)
+void mc_reduce_rows(int64_t mc_ptr, Tensor& out, const OptTensor& bias, const OptTensor& residual, int64_t col0, int64_t ncols,
+                    int64_t ldp, int64_t blocks) {
+  CHECK_BF16(out);
+  TORCH_CHECK(out.dim() == 2 && out.stride(1) == 1 && mc_ptr != 0);
+  c10::cuda::CUDAGuard guard(out.device());
+  long long ldr = 0;
+  if (residual.has_value()) { CHECK_BF16(*residual); TORCH_CHECK(residual->size(0) == out.size(0) && residual->stride(1) == 1); ldr = residual->stride(0); }
+  if (bias.has_value()) { CHECK_BF16(*bias); }
+  check(b200_mc_reduce_rows(reinterpret_cast<const void*>(mc_ptr), optptr(bias), optptr(residual), out.data_ptr(), out.size(0),
+                            (int)ncols, (int)col0, ldp, ldr, out.stride(0), (int)blocks, stream()),
+        "mc_reduce_rows");
+}
+
 // adds this rank's partial product x[M, K_local] . w[N, K_local]^T into the peers' fp32 accumulators (row-blocks by owner)
 void gemm_reduce_scatter(const Tensor& x, const Tensor& w, const std::vector<int64_t>& acc_peers, int64_t ldacc,
                          const OptTensor& bias) {
@@ -1037,6 +1054,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("epoch"), py::arg("rows_per_flag"), py::arg("first_chunk"));
   m.def("gemm_stage_scatter", &gemm_stage_scatter, py::arg("x"), py::arg("w"), py::arg("stage_peers"), py::arg("rank"),
         py::arg("ldstage"), py::arg("bias") = py::none());
+  m.def("mc_reduce_rows", &mc_reduce_rows, py::arg("mc_ptr"), py::arg("out"), py::arg("bias") = py::none(),
+        py::arg("residual") = py::none(), py::arg("col0") = 0, py::arg("ncols") = 0, py::arg("ldp") = 0, py::arg("blocks") = 0);
   m.def("stage_reduce", &stage_reduce, py::arg("stage"), py::arg("bias") = py::none(), py::arg("residual") = py::none());
   m.def("gemm_ex", &gemm_ex, py::arg("a"), py::arg("b"), py::arg("a_mn") = false, py::arg("b_mn") = false,
         py::arg("out_f32") = false, py::arg("split_k") = -1);

@@ -1798,6 +1798,58 @@ extern "C" int b200_stage_reduce(const void* stage, int world, const void* bias,
   return (int)cudaGetLastError();
 }
 
+// NVLS reduce-scatter tail of GEMM -> reduce-scatter: every rank's partial product [M, N] sits in a symmetric buffer that is also
+// mapped as one multicast address range; the owner of a row block issues multimem.ld_reduce over it — the NVSwitch sums the
+// `world` copies in fp32 and returns one bf16x8 vector, so each output byte crosses this GPU's links once and no staging slots or
+// per-peer loops exist.  `mc` already points at this rank's first row (col0 selects a column window for the split variant).
+__global__ void mc_reduce_rows_kernel(const __nv_bfloat16* mc, const __nv_bfloat16* __restrict__ bias,
+                                      const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ out, long long rows,
+                                      int ncols, int col0, long long ldp, long long ldr, long long ldo) {
+  const int nv = ncols >> 3;
+  const long long total = rows * nv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / nv;
+    const int c = col0 + (int)(i - r * nv) * 8;
+    const uint4 v = multimem_ld_reduce_add_bf16x8(mc + r * ldp + c);
+    uint4 o = v;
+    if (bias || residual) {
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(h[j]); acc[2 * j] = f.x; acc[2 * j + 1] = f.y; }
+      if (bias) {
+        const uint4 bv = *reinterpret_cast<const uint4*>(bias + c);
+        const __nv_bfloat162* bh = reinterpret_cast<const __nv_bfloat162*>(&bv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(bh[j]); acc[2 * j] += f.x; acc[2 * j + 1] += f.y; }
+      }
+      if (residual) {
+        const uint4 rv = *reinterpret_cast<const uint4*>(residual + r * ldr + c);
+        const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(rh[j]); acc[2 * j] += f.x; acc[2 * j + 1] += f.y; }
+      }
+      __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(acc[2 * j], acc[2 * j + 1]);
+    }
+    *reinterpret_cast<uint4*>(out + r * ldo + c) = o;
+  }
+}
+
+extern "C" int b200_mc_reduce_rows(const void* mc, const void* bias, const void* residual, void* out, long long rows, int ncols,
+                                   int col0, long long ldp, long long ldr, long long ldo, int blocks, cudaStream_t stream) {
+  if (rows <= 0 || ncols <= 0) return 0;
+  if (ncols % 8 || col0 % 8 || ldp % 8 || ldo % 8 || (residual && ldr % 8)) return -3;
+  long long want = (rows * (ncols / 8) + 255) / 256;
+  const long long cap = blocks > 0 ? blocks : 148 * 4;
+  if (want > cap) want = cap;
+  mc_reduce_rows_kernel<<<(int)want, 256, 0, stream>>>((const __nv_bfloat16*)mc, (const __nv_bfloat16*)bias,
+                                                       (const __nv_bfloat16*)residual, (__nv_bfloat16*)out, rows, ncols, col0, ldp,
+                                                       ldr, ldo);
+  return (int)cudaGetLastError();
+}
+
 // GEMM -> staged reduce-scatter: out partial tiles (bf16) are stored into slot `rank` of every owner's staging buffer
 // stage_peers[owner] ([world, M/world, ldstage] bf16, peer-mapped).  Follow with a barrier and b200_stage_reduce on the owner.
 extern "C" int b200_gemm_stage_scatter_bf16(const void* A, const void* B, void* const* stage_peers, int world, int rank, int M,

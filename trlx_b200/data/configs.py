@@ -122,6 +122,8 @@ class ParallelConfig(_Section):
 
     :param tensor_parallel: TP degree (ranks that share one replica along hidden dims)
     :param pipeline_parallel: PP degree
+    :param virtual_pipeline_parallel: model chunks per pipeline rank (interleaved 1F1B when > 1;
+        ``virtual_pipeline_model_parallel_size`` in the NeMo recipes)
     :param sequence_parallel: shard norm/dropout activations along sequence inside the TP group
     :param zero_stage: 0 = replicated optimizer (DDP-like), 1/2 = optimizer state + grads sharded
         across DP ranks (fused reduce-scatter + AdamW + all-gather), 3 = parameters sharded as well
@@ -136,6 +138,7 @@ class ParallelConfig(_Section):
 
     tensor_parallel: int = 1
     pipeline_parallel: int = 1
+    virtual_pipeline_parallel: int = 1
     sequence_parallel: bool = False
     zero_stage: int = 1
     precision: str = "bf16"

@@ -136,11 +136,53 @@ class FusedTP:
             ops.C.gemm_reduce_scatter(x, w, list(hdl.buffer_ptrs), N, bias)
             self.barrier()  # every partial sum has landed
             return ops.C.rs_finalize(acc, None, residual)
+        if os.environ.get("TRLX_B200_TP_RS_NVLS", "1") == "1" and N % 8 == 0:
+            out = self._gemm_rs_nvls(x, w, bias, residual)
+            if out is not None:
+                return out
         stage, hdl = self._symm(("rs_stage", rows, N), (self.size, rows, N), torch.bfloat16)
         self.barrier()  # the previous consumer of the staging slots is done
         ops.C.gemm_stage_scatter(x, w, list(hdl.buffer_ptrs), self.rank, N, bias)  # bias: real on one rank, zeros elsewhere
         self.barrier()  # every rank's partial tiles have landed
         return ops.C.stage_reduce(stage, None, residual)
+
+
+    def _gemm_rs_nvls(self, x, w, bias, residual):
+        """GEMM → reduce-scatter through the NVSwitch: the partial product is written LOCALLY (plain TMA-store epilogue, the GEMM
+        runs at its stand-alone speed) into a symmetric buffer that is also mapped at one multicast address; after a flag
+        barrier the owner of a row block reads it with ``multimem.ld_reduce`` — the switch adds the ``size`` copies in fp32 — and
+        applies bias / residual on the way out.  The columns are processed in ``TRLX_B200_TP_RS_SPLIT`` windows (default 2): the
+        reduction of window ``i`` runs on a side stream underneath the GEMM of window ``i + 1``."""
+        M, N = x.shape[0], w.shape[0]
+        rows = M // self.size
+        part, hdl = self._symm(("rs_part", M, N), (M, N), torch.bfloat16)
+        mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+        if mc == 0:
+            return None
+        split = int(os.environ.get("TRLX_B200_TP_RS_SPLIT", "2"))
+        while split > 1 and (N % (split * 128) or N // split < 1024):
+            split -= 1
+        out = torch.empty(rows, N, dtype=torch.bfloat16, device=x.device)
+        mine = mc + self.rank * rows * N * 2
+        main = torch.cuda.current_stream()
+        self._rs_stream = getattr(self, "_rs_stream", None) or torch.cuda.Stream(device=self.device)
+        side = self._rs_stream
+        res = residual
+        self.barrier()  # every rank has finished reducing the previous contents of the partial buffer
+        w_cols = N // split
+        for i in range(split):
+            c0 = i * w_cols
+            ops.C.gemm(x, w[c0:c0 + w_cols], None, None, "none", False, part[:, c0:c0 + w_cols])
+            self.barrier()  # this window's partials are complete on every rank
+            if i + 1 < split:
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    ops.C.mc_reduce_rows(mine, out, bias, res, c0, w_cols, N, 148)
+            else:
+                ops.C.mc_reduce_rows(mine, out, bias, res, c0, w_cols, N, 0)
+        if split > 1:
+            main.wait_stream(side)
+        return out
 
 
 def _fused_bwd() -> bool:

@@ -13,7 +13,7 @@ logger = logging.get_logger(__name__)
 
 class MegatronMixin:
     """Overrides model setup (shard after construction), the optimizer step under pipeline parallelism (1F1B over the
-    micro-batches) and checkpoint IO (``mp_rank_XX`` layout)."""
+    micro-batches, interleaved when ``virtual_pipeline_parallel`` > 1) and checkpoint IO (``mp_rank_XX`` layout)."""
 
     def __init__(self, config, **kwargs):
         tk = dict(config.train.trainer_kwargs or {})
@@ -67,7 +67,8 @@ class MegatronMixin:
         if rt.pp_size > 1:
             from trlx_b200.parallel.pipeline_parallel import apply_pipeline_parallel
 
-            apply_pipeline_parallel(model, rt.pp_group, rt.pp_rank, rt.pp_size)
+            apply_pipeline_parallel(model, rt.pp_group, rt.pp_rank, rt.pp_size,
+                                    int(getattr(self.config.train.parallel, "virtual_pipeline_parallel", 1) or 1))
         model._model_parallel_applied = True
 
     def setup_model(self):
@@ -82,7 +83,8 @@ class MegatronMixin:
         if rt.pp_size > 1:
             from trlx_b200.parallel.pipeline_parallel import apply_pipeline_parallel
 
-            self._pp_stage = apply_pipeline_parallel(model, rt.pp_group, rt.pp_rank, rt.pp_size)
+            self._pp_stage = apply_pipeline_parallel(model, rt.pp_group, rt.pp_rank, rt.pp_size,
+                                                     int(getattr(self.config.train.parallel, "virtual_pipeline_parallel", 1) or 1))
         return model
 
     def _optimizer_param_groups(self, params, optimizer_class):
@@ -121,8 +123,8 @@ class MegatronMixin:
         microbatches = list(minibatch)
         for _ in microbatches:
             self.mb_count += 1
-        per_mb = pp.run_1f1b(stage, microbatches, self.loss, self.runtime.device,
-                             before_backward=self.model.train, after_backward=self.model.eval)
+        per_mb = pp.run_schedule(stage, microbatches, self.loss, self.runtime.device,
+                                 before_backward=self.model.train, after_backward=self.model.eval)
         stats = None
         if stage.last:
             stats = {k: sum(s[k] for s in per_mb) / self.num_mb for k in per_mb[0]}

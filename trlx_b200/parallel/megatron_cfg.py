@@ -68,6 +68,7 @@ def parse_megatron_cfg(cfg) -> Dict[str, Any]:
     model = raw.get("model", raw)
     parallel = dict(tensor_parallel=int(model.get("tensor_model_parallel_size", 1)),
                     pipeline_parallel=int(model.get("pipeline_model_parallel_size", 1)),
+                    virtual_pipeline_parallel=int(model.get("virtual_pipeline_model_parallel_size") or 1),
                     sequence_parallel=bool(model.get("sequence_parallel", False)),
                     activation_checkpointing=model.get("activations_checkpoint_granularity") in ("full", "selective"))
     prec = str((raw.get("trainer") or {}).get("precision", model.get("precision", "bf16")))

@@ -65,12 +65,12 @@ class _RecvFromPrev(torch.autograd.Function):
     def forward(ctx, anchor: torch.Tensor, stage: "PipelineStage", shape, dtype):
         ctx.stage = stage
         buf = torch.empty(shape, dtype=dtype, device=anchor.device)
-        dist.recv(buf, src=stage.prev_global, group=stage.group)
+        dist.recv(buf, src=stage.ring_prev, group=stage.group)
         return buf
 
     @staticmethod
     def backward(ctx, grad):
-        dist.send(grad.contiguous(), dst=ctx.stage.prev_global, group=ctx.stage.group)
+        dist.send(grad.contiguous(), dst=ctx.stage.ring_prev, group=ctx.stage.group)
         return None, None, None, None
 
 
@@ -81,28 +81,37 @@ class _SendToNext(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x: torch.Tensor, stage: "PipelineStage"):
         ctx.stage, ctx.shape, ctx.dtype = stage, x.shape, x.dtype
-        dist.send(x.contiguous(), dst=stage.next_global, group=stage.group)
+        dist.send(x.contiguous(), dst=stage.ring_next, group=stage.group)
         return x.new_zeros(())
 
     @staticmethod
     def backward(ctx, _):
         g = torch.empty(ctx.shape, dtype=ctx.dtype, device=_.device)
-        dist.recv(g, src=ctx.stage.next_global, group=ctx.stage.group)
+        dist.recv(g, src=ctx.stage.ring_next, group=ctx.stage.group)
         return g, None
 
 
 class PipelineStage:
     """Per-LM pipeline state + the stage-local forward."""
 
-    def __init__(self, lm, group, rank: int, size: int):
+    def __init__(self, lm, group, rank: int, size: int, virtual: int = 1):
         self.lm, self.group, self.rank, self.size = lm, group, rank, size
         self.first, self.last = rank == 0, rank == size - 1
         ranks = dist.get_process_group_ranks(group) if group is not None else list(range(size))
         self.global_ranks = ranks
         self.prev_global = ranks[rank - 1] if rank > 0 else None
         self.next_global = ranks[rank + 1] if rank < size - 1 else None
+        # with virtual stages the activation travels round the ring `virtual` times: the last rank hands chunk c to chunk c + 1
+        # of the first rank
+        self.ring_prev, self.ring_next = ranks[(rank - 1) % size], ranks[(rank + 1) % size]
         self.last_global = ranks[-1]
-        self.lo, self.hi = partition_layers(len(lm.transformer.h), size)[rank]
+        L = len(lm.transformer.h)
+        self.virtual = max(1, min(int(virtual or 1), L // size)) if size > 1 else 1
+        parts = partition_layers(L, size * self.virtual)
+        # virtual stage s = c * size + rank owns `parts[s]`: every rank holds `virtual` model chunks (Megatron's interleaved layout)
+        self.chunks = [parts[c * size + rank] for c in range(self.virtual)]
+        self.lo, self.hi = self.chunks[0][0], self.chunks[-1][1]
+        self.chunk = 0  # the chunk a scheduled forward runs
         # schedule hand-off
         self.mode = "relay"  # "relay" | "schedule" | "probe"
         self.input_tensor: Optional[torch.Tensor] = None
@@ -139,38 +148,54 @@ class PipelineStage:
                 position_ids = torch.arange(past_len, past_len + T, device=device).unsqueeze(0).expand(B, T)
         grad_mode = torch.is_grad_enabled()
 
-        if self.first:
-            if inputs_embeds is not None:
-                x = inputs_embeds
-                if trunk.wpe is not None:
-                    x = x + trunk.wpe(position_ids + spec.pos_offset)
-                if trunk.emb_norm is not None:
-                    x = trunk.emb_norm(x)
-            else:
-                x = trunk.embed(input_ids, position_ids)
-        elif self.mode == "schedule":
-            x = self.input_tensor
-            assert x is not None and tuple(x.shape) == hshape, "pipeline schedule handed over a mismatched activation"
-        elif grad_mode:
-            anchor = torch.zeros((), device=device, requires_grad=True)
-            x = _RecvFromPrev.apply(anchor, self, hshape, dtype)
-        else:
-            x = torch.empty(hshape, dtype=dtype, device=device)
-            dist.recv(x, src=self.prev_global, group=self.group)
-
-        ctx = build_attn_context(spec, attention_mask, position_ids, T, past_len, x.dtype, device)
+        V = self.virtual
+        scheduled = self.mode == "schedule"
+        ctx, x, j = None, None, 0
         presents = [] if use_cache else None
-        for j, i in enumerate(range(self.lo, self.hi)):
-            past = past_key_values[j] if past_key_values else None
-            x, present = trunk.h[i](x, ctx, past, use_cache)
-            if presents is not None:
-                presents.append(present)
+        phantoms = []
+        for c in ([self.chunk] if scheduled else range(V)):
+            vfirst, vlast = self.first and c == 0, self.last and c == V - 1
+            if vfirst:
+                if inputs_embeds is not None:
+                    x = inputs_embeds
+                    if trunk.wpe is not None:
+                        x = x + trunk.wpe(position_ids + spec.pos_offset)
+                    if trunk.emb_norm is not None:
+                        x = trunk.emb_norm(x)
+                else:
+                    x = trunk.embed(input_ids, position_ids)
+            elif scheduled:
+                x = self.input_tensor
+                assert x is not None and tuple(x.shape) == hshape, "pipeline schedule handed over a mismatched activation"
+            elif grad_mode:
+                anchor = torch.zeros((), device=device, requires_grad=True)
+                x = _RecvFromPrev.apply(anchor, self, hshape, dtype)
+            else:
+                x = torch.empty(hshape, dtype=dtype, device=device)
+                dist.recv(x, src=self.ring_prev, group=self.group)
+            if ctx is None:
+                ctx = build_attn_context(spec, attention_mask, position_ids, T, past_len, x.dtype, device)
+            lo, hi = self.chunks[c]
+            for i in range(lo, hi):
+                past = past_key_values[j] if past_key_values else None
+                x, present = trunk.h[i](x, ctx, past, use_cache)
+                if presents is not None:
+                    presents.append(present)
+                j += 1
+            if vlast:
+                break
+            if scheduled:
+                self.output_tensor = x
+                raise StageBoundary()
+            # relay: hand the activation to the next rank of the ring
+            if grad_mode:
+                if not x.requires_grad:  # fully frozen chunk: the next stage still returns a gradient, consume it
+                    x = x.detach().requires_grad_(True)
+                phantoms.append(_SendToNext.apply(x, self))
+            else:
+                dist.send(x.contiguous(), dst=self.ring_next, group=self.group)
         if use_cache and not presents:  # a stage without blocks still has to report the cache length
             presents = [(x.new_zeros(B, 1, past_len + T, 1), x.new_zeros(B, 1, past_len + T, 1))]
-
-        if self.mode == "schedule" and not self.last:
-            self.output_tensor = x
-            raise StageBoundary()
 
         logits = None
         if self.last:
@@ -179,21 +204,15 @@ class PipelineStage:
                 logits = project(lm.lm_head, x)
             if self.mode == "relay":
                 self._broadcast_outputs(x, logits, compute_logits)
-        else:  # relay, non-final stage
-            phantom = None
-            if grad_mode:
-                if not x.requires_grad:  # fully frozen stage: the next stage still returns a gradient, consume it
-                    x = x.detach().requires_grad_(True)
-                phantom = _SendToNext.apply(x, self)
-            else:
-                dist.send(x.contiguous(), dst=self.next_global, group=self.group)
+        else:  # relay, a rank that does not hold the final chunk
             x = torch.empty(oshape, dtype=dtype, device=device)
             logits = torch.empty((B, T, spec.vocab_size), dtype=dtype, device=device) if compute_logits else None
             self._broadcast_outputs(x, logits, compute_logits)
-            if phantom is not None:  # ties the (complete, but constant) outputs to this stage's graph
-                x = x + phantom.to(x.dtype)
-                if logits is not None:
-                    logits = logits + phantom.to(logits.dtype)
+        if phantoms:  # ties the outputs to the graphs of the chunks whose activation left this rank
+            phantom = phantoms[0] if len(phantoms) == 1 else torch.stack(phantoms).sum()
+            x = x + phantom.to(x.dtype)
+            if logits is not None:
+                logits = logits + phantom.to(logits.dtype)
         loss = None
         if labels is not None and logits is not None:
             import torch.nn.functional as F
@@ -226,15 +245,16 @@ def _find_lm(model):
     raise TypeError("pipeline parallelism needs a decoder-only CausalLM inside the model")
 
 
-def apply_pipeline_parallel(model, group, rank: int, size: int) -> PipelineStage:
-    """Keep this stage's slice of ``model``'s decoder, free the rest, install the stage forward."""
+def apply_pipeline_parallel(model, group, rank: int, size: int, virtual: int = 1) -> PipelineStage:
+    """Keep this stage's slice(s) of ``model``'s decoder, free the rest, install the stage forward.  ``virtual`` > 1 gives
+    every rank that many non-adjacent model chunks (``virtual_pipeline_model_parallel_size`` in the NeMo recipes)."""
     lm = _find_lm(model)
     if getattr(lm, "_pp", None) is not None:
         return lm._pp
-    stage = PipelineStage(lm, group, rank, size)
+    stage = PipelineStage(lm, group, rank, size, virtual)
     trunk = lm.transformer
     for i in range(len(trunk.h)):
-        if not (stage.lo <= i < stage.hi):
+        if not any(lo <= i < hi for lo, hi in stage.chunks):
             trunk.h[i] = _Hole()
     tied = lm.lm_head.weight is trunk.wte.weight
     stage.tied = tied
@@ -259,7 +279,7 @@ def apply_pipeline_parallel(model, group, rank: int, size: int) -> PipelineStage
     lm._pp = stage
     if size > 1:  # every stage continues a generation with the token the last stage sampled (generation.sync_tokens)
         lm._sample_sync = getattr(lm, "_sample_sync", []) + [(group, stage.last_global)]
-    logger.info(f"pipeline stage {rank}/{size}: blocks [{stage.lo}, {stage.hi}) of {len(trunk.h)}"
+    logger.info(f"pipeline stage {rank}/{size}: blocks {' + '.join(f'[{lo}, {hi})' for lo, hi in stage.chunks)} of {len(trunk.h)}"
                 f"{' +embeddings' if stage.first else ''}{' +lm_head' if stage.last else ''}")
     return stage
 
@@ -388,6 +408,183 @@ def run_1f1b(stage: PipelineStage, microbatches: Sequence[Any], loss_fn: Callabl
         if not stage.first:
             _exchange(stage, send_prev=gx, **kw)
     return stats
+
+
+# ---- interleaved (virtual-stage) schedule -------------------------------------------------------------------------------------
+def interleaved_order(P: int, V: int, M: int, r: int) -> List[Tuple[str, int, int]]:
+    """The order in which rank ``r`` of ``P`` runs its ``2 * M * V`` operations ``(kind, microbatch, chunk)``.
+
+    Micro-batches advance in groups of ``P``: a rank runs chunk 0 for the whole group, then chunk 1, ... so that by the time
+    it returns to the first member of the group the activation has been round the ring once.  Backwards mirror the forwards
+    (last chunk first).  A rank starts alternating forward / backward after ``2 (P - r - 1) + (V - 1) P`` warm-up forwards,
+    which is what shrinks the bubble by ``V`` compared with plain 1F1B (reference recipes:
+    ``virtual_pipeline_model_parallel_size``, ``configs/nemo_configs/megatron_20b.yaml:53``)."""
+    seq_f: List[Tuple[str, int, int]] = []
+    seq_b: List[Tuple[str, int, int]] = []
+    for m0 in range(0, M, P):
+        group = range(m0, min(m0 + P, M))
+        for c in range(V):
+            seq_f += [("F", m, c) for m in group]
+            seq_b += [("B", m, V - 1 - c) for m in group]
+    total = M * V
+    warm = min(2 * (P - r - 1) + (V - 1) * P, total)
+    ops = seq_f[:warm]
+    for i in range(total - warm):
+        ops += [seq_f[warm + i], seq_b[i]]
+    return ops + seq_b[total - warm:]
+
+
+def interleaved_rounds(P: int, V: int, M: int) -> List[List[Optional[Tuple[str, int, int]]]]:
+    """Lock-step plan of the whole pipeline: ``rounds[t][r]`` is the operation rank ``r`` runs in round ``t`` (``None`` = idle).
+
+    Every rank derives the same plan by simulating all ranks: a rank runs the next operation of its
+    :func:`interleaved_order` as soon as the tensor it consumes was produced in an earlier round.  All transfers of a round
+    then form one matched set — rank ``a`` sends to ``b`` in round ``t`` exactly when ``b`` posts the receive in round ``t`` —
+    so each rank can issue them as a single grouped ``batch_isend_irecv`` and no ordering between neighbours can deadlock,
+    whatever ``P``, ``V`` and ``M`` are."""
+    S = P * V
+    orders = [interleaved_order(P, V, M, r) for r in range(P)]
+    ptr = [0] * P
+    have = set()  # (kind, m, virtual stage) whose input has been delivered / whose forward has run
+    rounds: List[List[Optional[Tuple[str, int, int]]]] = []
+    while any(ptr[r] < len(orders[r]) for r in range(P)):
+        acts: List[Optional[Tuple[str, int, int]]] = [None] * P
+
+        def ready(r, op):
+            kind, m, c = op
+            s = c * P + r
+            if kind == "F":
+                return s == 0 or ("F", m, s) in have
+            return ("done", m, s) in have and (s == S - 1 or ("B", m, s) in have)
+
+        for r in range(P):
+            if ptr[r] < len(orders[r]) and ready(r, orders[r][ptr[r]]):
+                acts[r] = orders[r][ptr[r]]
+        if not any(a is not None for a in acts):
+            # a micro-batch count that is not a multiple of P can leave every rank waiting on an operation that sits deeper
+            # in a neighbour's list: let each rank pull its first runnable operation forward (the dependency graph is acyclic,
+            # so one always exists)
+            for r in range(P):
+                for i in range(ptr[r], len(orders[r])):
+                    if ready(r, orders[r][i]):
+                        orders[r].insert(ptr[r], orders[r].pop(i))
+                        acts[r] = orders[r][ptr[r]]
+                        break
+        if not any(a is not None for a in acts):
+            raise RuntimeError(f"pipeline schedule cannot make progress (P={P}, V={V}, M={M})")
+        for r, a in enumerate(acts):
+            if a is None:
+                continue
+            ptr[r] += 1
+            kind, m, c = a
+            s = c * P + r
+            if kind == "F":
+                have.add(("done", m, s))
+                if s < S - 1:
+                    have.add(("F", m, s + 1))
+            elif s > 0:
+                have.add(("B", m, s - 1))
+        rounds.append(acts)
+    return rounds
+
+
+def run_interleaved(stage: PipelineStage, microbatches: Sequence[Any], loss_fn: Callable[[Any], Tuple[torch.Tensor, Dict]],
+                    device, loss_scale: float = 1.0, before_backward: Optional[Callable] = None,
+                    after_backward: Optional[Callable] = None) -> List[Optional[Dict]]:
+    """Interleaved 1F1B: every rank owns ``stage.virtual`` model chunks and a micro-batch visits each rank that many times.
+    Same contract as :func:`run_1f1b`."""
+    M, P, V, r = len(microbatches), stage.size, stage.virtual, stage.rank
+    S = P * V
+    dtype = stage.param_dtype()
+    plan = interleaved_rounds(P, V, M)
+    shapes: Dict[int, Tuple[int, ...]] = {}
+    inbox: Dict[Tuple[str, int, int], torch.Tensor] = {}
+    saved: Dict[Tuple[int, int], Tuple[Optional[torch.Tensor], torch.Tensor]] = {}
+    stats: List[Optional[Dict]] = [None] * M
+
+    def shape_of(m):
+        if m not in shapes:
+            stage.mode = "probe"
+            try:
+                with torch.no_grad():
+                    loss_fn(microbatches[m])
+                raise RuntimeError("the loss function never called the language model")
+            except StageBoundary:
+                shapes[m] = stage.probe_shape
+            finally:
+                stage.mode = "relay"
+        return shapes[m]
+
+    def forward(m, c):
+        s = c * P + r
+        x = inbox.pop(("F", m, s)) if s > 0 else None
+        if x is not None:
+            x.requires_grad_(True)
+        stage.mode, stage.chunk, stage.input_tensor, stage.output_tensor = "schedule", c, x, None
+        try:
+            loss, st = loss_fn(microbatches[m])
+            if s != S - 1:
+                raise RuntimeError("a non-final stage completed its loss function; the LM was not called")
+            out = loss * loss_scale
+            stats[m] = st
+        except StageBoundary:
+            out = stage.output_tensor
+        finally:
+            stage.mode, stage.chunk, stage.input_tensor = "relay", 0, None
+        saved[(m, c)] = (x, out)
+        return None if s == S - 1 else out.detach()
+
+    def backward(m, c):
+        s = c * P + r
+        x, y = saved.pop((m, c))
+        if before_backward is not None:
+            before_backward()
+        if s == S - 1:
+            y.backward()
+        else:
+            gy = inbox.pop(("B", m, s))
+            if y.requires_grad:  # (a fully frozen chunk has nothing to differentiate)
+                torch.autograd.backward(y, gy)
+        if after_backward is not None:
+            after_backward()
+        if x is None:
+            return None
+        return x.grad if x.grad is not None else torch.zeros_like(x)
+
+    for acts in plan:
+        mine = acts[r]
+        out = None
+        if mine is not None:
+            kind, m, c = mine
+            out = forward(m, c) if kind == "F" else backward(m, c)
+        ops = []
+        if out is not None:
+            dst = stage.ring_next if mine[0] == "F" else stage.ring_prev
+            ops.append(dist.P2POp(dist.isend, out.contiguous(), dst, stage.group))
+        for q, a in enumerate(acts):  # what the other ranks produced for this one in the same round
+            if a is None or q == r:
+                continue
+            kind, m, c = a
+            s = c * P + q
+            if kind == "F" and s < S - 1 and (q + 1) % P == r:
+                key, src = ("F", m, s + 1), stage.global_ranks[q]
+            elif kind == "B" and s > 0 and (q - 1) % P == r:
+                key, src = ("B", m, s - 1), stage.global_ranks[q]
+            else:
+                continue
+            buf = torch.empty(shape_of(m), dtype=dtype, device=device)
+            inbox[key] = buf
+            ops.append(dist.P2POp(dist.irecv, buf, src, stage.group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+    assert not saved and not inbox, "pipeline schedule finished with tensors in flight"
+    return stats if stage.last else [None] * M
+
+
+def run_schedule(stage: PipelineStage, microbatches, loss_fn, device, **kw) -> List[Optional[Dict]]:
+    """1F1B, interleaved when the stage holds more than one model chunk."""
+    return (run_interleaved if stage.virtual > 1 else run_1f1b)(stage, microbatches, loss_fn, device, **kw)
 
 
 def broadcast_stats(stage: PipelineStage, stats: Optional[Dict[str, Any]], device) -> Dict[str, Any]:
