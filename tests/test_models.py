@@ -21,6 +21,9 @@ CAUSAL = {
                   num_key_value_heads=2, intermediate_size=48, max_position_embeddings=64),
     "opt": dict(model_type="opt", vocab_size=64, hidden_size=32, num_hidden_layers=3, num_attention_heads=2, ffn_dim=64,
                 max_position_embeddings=64, word_embed_proj_dim=32),
+    # OPT-350m layout: narrower word embeddings (project_in / project_out), post-LN blocks, no final norm
+    "opt350": dict(model_type="opt", vocab_size=64, hidden_size=32, num_hidden_layers=3, num_attention_heads=2, ffn_dim=64,
+                   max_position_embeddings=64, word_embed_proj_dim=16, do_layer_norm_before=False),
     "bloom": dict(model_type="bloom", vocab_size=64, hidden_size=32, n_layer=3, n_head=2),
     "gpt_bigcode": dict(model_type="gpt_bigcode", vocab_size=64, n_embd=32, n_layer=3, n_head=2, n_positions=64),
     "gpt_neo": dict(model_type="gpt_neo", vocab_size=64, hidden_size=32, num_layers=4, num_heads=2, max_position_embeddings=64,

@@ -48,6 +48,8 @@ class ILQLDecodeEngine(RolloutEngine):
             return "needs a decoder-only bf16 model on CUDA"
         if spec.head_dim % 8 or spec.hidden_size % 8 or spec.head_dim > 256 or spec.ffn_size % 8:
             return "head_dim / hidden / ffn sizes must be multiples of 8 (head_dim <= 256)"
+        if getattr(spec, "post_norm", False) or not getattr(spec, "plain_tail", True):
+            return "post-LN blocks / embedding projections (OPT-350m layout) run on the PyTorch path"
         return None
 
     @staticmethod

@@ -235,7 +235,7 @@ class AutoModelForCausalLMWithILQLHeads(PreTrainedModelWrapper):
         super().__init__(base_model, peft_config=peft_config)
         lm = base_lm(base_model)
         self.two_qs, self.alpha = two_qs, alpha
-        self.ilql_heads = ILQLHeads(lm.config.hidden_size, lm.config.vocab_size, two_qs, alpha, dtype=lm.dtype).to(lm.device)
+        self.ilql_heads = ILQLHeads(getattr(lm.config, "final_hidden_size", None) or lm.config.hidden_size, lm.config.vocab_size, two_qs, alpha, dtype=lm.dtype).to(lm.device)
 
     def _base(self, bypass_adapter: bool = False, **kw):
         if self.peft_type == "PREFIX_TUNING" and not bypass_adapter:

@@ -266,7 +266,8 @@ def make_value_branch(base_model: nn.Module, num_value_layers_unfrozen: int) -> 
     """Value function: an MLP on the last hidden state, or (k>0) a *trainable* copy of the top-k blocks whose
     ``lm_head`` is that MLP."""
     lm = base_lm(base_model)
-    hidden = lm.config.hidden_size if hasattr(lm.config, "hidden_size") else lm.config.d_model
+    hidden = getattr(lm.config, "final_hidden_size", None) or (
+        lm.config.hidden_size if hasattr(lm.config, "hidden_size") else lm.config.d_model)
     dtype, device = lm.dtype, lm.device
     head = make_head(hidden, 1, dtype).to(device)
     if num_value_layers_unfrozen == 0:

@@ -47,6 +47,9 @@ class ArchSpec:
     mlp_bias: bool = True
     lm_head_bias: bool = False
     embed_norm: bool = False  # Bloom: LayerNorm right after the token embedding
+    embed_dim: int = 0  # OPT-350m: token embeddings / LM head live in a narrower space (project_in / project_out); 0 = hidden_size
+    post_norm: bool = False  # OPT-350m (`do_layer_norm_before=False`): norms follow the residual adds
+    final_norm: bool = True  # post-norm OPT has no final LayerNorm
     tie_word_embeddings: bool = True
     # token ids
     bos_token_id: Optional[int] = None
@@ -59,6 +62,19 @@ class ArchSpec:
     @property
     def n_embd(self) -> int:
         return self.hidden_size
+
+    @property
+    def word_embed_dim(self) -> int:
+        return self.embed_dim or self.hidden_size
+
+    @property
+    def final_hidden_size(self) -> int:
+        """Width of the final hidden state (what LM / value / Q heads consume)."""
+        return self.word_embed_dim
+
+    @property
+    def plain_tail(self) -> bool:
+        return self.final_norm and self.word_embed_dim == self.hidden_size
 
     @property
     def n_layer(self) -> int:
@@ -179,10 +195,12 @@ def spec_from_hf_config(cfg) -> ArchSpec:
                         gated_mlp=True, qkv_bias=bias, attn_out_bias=bias, mlp_bias=_get(cfg, "mlp_bias", default=False),
                         tie_word_embeddings=_get(cfg, "tie_word_embeddings", default=False), **common)
     if mt == "opt":
-        if _get(cfg, "word_embed_proj_dim", default=H) != H or not _get(cfg, "do_layer_norm_before", default=True):
-            raise NotImplementedError("OPT variants with embedding projections / post-LN (opt-350m) are not supported")
+        E = _get(cfg, "word_embed_proj_dim", default=H)
+        pre = bool(_get(cfg, "do_layer_norm_before", default=True))
         bias = _get(cfg, "enable_bias", default=True)
         return ArchSpec(family="opt", num_kv_heads=nh, head_dim=d, ffn_size=_get(cfg, "ffn_dim", default=4 * H),
+                        embed_dim=0 if E == H else E, post_norm=not pre,
+                        final_norm=pre and not _get(cfg, "_remove_final_layer_norm", default=False),
                         max_positions=_get(cfg, "max_position_embeddings", default=2048), pos_offset=2,
                         activation=_get(cfg, "activation_function", default="relu"), qkv_bias=bias, attn_out_bias=bias,
                         mlp_bias=bias, tie_word_embeddings=_get(cfg, "tie_word_embeddings", default=True), **common)
@@ -216,6 +234,9 @@ _PRESETS: Dict[str, Dict[str, Any]] = {
                        max_position_embeddings=4096, rms_norm_eps=1e-5, bos_token_id=1, eos_token_id=2),
     "opt-125m": dict(model_type="opt", vocab_size=50272, hidden_size=768, num_hidden_layers=12, num_attention_heads=12,
                      ffn_dim=3072, max_position_embeddings=2048, bos_token_id=2, eos_token_id=2, pad_token_id=1),
+    "opt-350m": dict(model_type="opt", vocab_size=50272, hidden_size=1024, num_hidden_layers=24, num_attention_heads=16,
+                     ffn_dim=4096, max_position_embeddings=2048, word_embed_proj_dim=512, do_layer_norm_before=False,
+                     bos_token_id=2, eos_token_id=2, pad_token_id=1),
     "opt-6.7b": dict(model_type="opt", vocab_size=50272, hidden_size=4096, num_hidden_layers=32, num_attention_heads=32,
                      ffn_dim=16384, max_position_embeddings=2048, bos_token_id=2, eos_token_id=2, pad_token_id=1),
     "bloom-560m": dict(model_type="bloom", vocab_size=250880, hidden_size=1024, n_layer=24, n_head=16,
@@ -230,7 +251,7 @@ _ALIASES = {
     "lvwerra/gpt2-imdb": "gpt2", "gpt2-imdb": "gpt2", "eleutherai/gpt-j-6b": "gpt-j-6b", "gptj": "gpt-j-6b",
     "eleutherai/gpt-neox-20b": "gpt-neox-20b", "eleutherai/pythia-160m": "pythia-160m",
     "meta-llama/llama-2-7b-hf": "llama-2-7b", "nousresearch/llama-2-7b-hf": "llama-2-7b",
-    "facebook/opt-125m": "opt-125m", "facebook/opt-6.7b": "opt-6.7b", "bigscience/bloom-560m": "bloom-560m",
+    "facebook/opt-125m": "opt-125m", "facebook/opt-350m": "opt-350m", "facebook/opt-6.7b": "opt-6.7b", "bigscience/bloom-560m": "bloom-560m",
     "bigcode/gpt_bigcode-santacoder": "gpt_bigcode-santacoder", "eleutherai/gpt-neo-125m": "gpt-neo-125m",
 }
 

@@ -190,6 +190,13 @@ def _group_blocks(sd: SD, prefix: str) -> Tuple[Dict[int, SD], SD]:
     return blocks, rest
 
 
+def _tail_keys(fam: FamilyMap) -> Dict[str, str]:
+    """Canonical → HF module names of the OPT-350m extras (final norm inside ``Tail``, project_in / project_out)."""
+    base = fam.ln_f.rpartition(".")[0]
+    return {"transformer.ln_f.norm": fam.ln_f, "transformer.ln_f.project_out": f"{base}.project_out",
+            "transformer.project_in": f"{base}.project_in"}
+
+
 def to_hf(spec: ArchSpec, canonical: SD) -> SD:
     """Full-model canonical state dict → HF key names/layouts."""
     fam = family(spec)
@@ -197,6 +204,7 @@ def to_hf(spec: ArchSpec, canonical: SD) -> SD:
     out: SD = {}
     top = {"transformer.wte": fam.wte, "transformer.wpe": fam.wpe, "transformer.ln_f": fam.ln_f,
            "lm_head": fam.lm_head, "transformer.emb_norm": fam.emb_norm}
+    top.update(_tail_keys(fam))
     for k, v in rest.items():
         mod, _, suffix = k.rpartition(".")
         if mod in top and top[mod]:
@@ -219,6 +227,10 @@ def from_hf(spec: ArchSpec, hf: SD) -> SD:
         top[fam.wpe] = "transformer.wpe"
     if fam.emb_norm:
         top[fam.emb_norm] = "transformer.emb_norm"
+    if not spec.plain_tail:
+        top[fam.ln_f] = "transformer.ln_f.norm"
+    if spec.word_embed_dim != spec.hidden_size:
+        top.update({hf: ours for ours, hf in _tail_keys(fam).items() if ours != "transformer.ln_f.norm"})
     for k, v in rest.items():
         mod, _, suffix = k.rpartition(".")
         if mod in top:

@@ -206,6 +206,10 @@ class Block(nn.Module):
         self.mlp = MLP(spec, dtype)
 
     def forward(self, x, ctx: AttnContext, past=None, use_cache=False):
+        if self.spec.post_norm:  # OPT-350m: attention / MLP read the raw stream, the norm follows the residual add
+            a, present = self.attn(x, ctx, past, use_cache)
+            x = self.norm1(x + a)
+            return self.norm2(x + self.mlp(x)), present
         if self.spec.parallel_residual:
             n1 = self.norm1(x)
             a, present = self.attn(n1, ctx, past, use_cache)
@@ -250,6 +254,22 @@ def build_attn_context(spec: ArchSpec, attention_mask: Optional[torch.Tensor], p
     return AttnContext(bias=bias, cos=cos, sin=sin, local_bias=local_bias)
 
 
+class Tail(nn.Module):
+    """What follows the last block when it is not a plain norm: optional final norm, then ``project_out`` down to the
+    word-embedding width (OPT-350m, HF ``OPTDecoder.final_layer_norm`` / ``project_out``)."""
+
+    def __init__(self, spec: ArchSpec, dtype=None):
+        super().__init__()
+        self.norm = Norm(spec, dtype) if spec.final_norm else None
+        E = spec.word_embed_dim
+        self.project_out = nn.Linear(spec.hidden_size, E, bias=False, dtype=dtype) if E != spec.hidden_size else None
+
+    def forward(self, x):
+        if self.norm is not None:
+            x = self.norm(x)
+        return x if self.project_out is None else self.project_out(x)
+
+
 class Trunk(nn.Module):
     """Embeddings + blocks + final norm (attribute names chosen so the generic ``hf_get_*`` getters find
     them: ``transformer.h`` / ``transformer.ln_f``)."""
@@ -257,17 +277,21 @@ class Trunk(nn.Module):
     def __init__(self, spec: ArchSpec, dtype=None):
         super().__init__()
         self.spec = spec
-        self.wte = nn.Embedding(spec.vocab_size, spec.hidden_size, dtype=dtype)
+        E = spec.word_embed_dim
+        self.wte = nn.Embedding(spec.vocab_size, E, dtype=dtype)
+        self.project_in = nn.Linear(E, spec.hidden_size, bias=False, dtype=dtype) if E != spec.hidden_size else None
         self.wpe = (nn.Embedding(spec.max_positions + spec.pos_offset, spec.hidden_size, dtype=dtype)
                     if spec.pos == "learned" else None)
         self.emb_norm = None
         if spec.embed_norm:
             self.emb_norm = Norm(spec, dtype)
         self.h = nn.ModuleList([Block(spec, i, dtype) for i in range(spec.num_layers)])
-        self.ln_f = Norm(spec, dtype)
+        self.ln_f = Norm(spec, dtype) if spec.plain_tail else Tail(spec, dtype)
 
-    def embed(self, input_ids, position_ids):
-        x = self.wte(input_ids)
+    def embed(self, input_ids, position_ids, inputs_embeds=None):
+        x = self.wte(input_ids) if inputs_embeds is None else inputs_embeds
+        if self.project_in is not None:
+            x = self.project_in(x)
         if self.wpe is not None:
             x = x + self.wpe(position_ids + self.spec.pos_offset)
         if self.emb_norm is not None:
@@ -283,7 +307,7 @@ class CausalLM(nn.Module):
         super().__init__()
         self.config = spec
         self.transformer = Trunk(spec, dtype)
-        self.lm_head = nn.Linear(spec.hidden_size, spec.vocab_size, bias=spec.lm_head_bias, dtype=dtype)
+        self.lm_head = nn.Linear(spec.word_embed_dim, spec.vocab_size, bias=spec.lm_head_bias, dtype=dtype)
         self.reset_parameters()
         if spec.tie_word_embeddings:
             self.lm_head.weight = self.transformer.wte.weight
@@ -353,14 +377,8 @@ class CausalLM(nn.Module):
 
         if hidden_in is not None:
             x = hidden_in
-        elif inputs_embeds is not None:
-            x = inputs_embeds
-            if trunk.wpe is not None:
-                x = x + trunk.wpe(position_ids + spec.pos_offset)
-            if trunk.emb_norm is not None:
-                x = trunk.emb_norm(x)
         else:
-            x = trunk.embed(input_ids, position_ids)
+            x = trunk.embed(input_ids, position_ids, inputs_embeds)
 
         ctx = build_attn_context(spec, attention_mask, position_ids, T, past_len, x.dtype, device)
         stop = len(trunk.h) if stop_layer is None else stop_layer

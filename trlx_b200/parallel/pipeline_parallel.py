@@ -130,13 +130,13 @@ class PipelineStage:
         ref = inputs_embeds if inputs_embeds is not None else input_ids
         B, T = ref.shape[0], ref.shape[1]
         device, dtype = ref.device, self.param_dtype()
-        oshape = (B, T, spec.hidden_size)
+        oshape = (B, T, spec.final_hidden_size)
         # with sequence parallelism the residual stream between blocks — and therefore every stage boundary — is this tensor-
         # parallel rank's 1 / tp slice of the sequence: each TP rank relays its own shard to the same TP rank of the next stage
         # (the reference runs TP x PP with SP on, configs/nemo_configs/megatron_65b.yaml:47-50,80)
         tpc = getattr(lm, "_tp_context", None)
         sp_on = tpc is not None and tpc.sp
-        hshape = (B, T // tpc.size, spec.hidden_size) if sp_on else oshape
+        hshape = (B, T // tpc.size, spec.hidden_size) if sp_on else (B, T, spec.hidden_size)
         if self.mode == "probe":
             self.probe_shape = hshape
             raise StageBoundary()
@@ -156,14 +156,7 @@ class PipelineStage:
         for c in ([self.chunk] if scheduled else range(V)):
             vfirst, vlast = self.first and c == 0, self.last and c == V - 1
             if vfirst:
-                if inputs_embeds is not None:
-                    x = inputs_embeds
-                    if trunk.wpe is not None:
-                        x = x + trunk.wpe(position_ids + spec.pos_offset)
-                    if trunk.emb_norm is not None:
-                        x = trunk.emb_norm(x)
-                else:
-                    x = trunk.embed(input_ids, position_ids)
+                x = trunk.embed(input_ids, position_ids, inputs_embeds)
             elif scheduled:
                 x = self.input_tensor
                 assert x is not None and tuple(x.shape) == hshape, "pipeline schedule handed over a mismatched activation"

@@ -332,6 +332,8 @@ def apply_tensor_parallel(model, group, rank: int, size: int, sequence_parallel:
     All ranks must hold identical full weights when this is called (same seed / same checkpoint)."""
     tp = TPContext(group, rank, size, sequence_parallel)
     lm = base_lm(getattr(model, "base_model", model))
+    if getattr(lm.config, "post_norm", False) or not getattr(lm.config, "plain_tail", True):
+        raise NotImplementedError("tensor parallelism does not cover the OPT-350m layout (post-LN blocks, project_in / project_out)")
     blocks = list(lm.transformer.h)
     for extra in ("frozen_head", "v_head"):
         branch = getattr(model, extra, None)

@@ -124,7 +124,8 @@ def hf_get_lm_head(model: nn.Module) -> nn.Module:
 
 
 def hf_get_hidden_size(config) -> int:
-    return findattr(config, ("hidden_size", "n_embd", "d_model"))
+    # `final_hidden_size`: ArchSpec of a model whose last hidden state is narrower than the residual stream (OPT-350m project_out)
+    return findattr(config, ("final_hidden_size", "hidden_size", "n_embd", "d_model"))
 
 
 def hf_get_num_hidden_layers(config) -> int:
