@@ -559,6 +559,45 @@ def test_adamw_flat(C):
     torch.testing.assert_close(param.float(), rw, atol=2e-2, rtol=1e-2)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("decoupled", [True, False])
+def test_adam8bit_kernel_matches_block_quantised_reference(C, dtype, decoupled):
+    """One launch per tensor (decode, update, block maxima, re-encode) against the PyTorch implementation of the same
+    code book, which itself tracks fp32 AdamW (tests/test_utils.py)."""
+    from trlx_b200.parallel import optim as O
+
+    torch.manual_seed(3)
+    n = 70001  # not a multiple of the 256-element block
+    w0 = torch.randn(n, device="cuda")
+    cls = O.AdamW8bit if decoupled else O.Adam8bit
+    pk = torch.nn.Parameter(w0.to(dtype).clone())
+    pr = torch.nn.Parameter(w0.to(dtype).clone())
+    ok, orf = cls([pk], lr=1e-2, weight_decay=0.05), cls([pr], lr=1e-2, weight_decay=0.05)
+    orf._kernel_ok = lambda p: False  # PyTorch path
+    fp = torch.nn.Parameter(w0.clone())
+    o32 = (torch.optim.AdamW if decoupled else torch.optim.Adam)([fp], lr=1e-2, weight_decay=0.05)
+    from trlx_b200 import ops as _ops
+
+    before = _ops.launch_count()
+    for step in range(6):
+        g = torch.randn(n, device="cuda") * (0.1 + step)
+        pk.grad, pr.grad, fp.grad = g.to(dtype), g.to(dtype), g.to(dtype).float()
+        ok.step(); orf.step(); o32.step()
+    assert _ops.launch_count() - before >= 6  # the kernel ran (no silent fallback)
+    st_k, st_r = ok.state[pk], orf.state[pr]
+    assert st_k["m"].dtype == torch.int8 and st_k["v"].dtype == torch.uint8
+    # codes may differ by one step where exp2f / log2f round differently: compare decoded moments and parameters
+    mk = O._dequantize(st_k["m"], st_k["ms"], n, True, (n,))
+    mr = O._dequantize(st_r["m"], st_r["ms"], n, True, (n,))
+    vk = O._dequantize(st_k["v"], st_k["vs"], n, False, (n,))
+    vr = O._dequantize(st_r["v"], st_r["vs"], n, False, (n,))
+    assert ((mk - mr).abs() <= 0.2 * mr.abs() + 1e-6).float().mean() > 0.999
+    assert ((vk - vr).abs() <= 0.1 * vr.abs() + 1e-9).float().mean() > 0.999
+    tol = 2e-2 if dtype == torch.bfloat16 else 5e-3
+    assert (pk.float() - pr.float()).abs().max() < tol
+    assert (pk.float() - fp).abs().mean() < 1e-2  # and both stay close to fp32 Adam
+
+
 def test_linear_autograd():
     torch.manual_seed(13)
     from trlx_b200 import ops

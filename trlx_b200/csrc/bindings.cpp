@@ -59,6 +59,8 @@ int b200_ppo_loss(const float*, const float*, const float*, const float*, const 
                   float, float, float*, float*, float*, int, float*, int, const int*, cudaStream_t);
 int b200_rollout_rewards(const float*, const float*, const float*, const long long*, const float*, int, int, int, float, float*,
                          float*, float*, int*, double*, cudaStream_t);
+int b200_adam8bit(void*, const void*, int, void*, float*, void*, float*, long long, float, float, float, float, int, float, float,
+                  float, cudaStream_t);
 int b200_adamw_flat(void*, float*, const void*, int, float*, float*, long long, float, float, float, float, int, const float*,
                     cudaStream_t);
 int b200_sqnorm(const void*, int, long long, double*, cudaStream_t);
@@ -693,6 +695,23 @@ std::vector<Tensor> rollout_rewards(const Tensor& lp, const Tensor& ref_lp, cons
   return {rewards, lp_out, v_out, slice_len, kl};
 }
 
+// 8-bit-state AdamW step on one parameter tensor (in place): mq int8 / vq uint8 codes padded to 256-element blocks + fp32 block scales
+void adam8bit(Tensor& param, const Tensor& grad, Tensor& mq, Tensor& mscale, Tensor& vq, Tensor& vscale, double lr, double beta1,
+              double beta2, double eps, double weight_decay, bool decoupled, int64_t step) {
+  TORCH_CHECK(param.is_cuda() && param.is_contiguous() && grad.is_contiguous() && grad.scalar_type() == param.scalar_type());
+  TORCH_CHECK(param.scalar_type() == at::kFloat || param.scalar_type() == at::kBFloat16, "adam8bit: fp32 or bf16 parameters");
+  const int64_t n = param.numel(), blocks = (n + 255) / 256;
+  TORCH_CHECK(mq.scalar_type() == at::kChar && vq.scalar_type() == at::kByte && mq.numel() == blocks * 256 && vq.numel() == blocks * 256);
+  CHECK_F32(mscale); CHECK_F32(vscale);
+  TORCH_CHECK(mscale.numel() == blocks && vscale.numel() == blocks && mq.is_contiguous() && vq.is_contiguous());
+  c10::cuda::CUDAGuard guard(param.device());
+  const double bc1 = 1.0 - std::pow(beta1, (double)step), bc2 = 1.0 - std::pow(beta2, (double)step);
+  check(b200_adam8bit(param.data_ptr(), grad.data_ptr(), param.scalar_type() == at::kFloat, mq.data_ptr(), mscale.data_ptr<float>(),
+                      vq.data_ptr(), vscale.data_ptr<float>(), n, (float)beta1, (float)beta2, (float)eps, (float)weight_decay,
+                      decoupled ? 1 : 0, (float)lr, (float)bc1, (float)bc2, stream()),
+        "adam8bit");
+}
+
 void adamw_flat(Tensor& param, Tensor& master, const Tensor& grad, Tensor& exp_avg, Tensor& exp_avg_sq, double beta1,
                 double beta2, double eps, double weight_decay, bool decoupled, const Tensor& hyper) {
   CHECK_BF16(param); CHECK_F32(master); CHECK_F32(exp_avg); CHECK_F32(exp_avg_sq); CHECK_F32(hyper);
@@ -1085,6 +1104,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("adv"), py::arg("ret"), py::arg("mask"), py::arg("clip"), py::arg("clip_v"), py::arg("vf_coef"),
         py::arg("width_tensor") = py::none());
   m.def("adamw_flat", &adamw_flat);
+  m.def("adam8bit", &adam8bit);
   m.def("sqnorm_", &sqnorm_);
   m.def("clip_coef_", &clip_coef_, py::arg("sqsum"), py::arg("max_norm"), py::arg("hyper"), py::arg("norm_out") = py::none());
   m.def("signal_barrier", &signal_barrier);

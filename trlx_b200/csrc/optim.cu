@@ -53,6 +53,78 @@ adamw_flat_kernel(__nv_bfloat16* __restrict__ param, float* __restrict__ master,
   }
 }
 
+// ---- 8-bit-state AdamW (bitsandbytes' Adam8bit / AdamW8bit role) ----------------------------------------------------------------
+// One CTA per 256-element block: decode both moments (log-domain codes x per-block fp32 absmax), apply the update in fp32,
+// reduce the new block maxima in shared memory, re-encode.  First moment: sign + 1/4-octave magnitude (codes +-1..127, 0 = exact
+// zero); second moment: 1/8-octave magnitude (codes 1..255).  Same code book as the PyTorch fallback in parallel/optim.py, so
+// optimizer state moves freely between the two.  Parameters / gradients are bf16 or fp32.
+__device__ __forceinline__ float block_max_256(float x, float* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, o));
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = x;
+  __syncthreads();
+  float r = sh[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) r = fmaxf(r, sh[i]);
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(256)
+adam8bit_kernel(void* __restrict__ param, const void* __restrict__ grad, int is_f32, signed char* __restrict__ mq,
+                float* __restrict__ mscale, unsigned char* __restrict__ vq, float* __restrict__ vscale, long long n, AdamArgs a,
+                float lr, float bc1, float bc2) {
+  __shared__ float sh[8];
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  const bool live = i < n;
+  float w = 0.f, g = 0.f;
+  if (live) {
+    w = is_f32 ? reinterpret_cast<float*>(param)[i] : __bfloat162float(reinterpret_cast<__nv_bfloat16*>(param)[i]);
+    g = is_f32 ? reinterpret_cast<const float*>(grad)[i] : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(grad)[i]);
+  }
+  const int cm = mq[i], cv = vq[i];  // state buffers are padded to whole blocks
+  const float ms = mscale[blockIdx.x], vs = vscale[blockIdx.x];
+  float m = cm == 0 ? 0.f : exp2f(((float)abs(cm) - 127.f) * 0.25f) * (cm < 0 ? -ms : ms);
+  float v = cv == 0 ? 0.f : exp2f(((float)cv - 255.f) * 0.125f) * vs;
+  if (live) {
+    if (!a.decoupled && a.weight_decay != 0.f) g += a.weight_decay * w;
+    m = a.beta1 * m + (1.f - a.beta1) * g;
+    v = a.beta2 * v + (1.f - a.beta2) * g * g;
+    if (a.decoupled && a.weight_decay != 0.f) w *= 1.f - lr * a.weight_decay;
+    w -= lr * (m / bc1) / (sqrtf(v / bc2) + a.eps);
+    if (is_f32) reinterpret_cast<float*>(param)[i] = w;
+    else reinterpret_cast<__nv_bfloat16*>(param)[i] = __float2bfloat16(w);
+  } else {
+    m = 0.f; v = 0.f;
+  }
+  const float nms = fmaxf(block_max_256(fabsf(m), sh), 1e-12f);
+  const float nvs = fmaxf(block_max_256(v, sh), 1e-12f);
+  int qm = 0, qv = 0;
+  if (m != 0.f) {
+    const float lg = log2f(fmaxf(fabsf(m) / nms, 9.094947e-13f));  // 2^-40
+    qm = (int)fminf(fmaxf(rintf(127.f + 4.f * lg), 1.f), 127.f);
+    if (m < 0.f) qm = -qm;
+  }
+  if (v > 0.f) {
+    const float lg = log2f(fmaxf(v / nvs, 9.094947e-13f));
+    qv = (int)fminf(fmaxf(rintf(255.f + 8.f * lg), 1.f), 255.f);
+  }
+  mq[i] = (signed char)qm;
+  vq[i] = (unsigned char)qv;
+  if (threadIdx.x == 0) { mscale[blockIdx.x] = nms; vscale[blockIdx.x] = nvs; }
+}
+
+extern "C" int b200_adam8bit(void* param, const void* grad, int is_f32, void* mq, float* mscale, void* vq, float* vscale,
+                             long long n, float beta1, float beta2, float eps, float weight_decay, int decoupled, float lr,
+                             float bc1, float bc2, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  AdamArgs a{beta1, beta2, eps, weight_decay, decoupled};
+  const long long blocks = (n + 255) / 256;
+  adam8bit_kernel<<<(unsigned)blocks, 256, 0, stream>>>(param, grad, is_f32, (signed char*)mq, mscale, (unsigned char*)vq, vscale, n,
+                                                        a, lr, bc1, bc2);
+  return (int)cudaGetLastError();
+}
+
 // sum of squares of a flat bf16/fp32 buffer -> out[0] (double, atomically accumulated; caller zeroes)
 __global__ void __launch_bounds__(256) sqnorm_kernel(const void* __restrict__ x, int is_f32, long long n, double* __restrict__ out) {
   float s = 0.f;

@@ -151,7 +151,7 @@ class FusedTP:
         """GEMM → reduce-scatter through the NVSwitch: the partial product is written LOCALLY (plain TMA-store epilogue, the GEMM
         runs at its stand-alone speed) into a symmetric buffer that is also mapped at one multicast address; after a flag
         barrier the owner of a row block reads it with ``multimem.ld_reduce`` — the switch adds the ``size`` copies in fp32 — and
-        applies bias / residual on the way out.  The columns are processed in ``TRLX_B200_TP_RS_SPLIT`` windows (default 2): the
+        adds the residual on the way out.  The columns are processed in ``TRLX_B200_TP_RS_SPLIT`` windows (default 2): the
         reduction of window ``i`` runs on a side stream underneath the GEMM of window ``i + 1``."""
         M, N = x.shape[0], w.shape[0]
         rows = M // self.size
@@ -172,14 +172,16 @@ class FusedTP:
         w_cols = N // split
         for i in range(split):
             c0 = i * w_cols
-            ops.C.gemm(x, w[c0:c0 + w_cols], None, None, "none", False, part[:, c0:c0 + w_cols])
+            # the bias rides in the partial product of the one rank that was handed it (callers pass it on a single rank)
+            ops.C.gemm(x, w[c0:c0 + w_cols], None if bias is None else bias[c0:c0 + w_cols], None, "none", False,
+                       part[:, c0:c0 + w_cols])
             self.barrier()  # this window's partials are complete on every rank
             if i + 1 < split:
                 side.wait_stream(main)
                 with torch.cuda.stream(side):
-                    ops.C.mc_reduce_rows(mine, out, bias, res, c0, w_cols, N, 148)
+                    ops.C.mc_reduce_rows(mine, out, None, res, c0, w_cols, N, 148)
             else:
-                ops.C.mc_reduce_rows(mine, out, bias, res, c0, w_cols, N, 0)
+                ops.C.mc_reduce_rows(mine, out, None, res, c0, w_cols, N, 0)
         if split > 1:
             main.wait_stream(side)
         return out

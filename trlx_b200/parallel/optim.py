@@ -11,7 +11,8 @@ the B200 replacement for DDP / DeepSpeed ZeRO-1/2 + ``torch.optim.AdamW`` used b
 On CPU / fp32 parameters the classes fall back to the equivalent ``torch.optim`` implementation (with an explicit
 gradient all-reduce across ranks), so the trainers behave identically in gloo tests.
 
-``Adam8bit`` / ``AdamW8bit`` keep the moments block-quantised to 8 bits (256-element blocks, absmax scales) — an
+``Adam8bit`` / ``AdamW8bit`` keep the moments block-quantised to 8 bits (256-element blocks, absmax scales; on a GPU one
+``adam8bit_kernel`` launch per tensor decodes, updates and re-encodes them) — an
 in-repo stand-in for ``bitsandbytes`` (reference: ``trlx/utils/__init__.py:104-123``).
 """
 from __future__ import annotations
@@ -564,6 +565,15 @@ class AdamW8bit(Optimizer):
         super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay))
         self.min_8bit_size = min_8bit_size
 
+    @staticmethod
+    def _kernel_ok(p) -> bool:
+        if not (p.is_cuda and p.is_contiguous() and p.grad.is_contiguous() and p.grad.dtype == p.dtype
+                and p.dtype in (torch.bfloat16, torch.float32)):
+            return False
+        from trlx_b200 import ops
+
+        return ops.available() and hasattr(ops.C, "adam8bit")
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None
@@ -584,6 +594,13 @@ class AdamW8bit(Optimizer):
                     else:
                         st["m"], st["v"] = z, z.clone()
                 st["step"] += 1
+                if st["q8"] and self._kernel_ok(p):
+                    # one launch per tensor: decode, update, block maxima, re-encode (csrc/optim.cu: adam8bit_kernel)
+                    from trlx_b200 import ops
+
+                    ops.C.adam8bit(p.data, p.grad, st["m"].view(-1), st["ms"], st["v"].view(-1), st["vs"], float(g["lr"]), float(b1),
+                                   float(b2), float(g["eps"]), float(g["weight_decay"]), bool(self.decoupled), int(st["step"]))
+                    continue
                 if st["q8"]:
                     m = _dequantize(st["m"], st["ms"], p.numel(), True, p.shape)
                     v = _dequantize(st["v"], st["vs"], p.numel(), False, p.shape)
