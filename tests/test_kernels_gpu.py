@@ -619,6 +619,42 @@ def test_linear_autograd():
         torch.testing.assert_close(a.float(), bb.float(), atol=2e-2 * scale, rtol=5e-2)
 
 
+def test_wgrad_accumulates_in_place_into_flat_grad_buffer():
+    """``gradient_accumulation_fusion``: with the fused optimizer owning the gradients, the weight-gradient GEMM adds into
+    ``.grad`` itself (no dW tensor, no AccumulateGrad add) — over several micro-batches the result equals autograd's."""
+    from trlx_b200.ops import functional as Fn
+    from trlx_b200.parallel.optim import FusedAdamW
+
+    torch.manual_seed(5)
+    lin = torch.nn.Linear(256, 384, bias=True).cuda().to(torch.bfloat16)
+    ref = torch.nn.Linear(256, 384, bias=True).cuda().to(torch.bfloat16)
+    ref.load_state_dict(lin.state_dict())
+    opt = FusedAdamW(list(lin.parameters()), lr=1e-3, process_group=None).prepare()
+    assert Fn.mark_inplace_wgrad(lin) == 1 and lin.weight._b200_inplace_ok
+    fired = []
+    lin.weight._b200_grad_sink = lambda: fired.append(1)
+    flat_ptr = lin.weight.grad.data_ptr()
+    xs = [(torch.randn(4, 96, 256, device="cuda") * 0.5).to(torch.bfloat16) for _ in range(3)]
+    for x in xs:
+        xa = x.clone().requires_grad_(True)
+        Fn.linear(xa, lin.weight, lin.bias).float().pow(2).sum().backward()
+        xb = x.clone().requires_grad_(True)
+        torch.nn.functional.linear(xb, ref.weight, ref.bias).float().pow(2).sum().backward()
+        torch.testing.assert_close(xa.grad.float(), xb.grad.float(), atol=2e-1, rtol=2e-2)
+    assert lin.weight.grad.data_ptr() == flat_ptr and len(fired) == 3  # accumulated in place, callback once per backward
+    gw, gr = lin.weight.grad.float(), ref.weight.grad.float()
+    assert (gw - gr).abs().max() <= 2e-2 * gr.abs().max() + 1e-2
+    torch.testing.assert_close(lin.bias.grad.float(), ref.bias.grad.float(), atol=5e-1, rtol=3e-2)
+    # a weight used twice in one graph: the callback fires after the second contribution only
+    fired.clear()
+    opt.zero_grad()
+    x = xs[0].clone().requires_grad_(True)
+    (Fn.linear(x, lin.weight, lin.bias).float().sum() + Fn.linear(x * 2, lin.weight, lin.bias).float().sum()).backward()
+    assert len(fired) == 1
+    expect = torch.ones(4 * 96, 384, device="cuda").t() @ (3 * xs[0].float().reshape(-1, 256))
+    assert (lin.weight.grad.float() - expect).abs().max() <= 2e-2 * expect.abs().max() + 1e-2
+
+
 def test_fused_logprob_autograd():
     torch.manual_seed(14)
     from trlx_b200 import ops

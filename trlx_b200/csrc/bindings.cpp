@@ -44,7 +44,7 @@ int b200_norm_quant_fp8(const void*, const void*, const void*, void*, float*, in
 int b200_gemm_bf16_ln(const void*, const void*, void*, int, int, int, long long, long long, long long, const void*, const void*,
                       long long, int, const float*, const float*, float, int, float*, cudaStream_t);
 int b200_gemm_bf16_ex(const void*, const void*, void*, int, int, int, long long, long long, long long, int, int, int, int, float*,
-                      cudaStream_t);
+                      int, cudaStream_t);
 int b200_gemm_splitk_plan(int, int, int);
 int b200_lmhead_dlogits_bf16(const void*, const void*, void*, int, int, int, long long, long long, long long, const void*,
                              const long long*, const float*, const float*, cudaStream_t);
@@ -232,7 +232,8 @@ std::vector<Tensor> norm_quant(const Tensor& x, const Tensor& w, const OptTensor
 
 // out[M, N] = sum_k A(m, k) B(n, k) with either operand optionally MN-major (stored transposed: A as [K, M], B as [K, N]).
 // These are the layouts of the backward GEMMs (dX = dY·W, dW = dYᵀ·X) — no transposed copies are made.
-Tensor gemm_ex(const Tensor& a, const Tensor& b, bool a_mn, bool b_mn, bool out_f32, int64_t split_k) {
+Tensor gemm_ex(const Tensor& a, const Tensor& b, bool a_mn, bool b_mn, bool out_f32, int64_t split_k, const OptTensor& out_,
+               bool accumulate) {
   CHECK_BF16(a); CHECK_BF16(b);
   TORCH_CHECK(a.dim() == 2 && b.dim() == 2 && a.stride(1) == 1 && b.stride(1) == 1, "gemm_ex: operands must be row-major 2-D");
   const int64_t M = a_mn ? a.size(1) : a.size(0), Ka = a_mn ? a.size(0) : a.size(1);
@@ -244,10 +245,19 @@ Tensor gemm_ex(const Tensor& a, const Tensor& b, bool a_mn, bool b_mn, bool out_
   const int splits = split_k < 0 ? b200_gemm_splitk_plan((int)M, (int)N, (int)Ka) : (int)std::max<int64_t>(split_k, 1);
   Tensor ws;
   if (splits > 1) ws = torch::zeros({M, N}, a.options().dtype(at::kFloat));  // partial products are red.add'ed into it
-  Tensor out = (splits > 1 && out_f32) ? ws : torch::empty({M, N}, a.options().dtype(out_f32 ? at::kFloat : at::kBFloat16));
+  Tensor out;
+  if (out_.has_value()) {  // caller-provided destination (accumulate: out += a.b — weight gradients added straight into .grad)
+    out = *out_;
+    CHECK_BF16(out);
+    TORCH_CHECK(!out_f32 && out.dim() == 2 && out.size(0) == M && out.size(1) == N && out.stride(1) == 1 && out.stride(0) % 8 == 0 &&
+                reinterpret_cast<uintptr_t>(out.data_ptr()) % 16 == 0, "gemm_ex: bad out");
+  } else {
+    TORCH_CHECK(!accumulate, "gemm_ex: accumulate needs out");
+    out = (splits > 1 && out_f32) ? ws : torch::empty({M, N}, a.options().dtype(out_f32 ? at::kFloat : at::kBFloat16));
+  }
   check(b200_gemm_bf16_ex(a.data_ptr(), b.data_ptr(), out.data_ptr(), (int)M, (int)N, (int)Ka, a.stride(0), b.stride(0),
                           out.stride(0), a_mn ? 1 : 0, b_mn ? 1 : 0, out_f32 ? 1 : 0, splits,
-                          splits > 1 ? ws.data_ptr<float>() : nullptr, stream()),
+                          splits > 1 ? ws.data_ptr<float>() : nullptr, accumulate ? 1 : 0, stream()),
         "gemm_ex");
   return out;
 }
@@ -1077,7 +1087,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("residual") = py::none(), py::arg("col0") = 0, py::arg("ncols") = 0, py::arg("ldp") = 0, py::arg("blocks") = 0);
   m.def("stage_reduce", &stage_reduce, py::arg("stage"), py::arg("bias") = py::none(), py::arg("residual") = py::none());
   m.def("gemm_ex", &gemm_ex, py::arg("a"), py::arg("b"), py::arg("a_mn") = false, py::arg("b_mn") = false,
-        py::arg("out_f32") = false, py::arg("split_k") = -1);
+        py::arg("out_f32") = false, py::arg("split_k") = -1, py::arg("out") = py::none(), py::arg("accumulate") = false);
   m.def("gemm_splitk_plan", [](int64_t m, int64_t n, int64_t k) { return (int64_t)b200_gemm_splitk_plan((int)m, (int)n, (int)k); },
         py::arg("m"), py::arg("n"), py::arg("k"));
   m.def("lmhead_tiles", [](int64_t n) { return (int64_t)b200_lmhead_tiles((int)n); }, py::arg("vocab"));

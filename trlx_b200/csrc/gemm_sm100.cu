@@ -1553,11 +1553,12 @@ static int splitk_plan(int M, int N, int K, int* bn_out) {
 extern "C" int b200_gemm_splitk_plan(int M, int N, int K) { return splitk_plan(M, N, K, nullptr); }
 
 __global__ void splitk_finalize_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ out, long long rows, int N,
-                                       long long ldo) {
+                                       long long ldo, int accumulate) {
   const long long total = rows * N;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / N;
-    out[r * ldo + (i - r * N)] = __float2bfloat16(acc[i]);
+    __nv_bfloat16* o = out + r * ldo + (i - r * N);
+    *o = __float2bfloat16(accumulate ? acc[i] + __bfloat162float(*o) : acc[i]);  // accumulate: out += product (wgrad into .grad)
   }
 }
 
@@ -1567,12 +1568,16 @@ __global__ void splitk_finalize_kernel(const float* __restrict__ acc, __nv_bfloa
 // lda / ldb are the row pitches of the arrays as stored.  bf16 (or fp32) output.
 // k_splits > 1 (from b200_gemm_splitk_plan) needs `ws`: a ZEROED fp32 [M, N] buffer the partial products are added into
 // (red.global.add.v4.f32 from the epilogue); it is then converted into `out` (or is the result itself when out_f32).
+// accumulate != 0 (bf16 out only): out += product — the weight-gradient GEMM adds straight into the parameter's .grad (Apex's
+// gradient_accumulation_fusion): the existing value rides in as the epilogue's residual operand, or is added by the split-K finalize.
 extern "C" int b200_gemm_bf16_ex(const void* A, const void* B, void* out, int M, int N, int K, long long lda, long long ldb,
-                                 long long ldo, int a_mn, int b_mn, int out_f32, int k_splits, float* ws,
+                                 long long ldo, int a_mn, int b_mn, int out_f32, int k_splits, float* ws, int accumulate,
                                  cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if (accumulate && out_f32) return -3;
   if (!a_mn && !b_mn && k_splits <= 1)
-    return b200_gemm_bf16(A, B, out, M, N, K, lda, ldb, ldo, nullptr, nullptr, 0, nullptr, 1.0f, ACT_NONE, out_f32, 0, stream);
+    return b200_gemm_bf16(A, B, out, M, N, K, lda, ldb, ldo, nullptr, accumulate ? out : nullptr, accumulate ? ldo : 0, nullptr,
+                          1.0f, ACT_NONE, out_f32, 0, stream);
   int bn = pick_bn(M, N);
   if (bn < 64) bn = 64;  // MN-major tiles are fetched in 64-element boxes
   if (k_splits > 1 && ws != nullptr) {
@@ -1591,7 +1596,8 @@ extern "C" int b200_gemm_bf16_ex(const void* A, const void* B, void* out, int M,
   const bool ok_a = a_mn ? make_map(&ma.m[0], A, K, M, lda, 64, 64) : make_map(&ma.m[0], A, M, K, lda, BM);
   const bool ok_b = b_mn ? make_map(&mb, B, K, N, ldb, 64, 64) : make_map(&mb, B, N, K, ldb, bn);
   if (!ok_a || !ok_b) return -1;
-  StoreEpilogue se{out, nullptr, nullptr, nullptr, ldo, 0, 1.0f, ACT_NONE, out_f32};
+  StoreEpilogue se{out, nullptr, accumulate ? (const __nv_bfloat16*)out : nullptr, nullptr, ldo, accumulate ? ldo : 0, 1.0f,
+                   ACT_NONE, out_f32};
   CUtensorMap mo{};
   LMHeadEpilogue le{};
   ReduceScatterEpilogue re{};
@@ -1620,7 +1626,7 @@ extern "C" int b200_gemm_bf16_ex(const void* A, const void* B, void* out, int M,
     if (e == cudaSuccess && !out_f32) {
       long long blocks = ((long long)M * N + 255) / 256;
       if (blocks > num_sms() * 8) blocks = num_sms() * 8;
-      splitk_finalize_kernel<<<(int)blocks, 256, 0, stream>>>(ws, (__nv_bfloat16*)out, M, N, ldo);
+      splitk_finalize_kernel<<<(int)blocks, 256, 0, stream>>>(ws, (__nv_bfloat16*)out, M, N, ldo, accumulate);
       e = cudaGetLastError();
     }
   } else {

@@ -111,6 +111,38 @@ def layer_norm(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], eps:
     return _Norm.apply(x, w, b, float(eps), bool(rms))
 
 
+_WGRAD_ACCUM = os.environ.get("TRLX_B200_WGRAD_ACCUM", "1") == "1"
+
+
+def _wgrad_sink(w: torch.Tensor, g2: torch.Tensor, x2: torch.Tensor):
+    """The optimizer's gradient-ready callback when ``dW`` may be accumulated in place into ``w.grad`` (a view of the fused
+    optimizer's flat bf16 buffer), else ``None``.  Parameters that several modules share (tied embeddings) keep the autograd
+    path: their hook must fire once per backward, after every contribution."""
+    if not (_WGRAD_ACCUM and _OWN_BACKWARD) or not getattr(w, "_b200_inplace_ok", False):
+        return None
+    sink = getattr(w, "_b200_grad_sink", None)
+    g = w.grad
+    if (sink is None or g is None or g.dtype != torch.bfloat16 or g.dim() != 2 or g.stride(-1) != 1 or g.stride(0) % 8
+            or g.data_ptr() % 16 or not (_ex_ok(g2) and _ex_ok(x2)) or torch.is_grad_enabled()):
+        return None
+    return sink
+
+
+def mark_inplace_wgrad(model: torch.nn.Module) -> int:
+    """Flag the ``nn.Linear`` weights whose gradient may be accumulated in place by the wgrad GEMM: 2-D, trainable, owned by
+    exactly one module (a tied LM head / embedding also receives gradient through other autograd paths and keeps the
+    autograd accumulation).  Called by the trainers once the fused optimizer owns the gradients."""
+    uses: Dict[int, int] = {}
+    for _, p in model.named_parameters(remove_duplicate=False):
+        uses[id(p)] = uses.get(id(p), 0) + 1
+    n = 0
+    for m in model.modules():
+        if type(m) is torch.nn.Linear and m.weight.requires_grad and uses.get(id(m.weight), 0) == 1:
+            m.weight._b200_inplace_ok = True
+            n += 1
+    return n
+
+
 class _Linear(torch.autograd.Function):
     """y = x @ w.T + b (+ residual) — forward and both backward GEMMs on the tcgen05 kernel."""
 
@@ -120,6 +152,8 @@ class _Linear(torch.autograd.Function):
         x2 = _as_2d(x)
         r2 = None if residual is None else _as_2d(residual)
         y = C.gemm(x2, w, b, r2, "none")
+        if getattr(w, "_b200_inplace_ok", False):  # uses of this weight recorded for the coming backward (see backward)
+            w._b200_uses = getattr(w, "_b200_uses", 0) + 1
         ctx.save_for_backward(x2, w)
         ctx.has_bias = b is not None
         ctx.has_res = residual is not None
@@ -134,7 +168,16 @@ class _Linear(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             gx = grad_input(g2, w).view(ctx.x_shape)
         if ctx.needs_input_grad[1]:
-            gw = grad_weight(g2, x2)
+            sink = _wgrad_sink(w, g2, x2)
+            if sink is not None:
+                # dW is added into the parameter's slice of the flat gradient buffer by the GEMM epilogue itself: no dW tensor,
+                # no separate accumulate kernel; the optimizer's "gradient ready" callback replaces the autograd hook
+                _ops().C.gemm_ex(g2, x2, True, True, False, -1, w.grad, True)
+                w._b200_uses = getattr(w, "_b200_uses", 1) - 1
+                if w._b200_uses <= 0:  # every recorded use of the weight has contributed: the gradient is final
+                    sink()
+            else:
+                gw = grad_weight(g2, x2)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = col_sum(g2)
         if ctx.has_res and ctx.needs_input_grad[3]:

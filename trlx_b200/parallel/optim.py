@@ -246,6 +246,17 @@ class FusedAdamW(Optimizer):
                     self._hooks.append(p.register_post_accumulate_grad_hook(
                         lambda _p, gi=gi, pi=pi: self._on_grad(gi, pi)))
 
+        # weight-gradient GEMMs may add straight into the flat gradient buffer (ops/functional.py: _Linear.backward) instead of
+        # returning a tensor for autograd to add (Apex `gradient_accumulation_fusion`, megatron_20b.yaml:72): the parameter
+        # carries the callback that stands in for its post-accumulate hook
+        if not self.local_only:
+            for gi, fg in enumerate(self._flat):
+                if fg is None:
+                    continue
+                for pi, p in enumerate(fg.params):
+                    if p.dim() == 2:
+                        p._b200_grad_sink = (lambda gi=gi, pi=pi: self._on_grad(gi, pi))
+
     def prepare(self):
         """Flatten storage now (call once after the model is on its device, before the first backward)."""
         self._lazy_init()
@@ -314,6 +325,9 @@ class FusedAdamW(Optimizer):
             if fg is not None:
                 fg.flat_grad.zero_()
                 fg.rebind_grads()
+                for p in fg.params:  # in-place wgrad bookkeeping: forwards that were never backpropagated must not linger
+                    if getattr(p, "_b200_uses", 0):
+                        p._b200_uses = 0
 
     @torch.no_grad()
     def step(self, closure=None, graph=None):

@@ -234,6 +234,10 @@ class AccelerateRLTrainer(BaseRLTrainer):
         opt = optimizer_class(self._optimizer_param_groups(params, optimizer_class), **kwargs)
         if hasattr(opt, "prepare"):
             opt.prepare()
+        if issubclass(optimizer_class, FusedAdamW) and self.zero3 is None:
+            from trlx_b200.ops.functional import mark_inplace_wgrad
+
+            mark_inplace_wgrad(self.model)
         if "8bit" in optimizer_class.__name__:
             for module in self.model.modules():  # keep embedding state in 32 bits (reference: :183-191)
                 if isinstance(module, torch.nn.Embedding):
