@@ -782,6 +782,12 @@ class RolloutEngine:
         logprobs = torch.cat([lp_p, st["lp_out"][:, :r_max]], 1)
         values = torch.cat([val_p, st["val_out"][:, :r_max]], 1)
         all_tokens = torch.cat([prompt, sample_outputs], 1)
+        # the sampled tokens start their trip to (pinned) host memory now, ahead of the scoring kernels queued below: the
+        # trainer detokenises and calls the reward function while the GPU is still scoring the rollout
+        host_tokens = torch.empty(all_tokens.shape, dtype=all_tokens.dtype, pin_memory=True)
+        host_tokens.copy_(all_tokens, non_blocking=True)
+        host_ready = torch.cuda.Event()
+        host_ready.record()
         full_mask = all_tokens.not_equal(self.pad).long()
         trunk = None
         if self.keep_trunk:
@@ -805,4 +811,5 @@ class RolloutEngine:
         else:
             ref_logprobs = torch.cat([ref_lp_p, st["ref_lp_out"][:, :r_max]], 1)
         return dict(samples=all_tokens, prompt_tensors=prompt, sample_outputs=sample_outputs, logprobs=logprobs,
-                    ref_logprobs=ref_logprobs, values=values, mask=full_mask, start=Q - 1, trunk=trunk)
+                    ref_logprobs=ref_logprobs, values=values, mask=full_mask, start=Q - 1, trunk=trunk,
+                    samples_host=(host_tokens, host_ready))

@@ -487,6 +487,13 @@ class AcceleratePPOTrainer(AccelerateRLTrainer):
                 with rt.nvtx("rollout/reward_fn"):
                     scores = self._score_with_reward_fn(*ro["strings"], metadata, device)
                 stats["time/rollout_score"] = time() - t0
+            elif "samples_host" in ro and not (self.rank0_reward and rt.distributed):
+                # the engine already sent the tokens to pinned host memory, ahead of its scoring kernels: wait for that copy
+                # only, then detokenise + score on the CPU while the GPU finishes the reference / value passes
+                host_tokens, host_ready = ro["samples_host"]
+                host_ready.synchronize()
+                with rt.nvtx("rollout/reward_fn"):
+                    scores = self._collect_scores(host_tokens[:, :prompt_tensors.shape[1]], host_tokens, metadata, device, stats)
             else:
                 with rt.nvtx("rollout/reward_fn"):
                     scores = self._collect_scores(prompt_tensors, ro["samples"], metadata, device, stats)
