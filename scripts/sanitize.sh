@@ -16,7 +16,7 @@ export PYTORCH_NO_CUDA_MEMORY_CACHING=1   # every tensor gets its own cudaMalloc
 GEMM_SMALL='test_gemm_matches_fp32 and (32-768-64 or 100-776-3072) or test_gemm_mn_major_operands and 300-200-136 or test_gemm_split_k and 3 or test_gemm_with_folded_norm or test_gemm_cta_pair and 512-512-256 or test_gemm_fp8 and 300- or test_gemm_epilogue or test_gemm_strided_input or test_lmhead_logprob and 77-1000-256 or test_lmhead_greedy'
 PLAIN='test_norm or test_embed_rowdot or test_decode_attention or test_logprob_from_logits or test_gae_whiten or test_ppo_loss_and_grads or test_rollout_rewards or test_adamw_flat'
 # round-2 kernels: radix-select samplers, ILQL sampler, 8-bit Adam, row-parallel column sums, in-place wgrad accumulation
-NEW='test_sample_filtered or test_ilql_sample or test_adam8bit or test_wgrad_accumulates or colsum'
+NEW='test_sample_filtered or test_ilql_sample or test_adam8bit or test_wgrad_accumulates or test_bias_gradient_column_sum'
 
 run() {  # name, tool, selection, seconds
   local name=$1 tool=$2 sel=$3 secs=$4
