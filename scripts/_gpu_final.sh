@@ -1,5 +1,5 @@
 # final single-GPU pass: the driver's tiers (pytest -m gpu, smoke, bench + reference arm), then the sanitizer passes for the new kernels
-echo "=== pytest -m gpu"; timeout 900 python -m pytest tests/ -x -q -m gpu -p no:cacheprovider 2>&1 | tail -6
+echo "=== pytest -m gpu"; timeout 900 python -m pytest tests/ -q -m gpu -p no:cacheprovider 2>&1 | tail -6
 echo "=== smoke"; timeout 200 python __graft_entry__.py --smoke 2>&1 | tail -2
 echo "=== bench"; BENCH_BREAKDOWN=1 timeout 300 python bench.py 2>&1 | tail -2 | cut -c1-1800
 echo "=== bench reference arm"; timeout 600 python bench.py --impl reference 2>&1 | tail -1 | cut -c1-1800

@@ -655,6 +655,42 @@ def test_wgrad_accumulates_in_place_into_flat_grad_buffer():
     assert (lin.weight.grad.float() - expect).abs().max() <= 2e-2 * expect.abs().max() + 1e-2
 
 
+def test_lora_update_as_gemm_epilogue(monkeypatch):
+    """LoRA on the CUDA path: frozen projection on the tcgen05 GEMM, all adapters of the projection as one skinny GEMM + one GEMM
+    whose residual operand is the frozen output (K = R = 8 or 16).  Outputs and gradients against fp32 maths."""
+    from trlx_b200.models.peft import LoRALinear
+
+    torch.manual_seed(7)
+    base = torch.nn.Linear(256, 768).cuda().to(torch.bfloat16)
+    lin = LoRALinear(base, r=8, alpha=32.0, dropout=0.0)
+    lin.add_adapter("q", (0, 256), "q_proj")
+    lin.add_adapter("v", (512, 768), "v_proj")
+    for k in lin.lora_B:
+        torch.nn.init.normal_(lin.lora_B[k], std=0.05)
+    x = (torch.randn(4, 96, 256, device="cuda") * 0.5).to(torch.bfloat16).requires_grad_(True)
+    params = [x, lin.lora_A["q"], lin.lora_B["q"], lin.lora_A["v"], lin.lora_B["v"]]
+    from trlx_b200 import ops as _ops
+
+    before = _ops.launch_count()
+    y = lin(x)
+    assert _ops.launch_count() - before >= 3  # base GEMM, skinny GEMM, epilogue GEMM
+    g = torch.autograd.grad(y.float().pow(2).mean(), params)
+    # fp32 oracle
+    xf = x.detach().float().requires_grad_(True)
+    pf = [p.detach().float().requires_grad_(True) for p in params[1:]]
+    yf = xf @ base.weight.float().t() + base.bias.float()
+    upd_q = (xf @ pf[0].t()) @ pf[1].t() * lin.scaling
+    upd_v = (xf @ pf[2].t()) @ pf[3].t() * lin.scaling
+    yf = torch.cat([yf[..., :256] + upd_q, yf[..., 256:512], yf[..., 512:] + upd_v], -1)
+    gf = torch.autograd.grad(yf.pow(2).mean(), [xf] + pf)
+    assert (y.float() - yf).abs().max() < 3e-2 * yf.abs().max()
+    for a, b in zip(g, gf):
+        assert (a.float() - b).abs().max() <= 4e-2 * b.abs().max() + 1e-6, (a.shape, (a.float() - b).abs().max(), b.abs().max())
+    monkeypatch.setenv("TRLX_B200_LORA_FUSED", "0")
+    y0 = lin(x)
+    assert (y0.float() - y.float()).abs().max() < 3e-2 * yf.abs().max()
+
+
 def test_fused_logprob_autograd():
     torch.manual_seed(14)
     from trlx_b200 import ops

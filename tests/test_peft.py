@@ -126,6 +126,32 @@ def test_lora_on_fused_projections(cfg, targets, key):
         assert sd[key].shape == (cfg["hidden_size"] // cfg["num_attention_heads"] * cfg["num_key_value_heads"], 4)
 
 
+def test_stacked_low_rank_epilogue_form_equals_per_adapter_updates(monkeypatch):
+    """The CUDA path writes every adapter of a projection as ONE pair of GEMMs (stacked A, block-structured B with the
+    scaling folded in, frozen output as the residual operand).  Same maths on the CPU through the reference ops."""
+    from trlx_b200.models.peft import LoRALinear
+
+    torch.manual_seed(0)
+    base = torch.nn.Linear(24, 40)
+    lin = LoRALinear(base, r=4, alpha=12.0, dropout=0.0)
+    lin.add_adapter("q", (0, 16), "q_proj")
+    lin.add_adapter("v", (24, 40), "v_proj")
+    for k in lin.lora_B:
+        torch.nn.init.normal_(lin.lora_B[k], std=0.3)
+    x = torch.randn(3, 5, 24, requires_grad=True)
+    plain = base(x) + lin.delta(x)
+    g_plain = torch.autograd.grad(plain.pow(2).sum(), [x, lin.lora_A["q"], lin.lora_B["v"]])
+    monkeypatch.setattr(LoRALinear, "_fused_ok", lambda self, x: True)
+    fused = lin(x)
+    g_fused = torch.autograd.grad(fused.pow(2).sum(), [x, lin.lora_A["q"], lin.lora_B["v"]])
+    torch.testing.assert_close(fused, plain, atol=1e-5, rtol=1e-5)
+    for a, b in zip(g_fused, g_plain):
+        torch.testing.assert_close(a, b, atol=1e-4, rtol=1e-4)
+    both, ref = lin.forward_both(x)
+    torch.testing.assert_close(both, plain, atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(ref, base(x))
+
+
 def test_unknown_target_module_and_bad_config():
     with pytest.raises(ValueError):
         AutoModelForCausalLMWithHydraValueHead.from_config(GPT2, peft_config=dict(peft_type="LORA", target_modules=["nope"]))

@@ -184,16 +184,49 @@ class LoRALinear(nn.Module):
                 full = torch.cat([full[..., :lo], full[..., lo:hi] + upd, full[..., hi:]], dim=-1)
         return full
 
+    def _fused_ok(self, x: torch.Tensor) -> bool:
+        if not (x.is_cuda and x.dtype == torch.bfloat16 and os.environ.get("TRLX_B200_LORA_FUSED", "1") == "1"):
+            return False
+        if self.training and isinstance(self.dropout, nn.Dropout) and self.dropout.p > 0:
+            return False  # dropout decouples the adapter input from the base input
+        from trlx_b200 import ops
+
+        return ops.available() and (self.r * len(self.lora_A)) % 8 == 0 and self.base.out_features % 8 == 0
+
+    def add_delta(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        """``y + Δ(x)``.  On the CUDA path the update is the epilogue of one GEMM: all adapters of this projection
+        are stacked into one down-projection ``A`` ``[R, in]`` and one block-structured up-projection ``B`` ``[out, R]`` (zero
+        outside each adapter's row slice, scaling folded in), so ``y_pol = (x Aᵀ) Bᵀ + y_ref`` is a skinny GEMM followed by a GEMM
+        whose residual operand is the frozen projection's output — no separate multiply / add / concatenate kernels."""
+        if not self._fused_ok(x):
+            return y + self.delta(x)
+        from trlx_b200 import ops
+
+        keys = list(self.lora_A)
+        R, out = self.r * len(keys), self.base.out_features
+        A = self.lora_A[keys[0]] if len(keys) == 1 else torch.cat([self.lora_A[k] for k in keys], 0)
+        Bf = None
+        for i, k in enumerate(keys):
+            lo, hi = self.slices[k]
+            blk = F.pad(self.lora_B[k] * self.scaling, (i * self.r, R - (i + 1) * self.r, lo, out - hi))
+            Bf = blk if Bf is None else Bf + blk
+        t = ops.linear(x, A)
+        return ops.linear(t, Bf, None, "none", y)
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        y = self.base(x)
+        from trlx_b200.nn.transformer import project
+
+        y = project(self.base, x)  # the frozen projection runs on the tcgen05 GEMM like an unadapted one
         if self.enabled and len(self.lora_A):
-            y = y + self.delta(x)
+            y = self.add_delta(x, y)
         return y
 
     def forward_both(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         """``(adapted, frozen)`` outputs from a single base GEMM."""
-        y_ref = self.base(x)
-        return (y_ref + self.delta(x)) if len(self.lora_A) else y_ref, y_ref
+        from trlx_b200.nn.transformer import project
+
+        y_ref = project(self.base, x)
+        return self.add_delta(x, y_ref) if len(self.lora_A) else y_ref, y_ref
 
     def merged_weight(self) -> torch.Tensor:
         w = self.base.weight.detach().clone()

@@ -367,8 +367,8 @@ def _install_sequence_parallel(lm, tp: TPContext) -> None:
     trunk = lm.transformer
     orig_embed = trunk.embed
 
-    def embed(input_ids, position_ids):
-        x = orig_embed(input_ids, position_ids)
+    def embed(input_ids, position_ids, inputs_embeds=None):
+        x = orig_embed(input_ids, position_ids, inputs_embeds)
         if not tp.sp:
             return x
         return _SplitSeqReplicated.apply(x, tp.group, tp.rank) if x.requires_grad else split_sequence(x, tp.rank, tp.size)
