@@ -44,4 +44,17 @@ if which in ("all", "lmhead"):
     lab = torch.randint(0, 50257, (1280,), device=dev)
     for _ in range(3):
         C.lmhead(h, w, None, lab)
+if which in ("all", "optim"):
+    # HBM-bound optimizer kernels: flat AdamW (bf16 param + fp32 master / moments) and the 8-bit-state variant, 32 M parameters
+    n = 32 * 1024 * 1024
+    master = torch.randn(n, device=dev)
+    param, grad = master.to(torch.bfloat16), (torch.randn(n, device=dev) * 0.01).to(torch.bfloat16)
+    m, v = torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    hyper = torch.tensor([1e-3, 0.1, 0.05, 1.0], device=dev)
+    for _ in range(2):
+        C.adamw_flat(param, master, grad, m, v, 0.9, 0.95, 1e-8, 0.01, True, hyper)
+    mq, vq = torch.zeros(n, dtype=torch.int8, device=dev), torch.zeros(n, dtype=torch.uint8, device=dev)
+    ms, vs = torch.full((n // 256,), 1e-12, device=dev), torch.full((n // 256,), 1e-12, device=dev)
+    for step in (1, 2):
+        C.adam8bit(param, grad, mq, ms, vq, vs, 1e-3, 0.9, 0.95, 1e-8, 0.01, True, step)
 torch.cuda.synchronize()

@@ -115,15 +115,18 @@ def test_ppo_trainer_runs_on_engine(tmp_path):
     assert trainer.iter_count == 4
 
 
-def test_fp8_rollout_stays_close_to_bf16(monkeypatch):
+@pytest.mark.parametrize("all_four", [False, True])
+def test_fp8_rollout_stays_close_to_bf16(monkeypatch, all_four):
     """rollout_dtype = fp8: teacher-forced log-probs of the fp8 engine's own samples, re-scored by the bf16 torch model, stay
-    within quantisation noise of what the engine reported."""
+    within quantisation noise of what the engine reported — with the two norm → GEMM pairs in e4m3, and with all four GEMMs of
+    a block in e4m3 (``TRLX_B200_FP8_ALL=1``; automatic from hidden size 2048)."""
     from trlx_b200.engine.rollout import RolloutEngine
 
+    monkeypatch.setenv("TRLX_B200_FP8_ALL", "1" if all_four else "0")
     m = _model("gpt2")
     gen = dict(max_new_tokens=8, do_sample=False, eos_token_id=999, pad_token_id=999, top_k=0, top_p=1.0, _rollout_dtype="fp8")
     eng = RolloutEngine(m, 999, 999, gen, seed=0)
-    assert eng.fp8
+    assert eng.fp8 and eng.fp8_all == all_four
     torch.manual_seed(1)
     prompts = torch.randint(0, 990, (16, 7), device="cuda")
     ro = eng.rollout(prompts, torch.ones_like(prompts))
@@ -135,7 +138,8 @@ def test_fp8_rollout_stays_close_to_bf16(monkeypatch):
     start = ro["start"]
     valid = mask[:, start + 1:].bool()
     diff = (lp[:, start:] - ro["logprobs"][:, start:])[valid].abs()
-    assert diff.mean().item() < 0.15 and torch.isfinite(ro["values"]).all()
+    assert diff.mean().item() < (0.2 if all_four else 0.15) and torch.isfinite(ro["values"]).all()
+    assert (eng.fp8_w[0].out_w is not None) == all_four
 
 
 def _mid_model(L=3, H=256, nh=4, F=1024):

@@ -559,13 +559,15 @@ def test_adamw_flat(C):
     torch.testing.assert_close(param.float(), rw, atol=2e-2, rtol=1e-2)
 
 
+@pytest.mark.parametrize("warp", [False, True])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("decoupled", [True, False])
-def test_adam8bit_kernel_matches_block_quantised_reference(C, dtype, decoupled):
+def test_adam8bit_kernel_matches_block_quantised_reference(C, dtype, decoupled, warp, monkeypatch):
     """One launch per tensor (decode, update, block maxima, re-encode) against the PyTorch implementation of the same
     code book, which itself tracks fp32 AdamW (tests/test_utils.py)."""
     from trlx_b200.parallel import optim as O
 
+    monkeypatch.setenv("TRLX_B200_ADAM8BIT_WARP", "1" if warp else "0")  # warp-per-block variant (8 elements per lane)
     torch.manual_seed(3)
     n = 70001  # not a multiple of the 256-element block
     w0 = torch.randn(n, device="cuda")
@@ -653,6 +655,20 @@ def test_wgrad_accumulates_in_place_into_flat_grad_buffer():
     assert len(fired) == 1
     expect = torch.ones(4 * 96, 384, device="cuda").t() @ (3 * xs[0].float().reshape(-1, 256))
     assert (lin.weight.grad.float() - expect).abs().max() <= 2e-2 * expect.abs().max() + 1e-2
+
+
+def test_quant_rows_fp8(C):
+    torch.manual_seed(2)
+    x = (torch.randn(37, 3072, device="cuda") * torch.rand(37, 1, device="cuda") * 4).to(torch.bfloat16)
+    x[5] = 0
+    q, s = C.quant_rows(x)
+    assert q.dtype == torch.uint8 and q.shape == x.shape and s.shape == (37,)
+    amax = x.float().abs().amax(1)
+    torch.testing.assert_close(s, amax.clamp_min(1e-12) / 448.0, rtol=1e-6, atol=0)
+    back = q.view(torch.float8_e4m3fn).float() * s[:, None]
+    err = (back - x.float()).abs()
+    assert (err <= 0.0625 * x.float().abs() + s[:, None] * 2 ** -9 + 1e-9).all()  # e4m3: 3 mantissa bits
+    assert back[5].abs().max() == 0
 
 
 def test_lora_update_as_gemm_epilogue(monkeypatch):

@@ -39,6 +39,7 @@ int b200_paged_kv_write(const void*, const void*, void*, void*, const int*, cons
 int b200_logprob_from_logits(const void*, const long long*, float*, float*, long long, int, long long, int, cudaStream_t);
 int b200_gemm_fp8(const void*, const void*, void*, int, int, int, long long, long long, long long, const float*, const float*,
                   const void*, const void*, long long, int, cudaStream_t);
+int b200_quant_rows_fp8(const void*, void*, float*, int, int, long long, long long, cudaStream_t);
 int b200_norm_quant_fp8(const void*, const void*, const void*, void*, float*, int, int, long long, long long, float, int,
                         cudaStream_t);
 int b200_gemm_bf16_ln(const void*, const void*, void*, int, int, int, long long, long long, long long, const void*, const void*,
@@ -227,6 +228,21 @@ std::vector<Tensor> norm_quant(const Tensor& x, const Tensor& w, const OptTensor
   check(b200_norm_quant_fp8(x.data_ptr(), w.data_ptr(), optptr(b), y8.data_ptr(), scale.data_ptr<float>(), (int)rows, (int)H,
                             x.stride(0), y8.stride(0), (float)eps, rms ? 1 : 0, stream()),
         "norm_quant");
+  return {y8, scale};
+}
+
+// (y8 [rows, H] e4m3 bytes, scale [rows]) = per-row quantisation of a bf16 matrix
+std::vector<Tensor> quant_rows(const Tensor& x) {
+  CHECK_BF16(x);
+  TORCH_CHECK(x.dim() == 2 && x.stride(1) == 1 && x.size(1) % 16 == 0 && x.stride(0) % 8 == 0 &&
+              reinterpret_cast<uintptr_t>(x.data_ptr()) % 16 == 0, "quant_rows: [rows, H] bf16 with H % 16 == 0");
+  c10::cuda::CUDAGuard guard(x.device());
+  const int64_t rows = x.size(0), H = x.size(1);
+  Tensor y8 = torch::empty({rows, H}, x.options().dtype(at::kByte));
+  Tensor scale = torch::empty({rows}, x.options().dtype(at::kFloat));
+  check(b200_quant_rows_fp8(x.data_ptr(), y8.data_ptr(), scale.data_ptr<float>(), (int)rows, (int)H, x.stride(0), y8.stride(0),
+                            stream()),
+        "quant_rows");
   return {y8, scale};
 }
 
@@ -1077,6 +1093,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("ln_rms") = false, py::arg("stats_out") = py::none());
   m.def("gemm_fp8", &gemm_fp8, py::arg("a8"), py::arg("b8"), py::arg("row_scale"), py::arg("col_scale"), py::arg("bias") = py::none(),
         py::arg("residual") = py::none(), py::arg("act") = "none");
+  m.def("quant_rows", &quant_rows);
   m.def("norm_quant", &norm_quant, py::arg("x"), py::arg("w"), py::arg("b") = py::none(), py::arg("eps") = 1e-5,
         py::arg("rms") = false);
   m.def("gemm_flagged", &gemm_flagged, py::arg("a"), py::arg("w"), py::arg("bias"), py::arg("act"), py::arg("flags"),

@@ -432,6 +432,50 @@ extern "C" int b200_norm_bf16(const void* x, const void* w, const void* b, void*
                             (const __nv_bfloat16*)w, (const __nv_bfloat16*)b, (__nv_bfloat16*)y, H, ldx, ldy, eps);
 }
 
+// Per-row e4m3 quantisation without a norm (fp8 rollouts: the attention output feeding the out-projection and the MLP activation
+// feeding the down-projection): y8[row, :] = e4m3(x / scale[row]), scale[row] = max|x| / 448.  One CTA per row, two passes (the row
+// stays in L1 between them).
+__global__ void __launch_bounds__(128) quant_rows_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ y8,
+                                                         float* __restrict__ scale_out, int H, long long ldx, long long ldy) {
+  griddep_wait();
+  griddep_launch();
+  const int row = blockIdx.x;
+  const __nv_bfloat16* xr = x + (size_t)row * ldx;
+  uint8_t* yr = y8 + (size_t)row * ldy;
+  __shared__ float red[4];
+  const int nvec = H >> 3;
+  float amax = 0.f;
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+    const uint4 v = *reinterpret_cast<const uint4*>(xr + i * 8);
+    const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) amax = fmaxf(amax, fabsf(__bfloat162float(h[j])));
+  }
+  amax = warp_max(amax);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = amax;
+  __syncthreads();
+  amax = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  const float scale = fmaxf(amax, 1e-12f) / 448.f, inv = 1.f / scale;
+  if (threadIdx.x == 0) scale_out[row] = scale;
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+    const uint4 v = *reinterpret_cast<const uint4*>(xr + i * 8);
+    const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&v);
+    uint2 q;
+    uint8_t* qb = reinterpret_cast<uint8_t*>(&q);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) qb[j] = (uint8_t)__nv_cvt_float_to_fp8(__bfloat162float(h[j]) * inv, __NV_SATFINITE, __NV_E4M3);
+    *reinterpret_cast<uint2*>(yr + i * 8) = q;
+  }
+}
+
+extern "C" int b200_quant_rows_fp8(const void* x, void* y8, float* scale, int rows, int H, long long ldx, long long ldy,
+                                   cudaStream_t stream) {
+  if (rows <= 0) return 0;
+  if (H % 16) return -2;
+  return (int)launch_kernel(quant_rows_kernel, dim3(rows), dim3(128), 0, stream, (const __nv_bfloat16*)x, (uint8_t*)y8, scale, H, ldx,
+                            ldy);
+}
+
 extern "C" int b200_norm_quant_fp8(const void* x, const void* w, const void* b, void* y8, float* scale, int rows, int H,
                                    long long ldx, long long ldy, float eps, int rms, cudaStream_t stream) {
   if (rows <= 0) return 0;

@@ -85,6 +85,12 @@ class _Fp8W:
     up_w: torch.Tensor
     up_s: torch.Tensor
     trainable: bool
+    # all four GEMMs of a block in e4m3 (``fp8_all``): out-projection and MLP-down copies; their activations (attention output,
+    # MLP activation) are quantised per row by ``quant_rows_kernel``
+    out_w: Optional[torch.Tensor] = None
+    out_s: Optional[torch.Tensor] = None
+    down_w: Optional[torch.Tensor] = None
+    down_s: Optional[torch.Tensor] = None
 
 
 def _quant_e4m3(w: torch.Tensor):
@@ -216,9 +222,15 @@ class RolloutEngine:
                                                                   for W in self.layers + self.ref_layers)
                            and folded_bytes <= int(os.environ.get("TRLX_B200_FOLD_BUDGET_MB", "4096")) << 20)
         # fp8 rollout (config.train.parallel.rollout_dtype == "fp8" or TRLX_B200_ROLLOUT_FP8=1): the norm → GEMM pairs of every
-        # block (QKV, MLP up) run e4m3 x e4m3 on the tensor cores with per-row / per-channel scales; half the weight bytes
+        # block (QKV, MLP up) — and with `fp8_all` the out- and down-projections too — run e4m3 x e4m3 on the tensor cores with
+        # per-row / per-channel scales; half the weight bytes
         self.fp8 = (str(gen_kwargs.get("_rollout_dtype", os.environ.get("TRLX_B200_ROLLOUT_FP8", ""))).lower() in ("fp8", "1", "true")
                     and spec.hidden_size % 16 == 0 and not self.fold_norms)
+        # all four GEMMs of a block in e4m3 (+ one row-quantisation kernel in front of the out- and down-projections): pays when the
+        # weights dominate a decode step (hidden >= 2048); small models are launch-latency bound and keep those two in bf16.
+        # TRLX_B200_FP8_ALL=1 / 0 forces it.
+        mode = os.environ.get("TRLX_B200_FP8_ALL", "auto")
+        self.fp8_all = self.fp8 and spec.ffn_size % 16 == 0 and (mode == "1" or (mode == "auto" and spec.hidden_size >= 2048))
         self.fp8_w: List[_Fp8W] = []
         self.ref_fp8_w: List[_Fp8W] = []
         self.folded: List[_FoldW] = []
@@ -303,15 +315,18 @@ class RolloutEngine:
         first = not self.fp8_w
 
         def build(W: _LayerW, old: Optional[_Fp8W]) -> _Fp8W:
-            trainable = any(t.requires_grad for t in (W.qkv_w, W.up_w)) or self.lora  # merged LoRA copies change every step
+            trainable = any(t.requires_grad for t in (W.qkv_w, W.up_w, W.out_w, W.down_w)) or self.lora  # merged LoRA copies change every step
             if old is not None and not trainable:
                 return old
             q, qs = _quant_e4m3(W.qkv_w)
             u, us = _quant_e4m3(W.up_w)
+            extra = (*_quant_e4m3(W.out_w), *_quant_e4m3(W.down_w)) if self.fp8_all else (None,) * 4
             if old is None:
-                return _Fp8W(q, qs, u, us, trainable)
-            for dst, src in zip((old.qkv_w, old.qkv_s, old.up_w, old.up_s), (q, qs, u, us)):
-                dst.copy_(src)
+                return _Fp8W(q, qs, u, us, trainable, *extra)
+            for dst, src in zip((old.qkv_w, old.qkv_s, old.up_w, old.up_s, old.out_w, old.out_s, old.down_w, old.down_s),
+                                (q, qs, u, us, *extra)):
+                if dst is not None:
+                    dst.copy_(src)
             return old
 
         self.fp8_w = [build(W, None if first else self.fp8_w[i]) for i, W in enumerate(self.layers)]
@@ -404,13 +419,25 @@ class RolloutEngine:
                 return (F.silu(g) * u).contiguous() if spec.activation in ("silu", "swish") else (F.gelu(g, approximate="tanh") * u).contiguous()
             return C.gemm_fp8(h8_, Q.up_w, hs_, Q.up_s, W.up_b, None, spec.activation)
 
+        def out_proj(a_, res):
+            if Q.out_w is None:
+                return C.gemm(a_, W.out_w, W.out_b, res)
+            a8, a_s = C.quant_rows(a_)
+            return C.gemm_fp8(a8, Q.out_w, a_s, Q.out_s, W.out_b, res, "none")
+
+        def down_proj(mid, res):
+            if Q.down_w is None:
+                return C.gemm(mid, W.down_w, W.down_b, res)
+            m8, m_s = C.quant_rows(mid)
+            return C.gemm_fp8(m8, Q.down_w, m_s, Q.down_s, W.down_b, res, "none")
+
         if spec.parallel_residual:
             h2 = (h8, hs) if W.n2w is None else tuple(C.norm_quant(x, W.n2w, W.n2b, eps, rms))
-            t = C.gemm(a, W.out_w, W.out_b, x)
-            return C.gemm(mlp_mid(*h2), W.down_w, W.down_b, t)
-        x = C.gemm(a, W.out_w, W.out_b, x)
+            t = out_proj(a, x)
+            return down_proj(mlp_mid(*h2), t)
+        x = out_proj(a, x)
         h2 = C.norm_quant(x, W.n2w, W.n2b, eps, rms)
-        return C.gemm(mlp_mid(*h2), W.down_w, W.down_b, x)
+        return down_proj(mlp_mid(*h2), x)
 
     def _layer(self, x, W: _LayerW, kc, vc, st):
         C, spec = ops.C, self.spec
