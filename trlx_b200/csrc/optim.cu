@@ -122,6 +122,11 @@ __global__ void __launch_bounds__(256)
 adam8bit_warp_kernel(void* __restrict__ param, const void* __restrict__ grad, signed char* __restrict__ mq, float* __restrict__ mscale,
                      unsigned char* __restrict__ vq, float* __restrict__ vscale, long long n, AdamArgs a, float lr, float bc1,
                      float bc2) {
+  // decode tables (code -> magnitude relative to the block scale): 127 first-moment and 255 second-moment magnitudes
+  __shared__ float tab_m[128], tab_v[256];
+  tab_v[threadIdx.x] = threadIdx.x == 0 ? 0.f : exp2f(((float)threadIdx.x - 255.f) * 0.125f);
+  if (threadIdx.x < 128) tab_m[threadIdx.x] = threadIdx.x == 0 ? 0.f : exp2f(((float)threadIdx.x - 127.f) * 0.25f);
+  __syncthreads();
   const long long blk = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (blk >= (n + 255) / 256) return;  // whole warps leave together; nothing below synchronises across warps
   const int lane = threadIdx.x & 31;
@@ -162,18 +167,19 @@ adam8bit_warp_kernel(void* __restrict__ param, const void* __restrict__ grad, si
   const unsigned char* cv = reinterpret_cast<const unsigned char*>(&cvv);
   const float ms = mscale[blk], vs = vscale[blk];
   float amax = 0.f, vmax = 0.f;
+  const float step = lr / bc1, inv_bc2 = 1.f / bc2, decay = 1.f - lr * a.weight_decay;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = cm[j], d = cv[j];
-    m[j] = c == 0 ? 0.f : exp2f(((float)abs(c) - 127.f) * 0.25f) * (c < 0 ? -ms : ms);
-    v[j] = d == 0 ? 0.f : exp2f(((float)d - 255.f) * 0.125f) * vs;
+    m[j] = tab_m[abs(c)] * (c < 0 ? -ms : ms);
+    v[j] = tab_v[d] * vs;
     if (i0 + j < n) {
       float gj = g[j];
       if (!a.decoupled && a.weight_decay != 0.f) gj += a.weight_decay * w[j];
       m[j] = a.beta1 * m[j] + (1.f - a.beta1) * gj;
       v[j] = a.beta2 * v[j] + (1.f - a.beta2) * gj * gj;
-      if (a.decoupled && a.weight_decay != 0.f) w[j] *= 1.f - lr * a.weight_decay;
-      w[j] -= lr * (m[j] / bc1) / (sqrtf(v[j] / bc2) + a.eps);
+      if (a.decoupled && a.weight_decay != 0.f) w[j] *= decay;
+      w[j] -= __fdividef(step * m[j], sqrtf(v[j] * inv_bc2) + a.eps);
     } else {
       m[j] = 0.f; v[j] = 0.f;
     }
@@ -233,8 +239,8 @@ extern "C" int b200_adam8bit(void* param, const void* grad, int is_f32, void* mq
   if (n <= 0) return 0;
   AdamArgs a{beta1, beta2, eps, weight_decay, decoupled};
   const long long blocks = (n + 255) / 256;
-  const char* wv = getenv("TRLX_B200_ADAM8BIT_WARP");  // read per call: tests flip it
-  const bool warp_variant = wv != nullptr && wv[0] == '1';
+  const char* wv = getenv("TRLX_B200_ADAM8BIT_WARP");  // default on; "0" selects the one-element-per-thread kernel (read per call: tests flip it)
+  const bool warp_variant = wv == nullptr || wv[0] != '0';
   const bool aligned = ((uintptr_t)param % 16 == 0) && ((uintptr_t)grad % 16 == 0) && ((uintptr_t)mq % 8 == 0) && ((uintptr_t)vq % 8 == 0);
   if (warp_variant && aligned) {
     const unsigned ctas = (unsigned)((blocks + 7) / 8);
