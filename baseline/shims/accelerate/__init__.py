@@ -28,6 +28,19 @@ class _AutocastModule(torch.nn.Module):
             return getattr(self.module, name)
 
 
+class _EngineLikeDDP(torch.nn.parallel.DistributedDataParallel):
+    """DDP whose missing attributes resolve on the wrapped module.  The reference reads ``model.peft_type`` / ``model.frozen_head``
+    and calls ``model.generate`` / ``model.forward_hydra`` on whatever ``accelerator.prepare`` returned
+    (``trlx/trainer/accelerate_ppo_trainer.py:70-80``); its multi-GPU default is DeepSpeed (``configs/accelerate/zero2-bf16.yaml``),
+    whose engine forwards attribute access exactly like this — plain ``torch`` DDP does not, and the trainer would not construct."""
+
+    def __getattr__(self, name):
+        try:
+            return super().__getattr__(name)
+        except AttributeError:
+            return getattr(super().__getattr__("module"), name)
+
+
 class Accelerator:
     def __init__(self, log_with=None, project_dir=None, **kw):
         self.rank = int(os.environ.get("RANK", 0))
@@ -55,7 +68,7 @@ class Accelerator:
             if isinstance(o, torch.nn.Module):
                 o = o.to(self.device)
                 if self.num_processes > 1 and any(p.requires_grad for p in o.parameters()):
-                    o = torch.nn.parallel.DistributedDataParallel(
+                    o = _EngineLikeDDP(
                         o, device_ids=[self.local_rank] if self.device.type == "cuda" else None, find_unused_parameters=True)
                 if self.mixed_precision == "bf16" and self.device.type == "cuda":
                     inner = o
@@ -115,8 +128,17 @@ class Accelerator:
             dist.barrier()
 
     def gather(self, t):
+        """All-gather along dim 0; lists / tuples / dicts of tensors are gathered leaf by leaf (Accelerate's behaviour)."""
         if self.num_processes == 1:
             return t
+        if isinstance(t, (list, tuple)):
+            return type(t)(self.gather(x) for x in t)
+        if isinstance(t, dict):
+            return {k: self.gather(v) for k, v in t.items()}
+        if not isinstance(t, torch.Tensor):
+            return t
+        if t.dim() == 0:
+            t = t[None]
         out = [torch.empty_like(t) for _ in range(self.num_processes)]
         dist.all_gather(out, t.contiguous())
         return torch.cat(out, 0)
