@@ -201,17 +201,22 @@ def _optimizer_note(trainer) -> str:
 def ppo_iteration(trainer):
     """Exactly the per-epoch body of ``AccelerateRLTrainer.learn`` for PPO (without eval / checkpoint IO)."""
     from trlx_b200.pipeline import MiniBatchIterator
-    from trlx_b200.trainer.accelerate_base_trainer import _materialise
+    from trlx_b200.trainer.accelerate_base_trainer import PendingStats
 
     trainer.store.clear_history()
     trainer.make_experience(trainer.config.method.num_rollouts, trainer.iter_count)
-    last = None
+    last, pending = None, None
     for _ in range(trainer.n_inner_epochs):
         loader = trainer.create_train_dataloader()
         for minibatch in MiniBatchIterator(loader, trainer.mb_size, trainer.num_mb):
             stats = trainer.train_step(minibatch)
-            last = _materialise(stats)  # device→host read of the step's loss / statistics
+            handle = PendingStats(stats)  # device→host read of the step's loss / statistics, queued behind the step ...
+            if pending is not None:
+                last = pending.get()      # ... and consumed one step late, as in `learn()`
+            pending = handle
         trainer.post_backward_callback()
+    if pending is not None:
+        last = pending.get()              # every step's statistics reach the host inside the iteration
     return last
 
 

@@ -44,6 +44,25 @@ def test_ppo_end_to_end_checkpoints(tmp_path):
     assert all(not p.requires_grad for p in trainer.model.base_model.transformer.h[0].parameters())
 
 
+@pytest.mark.parametrize("lag", [True, False])
+def test_train_statistics_are_logged_once_per_step_in_order(tmp_path, lag):
+    """The loop reads a step's statistics after launching the next one (``PendingStats``); every optimizer step is still logged
+    exactly once, under its own index, in increasing order — checkpoints / evaluations happen on the same steps either way."""
+    import json
+
+    cfg = ppo_config(tmp_path / "ckpt", train=dict(total_steps=7, checkpoint_interval=3, eval_interval=5, tracker="jsonl",
+                                                     logging_dir=str(tmp_path / "logs"), trainer_kwargs=dict(lag_stats=lag)))
+    trainer = trlx.train(reward_fn=reward_fn, prompts=PROMPTS, eval_prompts=PROMPTS[:2], config=cfg)
+    assert trainer.iter_count == 7
+    logs = [json.loads(line) for f in os.listdir(tmp_path / "logs") for line in open(tmp_path / "logs" / f)]
+    train_steps = [int(r["step"]) for r in logs if "losses/total_loss" in r]
+    assert train_steps == list(range(1, 8)), train_steps
+    assert all(r["losses/total_loss"] == r["losses/total_loss"] for r in logs if "losses/total_loss" in r)  # finite numbers
+    assert {"checkpoint_3", "checkpoint_6", "checkpoint_7"} <= set(os.listdir(tmp_path / "ckpt"))
+    evals = [int(r["step"]) for r in logs if "reward/mean" in r and int(r["step"]) > 0]
+    assert evals == [5, 7], evals
+
+
 def test_ppo_stats_keys_and_rollout_arithmetic(tmp_path):
     cfg = ppo_config(tmp_path, train=dict(total_steps=2, checkpoint_interval=100, eval_interval=100))
     trainer = get_trainer(cfg.train.trainer)(config=cfg, reward_fn=reward_fn, metric_fn=None, stop_sequences=[])

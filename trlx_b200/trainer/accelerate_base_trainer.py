@@ -52,18 +52,43 @@ class EventTimer:
         return self.start.elapsed_time(self.end) / 1e3
 
 
+class PendingStats:
+    """Statistics of an optimizer step on their way to the host.  Construction enqueues ONE device→host transfer of all 0-dim
+    device tensors (packed, into pinned memory, followed by an event); :meth:`get` waits for that event only.  The training loop
+    reads the statistics of step ``i`` after it has launched step ``i + 1``, so the GPU never idles on the host's bookkeeping
+    (the values are copied in stream order, i.e. before a replayed CUDA graph overwrites its static output buffers)."""
+
+    def __init__(self, stats: Dict[str, Any]):
+        self.stats = dict(stats)
+        self.keys = [k for k, v in stats.items() if isinstance(v, torch.Tensor) and v.numel() == 1]
+        self.host, self.event, self.vals = None, None, None
+        if self.keys:
+            dev = [stats[k].detach().float().reshape(()) for k in self.keys]
+            if dev[0].is_cuda:
+                packed = torch.stack(dev)
+                self.host = torch.empty(packed.shape, dtype=packed.dtype, pin_memory=True)
+                self.host.copy_(packed, non_blocking=True)
+                self.event = torch.cuda.Event()
+                self.event.record()
+            else:
+                self.vals = [float(v) for v in dev]
+
+    def get(self) -> Dict[str, Any]:
+        if self.event is not None:
+            self.event.synchronize()
+            self.vals, self.event = self.host.tolist(), None
+        out = self.stats
+        if self.keys:
+            out.update(zip(self.keys, self.vals))
+        for k, v in list(out.items()):
+            if isinstance(v, EventTimer):
+                out[k] = float(v)
+        return out
+
+
 def _materialise(stats: Dict[str, Any]) -> Dict[str, Any]:
     """Turn 0-dim device tensors into python floats with a single device→host transfer."""
-    keys = [k for k, v in stats.items() if isinstance(v, torch.Tensor) and v.numel() == 1]
-    if keys:
-        dev = [stats[k].detach().float().reshape(()) for k in keys]
-        vals = torch.stack(dev).tolist() if dev[0].is_cuda else [float(v) for v in dev]
-        stats = dict(stats)
-        stats.update(zip(keys, vals))
-    for k, v in list(stats.items()):
-        if isinstance(v, EventTimer):
-            stats[k] = float(v)
-    return stats
+    return PendingStats(stats).get()
 
 
 def _parse_max_time(value) -> Optional[float]:
@@ -86,7 +111,7 @@ class AccelerateRLTrainer(BaseRLTrainer):
     #: ``train.trainer_kwargs`` keys that configure this framework's trainers (read from the config where they are used);
     #: everything else in ``trainer_kwargs`` is a constructor argument, exactly as in the reference (``trlx/trlx.py:92-98``)
     FRAMEWORK_KWARGS = ("prompt_bucket", "rank0_reward", "cache_trunk", "zero_stage", "max_time", "megatron_cfg",
-                        "pretrained_model", "offload_reference", "no_train_graph", "max_nonfinite_steps")
+                        "pretrained_model", "offload_reference", "no_train_graph", "max_nonfinite_steps", "lag_stats")
 
     def __init__(self, config: TRLConfig, **kwargs):
         for key in self.FRAMEWORK_KWARGS:
@@ -589,7 +614,7 @@ class AccelerateRLTrainer(BaseRLTrainer):
 
     _LOSS_KEYS = ("loss", "losses/loss", "losses/total_loss")
 
-    def _check_finite(self, stats: Dict[str, Any]) -> bool:
+    def _check_finite(self, stats: Dict[str, Any], step: Optional[int] = None) -> bool:
         """Divergence watchdog (the reference has none): a non-finite loss is logged, its step never overwrites a
         checkpoint, and after ``trainer_kwargs.max_nonfinite_steps`` (default 8) consecutive ones training stops with an error
         instead of burning the remaining budget on NaN weights.  Reads the already-materialised statistics: no extra sync."""
@@ -601,7 +626,8 @@ class AccelerateRLTrainer(BaseRLTrainer):
             return True
         self._nonfinite_streak = getattr(self, "_nonfinite_streak", 0) + 1
         limit = int((self.config.train.trainer_kwargs or {}).get("max_nonfinite_steps", 8))
-        logger.warning(f"step {self.iter_count}: non-finite {bad[0]} ({self._nonfinite_streak} in a row; abort at {limit})")
+        logger.warning(f"step {self.iter_count if step is None else step}: non-finite {bad[0]} "
+                       f"({self._nonfinite_streak} in a row; abort at {limit})")
         if self._nonfinite_streak >= limit:
             raise FloatingPointError(
                 f"training diverged: {bad[0]} has been non-finite for {self._nonfinite_streak} consecutive steps "
@@ -623,6 +649,20 @@ class AccelerateRLTrainer(BaseRLTrainer):
         best_reward = -float("inf")
         time_limit = _parse_max_time((self.config.train.trainer_kwargs or {}).get("max_time", getattr(self, "_max_time", None)))
         t_start = time()
+        # Statistics are read one optimizer step late (`PendingStats`): the transfer of step i is queued right behind it, the host
+        # blocks on it only after step i + 1 has been launched.  Steps on which something depends on the numbers right away
+        # (checkpoint, evaluation, last step, wall-clock budget) are read synchronously.  `trainer_kwargs.lag_stats=False` restores
+        # the strictly synchronous loop.
+        lag_ok = bool((self.config.train.trainer_kwargs or {}).get("lag_stats", True)) and time_limit is None
+        lagging: List[Any] = []  # at most one (PendingStats, step index)
+
+        def flush():
+            while lagging:
+                handle, step = lagging.pop(0)
+                st = handle.get()
+                self._check_finite(st, step)
+                self.runtime.log(st, step=step)
+
         for _ in range(self.config.train.epochs):
             for _ in range(self.n_inner_epochs):
                 train_dataloader = self.create_train_dataloader()
@@ -631,7 +671,15 @@ class AccelerateRLTrainer(BaseRLTrainer):
                         stats = self.train_step(minibatch)
                     for gi, lr in enumerate(self.scheduler.get_last_lr()):
                         stats[f"learning_rate_group_{gi}"] = lr
-                    stats = _materialise(stats)
+                    handle = PendingStats(stats)
+                    flush()  # the previous step's numbers: this step is already running on the device
+                    due = (self.iter_count % self.config.train.checkpoint_interval == 0 or self.iter_count >= self.total_steps
+                           or self.iter_count % self.config.train.eval_interval == 0)
+                    if lag_ok and not due:
+                        lagging.append((handle, self.iter_count))
+                        tbar.update()
+                        continue
+                    stats = handle.get()
                     healthy = self._check_finite(stats)
                     if healthy and (self.iter_count % self.config.train.checkpoint_interval == 0
                                     or self.iter_count >= self.total_steps):
@@ -668,7 +716,9 @@ class AccelerateRLTrainer(BaseRLTrainer):
                             tbar.close()
                             return results
                 self.post_backward_callback()
+            flush()  # before the next rollouts log under a later step index
             self.post_epoch_callback()
+        flush()
         tbar.close()
         return results
 
