@@ -459,7 +459,7 @@ def test_zero3_parameter_partitioning_matches_replicated_training(tmp_path):
 
 
 # ---- tensor x pipeline parallelism with sequence parallelism ---------------------------------------------------------------------
-def _tp_pp_sp_job(rank, world):
+def _tp_pp_sp_job(rank, world, virtual=1):
     """4 ranks = TP 2 x PP 2, sequence parallel on: stage boundaries carry each TP rank's sequence shard."""
     import copy
 
@@ -480,7 +480,7 @@ def _tp_pp_sp_job(rank, world):
     full = CausalLM(spec).float()
     staged = copy.deepcopy(full)
     tpc = apply_tensor_parallel(staged, tp_group, tp_rank, tp_size, sequence_parallel=True)
-    stage = pp.apply_pipeline_parallel(staged, pp_group, pp_rank, pp_size)
+    stage = pp.apply_pipeline_parallel(staged, pp_group, pp_rank, pp_size, virtual)
     g = torch.Generator().manual_seed(1)
     mbs = []
     for i in range(4):
@@ -511,8 +511,21 @@ def _tp_pp_sp_job(rank, world):
         out = staged(**mb)
         return out.loss, {"loss": out.loss.detach()}
 
-    stats = pp.run_1f1b(stage, mbs, loss_fn, torch.device("cpu"))
-    pp._exchange = orig_exchange
+    if virtual > 1:  # interleaved schedule: record the shapes of the buffers its grouped transfers receive into
+        orig_empty = torch.empty
+
+        def empty_spy(*a, **k):
+            if a and isinstance(a[0], tuple) and len(a[0]) == 3:
+                boundary_shapes.append(tuple(a[0]))
+            return orig_empty(*a, **k)
+
+        pp.torch.empty = empty_spy
+    try:
+        stats = pp.run_schedule(stage, mbs, loss_fn, torch.device("cpu"))
+    finally:
+        pp._exchange = orig_exchange
+        if virtual > 1:
+            pp.torch.empty = orig_empty
     allreduce_sequence_parallel_grads(staged, tp_group)
     shared = pp.broadcast_stats(stage, {"loss": sum(s["loss"] for s in stats) / len(mbs)} if stage.last else None, torch.device("cpu"))
     blk = staged.transformer.h[stage.lo]
@@ -523,8 +536,9 @@ def _tp_pp_sp_job(rank, world):
                 shapes=boundary_shapes, sp=tpc.sequence_parallel)
 
 
-def test_tensor_pipeline_sequence_parallel_matches_single_rank():
-    res = run_distributed(_tp_pp_sp_job, 4)
+@pytest.mark.parametrize("virtual", [1, 2])
+def test_tensor_pipeline_sequence_parallel_matches_single_rank(virtual):
+    res = run_distributed(_tp_pp_sp_job, 4, (virtual,))
     for r in res:
         assert r["sp"]
         torch.testing.assert_close(r["mean_loss"], r["ref_mean"], atol=1e-5, rtol=1e-5)
