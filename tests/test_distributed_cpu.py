@@ -246,6 +246,16 @@ def test_interleaved_schedule_plan():
                 for r in range(P):
                     mine = [a[r] for a in rounds if a[r] is not None]
                     assert len(mine) == len(set(mine)) == 2 * M * V
+    # activations in flight on a rank never exceed its warm-up depth + 1 (what bounds the memory of the schedule)
+    for P, V, M in ((4, 2, 8), (4, 1, 8), (2, 3, 6)):
+        rounds = interleaved_rounds(P, V, M)
+        for r in range(P):
+            live = peak = 0
+            for acts in rounds:
+                if acts[r] is not None:
+                    live += 1 if acts[r][0] == "F" else -1
+                    peak = max(peak, live)
+            assert live == 0 and peak <= min(2 * (P - r - 1) + (V - 1) * P, M * V) + 1, (P, V, M, r, peak)
     # the bubble shrinks with the number of chunks: P = 4, 16 micro-batches, measured in whole-stage units
     cost = {V: len(interleaved_rounds(4, V, 16)) / V for V in (1, 2, 4)}
     assert cost[4] < cost[2] < cost[1]

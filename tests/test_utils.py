@@ -243,3 +243,27 @@ def test_relative_outputs_never_land_in_the_source_checkout(tmp_path, monkeypatc
     assert U.resolve_output_dir("ckpts") == str(tmp_path / "o" / "ckpts")
     (tmp_path / "here").mkdir()
     assert U.resolve_output_dir("here", for_read=True) == "here"  # an existing cwd-relative checkpoint is read where it is
+
+
+def test_inplace_wgrad_marks_only_unshared_linear_weights():
+    """``gradient_accumulation_fusion`` eligibility: trainable ``nn.Linear`` weights owned by exactly one module; tied embeddings /
+    LM heads, frozen weights and non-Linear parameters keep the autograd accumulation.  Without the CUDA extension the sink is
+    never used (the wgrad GEMM path is CUDA-only)."""
+    from trlx_b200.models.modeling_ppo import AutoModelForCausalLMWithHydraValueHead
+    from trlx_b200.ops import functional as Fn
+
+    cfg = dict(model_type="gpt2", vocab_size=64, n_embd=32, n_layer=2, n_head=2, n_positions=32, tie_word_embeddings=True)
+    model = AutoModelForCausalLMWithHydraValueHead.from_config(cfg, num_layers_unfrozen=1)
+    lm = model.base_model
+    assert lm.lm_head.weight is lm.transformer.wte.weight
+    for p in lm.transformer.h[0].parameters():
+        p.requires_grad_(False)
+    n = Fn.mark_inplace_wgrad(model)
+    marked = {name for name, p in model.named_parameters() if getattr(p, "_b200_inplace_ok", False)}
+    assert n == len(marked) and n > 0
+    assert not any("wte" in k or "lm_head" in k or "wpe" in k or "norm" in k or k.endswith(".bias") for k in marked), marked
+    assert not any(k.startswith("base_model.transformer.h.0.") for k in marked)  # frozen block
+    assert any(k.startswith("base_model.transformer.h.1.") and k.endswith("weight") for k in marked)
+    w = lm.transformer.h[1].mlp.up.weight
+    x = torch.randn(4, 32)
+    assert Fn._wgrad_sink(w, x, x) is None  # no sink registered / CPU tensors: autograd path
