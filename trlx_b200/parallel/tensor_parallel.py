@@ -16,11 +16,13 @@ module                 kind                        local shape
 
 Communication per block (forward): without sequence parallelism one all-reduce after each row-parallel GEMM; with it
 the activations between blocks are sharded along the sequence, the column-parallel GEMM is preceded by an
-all-gather and the row-parallel GEMM followed by a reduce-scatter.  On CUDA those pairs run as SINGLE fused kernels
-(``csrc/tp_gemm.cu``): *all-gather→GEMM* streams A-operand tiles straight out of the peers' HBM with TMA,
-*GEMM→reduce-scatter* adds each accumulator tile into the owning rank's fp32 buffer with NVLink ``red.add`` from the
-epilogue — so the transfer overlaps the tensor-core work tile by tile.  Elsewhere (CPU/gloo tests, backward) the same
-maths runs on ``torch.distributed`` collectives through the autograd functions below.
+all-gather and the row-parallel GEMM followed by a reduce-scatter.  On CUDA those pairs run on the fused kernels of
+``parallel/fused_tp.py``, forward and backward: *all-gather→GEMM* — the peers' shards arrive in a local
+gathered buffer by NVLink copies on a side stream while ONE tcgen05 GEMM is already running, its TMA producer gated per shard
+by device-side ready flags; *GEMM→reduce-scatter* — the partial product is written locally into a symmetric buffer and the
+owner of a row block sums the ranks' copies inside the NVSwitch with ``multimem.ld_reduce`` (two column windows, the
+reduction of one under the GEMM of the next).  Elsewhere (CPU / gloo tests, shapes the kernels do not cover) the same maths
+runs on ``torch.distributed`` collectives through the autograd functions below.
 """
 from __future__ import annotations
 
