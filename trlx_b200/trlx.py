@@ -7,8 +7,10 @@ from typing import Callable, Dict, Iterable, List, Optional, Tuple
 
 from trlx_b200.data.configs import TRLConfig
 from trlx_b200.data.default_configs import default_ilql_config, default_ppo_config, default_sft_config
-from trlx_b200.utils import set_seed
+from trlx_b200.utils import logging, set_seed
 from trlx_b200.utils.loading import get_pipeline, get_trainer
+
+logger = logging.get_logger(__name__)
 
 
 def train(  # noqa: C901
@@ -76,6 +78,10 @@ def train(  # noqa: C901
         eval_prompts = [bos] * global_batch if eval_prompts is None else eval_prompts
     else:
         raise ValueError("Either `samples` or `reward_fn` should be given for training")
+    cap = int(os.environ.get("TRLX_B200_MAX_EVAL_PROMPTS", "0") or 0)
+    if cap > 0 and len(eval_prompts) > cap:  # smoke runs on a CPU (scripts/smoke_examples.sh): keep evaluation short
+        logger.info(f"TRLX_B200_MAX_EVAL_PROMPTS={cap}: evaluating on {cap} of {len(eval_prompts)} prompts")
+        eval_prompts = eval_prompts[:cap]
     trainer.add_eval_pipeline(prompt_pipeline(eval_prompts))
 
     checkpoint = config.train.resume_from_checkpoint
