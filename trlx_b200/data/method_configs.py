@@ -9,9 +9,9 @@ from trlx_b200.utils.registry import Registry
 _METHODS: Registry = Registry("method config")
 
 
-def register_method(target=None):
+def register_method(name=None):
     """``@register_method`` / ``@register_method("name")`` — names are lower-cased."""
-    return _METHODS.register(target)
+    return _METHODS.register(name)
 
 
 @dataclass

@@ -256,3 +256,26 @@ class MegatronModelMixin:
         """Generation caches live in the rollout engine's paged allocator, not in the module (reference ``:870``)."""
         if torch.cuda.is_available():
             torch.cuda.empty_cache()
+
+
+class PipelineTensorAPI:
+    """The two Megatron module hooks the reference's head wrappers forward to their language model
+    (``trlx/models/modeling_nemo_ppo.py:198-203``): ``set_input_tensor`` (the activation handed over by the previous pipeline
+    stage) and ``word_embeddings_weight`` (the tensor the first / last stage keep in sync when embeddings are tied).  Expects
+    ``self.language_model``."""
+
+    def _causal_lm(self):
+        from trlx_b200.models.modeling_base import base_lm
+
+        return base_lm(self.language_model)
+
+    def set_input_tensor(self, input_tensor) -> None:
+        stage = getattr(self._causal_lm(), "_pp", None)
+        if stage is None:
+            if input_tensor is not None:
+                raise RuntimeError("set_input_tensor: this model holds no pipeline stage")
+            return
+        stage.input_tensor = input_tensor
+
+    def word_embeddings_weight(self):
+        return self._causal_lm().transformer.wte.weight

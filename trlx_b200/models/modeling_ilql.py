@@ -364,13 +364,19 @@ class AutoModelForSeq2SeqLMWithILQLHeads(PreTrainedModelWrapper):
 
     def forward(self, input_ids=None, attention_mask=None, decoder_input_ids=None, past_key_values=None,
                 encoder_outputs=None, actions_ixs=None, states_ixs=None, output_attentions=None,
-                output_hidden_states=True, return_dict=False, bypass_peft_prompt_adapter=False, position_ids=None):
+                output_hidden_states=True, return_dict=False, bypass_peft_prompt_adapter=False, position_ids=None,
+                decoder_attention_mask=None, decoder_inputs_embeds=None):
         model = self.base_model
         if bypass_peft_prompt_adapter and isinstance(model, PeftModel):
             model = model.base_model
+        extra = {}
+        if decoder_attention_mask is not None:
+            extra["decoder_attention_mask"] = decoder_attention_mask
+        if decoder_inputs_embeds is not None:
+            extra["decoder_inputs_embeds"] = decoder_inputs_embeds
         out = model(input_ids=input_ids, attention_mask=attention_mask, decoder_input_ids=decoder_input_ids,
                     past_key_values=past_key_values, encoder_outputs=encoder_outputs, use_cache=True,
-                    output_hidden_states=True)
+                    output_hidden_states=True, **extra)
         hs = out.decoder_hidden_states[-1]
         qs, target_qs, vs = self.ilql_heads(hs, states_ixs=states_ixs, actions_ixs=actions_ixs)
         enc = (out.encoder_last_hidden_state,)
@@ -381,7 +387,9 @@ class AutoModelForSeq2SeqLMWithILQLHeads(PreTrainedModelWrapper):
     @torch.no_grad()
     def generate(self, input_ids=None, attention_mask=None, decoder_input_ids=None, past_key_values=None,
                  encoder_outputs=None, beta=1, max_new_tokens=32, max_length=1024, temperature=1, top_k=20,
-                 logit_mask=None, pad_token_id=None, eos_token_id=None):
+                 logit_mask=None, pad_token_id=None, eos_token_id=None, decoder_attention_mask=None):
+        # (`decoder_attention_mask` is accepted for signature parity; like the reference, ``:622-666``, generation starts from the
+        # decoder start token and every generated position is attended)
         cfg = base_lm(self.base_model).config
         pad_token_id = pad_token_id if pad_token_id is not None else cfg.pad_token_id
         eos_token_id = eos_token_id if eos_token_id is not None else cfg.eos_token_id

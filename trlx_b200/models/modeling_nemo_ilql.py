@@ -15,8 +15,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from trlx_b200.models.megatron_api import MegatronModelMixin, unwrap_float16_module  # noqa: F401
-from trlx_b200.models.modeling_nemo_ppo import make_parallel_head, reshard_for_pipeline_parallelism  # noqa: F401
+from trlx_b200.models.megatron_api import MegatronModelMixin, PipelineTensorAPI, unwrap_float16_module  # noqa: F401
+from trlx_b200.models.modeling_nemo_ppo import ParallelLinear, make_parallel_head, reshard_for_pipeline_parallelism  # noqa: F401
 from trlx_b200.parallel import state as parallel_state
 
 
@@ -50,7 +50,7 @@ class ParallelILQLHeads(nn.Module):
         self._sync_target_q_heads(self.config.alpha)
 
 
-class LMHeads(nn.Module):
+class LMHeads(PipelineTensorAPI, nn.Module):
     """Language model + extra heads evaluated on its last hidden state (reference ``:162-212``): returns
     ``(logits, heads_output)``."""
 

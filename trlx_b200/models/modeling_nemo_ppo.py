@@ -30,7 +30,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from trlx_b200.models.megatron_api import (MegatronBatchSampler, MegatronModelMixin,  # noqa: F401  (re-exported)
-                                           patch_attention_for_llama, unwrap_float16_module)
+                                           PipelineTensorAPI, patch_attention_for_llama, unwrap_float16_module)
 from trlx_b200.parallel import state as parallel_state
 from trlx_b200.parallel.tensor_parallel import _CopyToTP, _ReduceFromTP
 from trlx_b200.utils import logging
@@ -183,7 +183,7 @@ class ValueHead(nn.Module):
         return vs.transpose(0, 1) if self.seq_first else vs
 
 
-class RefLMHeads(nn.Module):
+class RefLMHeads(PipelineTensorAPI, nn.Module):
     """Policy LM + heads with the frozen *reference* policy kept as pinned host copies of the trainable parameters and
     swapped into the same modules on demand (reference ``:167-312``) — one set of weights in HBM at any time.
 

@@ -21,9 +21,9 @@ logger = logging.get_logger(__name__)
 _DATAPIPELINE: Registry = Registry("pipeline")
 
 
-def register_datapipeline(target=None):
+def register_datapipeline(name=None):
     """Register a pipeline class under its lower-cased name (or an explicit alias)."""
-    return _DATAPIPELINE.register(target)
+    return _DATAPIPELINE.register(name)
 
 
 @register_datapipeline

@@ -236,12 +236,18 @@ class ILQLRolloutStorage(_ColumnarStore):
     element_cls = ILQLElement
     batch_cls = ILQLBatch
 
+    def __init__(self, input_ids, attention_mask, rewards, states_ixs, actions_ixs, dones):
+        super().__init__(input_ids, attention_mask, rewards, states_ixs, actions_ixs, dones)
+
 
 class ILQLSeq2SeqRolloutStorage(_ColumnarStore):
     """Seq2seq variant with an extra ``decoder_input_ids`` column."""
 
     element_cls = ILQLSeq2SeqElement
     batch_cls = ILQLSeq2SeqBatch
+
+    def __init__(self, input_ids, attention_mask, decoder_input_ids, rewards, states_ixs, actions_ixs, dones):
+        super().__init__(input_ids, attention_mask, decoder_input_ids, rewards, states_ixs, actions_ixs, dones)
 
 
 def ilql_collate_fn(elems: Iterable[ILQLElement]) -> ILQLBatch:

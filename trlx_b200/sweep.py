@@ -461,9 +461,55 @@ def write_report(results, space, metric: str, mode: str, script: str, path: str)
         fh.write("\n".join(lines) + "\n")
 
 
-def create_report(results, space, metric: str, mode: str, script: str, path: str) -> None:
-    """Name used by the reference (``trlx/sweep.py:177-264``, a W&B report there); writes the Markdown report."""
-    write_report(results, space, metric, mode, script, path)
+def create_report(target_metric, column_names, entity_name, project_name, group_name, best_config):
+    """Publish a Weights & Biases report for a finished sweep whose trials logged to ``project_name`` / ``group_name``
+    (reference: ``trlx/sweep.py:177-264``): parallel coordinates and parameter importance over the swept columns, a scatter of the
+    target metric per trial, line plots of every logged metric family, and the best configuration.  Sweeps here always get the
+    local Markdown report (:func:`write_report`); this is the optional W&B view of the same runs.  Returns the report URL, or
+    ``None`` when the ``wandb`` reports API is unavailable (offline boxes)."""
+    try:
+        import wandb.apis.reports as wb
+
+        needed = ("Report", "Runset", "PanelGrid", "ParallelCoordinatesPlot", "ParameterImportancePlot", "ScatterPlot", "LinePlot",
+                  "PCColumn", "H2", "CodeBlock")
+        lacking = [n for n in needed if not hasattr(wb, n)]
+        if lacking:
+            raise ImportError(f"wandb reports API incomplete (no {lacking[0]}; `pip install wandb[workspaces]`)")
+    except Exception as err:  # no wandb / stubbed wandb: the Markdown report is the deliverable
+        print(f"[sweep] W&B report skipped ({type(err).__name__}: {err}); see report.md")
+        return None
+    runs = wb.Runset(project=project_name, entity=entity_name).set_filters_with_python_expr(f'group == "{group_name}"')
+    swept = [wb.PCColumn(f"c::{c}") for c in column_names]
+    overview = wb.PanelGrid(runsets=[runs], panels=[
+        wb.ParallelCoordinatesPlot(columns=swept + [wb.PCColumn(target_metric)], layout={"x": 0, "y": 0, "w": 24, "h": 10}),
+        wb.ParameterImportancePlot(with_respect_to=target_metric, layout={"x": 0, "y": 10, "w": 12, "h": 10}),
+        wb.ScatterPlot(x="Index", y=target_metric, running_ymax=True, font_size="small",
+                       layout={"x": 12, "y": 10, "w": 12, "h": 10}),
+    ])
+    families = {}  # one line plot per logged metric, grouped by prefix ("reward/", "losses/", ...)
+    try:
+        import wandb
+
+        for run in wandb.Api().runs(f"{entity_name}/{project_name}" if entity_name else project_name, filters={"group": group_name}):
+            for key in run.history(samples=1).columns:
+                if not key.startswith("_"):
+                    families.setdefault(key.split("/")[0], set()).add(key)
+            break
+    except Exception:
+        families = {target_metric.split("/")[0]: {target_metric}}
+    curves, row = [], 0
+    for _, keys in sorted(families.items()):
+        for i, key in enumerate(sorted(keys)):
+            curves.append(wb.LinePlot(x="Step", y=[key], title=key, layout={"x": 12 * (i % 2), "y": row, "w": 12, "h": 8}))
+            row += 8 * (i % 2)
+        row += 8
+    report = wb.Report(project=project_name, entity=entity_name, title=f"Hyperparameter sweep: {project_name}",
+                       description=group_name)
+    report.blocks = [overview, wb.PanelGrid(runsets=[runs], panels=curves),
+                     wb.H2(text="Best configuration"), wb.CodeBlock(code=[json.dumps(best_config, indent=2, default=str)], language="json")]
+    report.save()
+    print(f"[sweep] W&B report: {report.url}")
+    return report.url
 
 
 def main(argv: Optional[List[str]] = None) -> int:

@@ -16,9 +16,9 @@ from trlx_b200.utils.registry import Registry
 _TRAINERS: Registry = Registry("trainer")
 
 
-def register_trainer(target=None):
+def register_trainer(name=None):
     """Class decorator (bare or with an explicit alias) that adds a trainer to the registry."""
-    return _TRAINERS.register(target)
+    return _TRAINERS.register(name)
 
 
 @register_trainer

@@ -119,10 +119,12 @@ def set_seed(seed: int, parallel=None) -> None:
         torch.cuda.manual_seed_all(seed)
 
 
-def get_distributed_config(runtime=None) -> Dict[str, Any]:
-    """Summary of the parallel layout for trackers (reference: ``utils/__init__.py:58-80``)."""
+def get_distributed_config(accelerator=None, runtime=None) -> Dict[str, Any]:
+    """Summary of the parallel layout for trackers (reference: ``utils/__init__.py:58-80``, which takes an ``Accelerator``;
+    here the first argument is the :class:`trlx_b200.parallel.runtime.Runtime` — anything with ``describe()``)."""
+    runtime = runtime if runtime is not None else accelerator
     cfg = {"mixed_precision": "bf16", "num_gpus": world_size()}
-    if runtime is not None:
+    if runtime is not None and hasattr(runtime, "describe"):
         cfg.update(runtime.describe())
     return cfg
 

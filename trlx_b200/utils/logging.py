@@ -221,3 +221,14 @@ def enable_progress_bar() -> None:
 
 def disable_progress_bar() -> None:
     _State.progress_bars = False
+
+
+def warning_advice(self, *args, **kwargs):
+    """``logger.warning`` that stays silent when ``TRLX_NO_ADVISORY_WARNINGS`` is set (reference ``trlx/utils/logging.py:264-275``:
+    a module-level function installed on ``logging.Logger``; the per-process adapter has the same method)."""
+    if os.getenv("TRLX_NO_ADVISORY_WARNINGS", False):
+        return
+    self.warning(*args, **kwargs)
+
+
+logging.Logger.warning_advice = warning_advice

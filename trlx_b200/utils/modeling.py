@@ -217,8 +217,14 @@ def flatten_dict(d: Union[dict, MutableMapping], parent_key: str = "", sep: str 
     return out
 
 
-def gather_dict(obj: Dict, remainder: Optional[int] = None, group=None) -> Dict:
-    """Concatenate dict-of-lists across ranks (pickle all-gather); optionally trim dataloader padding."""
+def gather_dict(obj: Dict, grad_state=None, remainder: Optional[int] = None, group=None) -> Dict:
+    """Concatenate dict-of-lists across ranks (pickle all-gather); optionally trim dataloader padding — either an explicit
+    ``remainder`` or, as in the reference (``utils/modeling.py:238-259``), an object with ``end_of_dataloader`` / ``remainder``
+    attributes (Accelerate's ``GradientState``)."""
+    if isinstance(grad_state, int) and remainder is None:  # older call sites passed the remainder positionally
+        grad_state, remainder = None, grad_state
+    if grad_state is not None and getattr(grad_state, "end_of_dataloader", False) and getattr(grad_state, "remainder", 0) > 0:
+        remainder = int(grad_state.remainder)
     if not (dist.is_available() and dist.is_initialized()):
         return obj
     shards = [None] * dist.get_world_size(group)
