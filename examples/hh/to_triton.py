@@ -32,6 +32,13 @@ def build_repository(checkpoint: str, out: str, name: str, max_batch_size: int =
                 endpoint="POST /score  {\"samples\": [...]} -> {\"rewards\": [...]}")
     with open(os.path.join(out, name, "serving.json"), "w") as fh:
         json.dump(spec, fh, indent=2)
+    # for deployments that do have a Triton server: the matching ``config.pbtxt`` (a traced ``reward-model.pt`` goes into ``1/``)
+    template = os.path.join(os.path.dirname(os.path.abspath(__file__)), "triton_config.pbtxt")
+    if os.path.exists(template):
+        from string import Template
+
+        with open(template) as fh, open(os.path.join(out, name, "config.pbtxt"), "w") as dst:
+            dst.write(Template(fh.read()).substitute(model_name=name, max_batch_size=max_batch_size))
     return version_dir
 
 
