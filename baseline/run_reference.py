@@ -77,6 +77,22 @@ def main(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     cuda = torch.cuda.is_available()
+
+    # Safety net: a reference run that stalls (an untested collective pattern on a new topology, a wedged rendezvous) must not
+    # hang the harness that compares the two arms.  Every rank arms the same timer; when it fires, rank 0 reports the arm as
+    # unavailable — the contract bench.py documents — and all ranks leave.
+    import threading
+
+    limit = float(os.environ.get("REF_TIMEOUT", "900"))
+
+    def give_up():
+        if rank == 0:
+            print(json.dumps({"impl": "reference", "unavailable": f"no result after {limit:.0f} s on {world} rank(s)"}), flush=True)
+        os._exit(0)
+
+    watchdog = threading.Timer(limit, give_up)
+    watchdog.daemon = True
+    watchdog.start()
     if cuda:
         torch.cuda.set_device(local_rank)
     if world > 1 and not dist.is_initialized():
