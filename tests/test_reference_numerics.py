@@ -1,0 +1,130 @@
+"""Numerical parity with the UNMODIFIED reference (installed under ``baseline/_ref`` for the bench's reference arm): its PPO
+advantage / loss maths, ILQL loss, log-prob gather, whitening and running moments are evaluated in a separate interpreter (the
+repository's ``trlx`` alias package would shadow it here) on fixed random inputs, and compared with this framework's
+implementations of the same entry points.  Skipped when the reference is not installed."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "baseline", "_ref")
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "trlx")), reason="baseline/_ref is not installed")
+
+PRODUCER = textwrap.dedent("""
+    import sys, torch
+    import transformers  # before the stand-in `accelerate` is importable (its version probe runs at import time)
+    sys.path.insert(0, {shims!r}); sys.path.insert(0, {ref!r})
+    import transformers_compat  # noqa: F401
+    import trlx
+    assert {ref!r} in trlx.__file__, trlx.__file__
+    from trlx.data.default_configs import default_ppo_config, default_ilql_config
+    from trlx.data.ilql_types import ILQLBatch
+    from trlx.utils.modeling import logprobs_of_labels, whiten, RunningMoments, get_tensor_stats
+    inp = torch.load({inp!r})
+    out = {{}}
+    ppo = default_ppo_config().method
+    adv, ret = ppo.get_advantages_and_returns(inp["values"], inp["rewards"], inp["values"].shape[1])
+    loss, stats = ppo.loss(inp["logprobs"], inp["new_values"], inp["old_logprobs"], inp["values"], adv, ret, inp["mask"])
+    out["ppo"] = dict(adv=adv, ret=ret, loss=loss.detach(), stats={{k: float(v) for k, v in stats.items()}})
+    adv_raw, _ = ppo.get_advantages_and_returns(inp["values"], inp["rewards"], inp["values"].shape[1], use_whitening=False)
+    out["adv_raw"] = adv_raw
+    ilql = default_ilql_config().method
+    b = inp["ilql"]
+    batch = ILQLBatch(b["input_ids"], b["attention_mask"], b["rewards"], b["states_ixs"], b["actions_ixs"], b["dones"])
+    loss, stats = ilql.loss((b["logits"], (b["qs"], b["target_qs"], b["vs"])), batch)
+    out["ilql"] = dict(loss=loss.detach(), stats={{k: float(v) for k, v in stats.items()}})
+    out["logprobs"] = logprobs_of_labels(inp["logits"], inp["labels"])
+    out["whiten"] = whiten(inp["values"], shift_mean=True)
+    out["whiten_noshift"] = whiten(inp["values"], shift_mean=False)
+    rm = RunningMoments()
+    out["moments"] = [tuple(float(x) for x in rm.update(chunk)) + (float(rm.mean), float(rm.std)) for chunk in inp["chunks"]]
+    torch.save(out, {outp!r})
+""")
+
+
+def _inputs():
+    g = torch.Generator().manual_seed(0)
+    B, R, V = 6, 9, 37
+    mask = torch.ones(B, R)
+    mask[0, 6:] = 0
+    mask[3, 2:] = 0
+    inp = dict(values=torch.randn(B, R, generator=g), rewards=torch.randn(B, R, generator=g) * 0.3 * mask,
+               logprobs=-torch.rand(B, R, generator=g) * 3, old_logprobs=-torch.rand(B, R, generator=g) * 3,
+               new_values=torch.randn(B, R, generator=g), mask=mask,
+               logits=torch.randn(B, R, V, generator=g), labels=torch.randint(0, V, (B, R), generator=g),
+               chunks=[torch.randn(11, generator=g) * 2 + 1, torch.randn(7, generator=g) - 3, torch.randn(16, generator=g)])
+    # ILQL: 4 sequences of 8 tokens, 5 actions / 6 states each
+    T, A = 8, 5
+    ids = torch.randint(0, V, (4, T), generator=g)
+    actions_ixs = torch.arange(2, 2 + A).repeat(4, 1)
+    states_ixs = torch.arange(2, 3 + A).repeat(4, 1)
+    dones = torch.ones(4, A + 1, dtype=torch.long)
+    dones[:, -1] = 0
+    dones[1, 3:] = 0
+    inp["ilql"] = dict(input_ids=ids, attention_mask=torch.ones_like(ids), rewards=torch.randn(4, A, generator=g),
+                       states_ixs=states_ixs, actions_ixs=actions_ixs, dones=dones, logits=torch.randn(4, T, V, generator=g),
+                       qs=tuple(torch.randn(4, A, V, generator=g) for _ in range(2)),
+                       target_qs=tuple(torch.randn(4, A, V, generator=g) for _ in range(2)), vs=torch.randn(4, A + 1, 1, generator=g))
+    return inp
+
+
+@pytest.fixture(scope="module")
+def reference_outputs(tmp_path_factory):
+    d = tmp_path_factory.mktemp("refnum")
+    inp, outp = str(d / "in.pt"), str(d / "out.pt")
+    torch.save(_inputs(), inp)
+    code = PRODUCER.format(shims=os.path.join(ROOT, "baseline", "shims"), ref=REF, inp=inp, outp=outp)
+    env = {k: v for k, v in os.environ.items() if k != "PYTHONPATH"}
+    res = subprocess.run([sys.executable, "-c", code], cwd=str(d), env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-3000:]
+    return torch.load(outp, weights_only=False)
+
+
+def test_ppo_advantages_and_loss_match_the_reference(reference_outputs):
+    from trlx_b200.data.default_configs import default_ppo_config
+
+    inp, ref = _inputs(), reference_outputs
+    ppo = default_ppo_config().method
+    adv, ret = ppo.get_advantages_and_returns(inp["values"], inp["rewards"], inp["values"].shape[1])
+    torch.testing.assert_close(adv, ref["ppo"]["adv"], atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(ret, ref["ppo"]["ret"], atol=1e-5, rtol=1e-5)
+    raw, _ = ppo.get_advantages_and_returns(inp["values"], inp["rewards"], inp["values"].shape[1], use_whitening=False)
+    torch.testing.assert_close(raw, ref["adv_raw"], atol=1e-5, rtol=1e-5)
+    loss, stats = ppo.loss(inp["logprobs"], inp["new_values"], inp["old_logprobs"], inp["values"], adv, ret, inp["mask"])
+    torch.testing.assert_close(loss.detach(), ref["ppo"]["loss"], atol=1e-5, rtol=1e-5)
+    mine = {k: float(v) for k, v in stats.items()}
+    assert set(ref["ppo"]["stats"]) <= set(mine), set(ref["ppo"]["stats"]) - set(mine)
+    for k, v in ref["ppo"]["stats"].items():
+        assert abs(mine[k] - v) <= 1e-4 * max(1.0, abs(v)), (k, mine[k], v)
+
+
+def test_ilql_loss_matches_the_reference(reference_outputs):
+    from trlx_b200.data.default_configs import default_ilql_config
+    from trlx_b200.data.ilql_types import ILQLBatch
+
+    b, ref = _inputs()["ilql"], reference_outputs["ilql"]
+    batch = ILQLBatch(b["input_ids"], b["attention_mask"], b["rewards"], b["states_ixs"], b["actions_ixs"], b["dones"])
+    loss, stats = default_ilql_config().method.loss((b["logits"], (b["qs"], b["target_qs"], b["vs"])), batch)
+    torch.testing.assert_close(loss.detach(), ref["loss"], atol=1e-4, rtol=1e-5)
+    mine = {k: float(v) for k, v in stats.items()}
+    assert set(ref["stats"]) <= set(mine), set(ref["stats"]) - set(mine)
+    for k, v in ref["stats"].items():
+        assert abs(mine[k] - v) <= 2e-4 * max(1.0, abs(v)), (k, mine[k], v)
+
+
+def test_statistics_helpers_match_the_reference(reference_outputs):
+    from trlx_b200.utils.modeling import RunningMoments, logprobs_of_labels, whiten
+
+    inp, ref = _inputs(), reference_outputs
+    torch.testing.assert_close(logprobs_of_labels(inp["logits"], inp["labels"]), ref["logprobs"], atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(whiten(inp["values"], shift_mean=True), ref["whiten"], atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(whiten(inp["values"], shift_mean=False), ref["whiten_noshift"], atol=1e-5, rtol=1e-5)
+    rm = RunningMoments()
+    for chunk, want in zip(inp["chunks"], ref["moments"]):
+        got = tuple(float(x) for x in rm.update(chunk)) + (float(rm.mean), float(rm.std))
+        for a, b in zip(got, want):
+            assert abs(a - b) <= 1e-5 * max(1.0, abs(b)), (got, want)
