@@ -1,0 +1,143 @@
+"""Interoperability with the UNMODIFIED reference (``baseline/_ref``, run in a separate interpreter):
+
+* checkpoints — a hydra value-head model saved by the reference's ``save_pretrained`` loads here and produces the same logits,
+  values and frozen-branch logits; a checkpoint saved here loads in the reference and reproduces them too (the
+  checkpoint format is part of the public contract);
+* data — ``tokenize_dialogue`` and the offline (ILQL) experience construction give identical token / index / reward tensors.
+
+Skipped when the reference is not installed."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "baseline", "_ref")
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "trlx")), reason="baseline/_ref is not installed")
+
+HEADER = textwrap.dedent("""
+    import os, sys, torch
+    import transformers, transformers.modeling_utils, transformers.generation  # before the stand-in packages are importable
+    sys.path.insert(0, {root!r})
+    sys.path.insert(0, os.path.join({root!r}, "baseline"))
+    from run_reference import prepare_assets
+    sys.path.remove({root!r}); sys.path.remove(os.path.join({root!r}, "baseline"))
+    for m in [k for k in sys.modules if k == "trlx_b200" or k.startswith("trlx_b200.")]:
+        sys.modules.pop(m)  # (prepare_assets used this framework's tokenizer builder; the reference must not see it)
+    sys.path.insert(0, {shims!r}); sys.path.insert(0, {ref!r})
+    import transformers_compat  # noqa: F401
+    import trlx
+    assert {ref!r} in trlx.__file__, trlx.__file__
+""")
+
+STAGE1 = HEADER + textwrap.dedent("""
+    from trlx.models.modeling_ppo import AutoModelForCausalLMWithHydraValueHead
+    from trlx.pipeline.offline_pipeline import tokenize_dialogue
+    from trlx.trainer.accelerate_ilql_trainer import make_experience
+    work = {work!r}
+    model_dir, tok_dir = prepare_assets(work, tiny=True)
+    torch.manual_seed(5)
+    model = AutoModelForCausalLMWithHydraValueHead.from_pretrained(model_dir, num_layers_unfrozen=2).eval()
+    with torch.no_grad():
+        for p in model.v_head.parameters():
+            p.copy_(torch.randn_like(p) * 0.1)
+        for p in model.frozen_head.parameters():   # make the frozen branch distinguishable from the live one
+            p.add_(torch.randn_like(p) * 0.01)
+    ids = torch.load({ids!r})
+    mask = torch.ones_like(ids); mask[0, :3] = 0
+    pos = (mask.cumsum(-1) - 1).clamp_min(0)
+    with torch.no_grad():
+        out = model(input_ids=ids, attention_mask=mask, position_ids=pos, return_dict=True)
+        hydra = model.forward_hydra(input_ids=ids, attention_mask=mask, position_ids=pos, return_dict=True).logits
+    model.save_pretrained(os.path.join(work, "ref_ckpt"))
+    tok = transformers.AutoTokenizer.from_pretrained(tok_dir)
+    dialogues = {dialogues!r}
+    toks = [[(m.is_output, list(m.tokens)) for m in tokenize_dialogue(d, tok, L)] for d, L in dialogues]
+    store = make_experience([d for d, _ in dialogues], {rewards!r}, tok, max_length=24, verbose=False)
+    cols = {{k: [t.clone() for t in getattr(store, k)] for k in ("input_ids", "attention_mask", "rewards", "states_ixs", "actions_ixs", "dones")}}
+    torch.save(dict(logits=out.logits, value=out.value, hydra=hydra, toks=toks, store=cols, model_dir=model_dir, tok_dir=tok_dir),
+               os.path.join(work, "stage1.pt"))
+""")
+
+STAGE2 = HEADER + textwrap.dedent("""
+    from trlx.models.modeling_ppo import AutoModelForCausalLMWithHydraValueHead
+    work = {work!r}
+    model = AutoModelForCausalLMWithHydraValueHead.from_pretrained(os.path.join(work, "our_ckpt"), num_layers_unfrozen=2).eval()
+    ids = torch.load({ids!r})
+    mask = torch.ones_like(ids); mask[0, :3] = 0
+    pos = (mask.cumsum(-1) - 1).clamp_min(0)
+    with torch.no_grad():
+        out = model(input_ids=ids, attention_mask=mask, position_ids=pos, return_dict=True)
+        hydra = model.forward_hydra(input_ids=ids, attention_mask=mask, position_ids=pos, return_dict=True).logits
+    torch.save(dict(logits=out.logits, value=out.value, hydra=hydra), os.path.join(work, "stage2.pt"))
+""")
+
+DIALOGUES = [("hello there general", 24), (("question one", "answer one is long enough"), 24),
+             (["a first prompt", "a reply", "a follow up", "the final reply of the dialogue"], 24),
+             (("short", "this reply will be truncated because the budget is tiny"), 8)]
+REWARDS = [1.0, -0.5, 2.0, 0.25]
+
+
+def _run(code, work):
+    env = {k: v for k, v in os.environ.items() if k != "PYTHONPATH"}
+    res = subprocess.run([sys.executable, "-c", code], cwd=work, env=env, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stderr[-4000:]
+
+
+@pytest.fixture(scope="module")
+def stage1(tmp_path_factory):
+    work = str(tmp_path_factory.mktemp("interop"))
+    ids = torch.randint(5, 900, (3, 11), generator=torch.Generator().manual_seed(2))
+    torch.save(ids, os.path.join(work, "ids.pt"))
+    fmt = dict(root=ROOT, shims=os.path.join(ROOT, "baseline", "shims"), ref=REF, work=work, ids=os.path.join(work, "ids.pt"),
+               dialogues=DIALOGUES, rewards=REWARDS)
+    _run(STAGE1.format(**fmt), work)
+    return work, fmt, ids, torch.load(os.path.join(work, "stage1.pt"), weights_only=False)
+
+
+def _forward(model, ids):
+    mask = torch.ones_like(ids)
+    mask[0, :3] = 0
+    pos = (mask.cumsum(-1) - 1).clamp_min(0)
+    with torch.no_grad():
+        out = model(input_ids=ids, attention_mask=mask, position_ids=pos, return_dict=True)
+        hydra = model.forward_hydra(input_ids=ids, attention_mask=mask, position_ids=pos, return_dict=True).logits
+    return out.logits, out.value, hydra, mask.bool()
+
+
+def test_checkpoints_round_trip_between_the_reference_and_this_framework(stage1):
+    from trlx_b200.models.modeling_ppo import AutoModelForCausalLMWithHydraValueHead
+
+    work, fmt, ids, ref = stage1
+    ours = AutoModelForCausalLMWithHydraValueHead.from_pretrained(os.path.join(work, "ref_ckpt"), num_layers_unfrozen=2).eval()
+    logits, value, hydra, m = _forward(ours, ids)
+    assert (logits - ref["logits"])[m].abs().max() < 2e-4
+    assert (value - ref["value"])[m].abs().max() < 2e-4
+    assert (hydra - ref["hydra"])[m].abs().max() < 2e-4
+    assert (hydra - logits)[m].abs().max() > 1e-3  # the frozen branch really is a different set of weights
+    ours.save_pretrained(os.path.join(work, "our_ckpt"))
+    _run(STAGE2.format(**fmt), work)
+    back = torch.load(os.path.join(work, "stage2.pt"), weights_only=False)
+    for k in ("logits", "value", "hydra"):
+        assert (back[k] - ref[k])[m].abs().max() < 2e-4, k
+
+
+def test_dialogue_tokenisation_and_offline_experience_match_the_reference(stage1):
+    import transformers
+
+    from trlx_b200.pipeline.offline_pipeline import tokenize_dialogue
+    from trlx_b200.trainer.accelerate_ilql_trainer import make_experience
+
+    work, fmt, ids, ref = stage1
+    tok = transformers.AutoTokenizer.from_pretrained(ref["tok_dir"])
+    mine = [[(m.is_output, list(m.tokens)) for m in tokenize_dialogue(d, tok, L)] for d, L in DIALOGUES]
+    assert mine == ref["toks"]
+    store = make_experience([d for d, _ in DIALOGUES], REWARDS, tok, max_length=24, verbose=False)
+    for k, want in ref["store"].items():
+        got = getattr(store, k)
+        assert len(got) == len(want), k
+        for a, b in zip(got, want):
+            torch.testing.assert_close(torch.as_tensor(a).to(b.dtype), b, atol=1e-6, rtol=1e-6, msg=lambda m: f"{k}: {m}")
