@@ -58,8 +58,29 @@ STAGE1 = HEADER + textwrap.dedent("""
     toks = [[(m.is_output, list(m.tokens)) for m in tokenize_dialogue(d, tok, L)] for d, L in dialogues]
     store = make_experience([d for d, _ in dialogues], {rewards!r}, tok, max_length=24, verbose=False)
     cols = {{k: [t.clone() for t in getattr(store, k)] for k in ("input_ids", "attention_mask", "rewards", "states_ixs", "actions_ixs", "dones")}}
-    torch.save(dict(logits=out.logits, value=out.value, hydra=hydra, toks=toks, store=cols, model_dir=model_dir, tok_dir=tok_dir),
-               os.path.join(work, "stage1.pt"))
+    # ILQL heads model: forward outputs + checkpoint
+    from trlx.models.modeling_ilql import AutoModelForCausalLMWithILQLHeads
+    torch.manual_seed(6)
+    ilql = AutoModelForCausalLMWithILQLHeads.from_pretrained(model_dir, two_qs=True, alpha=0.5).eval()
+    with torch.no_grad():
+        for p in ilql.ilql_heads.parameters():
+            p.copy_(torch.randn_like(p) * 0.05)
+    s_ix = torch.tensor([[4, 5, 6, 7]] * ids.shape[0]); a_ix = s_ix[:, :-1]
+    with torch.no_grad():
+        il_logits, qs, tqs, vs, _ = ilql(input_ids=ids, attention_mask=mask, position_ids=pos, states_ixs=s_ix, actions_ixs=a_ix)
+    ilql.save_pretrained(os.path.join(work, "ref_ilql_ckpt"))
+    # PPO store collation
+    from trlx.data.ppo_types import PPORLElement
+    from trlx.pipeline.ppo_pipeline import ppo_collate_fn
+    g = torch.Generator().manual_seed(9)
+    elems = [PPORLElement(torch.randint(1, 50, (q,), generator=g), torch.randint(1, 50, (r,), generator=g),
+                          torch.randn(r, generator=g), torch.randn(r, generator=g), torch.randn(r, generator=g))
+             for q, r in ((3, 5), (6, 2), (4, 4))]
+    collated = {{side: [getattr(ppo_collate_fn(side, 0, elems), f) for f in
+                        ("query_tensors", "response_tensors", "logprobs", "values", "rewards")] for side in ("left", "right")}}
+    torch.save(dict(logits=out.logits, value=out.value, hydra=hydra, toks=toks, store=cols, model_dir=model_dir, tok_dir=tok_dir,
+                    ilql=dict(logits=il_logits, qs=qs, tqs=tqs, vs=vs), elems=[tuple(e.__dict__.values()) for e in elems],
+                    collated=collated), os.path.join(work, "stage1.pt"))
 """)
 
 STAGE2 = HEADER + textwrap.dedent("""
@@ -141,3 +162,27 @@ def test_dialogue_tokenisation_and_offline_experience_match_the_reference(stage1
         assert len(got) == len(want), k
         for a, b in zip(got, want):
             torch.testing.assert_close(torch.as_tensor(a).to(b.dtype), b, atol=1e-6, rtol=1e-6, msg=lambda m: f"{k}: {m}")
+
+
+def test_ilql_heads_checkpoint_and_ppo_collation_match_the_reference(stage1):
+    from trlx_b200.data.ppo_types import PPORLElement
+    from trlx_b200.models.modeling_ilql import AutoModelForCausalLMWithILQLHeads
+    from trlx_b200.pipeline.ppo_pipeline import ppo_collate_fn
+
+    work, fmt, ids, ref = stage1
+    model = AutoModelForCausalLMWithILQLHeads.from_pretrained(os.path.join(work, "ref_ilql_ckpt"), two_qs=True, alpha=0.5).eval()
+    mask = torch.ones_like(ids)
+    mask[0, :3] = 0
+    pos = (mask.cumsum(-1) - 1).clamp_min(0)
+    s_ix = torch.tensor([[4, 5, 6, 7]] * ids.shape[0])
+    with torch.no_grad():
+        logits, qs, tqs, vs, _ = model(input_ids=ids, attention_mask=mask, position_ids=pos, states_ixs=s_ix, actions_ixs=s_ix[:, :-1])
+    want = ref["ilql"]
+    assert (logits - want["logits"])[mask.bool()].abs().max() < 2e-4
+    for got, exp in zip(list(qs) + list(tqs) + [vs], list(want["qs"]) + list(want["tqs"]) + [want["vs"]]):
+        torch.testing.assert_close(got, exp, atol=2e-4, rtol=1e-4)
+    elems = [PPORLElement(*fields) for fields in ref["elems"]]
+    for side in ("left", "right"):
+        batch = ppo_collate_fn(side, 0, elems)
+        for f, exp in zip(("query_tensors", "response_tensors", "logprobs", "values", "rewards"), ref["collated"][side]):
+            torch.testing.assert_close(getattr(batch, f), exp, msg=lambda m: f"{side} {f}: {m}")
