@@ -83,6 +83,37 @@ STAGE1 = HEADER + textwrap.dedent("""
                     collated=collated), os.path.join(work, "stage1.pt"))
 """)
 
+ROLLOUT = HEADER + textwrap.dedent("""
+    from trlx.data.default_configs import default_ppo_config
+    from trlx.pipeline.offline_pipeline import PromptPipeline
+    from trlx.trainer.accelerate_ppo_trainer import AcceleratePPOTrainer
+    work = {work!r}
+    st = torch.load(os.path.join(work, "stage1.pt"), weights_only=False)
+    cfg = default_ppo_config()
+    # perturbed value head and frozen branch (non-zero KL penalty); the copy re-saved by this framework, because the reference's
+    # loader only looks for `pytorch_model.bin` while its own `save_pretrained` writes safetensors under transformers 5
+    cfg.model.model_path = os.path.join(work, "our_ckpt")
+    cfg.model.num_layers_unfrozen = 2
+    cfg.tokenizer.tokenizer_path = st["tok_dir"]
+    cfg.train.tracker = None
+    cfg.train.seq_length, cfg.train.batch_size = 40, 4
+    cfg.train.checkpoint_dir = os.path.join(work, "ckpt_ref")
+    cfg.method.num_rollouts, cfg.method.chunk_size = 8, 4
+    cfg.method.init_kl_coef = 0.3
+    cfg.method.gen_kwargs = dict(max_new_tokens=8, do_sample=False, top_k=0, top_p=1.0)
+    torch.manual_seed(0)
+    trainer = AcceleratePPOTrainer(config=cfg, reward_fn=lambda samples, **kw: [float(len(s)) / 10 for s in samples],
+                                   metric_fn=None, stop_sequences=[])
+    trainer.add_prompt_pipeline(PromptPipeline({prompts!r}, 32, trainer.tokenizer))
+    trainer.make_experience(8)
+    torch.save([tuple(t.detach().float().cpu() if t.is_floating_point() else t.cpu() for t in
+                      (e.query_tensor, e.response_tensor, e.logprobs, e.values, e.rewards)) for e in trainer.store.history],
+               os.path.join(work, "rollouts_ref.pt"))
+""")
+
+PROMPTS = ["the movie was", "i thought this film", "quite", "after watching the director", "story plot acting felt very long",
+           "an", "really good scenes and", "boring but"]
+
 STAGE2 = HEADER + textwrap.dedent("""
     from trlx.models.modeling_ppo import AutoModelForCausalLMWithHydraValueHead
     work = {work!r}
@@ -119,6 +150,17 @@ def stage1(tmp_path_factory):
     return work, fmt, ids, torch.load(os.path.join(work, "stage1.pt"), weights_only=False)
 
 
+def _our_ckpt(work):
+    """``ref_ckpt`` (written by the reference) re-saved by this framework (``pytorch_model.bin`` layout)."""
+    from trlx_b200.models.modeling_ppo import AutoModelForCausalLMWithHydraValueHead
+
+    path = os.path.join(work, "our_ckpt")
+    if not os.path.exists(os.path.join(path, "pytorch_model.bin")):
+        model = AutoModelForCausalLMWithHydraValueHead.from_pretrained(os.path.join(work, "ref_ckpt"), num_layers_unfrozen=2)
+        model.save_pretrained(path)
+    return path
+
+
 def _forward(model, ids):
     mask = torch.ones_like(ids)
     mask[0, :3] = 0
@@ -140,6 +182,7 @@ def test_checkpoints_round_trip_between_the_reference_and_this_framework(stage1)
     assert (hydra - ref["hydra"])[m].abs().max() < 2e-4
     assert (hydra - logits)[m].abs().max() > 1e-3  # the frozen branch really is a different set of weights
     ours.save_pretrained(os.path.join(work, "our_ckpt"))
+    assert os.path.exists(os.path.join(work, "our_ckpt", "pytorch_model.bin"))
     _run(STAGE2.format(**fmt), work)
     back = torch.load(os.path.join(work, "stage2.pt"), weights_only=False)
     for k in ("logits", "value", "hydra"):
@@ -186,3 +229,54 @@ def test_ilql_heads_checkpoint_and_ppo_collation_match_the_reference(stage1):
         batch = ppo_collate_fn(side, 0, elems)
         for f, exp in zip(("query_tensors", "response_tensors", "logprobs", "values", "rewards"), ref["collated"][side]):
             torch.testing.assert_close(getattr(batch, f), exp, msg=lambda m: f"{side} {f}: {m}")
+
+
+def test_ppo_experience_matches_the_reference_rollout_arithmetic(stage1):
+    """Same checkpoint (distinct frozen branch and value head), same prompts, greedy decoding: every stored rollout — query,
+    response, per-token log-probs, values and KL-penalised rewards with the score on the last token — equals what the
+    reference's own ``make_experience`` stores (matched by prompt; both frameworks shuffle their prompt loaders)."""
+    from trlx_b200.data.default_configs import default_ppo_config
+    from trlx_b200.pipeline.offline_pipeline import PromptPipeline
+    from trlx_b200.utils.loading import get_trainer
+
+    work, fmt, ids, ref = stage1
+    ckpt = _our_ckpt(work)
+    _run(ROLLOUT.format(prompts=PROMPTS, **fmt), work)
+    want = torch.load(os.path.join(work, "rollouts_ref.pt"), weights_only=False)
+    cfg = default_ppo_config().evolve(
+        model=dict(model_path=ckpt, num_layers_unfrozen=2),
+        tokenizer=dict(tokenizer_path=ref["tok_dir"]),
+        train=dict(tracker=None, seq_length=40, batch_size=4, checkpoint_dir=os.path.join(work, "ckpt_ours")),
+        method=dict(num_rollouts=8, chunk_size=4, init_kl_coef=0.3, gen_kwargs=dict(max_new_tokens=8, do_sample=False, top_k=0, top_p=1.0)))
+    torch.manual_seed(0)
+    trainer = get_trainer(cfg.train.trainer)(config=cfg, reward_fn=lambda samples, **kw: [float(len(s)) / 10 for s in samples],
+                                             metric_fn=None, stop_sequences=[])
+    trainer.add_prompt_pipeline(PromptPipeline(PROMPTS, 32, trainer.tokenizer))
+    trainer.make_experience(8)
+    pad = trainer.tokenizer.pad_token_id
+    mine = {tuple(int(t) for t in e.query_tensor.tolist() if t != pad): e for e in trainer.store.history}
+    assert len(want) == 8 == len(mine)
+    for q, r, lp, v, rw in want:
+        e = mine[tuple(int(t) for t in q.tolist() if t != pad)]
+        # (the reference stores the response padded to its chunk's width, this framework trims it: trailing pads carry no maths —
+        # log-probs / values / rewards below are sliced to the true length in both)
+        def strip(t):
+            t = t.tolist()
+            while t and t[-1] == pad:
+                t.pop()
+            return t
+
+        assert strip(e.response_tensor) == strip(r)
+        assert len(e.logprobs) == len(lp) == len(v) == len(rw)
+        # One documented deviation (DESIGN §2): with pad == eos the last stored position of a finished sample is a token the
+        # reference's attention mask counts as padding, and the reference gives padded positions `position_id = 1`
+        # (`accelerate_ppo_trainer.py:417-418`) while this framework keeps counting.  That position is masked out of the loss; its
+        # log-prob / value are compared loosely, everything else — including every reward — exactly.
+        n = len(lp)
+        tail_is_pad = n >= 2 and int(e.response_tensor[n - 2]) == pad
+        k = n - 1 if tail_is_pad else n
+        torch.testing.assert_close(e.logprobs.float().cpu()[:k], lp[:k], atol=2e-4, rtol=1e-4)
+        torch.testing.assert_close(e.values.float().cpu()[:k], v[:k], atol=2e-4, rtol=1e-4)
+        torch.testing.assert_close(e.rewards.float().cpu(), rw, atol=2e-4, rtol=1e-4)
+        assert (e.values.float().cpu()[k:] - v[k:]).abs().max().item() < 1.0 if k < n else True
+        assert rw[:-1].abs().max() > 1e-4  # the KL penalty is really there (frozen branch differs from the policy)
