@@ -109,7 +109,64 @@ ROLLOUT = HEADER + textwrap.dedent("""
     torch.save([tuple(t.detach().float().cpu() if t.is_floating_point() else t.cpu() for t in
                       (e.query_tensor, e.response_tensor, e.logprobs, e.values, e.rewards)) for e in trainer.store.history],
                os.path.join(work, "rollouts_ref.pt"))
+    batch = next(iter(trainer.store.create_loader(4, shuffle=False)))
+    trainer.model.eval()  # (HF's GPT-2 config carries dropout 0.1, which the reference leaves on while training: not comparable)
+    loss, stats = trainer.loss(batch)
+    loss.backward()
+    inner = trainer.accelerator.unwrap_model(trainer.model)
+    torch.save(dict(batch=[getattr(batch, f) for f in ("query_tensors", "response_tensors", "logprobs", "values", "rewards")],
+                    loss=loss.detach(), stats={{k: float(v) for k, v in stats.items()}},
+                    g_vhead=inner.v_head[2].weight.grad.clone(), g_lnf=inner.base_model.transformer.ln_f.weight.grad.clone()),
+               os.path.join(work, "ppo_loss_ref.pt"))
 """)
+
+OFFLINE = HEADER + textwrap.dedent("""
+    from trlx.data.default_configs import default_ilql_config, default_sft_config
+    from trlx.trainer.accelerate_ilql_trainer import AccelerateILQLTrainer
+    from trlx.trainer.accelerate_sft_trainer import AccelerateSFTTrainer
+    work = {work!r}
+    st = torch.load(os.path.join(work, "stage1.pt"), weights_only=False)
+    samples = {samples!r}
+    # ---- ILQL
+    cfg = default_ilql_config()
+    cfg.model.model_path = os.path.join(work, "our_ilql_ckpt")
+    cfg.tokenizer.tokenizer_path = st["tok_dir"]
+    cfg.train.tracker, cfg.train.seq_length, cfg.train.batch_size = None, 32, 4
+    cfg.train.checkpoint_dir = os.path.join(work, "ckpt_ref_ilql")
+    cfg.method.alpha = 0.5
+    torch.manual_seed(0)
+    tr = AccelerateILQLTrainer(config=cfg, reward_fn=None, metric_fn=None, stop_sequences=[])
+    tr.make_experience(samples, {rewards!r}, 32)
+    batch = next(iter(tr.store.create_loader(4)))
+    tr.model.eval()
+    loss, stats = tr.loss(batch)
+    loss.backward()
+    inner = tr.accelerator.unwrap_model(tr.model)
+    out = dict(ilql=dict(loss=loss.detach(), stats={{k: float(v) for k, v in stats.items()}},
+                         batch=[getattr(batch, f) for f in ("input_ids", "attention_mask", "rewards", "states_ixs", "actions_ixs", "dones")],
+                         g_v=inner.ilql_heads.v_head[2].weight.grad.clone(), g_q=inner.ilql_heads.q_heads[1][0].weight.grad.clone(),
+                         g_lnf=inner.base_model.transformer.ln_f.weight.grad.clone()))
+    # ---- SFT
+    cfg = default_sft_config()
+    cfg.model.model_path = st["model_dir"]
+    cfg.tokenizer.tokenizer_path = st["tok_dir"]
+    cfg.train.tracker, cfg.train.seq_length, cfg.train.batch_size = None, 32, 4
+    cfg.train.checkpoint_dir = os.path.join(work, "ckpt_ref_sft")
+    torch.manual_seed(0)
+    tr = AccelerateSFTTrainer(config=cfg, reward_fn=None, metric_fn=None, stop_sequences=[])
+    tr.make_experience(samples, 32)
+    batch = next(iter(tr.store.create_loader(4)))
+    tr.model.eval()
+    loss, stats = tr.loss(batch)
+    loss.backward()
+    inner = tr.accelerator.unwrap_model(tr.model)
+    out["sft"] = dict(loss=loss.detach(), batch={{k: v for k, v in batch.items()}},
+                      g_lnf=inner.transformer.ln_f.weight.grad.clone(), g_wte=inner.transformer.wte.weight.grad.clone())
+    torch.save(out, os.path.join(work, "offline_ref.pt"))
+""")
+
+SAMPLES = [("the movie was", " really quite good"), ("i thought", " this plot felt very long and boring"), ("film", " great"),
+           ("after watching the director", " acting scenes")]
 
 PROMPTS = ["the movie was", "i thought this film", "quite", "after watching the director", "story plot acting felt very long",
            "an", "really good scenes and", "boring but"]
@@ -280,3 +337,90 @@ def test_ppo_experience_matches_the_reference_rollout_arithmetic(stage1):
         torch.testing.assert_close(e.rewards.float().cpu(), rw, atol=2e-4, rtol=1e-4)
         assert (e.values.float().cpu()[k:] - v[k:]).abs().max().item() < 1.0 if k < n else True
         assert rw[:-1].abs().max() > 1e-4  # the KL penalty is really there (frozen branch differs from the policy)
+
+
+def _stats_close(mine, want, tol=2e-4):
+    assert set(want) <= set(mine), set(want) - set(mine)
+    for k, v in want.items():
+        assert abs(float(mine[k]) - v) <= tol * max(1.0, abs(v)), (k, float(mine[k]), v)
+
+
+def test_ppo_trainer_loss_and_gradients_match_the_reference(stage1):
+    """``trainer.loss(batch)`` on the reference's own collated batch: loss, all statistics, and gradients."""
+    from trlx_b200.data.default_configs import default_ppo_config
+    from trlx_b200.data.ppo_types import PPORLBatch
+    from trlx_b200.utils.loading import get_trainer
+
+    work, fmt, ids, ref = stage1
+    ckpt = _our_ckpt(work)
+    if not os.path.exists(os.path.join(work, "ppo_loss_ref.pt")):
+        _run(ROLLOUT.format(prompts=PROMPTS, **fmt), work)
+    want = torch.load(os.path.join(work, "ppo_loss_ref.pt"), weights_only=False)
+    cfg = default_ppo_config().evolve(
+        model=dict(model_path=ckpt, num_layers_unfrozen=2), tokenizer=dict(tokenizer_path=ref["tok_dir"]),
+        train=dict(tracker=None, seq_length=40, batch_size=4, checkpoint_dir=os.path.join(work, "ckpt_ours2"),
+                   trainer_kwargs=dict(cache_trunk=False)),
+        method=dict(num_rollouts=8, chunk_size=4, init_kl_coef=0.3, gen_kwargs=dict(max_new_tokens=8, do_sample=False, top_k=0, top_p=1.0)))
+    trainer = get_trainer(cfg.train.trainer)(config=cfg, reward_fn=lambda samples, **kw: [0.0] * len(samples), metric_fn=None,
+                                             stop_sequences=[])
+    trainer.model.eval()
+    loss, stats = trainer.loss(PPORLBatch(*want["batch"]))
+    loss.backward()
+    torch.testing.assert_close(loss.detach().float().cpu(), want["loss"], atol=2e-5, rtol=1e-4)
+    _stats_close({k: float(v) for k, v in stats.items()}, want["stats"])
+    torch.testing.assert_close(trainer.model.v_head[2].weight.grad, want["g_vhead"], atol=1e-5, rtol=1e-3)
+    torch.testing.assert_close(trainer.model.base_model.transformer.ln_f.weight.grad, want["g_lnf"], atol=1e-5, rtol=1e-3)
+
+
+def test_ilql_and_sft_trainer_losses_and_gradients_match_the_reference(stage1):
+    from trlx_b200.data.default_configs import default_ilql_config, default_sft_config
+    from trlx_b200.data.ilql_types import ILQLBatch
+    from trlx_b200.models.modeling_ilql import AutoModelForCausalLMWithILQLHeads
+    from trlx_b200.utils.loading import get_trainer
+
+    work, fmt, ids, ref = stage1
+    path = os.path.join(work, "our_ilql_ckpt")
+    if not os.path.exists(os.path.join(path, "pytorch_model.bin")):
+        AutoModelForCausalLMWithILQLHeads.from_pretrained(os.path.join(work, "ref_ilql_ckpt"), two_qs=True, alpha=0.5).save_pretrained(path)
+    rewards = [1.0, -1.0, 0.5, 2.0]
+    _run(OFFLINE.format(samples=SAMPLES, **dict(fmt, rewards=rewards)), work)
+    want = torch.load(os.path.join(work, "offline_ref.pt"), weights_only=False)
+    # ---- ILQL: same stored experience, loss on the reference's batch
+    cfg = default_ilql_config().evolve(
+        model=dict(model_path=path), tokenizer=dict(tokenizer_path=ref["tok_dir"]), method=dict(alpha=0.5),
+        train=dict(tracker=None, seq_length=32, batch_size=4, checkpoint_dir=os.path.join(work, "ckpt_ours_ilql")))
+    tr = get_trainer(cfg.train.trainer)(config=cfg, reward_fn=None, metric_fn=None, stop_sequences=[])
+    tr.model.eval()
+    loss, stats = tr.loss(ILQLBatch(*want["ilql"]["batch"]))
+    loss.backward()
+    torch.testing.assert_close(loss.detach().float().cpu(), want["ilql"]["loss"], atol=1e-4, rtol=1e-4)
+    _stats_close({k: float(v) for k, v in stats.items()}, want["ilql"]["stats"], tol=5e-4)
+    heads = tr.model.ilql_heads
+    torch.testing.assert_close(heads.v_head[2].weight.grad, want["ilql"]["g_v"], atol=1e-5, rtol=2e-3)
+    torch.testing.assert_close(heads.q_heads[1][0].weight.grad, want["ilql"]["g_q"], atol=1e-5, rtol=2e-3)
+    torch.testing.assert_close(tr.model.base_model.transformer.ln_f.weight.grad, want["ilql"]["g_lnf"], atol=1e-5, rtol=2e-3)
+    # ---- SFT
+    cfg = default_sft_config().evolve(
+        model=dict(model_path=ref["model_dir"]), tokenizer=dict(tokenizer_path=ref["tok_dir"]),
+        train=dict(tracker=None, seq_length=32, batch_size=4, checkpoint_dir=os.path.join(work, "ckpt_ours_sft")))
+    tr = get_trainer(cfg.train.trainer)(config=cfg, reward_fn=None, metric_fn=None, stop_sequences=[])
+    tr.model.eval()
+    from transformers import BatchEncoding
+
+    enc = BatchEncoding(dict(want["sft"]["batch"]))
+    loss, stats = tr.loss(enc)
+    lm = tr.model.base_model if hasattr(tr.model, "base_model") else tr.model
+    if bool((enc["attention_mask"][:, 0] == 0).any()):
+        # Documented deviation (DESIGN §2): the reference calls HF's forward without position ids, so LEFT-padded rows are
+        # embedded at positions shifted by their padding; here positions always follow the attention mask (as HF's own
+        # `generate` does).  With the reference's positions this model gives the reference's loss and gradients exactly.
+        assert abs(float(loss.detach()) - float(want["sft"]["loss"])) < 0.2
+        ids, mask = enc["input_ids"], enc["attention_mask"]
+        labels = enc["labels"].clone() if "labels" in enc else ids.clone()  # DialogStore masks the prompt tokens out
+        labels[~mask.bool()] = -100
+        lm.zero_grad()
+        loss = lm(input_ids=ids, attention_mask=mask, position_ids=torch.arange(ids.shape[1]).expand_as(ids), labels=labels).loss
+    loss.backward()
+    torch.testing.assert_close(loss.detach().float().cpu(), want["sft"]["loss"], atol=2e-5, rtol=1e-4)
+    torch.testing.assert_close(lm.transformer.ln_f.weight.grad, want["sft"]["g_lnf"], atol=1e-5, rtol=2e-3)
+    torch.testing.assert_close(lm.transformer.wte.weight.grad, want["sft"]["g_wte"], atol=1e-5, rtol=2e-3)
