@@ -109,6 +109,17 @@ ROLLOUT = HEADER + textwrap.dedent("""
     torch.save([tuple(t.detach().float().cpu() if t.is_floating_point() else t.cpu() for t in
                       (e.query_tensor, e.response_tensor, e.logprobs, e.values, e.rewards)) for e in trainer.store.history],
                os.path.join(work, "rollouts_ref.pt"))
+    # evaluation: greedy generations on fixed prompts, reward + metric means; then the same with a `gen_kwargs` list (sweep)
+    trainer.metric_fn = lambda samples, prompts, outputs, **kw: dict(out_len=[float(len(o)) for o in outputs],
+                                                                     n_e=[float(s.count("e")) for s in samples])
+    trainer.add_eval_pipeline(PromptPipeline({prompts!r}[:4], 32, trainer.tokenizer))
+    trainer.eval_dataloader = trainer.eval_pipeline.create_loader(2)
+    ev = trainer.evaluate()
+    trainer.generate_sweep_kwarg = ("max_new_tokens", [3, 6])
+    ev2 = trainer.evaluate()
+    trainer.generate_sweep_kwarg = None
+    keep = lambda d: {{k: float(v) for k, v in d.items() if k.startswith(("reward/", "metrics/"))}}
+    torch.save(dict(plain=keep(ev), sweep=keep(ev2)), os.path.join(work, "eval_ref.pt"))
     batch = next(iter(trainer.store.create_loader(4, shuffle=False)))
     trainer.model.eval()  # (HF's GPT-2 config carries dropout 0.1, which the reference leaves on while training: not comparable)
     loss, stats = trainer.loss(batch)
@@ -424,3 +435,35 @@ def test_ilql_and_sft_trainer_losses_and_gradients_match_the_reference(stage1):
     torch.testing.assert_close(loss.detach().float().cpu(), want["sft"]["loss"], atol=2e-5, rtol=1e-4)
     torch.testing.assert_close(lm.transformer.ln_f.weight.grad, want["sft"]["g_lnf"], atol=1e-5, rtol=2e-3)
     torch.testing.assert_close(lm.transformer.wte.weight.grad, want["sft"]["g_wte"], atol=1e-5, rtol=2e-3)
+
+
+def test_evaluate_statistics_match_the_reference(stage1):
+    """``evaluate()``: greedy generations on fixed prompts → identical ``reward/mean`` and ``metrics/*`` means, with and without a
+    generation-kwarg sweep (``reward/mean@max_new_tokens=…`` keys)."""
+    from trlx_b200.data.default_configs import default_ppo_config
+    from trlx_b200.pipeline.offline_pipeline import PromptPipeline
+    from trlx_b200.utils.loading import get_trainer
+
+    work, fmt, ids, ref = stage1
+    ckpt = _our_ckpt(work)
+    if not os.path.exists(os.path.join(work, "eval_ref.pt")):
+        _run(ROLLOUT.format(prompts=PROMPTS, **fmt), work)
+    want = torch.load(os.path.join(work, "eval_ref.pt"), weights_only=False)
+    cfg = default_ppo_config().evolve(
+        model=dict(model_path=ckpt, num_layers_unfrozen=2), tokenizer=dict(tokenizer_path=ref["tok_dir"]),
+        train=dict(tracker=None, seq_length=40, batch_size=4, checkpoint_dir=os.path.join(work, "ckpt_ours3")),
+        method=dict(num_rollouts=8, chunk_size=4, gen_kwargs=dict(max_new_tokens=8, do_sample=False, top_k=0, top_p=1.0)))
+    trainer = get_trainer(cfg.train.trainer)(
+        config=cfg, reward_fn=lambda samples, **kw: [float(len(s)) / 10 for s in samples],
+        metric_fn=lambda samples, prompts, outputs, **kw: dict(out_len=[float(len(o)) for o in outputs],
+                                                                n_e=[float(s.count("e")) for s in samples]), stop_sequences=[])
+    trainer.add_eval_pipeline(PromptPipeline(PROMPTS[:4], 32, trainer.tokenizer))
+    trainer.eval_dataloader = trainer.eval_pipeline.create_loader(2)
+    keep = lambda d: {k: float(v) for k, v in d.items() if k.startswith(("reward/", "metrics/"))}  # noqa: E731
+    plain = keep(trainer.evaluate())
+    trainer.generate_sweep_kwarg = ("max_new_tokens", [3, 6])
+    sweep = keep(trainer.evaluate())
+    assert set(plain) == set(want["plain"]) and set(sweep) == set(want["sweep"]), (set(plain), set(want["plain"]), set(sweep), set(want["sweep"]))
+    for got, exp in ((plain, want["plain"]), (sweep, want["sweep"])):
+        for k, v in exp.items():
+            assert abs(got[k] - v) < 1e-6 * max(1.0, abs(v)), (k, got[k], v)

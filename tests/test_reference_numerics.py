@@ -42,6 +42,13 @@ PRODUCER = textwrap.dedent("""
     out["whiten_noshift"] = whiten(inp["values"], shift_mean=False)
     rm = RunningMoments()
     out["moments"] = [tuple(float(x) for x in rm.update(chunk)) + (float(rm.mean), float(rm.std)) for chunk in inp["chunks"]]
+    from trlx.models.modeling_ppo import AdaptiveKLController, FixedKLController
+    a, f = AdaptiveKLController(0.05, 6.0, 1000), FixedKLController(0.2)
+    trace = []
+    for kl, n in ((8.0, 128), (1.0, 64), (40.0, 256), (-3.0, 32), (6.0, 128)):
+        a.update(kl, n); f.update(kl, n)
+        trace.append((float(a.value), float(f.value)))
+    out["kl_ctl"] = trace
     torch.save(out, {outp!r})
 """)
 
@@ -128,3 +135,13 @@ def test_statistics_helpers_match_the_reference(reference_outputs):
         got = tuple(float(x) for x in rm.update(chunk)) + (float(rm.mean), float(rm.std))
         for a, b in zip(got, want):
             assert abs(a - b) <= 1e-5 * max(1.0, abs(b)), (got, want)
+
+
+def test_kl_controllers_match_the_reference(reference_outputs):
+    from trlx_b200.models.modeling_ppo import AdaptiveKLController, FixedKLController
+
+    a, f = AdaptiveKLController(0.05, 6.0, 1000), FixedKLController(0.2)
+    for (kl, n), (want_a, want_f) in zip(((8.0, 128), (1.0, 64), (40.0, 256), (-3.0, 32), (6.0, 128)), reference_outputs["kl_ctl"]):
+        a.update(kl, n)
+        f.update(kl, n)
+        assert abs(float(a.value) - want_a) < 1e-9 and abs(float(f.value) - want_f) < 1e-12
