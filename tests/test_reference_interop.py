@@ -129,6 +129,13 @@ ROLLOUT = HEADER + textwrap.dedent("""
                     loss=loss.detach(), stats={{k: float(v) for k, v in stats.items()}},
                     g_vhead=inner.v_head[2].weight.grad.clone(), g_lnf=inner.base_model.transformer.ln_f.weight.grad.clone()),
                os.path.join(work, "ppo_loss_ref.pt"))
+    # one optimizer + scheduler step with the recipe's AdamW / cosine schedule
+    before = inner.v_head[2].weight.detach().clone()
+    trainer.opt.step(); trainer.scheduler.step()
+    extra = torch.load(os.path.join(work, "ppo_loss_ref.pt"), weights_only=False)
+    extra.update(w_vhead=inner.v_head[2].weight.detach().clone(), w_lnf=inner.base_model.transformer.ln_f.weight.detach().clone(),
+                 moved=float((inner.v_head[2].weight.detach() - before).abs().max()), lr=float(trainer.scheduler.get_last_lr()[0]))
+    torch.save(extra, os.path.join(work, "ppo_loss_ref.pt"))
 """)
 
 OFFLINE = HEADER + textwrap.dedent("""
@@ -381,6 +388,14 @@ def test_ppo_trainer_loss_and_gradients_match_the_reference(stage1):
     _stats_close({k: float(v) for k, v in stats.items()}, want["stats"])
     torch.testing.assert_close(trainer.model.v_head[2].weight.grad, want["g_vhead"], atol=1e-5, rtol=1e-3)
     torch.testing.assert_close(trainer.model.base_model.transformer.ln_f.weight.grad, want["g_lnf"], atol=1e-5, rtol=1e-3)
+    # the optimizer step of the default recipe (AdamW 3e-5, betas (0.9, 0.95), weight decay 1e-6, cosine schedule) moves the weights
+    # exactly as the reference's does
+    trainer.opt.step()
+    trainer.scheduler.step()
+    assert want["moved"] > 1e-6
+    torch.testing.assert_close(trainer.model.v_head[2].weight.detach(), want["w_vhead"], atol=1e-7, rtol=1e-5)
+    torch.testing.assert_close(trainer.model.base_model.transformer.ln_f.weight.detach(), want["w_lnf"], atol=1e-7, rtol=1e-5)
+    assert abs(float(trainer.scheduler.get_last_lr()[0]) - want["lr"]) < 1e-12
 
 
 def test_ilql_and_sft_trainer_losses_and_gradients_match_the_reference(stage1):
