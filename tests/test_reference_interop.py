@@ -183,6 +183,44 @@ OFFLINE = HEADER + textwrap.dedent("""
     torch.save(out, os.path.join(work, "offline_ref.pt"))
 """)
 
+T5STAGE = HEADER + textwrap.dedent("""
+    from trlx.models.modeling_ppo import AutoModelForSeq2SeqLMWithValueHead
+    from trlx.models.modeling_ilql import AutoModelForSeq2SeqLMWithILQLHeads
+    work = {work!r}
+    d = os.path.join(work, "t5_hf")
+    os.makedirs(d, exist_ok=True)
+    # untied embeddings (flan-t5 style, what the reference's T5 examples use).  With TIED embeddings the reference's ILQL wrapper
+    # applies `lm_head` to the raw decoder state (`modeling_ilql.py:570-572`), skipping T5's d_model**-0.5 rescale that HF — and this
+    # framework — apply: a documented deviation (DESIGN §2), not comparable.
+    cfg = transformers.T5Config(vocab_size=128, d_model=32, d_kv=8, d_ff=64, num_layers=2, num_decoder_layers=2, num_heads=4,
+                                decoder_start_token_id=0, pad_token_id=0, eos_token_id=1, tie_word_embeddings=False)
+    cfg.architectures = ["T5ForConditionalGeneration"]
+    torch.manual_seed(0)
+    hf = transformers.T5ForConditionalGeneration(cfg)
+    cfg.save_pretrained(d)
+    torch.save(hf.state_dict(), os.path.join(d, "pytorch_model.bin"))
+    g = torch.Generator().manual_seed(4)
+    ids = torch.randint(2, 100, (3, 7), generator=g); mask = torch.ones_like(ids); mask[1, 5:] = 0
+    dec = torch.randint(2, 100, (3, 5), generator=g); dec[:, 0] = 0
+    torch.manual_seed(1)
+    model = AutoModelForSeq2SeqLMWithValueHead.from_pretrained(d).eval()
+    with torch.no_grad():
+        for p in model.v_head.parameters():
+            p.copy_(torch.randn_like(p) * 0.1)
+        out = model(input_ids=ids, attention_mask=mask, decoder_input_ids=dec, return_dict=True)
+    model.save_pretrained(os.path.join(work, "t5_ref_ckpt"))
+    torch.manual_seed(2)
+    il = AutoModelForSeq2SeqLMWithILQLHeads.from_pretrained(d, two_qs=True, alpha=0.3).eval()
+    with torch.no_grad():
+        for p in il.ilql_heads.parameters():
+            p.copy_(torch.randn_like(p) * 0.05)
+        s_ix = torch.arange(0, 5).repeat(3, 1); a_ix = s_ix[:, :-1]
+        lg, qs, tqs, vs, _, _ = il(input_ids=ids, attention_mask=mask, decoder_input_ids=dec, states_ixs=s_ix, actions_ixs=a_ix)
+    il.save_pretrained(os.path.join(work, "t5_ref_ilql_ckpt"))
+    torch.save(dict(ids=ids, mask=mask, dec=dec, logits=out.logits, value=out.value, il=dict(logits=lg, qs=qs, tqs=tqs, vs=vs)),
+               os.path.join(work, "t5_ref.pt"))
+""")
+
 SAMPLES = [("the movie was", " really quite good"), ("i thought", " this plot felt very long and boring"), ("film", " great"),
            ("after watching the director", " acting scenes")]
 
@@ -482,3 +520,28 @@ def test_evaluate_statistics_match_the_reference(stage1):
     for got, exp in ((plain, want["plain"]), (sweep, want["sweep"])):
         for k, v in exp.items():
             assert abs(got[k] - v) < 1e-6 * max(1.0, abs(v)), (k, got[k], v)
+
+
+def test_seq2seq_value_head_and_ilql_checkpoints_from_the_reference_load_here(stage1):
+    """T5: value-head and ILQL-heads wrappers saved by the reference load here with the same logits / values / Q values.  (The
+    reference's seq2seq *hydra* branch is not compared: under this image's transformers its frozen branch no longer reproduces the
+    model it was copied from.)"""
+    from trlx_b200.models.modeling_ilql import AutoModelForSeq2SeqLMWithILQLHeads
+    from trlx_b200.models.modeling_ppo import AutoModelForSeq2SeqLMWithValueHead
+
+    work, fmt, _, _ = stage1
+    _run(T5STAGE.format(**fmt), work)
+    ref = torch.load(os.path.join(work, "t5_ref.pt"), weights_only=False)
+    ids, mask, dec = ref["ids"], ref["mask"], ref["dec"]
+    model = AutoModelForSeq2SeqLMWithValueHead.from_pretrained(os.path.join(work, "t5_ref_ckpt")).eval()
+    with torch.no_grad():
+        out = model(input_ids=ids, attention_mask=mask, decoder_input_ids=dec, return_dict=True)
+    torch.testing.assert_close(out.logits, ref["logits"], atol=2e-4, rtol=1e-4)
+    torch.testing.assert_close(out.value, ref["value"], atol=2e-4, rtol=1e-4)
+    il = AutoModelForSeq2SeqLMWithILQLHeads.from_pretrained(os.path.join(work, "t5_ref_ilql_ckpt"), two_qs=True, alpha=0.3).eval()
+    s_ix = torch.arange(0, 5).repeat(3, 1)
+    with torch.no_grad():
+        lg, qs, tqs, vs, _, _ = il(input_ids=ids, attention_mask=mask, decoder_input_ids=dec, states_ixs=s_ix, actions_ixs=s_ix[:, :-1])
+    torch.testing.assert_close(lg, ref["il"]["logits"], atol=2e-4, rtol=1e-4)
+    for got, exp in zip(list(qs) + list(tqs) + [vs], list(ref["il"]["qs"]) + list(ref["il"]["tqs"]) + [ref["il"]["vs"]]):
+        torch.testing.assert_close(got, exp, atol=2e-4, rtol=1e-4)

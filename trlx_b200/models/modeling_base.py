@@ -110,6 +110,10 @@ def import_base_state_dict(model: nn.Module, hf_sd: Dict[str, torch.Tensor], str
         missing.remove("lm_head.weight")
     buffers = {k for k, _ in lm.named_buffers()}
     missing = [k for k in missing if k not in buffers]
+    # tensors that alias a loaded one (T5's encoder / decoder `embed_tokens` are the `shared` embedding; newer HF checkpoints
+    # store such duplicates once) receive their values through that alias
+    loaded_storage = {target[k].data_ptr() for k in remap if k in target and target[k].numel()}
+    missing = [k for k in missing if not (target[k].numel() and target[k].data_ptr() in loaded_storage)]
     if missing:
         msg = (f"{len(missing)} of {len(target)} model tensors are NOT in the checkpoint and keep their initial values: "
                f"{missing[:8]}{'…' if len(missing) > 8 else ''}")
