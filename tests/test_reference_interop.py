@@ -69,6 +69,12 @@ STAGE1 = HEADER + textwrap.dedent("""
     with torch.no_grad():
         il_logits, qs, tqs, vs, _ = ilql(input_ids=ids, attention_mask=mask, position_ids=pos, states_ixs=s_ix, actions_ixs=a_ix)
     ilql.save_pretrained(os.path.join(work, "ref_ilql_ckpt"))
+    # advantage-shifted decoding, made deterministic by top_k = 1 (argmax of log pi + beta (min Q - V)); beta = 0 -> plain greedy
+    gen = {{}}
+    for beta in (0.0, 1.0, 4.0):
+        with torch.no_grad():
+            gen[beta] = ilql.generate(input_ids=ids[:, :6], attention_mask=mask[:, :6], beta=beta, top_k=1, temperature=1.0,
+                                      max_new_tokens=6, pad_token_id=1023, eos_token_id=1023)
     # PPO store collation
     from trlx.data.ppo_types import PPORLElement
     from trlx.pipeline.ppo_pipeline import ppo_collate_fn
@@ -79,7 +85,7 @@ STAGE1 = HEADER + textwrap.dedent("""
     collated = {{side: [getattr(ppo_collate_fn(side, 0, elems), f) for f in
                         ("query_tensors", "response_tensors", "logprobs", "values", "rewards")] for side in ("left", "right")}}
     torch.save(dict(logits=out.logits, value=out.value, hydra=hydra, toks=toks, store=cols, model_dir=model_dir, tok_dir=tok_dir,
-                    ilql=dict(logits=il_logits, qs=qs, tqs=tqs, vs=vs), elems=[tuple(e.__dict__.values()) for e in elems],
+                    ilql=dict(logits=il_logits, qs=qs, tqs=tqs, vs=vs, gen=gen), elems=[tuple(e.__dict__.values()) for e in elems],
                     collated=collated), os.path.join(work, "stage1.pt"))
 """)
 
@@ -337,6 +343,12 @@ def test_ilql_heads_checkpoint_and_ppo_collation_match_the_reference(stage1):
     assert (logits - want["logits"])[mask.bool()].abs().max() < 2e-4
     for got, exp in zip(list(qs) + list(tqs) + [vs], list(want["qs"]) + list(want["tqs"]) + [want["vs"]]):
         torch.testing.assert_close(got, exp, atol=2e-4, rtol=1e-4)
+    for beta, exp in want["gen"].items():
+        with torch.no_grad():
+            got = model.generate(input_ids=ids[:, :6], attention_mask=mask[:, :6], beta=beta, top_k=1, temperature=1.0,
+                                 max_new_tokens=6, pad_token_id=1023, eos_token_id=1023)
+        assert got.tolist() == exp.tolist(), (beta, got.tolist(), exp.tolist())
+    assert want["gen"][0.0].tolist() != want["gen"][4.0].tolist()  # the Q / V shift really changes what is decoded
     elems = [PPORLElement(*fields) for fields in ref["elems"]]
     for side in ("left", "right"):
         batch = ppo_collate_fn(side, 0, elems)
