@@ -189,6 +189,56 @@ OFFLINE = HEADER + textwrap.dedent("""
     torch.save(out, os.path.join(work, "offline_ref.pt"))
 """)
 
+LEARN = HEADER + textwrap.dedent("""
+    from trlx.data.default_configs import default_ppo_config, default_ilql_config, default_sft_config
+    work = {work!r}
+    st = torch.load(os.path.join(work, "stage1.pt"), weights_only=False)
+    import accelerate
+    logged = {{}}
+    def capture(kind):
+        def log(self, stats, step=None, **kw):
+            logged.setdefault(kind, set()).update(k for k in stats if not k.startswith("samples"))
+        return log
+    def tree(root):
+        out = []
+        for d, _, fs in os.walk(root):
+            out += [os.path.relpath(os.path.join(d, f), root) for f in fs]
+        return sorted(out)
+    trees = {{}}
+    prompts = {prompts!r}
+    common = dict(tracker=None, total_steps=2, epochs=2, checkpoint_interval=1, eval_interval=1, save_best=True)
+    # PPO
+    cfg = default_ppo_config()
+    cfg.model.model_path, cfg.model.num_layers_unfrozen = os.path.join(work, "our_ckpt"), 2
+    cfg.tokenizer.tokenizer_path = st["tok_dir"]
+    for k, v in dict(common, seq_length=40, batch_size=4, checkpoint_dir=os.path.join(work, "learn_ref_ppo")).items():
+        setattr(cfg.train, k, v)
+    cfg.method.num_rollouts, cfg.method.chunk_size, cfg.method.ppo_epochs = 4, 4, 1
+    cfg.method.gen_kwargs = dict(max_new_tokens=6, do_sample=False, top_k=0, top_p=1.0)
+    accelerate.Accelerator.log = capture("ppo")
+    trlx.train(reward_fn=lambda samples, **kw: [float(len(s)) / 10 for s in samples], prompts=prompts, eval_prompts=prompts[:2], config=cfg)
+    trees["ppo"] = tree(cfg.train.checkpoint_dir)
+    # ILQL
+    cfg = default_ilql_config()
+    cfg.model.model_path, cfg.tokenizer.tokenizer_path = os.path.join(work, "our_ilql_ckpt"), st["tok_dir"]
+    for k, v in dict(common, seq_length=32, batch_size=4, checkpoint_dir=os.path.join(work, "learn_ref_ilql")).items():
+        setattr(cfg.train, k, v)
+    cfg.method.gen_kwargs = dict(max_new_tokens=4, top_k=1, beta=1, temperature=1.0)
+    accelerate.Accelerator.log = capture("ilql")
+    trlx.train(samples={samples!r}, rewards=[1.0, -1.0, 0.5, 2.0], eval_prompts=prompts[:2], config=cfg)
+    trees["ilql"] = tree(cfg.train.checkpoint_dir)
+    # SFT
+    cfg = default_sft_config()
+    cfg.model.model_path, cfg.tokenizer.tokenizer_path = st["model_dir"], st["tok_dir"]
+    for k, v in dict(common, seq_length=32, batch_size=4, checkpoint_dir=os.path.join(work, "learn_ref_sft")).items():
+        setattr(cfg.train, k, v)
+    cfg.method.gen_kwargs = dict(max_new_tokens=4, do_sample=False)
+    accelerate.Accelerator.log = capture("sft")
+    trlx.train(samples={samples!r}, eval_prompts=prompts[:2], config=cfg)
+    trees["sft"] = tree(cfg.train.checkpoint_dir)
+    torch.save(dict(logged={{k: sorted(v) for k, v in logged.items()}}, trees=trees), os.path.join(work, "learn_ref.pt"))
+""")
+
 T5STAGE = HEADER + textwrap.dedent("""
     from trlx.models.modeling_ppo import AutoModelForSeq2SeqLMWithValueHead
     from trlx.models.modeling_ilql import AutoModelForSeq2SeqLMWithILQLHeads
@@ -557,3 +607,68 @@ def test_seq2seq_value_head_and_ilql_checkpoints_from_the_reference_load_here(st
     torch.testing.assert_close(lg, ref["il"]["logits"], atol=2e-4, rtol=1e-4)
     for got, exp in zip(list(qs) + list(tqs) + [vs], list(ref["il"]["qs"]) + list(ref["il"]["tqs"]) + [ref["il"]["vs"]]):
         torch.testing.assert_close(got, exp, atol=2e-4, rtol=1e-4)
+
+
+def test_learn_logs_the_same_statistic_keys_and_writes_the_same_checkpoint_tree(stage1, monkeypatch):
+    """Two optimizer steps of ``trlx.train`` per method in both frameworks: every statistic key the reference hands to its tracker
+    is logged here too (dashboards keep working), and the checkpoint directory has the same sub-directories (``checkpoint_N``,
+    ``best_checkpoint``) with an ``hf_model`` folder holding ``config.json`` + weights."""
+    import trlx_b200 as trlx
+    from trlx_b200.data.default_configs import default_ilql_config, default_ppo_config, default_sft_config
+    from trlx_b200.models.modeling_ilql import AutoModelForCausalLMWithILQLHeads
+    from trlx_b200.parallel.runtime import Runtime
+
+    work, fmt, ids, ref = stage1
+    _our_ckpt(work)
+    path = os.path.join(work, "our_ilql_ckpt")
+    if not os.path.exists(os.path.join(path, "pytorch_model.bin")):
+        AutoModelForCausalLMWithILQLHeads.from_pretrained(os.path.join(work, "ref_ilql_ckpt"), two_qs=True, alpha=0.5).save_pretrained(path)
+    _run(LEARN.format(prompts=PROMPTS, samples=SAMPLES, **fmt), work)
+    want = torch.load(os.path.join(work, "learn_ref.pt"), weights_only=False)
+
+    logged = {}
+    kind = {"name": None}
+    monkeypatch.setattr(Runtime, "log", lambda self, stats, step=None: logged.setdefault(kind["name"], set()).update(stats))
+    common = dict(tracker=None, total_steps=2, epochs=2, checkpoint_interval=1, eval_interval=1, save_best=True)
+
+    def tree(root):
+        out = []
+        for d, _, fs in os.walk(root):
+            out += [os.path.relpath(os.path.join(d, f), root) for f in fs]
+        return sorted(out)
+
+    trees = {}
+    kind["name"] = "ppo"
+    cfg = default_ppo_config().evolve(
+        model=dict(model_path=os.path.join(work, "our_ckpt"), num_layers_unfrozen=2), tokenizer=dict(tokenizer_path=ref["tok_dir"]),
+        train=dict(common, seq_length=40, batch_size=4, checkpoint_dir=os.path.join(work, "learn_our_ppo")),
+        method=dict(num_rollouts=4, chunk_size=4, ppo_epochs=1, gen_kwargs=dict(max_new_tokens=6, do_sample=False, top_k=0, top_p=1.0)))
+    trlx.train(reward_fn=lambda samples, **kw: [float(len(s)) / 10 for s in samples], prompts=PROMPTS, eval_prompts=PROMPTS[:2], config=cfg)
+    trees["ppo"] = tree(cfg.train.checkpoint_dir)
+    kind["name"] = "ilql"
+    cfg = default_ilql_config().evolve(
+        model=dict(model_path=path), tokenizer=dict(tokenizer_path=ref["tok_dir"]),
+        train=dict(common, seq_length=32, batch_size=4, checkpoint_dir=os.path.join(work, "learn_our_ilql")),
+        method=dict(gen_kwargs=dict(max_new_tokens=4, top_k=1, beta=1, temperature=1.0)))
+    trlx.train(samples=SAMPLES, rewards=[1.0, -1.0, 0.5, 2.0], eval_prompts=PROMPTS[:2], config=cfg)
+    trees["ilql"] = tree(cfg.train.checkpoint_dir)
+    kind["name"] = "sft"
+    cfg = default_sft_config().evolve(
+        model=dict(model_path=ref["model_dir"]), tokenizer=dict(tokenizer_path=ref["tok_dir"]),
+        train=dict(common, seq_length=32, batch_size=4, checkpoint_dir=os.path.join(work, "learn_our_sft")),
+        method=dict(gen_kwargs=dict(max_new_tokens=4, do_sample=False)))
+    trlx.train(samples=SAMPLES, eval_prompts=PROMPTS[:2], config=cfg)
+    trees["sft"] = tree(cfg.train.checkpoint_dir)
+
+    for k in ("ppo", "ilql", "sft"):
+        missing = set(want["logged"][k]) - logged[k]
+        assert not missing, (k, sorted(missing))
+        ref_dirs = {p.split(os.sep)[0] for p in want["trees"][k]}
+        our_dirs = {p.split(os.sep)[0] for p in trees[k]}
+        assert ref_dirs <= our_dirs, (k, ref_dirs, our_dirs)
+        for d in ref_dirs:
+            ours_hf = {os.path.basename(p) for p in trees[k] if p.startswith(os.path.join(d, "hf_model") + os.sep)}
+            assert "config.json" in ours_hf and ({"pytorch_model.bin", "model.safetensors"} & ours_hf), (k, d, ours_hf)
+            ref_hf = {os.path.basename(p) for p in want["trees"][k] if p.startswith(os.path.join(d, "hf_model") + os.sep)}
+            # (weights may be .bin or .safetensors; `generation_config.json` is HF's own addition for its model classes)
+            assert ref_hf - {"pytorch_model.bin", "model.safetensors", "generation_config.json"} <= ours_hf, (k, d, ref_hf, ours_hf)
