@@ -89,7 +89,7 @@ STAGE1 = HEADER + textwrap.dedent("""
                     collated=collated), os.path.join(work, "stage1.pt"))
 """)
 
-ROLLOUT = HEADER + textwrap.dedent("""
+ROLLOUT = textwrap.dedent("""
     from trlx.data.default_configs import default_ppo_config
     from trlx.pipeline.offline_pipeline import PromptPipeline
     from trlx.trainer.accelerate_ppo_trainer import AcceleratePPOTrainer
@@ -144,7 +144,7 @@ ROLLOUT = HEADER + textwrap.dedent("""
     torch.save(extra, os.path.join(work, "ppo_loss_ref.pt"))
 """)
 
-OFFLINE = HEADER + textwrap.dedent("""
+OFFLINE = textwrap.dedent("""
     from trlx.data.default_configs import default_ilql_config, default_sft_config
     from trlx.trainer.accelerate_ilql_trainer import AccelerateILQLTrainer
     from trlx.trainer.accelerate_sft_trainer import AccelerateSFTTrainer
@@ -189,7 +189,7 @@ OFFLINE = HEADER + textwrap.dedent("""
     torch.save(out, os.path.join(work, "offline_ref.pt"))
 """)
 
-LEARN = HEADER + textwrap.dedent("""
+LEARN = textwrap.dedent("""
     from trlx.data.default_configs import default_ppo_config, default_ilql_config, default_sft_config
     work = {work!r}
     st = torch.load(os.path.join(work, "stage1.pt"), weights_only=False)
@@ -239,7 +239,7 @@ LEARN = HEADER + textwrap.dedent("""
     torch.save(dict(logged={{k: sorted(v) for k, v in logged.items()}}, trees=trees), os.path.join(work, "learn_ref.pt"))
 """)
 
-T5STAGE = HEADER + textwrap.dedent("""
+T5STAGE = textwrap.dedent("""
     from trlx.models.modeling_ppo import AutoModelForSeq2SeqLMWithValueHead
     from trlx.models.modeling_ilql import AutoModelForSeq2SeqLMWithILQLHeads
     work = {work!r}
@@ -283,7 +283,7 @@ SAMPLES = [("the movie was", " really quite good"), ("i thought", " this plot fe
 PROMPTS = ["the movie was", "i thought this film", "quite", "after watching the director", "story plot acting felt very long",
            "an", "really good scenes and", "boring but"]
 
-STAGE2 = HEADER + textwrap.dedent("""
+STAGE2 = textwrap.dedent("""
     from trlx.models.modeling_ppo import AutoModelForCausalLMWithHydraValueHead
     work = {work!r}
     model = AutoModelForCausalLMWithHydraValueHead.from_pretrained(os.path.join(work, "our_ckpt"), num_layers_unfrozen=2).eval()
@@ -319,6 +319,23 @@ def stage1(tmp_path_factory):
     return work, fmt, ids, torch.load(os.path.join(work, "stage1.pt"), weights_only=False)
 
 
+@pytest.fixture(scope="module")
+def stage2(stage1):
+    """Everything else the reference has to compute, in ONE more interpreter (its start-up dominates): reload of this framework's
+    re-saved checkpoints, rollouts + evaluation + loss + optimizer step, offline trainers, two-step ``learn()`` runs, T5 wrappers."""
+    from trlx_b200.models.modeling_ilql import AutoModelForCausalLMWithILQLHeads
+
+    work, fmt, ids, ref = stage1
+    _our_ckpt(work)
+    path = os.path.join(work, "our_ilql_ckpt")
+    if not os.path.exists(os.path.join(path, "pytorch_model.bin")):
+        AutoModelForCausalLMWithILQLHeads.from_pretrained(os.path.join(work, "ref_ilql_ckpt"), two_qs=True, alpha=0.5).save_pretrained(path)
+    full = dict(fmt, prompts=PROMPTS, samples=SAMPLES, rewards=[1.0, -1.0, 0.5, 2.0])
+    code = HEADER.format(**full) + "".join(body.format(**full) for body in (STAGE2, ROLLOUT, OFFLINE, T5STAGE, LEARN))
+    _run(code, work)
+    return stage1
+
+
 def _our_ckpt(work):
     """``ref_ckpt`` (written by the reference) re-saved by this framework (``pytorch_model.bin`` layout)."""
     from trlx_b200.models.modeling_ppo import AutoModelForCausalLMWithHydraValueHead
@@ -340,19 +357,17 @@ def _forward(model, ids):
     return out.logits, out.value, hydra, mask.bool()
 
 
-def test_checkpoints_round_trip_between_the_reference_and_this_framework(stage1):
+def test_checkpoints_round_trip_between_the_reference_and_this_framework(stage2):
     from trlx_b200.models.modeling_ppo import AutoModelForCausalLMWithHydraValueHead
 
-    work, fmt, ids, ref = stage1
+    work, fmt, ids, ref = stage2
     ours = AutoModelForCausalLMWithHydraValueHead.from_pretrained(os.path.join(work, "ref_ckpt"), num_layers_unfrozen=2).eval()
     logits, value, hydra, m = _forward(ours, ids)
     assert (logits - ref["logits"])[m].abs().max() < 2e-4
     assert (value - ref["value"])[m].abs().max() < 2e-4
     assert (hydra - ref["hydra"])[m].abs().max() < 2e-4
     assert (hydra - logits)[m].abs().max() > 1e-3  # the frozen branch really is a different set of weights
-    ours.save_pretrained(os.path.join(work, "our_ckpt"))
-    assert os.path.exists(os.path.join(work, "our_ckpt", "pytorch_model.bin"))
-    _run(STAGE2.format(**fmt), work)
+    assert os.path.exists(os.path.join(work, "our_ckpt", "pytorch_model.bin"))  # written by this framework (fixture), reloaded there
     back = torch.load(os.path.join(work, "stage2.pt"), weights_only=False)
     for k in ("logits", "value", "hydra"):
         assert (back[k] - ref[k])[m].abs().max() < 2e-4, k
@@ -406,7 +421,7 @@ def test_ilql_heads_checkpoint_and_ppo_collation_match_the_reference(stage1):
             torch.testing.assert_close(getattr(batch, f), exp, msg=lambda m: f"{side} {f}: {m}")
 
 
-def test_ppo_experience_matches_the_reference_rollout_arithmetic(stage1):
+def test_ppo_experience_matches_the_reference_rollout_arithmetic(stage2):
     """Same checkpoint (distinct frozen branch and value head), same prompts, greedy decoding: every stored rollout — query,
     response, per-token log-probs, values and KL-penalised rewards with the score on the last token — equals what the
     reference's own ``make_experience`` stores (matched by prompt; both frameworks shuffle their prompt loaders)."""
@@ -414,9 +429,8 @@ def test_ppo_experience_matches_the_reference_rollout_arithmetic(stage1):
     from trlx_b200.pipeline.offline_pipeline import PromptPipeline
     from trlx_b200.utils.loading import get_trainer
 
-    work, fmt, ids, ref = stage1
+    work, fmt, ids, ref = stage2
     ckpt = _our_ckpt(work)
-    _run(ROLLOUT.format(prompts=PROMPTS, **fmt), work)
     want = torch.load(os.path.join(work, "rollouts_ref.pt"), weights_only=False)
     cfg = default_ppo_config().evolve(
         model=dict(model_path=ckpt, num_layers_unfrozen=2),
@@ -463,16 +477,14 @@ def _stats_close(mine, want, tol=2e-4):
         assert abs(float(mine[k]) - v) <= tol * max(1.0, abs(v)), (k, float(mine[k]), v)
 
 
-def test_ppo_trainer_loss_and_gradients_match_the_reference(stage1):
+def test_ppo_trainer_loss_and_gradients_match_the_reference(stage2):
     """``trainer.loss(batch)`` on the reference's own collated batch: loss, all statistics, and gradients."""
     from trlx_b200.data.default_configs import default_ppo_config
     from trlx_b200.data.ppo_types import PPORLBatch
     from trlx_b200.utils.loading import get_trainer
 
-    work, fmt, ids, ref = stage1
+    work, fmt, ids, ref = stage2
     ckpt = _our_ckpt(work)
-    if not os.path.exists(os.path.join(work, "ppo_loss_ref.pt")):
-        _run(ROLLOUT.format(prompts=PROMPTS, **fmt), work)
     want = torch.load(os.path.join(work, "ppo_loss_ref.pt"), weights_only=False)
     cfg = default_ppo_config().evolve(
         model=dict(model_path=ckpt, num_layers_unfrozen=2), tokenizer=dict(tokenizer_path=ref["tok_dir"]),
@@ -498,18 +510,14 @@ def test_ppo_trainer_loss_and_gradients_match_the_reference(stage1):
     assert abs(float(trainer.scheduler.get_last_lr()[0]) - want["lr"]) < 1e-12
 
 
-def test_ilql_and_sft_trainer_losses_and_gradients_match_the_reference(stage1):
+def test_ilql_and_sft_trainer_losses_and_gradients_match_the_reference(stage2):
     from trlx_b200.data.default_configs import default_ilql_config, default_sft_config
     from trlx_b200.data.ilql_types import ILQLBatch
     from trlx_b200.models.modeling_ilql import AutoModelForCausalLMWithILQLHeads
     from trlx_b200.utils.loading import get_trainer
 
-    work, fmt, ids, ref = stage1
+    work, fmt, ids, ref = stage2
     path = os.path.join(work, "our_ilql_ckpt")
-    if not os.path.exists(os.path.join(path, "pytorch_model.bin")):
-        AutoModelForCausalLMWithILQLHeads.from_pretrained(os.path.join(work, "ref_ilql_ckpt"), two_qs=True, alpha=0.5).save_pretrained(path)
-    rewards = [1.0, -1.0, 0.5, 2.0]
-    _run(OFFLINE.format(samples=SAMPLES, **dict(fmt, rewards=rewards)), work)
     want = torch.load(os.path.join(work, "offline_ref.pt"), weights_only=False)
     # ---- ILQL: same stored experience, loss on the reference's batch
     cfg = default_ilql_config().evolve(
@@ -552,17 +560,15 @@ def test_ilql_and_sft_trainer_losses_and_gradients_match_the_reference(stage1):
     torch.testing.assert_close(lm.transformer.wte.weight.grad, want["sft"]["g_wte"], atol=1e-5, rtol=2e-3)
 
 
-def test_evaluate_statistics_match_the_reference(stage1):
+def test_evaluate_statistics_match_the_reference(stage2):
     """``evaluate()``: greedy generations on fixed prompts → identical ``reward/mean`` and ``metrics/*`` means, with and without a
     generation-kwarg sweep (``reward/mean@max_new_tokens=…`` keys)."""
     from trlx_b200.data.default_configs import default_ppo_config
     from trlx_b200.pipeline.offline_pipeline import PromptPipeline
     from trlx_b200.utils.loading import get_trainer
 
-    work, fmt, ids, ref = stage1
+    work, fmt, ids, ref = stage2
     ckpt = _our_ckpt(work)
-    if not os.path.exists(os.path.join(work, "eval_ref.pt")):
-        _run(ROLLOUT.format(prompts=PROMPTS, **fmt), work)
     want = torch.load(os.path.join(work, "eval_ref.pt"), weights_only=False)
     cfg = default_ppo_config().evolve(
         model=dict(model_path=ckpt, num_layers_unfrozen=2), tokenizer=dict(tokenizer_path=ref["tok_dir"]),
@@ -584,15 +590,14 @@ def test_evaluate_statistics_match_the_reference(stage1):
             assert abs(got[k] - v) < 1e-6 * max(1.0, abs(v)), (k, got[k], v)
 
 
-def test_seq2seq_value_head_and_ilql_checkpoints_from_the_reference_load_here(stage1):
+def test_seq2seq_value_head_and_ilql_checkpoints_from_the_reference_load_here(stage2):
     """T5: value-head and ILQL-heads wrappers saved by the reference load here with the same logits / values / Q values.  (The
     reference's seq2seq *hydra* branch is not compared: under this image's transformers its frozen branch no longer reproduces the
     model it was copied from.)"""
     from trlx_b200.models.modeling_ilql import AutoModelForSeq2SeqLMWithILQLHeads
     from trlx_b200.models.modeling_ppo import AutoModelForSeq2SeqLMWithValueHead
 
-    work, fmt, _, _ = stage1
-    _run(T5STAGE.format(**fmt), work)
+    work, fmt, _, _ = stage2
     ref = torch.load(os.path.join(work, "t5_ref.pt"), weights_only=False)
     ids, mask, dec = ref["ids"], ref["mask"], ref["dec"]
     model = AutoModelForSeq2SeqLMWithValueHead.from_pretrained(os.path.join(work, "t5_ref_ckpt")).eval()
@@ -609,7 +614,7 @@ def test_seq2seq_value_head_and_ilql_checkpoints_from_the_reference_load_here(st
         torch.testing.assert_close(got, exp, atol=2e-4, rtol=1e-4)
 
 
-def test_learn_logs_the_same_statistic_keys_and_writes_the_same_checkpoint_tree(stage1, monkeypatch):
+def test_learn_logs_the_same_statistic_keys_and_writes_the_same_checkpoint_tree(stage2, monkeypatch):
     """Two optimizer steps of ``trlx.train`` per method in both frameworks: every statistic key the reference hands to its tracker
     is logged here too (dashboards keep working), and the checkpoint directory has the same sub-directories (``checkpoint_N``,
     ``best_checkpoint``) with an ``hf_model`` folder holding ``config.json`` + weights."""
@@ -618,12 +623,8 @@ def test_learn_logs_the_same_statistic_keys_and_writes_the_same_checkpoint_tree(
     from trlx_b200.models.modeling_ilql import AutoModelForCausalLMWithILQLHeads
     from trlx_b200.parallel.runtime import Runtime
 
-    work, fmt, ids, ref = stage1
-    _our_ckpt(work)
+    work, fmt, ids, ref = stage2
     path = os.path.join(work, "our_ilql_ckpt")
-    if not os.path.exists(os.path.join(path, "pytorch_model.bin")):
-        AutoModelForCausalLMWithILQLHeads.from_pretrained(os.path.join(work, "ref_ilql_ckpt"), two_qs=True, alpha=0.5).save_pretrained(path)
-    _run(LEARN.format(prompts=PROMPTS, samples=SAMPLES, **fmt), work)
     want = torch.load(os.path.join(work, "learn_ref.pt"), weights_only=False)
 
     logged = {}
