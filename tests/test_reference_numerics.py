@@ -49,6 +49,16 @@ PRODUCER = textwrap.dedent("""
         a.update(kl, n); f.update(kl, n)
         trace.append((float(a.value), float(f.value)))
     out["kl_ctl"] = trace
+    from trlx.utils import significant, filter_non_scalars
+    from trlx.utils.modeling import flatten_dict, get_tensor_stats
+    from trlx.models.modeling_ilql import topk_mask, batched_index_select
+    out["significant"] = [significant(x) for x in (0, 1234.5678, 0.000123456, -98.7654, 3, 1e-12, 12345678.9)]
+    nested = dict(a=1.5, b=dict(c=2, d=dict(e=torch.tensor(3.0))), f="text", g=[1, 2])
+    out["flat"] = {{k: (float(v) if isinstance(v, (int, float, torch.Tensor)) else repr(v)) for k, v in flatten_dict(nested).items()}}
+    out["scalars"] = sorted(filter_non_scalars(dict(a=1, b=2.5, d=[1], e=torch.tensor(1.0), f=object())).keys())
+    out["topk"] = topk_mask(inp["logits"][0], 5)
+    out["bis"] = batched_index_select(inp["logits"], inp["labels"][:, :4] % inp["logits"].shape[1], 1)
+    out["tstats"] = {{k: float(v) for k, v in get_tensor_stats(inp["values"], inp["mask"], inp["mask"].sum()).items()}}
     torch.save(out, {outp!r})
 """)
 
@@ -145,3 +155,22 @@ def test_kl_controllers_match_the_reference(reference_outputs):
         a.update(kl, n)
         f.update(kl, n)
         assert abs(float(a.value) - want_a) < 1e-9 and abs(float(f.value) - want_f) < 1e-12
+
+
+def test_small_utilities_match_the_reference(reference_outputs):
+    from trlx_b200.models.modeling_ilql import batched_index_select, topk_mask
+    from trlx_b200.utils import filter_non_scalars, significant
+    from trlx_b200.utils.modeling import flatten_dict, get_tensor_stats
+
+    inp, ref = _inputs(), reference_outputs
+    assert [significant(x) for x in (0, 1234.5678, 0.000123456, -98.7654, 3, 1e-12, 12345678.9)] == ref["significant"]
+    nested = dict(a=1.5, b=dict(c=2, d=dict(e=torch.tensor(3.0))), f="text", g=[1, 2])
+    flat = {k: (float(v) if isinstance(v, (int, float, torch.Tensor)) else repr(v)) for k, v in flatten_dict(nested).items()}
+    assert flat == ref["flat"]
+    assert sorted(filter_non_scalars(dict(a=1, b=2.5, d=[1], e=torch.tensor(1.0), f=object())).keys()) == ref["scalars"]
+    torch.testing.assert_close(topk_mask(inp["logits"][0], 5), ref["topk"])
+    torch.testing.assert_close(batched_index_select(inp["logits"], inp["labels"][:, :4] % inp["logits"].shape[1], 1), ref["bis"])
+    mine = {k: float(v) for k, v in get_tensor_stats(inp["values"], inp["mask"], inp["mask"].sum()).items()}
+    assert set(mine) == set(ref["tstats"])
+    for k, v in ref["tstats"].items():
+        assert abs(mine[k] - v) < 1e-5, (k, mine[k], v)
