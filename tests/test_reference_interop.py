@@ -84,6 +84,15 @@ STAGE1 = HEADER + textwrap.dedent("""
              for q, r in ((3, 5), (6, 2), (4, 4))]
     collated = {{side: [getattr(ppo_collate_fn(side, 0, elems), f) for f in
                         ("query_tensors", "response_tensors", "logprobs", "values", "rewards")] for side in ("left", "right")}}
+    from trlx.pipeline.offline_pipeline import PromptPipeline, DialogStore
+    pp_items = {pp_prompts!r}
+    tok.pad_token, tok.padding_side, tok.truncation_side = tok.eos_token, "left", "right"   # what the trainers set up
+    pipe = PromptPipeline(pp_items, 5, tok)
+    pp_rows = [dict(pipe[i]) for i in range(len(pipe))]
+    pp_batch = dict(next(iter(pipe.create_loader(4, shuffle=False))))
+    ds = DialogStore([tokenize_dialogue(d, tok, L) for d, L in dialogues], tok)
+    ds_batch = dict(next(iter(ds.create_loader(4, shuffle=False))))
+    torch.save(dict(rows=pp_rows, batch=pp_batch, dialog=ds_batch), os.path.join(work, "pipelines_ref.pt"))
     torch.save(dict(logits=out.logits, value=out.value, hydra=hydra, toks=toks, store=cols, model_dir=model_dir, tok_dir=tok_dir,
                     ilql=dict(logits=il_logits, qs=qs, tqs=tqs, vs=vs, gen=gen), elems=[tuple(e.__dict__.values()) for e in elems],
                     collated=collated), os.path.join(work, "stage1.pt"))
@@ -300,6 +309,9 @@ DIALOGUES = [("hello there general", 24), (("question one", "answer one is long 
              (["a first prompt", "a reply", "a follow up", "the final reply of the dialogue"], 24),
              (("short", "this reply will be truncated because the budget is tiny"), 8)]
 REWARDS = [1.0, -0.5, 2.0, 0.25]
+PP_PROMPTS = [dict(prompt="the movie was really quite long and boring after", tag="x", score=0.0),
+              dict(prompt="i thought", tag="a", score=1.5), dict(prompt="film", tag="c", score=3.0),
+              dict(prompt="after watching the director scenes story plot", tag="b", score=-2.0)]
 
 
 def _run(code, work):
@@ -314,7 +326,7 @@ def stage1(tmp_path_factory):
     ids = torch.randint(5, 900, (3, 11), generator=torch.Generator().manual_seed(2))
     torch.save(ids, os.path.join(work, "ids.pt"))
     fmt = dict(root=ROOT, shims=os.path.join(ROOT, "baseline", "shims"), ref=REF, work=work, ids=os.path.join(work, "ids.pt"),
-               dialogues=DIALOGUES, rewards=REWARDS)
+               dialogues=DIALOGUES, rewards=REWARDS, pp_prompts=PP_PROMPTS)
     _run(STAGE1.format(**fmt), work)
     return work, fmt, ids, torch.load(os.path.join(work, "stage1.pt"), weights_only=False)
 
@@ -673,3 +685,35 @@ def test_learn_logs_the_same_statistic_keys_and_writes_the_same_checkpoint_tree(
             ref_hf = {os.path.basename(p) for p in want["trees"][k] if p.startswith(os.path.join(d, "hf_model") + os.sep)}
             # (weights may be .bin or .safetensors; `generation_config.json` is HF's own addition for its model classes)
             assert ref_hf - {"pytorch_model.bin", "model.safetensors", "generation_config.json"} <= ours_hf, (k, d, ref_hf, ours_hf)
+
+
+def test_prompt_pipeline_and_dialog_store_batches_match_the_reference(stage1):
+    """Prompt truncation to ``max_prompt_length``, metadata pass-through, left-padded collation; dialogue store collation with the
+    loss mask of the non-output tokens."""
+    import transformers
+
+    from trlx_b200.pipeline.offline_pipeline import DialogStore, PromptPipeline, tokenize_dialogue
+
+    work, fmt, ids, ref = stage1
+    want = torch.load(os.path.join(work, "pipelines_ref.pt"), weights_only=False)
+    tok = transformers.AutoTokenizer.from_pretrained(ref["tok_dir"])
+    tok.pad_token, tok.padding_side, tok.truncation_side = tok.eos_token, "left", "right"
+    pipe = PromptPipeline(PP_PROMPTS, 5, tok)
+    assert len(pipe) == len(want["rows"])
+    for i, exp in enumerate(want["rows"]):
+        got = dict(pipe[i])
+        assert set(got) == set(exp), (set(got), set(exp))
+        for k, v in exp.items():
+            assert list(got[k]) == list(v) if isinstance(v, (list, tuple)) else got[k] == v, (i, k, got[k], v)
+    batch = dict(next(iter(pipe.create_loader(4, shuffle=False))))
+    assert set(batch) == set(want["batch"])
+    for k, v in want["batch"].items():
+        if isinstance(v, torch.Tensor):
+            assert torch.equal(torch.as_tensor(batch[k]), v), k
+        else:
+            assert list(batch[k]) == list(v), k
+    ds = DialogStore([tokenize_dialogue(d, tok, L) for d, L in DIALOGUES], tok)
+    got = dict(next(iter(ds.create_loader(4, shuffle=False))))
+    assert set(got) == set(want["dialog"])
+    for k, v in want["dialog"].items():
+        assert torch.equal(torch.as_tensor(got[k]), v), k
