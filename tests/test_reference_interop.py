@@ -92,7 +92,17 @@ STAGE1 = HEADER + textwrap.dedent("""
     pp_batch = dict(next(iter(pipe.create_loader(4, shuffle=False))))
     ds = DialogStore([tokenize_dialogue(d, tok, L) for d, L in dialogues], tok)
     ds_batch = dict(next(iter(ds.create_loader(4, shuffle=False))))
-    torch.save(dict(rows=pp_rows, batch=pp_batch, dialog=ds_batch), os.path.join(work, "pipelines_ref.pt"))
+    # micro-batching of an optimizer batch (PPO dataclass batches and BatchEncoding dicts, uneven tail)
+    from trlx.pipeline import MiniBatchIterator
+    from trlx.pipeline.ppo_pipeline import PPORolloutStorage
+    store = PPORolloutStorage(0, "left")
+    store.clear_history()   # (the reference's store starts with a `None` placeholder that its trainer clears first)
+    store.push(elems)
+    ppo_mbs = [[[getattr(mb, f) for f in ("query_tensors", "response_tensors", "logprobs", "values", "rewards")] for mb in group]
+               for group in MiniBatchIterator(store.create_loader(3, shuffle=False), 2, 2)]
+    enc_mbs = [[dict(mb) for mb in group] for group in MiniBatchIterator(ds.create_loader(4, shuffle=False), 3, 2)]
+    torch.save(dict(rows=pp_rows, batch=pp_batch, dialog=ds_batch, ppo_mbs=ppo_mbs, enc_mbs=enc_mbs),
+               os.path.join(work, "pipelines_ref.pt"))
     torch.save(dict(logits=out.logits, value=out.value, hydra=hydra, toks=toks, store=cols, model_dir=model_dir, tok_dir=tok_dir,
                     ilql=dict(logits=il_logits, qs=qs, tqs=tqs, vs=vs, gen=gen), elems=[tuple(e.__dict__.values()) for e in elems],
                     collated=collated), os.path.join(work, "stage1.pt"))
@@ -717,3 +727,36 @@ def test_prompt_pipeline_and_dialog_store_batches_match_the_reference(stage1):
     assert set(got) == set(want["dialog"])
     for k, v in want["dialog"].items():
         assert torch.equal(torch.as_tensor(got[k]), v), k
+
+
+def test_minibatch_iterator_matches_the_reference(stage1):
+    from trlx_b200.data.ppo_types import PPORLElement
+    from trlx_b200.pipeline import MiniBatchIterator
+    from trlx_b200.pipeline.offline_pipeline import DialogStore, tokenize_dialogue
+    from trlx_b200.pipeline.ppo_pipeline import PPORolloutStorage
+    import transformers
+
+    work, fmt, ids, ref = stage1
+    want = torch.load(os.path.join(work, "pipelines_ref.pt"), weights_only=False)
+    store = PPORolloutStorage(0, "left")
+    store.clear_history()
+    store.push([PPORLElement(*fields) for fields in ref["elems"]])
+    got = [[[getattr(mb, f) for f in ("query_tensors", "response_tensors", "logprobs", "values", "rewards")] for mb in group]
+           for group in MiniBatchIterator(store.create_loader(3, shuffle=False), 2, 2)]
+    assert len(got) == len(want["ppo_mbs"])
+    for g, w in zip(got, want["ppo_mbs"]):
+        assert len(g) == len(w)
+        for mb_g, mb_w in zip(g, w):
+            for a, b in zip(mb_g, mb_w):
+                torch.testing.assert_close(torch.as_tensor(a).cpu(), b)
+    tok = transformers.AutoTokenizer.from_pretrained(ref["tok_dir"])
+    tok.pad_token, tok.padding_side, tok.truncation_side = tok.eos_token, "left", "right"
+    ds = DialogStore([tokenize_dialogue(d, tok, L) for d, L in DIALOGUES], tok)
+    got = [[dict(mb) for mb in group] for group in MiniBatchIterator(ds.create_loader(4, shuffle=False), 3, 2)]
+    assert len(got) == len(want["enc_mbs"])
+    for g, w in zip(got, want["enc_mbs"]):
+        assert len(g) == len(w)
+        for mb_g, mb_w in zip(g, w):
+            assert set(mb_g) == set(mb_w)
+            for k in mb_w:
+                assert torch.equal(torch.as_tensor(mb_g[k]), mb_w[k]), k
