@@ -59,8 +59,27 @@ PRODUCER = textwrap.dedent("""
     out["topk"] = topk_mask(inp["logits"][0], 5)
     out["bis"] = batched_index_select(inp["logits"], inp["labels"][:, :4] % inp["logits"].shape[1], 1)
     out["tstats"] = {{k: float(v) for k, v in get_tensor_stats(inp["values"], inp["mask"], inp["mask"].sum()).items()}}
+    from trlx.data.configs import TRLConfig
+    from trlx.data.default_configs import default_sft_config
+    cfgs = {{}}
+    for path in {yamls!r}:
+        cfgs[path] = TRLConfig.load_yaml(path).to_dict()
+    cfgs["default_ppo"], cfgs["default_ilql"], cfgs["default_sft"] = (default_ppo_config().to_dict(), default_ilql_config().to_dict(),
+                                                                     default_sft_config().to_dict())
+    cfgs["updated"] = TRLConfig.update(default_ppo_config().to_dict(), {{"train.seq_length": 77, "method.gamma": 0.5,
+                                                                        "optimizer.kwargs.lr": 1e-3}}).to_dict()
+    cfgs["evolved"] = default_ilql_config().evolve(train=dict(batch_size=3), method=dict(tau=0.9, gen_kwargs=dict(beta=2))).to_dict()
+    out["configs"] = cfgs
     torch.save(out, {outp!r})
 """)
+
+
+def _yamls():
+    """TRLConfig YAML files shipped with the reference checkout (when it is available next to the installed copy)."""
+    root = os.environ.get("TRLX_REFERENCE", "/root/reference")
+    cands = [os.path.join(root, "configs", "test_config.yml"),
+             os.path.join(root, "examples", "experiments", "grounded_program_synthesis", "configs", "trlx_ppo_config.yml")]
+    return [c for c in cands if os.path.exists(c)]
 
 
 def _inputs():
@@ -94,7 +113,7 @@ def reference_outputs(tmp_path_factory):
     d = tmp_path_factory.mktemp("refnum")
     inp, outp = str(d / "in.pt"), str(d / "out.pt")
     torch.save(_inputs(), inp)
-    code = PRODUCER.format(shims=os.path.join(ROOT, "baseline", "shims"), ref=REF, inp=inp, outp=outp)
+    code = PRODUCER.format(shims=os.path.join(ROOT, "baseline", "shims"), ref=REF, inp=inp, outp=outp, yamls=_yamls())
     env = {k: v for k, v in os.environ.items() if k != "PYTHONPATH"}
     res = subprocess.run([sys.executable, "-c", code], cwd=str(d), env=env, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stderr[-3000:]
@@ -174,3 +193,29 @@ def test_small_utilities_match_the_reference(reference_outputs):
     assert set(mine) == set(ref["tstats"])
     for k, v in ref["tstats"].items():
         assert abs(mine[k] - v) < 1e-5, (k, mine[k], v)
+
+
+def test_config_trees_match_the_reference(reference_outputs):
+    """Default configs, YAML loading, dotted ``update`` and ``evolve``: the resulting trees contain everything the reference's do,
+    with equal values (this framework adds keys — ``train.parallel`` … — but never renames or drops one)."""
+    from trlx_b200.data.configs import TRLConfig
+    from trlx_b200.data.default_configs import default_ilql_config, default_ppo_config, default_sft_config
+
+    def covers(ours, ref, path=""):
+        for k, v in ref.items():
+            assert k in ours, f"{path}{k} missing"
+            if isinstance(v, dict) and isinstance(ours[k], dict):
+                covers(ours[k], v, f"{path}{k}.")
+            else:
+                assert ours[k] == v or (isinstance(v, float) and abs(ours[k] - v) < 1e-12), f"{path}{k}: {ours[k]!r} != {v!r}"
+
+    want = reference_outputs["configs"]
+    mine = {p: TRLConfig.load_yaml(p).to_dict() for p in _yamls()}
+    mine.update(default_ppo=default_ppo_config().to_dict(), default_ilql=default_ilql_config().to_dict(),
+                default_sft=default_sft_config().to_dict(),
+                updated=TRLConfig.update(default_ppo_config().to_dict(), {"train.seq_length": 77, "method.gamma": 0.5,
+                                                                          "optimizer.kwargs.lr": 1e-3}).to_dict(),
+                evolved=default_ilql_config().evolve(train=dict(batch_size=3), method=dict(tau=0.9, gen_kwargs=dict(beta=2))).to_dict())
+    assert set(want) == set(mine)
+    for name, ref_tree in want.items():
+        covers(mine[name], ref_tree, f"[{os.path.basename(name)}] ")
