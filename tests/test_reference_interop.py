@@ -134,6 +134,18 @@ ROLLOUT = textwrap.dedent("""
     torch.save([tuple(t.detach().float().cpu() if t.is_floating_point() else t.cpu() for t in
                       (e.query_tensor, e.response_tensor, e.logprobs, e.values, e.rewards)) for e in trainer.store.history],
                os.path.join(work, "rollouts_ref.pt"))
+    # reward scaling variants, one chunk of 8 (running moments / reference moments do not depend on the shuffled order then)
+    scaled = {{}}
+    for mode, clip in (("running", 10.0), ("ref", 0.8)):
+        trainer.config.method.scale_reward, trainer.config.method.cliprange_reward = mode, clip
+        trainer.config.method.chunk_size = 8
+        trainer.ref_mean = trainer.ref_std = None   # the reference moments are taken from the first chunk seen: take them here
+        trainer.add_prompt_pipeline(PromptPipeline({prompts!r}, 32, trainer.tokenizer))
+        trainer.store.clear_history()
+        trainer.make_experience(8)
+        scaled[mode] = [(e.query_tensor.cpu(), e.rewards.detach().float().cpu()) for e in trainer.store.history]
+    torch.save(scaled, os.path.join(work, "rollouts_scaled_ref.pt"))
+    trainer.config.method.scale_reward, trainer.config.method.cliprange_reward, trainer.config.method.chunk_size = "ignored", 10, 4
     # evaluation: greedy generations on fixed prompts, reward + metric means; then the same with a `gen_kwargs` list (sweep)
     trainer.metric_fn = lambda samples, prompts, outputs, **kw: dict(out_len=[float(len(o)) for o in outputs],
                                                                      n_e=[float(s.count("e")) for s in samples])
@@ -491,6 +503,19 @@ def test_ppo_experience_matches_the_reference_rollout_arithmetic(stage2):
         torch.testing.assert_close(e.rewards.float().cpu(), rw, atol=2e-4, rtol=1e-4)
         assert (e.values.float().cpu()[k:] - v[k:]).abs().max().item() < 1.0 if k < n else True
         assert rw[:-1].abs().max() > 1e-4  # the KL penalty is really there (frozen branch differs from the policy)
+    # reward scaling by running / reference moments and reward clipping (single chunk: order-independent statistics)
+    scaled = torch.load(os.path.join(work, "rollouts_scaled_ref.pt"), weights_only=False)
+    for mode, clip in (("running", 10.0), ("ref", 0.8)):
+        trainer.config.method.scale_reward, trainer.config.method.cliprange_reward = mode, clip
+        trainer.config.method.chunk_size = 8
+        trainer.ref_mean = trainer.ref_std = None
+        trainer.add_prompt_pipeline(PromptPipeline(PROMPTS, 32, trainer.tokenizer))
+        trainer.store.clear_history()
+        trainer.make_experience(8)
+        mine = {tuple(int(t) for t in e.query_tensor.tolist() if t != pad): e for e in trainer.store.history}
+        for q, rw in scaled[mode]:
+            e = mine[tuple(int(t) for t in q.tolist() if t != pad)]
+            torch.testing.assert_close(e.rewards.float().cpu(), rw, atol=3e-4, rtol=2e-4, msg=lambda m: f"scale_reward={mode}: {m}")
 
 
 def _stats_close(mine, want, tol=2e-4):
