@@ -59,6 +59,22 @@ PRODUCER = textwrap.dedent("""
     out["topk"] = topk_mask(inp["logits"][0], 5)
     out["bis"] = batched_index_select(inp["logits"], inp["labels"][:, :4] % inp["logits"].shape[1], 1)
     out["tstats"] = {{k: float(v) for k, v in get_tensor_stats(inp["values"], inp["mask"], inp["mask"].sum()).items()}}
+    from trlx.utils.modeling import (freeze_bottom_causal_layers, hf_get_decoder_blocks, hf_get_hidden_size,
+                                     hf_get_num_hidden_layers, hf_get_decoder_final_norm, hf_get_lm_head)
+    fams = {{}}
+    for name, kw in {families!r}.items():
+        row = {{}}
+        for k in (0, 1, 2, -1):
+            torch.manual_seed(0)
+            hf = transformers.AutoModelForCausalLM.from_config(transformers.AutoConfig.for_model(**kw))
+            freeze_bottom_causal_layers(hf, k)
+            row[k] = sum(p.numel() for p in hf.parameters() if p.requires_grad)
+        row["blocks"] = len(hf_get_decoder_blocks(hf)); row["hidden"] = hf_get_hidden_size(hf.config)
+        row["layers"] = hf_get_num_hidden_layers(hf.config)
+        row["norm_numel"] = sum(p.numel() for p in hf_get_decoder_final_norm(hf).parameters())
+        row["head_shape"] = tuple(hf_get_lm_head(hf).weight.shape)
+        fams[name] = row
+    out["families"] = fams
     from trlx.data.configs import TRLConfig
     from trlx.data.default_configs import default_sft_config
     cfgs = {{}}
@@ -72,6 +88,22 @@ PRODUCER = textwrap.dedent("""
     out["configs"] = cfgs
     torch.save(out, {outp!r})
 """)
+
+
+FAMILIES = {
+    "gpt2": dict(model_type="gpt2", vocab_size=64, n_embd=32, n_layer=3, n_head=2, n_positions=64),
+    "gptj": dict(model_type="gptj", vocab_size=64, n_embd=32, n_layer=3, n_head=2, rotary_dim=8, n_positions=64),
+    "gpt_neox": dict(model_type="gpt_neox", vocab_size=64, hidden_size=32, num_hidden_layers=3, num_attention_heads=2,
+                     intermediate_size=64, max_position_embeddings=64),
+    "llama": dict(model_type="llama", vocab_size=64, hidden_size=32, num_hidden_layers=3, num_attention_heads=4,
+                  num_key_value_heads=2, intermediate_size=48, max_position_embeddings=64),
+    "opt": dict(model_type="opt", vocab_size=64, hidden_size=32, num_hidden_layers=3, num_attention_heads=2, ffn_dim=64,
+                max_position_embeddings=64, word_embed_proj_dim=32),
+    "bloom": dict(model_type="bloom", vocab_size=64, hidden_size=32, n_layer=3, n_head=2),
+    "gpt_bigcode": dict(model_type="gpt_bigcode", vocab_size=64, n_embd=32, n_layer=3, n_head=2, n_positions=64),
+    "gpt_neo": dict(model_type="gpt_neo", vocab_size=64, hidden_size=32, num_layers=4, num_heads=2, max_position_embeddings=64,
+                    attention_types=[[["global", "local"], 2]], window_size=4),
+}
 
 
 def _yamls():
@@ -113,7 +145,7 @@ def reference_outputs(tmp_path_factory):
     d = tmp_path_factory.mktemp("refnum")
     inp, outp = str(d / "in.pt"), str(d / "out.pt")
     torch.save(_inputs(), inp)
-    code = PRODUCER.format(shims=os.path.join(ROOT, "baseline", "shims"), ref=REF, inp=inp, outp=outp, yamls=_yamls())
+    code = PRODUCER.format(shims=os.path.join(ROOT, "baseline", "shims"), ref=REF, inp=inp, outp=outp, yamls=_yamls(), families=FAMILIES)
     env = {k: v for k, v in os.environ.items() if k != "PYTHONPATH"}
     res = subprocess.run([sys.executable, "-c", code], cwd=str(d), env=env, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stderr[-3000:]
@@ -219,3 +251,24 @@ def test_config_trees_match_the_reference(reference_outputs):
     assert set(want) == set(mine)
     for name, ref_tree in want.items():
         covers(mine[name], ref_tree, f"[{os.path.basename(name)}] ")
+
+
+def test_layer_freezing_and_getters_match_the_reference_for_every_family(reference_outputs):
+    """``freeze_bottom_causal_layers(model, k)`` leaves the same number of trainable elements as the reference does on the HF model
+    of the same configuration, for k in {0, 1, 2, -1} and all eight decoder families; block / hidden-size / final-norm / LM-head
+    getters agree."""
+    from trlx_b200.models.modeling_base import build_base_model
+    from trlx_b200.utils.modeling import (freeze_bottom_causal_layers, hf_get_decoder_blocks, hf_get_decoder_final_norm,
+                                          hf_get_hidden_size, hf_get_lm_head, hf_get_num_hidden_layers)
+
+    for name, kw in FAMILIES.items():
+        want = reference_outputs["families"][name]
+        for k in (0, 1, 2, -1):
+            model = build_base_model(kw)
+            freeze_bottom_causal_layers(model, k)
+            got = sum(p.numel() for p in model.parameters() if p.requires_grad)
+            assert got == want[k], (name, k, got, want[k])
+        assert len(hf_get_decoder_blocks(model)) == want["blocks"] and hf_get_hidden_size(model.config) == want["hidden"]
+        assert hf_get_num_hidden_layers(model.config) == want["layers"]
+        assert sum(p.numel() for p in hf_get_decoder_final_norm(model).parameters()) == want["norm_numel"]
+        assert tuple(hf_get_lm_head(model).weight.shape) == want["head_shape"]
