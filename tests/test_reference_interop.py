@@ -134,6 +134,23 @@ ROLLOUT = textwrap.dedent("""
     torch.save([tuple(t.detach().float().cpu() if t.is_floating_point() else t.cpu() for t in
                       (e.query_tensor, e.response_tensor, e.logprobs, e.values, e.rewards)) for e in trainer.store.history],
                os.path.join(work, "rollouts_ref.pt"))
+    # decode(): prompt / output split, stop-sequence trimming, EOS restoration
+    def build(tok):
+        P = [tok(t).input_ids for t in ("the movie", "acting", "film")]
+        O = [tok(t).input_ids for t in (" was really boring and long", " felt good zz very", " great")]
+        O[2] = O[2] + [tok.eos_token_id]
+        wp, wo = max(map(len, P)), max(map(len, O))
+        pad = tok.pad_token_id
+        prompts = torch.tensor([[pad] * (wp - len(p)) + p for p in P])
+        outs = torch.tensor([o + [pad] * (wo - len(o)) for o in O])
+        return prompts, torch.cat([prompts, outs], 1)
+    dec = {{}}
+    for stops in ([], ["ing", "zz"]):
+        trainer.stop_sequences = stops
+        pt, sm = build(trainer.tokenizer)
+        dec[tuple(stops)] = [trainer.decode(pt, sm, append_eos_token=flag) for flag in (True, False)]
+    trainer.stop_sequences = []
+    torch.save(dec, os.path.join(work, "decode_ref.pt"))
     # reward scaling variants, one chunk of 8 (running moments / reference moments do not depend on the shuffled order then)
     scaled = {{}}
     for mode, clip in (("running", 10.0), ("ref", 0.8)):
@@ -785,3 +802,27 @@ def test_minibatch_iterator_matches_the_reference(stage1):
             assert set(mb_g) == set(mb_w)
             for k in mb_w:
                 assert torch.equal(torch.as_tensor(mb_g[k]), mb_w[k]), k
+
+
+def test_decode_trims_stop_sequences_and_restores_eos_like_the_reference(stage2):
+    from trlx_b200.data.default_configs import default_ppo_config
+    from trlx_b200.utils.loading import get_trainer
+
+    work, fmt, ids, ref = stage2
+    want = torch.load(os.path.join(work, "decode_ref.pt"), weights_only=False)
+    cfg = default_ppo_config().evolve(
+        model=dict(model_path=_our_ckpt(work), num_layers_unfrozen=2), tokenizer=dict(tokenizer_path=ref["tok_dir"]),
+        train=dict(tracker=None, seq_length=40, batch_size=4, checkpoint_dir=os.path.join(work, "ckpt_ours4")))
+    trainer = get_trainer(cfg.train.trainer)(config=cfg, reward_fn=lambda samples, **kw: [0.0] * len(samples), metric_fn=None,
+                                             stop_sequences=[])
+    tok = trainer.tokenizer
+    P = [tok(t).input_ids for t in ("the movie", "acting", "film")]
+    O = [tok(t).input_ids for t in (" was really boring and long", " felt good zz very", " great")]
+    O[2] = O[2] + [tok.eos_token_id]
+    wp, wo, pad = max(map(len, P)), max(map(len, O)), tok.pad_token_id
+    prompts = torch.tensor([[pad] * (wp - len(p)) + p for p in P])
+    samples = torch.cat([prompts, torch.tensor([o + [pad] * (wo - len(o)) for o in O])], 1)
+    for stops, exp in want.items():
+        trainer.stop_sequences = list(stops)
+        got = [trainer.decode(prompts, samples, append_eos_token=flag) for flag in (True, False)]
+        assert [tuple(map(list, g)) for g in got] == [tuple(map(list, e)) for e in exp], (stops, got, exp)
