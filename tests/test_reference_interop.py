@@ -134,6 +134,19 @@ ROLLOUT = textwrap.dedent("""
     torch.save([tuple(t.detach().float().cpu() if t.is_floating_point() else t.cpu() for t in
                       (e.query_tensor, e.response_tensor, e.logprobs, e.values, e.rewards)) for e in trainer.store.history],
                os.path.join(work, "rollouts_ref.pt"))
+    # dense (per-token) rewards that depend on prompt metadata forwarded to the reward function
+    def dense_reward(samples, prompts, outputs, tokenizer, bonus, **kw):
+        return [[0.05 * b * (i + 1) for i in range(len(tokenizer(o).input_ids))] for o, b in zip(outputs, bonus)]
+    trainer.reward_fn = dense_reward
+    trainer.config.method.chunk_size = 8
+    trainer.add_prompt_pipeline(PromptPipeline([dict(prompt=p, bonus=float(i + 1)) for i, p in enumerate({prompts!r})], 32,
+                                               trainer.tokenizer))
+    trainer.store.clear_history()
+    trainer.make_experience(8)
+    torch.save([(e.query_tensor.cpu(), e.rewards.detach().float().cpu()) for e in trainer.store.history],
+               os.path.join(work, "rollouts_dense_ref.pt"))
+    trainer.reward_fn = lambda samples, **kw: [float(len(s)) / 10 for s in samples]
+    trainer.config.method.chunk_size = 4
     # decode(): prompt / output split, stop-sequence trimming, EOS restoration
     def build(tok):
         P = [tok(t).input_ids for t in ("the movie", "acting", "film")]
@@ -520,6 +533,22 @@ def test_ppo_experience_matches_the_reference_rollout_arithmetic(stage2):
         torch.testing.assert_close(e.rewards.float().cpu(), rw, atol=2e-4, rtol=1e-4)
         assert (e.values.float().cpu()[k:] - v[k:]).abs().max().item() < 1.0 if k < n else True
         assert rw[:-1].abs().max() > 1e-4  # the KL penalty is really there (frozen branch differs from the policy)
+    # dense per-token rewards driven by prompt metadata (`bonus`) that the pipeline forwards to the reward function
+    def dense_reward(samples, prompts, outputs, tokenizer, bonus, **kw):
+        return [[0.05 * b * (i + 1) for i in range(len(tokenizer(o).input_ids))] for o, b in zip(outputs, bonus)]
+
+    dense = torch.load(os.path.join(work, "rollouts_dense_ref.pt"), weights_only=False)
+    trainer.reward_fn = dense_reward
+    trainer.config.method.chunk_size = 8
+    trainer.add_prompt_pipeline(PromptPipeline([dict(prompt=p, bonus=float(i + 1)) for i, p in enumerate(PROMPTS)], 32, trainer.tokenizer))
+    trainer.store.clear_history()
+    trainer.make_experience(8)
+    mine = {tuple(int(t) for t in e.query_tensor.tolist() if t != pad): e for e in trainer.store.history}
+    assert len(dense) == 8
+    for q, rw in dense:
+        e = mine[tuple(int(t) for t in q.tolist() if t != pad)]
+        torch.testing.assert_close(e.rewards.float().cpu(), rw, atol=3e-4, rtol=2e-4, msg=lambda m: f"dense rewards: {m}")
+    trainer.reward_fn = lambda samples, **kw: [float(len(s)) / 10 for s in samples]
     # reward scaling by running / reference moments and reward clipping (single chunk: order-independent statistics)
     scaled = torch.load(os.path.join(work, "rollouts_scaled_ref.pt"), weights_only=False)
     for mode, clip in (("running", 10.0), ("ref", 0.8)):
