@@ -300,6 +300,34 @@ LEARN = textwrap.dedent("""
     torch.save(dict(logged={{k: sorted(v) for k, v in logged.items()}}, trees=trees), os.path.join(work, "learn_ref.pt"))
 """)
 
+RFTSTAGE = textwrap.dedent("""
+    from trlx.data.default_configs import default_sft_config
+    from trlx.trainer.accelerate_rft_trainer import AccelerateRFTTrainer, RFTConfig
+    from trlx.pipeline.offline_pipeline import PromptPipeline
+    work = {work!r}
+    st = torch.load(os.path.join(work, "stage1.pt"), weights_only=False)
+    cfg = default_sft_config()
+    cfg.method = RFTConfig(name="RFTConfig", gen_kwargs=dict(max_new_tokens=6, do_sample=False), start_percentile=0.5,
+                           end_percentile=0.9, n_improve_steps=2, n_generations_per_prompt=2)
+    cfg.model.model_path, cfg.tokenizer.tokenizer_path = st["model_dir"], st["tok_dir"]
+    cfg.train.tracker, cfg.train.seq_length, cfg.train.batch_size, cfg.train.trainer = None, 32, 4, "AccelerateRFTTrainer"
+    cfg.train.checkpoint_dir = os.path.join(work, "ckpt_ref_rft")
+    torch.manual_seed(0)
+    tr = AccelerateRFTTrainer(config=cfg, reward_fn=lambda samples, prompts, outputs, **kw: [float(len(o) % 7) for o in outputs],
+                              metric_fn=None, stop_sequences=[])
+    tr.add_prompt_pipeline(PromptPipeline({prompts!r}, 16, tr.tokenizer))
+    tr.add_eval_pipeline(PromptPipeline({prompts!r}[:2], 16, tr.tokenizer))
+    tr.epoch_count = tr.iter_count = 0
+    tr.generations_per_prompt = __import__("collections").defaultdict(list)
+    selected = []
+    for _ in range(2):   # a growth step, then an improvement step with the raised percentile
+        tr.make_experience()
+        selected.append(sorted((r["input_ids"] if isinstance(r, dict) else r.input_ids) for r in [tr.store[i] for i in range(len(tr.store))]))
+        tr.epoch_count += 1
+    scores = {{p: [(x["output"], x["score"]) for x in v] for p, v in tr.generations_per_prompt.items()}}
+    torch.save(dict(selected=selected, scores=scores), os.path.join(work, "rft_ref.pt"))
+""")
+
 T5STAGE = textwrap.dedent("""
     from trlx.models.modeling_ppo import AutoModelForSeq2SeqLMWithValueHead
     from trlx.models.modeling_ilql import AutoModelForSeq2SeqLMWithILQLHeads
@@ -395,7 +423,7 @@ def stage2(stage1):
     if not os.path.exists(os.path.join(path, "pytorch_model.bin")):
         AutoModelForCausalLMWithILQLHeads.from_pretrained(os.path.join(work, "ref_ilql_ckpt"), two_qs=True, alpha=0.5).save_pretrained(path)
     full = dict(fmt, prompts=PROMPTS, samples=SAMPLES, rewards=[1.0, -1.0, 0.5, 2.0])
-    code = HEADER.format(**full) + "".join(body.format(**full) for body in (STAGE2, ROLLOUT, OFFLINE, T5STAGE, LEARN))
+    code = HEADER.format(**full) + "".join(body.format(**full) for body in (STAGE2, ROLLOUT, OFFLINE, T5STAGE, LEARN, RFTSTAGE))
     _run(code, work)
     return stage1
 
@@ -855,3 +883,35 @@ def test_decode_trims_stop_sequences_and_restores_eos_like_the_reference(stage2)
         trainer.stop_sequences = list(stops)
         got = [trainer.decode(prompts, samples, append_eos_token=flag) for flag in (True, False)]
         assert [tuple(map(list, g)) for g in got] == [tuple(map(list, e)) for e in exp], (stops, got, exp)
+
+
+def test_rft_generation_scoring_and_percentile_selection_match_the_reference(stage2):
+    """RFT (greedy, so deterministic): the generations kept per prompt with their scores, and the samples that survive the
+    per-prompt percentile thresholds of a growth step and of the following improvement step."""
+    import collections
+
+    from trlx_b200.data.default_configs import default_sft_config
+    from trlx_b200.pipeline.offline_pipeline import PromptPipeline
+    from trlx_b200.trainer.accelerate_rft_trainer import RFTConfig
+    from trlx_b200.utils.loading import get_trainer
+
+    work, fmt, ids, ref = stage2
+    want = torch.load(os.path.join(work, "rft_ref.pt"), weights_only=False)
+    cfg = default_sft_config().evolve(
+        model=dict(model_path=ref["model_dir"]), tokenizer=dict(tokenizer_path=ref["tok_dir"]),
+        train=dict(tracker=None, seq_length=32, batch_size=4, trainer="AccelerateRFTTrainer", checkpoint_dir=os.path.join(work, "ckpt_ours_rft")))
+    cfg.method = RFTConfig(name="RFTConfig", gen_kwargs=dict(max_new_tokens=6, do_sample=False), start_percentile=0.5,
+                           end_percentile=0.9, n_improve_steps=2, n_generations_per_prompt=2)
+    tr = get_trainer("AccelerateRFTTrainer")(config=cfg, reward_fn=lambda samples, prompts, outputs, **kw: [float(len(o) % 7) for o in outputs],
+                                             metric_fn=None, stop_sequences=[])
+    tr.add_prompt_pipeline(PromptPipeline(PROMPTS, 16, tr.tokenizer))
+    tr.add_eval_pipeline(PromptPipeline(PROMPTS[:2], 16, tr.tokenizer))
+    tr.epoch_count = tr.iter_count = 0
+    tr.generations_per_prompt = collections.defaultdict(list)
+    for step in range(2):
+        tr.make_experience()
+        got = sorted(list((r["input_ids"] if isinstance(r, dict) else r.input_ids)) for r in [tr.store[i] for i in range(len(tr.store))])
+        assert got == [list(x) for x in want["selected"][step]], (step, got, want["selected"][step])
+        tr.epoch_count += 1
+    mine = {p: [(x["output"], x["score"]) for x in v] for p, v in tr.generations_per_prompt.items()}
+    assert mine == want["scores"]

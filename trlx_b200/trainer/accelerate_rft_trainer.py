@@ -108,5 +108,7 @@ class AccelerateRFTTrainer(AccelerateSFTTrainer):
         rt.log({"scores_mean": float(np.mean(flat_scores)), "scores_max": float(np.max(flat_scores)),
                 "thresholds_mean": float(np.mean(thresholds)), "len_samples_selected": len(selected)}, step=self.iter_count)
         if len(selected):
-            self.store = PromptPipeline([p + o for p, o in selected], max_prompt_length=2048, tokenizer=self.tokenizer,
+            # (prompt, output) PAIRS, as in the reference (``accelerate_rft_trainer.py:196-198``): the tokenizer encodes the two
+            # segments separately, so no BPE merge forms across the prompt / output boundary
+            self.store = PromptPipeline([[p, o] for p, o in selected], max_prompt_length=2048, tokenizer=self.tokenizer,
                                         add_special_tokens=True)
