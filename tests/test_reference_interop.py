@@ -645,6 +645,17 @@ def test_ilql_and_sft_trainer_losses_and_gradients_match_the_reference(stage2):
         model=dict(model_path=path), tokenizer=dict(tokenizer_path=ref["tok_dir"]), method=dict(alpha=0.5),
         train=dict(tracker=None, seq_length=32, batch_size=4, checkpoint_dir=os.path.join(work, "ckpt_ours_ilql")))
     tr = get_trainer(cfg.train.trainer)(config=cfg, reward_fn=None, metric_fn=None, stop_sequences=[])
+    tr.make_experience(SAMPLES, [1.0, -1.0, 0.5, 2.0], 32)  # the trainer's own experience: same first batch as the reference's
+    mine = next(iter(tr.store.create_loader(4)))
+    fields = ("input_ids", "attention_mask", "rewards", "states_ixs", "actions_ixs", "dones")
+
+    def rows(cols):  # the loaders shuffle: compare the batch as a set of rows
+        return sorted(tuple(tuple(c[i].reshape(-1).tolist()) for c in cols) for i in range(len(cols[0])))
+
+    got_rows, exp_rows = rows([getattr(mine, f).cpu() for f in fields]), rows(want["ilql"]["batch"])
+    for g, e in zip(got_rows, exp_rows):
+        for f, a, b in zip(fields, g, e):
+            assert len(a) == len(b) and all(abs(x - y) < 1e-6 for x, y in zip(a, b)), f"ILQL store {f}"
     tr.model.eval()
     loss, stats = tr.loss(ILQLBatch(*want["ilql"]["batch"]))
     loss.backward()
@@ -659,6 +670,11 @@ def test_ilql_and_sft_trainer_losses_and_gradients_match_the_reference(stage2):
         model=dict(model_path=ref["model_dir"]), tokenizer=dict(tokenizer_path=ref["tok_dir"]),
         train=dict(tracker=None, seq_length=32, batch_size=4, checkpoint_dir=os.path.join(work, "ckpt_ours_sft")))
     tr = get_trainer(cfg.train.trainer)(config=cfg, reward_fn=None, metric_fn=None, stop_sequences=[])
+    tr.make_experience(SAMPLES, 32)
+    mine = dict(next(iter(tr.store.create_loader(4))))
+    assert set(mine) == set(want["sft"]["batch"])
+    keys = sorted(mine)
+    assert rows([torch.as_tensor(mine[k]).cpu() for k in keys]) == rows([want["sft"]["batch"][k] for k in keys]), "SFT store"
     tr.model.eval()
     from transformers import BatchEncoding
 
