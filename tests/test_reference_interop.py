@@ -58,6 +58,14 @@ STAGE1 = HEADER + textwrap.dedent("""
     toks = [[(m.is_output, list(m.tokens)) for m in tokenize_dialogue(d, tok, L)] for d, L in dialogues]
     store = make_experience([d for d, _ in dialogues], {rewards!r}, tok, max_length=24, verbose=False)
     cols = {{k: [t.clone() for t in getattr(store, k)] for k in ("input_ids", "attention_mask", "rewards", "states_ixs", "actions_ixs", "dones")}}
+    # value BRANCH (a trainable copy of the top block ending in the value MLP) next to the hydra policy branch
+    torch.manual_seed(8)
+    vb = AutoModelForCausalLMWithHydraValueHead.from_pretrained(model_dir, num_layers_unfrozen=2, num_value_layers_unfrozen=1).eval()
+    with torch.no_grad():
+        for p in vb.v_head.parameters():
+            p.add_(torch.randn_like(p) * 0.05)
+        vb_out = vb(input_ids=ids, attention_mask=mask, position_ids=pos, return_dict=True)
+    vb.save_pretrained(os.path.join(work, "ref_vb_ckpt"))
     # ILQL heads model: forward outputs + checkpoint
     from trlx.models.modeling_ilql import AutoModelForCausalLMWithILQLHeads
     torch.manual_seed(6)
@@ -104,6 +112,7 @@ STAGE1 = HEADER + textwrap.dedent("""
     torch.save(dict(rows=pp_rows, batch=pp_batch, dialog=ds_batch, ppo_mbs=ppo_mbs, enc_mbs=enc_mbs),
                os.path.join(work, "pipelines_ref.pt"))
     torch.save(dict(logits=out.logits, value=out.value, hydra=hydra, toks=toks, store=cols, model_dir=model_dir, tok_dir=tok_dir,
+                    vb=dict(logits=vb_out.logits, value=vb_out.value),
                     ilql=dict(logits=il_logits, qs=qs, tqs=tqs, vs=vs, gen=gen), elems=[tuple(e.__dict__.values()) for e in elems],
                     collated=collated), os.path.join(work, "stage1.pt"))
 """)
@@ -931,3 +940,18 @@ def test_rft_generation_scoring_and_percentile_selection_match_the_reference(sta
         tr.epoch_count += 1
     mine = {p: [(x["output"], x["score"]) for x in v] for p, v in tr.generations_per_prompt.items()}
     assert mine == want["scores"]
+
+
+def test_value_branch_checkpoint_from_the_reference_loads_here(stage1):
+    """``num_value_layers_unfrozen=1``: the value function is a separate copy of the top block + MLP; its checkpoint keys
+    (``v_head.decoder_blocks…``) and outputs carry over."""
+    from trlx_b200.models.modeling_ppo import AutoModelForCausalLMWithHydraValueHead
+
+    work, fmt, ids, ref = stage1
+    model = AutoModelForCausalLMWithHydraValueHead.from_pretrained(os.path.join(work, "ref_vb_ckpt"), num_layers_unfrozen=2,
+                                                                   num_value_layers_unfrozen=1).eval()
+    logits, value, _, m = _forward(model, ids)
+    assert (logits - ref["vb"]["logits"])[m].abs().max() < 2e-4
+    assert (value - ref["vb"]["value"])[m].abs().max() < 2e-4
+    plain = AutoModelForCausalLMWithHydraValueHead.from_pretrained(os.path.join(work, "ref_ckpt"), num_layers_unfrozen=2).eval()
+    assert (_forward(plain, ids)[1] - value)[m].abs().max() > 1e-3  # a different value function than the plain head's
