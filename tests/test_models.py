@@ -357,3 +357,26 @@ def test_from_pretrained_accepts_base_model_checkpoints_and_never_stays_silently
     torch.save({"something.else": torch.zeros(3)}, bad / "pytorch_model.bin")
     with pytest.raises(ValueError, match="randomly initialised"):
         AutoModelForCausalLMWithValueHead.from_pretrained(str(bad))
+
+
+def test_sampling_filter_matches_hf_logits_warpers():
+    """``top_k_top_p_filter`` (the PyTorch sampler, and the oracle of the CUDA sampling kernel) keeps exactly the tokens HF's
+    ``TopKLogitsWarper`` → ``TopPLogitsWarper`` chain keeps — what the reference's ``generate`` kwargs mean."""
+    warpers = pytest.importorskip("transformers.generation.logits_process")
+    from trlx_b200.models.generation import top_k_top_p_filter
+
+    torch.manual_seed(0)
+    logits = torch.randn(5, 50) * 3
+    logits[2, :7] = logits[2, 0]  # ties
+    for t in (0.7, 1.0, 1.3):
+        for k in (0, 1, 5, 50):
+            for p in (1.0, 0.9, 0.5, 0.05):
+                x = logits / t
+                ref = x.clone()
+                if k > 0:
+                    ref = warpers.TopKLogitsWarper(k)(None, ref)
+                if p < 1.0:
+                    ref = warpers.TopPLogitsWarper(p)(None, ref)
+                got = top_k_top_p_filter(x.clone(), k, p)
+                assert torch.equal(torch.isinf(ref), torch.isinf(got)), (t, k, p)
+                torch.testing.assert_close(got[~torch.isinf(got)], ref[~torch.isinf(ref)])
