@@ -380,3 +380,29 @@ def test_sampling_filter_matches_hf_logits_warpers():
                 got = top_k_top_p_filter(x.clone(), k, p)
                 assert torch.equal(torch.isinf(ref), torch.isinf(got)), (t, k, p)
                 torch.testing.assert_close(got[~torch.isinf(got)], ref[~torch.isinf(ref)])
+
+
+def test_beam_search_matches_hf_generate():
+    """``generate(num_beams=…)`` returns the sequences HF's beam search returns for the same weights (left-padded prompts, several
+    beam widths and length penalties, EOS reachable)."""
+    transformers = pytest.importorskip("transformers")
+    from trlx_b200.models.generation import generate
+    from trlx_b200.models.modeling_base import build_base_model, import_base_state_dict
+
+    cfgd = dict(model_type="gpt2", vocab_size=24, n_embd=32, n_layer=2, n_head=2, n_positions=64, eos_token_id=23, bos_token_id=23,
+                pad_token_id=23)
+    for seed in (0, 1):
+        torch.manual_seed(seed)
+        hf = transformers.AutoModelForCausalLM.from_config(transformers.AutoConfig.for_model(**cfgd)).eval()
+        ours = build_base_model(cfgd).eval()
+        import_base_state_dict(ours, hf.state_dict(), strict=True)
+        ids = torch.randint(0, 22, (3, 5), generator=torch.Generator().manual_seed(seed + 10))
+        mask = torch.ones_like(ids)
+        mask[0, :2] = 0
+        for nb, lp in ((2, 1.0), (4, 1.0), (4, 0.0), (3, 2.0)):
+            with torch.no_grad():
+                a = hf.generate(ids, attention_mask=mask, num_beams=nb, max_new_tokens=7, do_sample=False, length_penalty=lp,
+                                early_stopping=False, pad_token_id=23, eos_token_id=23)
+                b = generate(ours, ids, attention_mask=mask, num_beams=nb, max_new_tokens=7, do_sample=False, length_penalty=lp,
+                             pad_token_id=23, eos_token_id=23)
+            assert a.shape == b.shape and torch.equal(a, b), (seed, nb, lp, a, b)
