@@ -406,3 +406,29 @@ def test_beam_search_matches_hf_generate():
                 b = generate(ours, ids, attention_mask=mask, num_beams=nb, max_new_tokens=7, do_sample=False, length_penalty=lp,
                              pad_token_id=23, eos_token_id=23)
             assert a.shape == b.shape and torch.equal(a, b), (seed, nb, lp, a, b)
+
+
+def test_greedy_generation_controls_match_hf_generate():
+    """Length controls and stopping of ``generate`` (``max_new_tokens`` / ``max_length`` / ``min_new_tokens`` / ``min_length`` /
+    several EOS ids, left-padded prompts, finished rows padded) give HF's sequences for the same weights."""
+    transformers = pytest.importorskip("transformers")
+    from trlx_b200.models.generation import generate
+    from trlx_b200.models.modeling_base import build_base_model, import_base_state_dict
+
+    cfgd = dict(model_type="gpt2", vocab_size=24, n_embd=32, n_layer=2, n_head=2, n_positions=64, eos_token_id=23, bos_token_id=23,
+                pad_token_id=23)
+    for seed in (0, 1, 2):
+        torch.manual_seed(seed)
+        hf = transformers.AutoModelForCausalLM.from_config(transformers.AutoConfig.for_model(**cfgd)).eval()
+        ours = build_base_model(cfgd).eval()
+        import_base_state_dict(ours, hf.state_dict(), strict=True)
+        ids = torch.randint(0, 22, (4, 6), generator=torch.Generator().manual_seed(seed + 3))
+        mask = torch.ones_like(ids)
+        mask[1, :3] = 0
+        for kw in (dict(max_new_tokens=8), dict(max_length=11), dict(max_new_tokens=8, min_new_tokens=5),
+                   dict(max_new_tokens=6, min_length=10), dict(max_new_tokens=8, eos_token_id=[23, 5])):
+            kw = {"eos_token_id": 23, **kw}
+            with torch.no_grad():
+                a = hf.generate(ids, attention_mask=mask, do_sample=False, pad_token_id=23, **kw)
+                b = generate(ours, ids, attention_mask=mask, do_sample=False, pad_token_id=23, **kw)
+            assert a.shape == b.shape and torch.equal(a, b), (seed, kw, a, b)
