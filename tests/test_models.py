@@ -432,3 +432,38 @@ def test_greedy_generation_controls_match_hf_generate():
                 a = hf.generate(ids, attention_mask=mask, do_sample=False, pad_token_id=23, **kw)
                 b = generate(ours, ids, attention_mask=mask, do_sample=False, pad_token_id=23, **kw)
             assert a.shape == b.shape and torch.equal(a, b), (seed, kw, a, b)
+
+
+@pytest.mark.parametrize("family", list(CAUSAL) + ["t5_tied", "t5_untied"])
+def test_cached_greedy_decoding_matches_hf_for_every_family(family):
+    """Incremental (KV-cache) greedy decoding from left-padded prompts produces HF's tokens for every decoder family — rotary
+    offsets, ALiBi, local attention windows, multi-query caches, post-LN OPT — and for T5 (tied and untied embeddings)."""
+    transformers = pytest.importorskip("transformers")
+    from trlx_b200.models.generation import generate
+    from trlx_b200.models.modeling_base import build_base_model, import_base_state_dict
+
+    g = torch.Generator().manual_seed(3)
+    ids = torch.randint(2, 60, (3, 6), generator=g)
+    mask = torch.ones_like(ids)
+    torch.manual_seed(0)
+    if family.startswith("t5"):
+        cfgd = dict(model_type="t5", vocab_size=64, d_model=32, d_kv=8, d_ff=64, num_layers=2, num_decoder_layers=2, num_heads=4,
+                    eos_token_id=1, pad_token_id=0, decoder_start_token_id=0, tie_word_embeddings=family == "t5_tied")
+        hf = transformers.AutoModelForSeq2SeqLM.from_config(transformers.AutoConfig.for_model(**cfgd)).eval()
+        ours = build_base_model(cfgd, "seq2seq").eval()
+        import_base_state_dict(ours, hf.state_dict(), strict=False)
+        mask[0, 4:] = 0  # encoder inputs are right-padded
+        with torch.no_grad():
+            a = hf.generate(ids, attention_mask=mask, do_sample=False, max_new_tokens=8)
+            b = generate(ours, ids, attention_mask=mask, do_sample=False, max_new_tokens=8, pad_token_id=0, eos_token_id=1,
+                         decoder_start_token_id=0)
+    else:
+        cfgd = dict(CAUSAL[family], eos_token_id=63, pad_token_id=63, bos_token_id=63)
+        hf = transformers.AutoModelForCausalLM.from_config(transformers.AutoConfig.for_model(**cfgd)).eval()
+        ours = build_base_model(cfgd).eval()
+        import_base_state_dict(ours, hf.state_dict(), strict=True)
+        mask[0, :2] = 0
+        with torch.no_grad():
+            a = hf.generate(ids, attention_mask=mask, do_sample=False, max_new_tokens=8, pad_token_id=63, eos_token_id=63)
+            b = generate(ours, ids, attention_mask=mask, do_sample=False, max_new_tokens=8, pad_token_id=63, eos_token_id=63)
+    assert a.shape == b.shape and torch.equal(a, b), (a, b)
