@@ -1,4 +1,5 @@
 import math
+import os
 
 import pytest
 import torch
@@ -267,3 +268,25 @@ def test_inplace_wgrad_marks_only_unshared_linear_weights():
     w = lm.transformer.h[1].mlp.up.weight
     x = torch.randn(4, 32)
     assert Fn._wgrad_sink(w, x, x) is None  # no sink registered / CPU tensors: autograd path
+
+
+def test_every_environment_switch_is_documented():
+    """docs/env.md lists every ``TRLX_B200_*`` variable the code reads."""
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    docs = os.path.join(root, "docs", "env.md")
+    if not os.path.exists(docs):
+        pytest.skip("docs/ not shipped with this snapshot")
+    documented = set(re.findall(r"TRLX_B200_[A-Z0-9_]+", open(docs).read()))
+    used = set()
+    for base in ("trlx_b200", "baseline"):
+        for d, _, files in os.walk(os.path.join(root, base)):
+            if "_ref" in d or "__pycache__" in d or os.sep + "build" in d:
+                continue
+            for f in files:
+                if f.endswith((".py", ".cu", ".cpp", ".cuh")):
+                    used |= set(re.findall(r"TRLX_B200_[A-Z0-9_]+", open(os.path.join(d, f), errors="ignore").read()))
+    for f in ("bench.py", "__graft_entry__.py"):
+        used |= set(re.findall(r"TRLX_B200_[A-Z0-9_]+", open(os.path.join(root, f)).read()))
+    assert not (used - documented), sorted(used - documented)
