@@ -955,3 +955,4 @@ def test_value_branch_checkpoint_from_the_reference_loads_here(stage1):
     assert (value - ref["vb"]["value"])[m].abs().max() < 2e-4
     plain = AutoModelForCausalLMWithHydraValueHead.from_pretrained(os.path.join(work, "ref_ckpt"), num_layers_unfrozen=2).eval()
     assert (_forward(plain, ids)[1] - value)[m].abs().max() > 1e-3  # a different value function than the plain head's
+
