@@ -143,6 +143,12 @@ ROLLOUT = textwrap.dedent("""
     torch.save([tuple(t.detach().float().cpu() if t.is_floating_point() else t.cpu() for t in
                       (e.query_tensor, e.response_tensor, e.logprobs, e.values, e.rewards)) for e in trainer.store.history],
                os.path.join(work, "rollouts_ref.pt"))
+    tk = trainer.tokenizer
+    torch.save(dict(padding_side=tk.padding_side, truncation_side=tk.truncation_side, pad_token=tk.pad_token, pad_id=tk.pad_token_id,
+                    eos_id=tk.eos_token_id, bos_id=tk.bos_token_id, sep=getattr(tk, "sep_token", None),
+                    gen=dict(trainer.generate_kwargs), gen_exp=dict(trainer.generate_experience_kwargs or {{}}),
+                    n_trainable=sum(p.numel() for p in trainer.model.parameters() if p.requires_grad)),
+               os.path.join(work, "trainer_setup_ref.pt"))
     # dense (per-token) rewards that depend on prompt metadata forwarded to the reward function
     def dense_reward(samples, prompts, outputs, tokenizer, bonus, **kw):
         return [[0.05 * b * (i + 1) for i in range(len(tokenizer(o).input_ids))] for o, b in zip(outputs, bonus)]
@@ -956,3 +962,35 @@ def test_value_branch_checkpoint_from_the_reference_loads_here(stage1):
     plain = AutoModelForCausalLMWithHydraValueHead.from_pretrained(os.path.join(work, "ref_ckpt"), num_layers_unfrozen=2).eval()
     assert (_forward(plain, ids)[1] - value)[m].abs().max() > 1e-3  # a different value function than the plain head's
 
+
+
+def test_trainer_setup_matches_the_reference(stage2):
+    """What the PPO trainer derives at construction: tokenizer sides / pad token, the generation kwargs actually used for
+    evaluation and for experience, and the number of trainable elements (``num_layers_unfrozen = 2`` + value head)."""
+    from trlx_b200.data.default_configs import default_ppo_config
+    from trlx_b200.utils.loading import get_trainer
+
+    work, fmt, ids, ref = stage2
+    want = torch.load(os.path.join(work, "trainer_setup_ref.pt"), weights_only=False)
+    cfg = default_ppo_config().evolve(
+        model=dict(model_path=_our_ckpt(work), num_layers_unfrozen=2), tokenizer=dict(tokenizer_path=ref["tok_dir"]),
+        train=dict(tracker=None, seq_length=40, batch_size=4, checkpoint_dir=os.path.join(work, "ckpt_ours5"),
+                   trainer_kwargs=dict(cache_trunk=False)),
+        method=dict(num_rollouts=8, chunk_size=4, init_kl_coef=0.3, gen_kwargs=dict(max_new_tokens=8, do_sample=False, top_k=0, top_p=1.0)))
+    os.environ["TRLX_B200_SHARE_TRUNK"] = "0"  # compare the reference's trainable set (it differentiates through the whole trunk)
+    try:
+        trainer = get_trainer(cfg.train.trainer)(config=cfg, reward_fn=lambda samples, **kw: [0.0] * len(samples), metric_fn=None,
+                                                 stop_sequences=[])
+    finally:
+        os.environ.pop("TRLX_B200_SHARE_TRUNK", None)
+    tk = trainer.tokenizer
+    got = dict(padding_side=tk.padding_side, truncation_side=tk.truncation_side, pad_token=tk.pad_token, pad_id=tk.pad_token_id,
+               eos_id=tk.eos_token_id, bos_id=tk.bos_token_id, sep=getattr(tk, "sep_token", None))
+    for k, v in got.items():
+        assert v == want[k], (k, v, want[k])
+    for name, mine in (("gen", trainer.generate_kwargs), ("gen_exp", trainer.generate_experience_kwargs or {})):
+        for k, v in want[name].items():
+            if k == "synced_gpus":  # DeepSpeed ZeRO-3 plumbing of HF's generate; ZeRO-3 is handled inside this framework's sampler
+                continue
+            assert k in mine and mine[k] == v, (name, k, mine.get(k), v)
+    assert sum(p.numel() for p in trainer.model.parameters() if p.requires_grad) == want["n_trainable"]
