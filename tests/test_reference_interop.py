@@ -189,6 +189,8 @@ ROLLOUT = textwrap.dedent("""
         trainer.store.clear_history()
         trainer.make_experience(8)
         scaled[mode] = [(e.query_tensor.cpu(), e.rewards.detach().float().cpu()) for e in trainer.store.history]
+        scaled[mode + "/mean_kl"] = float(trainer.mean_kl)
+        scaled[mode + "/running"] = (float(trainer.running_moments.mean), float(trainer.running_moments.std))
     torch.save(scaled, os.path.join(work, "rollouts_scaled_ref.pt"))
     trainer.config.method.scale_reward, trainer.config.method.cliprange_reward, trainer.config.method.chunk_size = "ignored", 10, 4
     # evaluation: greedy generations on fixed prompts, reward + metric means; then the same with a `gen_kwargs` list (sweep)
@@ -605,6 +607,8 @@ def test_ppo_experience_matches_the_reference_rollout_arithmetic(stage2):
         for q, rw in scaled[mode]:
             e = mine[tuple(int(t) for t in q.tolist() if t != pad)]
             torch.testing.assert_close(e.rewards.float().cpu(), rw, atol=3e-4, rtol=2e-4, msg=lambda m: f"scale_reward={mode}: {m}")
+        # the mean KL the adaptive controller is fed (k3 estimator summed over the response, averaged over the chunk)
+        assert abs(float(trainer.mean_kl) - scaled[mode + "/mean_kl"]) < 2e-4 * max(1.0, abs(scaled[mode + "/mean_kl"])), mode
 
 
 def _stats_close(mine, want, tol=2e-4):
