@@ -34,3 +34,45 @@ def test_randomwalks_task_is_the_reference_task():
         assert set(a) == set(b)
         for k in a:
             assert [float(x) for x in a[k]] == pytest.approx([float(x) for x in b[k]], abs=1e-9), k
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "examples", "summarize_rlhf", "reward_model", "reward_model.py")),
+                    reason="no reference checkout")
+def test_pairwise_reward_model_objective_is_the_reference_objective():
+    """The summarisation reward model: for the same per-token rewards, the vectorised pairwise loss (divergence index, padding,
+    end-of-sequence scores) equals the reference's per-pair Python loop — training batches and the inference form."""
+    ref_mod = _load(os.path.join(REF, "examples", "summarize_rlhf", "reward_model", "reward_model.py"), "_ref_reward_model")
+    from examples.summarize_rlhf.reward_model.reward_model import GPTRewardModel
+
+    PAD, T, H = 0, 12, 8
+    g = torch.Generator().manual_seed(0)
+    prompt = torch.randint(1, 50, (5, 4), generator=g)
+    lens_c, lens_r = [12, 9, 7, 12, 6], [10, 12, 7, 5, 11]
+    chosen, rejected = torch.full((5, T), PAD), torch.full((5, T), PAD)
+    for i in range(5):
+        chosen[i, :4], rejected[i, :4] = prompt[i], prompt[i]
+        chosen[i, 4:lens_c[i]] = torch.randint(1, 50, (lens_c[i] - 4,), generator=g)
+        rejected[i, 4:lens_r[i]] = torch.randint(50, 99, (lens_r[i] - 4,), generator=g)
+    hidden = torch.randn(10, T, H, generator=g)
+
+    class Trunk(torch.nn.Module):
+        def forward(self, input_ids, **kw):
+            return (hidden[: input_ids.shape[0]],)
+
+    ref = object.__new__(ref_mod.GPTRewardModel)
+    torch.nn.Module.__init__(ref)
+    ref.transformer, ref.v_head, ref.PAD_ID = Trunk(), torch.nn.Linear(H, 1, bias=False), PAD
+    ours = object.__new__(GPTRewardModel)
+    torch.nn.Module.__init__(ours)
+    ours.v_head, ours.PAD_ID = ref.v_head, PAD
+    ours.rewards = lambda input_ids, attention_mask=None: ref.v_head(hidden[: input_ids.shape[0]]).squeeze(-1)
+
+    pair = torch.cat([chosen, rejected])
+    a, b = ref(input_ids=pair), ours(pair)
+    assert set(a) == set(b) == {"loss", "chosen_end_scores", "rejected_end_scores"}
+    for k in a:
+        torch.testing.assert_close(b[k], a[k], atol=1e-6, rtol=1e-5)
+    same = torch.cat([chosen, chosen])  # inference form: identical halves -> scores at the last non-pad token
+    a, b = ref(input_ids=same), ours(same)
+    assert set(a) == set(b) == {"chosen_end_scores"}
+    torch.testing.assert_close(b["chosen_end_scores"], a["chosen_end_scores"])
