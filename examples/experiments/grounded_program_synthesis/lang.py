@@ -23,7 +23,7 @@ PRIMITIVES: Dict[str, Tuple[Callable[..., Value], Tuple[str, ...]]] = {
     "add_n": (lambda xs, n: [x + n for x in xs], ("list", "int")),
     "sub_n": (lambda xs, n: [x - n for x in xs], ("list", "int")),
     "mul_n": (lambda xs, n: [x * n for x in xs], ("list", "int")),
-    "div_n": (lambda xs, n: [x // n for x in xs], ("list", "int")),
+    "div_n": (lambda xs, n: [x / n for x in xs], ("list", "int")),  # true division, as in the reference (results are floats)
     "expand_copy": (lambda xs: xs + xs, ("list",)),
 }
 _TOKEN = re.compile(r"\s*(?:(-?\d+)|([A-Za-z_]\w*)|(.))")

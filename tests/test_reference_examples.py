@@ -76,3 +76,25 @@ def test_pairwise_reward_model_objective_is_the_reference_objective():
     a, b = ref(input_ids=same), ours(same)
     assert set(a) == set(b) == {"chosen_end_scores"}
     torch.testing.assert_close(b["chosen_end_scores"], a["chosen_end_scores"])
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "examples", "experiments", "grounded_program_synthesis", "lang.py")),
+                    reason="no reference checkout")
+def test_list_dsl_interpreter_agrees_with_the_reference_interpreter():
+    """The grounded-program-synthesis DSL: the parser-based interpreter here returns what the reference's ``eval``-based one
+    returns, on programs drawn by the reference's own sampler and on malformed / ill-typed ones (``"ERROR"``)."""
+    import random
+
+    ref = _load(os.path.join(REF, "examples", "experiments", "grounded_program_synthesis", "lang.py"), "_ref_lang")
+    ours = _load(os.path.join(ROOT, "examples", "experiments", "grounded_program_synthesis", "lang.py"), "_our_lang")
+    random.seed(0)
+    data = ref.create_synthetic_dataset(600)
+    ri, oi = ref.Interpreter(), ours.Interpreter()
+    programs = [d["output"] for d in data] + [
+        "take([1,2,3],2)", "take([1,2,3],5)", "drop([1,2,3],1)", "foo([1])", "add_n([1],[2])", "minimum([])", "maximum([3,1])",
+        "div_n([4,5],0)", "div_n([4,-5],2)", "expand_copy([1,2])", "reverse(3)", "take([1,2,3],", "mul_n(reverse([1,2]),-3)",
+        "sub_n([1,2],1) extra", "1", "[1,2]", "sort_asc(minimum([1,2]))"]
+    assert len(programs) > 300
+    for p in programs:
+        assert ri(p) == oi(p), (p, ri(p), oi(p))
+    assert all(oi(d["output"]) == d["io_out"] for d in data)
